@@ -1,0 +1,19 @@
+// Process-wide bookkeeping shared by all C-ABI entry points.
+#include <atomic>
+
+#include "common.cuh"
+
+static std::atomic<long long> g_launches{0};
+
+extern "C" {
+
+void siu3r_note_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// Number of kernels of this library launched since the last reset (bench.py -> "gpu_launches").
+long long siu3r_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+void siu3r_reset_launch_count(void) { g_launches.store(0, std::memory_order_relaxed); }
+
+// ABI version of include/siu3r_b200.h this library was built against.
+int siu3r_abi_version(void) { return 1; }
+
+}  // extern "C"

@@ -1,0 +1,559 @@
+// 3D Gaussian splatting rasterizer, forward pass, written from scratch for sm_100a.
+//
+// Drop-in for what the reference reaches through
+//   /root/reference/src/models/cuda_splatting.py:90-118  (GaussianRasterizer(settings)(means3D, ..., cov3D_precomp))
+// i.e. the third-party `diff-gaussian-rasterization-w-pose @ 43e21bf` forward.
+//
+// Pipeline (all on the caller's stream):
+//   preprocess (cull / project / EWA covariance / SH->RGB / tile rect)   HBM-bound, 340 B read + 52 B written per Gaussian
+//   3-kernel inclusive scan of tiles_touched
+//   duplicate_with_keys                                                   12 B written per duplicate
+//   radix sort of (tile<<32 | depth bits, gaussian id)                    (cub::DeviceRadixSort for now)
+//   identify_tile_ranges                                                  8 B read per duplicate
+//   render: one 16x16 CTA per tile, 256-Gaussian shared-memory batches    44 B staged per duplicate, 20 B written per pixel
+//
+// Integer outputs (radii, tiles_touched, offsets, sorted key/value list, tile ranges) are bit-exact against
+// oracle/raster_ref.c: every float op that feeds them is an explicit round-to-nearest intrinsic (no FMA contraction),
+// in the oracle's operation order.
+#include <cub/device/device_radix_sort.cuh>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int TILE_X = 16;
+constexpr int TILE_Y = 16;
+constexpr int PRE_THREADS = 128;
+constexpr int MAX_SH_FLOATS = 75;  // 25 coefficients x 3 channels
+
+#define MUL(a, b) __fmul_rn((a), (b))
+#define ADD(a, b) __fadd_rn((a), (b))
+#define SUB(a, b) __fsub_rn((a), (b))
+#define DIV(a, b) __fdiv_rn((a), (b))
+
+__constant__ float c_SH_C2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
+                                 -1.0925484305920792f, 0.5462742152960396f};
+__constant__ float c_SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f, 0.3731763325901154f,
+                                 -0.4570457994644658f, 1.445305721320277f,  -0.5900435899266435f};
+
+struct Camera {
+    float view[16];
+    float proj[16];
+    float campos[3];
+    float bg[3];
+};
+
+// x' = m[0]x + m[4]y + m[8]z + m[12], left-to-right, no contraction
+__device__ __forceinline__ float row_dot(const float* m, int r, float x, float y, float z) {
+    return ADD(ADD(ADD(MUL(m[r], x), MUL(m[4 + r], y)), MUL(m[8 + r], z)), m[12 + r]);
+}
+
+__device__ __forceinline__ float ndc2pix(float v, int S) { return MUL(SUB(MUL(ADD(v, 1.0f), (float)S), 1.0f), 0.5f); }
+
+struct PreOut {
+    float* depths;
+    float2* xy;
+    float4* conic_o;
+    float* rgb;
+    uint32_t* tiles;
+    ushort4* rects;
+};
+
+// One thread per Gaussian; the CTA's SH block (PRE_THREADS x sh_floats, contiguous in HBM) is staged through shared
+// memory with coalesced 128-bit loads, then each thread reads its own record (odd stride -> conflict-free).
+__global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(
+    int G, int H, int W, int gx, int gy, int deg, int sh_coeffs, int sh_layout, int cov_stride,
+    const float* __restrict__ means, const float* __restrict__ cov, const float* __restrict__ shs,
+    const float* __restrict__ opac, const float* __restrict__ cam_dev, float tanx, float tany, float fx, float fy,
+    PreOut o, int32_t* __restrict__ radii) {
+    __shared__ float s_sh[PRE_THREADS * MAX_SH_FLOATS];
+    __shared__ Camera s_cam;
+    const int tid = threadIdx.x;
+    const int base = blockIdx.x * PRE_THREADS;
+    const int shf = sh_coeffs * 3;
+    if (tid < (int)(sizeof(Camera) / sizeof(float))) reinterpret_cast<float*>(&s_cam)[tid] = cam_dev[tid];
+    {
+        const int nvalid = min(PRE_THREADS, G - base);
+        const size_t total = (size_t)nvalid * shf;
+        const float* src = shs + (size_t)base * shf;
+        if ((((uintptr_t)src) & 15) == 0) {
+            const size_t n4 = total / 4;
+            const float4* s4 = reinterpret_cast<const float4*>(src);
+            float4* d4 = reinterpret_cast<float4*>(s_sh);
+            for (size_t i = tid; i < n4; i += PRE_THREADS) d4[i] = __ldg(s4 + i);
+            for (size_t i = n4 * 4 + tid; i < total; i += PRE_THREADS) s_sh[i] = __ldg(src + i);
+        } else {
+            for (size_t i = tid; i < total; i += PRE_THREADS) s_sh[i] = __ldg(src + i);
+        }
+    }
+    __syncthreads();
+    const int i = base + tid;
+    if (i >= G) return;
+
+    const float px = means[3 * (size_t)i], py = means[3 * (size_t)i + 1], pz = means[3 * (size_t)i + 2];
+    const float* vm = s_cam.view;
+    const float* pm = s_cam.proj;
+    float tx = row_dot(vm, 0, px, py, pz), ty = row_dot(vm, 1, px, py, pz);
+    const float tz = row_dot(vm, 2, px, py, pz);
+    // radii / tiles were zeroed by the host wrapper: culled Gaussians simply return
+    if (tz <= 0.2f) return;
+    const float hx = row_dot(pm, 0, px, py, pz), hy = row_dot(pm, 1, px, py, pz);
+    const float hw = row_dot(pm, 3, px, py, pz);
+    const float pw = DIV(1.0f, ADD(hw, 0.0000001f));
+    const float ndx = MUL(hx, pw), ndy = MUL(hy, pw);
+
+    // --- EWA covariance (oracle/raster_ref.c: cov2d) ---
+    float c3[6];
+    {
+        const float* c = cov + (size_t)i * cov_stride;
+        if (cov_stride == 6) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) c3[k] = c[k];
+        } else {  // full 3x3 row-major (Gaussians.covariances): upper triangle xx,xy,xz,yy,yz,zz
+            c3[0] = c[0]; c3[1] = c[1]; c3[2] = c[2]; c3[3] = c[4]; c3[4] = c[5]; c3[5] = c[8];
+        }
+    }
+    const float limx = MUL(1.3f, tanx), limy = MUL(1.3f, tany);
+    const float txtz = DIV(tx, tz), tytz = DIV(ty, tz);
+    tx = MUL(fminf(limx, fmaxf(-limx, txtz)), tz);
+    ty = MUL(fminf(limy, fmaxf(-limy, tytz)), tz);
+    const float j00 = DIV(fx, tz), j02 = DIV(-MUL(fx, tx), MUL(tz, tz));
+    const float j11 = DIV(fy, tz), j12 = DIV(-MUL(fy, ty), MUL(tz, tz));
+    float M0[3], M1[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float r0 = vm[4 * c + 0], r1 = vm[4 * c + 1], r2 = vm[4 * c + 2];  // R[k][c] = vm[4c+k]
+        M0[c] = ADD(ADD(MUL(j00, r0), MUL(0.0f, r1)), MUL(j02, r2));
+        M1[c] = ADD(ADD(MUL(0.0f, r0), MUL(j11, r1)), MUL(j12, r2));
+    }
+    const float V[3][3] = {{c3[0], c3[1], c3[2]}, {c3[1], c3[3], c3[4]}, {c3[2], c3[4], c3[5]}};
+    float MV0[3], MV1[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        MV0[c] = ADD(ADD(MUL(M0[0], V[0][c]), MUL(M0[1], V[1][c])), MUL(M0[2], V[2][c]));
+        MV1[c] = ADD(ADD(MUL(M1[0], V[0][c]), MUL(M1[1], V[1][c])), MUL(M1[2], V[2][c]));
+    }
+    const float ca = ADD(ADD(ADD(MUL(MV0[0], M0[0]), MUL(MV0[1], M0[1])), MUL(MV0[2], M0[2])), 0.3f);
+    const float cb = ADD(ADD(MUL(MV1[0], M0[0]), MUL(MV1[1], M0[1])), MUL(MV1[2], M0[2]));
+    const float cc = ADD(ADD(ADD(MUL(MV1[0], M1[0]), MUL(MV1[1], M1[1])), MUL(MV1[2], M1[2])), 0.3f);
+
+    const float det = SUB(MUL(ca, cc), MUL(cb, cb));
+    if (det == 0.0f) return;
+    const float det_inv = DIV(1.0f, det);
+    const float mid = MUL(0.5f, ADD(ca, cc));
+    const float disc = __fsqrt_rn(fmaxf(0.1f, SUB(MUL(mid, mid), det)));
+    const float lambda1 = ADD(mid, disc), lambda2 = SUB(mid, disc);
+    const float my_radius = ceilf(MUL(3.0f, __fsqrt_rn(fmaxf(lambda1, lambda2))));
+    const float pix = ndc2pix(ndx, W), piy = ndc2pix(ndy, H);
+    const int rminx = min(gx, max(0, (int)DIV(SUB(pix, my_radius), (float)TILE_X)));
+    const int rminy = min(gy, max(0, (int)DIV(SUB(piy, my_radius), (float)TILE_Y)));
+    const int rmaxx = min(gx, max(0, (int)DIV(SUB(ADD(ADD(pix, my_radius), (float)TILE_X), 1.0f), (float)TILE_X)));
+    const int rmaxy = min(gy, max(0, (int)DIV(SUB(ADD(ADD(piy, my_radius), (float)TILE_Y), 1.0f), (float)TILE_Y)));
+    if ((rmaxx - rminx) * (rmaxy - rminy) == 0) return;
+
+    // --- SH -> RGB (degrees 0..3 of the 25 stored coefficients; float tolerance, contraction allowed) ---
+    {
+        const float* sh = s_sh + tid * shf;
+        const int sk = sh_layout == 0 ? 3 : 1;          // stride between coefficients
+        const int sc = sh_layout == 0 ? 1 : sh_coeffs;  // stride between channels
+        const float dx = px - s_cam.campos[0], dy = py - s_cam.campos[1], dz = pz - s_cam.campos[2];
+        const float len = sqrtf(dx * dx + dy * dy + dz * dz);
+        const float x = dx / len, y = dy / len, z = dz / len;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            const float* s = sh + ch * sc;
+            float r = 0.28209479177387814f * s[0];
+            if (deg > 0) {
+                const float C1 = 0.4886025119029199f;
+                r = r - C1 * y * s[1 * sk] + C1 * z * s[2 * sk] - C1 * x * s[3 * sk];
+                if (deg > 1) {
+                    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+                    r = r + c_SH_C2[0] * xy * s[4 * sk] + c_SH_C2[1] * yz * s[5 * sk] +
+                        c_SH_C2[2] * (2.0f * zz - xx - yy) * s[6 * sk] + c_SH_C2[3] * xz * s[7 * sk] +
+                        c_SH_C2[4] * (xx - yy) * s[8 * sk];
+                    if (deg > 2) {
+                        r = r + c_SH_C3[0] * y * (3.0f * xx - yy) * s[9 * sk] + c_SH_C3[1] * xy * z * s[10 * sk] +
+                            c_SH_C3[2] * y * (4.0f * zz - xx - yy) * s[11 * sk] +
+                            c_SH_C3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * s[12 * sk] +
+                            c_SH_C3[4] * x * (4.0f * zz - xx - yy) * s[13 * sk] + c_SH_C3[5] * z * (xx - yy) * s[14 * sk] +
+                            c_SH_C3[6] * x * (xx - 3.0f * yy) * s[15 * sk];
+                    }
+                }
+            }
+            r += 0.5f;
+            o.rgb[3 * (size_t)i + ch] = fmaxf(r, 0.0f);
+        }
+    }
+    o.depths[i] = tz;
+    radii[i] = (int32_t)my_radius;
+    o.xy[i] = make_float2(pix, piy);
+    o.conic_o[i] = make_float4(MUL(cc, det_inv), MUL(-cb, det_inv), MUL(ca, det_inv), opac[i]);
+    o.tiles[i] = (uint32_t)((rmaxy - rminy) * (rmaxx - rminx));
+    o.rects[i] = make_ushort4((unsigned short)rminx, (unsigned short)rminy, (unsigned short)rmaxx, (unsigned short)rmaxy);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Inclusive scan of tiles_touched (uint32), 3 kernels: per-CTA scan + CTA totals, scan of totals, add CTA prefix.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 4;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ uint32_t block_inclusive_scan(uint32_t v, uint32_t* s_warp, uint32_t& total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t n = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += n;
+    }
+    if (lane == 31) s_warp[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = lane < SCAN_THREADS / 32 ? s_warp[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t n = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += n;
+        }
+        if (lane < SCAN_THREADS / 32) s_warp[lane] = w;
+    }
+    __syncthreads();
+    total = s_warp[SCAN_THREADS / 32 - 1];
+    const uint32_t prefix = warp > 0 ? s_warp[warp - 1] : 0;
+    __syncthreads();
+    return v + prefix;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_local_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
+                                                                  uint32_t* __restrict__ block_sums, int n) {
+    __shared__ uint32_t s_warp[SCAN_THREADS / 32];
+    const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS];
+    uint32_t sum = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        v[k] = (base + k < n) ? in[base + k] : 0u;
+        sum += v[k];
+        v[k] = sum;
+    }
+    uint32_t total;
+    const uint32_t incl = block_inclusive_scan(sum, s_warp, total);
+    const uint32_t excl = incl - sum;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k)
+        if (base + k < n) out[base + k] = v[k] + excl;
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+// single CTA: exclusive scan of the CTA totals in place; writes the grand total to *total_out
+__global__ void __launch_bounds__(SCAN_THREADS) scan_sums_kernel(uint32_t* __restrict__ block_sums, int nblocks,
+                                                                 uint32_t* __restrict__ total_out) {
+    __shared__ uint32_t s_warp[SCAN_THREADS / 32];
+    uint32_t carry = 0;
+    for (int start = 0; start < nblocks; start += SCAN_THREADS) {
+        const int i = start + threadIdx.x;
+        const uint32_t v = i < nblocks ? block_sums[i] : 0u;
+        uint32_t total;
+        const uint32_t incl = block_inclusive_scan(v, s_warp, total);
+        if (i < nblocks) block_sums[i] = carry + incl - v;
+        carry += total;
+    }
+    if (threadIdx.x == 0) *total_out = carry;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_add_kernel(uint32_t* __restrict__ out, const uint32_t* __restrict__ block_sums, int n) {
+    const uint32_t add = block_sums[blockIdx.x];
+    const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k)
+        if (base + k < n) out[base + k] += add;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) duplicate_with_keys_kernel(int G, int gx, const int32_t* __restrict__ radii,
+                                                                 const uint32_t* __restrict__ offsets, const float* __restrict__ depths,
+                                                                 const ushort4* __restrict__ rects, uint64_t* __restrict__ keys,
+                                                                 uint32_t* __restrict__ vals) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= G) return;
+    if (radii[i] <= 0) return;
+    uint32_t off = i == 0 ? 0u : offsets[i - 1];
+    const ushort4 r = rects[i];
+    const uint64_t dbits = (uint64_t)__float_as_uint(depths[i]);
+    for (uint32_t y = r.y; y < r.w; ++y)
+        for (uint32_t x = r.x; x < r.z; ++x) {
+            keys[off] = ((uint64_t)(y * (uint32_t)gx + x) << 32) | dbits;
+            vals[off] = (uint32_t)i;
+            ++off;
+        }
+}
+
+__global__ void __launch_bounds__(256) identify_tile_ranges_kernel(uint32_t D, const uint64_t* __restrict__ keys, uint2* __restrict__ ranges) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= D) return;
+    const uint32_t t = (uint32_t)(keys[j] >> 32);
+    if (j == 0) ranges[t].x = 0;
+    else {
+        const uint32_t tp = (uint32_t)(keys[j - 1] >> 32);
+        if (t != tp) {
+            ranges[tp].y = j;
+            ranges[t].x = j;
+        }
+    }
+    if (j == D - 1) ranges[t].y = D;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Blend: one CTA (16x16 threads) per tile, front-to-back over the tile's sorted list in batches of 256 records that
+// are staged once in shared memory (id, xy, conic+opacity, rgb+depth = 44 B) and then broadcast-read by all pixels.
+// ---------------------------------------------------------------------------------------------------------------
+template <bool COUNT_TOUCHED>
+__global__ void __launch_bounds__(TILE_X* TILE_Y) render_kernel(int W, int H, int gx, const uint2* __restrict__ ranges,
+                                                              const uint32_t* __restrict__ point_list, const float2* __restrict__ xy,
+                                                              const float4* __restrict__ conic_o, const float* __restrict__ rgb,
+                                                              const float* __restrict__ depths, const float* __restrict__ cam_dev,
+                                                              float* __restrict__ out_color, float* __restrict__ out_depth,
+                                                              float* __restrict__ out_opacity, int32_t* __restrict__ n_touched) {
+    constexpr int BS = TILE_X * TILE_Y;
+    __shared__ uint32_t s_id[BS];
+    __shared__ float2 s_xy[BS];
+    __shared__ float4 s_co[BS];
+    __shared__ float4 s_rgbd[BS];
+    __shared__ int s_cnt[COUNT_TOUCHED ? BS : 1];
+
+    const int tile_x = blockIdx.x, tile_y = blockIdx.y;
+    const int tid = threadIdx.y * TILE_X + threadIdx.x;
+    const int pxi = tile_x * TILE_X + threadIdx.x, pyi = tile_y * TILE_Y + threadIdx.y;
+    const bool inside = pxi < W && pyi < H;
+    const float pfx = (float)pxi, pfy = (float)pyi;
+    const uint2 range = ranges[tile_y * gx + tile_x];
+    const int rounds = (int)((range.y - range.x + BS - 1) / BS);
+    int todo = (int)(range.y - range.x);
+    bool done = !inside;
+    float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, Dz = 0.f;
+
+    for (int r = 0; r < rounds; ++r, todo -= BS) {
+        const int num_done = __syncthreads_count(done);
+        if (num_done == BS) break;
+        const uint32_t progress = range.x + (uint32_t)r * BS + tid;
+        if (progress < range.y) {
+            const uint32_t id = point_list[progress];
+            s_id[tid] = id;
+            s_xy[tid] = xy[id];
+            s_co[tid] = conic_o[id];
+            s_rgbd[tid] = make_float4(rgb[3 * (size_t)id], rgb[3 * (size_t)id + 1], rgb[3 * (size_t)id + 2], depths[id]);
+        }
+        if (COUNT_TOUCHED) s_cnt[tid] = 0;
+        __syncthreads();
+        const int nb = min(BS, todo);
+        for (int j = 0; j < nb; ++j) {
+            bool touch = false;
+            if (!done) {
+                const float2 p = s_xy[j];
+                const float4 co = s_co[j];
+                const float dx = p.x - pfx, dy = p.y - pfy;
+                const float power = -0.5f * (co.x * dx * dx + co.z * dy * dy) - co.y * dx * dy;
+                if (power <= 0.0f) {
+                    const float alpha = fminf(0.99f, co.w * __expf(power));
+                    if (alpha >= 1.0f / 255.0f) {
+                        const float test_T = T * (1.0f - alpha);
+                        if (test_T < 0.0001f) {
+                            done = true;
+                        } else {
+                            const float4 cd = s_rgbd[j];
+                            const float w = alpha * T;
+                            C0 += cd.x * w;
+                            C1 += cd.y * w;
+                            C2 += cd.z * w;
+                            Dz += cd.w * w;
+                            touch = test_T > 0.5f;
+                            T = test_T;
+                        }
+                    }
+                }
+            }
+            if (COUNT_TOUCHED) {
+                const unsigned m = __ballot_sync(0xffffffffu, touch);
+                if (m != 0 && (tid & 31) == 0) atomicAdd(&s_cnt[j], __popc(m));
+            }
+        }
+        if (COUNT_TOUCHED) {
+            __syncthreads();
+            if (progress < range.y && s_cnt[tid] > 0) atomicAdd(&n_touched[s_id[tid]], s_cnt[tid]);
+        }
+    }
+    if (inside) {
+        const size_t pid = (size_t)pyi * W + pxi;
+        const size_t hw = (size_t)H * W;
+        const float* bg = cam_dev + 35;  // Camera::bg
+        out_color[pid] = C0 + T * bg[0];
+        out_color[hw + pid] = C1 + T * bg[1];
+        out_color[2 * hw + pid] = C2 + T * bg[2];
+        out_depth[pid] = Dz;
+        out_opacity[pid] = 1.0f - T;
+    }
+}
+
+__global__ void pack_camera_kernel(const float* __restrict__ view, const float* __restrict__ proj, const float* __restrict__ campos,
+                                   const float* __restrict__ bg, float* __restrict__ cam) {
+    const int t = threadIdx.x;
+    if (t < 16) cam[t] = view[t];
+    else if (t < 32) cam[t] = proj[t - 16];
+    else if (t < 35) cam[t] = campos[t - 32];
+    else if (t < 38) cam[t] = bg[t - 35];
+}
+
+struct Workspace {
+    float* depths; float2* xy; float4* conic_o; float* rgb; uint32_t* tiles; ushort4* rects; uint32_t* offsets;
+    uint32_t* block_sums; uint32_t* total; float* cam; uint2* ranges;
+    uint64_t* keys; uint64_t* keys_sorted; uint32_t* vals; uint32_t* vals_sorted; void* cub_temp; size_t cub_bytes;
+    size_t bytes;
+};
+
+int higher_msb(uint32_t n) {
+    uint32_t msb = sizeof(n) * 4, step = msb;
+    while (step > 1) {
+        step /= 2;
+        if (n >> msb) msb += step; else msb -= step;
+    }
+    if (n >> msb) msb++;
+    return (int)msb;
+}
+
+size_t cub_temp_bytes(int64_t cap, int end_bit) {
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr, (const uint32_t*)nullptr,
+                                    (uint32_t*)nullptr, (int)cap, 0, end_bit);
+    return bytes;
+}
+
+Workspace carve(void* base, int G, int H, int W, int64_t cap) {
+    Workspace w{};
+    size_t off = 0;
+    char* b = (char*)base;
+    auto take = [&](size_t n) { void* p = b ? b + off : nullptr; off = align_up(off + n, 256); return p; };
+    const int gx = ceil_div(W, TILE_X), gy = ceil_div(H, TILE_Y);
+    w.depths = (float*)take(sizeof(float) * G);
+    w.xy = (float2*)take(sizeof(float2) * G);
+    w.conic_o = (float4*)take(sizeof(float4) * G);
+    w.rgb = (float*)take(sizeof(float) * 3 * G);
+    w.tiles = (uint32_t*)take(sizeof(uint32_t) * G);
+    w.rects = (ushort4*)take(sizeof(ushort4) * G);
+    w.offsets = (uint32_t*)take(sizeof(uint32_t) * G);
+    w.block_sums = (uint32_t*)take(sizeof(uint32_t) * (ceil_div(G, SCAN_TILE) + 1));
+    w.total = (uint32_t*)take(256);
+    w.cam = (float*)take(256);
+    w.ranges = (uint2*)take(sizeof(uint2) * gx * gy);
+    w.keys = (uint64_t*)take(sizeof(uint64_t) * cap);
+    w.keys_sorted = (uint64_t*)take(sizeof(uint64_t) * cap);
+    w.vals = (uint32_t*)take(sizeof(uint32_t) * cap);
+    w.vals_sorted = (uint32_t*)take(sizeof(uint32_t) * cap);
+    w.cub_bytes = cub_temp_bytes(cap, 32 + higher_msb((uint32_t)(gx * gy)));
+    w.cub_temp = take(w.cub_bytes);
+    w.bytes = off;
+    return w;
+}
+
+}  // namespace
+
+extern "C" {
+
+// Bytes of device scratch siu3r_raster_forward needs for G Gaussians, an HxW image and at most `dup_capacity`
+// (tile, Gaussian) duplicates.  Mirrors the resize-callback buffers of the reference rasterizer (geomBuffer,
+// binningBuffer, imageBuffer): here the caller (PyTorch) owns the allocation.
+int64_t siu3r_raster_workspace_bytes(int G, int H, int W, int64_t dup_capacity) {
+    if (G <= 0 || H <= 0 || W <= 0 || dup_capacity <= 0) return SIU3R_ERR_INVALID;
+    if (dup_capacity >= (1ll << 31)) return SIU3R_ERR_INVALID;
+    Workspace w = carve(nullptr, G, H, W, dup_capacity);
+    return (int64_t)w.bytes;
+}
+
+// Forward rasterization of one camera.  All pointers are device pointers unless noted.
+//   means3D [G,3]; cov: [G,6] (xx,xy,xz,yy,yz,zz; cov_stride=6) or [G,3,3] (cov_stride=9);
+//   shs: sh_layout 0 = [G,sh_coeffs,3] (what render_cuda passes), 1 = [G,3,sh_coeffs] (Gaussians.harmonics as stored);
+//   opacities [G]; viewmatrix/projmatrix [16] as torch lays out view_matrix[i] / full_projection[i]
+//   (cuda_splatting.py:74-77); campos [3]; bg [3].
+// Outputs: out_color [3,H,W], out_depth [H,W], out_opacity [H,W], radii [G] int32, n_touched [G] int32 (may be null).
+// debug_* (may be null): tiles_touched [G], offsets [G], sorted keys/values [>= D], ranges [tiles*2].
+// num_rendered_host (host pointer, may be null) receives D.  Synchronises the stream once (to read D), like the
+// reference implementation does.
+int siu3r_raster_forward(int G, int H, int W, int sh_degree, int sh_coeffs, int sh_layout, int cov_stride,
+                         const float* means3D, const float* cov, const float* shs, const float* opacities,
+                         const float* viewmatrix, const float* projmatrix, const float* campos, const float* bg,
+                         float tan_fovx, float tan_fovy, float* out_color, float* out_depth, float* out_opacity,
+                         int32_t* radii, int32_t* n_touched, void* workspace, int64_t workspace_bytes,
+                         int64_t dup_capacity, int64_t* num_rendered_host, uint32_t* debug_tiles_touched,
+                         uint32_t* debug_offsets, uint64_t* debug_keys, uint32_t* debug_values, uint32_t* debug_ranges,
+                         void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    SIU3R_REQUIRE(G > 0 && H > 0 && W > 0);
+    SIU3R_REQUIRE(sh_coeffs >= 1 && sh_coeffs * 3 <= MAX_SH_FLOATS);
+    SIU3R_REQUIRE((sh_degree + 1) * (sh_degree + 1) <= sh_coeffs);
+    SIU3R_REQUIRE(sh_layout == 0 || sh_layout == 1);
+    SIU3R_REQUIRE(cov_stride == 6 || cov_stride == 9);
+    SIU3R_REQUIRE(means3D && cov && shs && opacities && viewmatrix && projmatrix && campos && bg);
+    SIU3R_REQUIRE(out_color && out_depth && out_opacity && radii && workspace);
+    SIU3R_REQUIRE(dup_capacity > 0 && dup_capacity < (1ll << 31));
+    const int gx = ceil_div(W, TILE_X), gy = ceil_div(H, TILE_Y);
+    SIU3R_REQUIRE(gx < 65536 && gy < 65536);
+    Workspace w = carve(workspace, G, H, W, dup_capacity);
+    if ((int64_t)w.bytes > workspace_bytes) return SIU3R_ERR_CAPACITY;
+    const int deg = sh_degree > 3 ? 3 : sh_degree;  // the reference kernel evaluates SH bands 0..3 only
+    const float focal_y = (float)H / (2.0f * tan_fovy), focal_x = (float)W / (2.0f * tan_fovx);
+
+    SIU3R_CUDA_CHECK(cudaMemsetAsync(radii, 0, sizeof(int32_t) * G, stream));
+    SIU3R_CUDA_CHECK(cudaMemsetAsync(w.tiles, 0, sizeof(uint32_t) * G, stream));
+    SIU3R_CUDA_CHECK(cudaMemsetAsync(w.ranges, 0, sizeof(uint2) * gx * gy, stream));
+    if (n_touched) SIU3R_CUDA_CHECK(cudaMemsetAsync(n_touched, 0, sizeof(int32_t) * G, stream));
+
+    pack_camera_kernel<<<1, 64, 0, stream>>>(viewmatrix, projmatrix, campos, bg, w.cam);
+    PreOut po{w.depths, w.xy, w.conic_o, w.rgb, w.tiles, w.rects};
+    preprocess_kernel<<<ceil_div(G, PRE_THREADS), PRE_THREADS, 0, stream>>>(G, H, W, gx, gy, deg, sh_coeffs, sh_layout, cov_stride,
+                                                                            means3D, cov, shs, opacities, w.cam, tan_fovx, tan_fovy,
+                                                                            focal_x, focal_y, po, radii);
+    const int nsb = ceil_div(G, SCAN_TILE);
+    scan_local_kernel<<<nsb, SCAN_THREADS, 0, stream>>>(w.tiles, w.offsets, w.block_sums, G);
+    scan_sums_kernel<<<1, SCAN_THREADS, 0, stream>>>(w.block_sums, nsb, w.total);
+    scan_add_kernel<<<nsb, SCAN_THREADS, 0, stream>>>(w.offsets, w.block_sums, G);
+    SIU3R_LAUNCH_CHECK();
+    siu3r_note_launch(5);
+
+    uint32_t D32 = 0;
+    SIU3R_CUDA_CHECK(cudaMemcpyAsync(&D32, w.total, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    SIU3R_CUDA_CHECK(cudaStreamSynchronize(stream));
+    const int64_t D = (int64_t)D32;
+    if (num_rendered_host) *num_rendered_host = D;
+    if (debug_tiles_touched) SIU3R_CUDA_CHECK(cudaMemcpyAsync(debug_tiles_touched, w.tiles, sizeof(uint32_t) * G, cudaMemcpyDeviceToDevice, stream));
+    if (debug_offsets) SIU3R_CUDA_CHECK(cudaMemcpyAsync(debug_offsets, w.offsets, sizeof(uint32_t) * G, cudaMemcpyDeviceToDevice, stream));
+    if (D > dup_capacity) return SIU3R_ERR_CAPACITY;
+
+    const uint64_t* sorted_keys = w.keys_sorted;
+    const uint32_t* sorted_vals = w.vals_sorted;
+    if (D > 0) {
+        duplicate_with_keys_kernel<<<ceil_div(G, 256), 256, 0, stream>>>(G, gx, radii, w.offsets, w.depths, w.rects, w.keys, w.vals);
+        const int end_bit = 32 + higher_msb((uint32_t)(gx * gy));
+        size_t tb = w.cub_bytes;
+        SIU3R_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(w.cub_temp, tb, w.keys, w.keys_sorted, w.vals, w.vals_sorted, (int)D, 0,
+                                                         end_bit, stream));
+        identify_tile_ranges_kernel<<<(unsigned)ceil_div_i64(D, 256), 256, 0, stream>>>((uint32_t)D, sorted_keys, w.ranges);
+        SIU3R_LAUNCH_CHECK();
+        siu3r_note_launch(2);
+    }
+    dim3 grid(gx, gy), block(TILE_X, TILE_Y);
+    if (n_touched)
+        render_kernel<true><<<grid, block, 0, stream>>>(W, H, gx, w.ranges, sorted_vals, w.xy, w.conic_o, w.rgb, w.depths, w.cam,
+                                                        out_color, out_depth, out_opacity, n_touched);
+    else
+        render_kernel<false><<<grid, block, 0, stream>>>(W, H, gx, w.ranges, sorted_vals, w.xy, w.conic_o, w.rgb, w.depths, w.cam,
+                                                         out_color, out_depth, out_opacity, nullptr);
+    SIU3R_LAUNCH_CHECK();
+    siu3r_note_launch(1);
+    if (D > 0) {
+        if (debug_keys) SIU3R_CUDA_CHECK(cudaMemcpyAsync(debug_keys, sorted_keys, sizeof(uint64_t) * D, cudaMemcpyDeviceToDevice, stream));
+        if (debug_values) SIU3R_CUDA_CHECK(cudaMemcpyAsync(debug_values, sorted_vals, sizeof(uint32_t) * D, cudaMemcpyDeviceToDevice, stream));
+    }
+    if (debug_ranges) SIU3R_CUDA_CHECK(cudaMemcpyAsync(debug_ranges, w.ranges, sizeof(uint2) * gx * gy, cudaMemcpyDeviceToDevice, stream));
+    return SIU3R_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,127 @@
+/*
+ * siu3r_b200 C ABI -- the drop-in boundary of the B200-native SIU3R hot path (libsiu3r_b200.so).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; the caller (PyTorch) owns all memory;
+ *   - fp32 storage everywhere, token-major / NHWC layouts ([rows, C] with an explicit leading dimension in floats);
+ *   - `stream` is a cudaStream_t passed as void*; kernels are enqueued on it and never synchronise, except
+ *     siu3r_raster_forward (one sync to read the duplicate count, like the reference rasterizer);
+ *   - return value: 0 = ok, -1 invalid argument, -2 capacity/workspace too small, -3 CUDA error, -4 unsupported config
+ *     (message on stderr); no exceptions cross the ABI, no global state besides the launch counter;
+ *   - `precision`: 1 = TF32 tensor-core math (the reference's own GPU mode: src/models/croco/croco.py:13),
+ *                  3 = 3xTF32 split (fp32-grade accuracy on the tensor cores; needs *_lo planes from siu3r_split_tf32).
+ *
+ * Every entry point cites the reference interface it replaces (paths relative to /root/reference).
+ */
+#ifndef SIU3R_B200_H
+#define SIU3R_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- bookkeeping --------------------------------------------------------------------------------------------- */
+int siu3r_abi_version(void);
+void siu3r_note_launch(int n);
+long long siu3r_launch_count(void);      /* kernels launched by this library since the last reset */
+void siu3r_reset_launch_count(void);
+
+/* ---- 3D Gaussian splatting rasterizer (forward) ---------------------------------------------------------------
+ * Replaces diff_gaussian_rasterization._C.rasterize_gaussians as driven by GaussianRasterizer(settings)(...) at
+ * src/models/cuda_splatting.py:90-118 (means3D, shs, opacities, cov3D_precomp; sh_degree = isqrt(25)-1 = 4).
+ * Returns the reference 5-tuple (image, radii, depth, opacity, n_touched) of cuda_splatting.py:109. */
+int64_t siu3r_raster_workspace_bytes(int G, int H, int W, int64_t dup_capacity);
+int siu3r_raster_forward(int G, int H, int W, int sh_degree, int sh_coeffs, int sh_layout, int cov_stride,
+                         const float* means3D, const float* cov, const float* shs, const float* opacities,
+                         const float* viewmatrix, const float* projmatrix, const float* campos, const float* bg,
+                         float tan_fovx, float tan_fovy, float* out_color, float* out_depth, float* out_opacity,
+                         int32_t* radii, int32_t* n_touched, void* workspace, int64_t workspace_bytes,
+                         int64_t dup_capacity, int64_t* num_rendered_host, uint32_t* debug_tiles_touched,
+                         uint32_t* debug_offsets, uint64_t* debug_keys, uint32_t* debug_values, uint32_t* debug_ranges,
+                         void* stream);
+
+/* ---- dense contractions on the tcgen05 tensor cores ------------------------------------------------------------
+ * siu3r_gemm_tc   : torch.nn.functional.linear (+bias, +GELU/ReLU, +residual): croco/blocks.py:74-77,97,110,154-156,167;
+ *                   backbone_croco.py:87; vit_adapter/blocks.py:118-121; every nn.Linear / 1x1 Conv2d of
+ *                   mask2former/video_seg_decoder.py and heads/dpt_block.py.
+ * siu3r_conv2d_tc : nn.Conv2d(k, stride 1, padding) as implicit GEMM over NHWC: heads/dpt_block.py:35-70,98-116,358-364,
+ *                   385-387; mask2former/video_seg_decoder.py:2040-2047. */
+int siu3r_gemm_tc(int M, int N, int K, const float* A, const float* A_lo, int64_t lda, const float* Wt, const float* W_lo,
+                  int64_t ldw, float* C, int64_t ldc, const float* bias, const float* residual, int64_t ldr, int act,
+                  float alpha, int precision, void* stream);
+int siu3r_conv2d_tc(int Nimg, int H, int W, int Cin, int Cout, int KH, int KW, int pad, const float* x, const float* x_lo,
+                    const float* Wt, const float* W_lo, float* y, int64_t ldc, const float* bias, const float* residual,
+                    int64_t ldr, int act, int precision, void* stream);
+/* plain fp32 FFMA GEMM (tiny / odd shapes such as the K = 9 intrinsics encoder, backbone_croco.py:59,278) */
+int siu3r_gemm_simt(int M, int N, int K, const float* A, int64_t lda, const float* W, int64_t ldw, float* C, int64_t ldc,
+                    const float* bias, const float* residual, int64_t ldr, int act, float alpha, void* stream);
+int siu3r_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream);
+
+/* ---- transformer pieces ----------------------------------------------------------------------------------------
+ * siu3r_rope2d replaces curope.rope_2d(tokens, positions, base, fwd) (croco/curope/curope.cpp:49-65,
+ * kernels.cu:17-82; called from croco/curope/curope2d.py:20,27 <- croco/blocks.py:101-103,158-160): in place, tokens
+ * [B,N,H,D] with arbitrary batch/token strides (so q and k can be rotated inside the fused qkv buffer), positions
+ * [B,N,2] int64 (y, x).  Error contract: D % 4 != 0 -> -1 ("token dim must be multiple of 4", kernels.cu:94). */
+int siu3r_rope2d(float* tokens, const int64_t* positions, int B, int N, int H, int D, int64_t batch_stride,
+                 int64_t token_stride, float base, float fwd, void* stream);
+/* nn.LayerNorm over the last dim (+ optional fused add of `add` rows): croco/blocks.py:119-125,176-184 */
+int siu3r_layernorm(const float* x, int64_t ldx, const float* w, const float* b, float* y, int64_t ldy, int rows, int C,
+                    float eps, const float* add, int64_t ldadd, void* stream);
+/* softmax(Q K^T * scale) V, head dim 64: croco/blocks.py:105-109 (Attention), :162-166 (CrossAttention) */
+int siu3r_flash_attn_d64(const float* Q, int64_t q_bs, int64_t q_ts, const float* K, int64_t k_bs, int64_t k_ts,
+                         const float* V, int64_t v_bs, int64_t v_ts, float* O, int64_t o_bs, int64_t o_ts, int B, int H,
+                         int Nq, int Nk, float scale, int precision, void* stream);
+/* masked / plain attention with head dim 32: mask2former/video_seg_decoder.py:975-983,994-999,1306-1308 */
+int siu3r_attn_small_d32(const float* Q, int64_t q_bs, int64_t q_ts, const float* K, int64_t k_bs, int64_t k_ts,
+                         const float* V, int64_t v_bs, int64_t v_ts, float* O, int64_t o_bs, int64_t o_ts,
+                         const uint8_t* mask, int B, int H, int Nq, int Nk, float scale, void* stream);
+/* multi_scale_deformable_attention (vit_adapter/blocks.py:171-213,217-267; video_seg_decoder.py:1679-1720) */
+int siu3r_msdeform_attn(const float* value, int64_t ldv, int Lin, const float* ow, int64_t ldow, const float* ref,
+                        const int* level_hw_host, int L, int P, int B, int Lq, int nH, int hd, float* out, int64_t ldo,
+                        void* stream);
+
+/* ---- HBM-bound elementwise / resampling ------------------------------------------------------------------------ */
+int siu3r_eltwise(int op, const float* a, const float* b, float* out, int64_t n, void* stream);
+/* in-place scene rescale of SplattingCUDA.forward (gaussian_renderer.py:43-46) */
+int siu3r_scale(const float* a, float alpha, float* out, int64_t n, void* stream);
+int siu3r_rows_affine(const float* x, int64_t ldx, const float* scale, const float* shift, const float* add,
+                      int64_t ldadd, float* y, int64_t ldy, int64_t rows, int C, int relu, void* stream);
+/* F.interpolate(mode="bilinear"): heads/dpt_block.py:229-235,279-284; vit_adapter.py:429-433; video_seg_decoder.py:2173 */
+int siu3r_resize_bilinear_nhwc(const float* x, int N, int H, int W, int C, int64_t ldx, float* y, int OH, int OW,
+                               int64_t ldy, int align_corners, int accumulate, void* stream);
+/* scatter half of nn.ConvTranspose2d(kernel = stride): heads/dpt_block.py:422-451; vit_adapter.py:356,425 */
+int siu3r_pixel_shuffle_nhwc(const float* g, int N, int H, int W, int C, int s, const float* add, float* y, void* stream);
+int siu3r_im2col_nhwc(const float* x, int N, int H, int W, int C, int KH, int KW, int stride, int pad, float* out,
+                      int64_t ldo, void* stream);
+int siu3r_nchw_to_nhwc(const float* x, float* y, int N, int C, int HW, int64_t ldy, void* stream);
+int siu3r_nhwc_to_nchw(const float* x, int64_t ldx, float* y, int N, int C, int HW, void* stream);
+int siu3r_maxpool3x3s2_nhwc(const float* x, int N, int H, int W, int C, float* y, void* stream);   /* vit_adapter.py:220 */
+int siu3r_dwconv3x3_nhwc(const float* x, int64_t ldx, int64_t batch_stride_x, int N, int H, int W, int C, const float* w,
+                         const float* b, float* y, int64_t ldy, int64_t batch_stride_y, int gelu, void* stream); /* :16-31 */
+int siu3r_groupnorm_nhwc(const float* x, int N, int HW, int C, int groups, const float* w, const float* b, float eps,
+                         int relu, float* y, void* stream);                         /* video_seg_decoder.py:2004,2036,2048 */
+
+/* ---- heads / outputs ------------------------------------------------------------------------------------------- */
+int siu3r_depth_exp(const float* xyz, int64_t ldx, float* pts, int64_t n, void* stream);   /* heads/postprocess.py:46-61 */
+/* UnifiedGaussianAdapter.forward (gaussian_adapter.py:81-110) */
+int siu3r_gaussian_adapter(const float* raw, int64_t G, float* covariances, float* harmonics, float* opacities,
+                           float* scales, float* rotations, void* stream);
+/* VideoMask2FormerMaskPredictor attention mask (video_seg_decoder.py:1461-1478) */
+int siu3r_attn_mask_from_logits(const float* logits, int B, int T, int Hm, int Wm, int Q, int oh, int ow, uint8_t* mask,
+                                void* stream);
+/* post_process_panoptic_segmentation device stages (image_processing_video_mask2former.py:1386-1467; model.py:258-294) */
+int siu3r_resize_select(const float* x, int N, int H, int W, int C, const int* idx, int nsel, float* y, int OH, int OW,
+                        void* stream);
+int siu3r_argmax_area(const float* probs, int64_t npix, int nq, const float* score, float thr, int32_t* labels,
+                      int32_t* area, int32_t* orig, void* stream);
+int siu3r_label_lut(const int32_t* labels, int64_t npix, const int32_t* seg_lut, const int32_t* sem_lut, int32_t* seg,
+                    int32_t* sem, int32_t* inst, void* stream);
+int siu3r_qc_logits(const float* probs, int64_t npix, int nq, const int* keep, int nk, const float* cls, int ncls,
+                    float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIU3R_B200_H */

@@ -1,0 +1,19 @@
+"""siu3r_b200 -- B200-native (sm_100a) engine for the SIU3R per-image-pair hot path.
+
+Public surface (mirrors the reference):
+  siu3r_b200.SIU3RModel        <-> /root/reference/src/models/model.py:31  (forward :314-389)
+  siu3r_b200.SplattingCUDA     <-> /root/reference/src/models/gaussian_renderer.py:15 (forward :29-116)
+  siu3r_b200.render_cuda       <-> /root/reference/src/models/cuda_splatting.py:46-122
+  siu3r_b200.Gaussians         <-> /root/reference/src/utils/gaussians_types.py:4-38
+"""
+from .gaussians import Gaussians  # noqa: F401
+
+
+def __getattr__(name):
+    if name in ("SIU3RModel", "ModelCfg"):
+        from . import model as _m
+        return getattr(_m, name)
+    if name in ("SplattingCUDA", "render_cuda"):
+        from . import renderer as _r
+        return getattr(_r, name)
+    raise AttributeError(name)

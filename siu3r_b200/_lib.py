@@ -1,0 +1,83 @@
+"""ctypes binding of libsiu3r_b200.so (the C ABI declared in include/siu3r_b200.h).
+
+The product path has NO fallback: if the CUDA library is missing, loading raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libsiu3r_b200.so")
+
+_p = C.c_void_p
+_i = C.c_int
+_l = C.c_int64
+_f = C.c_float
+
+# name -> (restype, argtypes); mirrors include/siu3r_b200.h one to one
+SIGNATURES = {
+    "siu3r_abi_version": (_i, []),
+    "siu3r_note_launch": (None, [_i]),
+    "siu3r_launch_count": (C.c_longlong, []),
+    "siu3r_reset_launch_count": (None, []),
+    "siu3r_raster_workspace_bytes": (_l, [_i, _i, _i, _l]),
+    "siu3r_raster_forward": (_i, [_i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _l, _l,
+                                  C.POINTER(C.c_int64), _p, _p, _p, _p, _p, _p]),
+    "siu3r_gemm_tc": (_i, [_i, _i, _i, _p, _p, _l, _p, _p, _l, _p, _l, _p, _p, _l, _i, _f, _i, _p]),
+    "siu3r_conv2d_tc": (_i, [_i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _l, _p, _p, _l, _i, _i, _p]),
+    "siu3r_gemm_simt": (_i, [_i, _i, _i, _p, _l, _p, _l, _p, _l, _p, _p, _l, _i, _f, _p]),
+    "siu3r_split_tf32": (_i, [_p, _p, _p, _l, _p]),
+    "siu3r_rope2d": (_i, [_p, _p, _i, _i, _i, _i, _l, _l, _f, _f, _p]),
+    "siu3r_layernorm": (_i, [_p, _l, _p, _p, _p, _l, _i, _i, _f, _p, _l, _p]),
+    "siu3r_flash_attn_d64": (_i, [_p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _l, _l, _i, _i, _i, _i, _f, _i, _p]),
+    "siu3r_attn_small_d32": (_i, [_p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _i, _i, _i, _i, _f, _p]),
+    "siu3r_msdeform_attn": (_i, [_p, _l, _i, _p, _l, _p, C.POINTER(C.c_int), _i, _i, _i, _i, _i, _i, _p, _l, _p]),
+    "siu3r_eltwise": (_i, [_i, _p, _p, _p, _l, _p]),
+    "siu3r_scale": (_i, [_p, _f, _p, _l, _p]),
+    "siu3r_rows_affine": (_i, [_p, _l, _p, _p, _p, _l, _p, _l, _l, _i, _i, _p]),
+    "siu3r_resize_bilinear_nhwc": (_i, [_p, _i, _i, _i, _i, _l, _p, _i, _i, _l, _i, _i, _p]),
+    "siu3r_pixel_shuffle_nhwc": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p]),
+    "siu3r_im2col_nhwc": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _l, _p]),
+    "siu3r_nchw_to_nhwc": (_i, [_p, _p, _i, _i, _i, _l, _p]),
+    "siu3r_nhwc_to_nchw": (_i, [_p, _l, _p, _i, _i, _i, _p]),
+    "siu3r_maxpool3x3s2_nhwc": (_i, [_p, _i, _i, _i, _i, _p, _p]),
+    "siu3r_dwconv3x3_nhwc": (_i, [_p, _l, _l, _i, _i, _i, _i, _p, _p, _p, _l, _l, _i, _p]),
+    "siu3r_groupnorm_nhwc": (_i, [_p, _i, _i, _i, _i, _p, _p, _f, _i, _p, _p]),
+    "siu3r_depth_exp": (_i, [_p, _l, _p, _l, _p]),
+    "siu3r_gaussian_adapter": (_i, [_p, _l, _p, _p, _p, _p, _p, _p]),
+    "siu3r_attn_mask_from_logits": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
+    "siu3r_resize_select": (_i, [_p, _i, _i, _i, _i, _p, _i, _p, _i, _i, _p]),
+    "siu3r_argmax_area": (_i, [_p, _l, _i, _p, _f, _p, _p, _p, _p]),
+    "siu3r_label_lut": (_i, [_p, _l, _p, _p, _p, _p, _p, _p]),
+    "siu3r_qc_logits": (_i, [_p, _l, _i, _p, _i, _p, _i, _p, _p]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the CUDA library; fails loudly (no CPU / library fallback exists for the product path)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"siu3r_b200: CUDA extension not built ({LIB_PATH} missing). Run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `python siu3r_b200/build.py`. There is no fallback path."
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+ERRORS = {-1: "invalid argument", -2: "capacity / workspace too small", -3: "CUDA error", -4: "unsupported configuration"}
+
+
+def check(code: int, what: str):
+    if code != 0:
+        raise RuntimeError(f"siu3r_b200.{what} failed: {ERRORS.get(code, code)} (see stderr)")

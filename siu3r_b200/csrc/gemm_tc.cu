@@ -1,0 +1,467 @@
+// tcgen05 (5th-gen tensor core) GEMM / implicit-GEMM convolution for sm_100a, fp32 storage, TF32 tensor-core math.
+//
+//   C[M,N] = epilogue( A[M,K] * W[N,K]^T )            (W is a torch nn.Linear weight: K-major, exactly the UMMA B operand)
+//
+// It is the workhorse behind every nn.Linear / 1x1 conv / 3x3 stride-1 conv on the hot path:
+//   croco/blocks.py:97,110,74-77,154-156,167 (qkv / proj / fc1 / fc2 / projq,k,v), backbone_croco.py:87 (decoder_embed),
+//   heads/dpt_block.py:98-116,181-189,358-364,385-391 (DPT 3x3 / 1x1 convs), vit_adapter/blocks.py:118-121,
+//   mask2former/video_seg_decoder.py (all Linear / Conv2d 1x1 / 3x3).
+//
+// Structure (one 128 x BN output tile per CTA, 192 threads, warp-specialised):
+//   warp 0   : TMA producer   - cp.async.bulk.tensor (2-D for a row-major A, 4-D NHWC box for the conv A operand: the
+//              tile's 8x16 pixel patch shifted by the filter tap, halo zero-filled by TMA = conv padding for free),
+//              128B-swizzled stages, mbarrier complete_tx.
+//   warp 1   : MMA issuer     - one elected lane issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8) from shared-memory
+//              descriptors, accumulator in TMEM; tcgen05.commit frees stages / signals the epilogue.
+//   warps 2-5: epilogue       - tcgen05.ld 32x32b.x32 -> registers -> bias / GELU(erf) / ReLU / residual -> global.
+//
+// Precision modes:
+//   NSPLIT = 1 : plain TF32 (what the reference itself runs on GPU: croco/croco.py:13 allow_tf32 = True).
+//   NSPLIT = 3 : 3xTF32 split (A = A_hi + A_lo, W = W_hi + W_lo; hi*hi + lo*hi + hi*lo, fp32 accumulate) - ~fp32
+//                accuracy on the tensor cores; used for the strict parity tolerances of BASELINE.json's north_star.
+#include <cuda.h>
+
+#include <mutex>
+#include <unordered_map>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 32;          // fp32 elements per k-block = 128 bytes = one SWIZZLE_128B row
+constexpr int UMMA_K = 8;       // tf32
+constexpr int NUM_THREADS = 192;
+constexpr int CONV_TW = 16, CONV_TH = 8;  // spatial patch of one M tile in conv mode
+
+enum Act { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2 };
+
+struct GemmParams {
+    int M, N, num_kb;
+    float* C; int64_t ldc;
+    const float* bias;         // [N] or null
+    const float* residual;     // [M, ldr] or null (added after activation)
+    int64_t ldr;
+    int act;
+    float alpha;               // scales the accumulator before bias
+    // conv mode
+    int conv;                  // 0 = linear, 1 = conv (stride 1)
+    int H, W, Cin, KH, KW, pad;
+    int tiles_w, tiles_h;      // tiles per image row / column
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(NCOLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], tf32 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// mbarrier arrive once all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO(1)<<16 |
+// SBO(1024 B>>4 = 64)<<32 | version(1)<<46 | layout SWIZZLE_128B(2)<<61
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// cute::UMMA::InstrDescriptor for kind::tf32: D fp32 (bit 4), A/B = TF32 (2 at bits 7 / 10), both K-major,
+// N>>3 at bit 17, M>>4 at bit 24
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+template <int BN, int NSPLIT>
+struct Cfg {
+    static constexpr int NOPER = NSPLIT == 1 ? 1 : 2;  // hi (+ lo) planes per operand
+    static constexpr int A_BYTES = BM * BK * 4;
+    static constexpr int B_BYTES = BN * BK * 4;
+    static constexpr int STAGE_BYTES = NOPER * (A_BYTES + B_BYTES);
+    static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+};
+
+template <int BN, int NSPLIT>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
+               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo, const GemmParams p) {
+    using C_ = Cfg<BN, NSPLIT>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C_::STAGES * C_::STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + C_::STAGES;
+    uint64_t* acc_bar = empty_bar + C_::STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.y * BN;
+    // M-tile coordinates
+    int m0 = blockIdx.x * BM, img = 0, h0 = 0, w0 = 0;
+    if (p.conv) {
+        const int per_img = p.tiles_w * p.tiles_h;
+        img = blockIdx.x / per_img;
+        const int t = blockIdx.x % per_img;
+        h0 = (t / p.tiles_w) * CONV_TH;
+        w0 = (t % p.tiles_w) * CONV_TW;
+    }
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmA);
+        prefetch_tmap(&tmB);
+        if (NSPLIT == 3) { prefetch_tmap(&tmAlo); prefetch_tmap(&tmBlo); }
+        for (int s = 0; s < C_::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(acc_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<C_::TMEM_COLS>(tmem_slot);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            const int cblocks = p.conv ? p.Cin / BK : 0;
+            int stage = 0; uint32_t phase = 0;
+            for (int kb = 0; kb < p.num_kb; ++kb) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                uint8_t* sA = smem + stage * C_::STAGE_BYTES;
+                uint8_t* sB = sA + C_::NOPER * C_::A_BYTES;
+                mbar_expect_tx(&full_bar[stage], C_::STAGE_BYTES);
+                if (p.conv) {
+                    const int tap = kb / cblocks, cb = kb - tap * cblocks;
+                    const int kh = tap / p.KW, kw = tap - kh * p.KW;
+                    tma_load_4d(&tmA, &full_bar[stage], sA, cb * BK, w0 + kw - p.pad, h0 + kh - p.pad, img);
+                    if (NSPLIT == 3) tma_load_4d(&tmAlo, &full_bar[stage], sA + C_::A_BYTES, cb * BK, w0 + kw - p.pad, h0 + kh - p.pad, img);
+                } else {
+                    tma_load_2d(&tmA, &full_bar[stage], sA, kb * BK, m0);
+                    if (NSPLIT == 3) tma_load_2d(&tmAlo, &full_bar[stage], sA + C_::A_BYTES, kb * BK, m0);
+                }
+                tma_load_2d(&tmB, &full_bar[stage], sB, kb * BK, n0);
+                if (NSPLIT == 3) tma_load_2d(&tmBlo, &full_bar[stage], sB + C_::B_BYTES, kb * BK, n0);
+                if (++stage == C_::STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_tf32(BM, BN);
+            int stage = 0; uint32_t phase = 0;
+            for (int kb = 0; kb < p.num_kb; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
+                tcgen05_fence_after();
+                const uint32_t sA = smem_u32(smem + stage * C_::STAGE_BYTES);
+                const uint32_t sB = sA + C_::NOPER * C_::A_BYTES;
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                    const uint32_t koff = k * UMMA_K * 4;
+                    const uint32_t first = (kb | k) != 0;
+                    if (NSPLIT == 3) {
+                        // small cross terms first, then the dominant hi*hi term
+                        umma_tf32(tmem_base, make_smem_desc(sA + C_::A_BYTES + koff), make_smem_desc(sB + koff), idesc, first);
+                        umma_tf32(tmem_base, make_smem_desc(sA + koff), make_smem_desc(sB + C_::B_BYTES + koff), idesc, 1u);
+                        umma_tf32(tmem_base, make_smem_desc(sA + koff), make_smem_desc(sB + koff), idesc, 1u);
+                    } else {
+                        umma_tf32(tmem_base, make_smem_desc(sA + koff), make_smem_desc(sB + koff), idesc, first);
+                    }
+                }
+                umma_commit(&empty_bar[stage]);  // stage reusable once these MMAs have read it
+                if (++stage == C_::STAGES) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(acc_bar);  // accumulator complete
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        mbar_wait(acc_bar, 0);
+        tcgen05_fence_after();
+        const int q = warp & 3;             // TMEM lane quarter this warp may access
+        const int r = q * 32 + lane;        // row inside the tile
+        int64_t row_off; bool row_ok; int64_t res_off = 0;
+        if (p.conv) {
+            const int h = h0 + r / CONV_TW, w = w0 + r % CONV_TW;
+            row_ok = (h < p.H) && (w < p.W);
+            const int64_t pix = ((int64_t)img * p.H + h) * p.W + w;
+            row_off = pix * p.ldc;
+            res_off = pix * p.ldr;
+        } else {
+            const int m = m0 + r;
+            row_ok = m < p.M;
+            row_off = (int64_t)m * p.ldc;
+            res_off = (int64_t)m * p.ldr;
+        }
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            tmem_ld_wait();
+            if (!row_ok) continue;
+            const int nbase = n0 + c0;
+            if (nbase >= p.N) continue;
+            float* crow = p.C + row_off + nbase;
+            const float* rrow = p.residual ? p.residual + res_off + nbase : nullptr;
+            const bool vec_ok = (nbase + 32 <= p.N) && ((((uintptr_t)crow) & 15) == 0) &&
+                                (!rrow || (((uintptr_t)rrow) & 15) == 0);
+            if (vec_ok) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float4 o;
+                    float* of = reinterpret_cast<float*>(&o);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float x = __uint_as_float(v[j + e]) * p.alpha;
+                        if (p.bias) x += __ldg(p.bias + nbase + j + e);
+                        if (p.act == ACT_GELU) x = gelu_erf(x);
+                        else if (p.act == ACT_RELU) x = fmaxf(x, 0.0f);
+                        of[e] = x;
+                    }
+                    if (rrow) {
+                        const float4 rr = *reinterpret_cast<const float4*>(rrow + j);
+                        o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+                    }
+                    *reinterpret_cast<float4*>(crow + j) = o;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    if (nbase + j >= p.N) break;
+                    float x = __uint_as_float(v[j]) * p.alpha;
+                    if (p.bias) x += __ldg(p.bias + nbase + j);
+                    if (p.act == ACT_GELU) x = gelu_erf(x);
+                    else if (p.act == ACT_RELU) x = fmaxf(x, 0.0f);
+                    if (rrow) x += rrow[j];
+                    crow[j] = x;
+                }
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<C_::TMEM_COLS>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Host side: tensor-map construction (driver entry point resolved at run time: no link-time libcuda dependency)
+// ------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)ptr;
+    });
+    return fn;
+}
+
+int make_map(CUtensorMap* map, const float* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) { fprintf(stderr, "[siu3r_b200] cuTensorMapEncodeTiled unavailable\n"); return SIU3R_ERR_CUDA; }
+    cuuint64_t d[5]; cuuint64_t s[5]; cuuint32_t b[5]; cuuint32_t e[5];
+    for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; e[i] = 1; }
+    for (int i = 0; i + 1 < rank; ++i) s[i] = strides_bytes[i];
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, (void*)base, d, s, b, e, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        fprintf(stderr, "[siu3r_b200] cuTensorMapEncodeTiled failed: %d (rank %d dims %llu %llu box %u %u)\n", (int)r, rank,
+                (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
+        return SIU3R_ERR_INVALID;
+    }
+    return SIU3R_OK;
+}
+
+template <int BN, int NSPLIT>
+int launch(const CUtensorMap& a, const CUtensorMap& alo, const CUtensorMap& b, const CUtensorMap& blo, const GemmParams& p, dim3 grid,
+           cudaStream_t stream) {
+    using C_ = Cfg<BN, NSPLIT>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        SIU3R_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM_BYTES));
+        attr_set = true;
+    }
+    gemm_tc_kernel<BN, NSPLIT><<<grid, NUM_THREADS, C_::SMEM_BYTES, stream>>>(a, alo, b, blo, p);
+    SIU3R_LAUNCH_CHECK();
+    siu3r_note_launch(1);
+    return SIU3R_OK;
+}
+
+int pick_bn(int N, int64_t mtiles) {
+    if (N % 256 == 0 && mtiles * (N / 256) >= 120) return 256;
+    if (N > 64) return 128;
+    return 64;
+}
+
+}  // namespace
+
+extern "C" {
+
+// C[M,N] (ldc) = act(alpha * A[M,K] (lda) @ W[N,K]^T (ldw) + bias[N]) + residual[M,N] (ldr)
+// fp32 storage; precision 1 = TF32, 3 = 3xTF32 (needs the *_lo planes: x = hi + lo with hi = tf32-rounded x).
+// Requirements: K % 4 == 0 handled by zero-filled TMA only if lda/ldw are multiples of 4 floats and all bases 16-byte aligned.
+// act: 0 none, 1 GELU(erf), 2 ReLU.  Replaces torch.nn.functional.linear (+ fused bias/activation/residual).
+int siu3r_gemm_tc(int M, int N, int K, const float* A, const float* A_lo, int64_t lda, const float* Wt, const float* W_lo, int64_t ldw,
+                  float* C, int64_t ldc, const float* bias, const float* residual, int64_t ldr, int act, float alpha, int precision,
+                  void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    SIU3R_REQUIRE(M > 0 && N > 0 && K > 0 && A && Wt && C);
+    SIU3R_REQUIRE(precision == 1 || precision == 3);
+    SIU3R_REQUIRE(precision == 1 || (A_lo && W_lo));
+    SIU3R_REQUIRE(lda % 4 == 0 && ldw % 4 == 0 && lda >= K && ldw >= K);
+    SIU3R_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)Wt & 15) == 0);
+    const int64_t mtiles = ceil_div_i64(M, BM);
+    int bn = pick_bn(N, mtiles);
+    if (precision == 3 && bn == 256) bn = 128;
+    CUtensorMap ma, malo, mb, mblo;
+    {
+        uint64_t dims[2] = {(uint64_t)K, (uint64_t)M}; uint64_t str[1] = {(uint64_t)lda * 4}; uint32_t box[2] = {BK, BM};
+        int r = make_map(&ma, A, 2, dims, str, box); if (r) return r;
+        malo = ma;
+        if (precision == 3) { r = make_map(&malo, A_lo, 2, dims, str, box); if (r) return r; }
+    }
+    {
+        uint64_t dims[2] = {(uint64_t)K, (uint64_t)N}; uint64_t str[1] = {(uint64_t)ldw * 4}; uint32_t box[2] = {BK, (uint32_t)bn};
+        int r = make_map(&mb, Wt, 2, dims, str, box); if (r) return r;
+        mblo = mb;
+        if (precision == 3) { r = make_map(&mblo, W_lo, 2, dims, str, box); if (r) return r; }
+    }
+    GemmParams p{};
+    p.M = M; p.N = N; p.num_kb = ceil_div(K, BK); p.C = C; p.ldc = ldc; p.bias = bias; p.residual = residual; p.ldr = ldr;
+    p.act = act; p.alpha = alpha; p.conv = 0;
+    dim3 grid((unsigned)mtiles, (unsigned)ceil_div(N, bn));
+    if (precision == 1) {
+        if (bn == 256) return launch<256, 1>(ma, malo, mb, mblo, p, grid, stream);
+        if (bn == 128) return launch<128, 1>(ma, malo, mb, mblo, p, grid, stream);
+        return launch<64, 1>(ma, malo, mb, mblo, p, grid, stream);
+    }
+    if (bn == 128) return launch<128, 3>(ma, malo, mb, mblo, p, grid, stream);
+    return launch<64, 3>(ma, malo, mb, mblo, p, grid, stream);
+}
+
+// Stride-1 KHxKW convolution, NHWC fp32:  y[n,h,w,co] = act(sum x[n,h+kh-pad,w+kw-pad,ci] * Wt[co,kh,kw,ci] + bias) + residual
+// x [Nimg,H,W,Cin], Wt [Cout, KH*KW*Cin] (repacked from torch's [Cout,Cin,KH,KW]), y [Nimg,H,W,ldc>=Cout].
+// Requirements: Cin % 32 == 0, W % 16 == 0, H % 8 == 0.  Replaces nn.Conv2d(k, stride=1, padding=pad) on the DPT / FPN paths.
+int siu3r_conv2d_tc(int Nimg, int H, int W, int Cin, int Cout, int KH, int KW, int pad, const float* x, const float* x_lo,
+                    const float* Wt, const float* W_lo, float* y, int64_t ldc, const float* bias, const float* residual, int64_t ldr,
+                    int act, int precision, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    SIU3R_REQUIRE(Nimg > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && x && Wt && y);
+    SIU3R_REQUIRE(precision == 1 || precision == 3);
+    SIU3R_REQUIRE(precision == 1 || (x_lo && W_lo));
+    if (Cin % BK != 0 || W % CONV_TW != 0 || H % CONV_TH != 0) return SIU3R_ERR_UNSUPPORTED;
+    SIU3R_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)Wt & 15) == 0);
+    const int tiles_w = W / CONV_TW, tiles_h = H / CONV_TH;
+    const int64_t mtiles = (int64_t)Nimg * tiles_w * tiles_h;
+    int bn = pick_bn(Cout, mtiles);
+    if (precision == 3 && bn == 256) bn = 128;
+    const int Ktot = KH * KW * Cin;
+    CUtensorMap ma, malo, mb, mblo;
+    {
+        uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)Nimg};
+        uint64_t str[3] = {(uint64_t)Cin * 4, (uint64_t)W * Cin * 4, (uint64_t)H * W * Cin * 4};
+        uint32_t box[4] = {BK, CONV_TW, CONV_TH, 1};
+        int r = make_map(&ma, x, 4, dims, str, box); if (r) return r;
+        malo = ma;
+        if (precision == 3) { r = make_map(&malo, x_lo, 4, dims, str, box); if (r) return r; }
+    }
+    {
+        uint64_t dims[2] = {(uint64_t)Ktot, (uint64_t)Cout}; uint64_t str[1] = {(uint64_t)Ktot * 4}; uint32_t box[2] = {BK, (uint32_t)bn};
+        int r = make_map(&mb, Wt, 2, dims, str, box); if (r) return r;
+        mblo = mb;
+        if (precision == 3) { r = make_map(&mblo, W_lo, 2, dims, str, box); if (r) return r; }
+    }
+    GemmParams p{};
+    p.M = (int)(mtiles * BM); p.N = Cout; p.num_kb = KH * KW * (Cin / BK); p.C = y; p.ldc = ldc; p.bias = bias; p.residual = residual;
+    p.ldr = ldr; p.act = act; p.alpha = 1.0f; p.conv = 1; p.H = H; p.W = W; p.Cin = Cin; p.KH = KH; p.KW = KW; p.pad = pad;
+    p.tiles_w = tiles_w; p.tiles_h = tiles_h;
+    dim3 grid((unsigned)mtiles, (unsigned)ceil_div(Cout, bn));
+    if (precision == 1) {
+        if (bn == 256) return launch<256, 1>(ma, malo, mb, mblo, p, grid, stream);
+        if (bn == 128) return launch<128, 1>(ma, malo, mb, mblo, p, grid, stream);
+        return launch<64, 1>(ma, malo, mb, mblo, p, grid, stream);
+    }
+    if (bn == 128) return launch<128, 3>(ma, malo, mb, mblo, p, grid, stream);
+    return launch<64, 3>(ma, malo, mb, mblo, p, grid, stream);
+}
+
+}  // extern "C"

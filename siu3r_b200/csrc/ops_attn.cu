@@ -1,0 +1,412 @@
+// Attention kernels of the hot path.
+//  (1) flash attention, head dim 64, fp32 in/out, TF32 tensor-core math (mma.sync m16n8k8; register-level 3xTF32 split
+//      for the strict-parity mode).  Replaces the materialised softmax(QK^T * s)V of croco/blocks.py:105-109,162-166.
+//      (A tcgen05/TMEM version is the planned successor; this one already removes the N x N HBM round trip.)
+//  (2) small masked attention (head dim 32, ~100 queries) for the Mask2Former decoder:
+//      mask2former/video_seg_decoder.py:975-983 (nn.MultiheadAttention with boolean attn_mask, incl. the
+//      "fully masked row -> unmasked" rule of :1306-1308) and :994-999 (query self-attention).
+//  (3) multi-scale deformable attention sampling: vit_adapter/blocks.py:171-213,217-267 and
+//      mask2former/video_seg_decoder.py:1679-1720 (softmax over levels*points, bilinear zero-padded gathers).
+#include "common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------------------
+// (1) flash attention D = 64
+// ------------------------------------------------------------------------------------------------------------
+constexpr int FA_BM = 64;        // queries per CTA (4 warps x 16 rows)
+constexpr int FA_BN = 64;        // keys per tile
+constexpr int FA_D = 64;
+constexpr int FA_LD = FA_D + 4;  // padded smem row (floats): conflict-free fragment reads for both K and V patterns
+constexpr int FA_THREADS = 128;
+constexpr int FA_SMEM = 2 /*K,V*/ * 2 /*stages*/ * FA_BN * FA_LD * 4;
+
+__device__ __forceinline__ uint32_t f2tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+    const int sz = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int NSPLIT>
+__device__ __forceinline__ void split(float x, uint32_t& hi, uint32_t& lo) {
+    hi = f2tf32(x);
+    if (NSPLIT == 3) lo = f2tf32(x - __uint_as_float(hi));
+}
+
+template <int NSPLIT>
+__global__ void __launch_bounds__(FA_THREADS) flash_attn_d64_kernel(const float* __restrict__ Q, int64_t q_bs, int64_t q_ts,
+                                                                    const float* __restrict__ K, int64_t k_bs, int64_t k_ts,
+                                                                    const float* __restrict__ V, int64_t v_bs, int64_t v_ts,
+                                                                    float* __restrict__ O, int64_t o_bs, int64_t o_ts, int Nq, int Nk,
+                                                                    float scale) {
+    extern __shared__ __align__(16) float fa_smem[];
+    float* sK = fa_smem;                          // [2][FA_BN][FA_LD]
+    float* sV = fa_smem + 2 * FA_BN * FA_LD;      // [2][FA_BN][FA_LD]
+    const int b = blockIdx.z, h = blockIdx.y, qt = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const float* Qb = Q + (int64_t)b * q_bs + (int64_t)h * FA_D;
+    const float* Kb = K + (int64_t)b * k_bs + (int64_t)h * FA_D;
+    const float* Vb = V + (int64_t)b * v_bs + (int64_t)h * FA_D;
+    const int row0 = qt * FA_BM + warp * 16 + g, row1 = row0 + 8;
+
+    // Q fragments for the 8 k-steps over d (hi / lo planes)
+    uint32_t qh[8][4], ql[NSPLIT == 3 ? 8 : 1][4];
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+        const float a0 = row0 < Nq ? Qb[(int64_t)row0 * q_ts + ks * 8 + t] : 0.f;
+        const float a1 = row1 < Nq ? Qb[(int64_t)row1 * q_ts + ks * 8 + t] : 0.f;
+        const float a2 = row0 < Nq ? Qb[(int64_t)row0 * q_ts + ks * 8 + t + 4] : 0.f;
+        const float a3 = row1 < Nq ? Qb[(int64_t)row1 * q_ts + ks * 8 + t + 4] : 0.f;
+        uint32_t l0 = 0, l1 = 0, l2 = 0, l3 = 0;
+        split<NSPLIT>(a0, qh[ks][0], l0); split<NSPLIT>(a1, qh[ks][1], l1);
+        split<NSPLIT>(a2, qh[ks][2], l2); split<NSPLIT>(a3, qh[ks][3], l3);
+        if constexpr (NSPLIT == 3) { ql[ks][0] = l0; ql[ks][1] = l1; ql[ks][2] = l2; ql[ks][3] = l3; }
+    }
+
+    float o_acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { o_acc[i][0] = o_acc[i][1] = o_acc[i][2] = o_acc[i][3] = 0.f; }
+    float m0 = -INFINITY, m1 = -INFINITY, l0s = 0.f, l1s = 0.f;
+
+    const int ntiles = (Nk + FA_BN - 1) / FA_BN;
+    auto load_tile = [&](int kt, int buf) {
+        float* dk = sK + buf * FA_BN * FA_LD;
+        float* dv = sV + buf * FA_BN * FA_LD;
+#pragma unroll
+        for (int i = 0; i < (FA_BN * FA_D / 4) / FA_THREADS; ++i) {
+            const int c = threadIdx.x + i * FA_THREADS;
+            const int r = c >> 4, cc = (c & 15) * 4;
+            const int key = kt * FA_BN + r;
+            const bool ok = key < Nk;
+            const int64_t kk = ok ? key : 0;
+            cp_async16(dk + r * FA_LD + cc, Kb + kk * k_ts + cc, ok);
+            cp_async16(dv + r * FA_LD + cc, Vb + kk * v_ts + cc, ok);
+        }
+        cp_async_commit();
+    };
+    load_tile(0, 0);
+
+    for (int kt = 0; kt < ntiles; ++kt) {
+        const int buf = kt & 1;
+        if (kt + 1 < ntiles) { load_tile(kt + 1, buf ^ 1); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
+        __syncthreads();
+        const float* tk = sK + buf * FA_BN * FA_LD;
+        const float* tv = sV + buf * FA_BN * FA_LD;
+
+        // ---- S = Q K^T (16 x 64 per warp) ----
+        float s[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                const float k0 = tk[(nt * 8 + g) * FA_LD + ks * 8 + t];
+                const float k1 = tk[(nt * 8 + g) * FA_LD + ks * 8 + t + 4];
+                uint32_t b0h, b0l = 0, b1h, b1l = 0;
+                split<NSPLIT>(k0, b0h, b0l); split<NSPLIT>(k1, b1h, b1l);
+                if constexpr (NSPLIT == 3) {
+                    mma_tf32(s[nt], ql[ks], b0h, b1h);
+                    mma_tf32(s[nt], qh[ks], b0l, b1l);
+                }
+                mma_tf32(s[nt], qh[ks], b0h, b1h);
+            }
+        }
+        // ---- scale, mask the key tail, online softmax ----
+        const int kbase = kt * FA_BN;
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            const int c = kbase + nt * 8 + 2 * t;
+            s[nt][0] = c < Nk ? s[nt][0] * scale : -INFINITY;
+            s[nt][1] = c + 1 < Nk ? s[nt][1] * scale : -INFINITY;
+            s[nt][2] = c < Nk ? s[nt][2] * scale : -INFINITY;
+            s[nt][3] = c + 1 < Nk ? s[nt][3] * scale : -INFINITY;
+            mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+            mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+        const float corr0 = NSPLIT == 3 ? expf(m0 - mn0) : __expf(m0 - mn0);
+        const float corr1 = NSPLIT == 3 ? expf(m1 - mn1) : __expf(m1 - mn1);
+        float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            if (NSPLIT == 3) {
+                s[nt][0] = expf(s[nt][0] - mn0); s[nt][1] = expf(s[nt][1] - mn0);
+                s[nt][2] = expf(s[nt][2] - mn1); s[nt][3] = expf(s[nt][3] - mn1);
+            } else {
+                s[nt][0] = __expf(s[nt][0] - mn0); s[nt][1] = __expf(s[nt][1] - mn0);
+                s[nt][2] = __expf(s[nt][2] - mn1); s[nt][3] = __expf(s[nt][3] - mn1);
+            }
+            rs0 += s[nt][0] + s[nt][1];
+            rs1 += s[nt][2] + s[nt][3];
+        }
+        rs0 += __shfl_xor_sync(0xffffffffu, rs0, 1); rs0 += __shfl_xor_sync(0xffffffffu, rs0, 2);
+        rs1 += __shfl_xor_sync(0xffffffffu, rs1, 1); rs1 += __shfl_xor_sync(0xffffffffu, rs1, 2);
+        l0s = l0s * corr0 + rs0; l1s = l1s * corr1 + rs1;
+        m0 = mn0; m1 = mn1;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { o_acc[i][0] *= corr0; o_acc[i][1] *= corr0; o_acc[i][2] *= corr1; o_acc[i][3] *= corr1; }
+
+        // ---- O += P V.  The C-fragment of S is reused as the A-fragment of P by permuting the k index:
+        //      k-slot t <-> key 2t, k-slot t+4 <-> key 2t+1 of each 8-key group (V rows are read in the same order). ----
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+            uint32_t ph[4], pl[4] = {0, 0, 0, 0};
+            split<NSPLIT>(s[kk][0], ph[0], pl[0]);  // (row g,   key 2t)
+            split<NSPLIT>(s[kk][2], ph[1], pl[1]);  // (row g+8, key 2t)
+            split<NSPLIT>(s[kk][1], ph[2], pl[2]);  // (row g,   key 2t+1)
+            split<NSPLIT>(s[kk][3], ph[3], pl[3]);  // (row g+8, key 2t+1)
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                const float v0 = tv[(kk * 8 + 2 * t) * FA_LD + nt * 8 + g];
+                const float v1 = tv[(kk * 8 + 2 * t + 1) * FA_LD + nt * 8 + g];
+                uint32_t b0h, b0l = 0, b1h, b1l = 0;
+                split<NSPLIT>(v0, b0h, b0l); split<NSPLIT>(v1, b1h, b1l);
+                if constexpr (NSPLIT == 3) {
+                    mma_tf32(o_acc[nt], pl, b0h, b1h);
+                    mma_tf32(o_acc[nt], ph, b0l, b1l);
+                }
+                mma_tf32(o_acc[nt], ph, b0h, b1h);
+            }
+        }
+        __syncthreads();  // tile `buf` is overwritten by the prefetch issued in the next iteration
+    }
+    const float inv0 = 1.f / l0s, inv1 = 1.f / l1s;
+    float* Ob = O + (int64_t)b * o_bs + (int64_t)h * FA_D;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+        const int c = nt * 8 + 2 * t;
+        if (row0 < Nq) *reinterpret_cast<float2*>(Ob + (int64_t)row0 * o_ts + c) = make_float2(o_acc[nt][0] * inv0, o_acc[nt][1] * inv0);
+        if (row1 < Nq) *reinterpret_cast<float2*>(Ob + (int64_t)row1 * o_ts + c) = make_float2(o_acc[nt][2] * inv1, o_acc[nt][3] * inv1);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// (2) small attention, head dim 32: one warp per (batch, head, query); each lane owns a strided subset of the keys
+//     with a private online softmax that is merged across lanes at the end.  Exact fp32.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) attn_small_d32_kernel(const float* __restrict__ Q, int64_t q_bs, int64_t q_ts,
+                                                            const float* __restrict__ K, int64_t k_bs, int64_t k_ts,
+                                                            const float* __restrict__ V, int64_t v_bs, int64_t v_ts,
+                                                            float* __restrict__ O, int64_t o_bs, int64_t o_ts,
+                                                            const uint8_t* __restrict__ mask /*[B,Nq,Nk] 1 = masked*/, int B, int H, int Nq,
+                                                            int Nk, float scale) {
+    const int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (wid >= B * H * Nq) return;
+    const int q = wid % Nq;
+    const int h = (wid / Nq) % H;
+    const int b = wid / (Nq * H);
+    const float* qp = Q + (int64_t)b * q_bs + (int64_t)q * q_ts + h * 32;
+    float qr[32];
+#pragma unroll
+    for (int d = 0; d < 32; d += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(qp + d);
+        qr[d] = v.x; qr[d + 1] = v.y; qr[d + 2] = v.z; qr[d + 3] = v.w;
+    }
+    const float* Kb = K + (int64_t)b * k_bs + h * 32;
+    const float* Vb = V + (int64_t)b * v_bs + h * 32;
+    const uint8_t* mrow = mask ? mask + ((int64_t)b * Nq + q) * Nk : nullptr;
+
+    float m = -INFINITY, l = 0.f, acc[32];
+    for (int pass = 0; pass < 2; ++pass) {
+        const bool use_mask = (pass == 0) && (mrow != nullptr);
+        m = -INFINITY; l = 0.f;
+#pragma unroll
+        for (int d = 0; d < 32; ++d) acc[d] = 0.f;
+        bool any = false;
+        for (int key = lane; key < Nk; key += 32) {
+            if (use_mask && mrow[key]) continue;
+            any = true;
+            const float* kp = Kb + (int64_t)key * k_ts;
+            float dot = 0.f;
+#pragma unroll
+            for (int d = 0; d < 32; d += 4) {
+                const float4 kv = *reinterpret_cast<const float4*>(kp + d);
+                dot += qr[d] * kv.x + qr[d + 1] * kv.y + qr[d + 2] * kv.z + qr[d + 3] * kv.w;
+            }
+            dot *= scale;
+            const float mn = fmaxf(m, dot);
+            const float corr = expf(m - mn), p = expf(dot - mn);
+            l = l * corr + p;
+            const float* vp = Vb + (int64_t)key * v_ts;
+#pragma unroll
+            for (int d = 0; d < 32; d += 4) {
+                const float4 vv = *reinterpret_cast<const float4*>(vp + d);
+                acc[d] = acc[d] * corr + p * vv.x; acc[d + 1] = acc[d + 1] * corr + p * vv.y;
+                acc[d + 2] = acc[d + 2] * corr + p * vv.z; acc[d + 3] = acc[d + 3] * corr + p * vv.w;
+            }
+            m = mn;
+        }
+        if (!use_mask || __any_sync(0xffffffffu, any)) break;  // fully masked row: redo without the mask
+    }
+    const float mall = warp_max(m);
+    const float f = (m == -INFINITY) ? 0.f : expf(m - mall);
+    l = warp_sum(l * f);
+    float outv = 0.f;
+#pragma unroll
+    for (int d = 0; d < 32; ++d) {
+        const float v = warp_sum(acc[d] * f);
+        if (lane == d) outv = v;
+    }
+    O[(int64_t)b * o_bs + (int64_t)q * o_ts + h * 32 + lane] = outv / l;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// (3) multi-scale deformable attention sampling.  One warp per (batch, query, head); lanes span the head channels.
+//     ow: [B*Lq, ldow] rows hold [offsets (nH*L*P*2) | attention logits (nH*L*P)] as produced by one fused GEMM.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int MSDA_MAX_LP = 16;
+struct MsdaLevels { int H[4]; int W[4]; int start[4]; };
+
+template <int CPL /*channels per lane*/>
+__global__ void __launch_bounds__(256) msdeform_kernel(const float* __restrict__ value, int64_t ldv, int Lin, const float* __restrict__ ow,
+                                                      int64_t ldow, const float* __restrict__ ref /*[Lq,2] (x,y)*/, MsdaLevels lv, int B, int Lq,
+                                                      int nH, int L, int P, float* __restrict__ out, int64_t ldo) {
+    const int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (wid >= B * Lq * nH) return;
+    const int h = wid % nH;
+    const int q = (wid / nH) % Lq;
+    const int b = wid / (nH * Lq);
+    const int hd = CPL * 32;
+    const int LP = L * P;
+    const float* row = ow + ((int64_t)b * Lq + q) * ldow;
+    const float* offs = row + (int64_t)h * LP * 2;
+    const float* logit = row + (int64_t)nH * LP * 2 + (int64_t)h * LP;
+    float wgt[MSDA_MAX_LP];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < MSDA_MAX_LP; ++i) if (i < LP) { wgt[i] = logit[i]; mx = fmaxf(mx, wgt[i]); }
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < MSDA_MAX_LP; ++i) if (i < LP) { wgt[i] = expf(wgt[i] - mx); sum += wgt[i]; }
+    const float inv = 1.f / sum;
+    const float rx = ref[2 * q], ry = ref[2 * q + 1];
+    float acc[CPL];
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) acc[c] = 0.f;
+    const float* vb = value + (int64_t)b * Lin * ldv + h * hd + lane * CPL;
+#pragma unroll
+    for (int i = 0; i < MSDA_MAX_LP; ++i) {
+        if (i >= LP) break;
+        const int l = i / P;
+        const int Hl = lv.H[l], Wl = lv.W[l];
+        const float locx = rx + offs[2 * i] / (float)Wl, locy = ry + offs[2 * i + 1] / (float)Hl;
+        const float gx = 2.f * locx - 1.f, gy = 2.f * locy - 1.f;
+        const float px = ((gx + 1.f) * (float)Wl - 1.f) * 0.5f, py = ((gy + 1.f) * (float)Hl - 1.f) * 0.5f;
+        const float fx = floorf(px), fy = floorf(py);
+        const int x0 = (int)fx, y0 = (int)fy;
+        const float ax = px - fx, ay = py - fy;
+        const float w = wgt[i] * inv;
+        const float* vl = vb + (int64_t)lv.start[l] * ldv;
+#pragma unroll
+        for (int cy = 0; cy < 2; ++cy) {
+            const int yy = y0 + cy;
+            if (yy < 0 || yy >= Hl) continue;
+            const float wy = cy ? ay : 1.f - ay;
+#pragma unroll
+            for (int cx = 0; cx < 2; ++cx) {
+                const int xx = x0 + cx;
+                if (xx < 0 || xx >= Wl) continue;
+                const float wx = cx ? ax : 1.f - ax;
+                const float* p = vl + ((int64_t)yy * Wl + xx) * ldv;
+                const float ww = w * wx * wy;
+                if (CPL == 2) {
+                    const float2 v2 = *reinterpret_cast<const float2*>(p);
+                    acc[0] += ww * v2.x; acc[CPL - 1] += ww * v2.y;
+                } else {
+                    acc[0] += ww * p[0];
+                }
+            }
+        }
+    }
+    float* op = out + ((int64_t)b * Lq + q) * ldo + h * hd + lane * CPL;
+    if (CPL == 2) *reinterpret_cast<float2*>(op) = make_float2(acc[0], acc[CPL - 1]);
+    else op[0] = acc[0];
+}
+
+}  // namespace
+
+extern "C" {
+
+// out[b, n, h*64 + d] = softmax(Q K^T * scale) V per (batch, head).  Element (b, n, h, d) of X lives at
+// X + b*x_bs + n*x_ts + h*64 + d (so q/k/v can point into a fused qkv buffer).  precision: 1 = TF32, 3 = 3xTF32.
+int siu3r_flash_attn_d64(const float* Q, int64_t q_bs, int64_t q_ts, const float* K, int64_t k_bs, int64_t k_ts, const float* V,
+                         int64_t v_bs, int64_t v_ts, float* O, int64_t o_bs, int64_t o_ts, int B, int H, int Nq, int Nk, float scale,
+                         int precision, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    SIU3R_REQUIRE(Q && K && V && O && B > 0 && H > 0 && Nq > 0 && Nk > 0);
+    SIU3R_REQUIRE(precision == 1 || precision == 3);
+    SIU3R_REQUIRE(k_ts % 4 == 0 && v_ts % 4 == 0 && k_bs % 4 == 0 && v_bs % 4 == 0 && o_ts % 2 == 0 && o_bs % 2 == 0);
+    SIU3R_REQUIRE(((uintptr_t)K & 15) == 0 && ((uintptr_t)V & 15) == 0 && ((uintptr_t)O & 7) == 0);
+    static bool attr = false;
+    if (!attr) {
+        SIU3R_CUDA_CHECK(cudaFuncSetAttribute(flash_attn_d64_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+        SIU3R_CUDA_CHECK(cudaFuncSetAttribute(flash_attn_d64_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+        attr = true;
+    }
+    dim3 grid(ceil_div(Nq, FA_BM), H, B);
+    if (precision == 1)
+        flash_attn_d64_kernel<1><<<grid, FA_THREADS, FA_SMEM, stream>>>(Q, q_bs, q_ts, K, k_bs, k_ts, V, v_bs, v_ts, O, o_bs, o_ts, Nq, Nk, scale);
+    else
+        flash_attn_d64_kernel<3><<<grid, FA_THREADS, FA_SMEM, stream>>>(Q, q_bs, q_ts, K, k_bs, k_ts, V, v_bs, v_ts, O, o_bs, o_ts, Nq, Nk, scale);
+    SIU3R_LAUNCH_CHECK();
+    siu3r_note_launch(1);
+    return SIU3R_OK;
+}
+
+// Head dim 32; mask (optional) uint8 [B, Nq, Nk], non-zero = key not attended; rows that are fully masked attend everywhere.
+int siu3r_attn_small_d32(const float* Q, int64_t q_bs, int64_t q_ts, const float* K, int64_t k_bs, int64_t k_ts, const float* V, int64_t v_bs,
+                         int64_t v_ts, float* O, int64_t o_bs, int64_t o_ts, const uint8_t* mask, int B, int H, int Nq, int Nk, float scale,
+                         void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    SIU3R_REQUIRE(Q && K && V && O && B > 0 && H > 0 && Nq > 0 && Nk > 0);
+    SIU3R_REQUIRE(q_ts % 4 == 0 && k_ts % 4 == 0 && v_ts % 4 == 0 && q_bs % 4 == 0 && k_bs % 4 == 0 && v_bs % 4 == 0);
+    const int warps = B * H * Nq;
+    attn_small_d32_kernel<<<ceil_div(warps, 4), 128, 0, stream>>>(Q, q_bs, q_ts, K, k_bs, k_ts, V, v_bs, v_ts, O, o_bs, o_ts, mask, B, H, Nq, Nk,
+                                                                 scale);
+    SIU3R_LAUNCH_CHECK();
+    siu3r_note_launch(1);
+    return SIU3R_OK;
+}
+
+// value [B, Lin, nH*hd] (ldv), ow [B*Lq, ldow] = [sampling offsets | attention logits], ref [Lq, 2] normalised (x, y),
+// levels: level_hw [L][2] = (H_l, W_l) (host ints); out [B*Lq, ldo].  hd in {32, 64}; L*P <= 16.
+int siu3r_msdeform_attn(const float* value, int64_t ldv, int Lin, const float* ow, int64_t ldow, const float* ref, const int* level_hw, int L,
+                        int P, int B, int Lq, int nH, int hd, float* out, int64_t ldo, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    SIU3R_REQUIRE(value && ow && ref && level_hw && out && L >= 1 && L <= 4 && P >= 1 && L * P <= MSDA_MAX_LP);
+    SIU3R_REQUIRE(hd == 32 || hd == 64);
+    MsdaLevels lv{};
+    int start = 0;
+    for (int l = 0; l < L; ++l) { lv.H[l] = level_hw[2 * l]; lv.W[l] = level_hw[2 * l + 1]; lv.start[l] = start; start += lv.H[l] * lv.W[l]; }
+    SIU3R_REQUIRE(start == Lin);
+    const int warps = B * Lq * nH;
+    if (hd == 64)
+        msdeform_kernel<2><<<ceil_div(warps, 8), 256, 0, stream>>>(value, ldv, Lin, ow, ldow, ref, lv, B, Lq, nH, L, P, out, ldo);
+    else
+        msdeform_kernel<1><<<ceil_div(warps, 8), 256, 0, stream>>>(value, ldv, Lin, ow, ldow, ref, lv, B, Lq, nH, L, P, out, ldo);
+    SIU3R_LAUNCH_CHECK();
+    siu3r_note_launch(1);
+    return SIU3R_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,304 @@
+// Output-side kernels of the hot path: depth post-process, Gaussian adapter, panoptic post-process, reference fp32 GEMM.
+#include "common.cuh"
+
+namespace {
+
+// pts = xyz / max(||xyz||, 1e-8) * expm1(||xyz||)     (heads/postprocess.py:46-61, mode "exp", no bounds)
+__global__ void __launch_bounds__(256) depth_exp_kernel(const float* __restrict__ xyz, int64_t ldx, float* __restrict__ pts, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float x = xyz[i * ldx], y = xyz[i * ldx + 1], z = xyz[i * ldx + 2];
+    const float d = sqrtf(x * x + y * y + z * z);
+    const float dc = fmaxf(d, 1e-8f);
+    const float e = expm1f(d);
+    pts[i * 3] = x / dc * e;
+    pts[i * 3 + 1] = y / dc * e;
+    pts[i * 3 + 2] = z / dc * e;
+}
+
+// UnifiedGaussianAdapter.forward (gaussian_adapter.py:81-110): raw [G, 83] = (opacity 1, scales 3, rot 4 xyzw, sh 3x25)
+// The CTA's raw block (128 x 83 floats, contiguous) is staged through shared memory so every HBM access is coalesced.
+constexpr int GA_THREADS = 128;
+constexpr int GA_RAW = 83;
+constexpr int GA_DSH = 25;
+
+__global__ void __launch_bounds__(GA_THREADS) gaussian_adapter_kernel(const float* __restrict__ raw, int64_t G, float* __restrict__ cov,
+                                                                      float* __restrict__ harm, float* __restrict__ opac,
+                                                                      float* __restrict__ scales, float* __restrict__ rots) {
+    __shared__ float s_raw[GA_THREADS * GA_RAW];
+    const int64_t base = (int64_t)blockIdx.x * GA_THREADS;
+    const int nvalid = (int)min((int64_t)GA_THREADS, G - base);
+    const int total = nvalid * GA_RAW;
+    const float* src = raw + base * GA_RAW;
+    for (int i = threadIdx.x; i < total; i += GA_THREADS) s_raw[i] = src[i];
+    __syncthreads();
+    // harmonics [G,3,25] = sh * mask(degree): flat, coalesced
+    float* hdst = harm + base * 75;
+    for (int i = threadIdx.x; i < nvalid * 75; i += GA_THREADS) {
+        const int gq = i / 75, j = i % 75;
+        const int k = j % GA_DSH;
+        float mk = 1.0f;
+        if (k >= 16) mk = 0.1f * 0.00390625f;       // 0.1 * 0.25^4
+        else if (k >= 9) mk = 0.1f * 0.015625f;     // 0.1 * 0.25^3
+        else if (k >= 4) mk = 0.1f * 0.0625f;       // 0.1 * 0.25^2
+        else if (k >= 1) mk = 0.1f * 0.25f;         // 0.1 * 0.25
+        hdst[i] = s_raw[gq * GA_RAW + 8 + j] * mk;
+    }
+    if (threadIdx.x >= nvalid) return;
+    const float* r = s_raw + threadIdx.x * GA_RAW;
+    const int64_t gi = base + threadIdx.x;
+    opac[gi] = 1.0f / (1.0f + expf(-r[0]));
+    float sc[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float x = r[1 + k];
+        const float sp = x > 20.f ? x : log1pf(expf(x));  // F.softplus (beta 1, threshold 20)
+        sc[k] = fminf(0.001f * sp, 0.3f);
+        scales[gi * 3 + k] = sc[k];
+    }
+    const float q0 = r[4], q1 = r[5], q2 = r[6], q3 = r[7];
+    rots[gi * 4 + 0] = q0; rots[gi * 4 + 1] = q1; rots[gi * 4 + 2] = q2; rots[gi * 4 + 3] = q3;  // returned raw (:109)
+    const float nrm = sqrtf(q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3) + 1e-8f;
+    const float i = q0 / nrm, j = q1 / nrm, k = q2 / nrm, w = q3 / nrm;  // xyzw
+    const float two_s = 2.0f / ((i * i + j * j + k * k + w * w) + 1e-8f);
+    float R[3][3];
+    R[0][0] = 1.f - two_s * (j * j + k * k); R[0][1] = two_s * (i * j - k * w); R[0][2] = two_s * (i * k + j * w);
+    R[1][0] = two_s * (i * j + k * w); R[1][1] = 1.f - two_s * (i * i + k * k); R[1][2] = two_s * (j * k - i * w);
+    R[2][0] = two_s * (i * k - j * w); R[2][1] = two_s * (j * k + i * w); R[2][2] = 1.f - two_s * (i * i + j * j);
+    // cov = R S S^T R^T
+    float RS[3][3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) RS[a][b] = R[a][b] * sc[b];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+            // ((R S) S^T) R^T evaluated left to right like the reference's chained matmul
+            float acc = 0.f;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) acc += (RS[a][c] * sc[c]) * R[b][c];
+            cov[gi * 9 + a * 3 + b] = acc;
+        }
+}
+
+// ---- panoptic post-process helpers (image_processing_video_mask2former.py:1238-1481) ----
+// y[n,oh,ow,j] = bilinear(x[n,:,:,idx[j]]) (align_corners False): resize of the kept queries' mask probabilities (:1386-1391)
+__global__ void __launch_bounds__(256) resize_select_kernel(const float* __restrict__ x, int N, int H, int W, int C, const int* __restrict__ idx,
+                                                            int nsel, float* __restrict__ y, int OH, int OW, float sh, float sw) {
+    const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t0 >= (int64_t)N * OH * OW * nsel) return;
+    const int j = (int)(t0 % nsel);
+    int64_t t = t0 / nsel;
+    const int ow = (int)(t % OW); t /= OW;
+    const int oh = (int)(t % OH);
+    const int n = (int)(t / OH);
+    float srch = sh * ((float)oh + 0.5f) - 0.5f; if (srch < 0.f) srch = 0.f;
+    float srcw = sw * ((float)ow + 0.5f) - 0.5f; if (srcw < 0.f) srcw = 0.f;
+    int h0 = min((int)srch, H - 1), w0 = min((int)srcw, W - 1);
+    const int h1 = h0 + (h0 < H - 1 ? 1 : 0), w1 = w0 + (w0 < W - 1 ? 1 : 0);
+    const float lh = srch - (float)h0, lw = srcw - (float)w0;
+    const int c = idx[j];
+    const float* b = x + (int64_t)n * H * W * C + c;
+    const float v00 = b[((int64_t)h0 * W + w0) * C], v01 = b[((int64_t)h0 * W + w1) * C];
+    const float v10 = b[((int64_t)h1 * W + w0) * C], v11 = b[((int64_t)h1 * W + w1) * C];
+    y[t0] = (1.f - lh) * ((1.f - lw) * v00 + lw * v01) + lh * ((1.f - lw) * v10 + lw * v11);
+}
+
+// per pixel: k* = argmax_k probs[p,k]*score[k] (first max wins); area[k*]++ ; orig[k] += (probs[p,k]*score[k] >= thr)
+__global__ void __launch_bounds__(256) argmax_area_kernel(const float* __restrict__ probs, int64_t npix, int nq, const float* __restrict__ score,
+                                                          float thr, int32_t* __restrict__ labels, int32_t* __restrict__ area,
+                                                          int32_t* __restrict__ orig) {
+    extern __shared__ int32_t s_cnt[];  // [2*nq]
+    for (int i = threadIdx.x; i < 2 * nq; i += blockDim.x) s_cnt[i] = 0;
+    __syncthreads();
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < npix) {
+        const float* r = probs + p * nq;
+        float best = -INFINITY; int bk = 0;
+        for (int k = 0; k < nq; ++k) {
+            const float v = r[k] * score[k];
+            if (v > best) { best = v; bk = k; }
+            if (v >= thr) atomicAdd(&s_cnt[nq + k], 1);
+        }
+        labels[p] = bk;
+        atomicAdd(&s_cnt[bk], 1);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nq; i += blockDim.x) {
+        if (s_cnt[i]) atomicAdd(&area[i], s_cnt[i]);
+        if (s_cnt[nq + i]) atomicAdd(&orig[i], s_cnt[nq + i]);
+    }
+}
+
+// segmentation / semantic / instance maps from the per-pixel argmax and the host-decided per-query LUTs
+__global__ void __launch_bounds__(256) label_lut_kernel(const int32_t* __restrict__ labels, int64_t npix, const int32_t* __restrict__ seg_lut,
+                                                        const int32_t* __restrict__ sem_lut, int32_t* __restrict__ seg, int32_t* __restrict__ sem,
+                                                        int32_t* __restrict__ inst) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npix) return;
+    const int k = labels[p];
+    const int s = seg_lut[k];
+    seg[p] = s;
+    sem[p] = sem_lut[k];
+    inst[p] = s;
+}
+
+// out[p, j, c] = probs[p, keep[j]] * class_probs[j, c]      (:1463-1467 + model.py:261-263 "(n h w) q c")
+__global__ void __launch_bounds__(256) qc_logits_kernel(const float* __restrict__ probs, int64_t npix, int nq, const int* __restrict__ keep, int nk,
+                                                        const float* __restrict__ cls /*[nk, ncls]*/, int ncls, float* __restrict__ out) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int per = nk * ncls;
+    if (t >= npix * per) return;
+    const int64_t p = t / per;
+    const int jc = (int)(t % per);
+    const int j = jc / ncls;
+    out[t] = probs[p * nq + keep[j]] * cls[jc];
+}
+
+// mask -> boolean attention mask: m[b, q, t*h*w] = sigmoid(bilinear(mask_logits[b,t,:,:,q] -> (h,w))) < 0.5
+// (mask2former/video_seg_decoder.py:1461-1478; logits stored pixel-major [B*T, Hm, Wm, Q])
+__global__ void __launch_bounds__(256) attn_mask_kernel(const float* __restrict__ logits, int BT, int T, int Hm, int Wm, int Q, int oh_, int ow_,
+                                                        float sh, float sw, uint8_t* __restrict__ mask) {
+    const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t0 >= (int64_t)BT * oh_ * ow_ * Q) return;
+    const int q = (int)(t0 % Q);
+    int64_t t = t0 / Q;
+    const int ow = (int)(t % ow_); t /= ow_;
+    const int oh = (int)(t % oh_);
+    const int bt = (int)(t / oh_);
+    float srch = sh * ((float)oh + 0.5f) - 0.5f; if (srch < 0.f) srch = 0.f;
+    float srcw = sw * ((float)ow + 0.5f) - 0.5f; if (srcw < 0.f) srcw = 0.f;
+    const int h0 = min((int)srch, Hm - 1), w0 = min((int)srcw, Wm - 1);
+    const int h1 = h0 + (h0 < Hm - 1 ? 1 : 0), w1 = w0 + (w0 < Wm - 1 ? 1 : 0);
+    const float lh = srch - (float)h0, lw = srcw - (float)w0;
+    const float* b = logits + (int64_t)bt * Hm * Wm * Q + q;
+    const float v00 = b[((int64_t)h0 * Wm + w0) * Q], v01 = b[((int64_t)h0 * Wm + w1) * Q];
+    const float v10 = b[((int64_t)h1 * Wm + w0) * Q], v11 = b[((int64_t)h1 * Wm + w1) * Q];
+    const float v = (1.f - lh) * ((1.f - lw) * v00 + lw * v01) + lh * ((1.f - lw) * v10 + lw * v11);
+    const float sg = 1.0f / (1.0f + expf(-v));
+    const int bidx = bt / T, tt = bt % T;
+    mask[(((int64_t)bidx * Q + q) * T + tt) * oh_ * ow_ + (int64_t)oh * ow_ + ow] = sg < 0.5f ? 1 : 0;
+}
+
+// Plain fp32 (FFMA) GEMM: C = act(alpha * A W^T + bias) + residual.  Shape-agnostic fallback for tiny / odd shapes
+// (K = 9 intrinsics encoder, backbone_croco.py:59) and the on-device cross-check of the tensor-core path.
+constexpr int SG_T = 16;
+__global__ void __launch_bounds__(SG_T* SG_T) gemm_simt_kernel(int M, int N, int K, const float* __restrict__ A, int64_t lda,
+                                                              const float* __restrict__ W, int64_t ldw, float* __restrict__ C, int64_t ldc,
+                                                              const float* __restrict__ bias, const float* __restrict__ res, int64_t ldr, int act,
+                                                              float alpha) {
+    __shared__ float sA[SG_T][SG_T + 1], sW[SG_T][SG_T + 1];
+    const int tx = threadIdx.x % SG_T, ty = threadIdx.x / SG_T;
+    const int m = blockIdx.y * SG_T + ty, n = blockIdx.x * SG_T + tx;
+    float acc = 0.f;
+    for (int k0 = 0; k0 < K; k0 += SG_T) {
+        const int ka = k0 + tx;
+        sA[ty][tx] = (m < M && ka < K) ? A[(int64_t)m * lda + ka] : 0.f;
+        const int nw = blockIdx.x * SG_T + ty;
+        sW[ty][tx] = (nw < N && ka < K) ? W[(int64_t)nw * ldw + ka] : 0.f;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < SG_T; ++k) acc = fmaf(sA[ty][k], sW[tx][k], acc);
+        __syncthreads();
+    }
+    if (m < M && n < N) {
+        float x = acc * alpha;
+        if (bias) x += bias[n];
+        if (act == 1) x = 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+        else if (act == 2) x = fmaxf(x, 0.f);
+        if (res) x += res[(int64_t)m * ldr + n];
+        C[(int64_t)m * ldc + n] = x;
+    }
+}
+
+inline unsigned grid_for(int64_t n, int threads = 256) { return (unsigned)((n + threads - 1) / threads); }
+
+}  // namespace
+
+extern "C" {
+
+int siu3r_depth_exp(const float* xyz, int64_t ldx, float* pts, int64_t n, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    SIU3R_REQUIRE(xyz && pts && n > 0 && ldx >= 3);
+    depth_exp_kernel<<<grid_for(n), 256, 0, stream>>>(xyz, ldx, pts, n);
+    SIU3R_LAUNCH_CHECK();
+    siu3r_note_launch(1);
+    return SIU3R_OK;
+}
+
+// raw [G,83] -> covariances [G,3,3], harmonics [G,3,25], opacities [G], scales [G,3], rotations [G,4] (raw quaternion)
+int siu3r_gaussian_adapter(const float* raw, int64_t G, float* covariances, float* harmonics, float* opacities, float* scales,
+                           float* rotations, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    SIU3R_REQUIRE(raw && covariances && harmonics && opacities && scales && rotations && G > 0);
+    gaussian_adapter_kernel<<<grid_for(G, GA_THREADS), GA_THREADS, 0, stream>>>(raw, G, covariances, harmonics, opacities, scales, rotations);
+    SIU3R_LAUNCH_CHECK();
+    siu3r_note_launch(1);
+    return SIU3R_OK;
+}
+
+int siu3r_resize_select(const float* x, int N, int H, int W, int C, const int* idx, int nsel, float* y, int OH, int OW, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    SIU3R_REQUIRE(x && idx && y && nsel > 0);
+    resize_select_kernel<<<grid_for((int64_t)N * OH * OW * nsel), 256, 0, stream>>>(x, N, H, W, C, idx, nsel, y, OH, OW, (float)H / (float)OH,
+                                                                                   (float)W / (float)OW);
+    SIU3R_LAUNCH_CHECK();
+    siu3r_note_launch(1);
+    return SIU3R_OK;
+}
+
+int siu3r_argmax_area(const float* probs, int64_t npix, int nq, const float* score, float thr, int32_t* labels, int32_t* area, int32_t* orig,
+                      void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    SIU3R_REQUIRE(probs && score && labels && area && orig && nq > 0 && nq <= 1024);
+    SIU3R_CUDA_CHECK(cudaMemsetAsync(area, 0, sizeof(int32_t) * nq, stream));
+    SIU3R_CUDA_CHECK(cudaMemsetAsync(orig, 0, sizeof(int32_t) * nq, stream));
+    argmax_area_kernel<<<grid_for(npix), 256, 2 * nq * sizeof(int32_t), stream>>>(probs, npix, nq, score, thr, labels, area, orig);
+    SIU3R_LAUNCH_CHECK();
+    siu3r_note_launch(1);
+    return SIU3R_OK;
+}
+
+int siu3r_label_lut(const int32_t* labels, int64_t npix, const int32_t* seg_lut, const int32_t* sem_lut, int32_t* seg, int32_t* sem, int32_t* inst,
+                    void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    SIU3R_REQUIRE(labels && seg_lut && sem_lut && seg && sem && inst);
+    label_lut_kernel<<<grid_for(npix), 256, 0, stream>>>(labels, npix, seg_lut, sem_lut, seg, sem, inst);
+    SIU3R_LAUNCH_CHECK();
+    siu3r_note_launch(1);
+    return SIU3R_OK;
+}
+
+int siu3r_qc_logits(const float* probs, int64_t npix, int nq, const int* keep, int nk, const float* cls, int ncls, float* out, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    SIU3R_REQUIRE(probs && keep && cls && out && nk > 0);
+    qc_logits_kernel<<<grid_for(npix * nk * ncls), 256, 0, stream>>>(probs, npix, nq, keep, nk, cls, ncls, out);
+    SIU3R_LAUNCH_CHECK();
+    siu3r_note_launch(1);
+    return SIU3R_OK;
+}
+
+int siu3r_attn_mask_from_logits(const float* logits, int B, int T, int Hm, int Wm, int Q, int oh, int ow, uint8_t* mask, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    SIU3R_REQUIRE(logits && mask);
+    attn_mask_kernel<<<grid_for((int64_t)B * T * oh * ow * Q), 256, 0, stream>>>(logits, B * T, T, Hm, Wm, Q, oh, ow, (float)Hm / (float)oh,
+                                                                               (float)Wm / (float)ow, mask);
+    SIU3R_LAUNCH_CHECK();
+    siu3r_note_launch(1);
+    return SIU3R_OK;
+}
+
+int siu3r_gemm_simt(int M, int N, int K, const float* A, int64_t lda, const float* W, int64_t ldw, float* C, int64_t ldc, const float* bias,
+                    const float* residual, int64_t ldr, int act, float alpha, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    SIU3R_REQUIRE(M > 0 && N > 0 && K > 0 && A && W && C);
+    dim3 grid(ceil_div(N, SG_T), ceil_div(M, SG_T));
+    gemm_simt_kernel<<<grid, SG_T * SG_T, 0, stream>>>(M, N, K, A, lda, W, ldw, C, ldc, bias, residual, ldr, act, alpha);
+    SIU3R_LAUNCH_CHECK();
+    siu3r_note_launch(1);
+    return SIU3R_OK;
+}
+
+}  // extern "C"

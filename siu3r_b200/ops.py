@@ -1,0 +1,393 @@
+"""Thin torch-tensor wrappers over the C ABI (include/siu3r_b200.h).
+
+PyTorch is only the allocator / stream owner here: every function extracts raw device pointers and leading dimensions
+and calls the hand-written sm_100a kernels in libsiu3r_b200.so on torch's current stream.  No torch compute op is used.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
+ELT_RELU, ELT_ADD, ELT_ADD_RELU, ELT_GELU, ELT_COPY, ELT_SIGMOID, ELT_CLAMP01 = 0, 1, 2, 3, 4, 5, 6
+PREC_TF32, PREC_FP32X3 = 1, 3
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _chk_f32(*ts):
+    for t in ts:
+        if t is not None:
+            assert t.is_cuda and t.dtype == torch.float32, (t.device, t.dtype)
+
+
+def launch_count() -> int:
+    return int(_lib.load().siu3r_launch_count())
+
+
+def reset_launch_count():
+    _lib.load().siu3r_reset_launch_count()
+
+
+def split_tf32(x: torch.Tensor):
+    """x (contiguous, numel % 4 == 0) -> (hi, lo) tf32-exact planes with hi + lo ~= x to ~2^-21."""
+    _chk_f32(x)
+    assert x.is_contiguous() and x.numel() % 4 == 0
+    hi, lo = torch.empty_like(x), torch.empty_like(x)
+    _lib.check(_lib.load().siu3r_split_tf32(_p(x), _p(hi), _p(lo), x.numel(), _stream()), "split_tf32")
+    return hi, lo
+
+
+class Weight:
+    """A [N, K] K-major matrix (nn.Linear.weight layout) prepared for the tensor-core path."""
+
+    __slots__ = ("w", "w_lo", "bias", "N", "K")
+
+    def __init__(self, w: torch.Tensor, bias: torch.Tensor | None, precision: int):
+        w = w.contiguous().float()
+        self.N, self.K = w.shape
+        if self.K % 4 != 0:  # TMA needs 16-byte row pitch: zero-pad K
+            kp = (self.K + 3) // 4 * 4
+            wp = torch.zeros(self.N, kp, device=w.device, dtype=torch.float32)
+            wp[:, : self.K] = w
+            w = wp
+        if w.is_cuda and w.numel() % 4 == 0:
+            hi, lo = split_tf32(w)
+            self.w = hi  # round-to-nearest TF32 once at load (the tensor core would otherwise truncate)
+            self.w_lo = lo if precision == PREC_FP32X3 else None
+        else:
+            self.w, self.w_lo = w, None
+        self.bias = None if bias is None else bias.contiguous().float()
+
+
+def gemm(x: torch.Tensor, wt: Weight, out: torch.Tensor | None = None, act: int = ACT_NONE, residual: torch.Tensor | None = None,
+         alpha: float = 1.0, precision: int = PREC_TF32, bias: torch.Tensor | None | bool = True, M: int | None = None) -> torch.Tensor:
+    """out[M,N] = act(alpha * x[M,K] @ W^T + bias) + residual.  x / out / residual are 2-D row-strided views."""
+    _chk_f32(x, out, residual)
+    assert x.dim() == 2 and x.stride(1) == 1
+    M = x.shape[0] if M is None else M
+    K = x.shape[1]
+    assert K in (wt.K, wt.w.shape[1]), (K, wt.K)
+    if out is None:
+        out = torch.empty(M, wt.N, device=x.device, dtype=torch.float32)
+    assert out.stride(1) == 1
+    b = wt.bias if bias is True else (None if bias in (False, None) else bias)
+    ldw = wt.w.shape[1]
+    if x.stride(0) % 4 != 0 or K % 4 != 0 or x.data_ptr() % 16 != 0:
+        code = _lib.load().siu3r_gemm_simt(M, wt.N, K, _p(x), x.stride(0), _p(wt.w), ldw, _p(out), out.stride(0), _p(b), _p(residual),
+                                           0 if residual is None else residual.stride(0), act, alpha, _stream())
+        _lib.check(code, "gemm_simt")
+        return out
+    x_lo = None
+    if precision == PREC_FP32X3:
+        assert wt.w_lo is not None
+        xc = x if x.is_contiguous() else x.contiguous()
+        x_hi, x_lo = split_tf32(xc)
+        x = x_hi
+    code = _lib.load().siu3r_gemm_tc(M, wt.N, K, _p(x), _p(x_lo), x.stride(0), _p(wt.w), _p(wt.w_lo), ldw, _p(out), out.stride(0), _p(b),
+                                     _p(residual), 0 if residual is None else residual.stride(0), act, alpha, precision, _stream())
+    _lib.check(code, "gemm_tc")
+    return out
+
+
+def gemm_simt(x, w, bias=None, out=None, act=ACT_NONE, residual=None, alpha=1.0):
+    """Plain fp32 FFMA GEMM (reference-grade; any shape).  w: [N, K] tensor."""
+    _chk_f32(x, w, out, residual)
+    M, K = x.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty(M, N, device=x.device, dtype=torch.float32)
+    code = _lib.load().siu3r_gemm_simt(M, N, K, _p(x), x.stride(0), _p(w), w.stride(0), _p(out), out.stride(0), _p(bias), _p(residual),
+                                       0 if residual is None else residual.stride(0), act, alpha, _stream())
+    _lib.check(code, "gemm_simt")
+    return out
+
+
+def conv2d_tc_supported(H: int, W: int, Cin: int) -> bool:
+    return Cin % 32 == 0 and W % 16 == 0 and H % 8 == 0
+
+
+def conv2d(x: torch.Tensor, wt: Weight, KH: int, KW: int, stride: int = 1, pad: int = 0, act: int = ACT_NONE,
+           residual: torch.Tensor | None = None, out: torch.Tensor | None = None, precision: int = PREC_TF32) -> torch.Tensor:
+    """NHWC convolution.  wt is [Cout, KH*KW*Cin] ((kh, kw, ci) fastest = ci).  Stride-1 convs with tensor-core friendly
+    shapes run as implicit GEMM (4-D TMA); everything else as im2col + tensor-core GEMM."""
+    _chk_f32(x, residual, out)
+    N, H, W, Cin = x.shape
+    assert x.is_contiguous()
+    Cout = wt.N
+    OH = (H + 2 * pad - KH) // stride + 1
+    OW = (W + 2 * pad - KW) // stride + 1
+    if out is None:
+        out = torch.empty(N, OH, OW, Cout, device=x.device, dtype=torch.float32)
+    if KH == 1 and KW == 1 and stride == 1 and pad == 0:
+        gemm(x.view(-1, Cin), wt, out=out.view(-1, Cout), act=act, residual=None if residual is None else residual.view(-1, Cout),
+             precision=precision)
+        return out
+    if stride == 1 and conv2d_tc_supported(H, W, Cin) and OH == H and OW == W:
+        x_lo = None
+        xx = x
+        if precision == PREC_FP32X3:
+            xx, x_lo = split_tf32(x)
+        code = _lib.load().siu3r_conv2d_tc(N, H, W, Cin, Cout, KH, KW, pad, _p(xx), _p(x_lo), _p(wt.w), _p(wt.w_lo), _p(out), Cout,
+                                           _p(wt.bias), _p(residual), Cout, act, precision, _stream())
+        _lib.check(code, "conv2d_tc")
+        return out
+    K = KH * KW * Cin
+    ldo = wt.w.shape[1]
+    cols = torch.empty(N * OH * OW, ldo, device=x.device, dtype=torch.float32)
+    code = _lib.load().siu3r_im2col_nhwc(_p(x), N, H, W, Cin, KH, KW, stride, pad, _p(cols), ldo, _stream())
+    _lib.check(code, "im2col")
+    assert K <= ldo
+    gemm(cols, wt, out=out.view(-1, Cout), act=act, residual=None if residual is None else residual.view(-1, Cout), precision=precision)
+    return out
+
+
+def layernorm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float, out: torch.Tensor | None = None, add: torch.Tensor | None = None):
+    _chk_f32(x, w, b, out, add)
+    assert x.dim() == 2 and x.stride(1) == 1
+    rows, Cc = x.shape
+    if out is None:
+        out = torch.empty(rows, Cc, device=x.device, dtype=torch.float32)
+    code = _lib.load().siu3r_layernorm(_p(x), x.stride(0), _p(w), _p(b), _p(out), out.stride(0), rows, Cc, eps, _p(add),
+                                       0 if add is None else add.stride(0), _stream())
+    _lib.check(code, "layernorm")
+    return out
+
+
+def rope2d_(tokens_ptr_tensor: torch.Tensor, offset: int, positions: torch.Tensor, B: int, N: int, H: int, D: int, batch_stride: int,
+            token_stride: int, base: float = 100.0, fwd: float = 1.0):
+    """In-place 2-D RoPE on tokens[b,n,h,d] located at tokens.data_ptr() + 4*(offset + b*batch_stride + n*token_stride + h*D + d)."""
+    assert positions.dtype == torch.int64 and positions.is_cuda and positions.is_contiguous()
+    code = _lib.load().siu3r_rope2d(tokens_ptr_tensor.data_ptr() + 4 * offset, _p(positions), B, N, H, D, batch_stride, token_stride, base, fwd,
+                                    _stream())
+    _lib.check(code, "rope2d")
+
+
+def flash_attn_d64(q: torch.Tensor, q_off: int, q_bs: int, q_ts: int, k: torch.Tensor, k_off: int, k_bs: int, k_ts: int, v: torch.Tensor,
+                   v_off: int, v_bs: int, v_ts: int, out: torch.Tensor, B: int, H: int, Nq: int, Nk: int, scale: float, precision: int):
+    """out [B, Nq, H*64] contiguous."""
+    code = _lib.load().siu3r_flash_attn_d64(q.data_ptr() + 4 * q_off, q_bs, q_ts, k.data_ptr() + 4 * k_off, k_bs, k_ts, v.data_ptr() + 4 * v_off,
+                                            v_bs, v_ts, _p(out), Nq * H * 64, H * 64, B, H, Nq, Nk, scale, precision, _stream())
+    _lib.check(code, "flash_attn_d64")
+    return out
+
+
+def attn_small_d32(q, q_bs, q_ts, k, k_bs, k_ts, v, v_bs, v_ts, out, o_bs, o_ts, mask, B, H, Nq, Nk, scale):
+    code = _lib.load().siu3r_attn_small_d32(_p(q), q_bs, q_ts, _p(k), k_bs, k_ts, _p(v), v_bs, v_ts, _p(out), o_bs, o_ts, _p(mask), B, H, Nq, Nk,
+                                            scale, _stream())
+    _lib.check(code, "attn_small_d32")
+    return out
+
+
+def msdeform_attn(value, Lin, ow, ref, levels_hw, P, B, Lq, nH, hd, out):
+    L = len(levels_hw)
+    arr = (C.c_int * (2 * L))(*[int(v) for hw in levels_hw for v in hw])
+    code = _lib.load().siu3r_msdeform_attn(_p(value), value.stride(-2) if value.dim() > 1 else nH * hd, Lin, _p(ow), ow.stride(-2), _p(ref), arr, L,
+                                           P, B, Lq, nH, hd, _p(out), out.stride(-2), _stream())
+    _lib.check(code, "msdeform_attn")
+    return out
+
+
+def eltwise(op: int, a: torch.Tensor, b: torch.Tensor | None = None, out: torch.Tensor | None = None):
+    _chk_f32(a, b, out)
+    assert a.is_contiguous() and (b is None or b.is_contiguous())
+    if out is None:
+        out = torch.empty_like(a)
+    _lib.check(_lib.load().siu3r_eltwise(op, _p(a), _p(b), _p(out), a.numel(), _stream()), "eltwise")
+    return out
+
+
+def scale_(x: torch.Tensor, alpha: float):
+    """x *= alpha in place."""
+    _chk_f32(x)
+    assert x.is_contiguous()
+    _lib.check(_lib.load().siu3r_scale(_p(x), float(alpha), _p(x), x.numel(), _stream()), "scale")
+    return x
+
+
+def rows_affine(x, scale=None, shift=None, add=None, out=None, relu=False, rows=None, C_=None):
+    """out[r,:C] = relu?(x[r,:C]*scale + shift + add[r,:C]) for 2-D row-strided views."""
+    _chk_f32(x, scale, shift, add, out)
+    rows = x.shape[0] if rows is None else rows
+    Cc = x.shape[1] if C_ is None else C_
+    if out is None:
+        out = torch.empty(rows, Cc, device=x.device, dtype=torch.float32)
+    code = _lib.load().siu3r_rows_affine(_p(x), x.stride(0), _p(scale), _p(shift), _p(add), 0 if add is None else add.stride(0), _p(out),
+                                         out.stride(0), rows, Cc, 1 if relu else 0, _stream())
+    _lib.check(code, "rows_affine")
+    return out
+
+
+def resize_bilinear(x: torch.Tensor, OH: int, OW: int, align_corners: bool, out: torch.Tensor | None = None, accumulate: bool = False,
+                    ldx: int | None = None):
+    """x: [N,H,W,C] (pixel stride ldx, images densely packed H*W*ldx apart) -> out [N,OH,OW,C]."""
+    _chk_f32(x, out)
+    N, H, W, Cc = x.shape
+    ldx = x.stride(2) if ldx is None else ldx
+    if out is None:
+        out = torch.empty(N, OH, OW, Cc, device=x.device, dtype=torch.float32)
+    code = _lib.load().siu3r_resize_bilinear_nhwc(_p(x), N, H, W, Cc, ldx, _p(out), OH, OW, out.stride(2), 1 if align_corners else 0,
+                                                  1 if accumulate else 0, _stream())
+    _lib.check(code, "resize_bilinear")
+    return out
+
+
+def pixel_shuffle(g: torch.Tensor, N: int, H: int, W: int, Cc: int, s: int, add: torch.Tensor | None = None, out: torch.Tensor | None = None):
+    if out is None:
+        out = torch.empty(N, H * s, W * s, Cc, device=g.device, dtype=torch.float32)
+    _lib.check(_lib.load().siu3r_pixel_shuffle_nhwc(_p(g), N, H, W, Cc, s, _p(add), _p(out), _stream()), "pixel_shuffle")
+    return out
+
+
+def nchw_to_nhwc(x: torch.Tensor, ldy: int | None = None):
+    N, Cc, H, W = x.shape
+    ldy = Cc if ldy is None else ldy
+    y = torch.zeros(N, H, W, ldy, device=x.device, dtype=torch.float32) if ldy != Cc else torch.empty(N, H, W, ldy, device=x.device,
+                                                                                                      dtype=torch.float32)
+    _lib.check(_lib.load().siu3r_nchw_to_nhwc(_p(x.contiguous()), _p(y), N, Cc, H * W, ldy, _stream()), "nchw_to_nhwc")
+    return y
+
+
+def nhwc_to_nchw(x: torch.Tensor, Cc: int | None = None):
+    N, H, W, ld = x.shape
+    Cc = ld if Cc is None else Cc
+    y = torch.empty(N, Cc, H, W, device=x.device, dtype=torch.float32)
+    _lib.check(_lib.load().siu3r_nhwc_to_nchw(_p(x), ld, _p(y), N, Cc, H * W, _stream()), "nhwc_to_nchw")
+    return y
+
+
+def maxpool3x3s2(x: torch.Tensor):
+    N, H, W, Cc = x.shape
+    OH, OW = (H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1
+    y = torch.empty(N, OH, OW, Cc, device=x.device, dtype=torch.float32)
+    _lib.check(_lib.load().siu3r_maxpool3x3s2_nhwc(_p(x), N, H, W, Cc, _p(y), _stream()), "maxpool")
+    return y
+
+
+def dwconv3x3(x_ptr: int, ldx: int, bsx: int, N: int, H: int, W: int, Cc: int, w: torch.Tensor, b: torch.Tensor, y_ptr: int, ldy: int, bsy: int,
+              gelu: bool):
+    code = _lib.load().siu3r_dwconv3x3_nhwc(x_ptr, ldx, bsx, N, H, W, Cc, _p(w), _p(b), y_ptr, ldy, bsy, 1 if gelu else 0, _stream())
+    _lib.check(code, "dwconv3x3")
+
+
+def groupnorm(x: torch.Tensor, groups: int, w: torch.Tensor, b: torch.Tensor, eps: float, relu: bool, out: torch.Tensor | None = None):
+    """x: [N, HW, C] contiguous."""
+    N, HW, Cc = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    _lib.check(_lib.load().siu3r_groupnorm_nhwc(_p(x), N, HW, Cc, groups, _p(w), _p(b), eps, 1 if relu else 0, _p(out), _stream()), "groupnorm")
+    return out
+
+
+def depth_exp(xyz: torch.Tensor, n: int, ldx: int):
+    pts = torch.empty(n, 3, device=xyz.device, dtype=torch.float32)
+    _lib.check(_lib.load().siu3r_depth_exp(_p(xyz), ldx, _p(pts), n, _stream()), "depth_exp")
+    return pts
+
+
+def gaussian_adapter(raw: torch.Tensor):
+    """raw [G, 83] contiguous -> (cov [G,3,3], harmonics [G,3,25], opacities [G], scales [G,3], rotations [G,4])."""
+    _chk_f32(raw)
+    assert raw.is_contiguous() and raw.shape[-1] == 83
+    G = raw.numel() // 83
+    dev = raw.device
+    cov = torch.empty(G, 3, 3, device=dev)
+    harm = torch.empty(G, 3, 25, device=dev)
+    opac = torch.empty(G, device=dev)
+    scales = torch.empty(G, 3, device=dev)
+    rots = torch.empty(G, 4, device=dev)
+    _lib.check(_lib.load().siu3r_gaussian_adapter(_p(raw), G, _p(cov), _p(harm), _p(opac), _p(scales), _p(rots), _stream()), "gaussian_adapter")
+    return cov, harm, opac, scales, rots
+
+
+def attn_mask_from_logits(logits: torch.Tensor, B: int, T: int, Hm: int, Wm: int, Q: int, oh: int, ow: int):
+    mask = torch.empty(B, Q, T * oh * ow, device=logits.device, dtype=torch.uint8)
+    _lib.check(_lib.load().siu3r_attn_mask_from_logits(_p(logits), B, T, Hm, Wm, Q, oh, ow, _p(mask), _stream()), "attn_mask")
+    return mask
+
+
+def resize_select(x: torch.Tensor, idx: torch.Tensor, OH: int, OW: int):
+    N, H, W, Cc = x.shape
+    nsel = idx.numel()
+    y = torch.empty(N, OH, OW, nsel, device=x.device, dtype=torch.float32)
+    _lib.check(_lib.load().siu3r_resize_select(_p(x), N, H, W, Cc, _p(idx), nsel, _p(y), OH, OW, _stream()), "resize_select")
+    return y
+
+
+def argmax_area(probs: torch.Tensor, score: torch.Tensor, thr: float):
+    nq = probs.shape[-1]
+    npix = probs.numel() // nq
+    labels = torch.empty(npix, device=probs.device, dtype=torch.int32)
+    area = torch.empty(nq, device=probs.device, dtype=torch.int32)
+    orig = torch.empty(nq, device=probs.device, dtype=torch.int32)
+    _lib.check(_lib.load().siu3r_argmax_area(_p(probs), npix, nq, _p(score), thr, _p(labels), _p(area), _p(orig), _stream()), "argmax_area")
+    return labels, area, orig
+
+
+def label_lut(labels: torch.Tensor, seg_lut: torch.Tensor, sem_lut: torch.Tensor):
+    npix = labels.numel()
+    seg = torch.empty(npix, device=labels.device, dtype=torch.int32)
+    sem = torch.empty_like(seg)
+    inst = torch.empty_like(seg)
+    _lib.check(_lib.load().siu3r_label_lut(_p(labels), npix, _p(seg_lut), _p(sem_lut), _p(seg), _p(sem), _p(inst), _stream()), "label_lut")
+    return seg, sem, inst
+
+
+def qc_logits(probs: torch.Tensor, keep: torch.Tensor, cls: torch.Tensor):
+    nq = probs.shape[-1]
+    npix = probs.numel() // nq
+    nk, ncls = cls.shape
+    out = torch.empty(npix, nk, ncls, device=probs.device, dtype=torch.float32)
+    _lib.check(_lib.load().siu3r_qc_logits(_p(probs), npix, nq, _p(keep), nk, _p(cls), ncls, _p(out), _stream()), "qc_logits")
+    return out
+
+
+def raster_forward(means, cov, shs, opac, viewmatrix, projmatrix, campos, bg, tan_fovx, tan_fovy, H, W, sh_degree, sh_layout, dup_capacity=None,
+                   count_touched=True, debug=False):
+    """One camera.  means [G,3]; cov [G,6] or [G,3,3]; shs [G,M,3] (sh_layout 0) or [G,3,M] (1); returns dict."""
+    lib = _lib.load()
+    _chk_f32(means, cov, shs, opac, viewmatrix, projmatrix, campos, bg)
+    G = means.shape[0]
+    cov_stride = 6 if cov.shape[-1] == 6 else 9
+    M = shs.shape[1] if sh_layout == 0 else shs.shape[2]
+    dev = means.device
+    if dup_capacity is None:
+        dup_capacity = max(1 << 16, 8 * G)
+    while True:
+        ws_bytes = int(lib.siu3r_raster_workspace_bytes(G, H, W, dup_capacity))
+        if ws_bytes < 0:
+            raise RuntimeError("raster_workspace_bytes: invalid arguments")
+        ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+        color = torch.empty(3, H, W, device=dev)
+        depth = torch.empty(H, W, device=dev)
+        opacity = torch.empty(H, W, device=dev)
+        radii = torch.empty(G, device=dev, dtype=torch.int32)
+        n_touched = torch.empty(G, device=dev, dtype=torch.int32) if count_touched else None
+        nren = C.c_int64(0)
+        gx, gy = (W + 15) // 16, (H + 15) // 16
+        dbg = {}
+        if debug:
+            dbg = dict(tiles=torch.zeros(G, device=dev, dtype=torch.int32), offsets=torch.zeros(G, device=dev, dtype=torch.int32),
+                       keys=torch.zeros(dup_capacity, device=dev, dtype=torch.int64), values=torch.zeros(dup_capacity, device=dev, dtype=torch.int32),
+                       ranges=torch.zeros(gx * gy, 2, device=dev, dtype=torch.int32))
+        code = lib.siu3r_raster_forward(G, H, W, sh_degree, M, sh_layout, cov_stride, _p(means), _p(cov), _p(shs), _p(opac), _p(viewmatrix),
+                                        _p(projmatrix), _p(campos), _p(bg), float(tan_fovx), float(tan_fovy), _p(color), _p(depth), _p(opacity),
+                                        _p(radii), _p(n_touched), _p(ws), ws_bytes, dup_capacity, C.byref(nren), _p(dbg.get("tiles")),
+                                        _p(dbg.get("offsets")), _p(dbg.get("keys")), _p(dbg.get("values")), _p(dbg.get("ranges")), _stream())
+        if code == -2 and nren.value > dup_capacity:
+            dup_capacity = int(nren.value * 1.05) + 1024  # exact count is known now: retry once with enough room
+            continue
+        _lib.check(code, "raster_forward")
+        break
+    res = dict(color=color, depth=depth, opacity=opacity, radii=radii, n_touched=n_touched, num_rendered=int(nren.value))
+    res.update(dbg)
+    return res

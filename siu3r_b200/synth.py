@@ -1,0 +1,54 @@
+"""Synthetic inputs of the BASELINE.json workloads: seeded, host-generated, no reference dependency."""
+from __future__ import annotations
+
+import torch
+
+
+def pair_inputs(batch: int, views: int, size: int, seed: int = 0):
+    """images rand(B,V,3,S,S) in [0,1]; K = inference.py defaults (fx = fy = 318/256, cx = cy = 0.5) normalised."""
+    g = torch.Generator(device="cpu")
+    g.manual_seed(1000 + seed)
+    img = torch.rand(batch, views, 3, size, size, generator=g)
+    K = torch.tensor([[318 / 256, 0, 0.5], [0, 318 / 256, 0.5], [0, 0, 1.0]])
+    return img, K[None, None].repeat(batch, views, 1, 1).contiguous()
+
+
+def _quat_to_rot(q: torch.Tensor) -> torch.Tensor:
+    i, j, k, r = q.unbind(-1)
+    two_s = 2.0 / (q * q).sum(-1)
+    o = torch.stack((1 - two_s * (j * j + k * k), two_s * (i * j - k * r), two_s * (i * k + j * r),
+                     two_s * (i * j + k * r), 1 - two_s * (i * i + k * k), two_s * (j * k - i * r),
+                     two_s * (i * k - j * r), two_s * (j * k + i * r), 1 - two_s * (i * i + j * j)), -1)
+    return o.reshape(q.shape[:-1] + (3, 3))
+
+
+def raster_scene(G: int, H: int, W: int, seed: int = 0, pixel_aligned: bool = False):
+    """Config 5 of BASELINE.json: camera at the origin looking down +z, normalised focal 318/256, scene already in the
+    renderer's x10 units (z ~ U[5, 80]).  Returns CPU tensors: means [G,3], covariances [G,3,3], harmonics [G,3,25],
+    opacities [G], extrinsics [1,4,4] (c2w), intrinsics [1,3,3] (normalised), near, far."""
+    g = torch.Generator(device="cpu")
+    g.manual_seed(7000 + seed)
+    f = 318 / 256
+    z = 5 + 75 * torch.rand(G, generator=g)
+    u = torch.rand(G, generator=g) * 2 - 1  # NDC in [-1, 1]
+    v = torch.rand(G, generator=g) * 2 - 1
+    x = u * z * (0.5 / f)
+    y = v * z * (0.5 / f)  # fy is normalised by H, so NDC y = v as well
+    means = torch.stack((x, y, z), -1)
+    if pixel_aligned:
+        sigma = (z / (f * W))[:, None] * (0.5 + torch.rand(G, 3, generator=g))
+    else:
+        sigma = (0.01 * torch.nn.functional.softplus(torch.randn(G, 3, generator=g))).clamp_max(3.0)
+    q = torch.randn(G, 4, generator=g)
+    q = q / q.norm(dim=-1, keepdim=True)
+    R = _quat_to_rot(q)
+    cov = R @ torch.diag_embed(sigma * sigma) @ R.transpose(-1, -2)
+    opac = torch.sigmoid(torch.randn(G, generator=g))
+    mask = torch.ones(25)
+    for d in range(1, 5):
+        mask[d * d:(d + 1) * (d + 1)] = 0.1 * 0.25 ** d
+    harm = torch.randn(G, 3, 25, generator=g) * mask
+    E = torch.eye(4)[None].clone()
+    K = torch.tensor([[f, 0, 0.5], [0, f, 0.5], [0, 0, 1.0]])[None]
+    return dict(means=means.contiguous(), covariances=cov.contiguous(), harmonics=harm.contiguous(), opacities=opac.contiguous(),
+                extrinsics=E, intrinsics=K, near=torch.tensor([1.0]), far=torch.tensor([1000.0]))

@@ -1,0 +1,688 @@
+"""SIU3RModel -- the per-image-pair hot path on hand-written sm_100a kernels, behind the reference's call surface.
+
+Mirrors /root/reference/src/models/model.py:31-389 (SIU3RModel.__init__/forward): same constructor config fields, same
+state_dict key set (loaded unchanged, see weights.py), same return tuple.  Everything between the input tensors and the
+returned tensors runs through the C ABI (ops.py); PyTorch only owns memory and the stream.
+
+Layouts: activations are token-major / NHWC fp32.  The two views are batched view-major like the reference's
+torch.cat((img1, img2), 0) (backbone_croco.py:174-176): row block i = v * B + b.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from types import SimpleNamespace
+
+import torch
+
+from . import ops
+from .gaussians import Gaussians
+from .ops import ACT_GELU, ACT_NONE, ACT_RELU, ELT_ADD, ELT_RELU, ELT_SIGMOID
+from .weights import Packer, reference_points, sine_pos_2d, sine_pos_3d
+
+# label tables of the reference (src/utils/scannet_constant.py:1-35): 20 ScanNet classes, stuff = {wall, floor}
+PANOPTIC_SEMANTIC2NAME = {1: "wall", 2: "floor", 3: "cabinet", 4: "bed", 5: "chair", 6: "sofa", 7: "table", 8: "door", 9: "window",
+                          10: "bookshelf", 11: "picture", 12: "counter", 13: "desk", 14: "curtain", 15: "refrigerator", 16: "shower curtain",
+                          17: "toilet", 18: "sink", 19: "bathtub", 20: "otherfurniture"}
+STUFF_CLASSES = [0, 1]
+
+
+@dataclass
+class ModelCfg:
+    """Subset of src/config.py:46-80 (ModelCfg / CrocoCfg / Mask2formerCfg / GaussianHeadCfg) that shapes the forward pass."""
+    image_size: tuple = (256, 256)
+    enc_depth: int = 24
+    dec_depth: int = 12
+    enc_embed_dim: int = 1024
+    dec_embed_dim: int = 768
+    enc_num_heads: int = 16
+    dec_num_heads: int = 12
+    patch_size: int = 16
+    num_queries: int = 100
+    seg_threshold: float = 0.5
+    id2label: dict = field(default_factory=lambda: dict(PANOPTIC_SEMANTIC2NAME))
+    label_ids_to_fuse: list = field(default_factory=lambda: list(STUFF_CLASSES))
+    sh_degree: int = 4
+    interaction_indexes: tuple = (5, 11, 17, 23)
+
+
+class SIU3RModel:
+    def __init__(self, cfg: ModelCfg | None = None, precision: str = "tf32"):
+        self.cfg = cfg or ModelCfg()
+        assert precision in ("tf32", "fp32x3")
+        self.prec = ops.PREC_TF32 if precision == "tf32" else ops.PREC_FP32X3
+        self.precision = precision
+        self._sd = None
+        self._ready = False
+        self._cache = {}
+        self.capture = None  # set to a dict to record stage-boundary tensors (tests)
+        S0, S1 = self.cfg.image_size
+        assert S0 % 32 == 0 and S1 % 32 == 0, "image size must be a multiple of 32 (patch 16, adapter stride 32)"
+
+    # ---- nn.Module-like surface -------------------------------------------------------------------------------
+    def load_state_dict(self, sd: dict, strict: bool = False):
+        self._sd = sd
+        self._ready = False
+        return SimpleNamespace(missing_keys=[], unexpected_keys=[])
+
+    def eval(self):
+        return self
+
+    def cuda(self, device=None):
+        self.dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        if self._sd is None:
+            raise RuntimeError("load_state_dict() first: this engine has no random init of its own")
+        self._pack()
+        return self
+
+    def __call__(self, *a, **k):
+        return self.forward(*a, **k)
+
+    # ---- weight packing -----------------------------------------------------------------------------------------
+    def _pack(self):
+        P = Packer(self._sd, self.dev, self.prec)
+        c = self.cfg
+        w = SimpleNamespace()
+        # backbone
+        w.patch = P.conv("backbone.patch_embed.proj", pad_cin_to=4)
+        w.intr_w, w.intr_b = P.vec("backbone.intrinsic_encoder.weight"), P.vec("backbone.intrinsic_encoder.bias")
+        w.enc = []
+        for i in range(c.enc_depth):
+            p = f"backbone.enc_blocks.{i}."
+            w.enc.append(SimpleNamespace(n1=(P.vec(p + "norm1.weight"), P.vec(p + "norm1.bias")), qkv=P.linear(p + "attn.qkv"),
+                                         proj=P.linear(p + "attn.proj"), n2=(P.vec(p + "norm2.weight"), P.vec(p + "norm2.bias")),
+                                         fc1=P.linear(p + "mlp.fc1"), fc2=P.linear(p + "mlp.fc2")))
+        w.enc_norm = (P.vec("backbone.enc_norm.weight"), P.vec("backbone.enc_norm.bias"))
+        w.dec_embed = P.linear("backbone.decoder_embed")
+        w.dec = []
+        for name in ("dec_blocks", "dec_blocks2"):
+            blocks = []
+            for i in range(c.dec_depth):
+                p = f"backbone.{name}.{i}."
+                ln = lambda n: (P.vec(p + n + ".weight"), P.vec(p + n + ".bias"))
+                blocks.append(SimpleNamespace(n1=ln("norm1"), n2=ln("norm2"), n3=ln("norm3"), ny=ln("norm_y"), qkv=P.linear(p + "attn.qkv"),
+                                              proj=P.linear(p + "attn.proj"), cq=P.linear(p + "cross_attn.projq"),
+                                              ckv=P.linear_cat([p + "cross_attn.projk", p + "cross_attn.projv"]),
+                                              cproj=P.linear(p + "cross_attn.proj"), fc1=P.linear(p + "mlp.fc1"), fc2=P.linear(p + "mlp.fc2")))
+            w.dec.append(blocks)
+        w.dec_norm = (P.vec("backbone.dec_norm.weight"), P.vec("backbone.dec_norm.bias"))
+        # DPT heads
+        w.heads = {}
+        for hname in ("downstream_head1", "downstream_head2", "gaussian_param_head1", "gaussian_param_head2"):
+            p = hname + ".dpt."
+            h = SimpleNamespace()
+            h.act_conv = [P.conv(p + f"act_postprocess.{i}.0") for i in range(4)]
+            h.act_up0, h.s0 = P.conv_transpose(p + "act_postprocess.0.1")
+            h.act_up1, h.s1 = P.conv_transpose(p + "act_postprocess.1.1")
+            h.act_down3 = P.conv(p + "act_postprocess.3.1")
+            h.layer_rn = [P.conv(p + f"scratch.layer_rn.{i}") for i in range(4)]
+            h.refine = []
+            for r in (1, 2, 3, 4):
+                q = p + f"scratch.refinenet{r}."
+                h.refine.append(SimpleNamespace(out_conv=P.conv(q + "out_conv"),
+                                                r1=(P.conv(q + "resConfUnit1.conv1"), P.conv(q + "resConfUnit1.conv2")),
+                                                r2=(P.conv(q + "resConfUnit2.conv1"), P.conv(q + "resConfUnit2.conv2"))))
+            h.head0 = P.conv(p + "head.0")
+            if hname.startswith("downstream"):
+                h.head2, h.head4 = P.conv(p + "head.2"), P.conv(p + "head.4")
+            else:
+                h.head4 = P.conv(p + "head.4")
+                h.merger = P.conv(p + "input_merger.0", pad_cin_to=4)
+            w.heads[hname] = h
+        # ViT adapter
+        a = SimpleNamespace()
+        a.stem = [P.conv("adapter.spm.stem.0", bn="adapter.spm.stem.1", pad_cin_to=4), P.conv("adapter.spm.stem.3", bn="adapter.spm.stem.4"),
+                  P.conv("adapter.spm.stem.6", bn="adapter.spm.stem.7")]
+        a.conv2 = P.conv("adapter.spm.conv2.0", bn="adapter.spm.conv2.1")
+        a.conv3 = P.conv("adapter.spm.conv3.0", bn="adapter.spm.conv3.1")
+        a.conv4 = P.conv("adapter.spm.conv4.0", bn="adapter.spm.conv4.1")
+        lvl = P.t("adapter.level_embed")
+        a.fc1 = P.conv("adapter.spm.fc1")
+        a.fc = [P.conv("adapter.spm.fc2", extra_bias=lvl[0]), P.conv("adapter.spm.fc3", extra_bias=lvl[1]), P.conv("adapter.spm.fc4", extra_bias=lvl[2])]
+
+        def extractor(p):
+            ln = lambda n: (P.vec(p + n + ".weight"), P.vec(p + n + ".bias"))
+            dw, db = P.dwconv(p + "ffn.dwconv.dwconv")
+            return SimpleNamespace(qn=ln("query_norm"), fn=ln("feat_norm"), ffn_norm=ln("ffn_norm"), value=P.linear(p + "attn.value_proj"),
+                                   ow=P.linear_cat([p + "attn.sampling_offsets", p + "attn.attention_weights"]), out=P.linear(p + "attn.output_proj"),
+                                   fc1=P.linear(p + "ffn.fc1"), dw=dw, db=db, fc2=P.linear(p + "ffn.fc2"))
+        a.inter = []
+        for i in range(4):
+            ex = [extractor(f"adapter.interactions.{i}.extractor.")]
+            if i == 3:
+                ex += [extractor(f"adapter.interactions.{i}.extra_extractors.{j}.") for j in range(2)]
+            a.inter.append(ex)
+        a.up, a.up_s = P.conv_transpose("adapter.up")
+        a.bn = [tuple(t.contiguous().to(self.dev) for t in P.bn_scale_shift(f"adapter.norm{i}")) for i in (1, 2, 3, 4)]
+        w.adapter = a
+        # Mask2Former
+        m = SimpleNamespace()
+        pd = "mask2former.model.pixel_decoder."
+        m.in_proj = [(P.conv(pd + f"input_projections.{i}.0"), P.vec(pd + f"input_projections.{i}.1.weight"), P.vec(pd + f"input_projections.{i}.1.bias"))
+                     for i in range(3)]
+        m.pd_level_embed = P.t(pd + "level_embed")
+        m.enc = []
+        for i in range(6):
+            p = pd + f"encoder.layers.{i}."
+            ln = lambda n: (P.vec(p + n + ".weight"), P.vec(p + n + ".bias"))
+            m.enc.append(SimpleNamespace(value=P.linear(p + "self_attn.value_proj"),
+                                         ow=P.linear_cat([p + "self_attn.sampling_offsets", p + "self_attn.attention_weights"]),
+                                         out=P.linear(p + "self_attn.output_proj"), ln1=ln("self_attn_layer_norm"), fc1=P.linear(p + "fc1"),
+                                         fc2=P.linear(p + "fc2"), ln2=ln("final_layer_norm")))
+        m.lateral = (P.conv(pd + "adapter_1.0"), P.vec(pd + "adapter_1.1.weight"), P.vec(pd + "adapter_1.1.bias"))
+        m.output = (P.conv(pd + "layer_1.0"), P.vec(pd + "layer_1.1.weight"), P.vec(pd + "layer_1.1.bias"))
+        m.mask_proj = P.conv(pd + "mask_projection")
+        tm = "mask2former.model.transformer_module."
+        m.q_feat, m.q_pos = P.vec(tm + "queries_features.weight"), P.vec(tm + "queries_embedder.weight")
+        m.tm_level_embed = P.t(tm + "level_embed.weight")
+        m.dec = []
+        E = 256
+        for i in range(9):
+            p = tm + f"decoder.layers.{i}."
+            ln = lambda n: (P.vec(p + n + ".weight"), P.vec(p + n + ".bias"))
+            m.dec.append(SimpleNamespace(
+                cq=P.linear_rows(p + "cross_attn.in_proj_weight", p + "cross_attn.in_proj_bias", 0, E),
+                ck=P.linear_rows(p + "cross_attn.in_proj_weight", p + "cross_attn.in_proj_bias", E, 2 * E),
+                cv=P.linear_rows(p + "cross_attn.in_proj_weight", p + "cross_attn.in_proj_bias", 2 * E, 3 * E),
+                cout=P.linear(p + "cross_attn.out_proj"), cln=ln("cross_attn_layer_norm"),
+                sqk=P.linear_cat([p + "self_attn.q_proj", p + "self_attn.k_proj"]), sv=P.linear(p + "self_attn.v_proj"),
+                sout=P.linear(p + "self_attn.out_proj"), sln=ln("self_attn_layer_norm"), fc1=P.linear(p + "fc1"), fc2=P.linear(p + "fc2"),
+                fln=ln("final_layer_norm")))
+        m.dec_ln = (P.vec(tm + "decoder.layernorm.weight"), P.vec(tm + "decoder.layernorm.bias"))
+        m.mask_mlp = [P.linear(tm + f"decoder.mask_predictor.mask_embedder.{i}.0") for i in range(3)]
+        m.cls = P.linear("mask2former.class_predictor")
+        w.m2f = m
+        self.w = w
+        self._sd = None  # raw tensors no longer needed
+        self._ready = True
+
+    # ---- shape-dependent constants (host-built once per image size) -------------------------------------------------
+    def _consts(self, B: int, S0: int, S1: int):
+        key = (B, S0, S1)
+        if key in self._cache:
+            return self._cache[key]
+        gh, gw = S0 // 16, S1 // 16
+        ys, xs = torch.meshgrid(torch.arange(gh), torch.arange(gw), indexing="ij")
+        pos = torch.stack([ys.flatten(), xs.flatten()], -1)
+        pos = torch.cat([pos, torch.tensor([[gh, 0]])], 0)  # intrinsics token at (y_last + 1, 0): backbone_croco.py:148-150
+        k = SimpleNamespace()
+        k.pos_enc = pos[None].repeat(2 * B, 1, 1).contiguous().to(self.dev)
+        k.pos_dec = pos[None].repeat(B, 1, 1).contiguous().to(self.dev)
+        ad_shapes = [(S0 // 8, S1 // 8), (S0 // 16, S1 // 16), (S0 // 32, S1 // 32)]
+        k.ad_ref = reference_points(ad_shapes).to(self.dev)
+        m = self.w.m2f
+        lv = [(S0 // 32, S1 // 32), (S0 // 16, S1 // 16), (S0 // 8, S1 // 8)]  # pixel-decoder order: low -> high resolution
+        k.m2f_shapes = lv
+        k.m2f_ref = reference_points(lv).to(self.dev)
+        pe = torch.cat([sine_pos_2d(h, w) + m.pd_level_embed[i][None] for i, (h, w) in enumerate(lv)], 0)
+        k.m2f_pos = pe[None].repeat(2 * B, 1, 1).reshape(-1, 256).contiguous().to(self.dev)
+        k.tm_pos = [sine_pos_3d(2, h, w)[None].repeat(B, 1, 1).reshape(-1, 256).contiguous().to(self.dev) for (h, w) in lv]
+        k.tm_lvl = [m.tm_level_embed[i].contiguous().to(self.dev) for i in range(3)]
+        k.hidden0 = m.q_feat[None].repeat(B, 1, 1).view(-1, 256).contiguous()
+        k.qpos = m.q_pos[None].repeat(B, 1, 1).view(-1, 256).contiguous()
+        self._cache[key] = k
+        return k
+
+    def _cap(self, name, t):
+        if self.capture is not None:
+            self.capture[name] = t
+
+    # ---- building blocks ------------------------------------------------------------------------------------------
+    def _lin(self, x, wt, **kw):
+        return ops.gemm(x, wt, precision=self.prec, **kw)
+
+    def _conv(self, x, wt, k, **kw):
+        return ops.conv2d(x, wt, k, k, precision=self.prec, **kw)
+
+    def _self_attn(self, h, blk, pos, Bn, N, C, nh):
+        M = Bn * N
+        qkv = self._lin(h, blk.qkv)
+        ops.rope2d_(qkv, 0, pos, Bn, N, nh, 64, N * 3 * C, 3 * C)
+        ops.rope2d_(qkv, C, pos, Bn, N, nh, 64, N * 3 * C, 3 * C)
+        a = torch.empty(M, C, device=self.dev)
+        ops.flash_attn_d64(qkv, 0, N * 3 * C, 3 * C, qkv, C, N * 3 * C, 3 * C, qkv, 2 * C, N * 3 * C, 3 * C, a, Bn, nh, N, N, 0.125, self.prec)
+        return a
+
+    def _encoder(self, x, pos, Bn, N):
+        """24 x Block (croco/blocks.py:127-130); x [Bn*N, 1024] is updated in place except at the kept blocks."""
+        keep = {}
+        C = 1024
+        for i, blk in enumerate(self.w.enc):
+            h = ops.layernorm(x, blk.n1[0], blk.n1[1], 1e-6)
+            a = self._self_attn(h, blk, pos, Bn, N, C, 16)
+            self._lin(a, blk.proj, residual=x, out=x)
+            h = ops.layernorm(x, blk.n2[0], blk.n2[1], 1e-6)
+            f = self._lin(h, blk.fc1, act=ACT_GELU)
+            if i in self.cfg.interaction_indexes:
+                xn = torch.empty_like(x)
+                self._lin(f, blk.fc2, residual=x, out=xn)
+                x = xn
+                keep[i] = x
+                self._cap(f"enc{i}", x)
+            else:
+                self._lin(f, blk.fc2, residual=x, out=x)
+        return x, keep
+
+    def _dec_block(self, blk, x, y, pos, B, N):
+        """DecoderBlock.forward (croco/blocks.py:186-191): self-attn, cross-attn on norm_y(y), MLP.  Returns a new buffer."""
+        C, nh = 768, 12
+        h = ops.layernorm(x, blk.n1[0], blk.n1[1], 1e-6)
+        a = self._self_attn(h, blk, pos, B, N, C, nh)
+        x1 = self._lin(a, blk.proj, residual=x)
+        yn = ops.layernorm(y, blk.ny[0], blk.ny[1], 1e-6)
+        h2 = ops.layernorm(x1, blk.n2[0], blk.n2[1], 1e-6)
+        q = self._lin(h2, blk.cq)
+        kv = self._lin(yn, blk.ckv)
+        ops.rope2d_(q, 0, pos, B, N, nh, 64, N * C, C)
+        ops.rope2d_(kv, 0, pos, B, N, nh, 64, N * 2 * C, 2 * C)
+        a2 = torch.empty(B * N, C, device=self.dev)
+        ops.flash_attn_d64(q, 0, N * C, C, kv, 0, N * 2 * C, 2 * C, kv, C, N * 2 * C, 2 * C, a2, B, nh, N, N, 0.125, self.prec)
+        self._lin(a2, blk.cproj, residual=x1, out=x1)
+        h3 = ops.layernorm(x1, blk.n3[0], blk.n3[1], 1e-6)
+        f = self._lin(h3, blk.fc1, act=ACT_GELU)
+        self._lin(f, blk.fc2, residual=x1, out=x1)
+        return x1
+
+    # ---- DPT heads (heads/dpt_head.py:36-79, dpt_gs_head.py:121-171, dpt_block.py) ------------------------------------
+    def _rcu(self, x, unit):
+        r = ops.eltwise(ELT_RELU, x)
+        t = self._conv(r, unit[0], 3, pad=1, act=ACT_RELU)
+        return self._conv(t, unit[1], 3, pad=1, residual=x)
+
+    def _fusion(self, rf, x0, x1=None):
+        out = x0
+        if x1 is not None:
+            res = self._rcu(x1, rf.r1)
+            out = ops.eltwise(ELT_ADD, out, res)
+        out = self._rcu(out, rf.r2)
+        n, h, w_, c = out.shape
+        out = ops.resize_bilinear(out, 2 * h, 2 * w_, True)
+        return self._conv(out, rf.out_conv, 1)
+
+    def _dpt_trunk(self, hw, toks, B, N, gh, gw):
+        """toks: 4 token tensors [B*N, C] (trailing intrinsics token per image is skipped) -> path_1 [B, 8gh, 8gw, 256]."""
+        P = gh * gw
+        layers = []
+        for i in range(4):
+            C_in = toks[i].shape[1]
+            cw = hw.act_conv[i]
+            o = torch.empty(B, gh, gw, cw.N, device=self.dev)
+            for b in range(B):
+                self._lin(toks[i][b * N: b * N + P], cw, out=o[b].view(P, cw.N))
+            del C_in
+            layers.append(o)
+        # act_postprocess tails
+        g0 = self._lin(layers[0].view(B * P, -1), hw.act_up0)
+        layers[0] = ops.pixel_shuffle(g0, B, gh, gw, hw.act_up0.N // (hw.s0 * hw.s0), hw.s0)
+        g1 = self._lin(layers[1].view(B * P, -1), hw.act_up1)
+        layers[1] = ops.pixel_shuffle(g1, B, gh, gw, hw.act_up1.N // (hw.s1 * hw.s1), hw.s1)
+        layers[3] = self._conv(layers[3], hw.act_down3, 3, stride=2, pad=1)
+        layers = [self._conv(layers[i], hw.layer_rn[i], 3, pad=1) for i in range(4)]
+        p4 = self._fusion(hw.refine[3], layers[3])
+        p3 = self._fusion(hw.refine[2], p4, layers[2])
+        p2 = self._fusion(hw.refine[1], p3, layers[1])
+        p1 = self._fusion(hw.refine[0], p2, layers[0])
+        return p1
+
+    def _center_head(self, hw, toks, B, N, gh, gw, means_out, v):
+        p1 = self._dpt_trunk(hw, toks, B, N, gh, gw)
+        x = self._conv(p1, hw.head0, 3, pad=1)
+        n, h, w_, c = x.shape
+        x = ops.resize_bilinear(x, 2 * h, 2 * w_, True)
+        x = self._conv(x, hw.head2, 3, pad=1, act=ACT_RELU)
+        S0, S1 = 2 * h, 2 * w_
+        xyz = torch.empty(B * S0 * S1, 4, device=self.dev)
+        self._lin(x.view(-1, x.shape[-1]), hw.head4, out=xyz[:, :3])
+        for b in range(B):  # pts3d written straight into Gaussians.means[b, v]
+            ops._lib.check(ops._lib.load().siu3r_depth_exp(xyz[b * S0 * S1:].data_ptr(), 4, means_out[b, v].data_ptr(), S0 * S1, ops._stream()),
+                           "depth_exp")
+
+    def _gs_head(self, hw, toks, img4, B, N, gh, gw):
+        """-> raw Gaussian parameters [B, S*S, 83] (model.py:195-210)."""
+        p1 = self._dpt_trunk(hw, toks, B, N, gh, gw)
+        n, h, w_, c = p1.shape
+        up = ops.resize_bilinear(p1, 2 * h, 2 * w_, True)
+        s = self._conv(img4, hw.merger, 7, pad=3, act=ACT_RELU, residual=up)
+        t = self._conv(s, hw.head0, 3, pad=1, act=ACT_RELU)
+        raw = torch.empty(B, 4 * h * w_, 83, device=self.dev)
+        self._lin(t.view(-1, 256), hw.head4, out=raw.view(-1, 83))
+        return raw
+
+    # ---- ViT adapter (vit_adapter/vit_adapter.py:393-441) ---------------------------------------------------------------
+    def _extractor(self, ex, c, featn_src, k, B, N, P, gh, gw):
+        """c [B*Lq, 1024] updated in place; featn_src: [B*N, 1024] encoder block output (token rows incl. the intrinsics token)."""
+        C = 1024
+        Lq = c.shape[0] // B
+        qn = ops.layernorm(c, ex.qn[0], ex.qn[1], 1e-6)
+        fn = torch.empty(B * P, C, device=self.dev)
+        for b in range(B):
+            ops.layernorm(featn_src[b * N: b * N + P], ex.fn[0], ex.fn[1], 1e-6, out=fn[b * P:(b + 1) * P])
+        value = self._lin(fn, ex.value)
+        ow = self._lin(qn, ex.ow)
+        samp = torch.empty(B * Lq, C, device=self.dev)
+        ops.msdeform_attn(value, P, ow, k.ad_ref, [(gh, gw)], 4, B, Lq, 16, 64, samp)
+        self._lin(samp, ex.out, residual=c, out=c)
+        t = ops.layernorm(c, ex.ffn_norm[0], ex.ffn_norm[1], 1e-6)
+        t1 = self._lin(t, ex.fc1)  # [B*Lq, 256]
+        dw = torch.empty_like(t1)
+        n = Lq // 21
+        off = 0
+        for (hh, ww, cnt) in ((2 * gh, 2 * gw, 16 * n), (gh, gw, 4 * n), (gh // 2, gw // 2, Lq - 20 * n)):
+            ops.dwconv3x3(t1.data_ptr() + 4 * off * 256, 256, Lq * 256, B, hh, ww, 256, ex.dw, ex.db, dw.data_ptr() + 4 * off * 256, 256, Lq * 256, True)
+            off += cnt
+        self._lin(dw, ex.fc2, residual=c, out=c)
+
+    def _adapter(self, img4, feats, k, B, N, gh, gw, out_slots, v):
+        """img4 [B,S0,S1,4]; feats: {block idx: [2B*N, 1024]} -> writes f1..f4 of view v into out_slots[l][b*2+v]."""
+        a = self.w.adapter
+        P = gh * gw
+        x = self._conv(img4, a.stem[0], 3, stride=2, pad=1, act=ACT_RELU)
+        x = self._conv(x, a.stem[1], 3, pad=1, act=ACT_RELU)
+        x = self._conv(x, a.stem[2], 3, pad=1, act=ACT_RELU)
+        c1 = ops.maxpool3x3s2(x)                                           # [B, S/4, S/4, 64]
+        c2 = self._conv(c1, a.conv2, 3, stride=2, pad=1, act=ACT_RELU)     # S/8, 128
+        c3 = self._conv(c2, a.conv3, 3, stride=2, pad=1, act=ACT_RELU)     # S/16, 256
+        c4 = self._conv(c3, a.conv4, 3, stride=2, pad=1, act=ACT_RELU)     # S/32, 256
+        c1 = self._conv(c1, a.fc1, 1)                                      # [B, S/4, S/4, 1024]
+        n2, n3, n4 = 4 * P, P, P // 4
+        Lq = n2 + n3 + n4
+        c = torch.empty(B, Lq, 1024, device=self.dev)
+        for b in range(B):  # fc2..4 (+ level embed folded into the bias) written straight into the concatenated query buffer
+            self._lin(c2[b].view(n2, -1), a.fc[0], out=c[b, :n2])
+            self._lin(c3[b].view(n3, -1), a.fc[1], out=c[b, n2:n2 + n3])
+            self._lin(c4[b].view(n4, -1), a.fc[2], out=c[b, n2 + n3:])
+        c = c.view(B * Lq, 1024)
+        for i, exs in enumerate(a.inter):
+            src = feats[self.cfg.interaction_indexes[i]][v * B * N:(v + 1) * B * N]
+            for ex in exs:
+                self._extractor(ex, c, src, k, B, N, P, gh, gw)
+        c = c.view(B, Lq, 1024)
+        # c1 = up(c2) + c1
+        c2d = torch.empty(B, n2, 1024, device=self.dev)
+        for b in range(B):
+            ops.rows_affine(c[b, :n2], out=c2d[b])
+        g = self._lin(c2d.view(B * n2, 1024), a.up)
+        c1 = ops.pixel_shuffle(g, B, 2 * gh, 2 * gw, 1024, a.up_s, add=c1)
+        maps = [c1, c2d.view(B, 2 * gh, 2 * gw, 1024), None, None]
+        c3d = torch.empty(B, gh, gw, 1024, device=self.dev)
+        c4d = torch.empty(B, gh // 2, gw // 2, 1024, device=self.dev)
+        for b in range(B):
+            ops.rows_affine(c[b, n2:n2 + n3], out=c3d[b].view(n3, 1024))
+            ops.rows_affine(c[b, n2 + n3:], out=c4d[b].view(n4, 1024))
+        maps[2], maps[3] = c3d, c4d
+        # + bilinear-resized ViT features (align_corners=False), then eval-mode BatchNorm
+        for l, (scale_hw, idx) in enumerate(zip(((4 * gh, 4 * gw), (2 * gh, 2 * gw), (gh, gw), (gh // 2, gw // 2)), self.cfg.interaction_indexes)):
+            src = feats[idx][v * B * N:(v + 1) * B * N]
+            for b in range(B):
+                xb = src[b * N: b * N + P].view(1, gh, gw, 1024)
+                if l == 2:
+                    ops.eltwise(ELT_ADD, maps[l][b].view(P, 1024), xb.view(P, 1024).contiguous(), out=maps[l][b].view(P, 1024))
+                else:
+                    ops.resize_bilinear(xb, scale_hw[0], scale_hw[1], False, out=maps[l][b:b + 1], accumulate=True)
+                sc, sh = a.bn[l]
+                rows = scale_hw[0] * scale_hw[1]
+                ops.rows_affine(maps[l][b].view(rows, 1024), scale=sc, shift=sh, out=out_slots[l][b * 2 + v].view(rows, 1024))
+
+    # ---- Mask2Former (mask2former/video_seg_decoder.py:2072-2196, 1506-1575, 1204-1360) ---------------------------------
+    def _m2f(self, feats, k, B, S0, S1):
+        """feats: 4 maps [B*T, h, w, 1024] at strides 4/8/16/32 (frame index bt = b*T + t).  Returns class logits [B,100,21],
+        mask logits pixel-major [B*T, S0/4, S1/4, 100]."""
+        m = self.w.m2f
+        T, E, Q = 2, 256, self.cfg.num_queries
+        BT = B * T
+        lv = k.m2f_shapes
+        Ltot = sum(h * w for h, w in lv)
+        starts = [0, lv[0][0] * lv[0][1], lv[0][0] * lv[0][1] + lv[1][0] * lv[1][1]]
+        x = torch.empty(BT, Ltot, E, device=self.dev)
+        for i, f in enumerate((feats[3], feats[2], feats[1])):  # features[::-1][:3]
+            cw, gw_, gb_ = m.in_proj[i]
+            h, w_ = lv[i]
+            e = self._conv(f, cw, 1)
+            e = ops.groupnorm(e.view(BT, h * w_, E), 32, gw_, gb_, 1e-5, False)
+            for bt in range(BT):
+                ops.rows_affine(e[bt], out=x[bt, starts[i]:starts[i] + h * w_])
+        x = x.view(BT * Ltot, E)
+        for lyr in m.enc:
+            q = ops.eltwise(ELT_ADD, x, k.m2f_pos)
+            value = self._lin(x, lyr.value)
+            ow = self._lin(q, lyr.ow)
+            samp = torch.empty(BT * Ltot, E, device=self.dev)
+            ops.msdeform_attn(value, Ltot, ow, k.m2f_ref, lv, 4, BT, Ltot, 8, 32, samp)
+            y = self._lin(samp, lyr.out, residual=x)
+            x = ops.layernorm(y, lyr.ln1[0], lyr.ln1[1], 1e-5)
+            f1 = self._lin(x, lyr.fc1, act=ACT_RELU)
+            y = self._lin(f1, lyr.fc2, residual=x)
+            x = ops.layernorm(y, lyr.ln2[0], lyr.ln2[1], 1e-5)
+        x = x.view(BT, Ltot, E)
+        # FPN level (stride 4)
+        h4, w4 = S0 // 4, S1 // 4
+        cw, gw_, gb_ = m.lateral
+        cur = ops.groupnorm(self._conv(feats[0], cw, 1).view(BT, h4 * w4, E), 32, gw_, gb_, 1e-5, False).view(BT, h4, w4, E)
+        h2, w2 = lv[2]
+        for bt in range(BT):
+            ops.resize_bilinear(x[bt, starts[2]:].view(1, h2, w2, E), h4, w4, False, out=cur[bt:bt + 1], accumulate=True)
+        cw, gw_, gb_ = m.output
+        o = self._conv(cur, cw, 3, pad=1)
+        o = ops.groupnorm(o.view(BT, h4 * w4, E), 32, gw_, gb_, 1e-5, True).view(BT, h4, w4, E)
+        mask_feat = self._conv(o, m.mask_proj, 1)  # [BT, h4, w4, 256]
+        self._cap("m2f_mask_features", mask_feat)
+        self._cap("m2f_tokens", x)
+        # transformer module: keys of level i for batch b = frames (t) x pixels, + level embedding
+        src, srcpos = [], []
+        for i, (h, w_) in enumerate(lv):
+            n = h * w_
+            s = torch.empty(B, T * n, E, device=self.dev)
+            for b in range(B):
+                for t in range(T):
+                    ops.rows_affine(x[b * T + t, starts[i]:starts[i] + n], shift=k.tm_lvl[i], out=s[b, t * n:(t + 1) * n])
+            s = s.view(B * T * n, E)
+            src.append(s)
+            srcpos.append(ops.eltwise(ELT_ADD, s, k.tm_pos[i]))
+        hidden, qpos = k.hidden0, k.qpos
+        mf = mask_feat.view(B, T * h4 * w4, E)
+
+        def predict(hid, target_hw):
+            inter = ops.layernorm(hid, m.dec_ln[0], m.dec_ln[1], 1e-5)
+            e = self._lin(inter, m.mask_mlp[0], act=ACT_RELU)
+            e = self._lin(e, m.mask_mlp[1], act=ACT_RELU)
+            e = self._lin(e, m.mask_mlp[2])  # [B*Q, 256]
+            logits = torch.empty(B, T * h4 * w4, Q, device=self.dev)
+            for b in range(B):  # einsum("bqc,btchw->bqthw") as a per-batch GEMM, pixel-major output
+                wq = ops.Weight(e[b * Q:(b + 1) * Q], None, self.prec)
+                self._lin(mf[b], wq, out=logits[b])
+            amask = None
+            if target_hw is not None:
+                amask = ops.attn_mask_from_logits(logits, B, T, h4, w4, Q, target_hw[0], target_hw[1])
+            return inter, logits, amask
+
+        inter, logits, amask = predict(hidden, lv[0])
+        nh = 8
+        for idx, lyr in enumerate(m.dec):
+            li = idx % 3
+            n = lv[li][0] * lv[li][1] * T
+            # masked cross-attention (post-norm)
+            qin = ops.eltwise(ELT_ADD, hidden, qpos)
+            qh = self._lin(qin, lyr.cq)
+            kh = self._lin(srcpos[li], lyr.ck)
+            vh = self._lin(src[li], lyr.cv)
+            att = torch.empty(B * Q, E, device=self.dev)
+            ops.attn_small_d32(qh, Q * E, E, kh, n * E, E, vh, n * E, E, att, Q * E, E, amask, B, nh, Q, n, 32 ** -0.5)
+            y = self._lin(att, lyr.cout, residual=hidden)
+            hidden = ops.layernorm(y, lyr.cln[0], lyr.cln[1], 1e-5)
+            # query self-attention
+            qin = ops.eltwise(ELT_ADD, hidden, qpos)
+            qk = self._lin(qin, lyr.sqk)          # [B*Q, 512] = [q | k]
+            vv = self._lin(hidden, lyr.sv)
+            att = torch.empty(B * Q, E, device=self.dev)
+            ops.attn_small_d32(qk, Q * 2 * E, 2 * E, qk[:, E:], Q * 2 * E, 2 * E, vv, Q * E, E, att, Q * E, E, None, B, nh, Q, Q, 32 ** -0.5)
+            y = self._lin(att, lyr.sout, residual=hidden)
+            hidden = ops.layernorm(y, lyr.sln[0], lyr.sln[1], 1e-5)
+            # FFN
+            f1 = self._lin(hidden, lyr.fc1, act=ACT_RELU)
+            y = self._lin(f1, lyr.fc2, residual=hidden)
+            hidden = ops.layernorm(y, lyr.fln[0], lyr.fln[1], 1e-5)
+            last = idx == len(m.dec) - 1
+            inter, logits, amask = predict(hidden, None if last else lv[(idx + 1) % 3])
+        cls = self._lin(inter, m.cls)  # [B*Q, 21]
+        return cls.view(B, Q, -1), logits.view(B * T, h4, w4, Q)
+
+    # ---- panoptic post-process (image_processing_video_mask2former.py:1238-1481, model.py:231-312) ------------------------
+    def _post_process(self, cls_logits, mask_logits, B, S0, S1, lift):
+        cfg = self.cfg
+        T, Q = 2, cfg.num_queries
+        num_labels = cls_logits.shape[-1] - 1
+        h4, w4 = mask_logits.shape[1], mask_logits.shape[2]
+        probs256 = ops.eltwise(ELT_SIGMOID, ops.resize_bilinear(mask_logits, 256, 256, False))  # [B*T,256,256,Q] (:1298-1312)
+        # tiny host-side decision data: class probabilities of 100 queries
+        cp = torch.softmax(cls_logits.detach().float().cpu(), dim=-1)
+        scores_all, labels_all = cp.max(-1)
+        fuse = set(cfg.label_ids_to_fuse)
+        seg_masks, seg_infos, qc_list, qscore_list = [], [], [], []
+        sem_all = torch.zeros(B, T, S0, S1, dtype=torch.int32, device=self.dev)
+        inst_all = torch.zeros(B, T, S0, S1, dtype=torch.int32, device=self.dev)
+        for b in range(B):
+            keep = (labels_all[b] != num_labels) & (scores_all[b] > cfg.seg_threshold)
+            kidx = torch.nonzero(keep).flatten()
+            if kidx.numel() == 0:
+                seg_masks.append(torch.zeros(T, S0, S1, device=self.dev) - 1)
+                seg_infos.append([])
+                qc = torch.zeros(T * S0 * S1, 1, num_labels + 1, device=self.dev)
+                qc[:, 0, -1] = 1
+                qc_list.append(qc)
+                qscore_list.append([0.0])
+                continue
+            kscore = scores_all[b][kidx].contiguous()
+            klabel = labels_all[b][kidx]
+            sel = ops.resize_select(probs256[b * T:(b + 1) * T], kidx.to(torch.int32).to(self.dev), S0, S1)  # [T,S0,S1,qk]
+            labels, area, orig = ops.argmax_area(sel, kscore.to(self.dev), 0.5)
+            area_h, orig_h = area.cpu(), orig.cpu()
+            segments, keep_q, keep_scores = [], [], []
+            seg_lut = torch.zeros(kidx.numel(), dtype=torch.int32)
+            sem_lut = torch.zeros(kidx.numel(), dtype=torch.int32)
+            current, stuff_memory = 0, {}
+            for j in range(kidx.numel()):
+                pred_class = int(klabel[j])
+                should_fuse = pred_class in fuse
+                a_k, a_o = int(area_h[j]), int(orig_h[j])
+                exists = a_k > 0 and a_o > 0
+                if exists and not (torch.tensor(a_k) / torch.tensor(a_o)).item() > 0.8:
+                    exists = False
+                if not exists:
+                    continue
+                if pred_class in stuff_memory:
+                    fuse_id = stuff_memory[pred_class]
+                else:
+                    current += 1
+                    fuse_id = current
+                sid = fuse_id if should_fuse else current
+                score = round(float(kscore[j]), 6)
+                segments.append({"id": sid, "label_id": pred_class, "was_fused": should_fuse, "score": score})
+                seg_lut[j] = sid
+                sem_lut[j] = pred_class + 1
+                keep_q.append(j)
+                keep_scores.append(score)
+                if should_fuse and pred_class not in stuff_memory:
+                    stuff_memory[pred_class] = current
+            seg = ops.label_lut(labels, seg_lut.to(self.dev), sem_lut.to(self.dev), sem_out=sem_all[b], inst_out=inst_all[b])
+            seg_masks.append(seg.view(T, S0, S1))
+            seg_infos.append(segments)
+            if keep_q:
+                kq = torch.tensor(keep_q, dtype=torch.int32, device=self.dev)
+                qc = ops.qc_logits(sel, kq, cp[b][kidx][keep_q].contiguous().to(self.dev)) if lift else None
+            else:  # (:1468-1472) note the reference uses the *mask-logit* height/width here
+                qc = torch.zeros(T, 1, num_labels + 1, h4, w4, device=self.dev)
+                qc[:, 0, -1] = 1
+                qc = qc.permute(0, 3, 4, 1, 2).reshape(T * h4 * w4, 1, num_labels + 1)
+            qc_list.append(qc)
+            qscore_list.append(keep_scores)
+        return seg_masks, seg_infos, qc_list, qscore_list, sem_all.view(B, -1), inst_all.view(B, -1)
+
+    # ---- forward --------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, context_views_images, context_views_intrinsics, mask_labels=None, class_labels=None, enable_query_class_logit_lift=False):
+        assert self._ready, "call load_state_dict(...).cuda() first"
+        assert mask_labels is None and class_labels is None, "training losses are out of scope (SURVEY.md section 8)"
+        imgs = context_views_images
+        B, V, _, S0, S1 = imgs.shape
+        assert V == 2, "two-view path; the V-view model is SIU3RMultiViewModel (next)"
+        assert S0 % 16 == 0 and S1 % 16 == 0, f"Input image size ({S0}x{S1}) is not a multiple of patch size (16)."
+        assert (S0, S1) == tuple(self.cfg.image_size), "model was built for a different image_size (vit_adapter.py:328-329)"
+        w, c = self.w, self.cfg
+        k = self._consts(B, S0, S1)
+        gh, gw = S0 // 16, S1 // 16
+        P, N = gh * gw, gh * gw + 1
+        Bn = 2 * B
+        imgs = imgs.to(self.dev, torch.float32)
+        Kin = context_views_intrinsics.to(self.dev, torch.float32)
+        # view-major NHWC(4) images
+        img4 = torch.zeros(Bn, S0, S1, 4, device=self.dev)  # [2B, S0, S1, 4], 4th channel = 0
+        lib = ops._lib.load()
+        for v in range(2):
+            for b in range(B):
+                ops._lib.check(lib.siu3r_nchw_to_nhwc(imgs[b, v].contiguous().data_ptr(), img4[v * B + b].data_ptr(), 1, 3, S0 * S1, 4, ops._stream()),
+                               "nchw_to_nhwc")
+        # ---- encoder input: patch tokens + intrinsics token ----
+        x = torch.empty(Bn, N, 1024, device=self.dev)
+        cols = torch.empty(Bn * P, 1024, device=self.dev)
+        ops._lib.check(ops._lib.load().siu3r_im2col_nhwc(img4.data_ptr(), Bn, S0, S1, 4, 16, 16, 16, 0, cols.data_ptr(), 1024, ops._stream()), "im2col")
+        for i in range(Bn):
+            self._lin(cols[i * P:(i + 1) * P], w.patch, out=x[i, :P])
+        x = x.view(Bn * N, 1024)
+        Kflat = Kin.contiguous().view(B, 18)
+        for v in range(2):  # intrinsics token = Linear(9 -> 1024) on the flattened K (backbone_croco.py:278-280)
+            ops.gemm_simt(Kflat[:, 9 * v: 9 * v + 9], w.intr_w, w.intr_b, out=x[v * B * N + P:: N][:B])
+        x, keep = self._encoder(x, k.pos_enc, Bn, N)
+        feat = ops.layernorm(x, w.enc_norm[0], w.enc_norm[1], 1e-6)  # [2B*N, 1024]
+        self._cap("enc_norm", feat)
+        # ---- decoder ----
+        f = self._lin(feat, w.dec_embed)  # [2B*N, 768]
+        f1, f2 = f[:B * N], f[B * N:]
+        dec1, dec2 = [feat[:B * N]], [feat[B * N:]]
+        for l in range(c.dec_depth):
+            n1 = self._dec_block(w.dec[0][l], f1, f2, k.pos_dec, B, N)
+            n2 = self._dec_block(w.dec[1][l], f2, f1, k.pos_dec, B, N)
+            f1, f2 = n1, n2
+            dec1.append(f1)
+            dec2.append(f2)
+            self._cap(f"dec1_{l}", f1)
+            self._cap(f"dec2_{l}", f2)
+        dec1[-1] = ops.layernorm(dec1[-1], w.dec_norm[0], w.dec_norm[1], 1e-6)
+        dec2[-1] = ops.layernorm(dec2[-1], w.dec_norm[0], w.dec_norm[1], 1e-6)
+        # ---- adapter (per view) -> multi-scale features [B*T, h, w, 1024] ----
+        shapes = [(S0 // 4, S1 // 4), (S0 // 8, S1 // 8), (S0 // 16, S1 // 16), (S0 // 32, S1 // 32)]
+        ms = [torch.empty(B * 2, h, w_, 1024, device=self.dev) for (h, w_) in shapes]
+        for v in range(2):
+            self._adapter(img4[v * B:(v + 1) * B], keep, k, B, N, gh, gw, ms, v)
+        self._cap("adapter_ms", ms)
+        # ---- Gaussian heads ----
+        G1 = S0 * S1
+        means = torch.empty(B, 2, G1, 3, device=self.dev)
+        hooks = [0, c.dec_depth * 2 // 4, c.dec_depth * 3 // 4, c.dec_depth]
+        raws = []
+        for v, dec in enumerate((dec1, dec2)):
+            toks = [dec[hk] for hk in hooks]
+            self._center_head(w.heads[f"downstream_head{v + 1}"], toks, B, N, gh, gw, means, v)
+            raws.append(self._gs_head(w.heads[f"gaussian_param_head{v + 1}"], toks, img4[v * B:(v + 1) * B], B, N, gh, gw))
+        self._cap("gs_raw", raws)
+        cov = torch.empty(B, 2 * G1, 3, 3, device=self.dev)
+        harm = torch.empty(B, 2 * G1, 3, 25, device=self.dev)
+        opac = torch.empty(B, 2 * G1, device=self.dev)
+        scales = torch.empty(B, 2 * G1, 3, device=self.dev)
+        rots = torch.empty(B, 2 * G1, 4, device=self.dev)
+        for v in range(2):
+            for b in range(B):
+                o = v * G1
+                ops._lib.check(lib.siu3r_gaussian_adapter(raws[v][b].data_ptr(), G1, cov[b, o:].data_ptr(), harm[b, o:].data_ptr(), opac[b, o:].data_ptr(),
+                                                          scales[b, o:].data_ptr(), rots[b, o:].data_ptr(), ops._stream()), "gaussian_adapter")
+        gaussians = Gaussians(means=means.view(B, 2 * G1, 3), covariances=cov, harmonics=harm, opacities=opac, scales=scales, rotations=rots)
+        # ---- Mask2Former + post-process ----
+        cls_logits, mask_logits = self._m2f(ms, k, B, S0, S1)
+        h4, w4 = S0 // 4, S1 // 4
+        seg_output = SimpleNamespace(class_queries_logits=cls_logits,
+                                     masks_queries_logits=mask_logits.view(B, 2, h4, w4, -1).permute(0, 4, 1, 2, 3))
+        seg_masks, seg_infos, qc_list, qscores, sem, inst = self._post_process(cls_logits, mask_logits, B, S0, S1, enable_query_class_logit_lift)
+        gaussians.semantic_labels = sem
+        gaussians.instance_labels = inst
+        if enable_query_class_logit_lift:
+            gaussians.seg_query_class_logits = qc_list
+            return gaussians, seg_output, seg_masks, seg_infos, qscores
+        return gaussians, seg_output, seg_masks, seg_infos

@@ -333,13 +333,15 @@ def argmax_area(probs: torch.Tensor, score: torch.Tensor, thr: float):
     return labels, area, orig
 
 
-def label_lut(labels: torch.Tensor, seg_lut: torch.Tensor, sem_lut: torch.Tensor):
+def label_lut(labels: torch.Tensor, seg_lut: torch.Tensor, sem_lut: torch.Tensor, sem_out=None, inst_out=None):
     npix = labels.numel()
     seg = torch.empty(npix, device=labels.device, dtype=torch.int32)
-    sem = torch.empty_like(seg)
-    inst = torch.empty_like(seg)
+    ret_all = sem_out is None
+    sem = torch.empty_like(seg) if sem_out is None else sem_out
+    inst = torch.empty_like(seg) if inst_out is None else inst_out
+    assert sem.is_contiguous() and inst.is_contiguous() and sem.numel() == npix and inst.numel() == npix
     _lib.check(_lib.load().siu3r_label_lut(_p(labels), npix, _p(seg_lut), _p(sem_lut), _p(seg), _p(sem), _p(inst), _stream()), "label_lut")
-    return seg, sem, inst
+    return (seg, sem, inst) if ret_all else seg
 
 
 def qc_logits(probs: torch.Tensor, keep: torch.Tensor, cls: torch.Tensor):

@@ -1,0 +1,147 @@
+"""End-to-end parity of siu3r_b200.SIU3RModel against golden fixtures generated from the UNMODIFIED reference
+(oracle/make_golden.py, CPU fp32) with the same seeded weights and inputs.
+
+Tolerances (BASELINE.json north_star): Gaussian parameters 1e-3 abs, segmentation logits 1e-4 rel, labels exact.
+  * precision="fp32x3" (3xTF32 tensor-core mode) is held to those tolerances.
+  * precision="tf32" is the reference's own GPU numerics (allow_tf32 = True, croco/croco.py:13); fp32-CPU goldens can only be
+    matched to TF32 accuracy, so it is checked with the looser bounds written below.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _load(S):
+    path = os.path.join(GOLD, f"model_S{S}.npz")
+    if not os.path.exists(path):
+        pytest.skip(f"{path} missing")
+    z = np.load(path, allow_pickle=False)
+    return z, json.loads(str(z["meta"]))
+
+
+def _samples(t: torch.Tensor, n=2048):
+    t = t.contiguous().flatten()
+    i = torch.arange(min(n, t.numel()), dtype=torch.int64, device=t.device)
+    idx = (i * 2654435761 + 12345) % t.numel()
+    return t[idx].cpu().numpy()
+
+
+_MODELS = {}
+
+
+def _run(S, precision):
+    key = (S, precision)
+    if key in _MODELS:
+        return _MODELS[key]
+    from siu3r_b200 import synth
+    from siu3r_b200.model import ModelCfg, SIU3RModel
+    model = SIU3RModel(ModelCfg(image_size=(S, S)), precision=precision)
+    model.load_state_dict(synth.make_state_dict())
+    model.cuda()
+    model.capture = {}
+    img, K = synth.pair_inputs(1, 2, S)
+    out = model(img.cuda(), K.cuda(), enable_query_class_logit_lift=True)
+    torch.cuda.synchronize()
+    cap = dict(model.capture)
+    model.capture = None
+    _MODELS[key] = (out, cap)
+    return out, cap
+
+
+def _stage_tensors(out, cap, S):
+    """Our tensors re-expressed in the reference's layouts, keyed like the golden."""
+    g, seg_out, seg_masks, seg_infos, qscores = out
+    B, N = 1, (S // 16) ** 2 + 1
+    d = {}
+    for i in (5, 11, 17, 23):
+        d[f"enc{i}"] = cap[f"enc{i}"].view(2 * B, N, 1024)
+    d["enc_norm"] = cap["enc_norm"].view(2 * B, N, 1024)
+    for i in (0, 5, 11):
+        d[f"dec1_{i}"] = cap[f"dec1_{i}"].view(B, N, 768)
+        d[f"dec2_{i}"] = cap[f"dec2_{i}"].view(B, N, 768)
+    for v in range(2):
+        for l in range(4):
+            d[f"adapter_v{v}_f{l + 1}"] = cap["adapter_ms"][l][v::2].permute(0, 3, 1, 2)
+        d[f"gs_raw_{v + 1}"] = cap["gs_raw"][v].view(B, S, S, 83).permute(0, 3, 1, 2)
+        d[f"pts3d_{v + 1}"] = g.means.view(B, 2, S, S, 3)[:, v]
+    mf = cap["m2f_mask_features"]
+    d["m2f_mask_features"] = mf.view(B, 2, S // 4, S // 4, 256).permute(0, 1, 4, 2, 3)
+    tok = cap["m2f_tokens"]  # [BT, Ltot, 256], levels low -> high resolution
+    off = 0
+    for j, hw in enumerate((S // 32, S // 16, S // 8)):
+        n = hw * hw
+        d[f"m2f_ms{j}"] = tok[:, off:off + n].reshape(B, 2, hw, hw, 256).permute(0, 1, 4, 2, 3)
+        off += n
+    d["class_queries_logits"] = seg_out.class_queries_logits
+    d["masks_queries_logits"] = seg_out.masks_queries_logits
+    for name in ("means", "covariances", "harmonics", "opacities", "scales", "rotations"):
+        d["g_" + name] = getattr(g, name)
+    return d
+
+
+def _check(S, precision, tol_stage, tol_gauss_abs, tol_logit_rel):
+    z, meta = _load(S)
+    out, cap = _run(S, precision)
+    d = _stage_tensors(out, cap, S)
+    report = []
+    for name, t in d.items():
+        ref = z[name + "__samples"]
+        assert list(t.shape) == meta[name]["shape"], (name, t.shape, meta[name]["shape"])
+        got = _samples(t)
+        err = np.abs(got - ref).max()
+        scale = meta[name]["absmax"]
+        report.append((name, err, err / max(scale, 1e-30)))
+    worst = {n: (e, r) for n, e, r in report}
+    msg = "\n".join(f"{n:28s} abs {e:.3e} rel {r:.3e}" for n, e, r in report)
+    print(f"\n[S={S} {precision}]\n{msg}")
+    for n, (e, r) in worst.items():
+        if n.startswith("g_") or n.startswith("pts3d"):
+            assert e < tol_gauss_abs, (n, e, msg)
+        elif n in ("class_queries_logits", "masks_queries_logits"):
+            assert r < tol_logit_rel, (n, r, msg)
+        else:
+            assert r < tol_stage, (n, r, msg)
+    return out, meta, z
+
+
+@pytest.mark.parametrize("S", [64, 256])
+def test_model_fp32x3_meets_north_star(S):
+    out, meta, z = _check(S, "fp32x3", tol_stage=2e-4, tol_gauss_abs=1e-3, tol_logit_rel=1e-4)
+    g, seg_out, seg_masks, seg_infos, qscores = out
+    # data-dependent panoptic branch: identical segments / scores / label maps
+    assert seg_infos == meta["seg_infos"], (seg_infos, meta["seg_infos"])
+    assert qscores == meta["query_scores"]
+    assert torch.bincount(g.semantic_labels.flatten().long(), minlength=22).tolist() == meta["sem_hist"]
+    assert torch.bincount(g.instance_labels.flatten().long()).tolist() == meta["inst_hist"]
+    sm = seg_masks[0]
+    assert list(sm.shape) == meta["seg_mask0"]["shape"]
+    assert np.array_equal(_samples(sm).astype(np.int64), z["seg_mask0__samples"].astype(np.int64))
+    qc = g.seg_query_class_logits[0]
+    assert list(qc.shape) == meta["qc0"]["shape"]
+    assert np.abs(_samples(qc) - z["qc0__samples"]).max() < 1e-4
+
+
+@pytest.mark.parametrize("S", [64, 256])
+def test_model_tf32_reference_gpu_numerics(S):
+    # TF32 mantissa = 10 bits: per-GEMM relative error ~5e-4; after 36 transformer layers + DPT stacks the
+    # reference's own TF32 GPU path sits at the same distance from its fp32 CPU path.
+    _check(S, "tf32", tol_stage=3e-2, tol_gauss_abs=5e-2, tol_logit_rel=3e-2)
+
+
+def test_model_rejects_bad_inputs():
+    from siu3r_b200 import synth
+    from siu3r_b200.model import ModelCfg, SIU3RModel
+    with pytest.raises(AssertionError):
+        SIU3RModel(ModelCfg(image_size=(60, 64)))
+    out, _ = _run(64, "tf32")
+    m = SIU3RModel(ModelCfg(image_size=(64, 64)))
+    with pytest.raises(AssertionError):
+        m(torch.zeros(1, 2, 3, 64, 64), torch.zeros(1, 2, 3, 3))  # not loaded
+    with pytest.raises(RuntimeError):
+        m.cuda()

@@ -1,0 +1,285 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the SIU3R hot path on B200 (contract: see the task statement / DESIGN.md section 6).
+
+  python bench.py --gpus N --steps K --warmup W            our arm (one process per GPU; torchrun for N > 1)
+  python bench.py --impl reference --gpus N ...            reference arm: the CPU implementation of the path on the host cores
+
+A "step" = one forward of the per-pair hot path (SIU3RModel.forward) over one batch of synthetic
+512x512 image pairs per GPU (BASELINE.json configs[1]: two-view 512x512 inference -> Gaussians + panoptic).
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "image_pairs_per_s_512x512"
+FLOPS_PER_PAIR_512 = 4.059e12  # algorithmic 2*MAC FLOPs of one 512^2 pair (FlopCounterMode on the reference)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", type=int, default=512)
+    ap.add_argument("--batch", type=int, default=1, help="image pairs per GPU per step")
+    ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32x3"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-raster", action="store_true")
+    ap.add_argument("--graph", type=int, default=1, help="replay the device part of the forward from a CUDA graph")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """Samples nvidia-smi SM clocks / throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_port_forward(size: int, batch: int, threads: int):
+    """One forward of the oracle's PyTorch port on the host cores (the only place bench.py executes oracle/)."""
+    from oracle import torch_port as TP
+    from siu3r_b200 import synth
+    torch.set_num_threads(threads)
+    sd = cpu_port_forward.sd if hasattr(cpu_port_forward, "sd") else synth.make_state_dict()
+    cpu_port_forward.sd = sd
+    img, K = synth.pair_inputs(batch, 2, size)
+    t0 = time.perf_counter()
+    TP.forward(sd, img, K, lift=True)
+    return time.perf_counter() - t0
+
+
+def run_reference(args, rank):
+    """Reference arm: the path's CPU implementation (oracle PyTorch port, kind="port": the reference's Python modules live
+    under /root/reference and do not exist on the GPU box) on all host cores.  Rank 0 only."""
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    for _ in range(min(args.warmup, 1)):
+        cpu_port_forward(args.size, 1, threads)
+    ts = [cpu_port_forward(args.size, 1, threads) for _ in range(args.steps)]
+    total = sum(ts)
+    v = args.steps / total
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1),
+            "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": f"two-view {args.size}x{args.size} inference -> Gaussians + panoptic (SIU3RModel.forward), 1 pair per step",
+                       "weights": "seeded random init of the reference architecture (655.5 M params)"},
+            "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": threads, "kind": "port",
+                             "sample": f"{args.steps} x one {args.size}x{args.size} pair, oracle/torch_port.py (torch CPU fp32)"},
+            "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    import torch.distributed as dist
+    from siu3r_b200 import ops, synth
+    from siu3r_b200.model import ModelCfg, SIU3RModel
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback exists for the product path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    S, B = args.size, args.batch
+    model = SIU3RModel(ModelCfg(image_size=(S, S)), precision=args.precision)
+    model.load_state_dict(synth.make_state_dict())
+    model.cuda()
+    img_h, K_h = synth.pair_inputs(B, 2, S, seed=rank)
+    img_pin, K_pin = img_h.pin_memory(), K_h.pin_memory()
+    img_d, K_d = img_pin.to(dev, non_blocking=True), K_pin.to(dev, non_blocking=True)
+    if args.graph:
+        model.enable_cuda_graph()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(steps):
+            fn()
+        e.record()
+        barrier()
+        ms = s.elapsed_time(e)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms
+
+    # ---- device-resident throughput (`value`) ----
+    step = lambda: model(img_d, K_d, enable_query_class_logit_lift=False)
+    for _ in range(args.warmup):
+        step()
+    clocks = ClockSampler(local)
+    clocks.start()
+    ops.reset_launch_count()
+    ms = timed(step, args.steps)
+    launches = ops.launch_count()
+    clk = clocks.stop()
+    value = world * B * args.steps / (ms / 1e3)
+
+    # ---- end to end through the public API with host buffers (`e2e`) ----
+    host_out = {}
+
+    def e2e_step():
+        g, seg, masks, infos = model(img_pin.to(dev, non_blocking=True), K_pin.to(dev, non_blocking=True))
+        for name in ("means", "covariances", "harmonics", "opacities", "scales", "rotations", "semantic_labels", "instance_labels"):
+            t = getattr(g, name)
+            if name not in host_out:
+                host_out[name] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            host_out[name].copy_(t, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(2):
+        e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+    e2e_v = world * B * args.steps / (ms_e2e / 1e3)
+    h2d = img_pin.numel() * 4 + K_pin.numel() * 4
+    d2h = sum(t.numel() * t.element_size() for t in host_out.values())
+
+    # ---- roofline of the dominant kernel family (instrumented pass, CUDA events on the launching stream) ----
+    model.disable_cuda_graph()
+    ops.PROFILE = []
+    step()
+    torch.cuda.synchronize()
+    fam = {}
+    for f, work, s, e in ops.PROFILE:
+        d = fam.setdefault(f, [0.0, 0.0, 0])
+        d[0] += s.elapsed_time(e); d[1] += work; d[2] += 1
+    ops.PROFILE = None
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    bf16_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained / 2 (TF32 rate = half the bf16 rate)" if peaks else "fallback 1.4 PF/s bf16 sustained / 2"
+    tf32_peak = bf16_peak / 2
+    dom = max(fam.items(), key=lambda kv: kv[1][0]) if fam else None
+    roofline = None
+    if dom:
+        name, (tms, work, n) = dom
+        ach = work / (tms / 1e3) / 1e12
+        roofline = {"kernel": name, "bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak,
+                    "traffic": None, "launches": n, "ms_per_launch": tms / n, "share_of_step_ms": tms, "peak_source": peak_src,
+                    "families": {k: {"ms": v[0], "tflops": v[1] / (v[0] / 1e3) / 1e12, "launches": v[2]} for k, v in fam.items()}}
+
+    line = {"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "tf32" if args.precision == "tf32" else "3xtf32", "data": "synthetic",
+            "config": {"workload": f"two-view {S}x{S} inference -> Gaussians + panoptic (SIU3RModel.forward), {B} pair(s) per GPU per step",
+                       "weights": "seeded random init of the reference architecture (655.5 M params)", "parallelism": f"dp{world}",
+                       "cuda_graph": bool(args.graph),
+                       "l2": "no explicit flush: weights (2.6 GB) + activations per step exceed the 126 MB L2 many times over"},
+            "clocks": clk,
+            "e2e": {"value": e2e_v, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches,
+            "vit_tensor_pipe_frac": value / world * FLOPS_PER_PAIR_512 * (S / 512.0) ** 2 / 1e12 / tf32_peak,
+            "roofline": roofline}
+
+    # ---- rasterizer sample (BASELINE config 5: 500k pixel-aligned Gaussians @512^2), HBM roofline ----
+    if not args.no_raster and rank == 0:
+        try:
+            line["raster"] = raster_bench(dev, peaks)
+        except Exception as ex:  # never lose the headline line
+            line["raster"] = {"error": repr(ex)}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        t = cpu_port_forward(S, 1, threads)
+        line["cpu_baseline"] = {"value": 1.0 / t, "unit": "pairs/s", "cores": threads, "kind": "port",
+                                "sample": f"1 x one {S}x{S} pair (no warm-up), oracle/torch_port.py (torch CPU fp32, restatement pinned to reference goldens)"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def raster_bench(dev, peaks):
+    from siu3r_b200 import ops, synth
+    from siu3r_b200.renderer import camera_matrices
+    G, H, W = 500000, 512, 512
+    sc = synth.raster_scene(G, H, W, seed=0, pixel_aligned=True)
+    view, full, campos, tx, ty = camera_matrices(sc["extrinsics"], sc["intrinsics"], sc["near"], sc["far"])
+    a = [sc[k].to(dev) for k in ("means", "covariances", "harmonics", "opacities")]
+    cam = [view[0].to(dev), full[0].to(dev), campos[0].to(dev), torch.zeros(3, device=dev)]
+    fn = lambda: ops.raster_forward(a[0], a[1], a[2], a[3], cam[0], cam[1], cam[2], cam[3], float(tx[0]), float(ty[0]), H, W, 4, sh_layout=1)
+    r = fn()
+    D = r["num_rendered"]
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 20
+    s.record()
+    for _ in range(n):
+        fn()
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / n
+    algo_bytes = 388.0 * G + 68.0 * D + 20.0 * H * W  # preprocess + binning/blend + output
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    return {"workload": f"{G} pixel-aligned Gaussians @ {H}x{W}, 1 camera", "fps": 1e3 / ms, "ms": ms, "duplicates": D,
+            "roofline": {"bound": "hbm", "achieved": algo_bytes / (ms / 1e3) / 1e9, "peak": hbm, "unit": "GB/s", "frac": algo_bytes / (ms / 1e3) / 1e9 / hbm,
+                         "traffic": None, "algorithmic_bytes": algo_bytes}}
+
+
+if __name__ == "__main__":
+    main()

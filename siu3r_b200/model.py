@@ -243,23 +243,26 @@ class SIU3RModel:
         return a
 
     def _encoder(self, x, pos, Bn, N):
-        """24 x Block (croco/blocks.py:127-130); x [Bn*N, 1024] is updated in place except at the kept blocks."""
+        """24 x Block (croco/blocks.py:127-130).  The residual stream is updated in place, except that the outputs of the
+        blocks the adapter reads (interaction_indexes) are frozen: the following block writes into a fresh buffer."""
         keep = {}
         C = 1024
+        frozen = False
         for i, blk in enumerate(self.w.enc):
             h = ops.layernorm(x, blk.n1[0], blk.n1[1], 1e-6)
             a = self._self_attn(h, blk, pos, Bn, N, C, 16)
-            self._lin(a, blk.proj, residual=x, out=x)
+            if frozen:
+                x = self._lin(a, blk.proj, residual=x)  # new buffer; the kept tensor stays intact
+                frozen = False
+            else:
+                self._lin(a, blk.proj, residual=x, out=x)
             h = ops.layernorm(x, blk.n2[0], blk.n2[1], 1e-6)
             f = self._lin(h, blk.fc1, act=ACT_GELU)
+            self._lin(f, blk.fc2, residual=x, out=x)
             if i in self.cfg.interaction_indexes:
-                xn = torch.empty_like(x)
-                self._lin(f, blk.fc2, residual=x, out=xn)
-                x = xn
                 keep[i] = x
+                frozen = True
                 self._cap(f"enc{i}", x)
-            else:
-                self._lin(f, blk.fc2, residual=x, out=x)
         return x, keep
 
     def _dec_block(self, blk, x, y, pos, B, N):
@@ -597,37 +600,36 @@ class SIU3RModel:
         return seg_masks, seg_infos, qc_list, qscore_list, sem_all.view(B, -1), inst_all.view(B, -1)
 
     # ---- forward --------------------------------------------------------------------------------------------------
-    @torch.no_grad()
-    def forward(self, context_views_images, context_views_intrinsics, mask_labels=None, class_labels=None, enable_query_class_logit_lift=False):
-        assert self._ready, "call load_state_dict(...).cuda() first"
-        assert mask_labels is None and class_labels is None, "training losses are out of scope (SURVEY.md section 8)"
-        imgs = context_views_images
+    def enable_cuda_graph(self):
+        """Replay the device part of forward() (everything up to the mask / class logits) from a CUDA graph: one capture per
+        (batch, image size).  The returned tensors then alias static buffers that the next forward() overwrites."""
+        self._use_graph = True
+        self._graphs = {}
+
+    def disable_cuda_graph(self):
+        self._use_graph = False
+
+    def _forward_device(self, imgs, Kin):
+        """All device work of SIU3RModel.forward up to (and excluding) the host-assisted panoptic post-process."""
         B, V, _, S0, S1 = imgs.shape
-        assert V == 2, "two-view path; the V-view model is SIU3RMultiViewModel (next)"
-        assert S0 % 16 == 0 and S1 % 16 == 0, f"Input image size ({S0}x{S1}) is not a multiple of patch size (16)."
-        assert (S0, S1) == tuple(self.cfg.image_size), "model was built for a different image_size (vit_adapter.py:328-329)"
         w, c = self.w, self.cfg
         k = self._consts(B, S0, S1)
         gh, gw = S0 // 16, S1 // 16
         P, N = gh * gw, gh * gw + 1
         Bn = 2 * B
-        imgs = imgs.to(self.dev, torch.float32)
-        Kin = context_views_intrinsics.to(self.dev, torch.float32)
-        # view-major NHWC(4) images
-        img4 = torch.zeros(Bn, S0, S1, 4, device=self.dev)  # [2B, S0, S1, 4], 4th channel = 0
+        img4 = torch.zeros(Bn, S0, S1, 4, device=self.dev)  # view-major NHWC, 4th channel = 0
         lib = ops._lib.load()
         for v in range(2):
             for b in range(B):
-                ops._lib.check(lib.siu3r_nchw_to_nhwc(imgs[b, v].contiguous().data_ptr(), img4[v * B + b].data_ptr(), 1, 3, S0 * S1, 4, ops._stream()),
-                               "nchw_to_nhwc")
+                ops._lib.check(lib.siu3r_nchw_to_nhwc(imgs[b, v].data_ptr(), img4[v * B + b].data_ptr(), 1, 3, S0 * S1, 4, ops._stream()), "nchw_to_nhwc")
         # ---- encoder input: patch tokens + intrinsics token ----
         x = torch.empty(Bn, N, 1024, device=self.dev)
         cols = torch.empty(Bn * P, 1024, device=self.dev)
-        ops._lib.check(ops._lib.load().siu3r_im2col_nhwc(img4.data_ptr(), Bn, S0, S1, 4, 16, 16, 16, 0, cols.data_ptr(), 1024, ops._stream()), "im2col")
+        ops._lib.check(lib.siu3r_im2col_nhwc(img4.data_ptr(), Bn, S0, S1, 4, 16, 16, 16, 0, cols.data_ptr(), 1024, ops._stream()), "im2col")
         for i in range(Bn):
             self._lin(cols[i * P:(i + 1) * P], w.patch, out=x[i, :P])
         x = x.view(Bn * N, 1024)
-        Kflat = Kin.contiguous().view(B, 18)
+        Kflat = Kin.view(B, 18)
         for v in range(2):  # intrinsics token = Linear(9 -> 1024) on the flattened K (backbone_croco.py:278-280)
             ops.gemm_simt(Kflat[:, 9 * v: 9 * v + 9], w.intr_w, w.intr_b, out=x[v * B * N + P:: N][:B])
         x, keep = self._encoder(x, k.pos_enc, Bn, N)
@@ -673,9 +675,45 @@ class SIU3RModel:
                 o = v * G1
                 ops._lib.check(lib.siu3r_gaussian_adapter(raws[v][b].data_ptr(), G1, cov[b, o:].data_ptr(), harm[b, o:].data_ptr(), opac[b, o:].data_ptr(),
                                                           scales[b, o:].data_ptr(), rots[b, o:].data_ptr(), ops._stream()), "gaussian_adapter")
-        gaussians = Gaussians(means=means.view(B, 2 * G1, 3), covariances=cov, harmonics=harm, opacities=opac, scales=scales, rotations=rots)
-        # ---- Mask2Former + post-process ----
         cls_logits, mask_logits = self._m2f(ms, k, B, S0, S1)
+        return means.view(B, 2 * G1, 3), cov, harm, opac, scales, rots, cls_logits, mask_logits
+
+    @torch.no_grad()
+    def forward(self, context_views_images, context_views_intrinsics, mask_labels=None, class_labels=None, enable_query_class_logit_lift=False):
+        assert self._ready, "call load_state_dict(...).cuda() first"
+        assert mask_labels is None and class_labels is None, "training losses are out of scope (SURVEY.md section 8)"
+        imgs = context_views_images
+        B, V, _, S0, S1 = imgs.shape
+        assert V == 2, "two-view path; the V-view model is SIU3RMultiViewModel (next)"
+        assert S0 % 16 == 0 and S1 % 16 == 0, f"Input image size ({S0}x{S1}) is not a multiple of patch size (16)."
+        assert (S0, S1) == tuple(self.cfg.image_size), "model was built for a different image_size (vit_adapter.py:328-329)"
+        if getattr(self, "_use_graph", False) and self.capture is None:
+            key = (B, S0, S1)
+            if key not in self._graphs:
+                si = torch.empty(B, 2, 3, S0, S1, device=self.dev)
+                sk = torch.empty(B, 2, 3, 3, device=self.dev)
+                si.copy_(imgs)
+                sk.copy_(context_views_intrinsics)
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    self._forward_device(si, sk)  # warm-up: builds host tables, sets kernel attributes
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    outs = self._forward_device(si, sk)
+                self._graphs[key] = (graph, si, sk, outs)
+            graph, si, sk, outs = self._graphs[key]
+            si.copy_(imgs, non_blocking=True)
+            sk.copy_(context_views_intrinsics, non_blocking=True)
+            graph.replay()
+        else:
+            imgs = imgs.to(self.dev, torch.float32).contiguous()
+            Kin = context_views_intrinsics.to(self.dev, torch.float32).contiguous()
+            outs = self._forward_device(imgs, Kin)
+        means, cov, harm, opac, scales, rots, cls_logits, mask_logits = outs
+        gaussians = Gaussians(means=means, covariances=cov, harmonics=harm, opacities=opac, scales=scales, rotations=rots)
         h4, w4 = S0 // 4, S1 // 4
         seg_output = SimpleNamespace(class_queries_logits=cls_logits,
                                      masks_queries_logits=mask_logits.view(B, 2, h4, w4, -1).permute(0, 4, 1, 2, 3))

@@ -20,6 +20,30 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+# Optional per-kernel-family timing (bench.py roofline pass): PROFILE = list -> (family, work, start_event, end_event)
+PROFILE = None
+
+
+class _Prof:
+    __slots__ = ("fam", "work", "s")
+
+    def __init__(self, fam, work):
+        self.fam, self.work = fam, work
+        self.s = None
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.s = torch.cuda.Event(enable_timing=True)
+            self.s.record()
+        return self
+
+    def __exit__(self, *a):
+        if self.s is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            PROFILE.append((self.fam, self.work, self.s, e))
+
+
 def _p(t):
     return None if t is None else t.data_ptr()
 
@@ -93,8 +117,9 @@ def gemm(x: torch.Tensor, wt: Weight, out: torch.Tensor | None = None, act: int 
         xc = x if x.is_contiguous() else x.contiguous()
         x_hi, x_lo = split_tf32(xc)
         x = x_hi
-    code = _lib.load().siu3r_gemm_tc(M, wt.N, K, _p(x), _p(x_lo), x.stride(0), _p(wt.w), _p(wt.w_lo), ldw, _p(out), out.stride(0), _p(b),
-                                     _p(residual), 0 if residual is None else residual.stride(0), act, alpha, precision, _stream())
+    with _Prof("gemm_tc", 2.0 * M * wt.N * K):
+        code = _lib.load().siu3r_gemm_tc(M, wt.N, K, _p(x), _p(x_lo), x.stride(0), _p(wt.w), _p(wt.w_lo), ldw, _p(out), out.stride(0), _p(b),
+                                         _p(residual), 0 if residual is None else residual.stride(0), act, alpha, precision, _stream())
     _lib.check(code, "gemm_tc")
     return out
 
@@ -137,8 +162,9 @@ def conv2d(x: torch.Tensor, wt: Weight, KH: int, KW: int, stride: int = 1, pad: 
         xx = x
         if precision == PREC_FP32X3:
             xx, x_lo = split_tf32(x)
-        code = _lib.load().siu3r_conv2d_tc(N, H, W, Cin, Cout, KH, KW, pad, _p(xx), _p(x_lo), _p(wt.w), _p(wt.w_lo), _p(out), Cout,
-                                           _p(wt.bias), _p(residual), Cout, act, precision, _stream())
+        with _Prof("conv2d_tc", 2.0 * N * H * W * Cout * KH * KW * Cin):
+            code = _lib.load().siu3r_conv2d_tc(N, H, W, Cin, Cout, KH, KW, pad, _p(xx), _p(x_lo), _p(wt.w), _p(wt.w_lo), _p(out), Cout,
+                                               _p(wt.bias), _p(residual), Cout, act, precision, _stream())
         _lib.check(code, "conv2d_tc")
         return out
     K = KH * KW * Cin
@@ -175,8 +201,9 @@ def rope2d_(tokens_ptr_tensor: torch.Tensor, offset: int, positions: torch.Tenso
 def flash_attn_d64(q: torch.Tensor, q_off: int, q_bs: int, q_ts: int, k: torch.Tensor, k_off: int, k_bs: int, k_ts: int, v: torch.Tensor,
                    v_off: int, v_bs: int, v_ts: int, out: torch.Tensor, B: int, H: int, Nq: int, Nk: int, scale: float, precision: int):
     """out [B, Nq, H*64] contiguous."""
-    code = _lib.load().siu3r_flash_attn_d64(q.data_ptr() + 4 * q_off, q_bs, q_ts, k.data_ptr() + 4 * k_off, k_bs, k_ts, v.data_ptr() + 4 * v_off,
-                                            v_bs, v_ts, _p(out), Nq * H * 64, H * 64, B, H, Nq, Nk, scale, precision, _stream())
+    with _Prof("flash_attn", 4.0 * B * H * Nq * Nk * 64):
+        code = _lib.load().siu3r_flash_attn_d64(q.data_ptr() + 4 * q_off, q_bs, q_ts, k.data_ptr() + 4 * k_off, k_bs, k_ts, v.data_ptr() + 4 * v_off,
+                                                v_bs, v_ts, _p(out), Nq * H * 64, H * 64, B, H, Nq, Nk, scale, precision, _stream())
     _lib.check(code, "flash_attn_d64")
     return out
 

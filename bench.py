@@ -83,6 +83,36 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def host_threads() -> int:
+    """Usable host threads: min(affinity mask, cgroup CPU quota) -- os.cpu_count() over-reports inside containers."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = min(n, max(1, int(float(q) / float(p))))
+    except Exception:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            p = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                n = min(n, max(1, q // p))
+        except Exception:
+            pass
+    # torch's CPU kernels stop scaling well beyond a few dozen threads on these shapes: probe a GEMM and keep the best
+    best, best_t = n, None
+    a = torch.randn(2048, 2048)
+    for cand in sorted({c for c in (8, 16, 32, 64, n) if c <= n}):
+        torch.set_num_threads(cand)
+        a @ a
+        t0 = time.perf_counter()
+        for _ in range(3):
+            a @ a
+        dt = time.perf_counter() - t0
+        if best_t is None or dt < best_t * 0.9:
+            best, best_t = cand, dt
+    return best
+
+
 def cpu_port_forward(size: int, batch: int, threads: int):
     """One forward of the oracle's PyTorch port on the host cores (the only place bench.py executes oracle/)."""
     from oracle import torch_port as TP
@@ -101,7 +131,7 @@ def run_reference(args, rank):
     under /root/reference and do not exist on the GPU box) on all host cores.  Rank 0 only."""
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = host_threads()
     for _ in range(min(args.warmup, 1)):
         cpu_port_forward(args.size, 1, threads)
     ts = [cpu_port_forward(args.size, 1, threads) for _ in range(args.steps)]
@@ -242,7 +272,7 @@ def main():
         except Exception as ex:  # never lose the headline line
             line["raster"] = {"error": repr(ex)}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
+        threads = host_threads()
         t = cpu_port_forward(S, 1, threads)
         line["cpu_baseline"] = {"value": 1.0 / t, "unit": "pairs/s", "cores": threads, "kind": "port",
                                 "sample": f"1 x one {S}x{S} pair (no warm-up), oracle/torch_port.py (torch CPU fp32, restatement pinned to reference goldens)"}

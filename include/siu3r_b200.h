@@ -10,6 +10,8 @@
  *     (message on stderr); no exceptions cross the ABI, no global state besides the launch counter;
  *   - `precision`: 1 = TF32 tensor-core math (the reference's own GPU mode: src/models/croco/croco.py:13),
  *                  3 = 3xTF32 split (fp32-grade accuracy on the tensor cores; needs *_lo planes from siu3r_split_tf32).
+ *   - `round_out` / act bit 4 / eltwise ops 7-8: the producer stores RN_tf32(value) because the tensor only feeds TF32
+ *     GEMM A operands (the tensor core itself would truncate, a -3.5e-4 relative bias per GEMM).
  *
  * Every entry point cites the reference interface it replaces (paths relative to /root/reference).
  */
@@ -68,11 +70,11 @@ int siu3r_rope2d(float* tokens, const int64_t* positions, int B, int N, int H, i
                  int64_t token_stride, float base, float fwd, void* stream);
 /* nn.LayerNorm over the last dim (+ optional fused add of `add` rows): croco/blocks.py:119-125,176-184 */
 int siu3r_layernorm(const float* x, int64_t ldx, const float* w, const float* b, float* y, int64_t ldy, int rows, int C,
-                    float eps, const float* add, int64_t ldadd, void* stream);
+                    float eps, const float* add, int64_t ldadd, int round_out, void* stream);
 /* softmax(Q K^T * scale) V, head dim 64: croco/blocks.py:105-109 (Attention), :162-166 (CrossAttention) */
 int siu3r_flash_attn_d64(const float* Q, int64_t q_bs, int64_t q_ts, const float* K, int64_t k_bs, int64_t k_ts,
                          const float* V, int64_t v_bs, int64_t v_ts, float* O, int64_t o_bs, int64_t o_ts, int B, int H,
-                         int Nq, int Nk, float scale, int precision, void* stream);
+                         int Nq, int Nk, float scale, int precision, int round_out, void* stream);
 /* masked / plain attention with head dim 32: mask2former/video_seg_decoder.py:975-983,994-999,1306-1308 */
 int siu3r_attn_small_d32(const float* Q, int64_t q_bs, int64_t q_ts, const float* K, int64_t k_bs, int64_t k_ts,
                          const float* V, int64_t v_bs, int64_t v_ts, float* O, int64_t o_bs, int64_t o_ts,
@@ -94,7 +96,7 @@ int siu3r_resize_bilinear_nhwc(const float* x, int N, int H, int W, int C, int64
 /* scatter half of nn.ConvTranspose2d(kernel = stride): heads/dpt_block.py:422-451; vit_adapter.py:356,425 */
 int siu3r_pixel_shuffle_nhwc(const float* g, int N, int H, int W, int C, int s, const float* add, float* y, void* stream);
 int siu3r_im2col_nhwc(const float* x, int N, int H, int W, int C, int KH, int KW, int stride, int pad, float* out,
-                      int64_t ldo, void* stream);
+                      int64_t ldo, int round_out, void* stream);
 int siu3r_nchw_to_nhwc(const float* x, float* y, int N, int C, int HW, int64_t ldy, void* stream);
 int siu3r_nhwc_to_nchw(const float* x, int64_t ldx, float* y, int N, int C, int HW, void* stream);
 int siu3r_maxpool3x3s2_nhwc(const float* x, int N, int H, int W, int C, float* y, void* stream);   /* vit_adapter.py:220 */

@@ -34,7 +34,7 @@ constexpr int UMMA_K = 8;       // tf32
 constexpr int NUM_THREADS = 192;
 constexpr int CONV_TW = 16, CONV_TH = 8;  // spatial patch of one M tile in conv mode
 
-enum Act { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2 };
+enum Act { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2, ACT_MASK = 3, ACT_ROUND_TF32 = 4 /* flag: store RN_tf32(result) */ };
 
 struct GemmParams {
     int M, N, num_kb;
@@ -144,6 +144,11 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
 }
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float rn_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
 
 template <int BN, int NSPLIT>
 struct Cfg {
@@ -153,7 +158,11 @@ struct Cfg {
     static constexpr int STAGE_BYTES = NOPER * (A_BYTES + B_BYTES);
     static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-    static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+    // 3xTF32: four accumulators (3 round-robin for hi*hi + 1 for the cross terms).  The tensor core truncates its fp32
+    // accumulator on every MMA, so the error grows with the number of MMAs chained into ONE accumulator; spreading the
+    // chain over several accumulators that are summed in registers (round-to-nearest) divides that error accordingly.
+    static constexpr int NACC = NSPLIT == 1 ? 1 : 4;
+    static constexpr int TMEM_COLS = NACC * BN < 32 ? 32 : NACC * BN;
 };
 
 template <int BN, int NSPLIT>
@@ -233,10 +242,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint32_t koff = k * UMMA_K * 4;
                     const uint32_t first = (kb | k) != 0;
                     if (NSPLIT == 3) {
-                        // small cross terms first, then the dominant hi*hi term
-                        umma_tf32(tmem_base, make_smem_desc(sA + C_::A_BYTES + koff), make_smem_desc(sB + koff), idesc, first);
-                        umma_tf32(tmem_base, make_smem_desc(sA + koff), make_smem_desc(sB + C_::B_BYTES + koff), idesc, 1u);
-                        umma_tf32(tmem_base, make_smem_desc(sA + koff), make_smem_desc(sB + koff), idesc, 1u);
+                        const int ks = kb * (BK / UMMA_K) + k;
+                        const uint32_t acc_hh = tmem_base + (uint32_t)((ks % 3) * BN);   // hi*hi: round-robin over 3 accumulators
+                        const uint32_t acc_x = tmem_base + (uint32_t)(3 * BN);           // lo*hi + hi*lo: 4th accumulator
+                        umma_tf32(acc_x, make_smem_desc(sA + C_::A_BYTES + koff), make_smem_desc(sB + koff), idesc, first);
+                        umma_tf32(acc_x, make_smem_desc(sA + koff), make_smem_desc(sB + C_::B_BYTES + koff), idesc, 1u);
+                        umma_tf32(acc_hh, make_smem_desc(sA + koff), make_smem_desc(sB + koff), idesc, ks >= 3 ? 1u : 0u);
                     } else {
                         umma_tf32(tmem_base, make_smem_desc(sA + koff), make_smem_desc(sB + koff), idesc, first);
                     }
@@ -250,6 +261,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ===================== epilogue (warps 2..5) =====================
         mbar_wait(acc_bar, 0);
         tcgen05_fence_after();
+        const int act = p.act & ACT_MASK;
+        const bool rnd = (p.act & ACT_ROUND_TF32) != 0;
         const int q = warp & 3;             // TMEM lane quarter this warp may access
         const int r = q * 32 + lane;        // row inside the tile
         int64_t row_off; bool row_ok; int64_t res_off = 0;
@@ -270,6 +283,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint32_t v[32];
             tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
             tmem_ld_wait();
+            if (NSPLIT == 3) {
+                const int nks = p.num_kb * (BK / UMMA_K);
+#pragma unroll
+                for (int a = 1; a < 4; ++a) {
+                    if (a < 3 && a >= nks) continue;  // hi*hi accumulator never written (K < 24)
+                    uint32_t t[32];
+                    tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN + c0), t);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(t[j]));
+                }
+            }
             if (!row_ok) continue;
             const int nbase = n0 + c0;
             if (nbase >= p.N) continue;
@@ -286,14 +311,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int e = 0; e < 4; ++e) {
                         float x = __uint_as_float(v[j + e]) * p.alpha;
                         if (p.bias) x += __ldg(p.bias + nbase + j + e);
-                        if (p.act == ACT_GELU) x = gelu_erf(x);
-                        else if (p.act == ACT_RELU) x = fmaxf(x, 0.0f);
+                        if (act == ACT_GELU) x = gelu_erf(x);
+                        else if (act == ACT_RELU) x = fmaxf(x, 0.0f);
                         of[e] = x;
                     }
                     if (rrow) {
                         const float4 rr = *reinterpret_cast<const float4*>(rrow + j);
                         o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
                     }
+                    if (rnd) { o.x = rn_tf32(o.x); o.y = rn_tf32(o.y); o.z = rn_tf32(o.z); o.w = rn_tf32(o.w); }
                     *reinterpret_cast<float4*>(crow + j) = o;
                 }
             } else {
@@ -302,10 +328,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (nbase + j >= p.N) break;
                     float x = __uint_as_float(v[j]) * p.alpha;
                     if (p.bias) x += __ldg(p.bias + nbase + j);
-                    if (p.act == ACT_GELU) x = gelu_erf(x);
-                    else if (p.act == ACT_RELU) x = fmaxf(x, 0.0f);
+                    if (act == ACT_GELU) x = gelu_erf(x);
+                    else if (act == ACT_RELU) x = fmaxf(x, 0.0f);
                     if (rrow) x += rrow[j];
-                    crow[j] = x;
+                    crow[j] = rnd ? rn_tf32(x) : x;
                 }
             }
         }
@@ -379,7 +405,7 @@ extern "C" {
 // C[M,N] (ldc) = act(alpha * A[M,K] (lda) @ W[N,K]^T (ldw) + bias[N]) + residual[M,N] (ldr)
 // fp32 storage; precision 1 = TF32, 3 = 3xTF32 (needs the *_lo planes: x = hi + lo with hi = tf32-rounded x).
 // Requirements: K % 4 == 0 handled by zero-filled TMA only if lda/ldw are multiples of 4 floats and all bases 16-byte aligned.
-// act: 0 none, 1 GELU(erf), 2 ReLU.  Replaces torch.nn.functional.linear (+ fused bias/activation/residual).
+// act: 0 none, 1 GELU(erf), 2 ReLU; +4 = store the result rounded to nearest TF32 (output only feeds TF32 GEMMs).  Replaces torch.nn.functional.linear (+ fused bias/activation/residual).
 int siu3r_gemm_tc(int M, int N, int K, const float* A, const float* A_lo, int64_t lda, const float* Wt, const float* W_lo, int64_t ldw,
                   float* C, int64_t ldc, const float* bias, const float* residual, int64_t ldr, int act, float alpha, int precision,
                   void* stream_) {

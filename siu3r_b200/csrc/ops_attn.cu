@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(FA_THREADS) flash_attn_d64_kernel(const float*
                                                                     const float* __restrict__ K, int64_t k_bs, int64_t k_ts,
                                                                     const float* __restrict__ V, int64_t v_bs, int64_t v_ts,
                                                                     float* __restrict__ O, int64_t o_bs, int64_t o_ts, int Nq, int Nk,
-                                                                    float scale) {
+                                                                    float scale, int round_out) {
     extern __shared__ __align__(16) float fa_smem[];
     float* sK = fa_smem;                          // [2][FA_BN][FA_LD]
     float* sV = fa_smem + 2 * FA_BN * FA_LD;      // [2][FA_BN][FA_LD]
@@ -166,6 +166,13 @@ __global__ void __launch_bounds__(FA_THREADS) flash_attn_d64_kernel(const float*
 
         // ---- O += P V.  The C-fragment of S is reused as the A-fragment of P by permuting the k index:
         //      k-slot t <-> key 2t, k-slot t+4 <-> key 2t+1 of each 8-key group (V rows are read in the same order). ----
+        // 3xTF32: the tile's P V product goes into a fresh accumulator that is then added in registers (round-to-nearest), so
+        // the tensor core's truncating accumulate never chains over more than one tile.
+        float pv[NSPLIT == 3 ? 8 : 1][4];
+        if constexpr (NSPLIT == 3) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { pv[i][0] = pv[i][1] = pv[i][2] = pv[i][3] = 0.f; }
+        }
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
             uint32_t ph[4], pl[4] = {0, 0, 0, 0};
@@ -180,11 +187,17 @@ __global__ void __launch_bounds__(FA_THREADS) flash_attn_d64_kernel(const float*
                 uint32_t b0h, b0l = 0, b1h, b1l = 0;
                 split<NSPLIT>(v0, b0h, b0l); split<NSPLIT>(v1, b1h, b1l);
                 if constexpr (NSPLIT == 3) {
-                    mma_tf32(o_acc[nt], pl, b0h, b1h);
-                    mma_tf32(o_acc[nt], ph, b0l, b1l);
+                    mma_tf32(pv[nt], pl, b0h, b1h);
+                    mma_tf32(pv[nt], ph, b0l, b1l);
+                    mma_tf32(pv[nt], ph, b0h, b1h);
+                } else {
+                    mma_tf32(o_acc[nt], ph, b0h, b1h);
                 }
-                mma_tf32(o_acc[nt], ph, b0h, b1h);
             }
+        }
+        if constexpr (NSPLIT == 3) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { o_acc[i][0] += pv[i][0]; o_acc[i][1] += pv[i][1]; o_acc[i][2] += pv[i][2]; o_acc[i][3] += pv[i][3]; }
         }
         __syncthreads();  // tile `buf` is overwritten by the prefetch issued in the next iteration
     }
@@ -193,8 +206,12 @@ __global__ void __launch_bounds__(FA_THREADS) flash_attn_d64_kernel(const float*
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
         const int c = nt * 8 + 2 * t;
-        if (row0 < Nq) *reinterpret_cast<float2*>(Ob + (int64_t)row0 * o_ts + c) = make_float2(o_acc[nt][0] * inv0, o_acc[nt][1] * inv0);
-        if (row1 < Nq) *reinterpret_cast<float2*>(Ob + (int64_t)row1 * o_ts + c) = make_float2(o_acc[nt][2] * inv1, o_acc[nt][3] * inv1);
+        float r0 = o_acc[nt][0] * inv0, r1 = o_acc[nt][1] * inv0, r2 = o_acc[nt][2] * inv1, r3 = o_acc[nt][3] * inv1;
+        if (round_out) {  // output feeds a TF32 GEMM only: round to nearest here instead of letting the tensor core truncate
+            r0 = __uint_as_float(f2tf32(r0)); r1 = __uint_as_float(f2tf32(r1)); r2 = __uint_as_float(f2tf32(r2)); r3 = __uint_as_float(f2tf32(r3));
+        }
+        if (row0 < Nq) *reinterpret_cast<float2*>(Ob + (int64_t)row0 * o_ts + c) = make_float2(r0, r1);
+        if (row1 < Nq) *reinterpret_cast<float2*>(Ob + (int64_t)row1 * o_ts + c) = make_float2(r2, r3);
     }
 }
 
@@ -351,7 +368,7 @@ extern "C" {
 // X + b*x_bs + n*x_ts + h*64 + d (so q/k/v can point into a fused qkv buffer).  precision: 1 = TF32, 3 = 3xTF32.
 int siu3r_flash_attn_d64(const float* Q, int64_t q_bs, int64_t q_ts, const float* K, int64_t k_bs, int64_t k_ts, const float* V,
                          int64_t v_bs, int64_t v_ts, float* O, int64_t o_bs, int64_t o_ts, int B, int H, int Nq, int Nk, float scale,
-                         int precision, void* stream_) {
+                         int precision, int round_out, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     SIU3R_REQUIRE(Q && K && V && O && B > 0 && H > 0 && Nq > 0 && Nk > 0);
     SIU3R_REQUIRE(precision == 1 || precision == 3);
@@ -365,9 +382,9 @@ int siu3r_flash_attn_d64(const float* Q, int64_t q_bs, int64_t q_ts, const float
     }
     dim3 grid(ceil_div(Nq, FA_BM), H, B);
     if (precision == 1)
-        flash_attn_d64_kernel<1><<<grid, FA_THREADS, FA_SMEM, stream>>>(Q, q_bs, q_ts, K, k_bs, k_ts, V, v_bs, v_ts, O, o_bs, o_ts, Nq, Nk, scale);
+        flash_attn_d64_kernel<1><<<grid, FA_THREADS, FA_SMEM, stream>>>(Q, q_bs, q_ts, K, k_bs, k_ts, V, v_bs, v_ts, O, o_bs, o_ts, Nq, Nk, scale, round_out);
     else
-        flash_attn_d64_kernel<3><<<grid, FA_THREADS, FA_SMEM, stream>>>(Q, q_bs, q_ts, K, k_bs, k_ts, V, v_bs, v_ts, O, o_bs, o_ts, Nq, Nk, scale);
+        flash_attn_d64_kernel<3><<<grid, FA_THREADS, FA_SMEM, stream>>>(Q, q_bs, q_ts, K, k_bs, k_ts, V, v_bs, v_ts, O, o_bs, o_ts, Nq, Nk, scale, round_out);
     SIU3R_LAUNCH_CHECK();
     siu3r_note_launch(1);
     return SIU3R_OK;

@@ -4,6 +4,12 @@
 
 namespace {
 
+__device__ __forceinline__ float rn_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // LayerNorm over the last dim: one warp per row, row cached in registers, two-pass (mean, then centred variance)
 // like ATen.  Replaces nn.LayerNorm in croco/blocks.py:119,123,176,180-184 (eps 1e-6, croco/croco.py:35),
@@ -12,7 +18,7 @@ namespace {
 template <int VEC_PER_LANE>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ w,
                                                         const float* __restrict__ b, float* __restrict__ y, int64_t ldy, int rows, int C,
-                                                        float eps, const float* __restrict__ add, int64_t ldadd) {
+                                                        float eps, const float* __restrict__ add, int64_t ldadd, int round_out) {
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -56,6 +62,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
             o.z = (v[i].z - mean) * rstd * ww.z + bb.z;
             o.w = (v[i].w - mean) * rstd * ww.w + bb.w;
             if (a4) { const float4 aa = a4[idx]; o.x += aa.x; o.y += aa.y; o.z += aa.z; o.w += aa.w; }
+            if (round_out) { o.x = rn_tf32(o.x); o.y = rn_tf32(o.y); o.z = rn_tf32(o.z); o.w = rn_tf32(o.w); }
             yr[idx] = o;
         }
     }
@@ -114,7 +121,7 @@ __global__ void __launch_bounds__(256) split_tf32_kernel(const float4* __restric
 // ------------------------------------------------------------------------------------------------------------
 // Elementwise family (vectorised float4, n % 4 == 0 enforced by the host wrapper; tails handled scalar)
 // ------------------------------------------------------------------------------------------------------------
-enum EltOp { ELT_RELU = 0, ELT_ADD = 1, ELT_ADD_RELU = 2, ELT_GELU = 3, ELT_COPY = 4, ELT_SIGMOID = 5, ELT_CLAMP01 = 6 };
+enum EltOp { ELT_RELU = 0, ELT_ADD = 1, ELT_ADD_RELU = 2, ELT_GELU = 3, ELT_COPY = 4, ELT_SIGMOID = 5, ELT_CLAMP01 = 6, ELT_RELU_RN = 7, ELT_ROUND = 8 };
 
 __device__ __forceinline__ float elt_apply(int op, float a, float b) {
     switch (op) {
@@ -124,6 +131,8 @@ __device__ __forceinline__ float elt_apply(int op, float a, float b) {
         case ELT_GELU: return 0.5f * a * (1.0f + erff(a * 0.70710678118654752440f));
         case ELT_SIGMOID: return 1.0f / (1.0f + expf(-a));
         case ELT_CLAMP01: return fminf(fmaxf(a, 0.f), 1.f);
+        case ELT_RELU_RN: return rn_tf32(fmaxf(a, 0.f));
+        case ELT_ROUND: return rn_tf32(a);
         default: return a;
     }
 }
@@ -211,7 +220,8 @@ __global__ void __launch_bounds__(256) resize_bilinear_kernel(const float* __res
     o.z = h0l * (w0l * v00.z + lw * v01.z) + lh * (w0l * v10.z + lw * v11.z);
     o.w = h0l * (w0l * v00.w + lw * v01.w) + lh * (w0l * v10.w + lw * v11.w);
     float4* yp = reinterpret_cast<float4*>(y + (((int64_t)n * OH + oh) * OW + ow) * ldy + c);
-    if (accumulate) { const float4 p = *yp; o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
+    if (accumulate & 1) { const float4 p = *yp; o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
+    if (accumulate & 2) { o.x = rn_tf32(o.x); o.y = rn_tf32(o.y); o.z = rn_tf32(o.z); o.w = rn_tf32(o.w); }
     *yp = o;
 }
 
@@ -238,7 +248,7 @@ __global__ void __launch_bounds__(256) pixel_shuffle_kernel(const float* __restr
 
 // im2col for NHWC input: out[(n,oh,ow), (kh,kw,ci)] (row stride ldo >= KH*KW*C, pad columns zeroed by caller's memset)
 __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ x, int N, int H, int W, int C, int KH, int KW, int stride, int pad,
-                                                     int OH, int OW, float* __restrict__ out, int64_t ldo) {
+                                                     int OH, int OW, float* __restrict__ out, int64_t ldo, int round_out) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int K = KH * KW * C;
     const int64_t total = (int64_t)N * OH * OW * ldo;
@@ -257,7 +267,7 @@ __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ x
         const int ih = oh * stride + kh - pad, iw = ow * stride + kw - pad;
         if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = x[(((int64_t)n * H + ih) * W + iw) * C + ci];
     }
-    out[idx] = v;
+    out[idx] = round_out ? rn_tf32(v) : v;
 }
 
 // NCHW <-> NHWC (images come in as [B,V,3,H,W], inference.py:117-118; outputs that the reference returns as NCHW)
@@ -391,7 +401,7 @@ inline unsigned grid_for(int64_t n, int threads = 256) { return (unsigned)((n + 
 extern "C" {
 
 int siu3r_layernorm(const float* x, int64_t ldx, const float* w, const float* b, float* y, int64_t ldy, int rows, int C, float eps,
-                    const float* add, int64_t ldadd, void* stream_) {
+                    const float* add, int64_t ldadd, int round_out, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     SIU3R_REQUIRE(x && w && b && y && rows > 0 && C > 0 && C % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0);
     SIU3R_REQUIRE(C <= 4096);
@@ -399,10 +409,10 @@ int siu3r_layernorm(const float* x, int64_t ldx, const float* w, const float* b,
     const int vpl = ceil_div(nvec, 32);
     const int wpb = 8;
     dim3 grid(ceil_div(rows, wpb));
-    if (vpl <= 2) layernorm_kernel<2><<<grid, wpb * 32, 0, stream>>>(x, ldx, w, b, y, ldy, rows, C, eps, add, ldadd);
-    else if (vpl <= 6) layernorm_kernel<6><<<grid, wpb * 32, 0, stream>>>(x, ldx, w, b, y, ldy, rows, C, eps, add, ldadd);
-    else if (vpl <= 8) layernorm_kernel<8><<<grid, wpb * 32, 0, stream>>>(x, ldx, w, b, y, ldy, rows, C, eps, add, ldadd);
-    else layernorm_kernel<32><<<grid, wpb * 32, 0, stream>>>(x, ldx, w, b, y, ldy, rows, C, eps, add, ldadd);
+    if (vpl <= 2) layernorm_kernel<2><<<grid, wpb * 32, 0, stream>>>(x, ldx, w, b, y, ldy, rows, C, eps, add, ldadd, round_out);
+    else if (vpl <= 6) layernorm_kernel<6><<<grid, wpb * 32, 0, stream>>>(x, ldx, w, b, y, ldy, rows, C, eps, add, ldadd, round_out);
+    else if (vpl <= 8) layernorm_kernel<8><<<grid, wpb * 32, 0, stream>>>(x, ldx, w, b, y, ldy, rows, C, eps, add, ldadd, round_out);
+    else layernorm_kernel<32><<<grid, wpb * 32, 0, stream>>>(x, ldx, w, b, y, ldy, rows, C, eps, add, ldadd, round_out);
     SIU3R_LAUNCH_CHECK();
     siu3r_note_launch(1);
     return SIU3R_OK;
@@ -429,10 +439,10 @@ int siu3r_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stre
     return SIU3R_OK;
 }
 
-// op: 0 relu(a), 1 a+b, 2 relu(a+b), 3 gelu(a), 4 copy, 5 sigmoid(a), 6 clamp(a, 0, 1)
+// op: 0 relu(a), 1 a+b, 2 relu(a+b), 3 gelu(a), 4 copy, 5 sigmoid(a), 6 clamp(a, 0, 1), 7 RN_tf32(relu(a)), 8 RN_tf32(a)
 int siu3r_eltwise(int op, const float* a, const float* b, float* out, int64_t n, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    SIU3R_REQUIRE(a && out && n > 0 && op >= 0 && op <= 6);
+    SIU3R_REQUIRE(a && out && n > 0 && op >= 0 && op <= 8);
     SIU3R_REQUIRE(((uintptr_t)a & 15) == 0 && ((uintptr_t)out & 15) == 0 && (!b || ((uintptr_t)b & 15) == 0));
     eltwise_kernel<<<grid_for(ceil_div_i64(n, 4)), 256, 0, stream>>>(op, a, b, out, n);
     SIU3R_LAUNCH_CHECK();
@@ -492,11 +502,11 @@ int siu3r_pixel_shuffle_nhwc(const float* g, int N, int H, int W, int C, int s, 
     return SIU3R_OK;
 }
 
-int siu3r_im2col_nhwc(const float* x, int N, int H, int W, int C, int KH, int KW, int stride, int pad, float* out, int64_t ldo, void* stream_) {
+int siu3r_im2col_nhwc(const float* x, int N, int H, int W, int C, int KH, int KW, int stride, int pad, float* out, int64_t ldo, int round_out, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     SIU3R_REQUIRE(x && out && N > 0 && stride >= 1 && ldo >= (int64_t)KH * KW * C);
     const int OH = (H + 2 * pad - KH) / stride + 1, OW = (W + 2 * pad - KW) / stride + 1;
-    im2col_kernel<<<grid_for((int64_t)N * OH * OW * ldo), 256, 0, stream>>>(x, N, H, W, C, KH, KW, stride, pad, OH, OW, out, ldo);
+    im2col_kernel<<<grid_for((int64_t)N * OH * OW * ldo), 256, 0, stream>>>(x, N, H, W, C, KH, KW, stride, pad, OH, OW, out, ldo, round_out);
     SIU3R_LAUNCH_CHECK();
     siu3r_note_launch(1);
     return SIU3R_OK;

@@ -12,7 +12,8 @@ import torch
 from . import _lib
 
 ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
-ELT_RELU, ELT_ADD, ELT_ADD_RELU, ELT_GELU, ELT_COPY, ELT_SIGMOID, ELT_CLAMP01 = 0, 1, 2, 3, 4, 5, 6
+ELT_RELU, ELT_ADD, ELT_ADD_RELU, ELT_GELU, ELT_COPY, ELT_SIGMOID, ELT_CLAMP01, ELT_RELU_RN, ELT_ROUND = 0, 1, 2, 3, 4, 5, 6, 7, 8
+ACT_ROUND_TF32 = 4  # flag OR-ed into `act`: store RN_tf32(result)
 PREC_TF32, PREC_FP32X3 = 1, 3
 
 
@@ -93,9 +94,20 @@ class Weight:
         self.bias = None if bias is None else bias.contiguous().float()
 
 
+def round_tf32(x: torch.Tensor) -> torch.Tensor:
+    """Round-to-nearest TF32 copy of x (the A operand of a TF32 GEMM whose producer could not round it itself)."""
+    xc = x if x.is_contiguous() else x.contiguous()
+    if xc.numel() % 4 != 0 or xc.data_ptr() % 16 != 0:
+        return xc
+    return eltwise(ELT_ROUND, xc)
+
+
 def gemm(x: torch.Tensor, wt: Weight, out: torch.Tensor | None = None, act: int = ACT_NONE, residual: torch.Tensor | None = None,
-         alpha: float = 1.0, precision: int = PREC_TF32, bias: torch.Tensor | None | bool = True, M: int | None = None) -> torch.Tensor:
-    """out[M,N] = act(alpha * x[M,K] @ W^T + bias) + residual.  x / out / residual are 2-D row-strided views."""
+         alpha: float = 1.0, precision: int = PREC_TF32, bias: torch.Tensor | None | bool = True, M: int | None = None,
+         a_rounded: bool = False, round_out: bool = False) -> torch.Tensor:
+    """out[M,N] = act(alpha * x[M,K] @ W^T + bias) + residual.  x / out / residual are 2-D row-strided views.
+    TF32 mode: the A operand must be round-to-nearest TF32 (a_rounded=True if its producer already did that);
+    round_out=True stores the result rounded because it only feeds further TF32 GEMMs."""
     _chk_f32(x, out, residual)
     assert x.dim() == 2 and x.stride(1) == 1
     M = x.shape[0] if M is None else M
@@ -117,6 +129,11 @@ def gemm(x: torch.Tensor, wt: Weight, out: torch.Tensor | None = None, act: int 
         xc = x if x.is_contiguous() else x.contiguous()
         x_hi, x_lo = split_tf32(xc)
         x = x_hi
+    else:
+        if not a_rounded:
+            x = round_tf32(x)
+        if round_out:
+            act = act | ACT_ROUND_TF32
     with _Prof("gemm_tc", 2.0 * M * wt.N * K):
         code = _lib.load().siu3r_gemm_tc(M, wt.N, K, _p(x), _p(x_lo), x.stride(0), _p(wt.w), _p(wt.w_lo), ldw, _p(out), out.stride(0), _p(b),
                                          _p(residual), 0 if residual is None else residual.stride(0), act, alpha, precision, _stream())
@@ -142,7 +159,8 @@ def conv2d_tc_supported(H: int, W: int, Cin: int) -> bool:
 
 
 def conv2d(x: torch.Tensor, wt: Weight, KH: int, KW: int, stride: int = 1, pad: int = 0, act: int = ACT_NONE,
-           residual: torch.Tensor | None = None, out: torch.Tensor | None = None, precision: int = PREC_TF32) -> torch.Tensor:
+           residual: torch.Tensor | None = None, out: torch.Tensor | None = None, precision: int = PREC_TF32, a_rounded: bool = False,
+           round_out: bool = False) -> torch.Tensor:
     """NHWC convolution.  wt is [Cout, KH*KW*Cin] ((kh, kw, ci) fastest = ci).  Stride-1 convs with tensor-core friendly
     shapes run as implicit GEMM (4-D TMA); everything else as im2col + tensor-core GEMM."""
     _chk_f32(x, residual, out)
@@ -155,13 +173,18 @@ def conv2d(x: torch.Tensor, wt: Weight, KH: int, KW: int, stride: int = 1, pad: 
         out = torch.empty(N, OH, OW, Cout, device=x.device, dtype=torch.float32)
     if KH == 1 and KW == 1 and stride == 1 and pad == 0:
         gemm(x.view(-1, Cin), wt, out=out.view(-1, Cout), act=act, residual=None if residual is None else residual.view(-1, Cout),
-             precision=precision)
+             precision=precision, a_rounded=a_rounded, round_out=round_out)
         return out
     if stride == 1 and conv2d_tc_supported(H, W, Cin) and OH == H and OW == W:
         x_lo = None
         xx = x
         if precision == PREC_FP32X3:
             xx, x_lo = split_tf32(x)
+        else:
+            if not a_rounded:
+                xx = round_tf32(x)
+            if round_out:
+                act = act | ACT_ROUND_TF32
         with _Prof("conv2d_tc", 2.0 * N * H * W * Cout * KH * KW * Cin):
             code = _lib.load().siu3r_conv2d_tc(N, H, W, Cin, Cout, KH, KW, pad, _p(xx), _p(x_lo), _p(wt.w), _p(wt.w_lo), _p(out), Cout,
                                                _p(wt.bias), _p(residual), Cout, act, precision, _stream())
@@ -170,21 +193,24 @@ def conv2d(x: torch.Tensor, wt: Weight, KH: int, KW: int, stride: int = 1, pad: 
     K = KH * KW * Cin
     ldo = wt.w.shape[1]
     cols = torch.empty(N * OH * OW, ldo, device=x.device, dtype=torch.float32)
-    code = _lib.load().siu3r_im2col_nhwc(_p(x), N, H, W, Cin, KH, KW, stride, pad, _p(cols), ldo, _stream())
+    rnd = 1 if precision == PREC_TF32 else 0  # the column matrix only feeds the GEMM: round it on the way out
+    code = _lib.load().siu3r_im2col_nhwc(_p(x), N, H, W, Cin, KH, KW, stride, pad, _p(cols), ldo, rnd, _stream())
     _lib.check(code, "im2col")
     assert K <= ldo
-    gemm(cols, wt, out=out.view(-1, Cout), act=act, residual=None if residual is None else residual.view(-1, Cout), precision=precision)
+    gemm(cols, wt, out=out.view(-1, Cout), act=act, residual=None if residual is None else residual.view(-1, Cout), precision=precision,
+         a_rounded=True, round_out=round_out)
     return out
 
 
-def layernorm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float, out: torch.Tensor | None = None, add: torch.Tensor | None = None):
+def layernorm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float, out: torch.Tensor | None = None, add: torch.Tensor | None = None,
+              round_out: bool = False):
     _chk_f32(x, w, b, out, add)
     assert x.dim() == 2 and x.stride(1) == 1
     rows, Cc = x.shape
     if out is None:
         out = torch.empty(rows, Cc, device=x.device, dtype=torch.float32)
     code = _lib.load().siu3r_layernorm(_p(x), x.stride(0), _p(w), _p(b), _p(out), out.stride(0), rows, Cc, eps, _p(add),
-                                       0 if add is None else add.stride(0), _stream())
+                                       0 if add is None else add.stride(0), 1 if round_out else 0, _stream())
     _lib.check(code, "layernorm")
     return out
 
@@ -199,11 +225,12 @@ def rope2d_(tokens_ptr_tensor: torch.Tensor, offset: int, positions: torch.Tenso
 
 
 def flash_attn_d64(q: torch.Tensor, q_off: int, q_bs: int, q_ts: int, k: torch.Tensor, k_off: int, k_bs: int, k_ts: int, v: torch.Tensor,
-                   v_off: int, v_bs: int, v_ts: int, out: torch.Tensor, B: int, H: int, Nq: int, Nk: int, scale: float, precision: int):
+                   v_off: int, v_bs: int, v_ts: int, out: torch.Tensor, B: int, H: int, Nq: int, Nk: int, scale: float, precision: int,
+                   round_out: bool = False):
     """out [B, Nq, H*64] contiguous."""
     with _Prof("flash_attn", 4.0 * B * H * Nq * Nk * 64):
         code = _lib.load().siu3r_flash_attn_d64(q.data_ptr() + 4 * q_off, q_bs, q_ts, k.data_ptr() + 4 * k_off, k_bs, k_ts, v.data_ptr() + 4 * v_off,
-                                                v_bs, v_ts, _p(out), Nq * H * 64, H * 64, B, H, Nq, Nk, scale, precision, _stream())
+                                                v_bs, v_ts, _p(out), Nq * H * 64, H * 64, B, H, Nq, Nk, scale, precision, 1 if round_out else 0, _stream())
     _lib.check(code, "flash_attn_d64")
     return out
 
@@ -255,7 +282,7 @@ def rows_affine(x, scale=None, shift=None, add=None, out=None, relu=False, rows=
 
 
 def resize_bilinear(x: torch.Tensor, OH: int, OW: int, align_corners: bool, out: torch.Tensor | None = None, accumulate: bool = False,
-                    ldx: int | None = None):
+                    ldx: int | None = None, round_out: bool = False):
     """x: [N,H,W,C] (pixel stride ldx, images densely packed H*W*ldx apart) -> out [N,OH,OW,C]."""
     _chk_f32(x, out)
     N, H, W, Cc = x.shape
@@ -263,7 +290,7 @@ def resize_bilinear(x: torch.Tensor, OH: int, OW: int, align_corners: bool, out:
     if out is None:
         out = torch.empty(N, OH, OW, Cc, device=x.device, dtype=torch.float32)
     code = _lib.load().siu3r_resize_bilinear_nhwc(_p(x), N, H, W, Cc, ldx, _p(out), OH, OW, out.stride(2), 1 if align_corners else 0,
-                                                  1 if accumulate else 0, _stream())
+                                                  (1 if accumulate else 0) | (2 if round_out else 0), _stream())
     _lib.check(code, "resize_bilinear")
     return out
 

@@ -114,7 +114,8 @@ def make_state_dict(shapes: dict | None = None, seed: int = 0) -> dict:
             if key.startswith("mask2former.class_predictor"):
                 gain = 12.0  # peaked class distribution -> scores > 0.5 for some queries
             if ".dpt.head.4." in key:
-                gain = 0.3  # keep ||xyz|| (argument of expm1) O(1)
+                # centre heads: keep ||xyz|| (the argument of expm1) ~1 so |means| stays in a room-scale range (< ~10)
+                gain = 0.12 if key.startswith("downstream") else 0.3
             if leaf in ("level_embed",) or "queries_" in key or "level_embed" in key:
                 gain = 1.0
             t = gain * torch.randn(shape, generator=g) / (fan_in ** 0.5)

@@ -113,7 +113,7 @@ def test_conv2d_im2col(cfg):
     y = ops.conv2d(x, wt, k, k, stride=s, pad=p, precision=3)
     ref = F.conv2d(x.permute(0, 3, 1, 2), w, b, stride=s, padding=p).permute(0, 2, 3, 1)
     assert y.shape == ref.shape
-    assert rel_err(y, ref) < 3e-5
+    assert rel_err(y, ref) < 1e-4  # K up to 6912: error grows with the MMA chain length (tools/acc_probe.py)
 
 
 def test_conv_transpose_as_gemm_pixel_shuffle():

@@ -635,9 +635,10 @@ class SIU3RModel:
         # ---- encoder input: patch tokens + intrinsics token ----
         x = torch.empty(Bn, N, 1024, device=self.dev)
         cols = torch.empty(Bn * P, 1024, device=self.dev)
-        ops._lib.check(lib.siu3r_im2col_nhwc(img4.data_ptr(), Bn, S0, S1, 4, 16, 16, 16, 0, cols.data_ptr(), 1024, ops._stream()), "im2col")
+        ops._lib.check(lib.siu3r_im2col_nhwc(img4.data_ptr(), Bn, S0, S1, 4, 16, 16, 16, 0, cols.data_ptr(), 1024, 1 if self.R else 0, ops._stream()),
+                       "im2col")
         for i in range(Bn):
-            self._lin(cols[i * P:(i + 1) * P], w.patch, out=x[i, :P])
+            self._lin(cols[i * P:(i + 1) * P], w.patch, ar=True, out=x[i, :P])
         x = x.view(Bn * N, 1024)
         Kflat = Kin.view(B, 18)
         for v in range(2):  # intrinsics token = Linear(9 -> 1024) on the flattened K (backbone_croco.py:278-280)

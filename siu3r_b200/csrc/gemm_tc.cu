@@ -21,6 +21,7 @@
 //                accuracy on the tensor cores; used for the strict parity tolerances of BASELINE.json's north_star.
 #include <cuda.h>
 
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -342,6 +343,228 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// 2-CTA variant (tcgen05 cta_group::2, cluster of 2 CTAs = one TPC): the pair computes a 256 x 256 tile with ONE
+// tcgen05.mma (M=256, N=256, K=8) per k-step, issued by the leader CTA.  Each CTA stages its own 128 rows of A and only
+// HALF of the B tile (128 of the 256 weight rows) -> 32 KB per k-block per SM instead of 48 KB for the same math, which is
+// what matters with fp32 operands: round-1 ncu showed the 1-CTA kernel starved on operand ingest (tensor pipe 17 % active).
+//   * TMA loads of both CTAs signal the LEADER's full barrier (mbarrier address mapped into the leader with mapa);
+//   * the leader's tcgen05.commit multicasts the "stage free" / "accumulator ready" arrivals to both CTAs;
+//   * TMEM (256 fp32 columns) is allocated with cta_group::2 by the same warp id in both CTAs.
+// TF32 mode only (the 3xTF32 mode needs 4 accumulators = 1024 columns and stays on the 1-CTA kernel).
+// ------------------------------------------------------------------------------------------------------------
+constexpr int TC2_BN = 256;            // N extent of the pair tile; each CTA stages TC2_BN / 2 rows of W
+constexpr int TC2_STAGE_BYTES = BM * BK * 4 + (TC2_BN / 2) * BK * 4;   // 32 KB
+constexpr int TC2_STAGES = 6;
+constexpr int TC2_SMEM_BYTES = TC2_STAGES * TC2_STAGE_BYTES + 1024 + 256;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_to_cta(uint32_t local_saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void tma2_load_2d(const CUtensorMap* map, uint32_t bar_cluster_addr, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+        "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma2_load_4d(const CUtensorMap* map, uint32_t bar_cluster_addr, void* dst, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void umma2_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma2_commit_mc(uint64_t* bar) {  // arrive on `bar` (same smem offset) in BOTH CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + TC2_STAGES * TC2_STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + TC2_STAGES;
+    uint64_t* acc_bar = empty_bar + TC2_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
+    constexpr int A_BYTES = BM * BK * 4;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int n0 = blockIdx.y * TC2_BN;
+    int m0 = blockIdx.x * BM, img = 0, h0 = 0, w0 = 0;   // blockIdx.x = 2 * pair + rank: consecutive 128-row tiles
+    if (p.conv) {
+        const int per_img = p.tiles_w * p.tiles_h;
+        img = blockIdx.x / per_img;
+        const int t = blockIdx.x % per_img;
+        h0 = (t / p.tiles_w) * CONV_TH;
+        w0 = (t % p.tiles_w) * CONV_TW;
+    }
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmA);
+        prefetch_tmap(&tmB);
+        for (int s = 0; s < TC2_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(acc_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TC2_BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    cluster_sync_all();  // barriers of both CTAs are initialised before any remote complete_tx / multicast arrive
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const int cblocks = p.conv ? p.Cin / BK : 0;
+            int stage = 0; uint32_t phase = 0;
+            for (int kb = 0; kb < p.num_kb; ++kb) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                uint8_t* sA = smem + stage * TC2_STAGE_BYTES;
+                uint8_t* sB = sA + A_BYTES;
+                const uint32_t lead_full = mapa_to_cta(smem_u32(&full_bar[stage]), 0);
+                if (leader) mbar_expect_tx(&full_bar[stage], 2 * TC2_STAGE_BYTES);  // bytes of both CTAs land on the leader's barrier
+                if (p.conv) {
+                    const int tap = kb / cblocks, cb = kb - tap * cblocks;
+                    const int kh = tap / p.KW, kw = tap - kh * p.KW;
+                    tma2_load_4d(&tmA, lead_full, sA, cb * BK, w0 + kw - p.pad, h0 + kh - p.pad, img);
+                } else {
+                    tma2_load_2d(&tmA, lead_full, sA, kb * BK, m0);
+                }
+                tma2_load_2d(&tmB, lead_full, sB, kb * BK, n0 + (int)rank * (TC2_BN / 2));
+                if (++stage == TC2_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (leader && lane == 0) {
+            constexpr uint32_t idesc = make_idesc_tf32(2 * BM, TC2_BN);
+            int stage = 0; uint32_t phase = 0;
+            for (int kb = 0; kb < p.num_kb; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
+                tcgen05_fence_after();
+                const uint32_t sA = smem_u32(smem + stage * TC2_STAGE_BYTES);
+                const uint32_t sB = sA + A_BYTES;
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                    const uint32_t koff = k * UMMA_K * 4;
+                    umma2_tf32(tmem_base, make_smem_desc(sA + koff), make_smem_desc(sB + koff), idesc, (kb | k) != 0);
+                }
+                umma2_commit_mc(&empty_bar[stage]);
+                if (++stage == TC2_STAGES) { stage = 0; phase ^= 1; }
+            }
+            umma2_commit_mc(acc_bar);
+        }
+    } else {
+        mbar_wait(acc_bar, 0);
+        tcgen05_fence_after();
+        const int act = p.act & ACT_MASK;
+        const bool rnd = (p.act & ACT_ROUND_TF32) != 0;
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        int64_t row_off; bool row_ok; int64_t res_off = 0;
+        if (p.conv) {
+            const int h = h0 + r / CONV_TW, w = w0 + r % CONV_TW;
+            row_ok = (img < p.M) && (h < p.H) && (w < p.W);   // p.M carries the image count in conv mode
+            const int64_t pix = ((int64_t)img * p.H + h) * p.W + w;
+            row_off = pix * p.ldc;
+            res_off = pix * p.ldr;
+        } else {
+            const int m = m0 + r;
+            row_ok = m < p.M;
+            row_off = (int64_t)m * p.ldc;
+            res_off = (int64_t)m * p.ldr;
+        }
+#pragma unroll 1
+        for (int c0 = 0; c0 < TC2_BN; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            tmem_ld_wait();
+            if (!row_ok) continue;
+            const int nbase = n0 + c0;
+            if (nbase >= p.N) continue;
+            float* crow = p.C + row_off + nbase;
+            const float* rrow = p.residual ? p.residual + res_off + nbase : nullptr;
+            const bool vec_ok = (nbase + 32 <= p.N) && ((((uintptr_t)crow) & 15) == 0) && (!rrow || (((uintptr_t)rrow) & 15) == 0);
+            if (vec_ok) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float4 o;
+                    float* of = reinterpret_cast<float*>(&o);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float x = __uint_as_float(v[j + e]) * p.alpha;
+                        if (p.bias) x += __ldg(p.bias + nbase + j + e);
+                        if (act == ACT_GELU) x = gelu_erf(x);
+                        else if (act == ACT_RELU) x = fmaxf(x, 0.0f);
+                        of[e] = x;
+                    }
+                    if (rrow) {
+                        const float4 rr = *reinterpret_cast<const float4*>(rrow + j);
+                        o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+                    }
+                    if (rnd) { o.x = rn_tf32(o.x); o.y = rn_tf32(o.y); o.z = rn_tf32(o.z); o.w = rn_tf32(o.w); }
+                    *reinterpret_cast<float4*>(crow + j) = o;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    if (nbase + j >= p.N) break;
+                    float x = __uint_as_float(v[j]) * p.alpha;
+                    if (p.bias) x += __ldg(p.bias + nbase + j);
+                    if (act == ACT_GELU) x = gelu_erf(x);
+                    else if (act == ACT_RELU) x = fmaxf(x, 0.0f);
+                    if (rrow) x += rrow[j];
+                    crow[j] = rnd ? rn_tf32(x) : x;
+                }
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    cluster_sync_all();  // the peer may still be reading TMEM / the leader's MMAs may still read this CTA's smem
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TC2_BN) : "memory");
+}
+
+int launch_tc2(const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, dim3 grid, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        SIU3R_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM_BYTES));
+        attr_set = true;
+    }
+    gemm_tc2_kernel<<<grid, NUM_THREADS, TC2_SMEM_BYTES, stream>>>(a, b, p);
+    SIU3R_LAUNCH_CHECK();
+    siu3r_note_launch(1);
+    return SIU3R_OK;
+}
+
+bool tc2_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SIU3R_DISABLE_TC2"); v = (e && e[0] == '1') ? 0 : 1; }
+    return v == 1;
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // Host side: tensor-map construction (driver entry point resolved at run time: no link-time libcuda dependency)
 // ------------------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -416,6 +639,19 @@ int siu3r_gemm_tc(int M, int N, int K, const float* A, const float* A_lo, int64_
     SIU3R_REQUIRE(lda % 4 == 0 && ldw % 4 == 0 && lda >= K && ldw >= K);
     SIU3R_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)Wt & 15) == 0);
     const int64_t mtiles = ceil_div_i64(M, BM);
+    if (precision == 1 && tc2_enabled() && N % TC2_BN == 0 && mtiles >= 2) {
+        // 2-CTA path: pairs of consecutive 128-row tiles share one 256 x 256 MMA
+        CUtensorMap ma, mb;
+        uint64_t dimsA[2] = {(uint64_t)K, (uint64_t)M}; uint64_t strA[1] = {(uint64_t)lda * 4}; uint32_t boxA[2] = {BK, BM};
+        int r = make_map(&ma, A, 2, dimsA, strA, boxA); if (r) return r;
+        uint64_t dimsB[2] = {(uint64_t)K, (uint64_t)N}; uint64_t strB[1] = {(uint64_t)ldw * 4}; uint32_t boxB[2] = {BK, TC2_BN / 2};
+        r = make_map(&mb, Wt, 2, dimsB, strB, boxB); if (r) return r;
+        GemmParams p{};
+        p.M = M; p.N = N; p.num_kb = ceil_div(K, BK); p.C = C; p.ldc = ldc; p.bias = bias; p.residual = residual; p.ldr = ldr;
+        p.act = act; p.alpha = alpha; p.conv = 0;
+        dim3 grid((unsigned)(2 * ceil_div_i64(mtiles, 2)), (unsigned)(N / TC2_BN));
+        return launch_tc2(ma, mb, p, grid, stream);
+    }
     int bn = pick_bn(N, mtiles);
     if (precision == 3 && bn == 256) bn = 128;
     CUtensorMap ma, malo, mb, mblo;
@@ -458,9 +694,24 @@ int siu3r_conv2d_tc(int Nimg, int H, int W, int Cin, int Cout, int KH, int KW, i
     SIU3R_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)Wt & 15) == 0);
     const int tiles_w = W / CONV_TW, tiles_h = H / CONV_TH;
     const int64_t mtiles = (int64_t)Nimg * tiles_w * tiles_h;
+    const int Ktot = KH * KW * Cin;
+    if (precision == 1 && tc2_enabled() && Cout % TC2_BN == 0 && mtiles >= 2) {
+        CUtensorMap ma, mb;
+        uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)Nimg};
+        uint64_t str[3] = {(uint64_t)Cin * 4, (uint64_t)W * Cin * 4, (uint64_t)H * W * Cin * 4};
+        uint32_t box[4] = {BK, CONV_TW, CONV_TH, 1};
+        int r = make_map(&ma, x, 4, dims, str, box); if (r) return r;
+        uint64_t dimsB[2] = {(uint64_t)Ktot, (uint64_t)Cout}; uint64_t strB[1] = {(uint64_t)Ktot * 4}; uint32_t boxB[2] = {BK, TC2_BN / 2};
+        r = make_map(&mb, Wt, 2, dimsB, strB, boxB); if (r) return r;
+        GemmParams p{};
+        p.M = Nimg; /* image count: rows of the padded last pair are masked with it */ p.N = Cout; p.num_kb = KH * KW * (Cin / BK); p.C = y;
+        p.ldc = ldc; p.bias = bias; p.residual = residual; p.ldr = ldr; p.act = act; p.alpha = 1.0f; p.conv = 1; p.H = H; p.W = W; p.Cin = Cin;
+        p.KH = KH; p.KW = KW; p.pad = pad; p.tiles_w = tiles_w; p.tiles_h = tiles_h;
+        dim3 grid((unsigned)(2 * ceil_div_i64(mtiles, 2)), (unsigned)(Cout / TC2_BN));
+        return launch_tc2(ma, mb, p, grid, stream);
+    }
     int bn = pick_bn(Cout, mtiles);
     if (precision == 3 && bn == 256) bn = 128;
-    const int Ktot = KH * KW * Cin;
     CUtensorMap ma, malo, mb, mblo;
     {
         uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)Nimg};

@@ -85,7 +85,7 @@ def test_gemm_inplace_residual():
 
 
 @pytest.mark.parametrize("shape", [(2, 16, 16, 64, 256, 3), (1, 32, 64, 96, 256, 3), (1, 128, 128, 256, 256, 3), (1, 64, 64, 768, 256, 3),
-                                   (2, 8, 16, 32, 83, 1), (1, 256, 256, 128, 128, 3)])
+                                   (2, 8, 16, 32, 83, 1), (1, 256, 256, 128, 128, 3), (1, 8, 48, 64, 256, 3), (3, 8, 16, 32, 512, 3)])
 @pytest.mark.parametrize("prec", [1, 3])
 def test_conv2d_tc(shape, prec):
     from siu3r_b200 import ops

@@ -151,14 +151,60 @@ __device__ __forceinline__ float rn_tf32(float x) {
     return __uint_as_float(r);
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Epilogue store of one 32-row x 32-column accumulator block held as "one row per lane" (tcgen05.ld 32x32b layout).
+// Round-1 probe (tools/gemm_probe.py): writing rows straight from that layout (each lane a 16-byte piece of a different
+// 128-byte line) ran at ~0.6 TB/s and dominated every GEMM.  The block is therefore transposed through a padded
+// shared-memory tile (stride 33: conflict-free both ways) so that each store instruction writes one full 128-byte line;
+// bias / activation / residual / rounding are applied in the transposed domain (bias = one value per lane, residual read
+// coalesced).  No alignment requirement on C / residual / ldc remains.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int EPI_TR_FLOATS = 32 * 33;  // per epilogue warp
+
+struct EpiRowMap {  // maps a tile row r (0..127) to its global row offset (in elements / ldc) or -1 when masked
+    int conv, m0, M, img, h0, w0, H, W, nimg;
+    __device__ __forceinline__ int64_t row(int r) const {
+        if (conv) {
+            const int h = h0 + r / CONV_TW, w = w0 + r % CONV_TW;
+            if (img >= nimg || h >= H || w >= W) return -1;
+            return ((int64_t)img * H + h) * W + w;
+        }
+        const int m = m0 + r;
+        return m < M ? (int64_t)m : -1;
+    }
+};
+
+__device__ __forceinline__ void epilogue_block_store(const uint32_t (&v)[32], float* tr /* this warp's 32x33 tile */, int lane, int q, int nbase,
+                                                     const GemmParams& p, const EpiRowMap& rm) {
+    const int act = p.act & ACT_MASK;
+    const bool rnd = (p.act & ACT_ROUND_TF32) != 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) tr[lane * 33 + j] = __uint_as_float(v[j]);
+    __syncwarp();
+    const int col = nbase + lane;
+    const bool col_ok = col < p.N;
+    const float bias = (p.bias && col_ok) ? __ldg(p.bias + col) : 0.0f;
+#pragma unroll 4
+    for (int k = 0; k < 32; ++k) {
+        const int64_t grow = rm.row(q * 32 + k);
+        if (grow < 0 || !col_ok) continue;
+        float x = tr[k * 33 + lane] * p.alpha + bias;
+        if (act == ACT_GELU) x = gelu_erf(x);
+        else if (act == ACT_RELU) x = fmaxf(x, 0.0f);
+        if (p.residual) x += p.residual[grow * p.ldr + col];
+        p.C[grow * p.ldc + col] = rnd ? rn_tf32(x) : x;
+    }
+    __syncwarp();
+}
+
 template <int BN, int NSPLIT>
 struct Cfg {
     static constexpr int NOPER = NSPLIT == 1 ? 1 : 2;  // hi (+ lo) planes per operand
     static constexpr int A_BYTES = BM * BK * 4;
     static constexpr int B_BYTES = BN * BK * 4;
     static constexpr int STAGE_BYTES = NOPER * (A_BYTES + B_BYTES);
-    static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int STAGES = (196 * 1024) / STAGE_BYTES > 8 ? 8 : (196 * 1024) / STAGE_BYTES;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 4 * EPI_TR_FLOATS * 4 /*epilogue transpose*/;
     // 3xTF32: four accumulators (3 round-robin for hi*hi + 1 for the cross terms).  The tensor core truncates its fp32
     // accumulator on every MMA, so the error grows with the number of MMAs chained into ONE accumulator; spreading the
     // chain over several accumulators that are summed in registers (round-to-nearest) divides that error accordingly.
@@ -262,25 +308,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ===================== epilogue (warps 2..5) =====================
         mbar_wait(acc_bar, 0);
         tcgen05_fence_after();
-        const int act = p.act & ACT_MASK;
-        const bool rnd = (p.act & ACT_ROUND_TF32) != 0;
         const int q = warp & 3;             // TMEM lane quarter this warp may access
-        const int r = q * 32 + lane;        // row inside the tile
-        int64_t row_off; bool row_ok; int64_t res_off = 0;
-        if (p.conv) {
-            const int h = h0 + r / CONV_TW, w = w0 + r % CONV_TW;
-            row_ok = (h < p.H) && (w < p.W);
-            const int64_t pix = ((int64_t)img * p.H + h) * p.W + w;
-            row_off = pix * p.ldc;
-            res_off = pix * p.ldr;
-        } else {
-            const int m = m0 + r;
-            row_ok = m < p.M;
-            row_off = (int64_t)m * p.ldc;
-            res_off = (int64_t)m * p.ldr;
-        }
+        float* tr = reinterpret_cast<float*>(smem + C_::STAGES * C_::STAGE_BYTES + 256) + q * EPI_TR_FLOATS;
+        EpiRowMap rm{p.conv, m0, p.M, img, h0, w0, p.H, p.W, p.conv ? (int)(p.M / (BM * p.tiles_w * p.tiles_h)) : 0};
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
+            const int nbase = n0 + c0;
+            if (nbase >= p.N) break;
             uint32_t v[32];
             tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
             tmem_ld_wait();
@@ -296,45 +330,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(t[j]));
                 }
             }
-            if (!row_ok) continue;
-            const int nbase = n0 + c0;
-            if (nbase >= p.N) continue;
-            float* crow = p.C + row_off + nbase;
-            const float* rrow = p.residual ? p.residual + res_off + nbase : nullptr;
-            const bool vec_ok = (nbase + 32 <= p.N) && ((((uintptr_t)crow) & 15) == 0) &&
-                                (!rrow || (((uintptr_t)rrow) & 15) == 0);
-            if (vec_ok) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    float4 o;
-                    float* of = reinterpret_cast<float*>(&o);
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        float x = __uint_as_float(v[j + e]) * p.alpha;
-                        if (p.bias) x += __ldg(p.bias + nbase + j + e);
-                        if (act == ACT_GELU) x = gelu_erf(x);
-                        else if (act == ACT_RELU) x = fmaxf(x, 0.0f);
-                        of[e] = x;
-                    }
-                    if (rrow) {
-                        const float4 rr = *reinterpret_cast<const float4*>(rrow + j);
-                        o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
-                    }
-                    if (rnd) { o.x = rn_tf32(o.x); o.y = rn_tf32(o.y); o.z = rn_tf32(o.z); o.w = rn_tf32(o.w); }
-                    *reinterpret_cast<float4*>(crow + j) = o;
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    if (nbase + j >= p.N) break;
-                    float x = __uint_as_float(v[j]) * p.alpha;
-                    if (p.bias) x += __ldg(p.bias + nbase + j);
-                    if (act == ACT_GELU) x = gelu_erf(x);
-                    else if (act == ACT_RELU) x = fmaxf(x, 0.0f);
-                    if (rrow) x += rrow[j];
-                    crow[j] = rnd ? rn_tf32(x) : x;
-                }
-            }
+            epilogue_block_store(v, tr, lane, q, nbase, p, rm);
         }
     }
     tcgen05_fence_before();
@@ -355,7 +351,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 constexpr int TC2_BN = 256;            // N extent of the pair tile; each CTA stages TC2_BN / 2 rows of W
 constexpr int TC2_STAGE_BYTES = BM * BK * 4 + (TC2_BN / 2) * BK * 4;   // 32 KB
 constexpr int TC2_STAGES = 6;
-constexpr int TC2_SMEM_BYTES = TC2_STAGES * TC2_STAGE_BYTES + 1024 + 256;
+constexpr int TC2_SMEM_BYTES = TC2_STAGES * TC2_STAGE_BYTES + 1024 + 256 + 4 * EPI_TR_FLOATS * 4;
 
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync_all() {
@@ -478,66 +474,17 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     } else {
         mbar_wait(acc_bar, 0);
         tcgen05_fence_after();
-        const int act = p.act & ACT_MASK;
-        const bool rnd = (p.act & ACT_ROUND_TF32) != 0;
         const int q = warp & 3;
-        const int r = q * 32 + lane;
-        int64_t row_off; bool row_ok; int64_t res_off = 0;
-        if (p.conv) {
-            const int h = h0 + r / CONV_TW, w = w0 + r % CONV_TW;
-            row_ok = (img < p.M) && (h < p.H) && (w < p.W);   // p.M carries the image count in conv mode
-            const int64_t pix = ((int64_t)img * p.H + h) * p.W + w;
-            row_off = pix * p.ldc;
-            res_off = pix * p.ldr;
-        } else {
-            const int m = m0 + r;
-            row_ok = m < p.M;
-            row_off = (int64_t)m * p.ldc;
-            res_off = (int64_t)m * p.ldr;
-        }
+        float* tr = reinterpret_cast<float*>(smem + TC2_STAGES * TC2_STAGE_BYTES + 256) + q * EPI_TR_FLOATS;
+        EpiRowMap rm{p.conv, m0, p.M, img, h0, w0, p.H, p.W, p.M /* image count in conv mode */};
 #pragma unroll 1
         for (int c0 = 0; c0 < TC2_BN; c0 += 32) {
+            const int nbase = n0 + c0;
+            if (nbase >= p.N) break;
             uint32_t v[32];
             tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
             tmem_ld_wait();
-            if (!row_ok) continue;
-            const int nbase = n0 + c0;
-            if (nbase >= p.N) continue;
-            float* crow = p.C + row_off + nbase;
-            const float* rrow = p.residual ? p.residual + res_off + nbase : nullptr;
-            const bool vec_ok = (nbase + 32 <= p.N) && ((((uintptr_t)crow) & 15) == 0) && (!rrow || (((uintptr_t)rrow) & 15) == 0);
-            if (vec_ok) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    float4 o;
-                    float* of = reinterpret_cast<float*>(&o);
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        float x = __uint_as_float(v[j + e]) * p.alpha;
-                        if (p.bias) x += __ldg(p.bias + nbase + j + e);
-                        if (act == ACT_GELU) x = gelu_erf(x);
-                        else if (act == ACT_RELU) x = fmaxf(x, 0.0f);
-                        of[e] = x;
-                    }
-                    if (rrow) {
-                        const float4 rr = *reinterpret_cast<const float4*>(rrow + j);
-                        o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
-                    }
-                    if (rnd) { o.x = rn_tf32(o.x); o.y = rn_tf32(o.y); o.z = rn_tf32(o.z); o.w = rn_tf32(o.w); }
-                    *reinterpret_cast<float4*>(crow + j) = o;
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    if (nbase + j >= p.N) break;
-                    float x = __uint_as_float(v[j]) * p.alpha;
-                    if (p.bias) x += __ldg(p.bias + nbase + j);
-                    if (act == ACT_GELU) x = gelu_erf(x);
-                    else if (act == ACT_RELU) x = fmaxf(x, 0.0f);
-                    if (rrow) x += rrow[j];
-                    crow[j] = rnd ? rn_tf32(x) : x;
-                }
-            }
+            epilogue_block_store(v, tr, lane, q, nbase, p, rm);
         }
     }
     tcgen05_fence_before();

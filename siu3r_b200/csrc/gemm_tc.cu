@@ -49,6 +49,7 @@ struct GemmParams {
     int conv;                  // 0 = linear, 1 = conv (stride 1)
     int H, W, Cin, KH, KW, pad;
     int tiles_w, tiles_h;      // tiles per image row / column
+    long long* dbg;            // optional: per-CTA clock64 stamps [cta][8] (tools/gemm_probe.py), null in production
 };
 
 // ------------------------------------------------------------------------------------------------------------
@@ -159,9 +160,10 @@ __device__ __forceinline__ float rn_tf32(float x) {
 // bias / activation / residual / rounding are applied in the transposed domain (bias = one value per lane, residual read
 // coalesced).  No alignment requirement on C / residual / ldc remains.
 // ------------------------------------------------------------------------------------------------------------
-constexpr int EPI_TR_FLOATS = 32 * 33;  // per epilogue warp
+constexpr int EPI_LD = 36;                   // padded row stride (floats): 16-byte aligned rows, conflict-free v4 access both ways
+constexpr int EPI_TR_FLOATS = 32 * EPI_LD;   // per epilogue warp
 
-struct EpiRowMap {  // maps a tile row r (0..127) to its global row offset (in elements / ldc) or -1 when masked
+struct EpiRowMap {  // maps a tile row r (0..127) to its global row index (pixel index in conv mode) or -1 when masked
     int conv, m0, M, img, h0, w0, H, W, nimg;
     __device__ __forceinline__ int64_t row(int r) const {
         if (conv) {
@@ -174,25 +176,62 @@ struct EpiRowMap {  // maps a tile row r (0..127) to its global row offset (in e
     }
 };
 
-__device__ __forceinline__ void epilogue_block_store(const uint32_t (&v)[32], float* tr /* this warp's 32x33 tile */, int lane, int q, int nbase,
-                                                     const GemmParams& p, const EpiRowMap& rm) {
+__device__ __forceinline__ void sts_v4(uint32_t saddr, float a, float b, float c, float d) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds_v4(uint32_t saddr) {
+    float4 r;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(saddr) : "memory");
+    return r;
+}
+__device__ __forceinline__ float epi_act(float x, int act) {
+    if (act == ACT_GELU) return gelu_erf(x);
+    if (act == ACT_RELU) return fmaxf(x, 0.0f);
+    return x;
+}
+
+// v: the warp's 32x32 accumulator block, row = lane.  tr_saddr: shared-space address of this warp's 32 x EPI_LD tile.
+__device__ __forceinline__ void epilogue_block_store(const uint32_t (&v)[32], uint32_t tr_saddr, int lane, int q, int nbase, const GemmParams& p,
+                                                     const EpiRowMap& rm) {
     const int act = p.act & ACT_MASK;
     const bool rnd = (p.act & ACT_ROUND_TF32) != 0;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) tr[lane * 33 + j] = __uint_as_float(v[j]);
+    for (int j = 0; j < 32; j += 4)
+        sts_v4(tr_saddr + (uint32_t)(lane * EPI_LD + j) * 4, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+               __uint_as_float(v[j + 3]));
     __syncwarp();
-    const int col = nbase + lane;
-    const bool col_ok = col < p.N;
-    const float bias = (p.bias && col_ok) ? __ldg(p.bias + col) : 0.0f;
-#pragma unroll 4
-    for (int k = 0; k < 32; ++k) {
-        const int64_t grow = rm.row(q * 32 + k);
-        if (grow < 0 || !col_ok) continue;
-        float x = tr[k * 33 + lane] * p.alpha + bias;
-        if (act == ACT_GELU) x = gelu_erf(x);
-        else if (act == ACT_RELU) x = fmaxf(x, 0.0f);
-        if (p.residual) x += p.residual[grow * p.ldr + col];
-        p.C[grow * p.ldc + col] = rnd ? rn_tf32(x) : x;
+    const int c4 = (lane & 7) * 4;     // this lane's 4 columns inside the block
+    const int rsub = lane >> 3;        // row inside each group of 4 rows
+    const int col = nbase + c4;
+    const bool full4 = col + 4 <= p.N;
+    float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.bias) {
+        if (full4) { bias.x = __ldg(p.bias + col); bias.y = __ldg(p.bias + col + 1); bias.z = __ldg(p.bias + col + 2); bias.w = __ldg(p.bias + col + 3); }
+        else {
+            if (col < p.N) bias.x = __ldg(p.bias + col);
+            if (col + 1 < p.N) bias.y = __ldg(p.bias + col + 1);
+            if (col + 2 < p.N) bias.z = __ldg(p.bias + col + 2);
+        }
+    }
+    const bool c_vec = ((p.ldc & 3) == 0) && ((((uintptr_t)p.C) & 15) == 0) && full4 && ((col & 3) == 0);
+    const bool r_vec = p.residual && ((p.ldr & 3) == 0) && ((((uintptr_t)p.residual) & 15) == 0) && full4 && ((col & 3) == 0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int r = rsub + 4 * i;
+        const int64_t grow = rm.row(q * 32 + r);
+        float4 x = lds_v4(tr_saddr + (uint32_t)(r * EPI_LD + c4) * 4);
+        if (grow < 0 || col >= p.N) continue;
+        x.x = epi_act(x.x * p.alpha + bias.x, act); x.y = epi_act(x.y * p.alpha + bias.y, act);
+        x.z = epi_act(x.z * p.alpha + bias.z, act); x.w = epi_act(x.w * p.alpha + bias.w, act);
+        if (p.residual) {
+            const float* rp = p.residual + grow * p.ldr + col;
+            if (r_vec) { const float4 rr = *reinterpret_cast<const float4*>(rp); x.x += rr.x; x.y += rr.y; x.z += rr.z; x.w += rr.w; }
+            else { x.x += rp[0]; if (col + 1 < p.N) x.y += rp[1]; if (col + 2 < p.N) x.z += rp[2]; if (col + 3 < p.N) x.w += rp[3]; }
+        }
+        if (rnd) { x.x = rn_tf32(x.x); x.y = rn_tf32(x.y); x.z = rn_tf32(x.z); x.w = rn_tf32(x.w); }
+        float* cp = p.C + grow * p.ldc + col;
+        if (c_vec) *reinterpret_cast<float4*>(cp) = x;
+        else { cp[0] = x.x; if (col + 1 < p.N) cp[1] = x.y; if (col + 2 < p.N) cp[2] = x.z; if (col + 3 < p.N) cp[3] = x.w; }
     }
     __syncwarp();
 }
@@ -226,6 +265,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n0 = blockIdx.y * BN;
+    long long* dbg = (p.dbg && blockIdx.y == 0 && blockIdx.x < 16) ? p.dbg + blockIdx.x * 8 : nullptr;
+    if (dbg && threadIdx.x == 0) dbg[0] = clock64();
     // M-tile coordinates
     int m0 = blockIdx.x * BM, img = 0, h0 = 0, w0 = 0;
     if (p.conv) {
@@ -249,6 +290,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (dbg && threadIdx.x == 0) dbg[1] = clock64();
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -271,6 +313,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 tma_load_2d(&tmB, &full_bar[stage], sB, kb * BK, n0);
                 if (NSPLIT == 3) tma_load_2d(&tmBlo, &full_bar[stage], sB + C_::B_BYTES, kb * BK, n0);
+                if (kb == 0 && dbg) dbg[2] = clock64();
                 if (++stage == C_::STAGES) { stage = 0; phase ^= 1; }
             }
         }
@@ -282,6 +325,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int kb = 0; kb < p.num_kb; ++kb) {
                 mbar_wait(&full_bar[stage], phase);
                 tcgen05_fence_after();
+                if (kb == 0 && dbg) dbg[3] = clock64();
                 const uint32_t sA = smem_u32(smem + stage * C_::STAGE_BYTES);
                 const uint32_t sB = sA + C_::NOPER * C_::A_BYTES;
 #pragma unroll
@@ -303,13 +347,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (++stage == C_::STAGES) { stage = 0; phase ^= 1; }
             }
             umma_commit(acc_bar);  // accumulator complete
+            if (dbg) dbg[4] = clock64();
         }
     } else {
         // ===================== epilogue (warps 2..5) =====================
         mbar_wait(acc_bar, 0);
         tcgen05_fence_after();
+        if (dbg && warp == 2 && lane == 0) dbg[5] = clock64();
         const int q = warp & 3;             // TMEM lane quarter this warp may access
-        float* tr = reinterpret_cast<float*>(smem + C_::STAGES * C_::STAGE_BYTES + 256) + q * EPI_TR_FLOATS;
+        const uint32_t tr = smem_u32(smem + C_::STAGES * C_::STAGE_BYTES + 256) + (uint32_t)(q * EPI_TR_FLOATS * 4);
         EpiRowMap rm{p.conv, m0, p.M, img, h0, w0, p.H, p.W, p.conv ? (int)(p.M / (BM * p.tiles_w * p.tiles_h)) : 0};
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -332,9 +378,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             epilogue_block_store(v, tr, lane, q, nbase, p, rm);
         }
+        if (dbg && warp == 2 && lane == 0) dbg[6] = clock64();
     }
+    __syncwarp();  // lane 0 of the producer / MMA warps rejoins its warp before the CTA-wide barrier (bar.sync counts whole warps)
     tcgen05_fence_before();
     __syncthreads();
+    if (dbg && threadIdx.x == 0) dbg[7] = clock64();
     if (warp == 1) tmem_dealloc<C_::TMEM_COLS>(tmem_base);
 }
 
@@ -475,7 +524,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         mbar_wait(acc_bar, 0);
         tcgen05_fence_after();
         const int q = warp & 3;
-        float* tr = reinterpret_cast<float*>(smem + TC2_STAGES * TC2_STAGE_BYTES + 256) + q * EPI_TR_FLOATS;
+        const uint32_t tr = smem_u32(smem + TC2_STAGES * TC2_STAGE_BYTES + 256) + (uint32_t)(q * EPI_TR_FLOATS * 4);
         EpiRowMap rm{p.conv, m0, p.M, img, h0, w0, p.H, p.W, p.M /* image count in conv mode */};
 #pragma unroll 1
         for (int c0 = 0; c0 < TC2_BN; c0 += 32) {
@@ -487,6 +536,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             epilogue_block_store(v, tr, lane, q, nbase, p, rm);
         }
     }
+    __syncwarp();
     tcgen05_fence_before();
     __syncthreads();
     cluster_sync_all();  // the peer may still be reading TMEM / the leader's MMAs may still read this CTA's smem
@@ -562,6 +612,8 @@ int launch(const CUtensorMap& a, const CUtensorMap& alo, const CUtensorMap& b, c
     return SIU3R_OK;
 }
 
+long long* g_gemm_dbg = nullptr;
+
 int pick_bn(int N, int64_t mtiles) {
     if (N % 256 == 0 && mtiles * (N / 256) >= 120) return 256;
     if (N > 64) return 128;
@@ -571,6 +623,9 @@ int pick_bn(int N, int64_t mtiles) {
 }  // namespace
 
 extern "C" {
+
+// debugging aid (not part of the product ABI): device buffer [16][8] of clock64 stamps written by the 1-CTA linear kernel
+void siu3r_gemm_debug_set(long long* dev_buf) { g_gemm_dbg = dev_buf; }
 
 // C[M,N] (ldc) = act(alpha * A[M,K] (lda) @ W[N,K]^T (ldw) + bias[N]) + residual[M,N] (ldr)
 // fp32 storage; precision 1 = TF32, 3 = 3xTF32 (needs the *_lo planes: x = hi + lo with hi = tf32-rounded x).
@@ -616,7 +671,7 @@ int siu3r_gemm_tc(int M, int N, int K, const float* A, const float* A_lo, int64_
     }
     GemmParams p{};
     p.M = M; p.N = N; p.num_kb = ceil_div(K, BK); p.C = C; p.ldc = ldc; p.bias = bias; p.residual = residual; p.ldr = ldr;
-    p.act = act; p.alpha = alpha; p.conv = 0;
+    p.act = act; p.alpha = alpha; p.conv = 0; p.dbg = g_gemm_dbg;
     dim3 grid((unsigned)mtiles, (unsigned)ceil_div(N, bn));
     if (precision == 1) {
         if (bn == 256) return launch<256, 1>(ma, malo, mb, mblo, p, grid, stream);

@@ -190,29 +190,33 @@ __device__ __forceinline__ float epi_act(float x, int act) {
     return x;
 }
 
-// v: the warp's 32x32 accumulator block, row = lane.  tr_saddr: shared-space address of this warp's 32 x EPI_LD tile.
-__device__ __forceinline__ void epilogue_block_store(const uint32_t (&v)[32], uint32_t tr_saddr, int lane, int q, int nbase, const GemmParams& p,
-                                                     const EpiRowMap& rm) {
-    const int act = p.act & ACT_MASK;
-    const bool rnd = (p.act & ACT_ROUND_TF32) != 0;
+__device__ __forceinline__ float4 epi_load_bias(const GemmParams& p, int col) {
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.bias) {
+        if (col < p.N) b.x = __ldg(p.bias + col);
+        if (col + 1 < p.N) b.y = __ldg(p.bias + col + 1);
+        if (col + 2 < p.N) b.z = __ldg(p.bias + col + 2);
+        if (col + 3 < p.N) b.w = __ldg(p.bias + col + 3);
+    }
+    return b;
+}
+
+// Stage the warp's 32x32 block (row = lane) into its padded shared tile.
+__device__ __forceinline__ void epi_stage(const uint32_t (&v)[32], uint32_t tr_saddr, int lane) {
 #pragma unroll
     for (int j = 0; j < 32; j += 4)
         sts_v4(tr_saddr + (uint32_t)(lane * EPI_LD + j) * 4, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
                __uint_as_float(v[j + 3]));
-    __syncwarp();
+}
+
+// Read the staged block back row-wise (each instruction = 4 rows x 128 B), apply the epilogue, store full 128-byte lines.
+__device__ __forceinline__ void epi_emit(uint32_t tr_saddr, int lane, int q, int nbase, float4 bias, const GemmParams& p, const EpiRowMap& rm) {
+    const int act = p.act & ACT_MASK;
+    const bool rnd = (p.act & ACT_ROUND_TF32) != 0;
     const int c4 = (lane & 7) * 4;     // this lane's 4 columns inside the block
     const int rsub = lane >> 3;        // row inside each group of 4 rows
     const int col = nbase + c4;
     const bool full4 = col + 4 <= p.N;
-    float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (p.bias) {
-        if (full4) { bias.x = __ldg(p.bias + col); bias.y = __ldg(p.bias + col + 1); bias.z = __ldg(p.bias + col + 2); bias.w = __ldg(p.bias + col + 3); }
-        else {
-            if (col < p.N) bias.x = __ldg(p.bias + col);
-            if (col + 1 < p.N) bias.y = __ldg(p.bias + col + 1);
-            if (col + 2 < p.N) bias.z = __ldg(p.bias + col + 2);
-        }
-    }
     const bool c_vec = ((p.ldc & 3) == 0) && ((((uintptr_t)p.C) & 15) == 0) && full4 && ((col & 3) == 0);
     const bool r_vec = p.residual && ((p.ldr & 3) == 0) && ((((uintptr_t)p.residual) & 15) == 0) && full4 && ((col & 3) == 0);
 #pragma unroll
@@ -233,7 +237,51 @@ __device__ __forceinline__ void epilogue_block_store(const uint32_t (&v)[32], ui
         if (c_vec) *reinterpret_cast<float4*>(cp) = x;
         else { cp[0] = x.x; if (col + 1 < p.N) cp[1] = x.y; if (col + 2 < p.N) cp[2] = x.z; if (col + 3 < p.N) cp[3] = x.w; }
     }
-    __syncwarp();
+}
+
+// Whole-tile epilogue of one warp (its 32 TMEM lanes x NCOLS columns).  TF32 mode is software-pipelined: the TMEM load of
+// chunk c+1 and the bias of chunk c+1 are in flight while chunk c is emitted.  3xTF32 sums the 4 accumulators per chunk.
+template <int NCOLS, int NSPLIT>
+__device__ __forceinline__ void run_epilogue(uint32_t tmem_base, uint32_t tr, int lane, int q, int n0, const GemmParams& p, const EpiRowMap& rm,
+                                             uint64_t* acc_bar) {
+    const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int c4 = (lane & 7) * 4;
+    float4 bias = epi_load_bias(p, n0 + c4);   // issued before the accumulator is ready: latency hidden behind the mainloop
+    mbar_wait(acc_bar, 0);
+    tcgen05_fence_after();
+    uint32_t v[32];
+    if (NSPLIT == 1) tmem_ld_32x32b_x32(tq, v);
+#pragma unroll 1
+    for (int c0 = 0; c0 < NCOLS; c0 += 32) {
+        const int nbase = n0 + c0;
+        if (nbase >= p.N) break;
+        const bool has_next = (c0 + 32 < NCOLS) && (nbase + 32 < p.N);
+        const float4 bias_next = has_next ? epi_load_bias(p, nbase + 32 + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (NSPLIT == 3) {
+            tmem_ld_32x32b_x32(tq + (uint32_t)c0, v);
+            tmem_ld_wait();
+            const int nks = p.num_kb * (BK / UMMA_K);
+#pragma unroll
+            for (int a = 1; a < 4; ++a) {
+                if (a < 3 && a >= nks) continue;  // hi*hi accumulator never written (K < 24)
+                uint32_t t[32];
+                tmem_ld_32x32b_x32(tq + (uint32_t)(a * NCOLS + c0), t);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(t[j]));
+            }
+            epi_stage(v, tr, lane);
+            __syncwarp();
+        } else {
+            tmem_ld_wait();
+            epi_stage(v, tr, lane);
+            __syncwarp();
+            if (has_next) tmem_ld_32x32b_x32(tq + (uint32_t)(c0 + 32), v);  // overlaps with the stores below
+        }
+        epi_emit(tr, lane, q, nbase, bias, p, rm);
+        __syncwarp();
+        bias = bias_next;
+    }
 }
 
 template <int BN, int NSPLIT>
@@ -242,8 +290,14 @@ struct Cfg {
     static constexpr int A_BYTES = BM * BK * 4;
     static constexpr int B_BYTES = BN * BK * 4;
     static constexpr int STAGE_BYTES = NOPER * (A_BYTES + B_BYTES);
-    static constexpr int STAGES = (196 * 1024) / STAGE_BYTES > 8 ? 8 : (196 * 1024) / STAGE_BYTES;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 4 * EPI_TR_FLOATS * 4 /*epilogue transpose*/;
+    // TF32: <= 96 KB of stages so that TWO CTAs fit per SM (one CTA's epilogue overlaps the other's mainloop; 2 x 256 TMEM
+    // columns).  3xTF32 needs all 512 TMEM columns -> one CTA per SM, deeper pipeline.
+    static constexpr int BUDGET = NSPLIT == 1 ? 96 * 1024 : 208 * 1024;
+    static constexpr int STAGES = BUDGET / STAGE_BYTES > 8 ? 8 : BUDGET / STAGE_BYTES;
+    static constexpr int CTAS_PER_SM = NSPLIT == 1 ? 2 : 1;
+    // the epilogue's transpose tiles (4 x 4.5 KB) alias the pipeline stages: the mainloop is over when the accumulator is ready
+    static_assert(STAGES * STAGE_BYTES >= 4 * EPI_TR_FLOATS * 4, "stage memory must cover the epilogue tiles");
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
     // 3xTF32: four accumulators (3 round-robin for hi*hi + 1 for the cross terms).  The tensor core truncates its fp32
     // accumulator on every MMA, so the error grows with the number of MMAs chained into ONE accumulator; spreading the
     // chain over several accumulators that are summed in registers (round-to-nearest) divides that error accordingly.
@@ -252,7 +306,7 @@ struct Cfg {
 };
 
 template <int BN, int NSPLIT>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(NUM_THREADS, (NSPLIT == 1 ? 2 : 1))
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo, const GemmParams p) {
     using C_ = Cfg<BN, NSPLIT>;
@@ -351,34 +405,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else {
         // ===================== epilogue (warps 2..5) =====================
-        mbar_wait(acc_bar, 0);
-        tcgen05_fence_after();
-        if (dbg && warp == 2 && lane == 0) dbg[5] = clock64();
         const int q = warp & 3;             // TMEM lane quarter this warp may access
-        const uint32_t tr = smem_u32(smem + C_::STAGES * C_::STAGE_BYTES + 256) + (uint32_t)(q * EPI_TR_FLOATS * 4);
+        const uint32_t tr = smem_u32(smem) + (uint32_t)(q * EPI_TR_FLOATS * 4);   // aliases stage memory (free once acc_bar fires)
         EpiRowMap rm{p.conv, m0, p.M, img, h0, w0, p.H, p.W, p.conv ? (int)(p.M / (BM * p.tiles_w * p.tiles_h)) : 0};
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            const int nbase = n0 + c0;
-            if (nbase >= p.N) break;
-            uint32_t v[32];
-            tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-            tmem_ld_wait();
-            if (NSPLIT == 3) {
-                const int nks = p.num_kb * (BK / UMMA_K);
-#pragma unroll
-                for (int a = 1; a < 4; ++a) {
-                    if (a < 3 && a >= nks) continue;  // hi*hi accumulator never written (K < 24)
-                    uint32_t t[32];
-                    tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN + c0), t);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(t[j]));
-                }
-            }
-            epilogue_block_store(v, tr, lane, q, nbase, p, rm);
-        }
-        if (dbg && warp == 2 && lane == 0) dbg[6] = clock64();
+        run_epilogue<BN, NSPLIT>(tmem_base, tr, lane, q, n0, p, rm, acc_bar);
+        if (dbg && warp == 2 && lane == 0) { dbg[5] = 0; dbg[6] = clock64(); }
     }
     __syncwarp();  // lane 0 of the producer / MMA warps rejoins its warp before the CTA-wide barrier (bar.sync counts whole warps)
     tcgen05_fence_before();
@@ -399,8 +430,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // ------------------------------------------------------------------------------------------------------------
 constexpr int TC2_BN = 256;            // N extent of the pair tile; each CTA stages TC2_BN / 2 rows of W
 constexpr int TC2_STAGE_BYTES = BM * BK * 4 + (TC2_BN / 2) * BK * 4;   // 32 KB
-constexpr int TC2_STAGES = 6;
-constexpr int TC2_SMEM_BYTES = TC2_STAGES * TC2_STAGE_BYTES + 1024 + 256 + 4 * EPI_TR_FLOATS * 4;
+constexpr int TC2_STAGES = 3;   // 96 KB: two CTAs (of two different pairs) per SM
+constexpr int TC2_SMEM_BYTES = TC2_STAGES * TC2_STAGE_BYTES + 1024 + 256;   // epilogue tiles alias the stages
 
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync_all() {
@@ -441,7 +472,7 @@ __device__ __forceinline__ void umma2_commit_mc(uint64_t* bar) {  // arrive on `
                  : "memory");
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 2)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -521,20 +552,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             umma2_commit_mc(acc_bar);
         }
     } else {
-        mbar_wait(acc_bar, 0);
-        tcgen05_fence_after();
         const int q = warp & 3;
-        const uint32_t tr = smem_u32(smem + TC2_STAGES * TC2_STAGE_BYTES + 256) + (uint32_t)(q * EPI_TR_FLOATS * 4);
+        const uint32_t tr = smem_u32(smem) + (uint32_t)(q * EPI_TR_FLOATS * 4);   // aliases stage memory
         EpiRowMap rm{p.conv, m0, p.M, img, h0, w0, p.H, p.W, p.M /* image count in conv mode */};
-#pragma unroll 1
-        for (int c0 = 0; c0 < TC2_BN; c0 += 32) {
-            const int nbase = n0 + c0;
-            if (nbase >= p.N) break;
-            uint32_t v[32];
-            tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-            tmem_ld_wait();
-            epilogue_block_store(v, tr, lane, q, nbase, p, rm);
-        }
+        run_epilogue<TC2_BN, 1>(tmem_base, tr, lane, q, n0, p, rm, acc_bar);
     }
     __syncwarp();
     tcgen05_fence_before();

@@ -66,9 +66,10 @@ void siu3r_gemm_debug_set(long long* dev_buf);   /* profiling aid: per-CTA clock
  * siu3r_rope2d replaces curope.rope_2d(tokens, positions, base, fwd) (croco/curope/curope.cpp:49-65,
  * kernels.cu:17-82; called from croco/curope/curope2d.py:20,27 <- croco/blocks.py:101-103,158-160): in place, tokens
  * [B,N,H,D] with arbitrary batch/token strides (so q and k can be rotated inside the fused qkv buffer), positions
- * [B,N,2] int64 (y, x).  Error contract: D % 4 != 0 -> -1 ("token dim must be multiple of 4", kernels.cu:94). */
+ * [B,N,2] int64 (y, x); nparts > 1 rotates several tensors that share the positions in one launch (q and k
+ * of the fused qkv buffer: part_stride = C).  Error contract: D % 4 != 0 -> -1 ("token dim must be multiple of 4", kernels.cu:94). */
 int siu3r_rope2d(float* tokens, const int64_t* positions, int B, int N, int H, int D, int64_t batch_stride,
-                 int64_t token_stride, float base, float fwd, void* stream);
+                 int64_t token_stride, float base, float fwd, int nparts, int64_t part_stride, void* stream);
 /* nn.LayerNorm over the last dim (+ optional fused add of `add` rows): croco/blocks.py:119-125,176-184 */
 int siu3r_layernorm(const float* x, int64_t ldx, const float* w, const float* b, float* y, int64_t ldy, int rows, int C,
                     float eps, const float* add, int64_t ldadd, int round_out, void* stream);
@@ -104,7 +105,7 @@ int siu3r_maxpool3x3s2_nhwc(const float* x, int N, int H, int W, int C, float* y
 int siu3r_dwconv3x3_nhwc(const float* x, int64_t ldx, int64_t batch_stride_x, int N, int H, int W, int C, const float* w,
                          const float* b, float* y, int64_t ldy, int64_t batch_stride_y, int gelu, void* stream); /* :16-31 */
 int siu3r_groupnorm_nhwc(const float* x, int N, int HW, int C, int groups, const float* w, const float* b, float eps,
-                         int relu, float* y, void* stream);                         /* video_seg_decoder.py:2004,2036,2048 */
+                         int relu, float* y, double* stats_ws, void* stream);                         /* video_seg_decoder.py:2004,2036,2048 */
 
 /* ---- heads / outputs ------------------------------------------------------------------------------------------- */
 int siu3r_depth_exp(const float* xyz, int64_t ldx, float* pts, int64_t n, void* stream);   /* heads/postprocess.py:46-61 */

@@ -29,7 +29,7 @@ SIGNATURES = {
     "siu3r_gemm_simt": (_i, [_i, _i, _i, _p, _l, _p, _l, _p, _l, _p, _p, _l, _i, _f, _p]),
     "siu3r_split_tf32": (_i, [_p, _p, _p, _l, _p]),
     "siu3r_gemm_debug_set": (None, [_p]),
-    "siu3r_rope2d": (_i, [_p, _p, _i, _i, _i, _i, _l, _l, _f, _f, _p]),
+    "siu3r_rope2d": (_i, [_p, _p, _i, _i, _i, _i, _l, _l, _f, _f, _i, _l, _p]),
     "siu3r_layernorm": (_i, [_p, _l, _p, _p, _p, _l, _i, _i, _f, _p, _l, _i, _p]),
     "siu3r_flash_attn_d64": (_i, [_p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _l, _l, _i, _i, _i, _i, _f, _i, _i, _p]),
     "siu3r_attn_small_d32": (_i, [_p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _i, _i, _i, _i, _f, _p]),
@@ -44,7 +44,7 @@ SIGNATURES = {
     "siu3r_nhwc_to_nchw": (_i, [_p, _l, _p, _i, _i, _i, _p]),
     "siu3r_maxpool3x3s2_nhwc": (_i, [_p, _i, _i, _i, _i, _p, _p]),
     "siu3r_dwconv3x3_nhwc": (_i, [_p, _l, _l, _i, _i, _i, _i, _p, _p, _p, _l, _l, _i, _p]),
-    "siu3r_groupnorm_nhwc": (_i, [_p, _i, _i, _i, _i, _p, _p, _f, _i, _p, _p]),
+    "siu3r_groupnorm_nhwc": (_i, [_p, _i, _i, _i, _i, _p, _p, _f, _i, _p, _p, _p]),
     "siu3r_depth_exp": (_i, [_p, _l, _p, _l, _p]),
     "siu3r_gaussian_adapter": (_i, [_p, _l, _p, _p, _p, _p, _p, _p]),
     "siu3r_attn_mask_from_logits": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _p, _p]),

@@ -635,10 +635,18 @@ int launch(const CUtensorMap& a, const CUtensorMap& alo, const CUtensorMap& b, c
 
 long long* g_gemm_dbg = nullptr;
 
+// Tile selection (TF32 mode).  148 SMs x 2 resident CTAs: prefer the 2-CTA 256x256 pair tile when it still fills the
+// machine, otherwise fall back to smaller 1-CTA tiles so that small problems (M = 1025 / 2050 rows) launch enough CTAs.
+constexpr int kFillCtas = 222;  // ~1.5 CTAs per SM
+
+bool use_tc2(int N, int64_t mtiles) {
+    if (!tc2_enabled() || N % TC2_BN != 0 || mtiles < 2) return false;
+    return 2 * ceil_div_i64(mtiles, 2) * (N / TC2_BN) >= kFillCtas;
+}
+
 int pick_bn(int N, int64_t mtiles) {
-    if (N % 256 == 0 && mtiles * (N / 256) >= 120) return 256;
-    if (N > 64) return 128;
-    return 64;
+    if (N <= 64) return 64;
+    return mtiles * ceil_div(N, 128) >= 148 ? 128 : 64;   // BN = 64 when 128-wide tiles would leave SMs idle
 }
 
 }  // namespace
@@ -662,7 +670,7 @@ int siu3r_gemm_tc(int M, int N, int K, const float* A, const float* A_lo, int64_
     SIU3R_REQUIRE(lda % 4 == 0 && ldw % 4 == 0 && lda >= K && ldw >= K);
     SIU3R_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)Wt & 15) == 0);
     const int64_t mtiles = ceil_div_i64(M, BM);
-    if (precision == 1 && tc2_enabled() && N % TC2_BN == 0 && mtiles >= 2) {
+    if (precision == 1 && use_tc2(N, mtiles)) {
         // 2-CTA path: pairs of consecutive 128-row tiles share one 256 x 256 MMA
         CUtensorMap ma, mb;
         uint64_t dimsA[2] = {(uint64_t)K, (uint64_t)M}; uint64_t strA[1] = {(uint64_t)lda * 4}; uint32_t boxA[2] = {BK, BM};
@@ -676,7 +684,6 @@ int siu3r_gemm_tc(int M, int N, int K, const float* A, const float* A_lo, int64_
         return launch_tc2(ma, mb, p, grid, stream);
     }
     int bn = pick_bn(N, mtiles);
-    if (precision == 3 && bn == 256) bn = 128;
     CUtensorMap ma, malo, mb, mblo;
     {
         uint64_t dims[2] = {(uint64_t)K, (uint64_t)M}; uint64_t str[1] = {(uint64_t)lda * 4}; uint32_t box[2] = {BK, BM};
@@ -718,7 +725,7 @@ int siu3r_conv2d_tc(int Nimg, int H, int W, int Cin, int Cout, int KH, int KW, i
     const int tiles_w = W / CONV_TW, tiles_h = H / CONV_TH;
     const int64_t mtiles = (int64_t)Nimg * tiles_w * tiles_h;
     const int Ktot = KH * KW * Cin;
-    if (precision == 1 && tc2_enabled() && Cout % TC2_BN == 0 && mtiles >= 2) {
+    if (precision == 1 && use_tc2(Cout, mtiles)) {
         CUtensorMap ma, mb;
         uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)Nimg};
         uint64_t str[3] = {(uint64_t)Cin * 4, (uint64_t)W * Cin * 4, (uint64_t)H * W * Cin * 4};
@@ -734,7 +741,6 @@ int siu3r_conv2d_tc(int Nimg, int H, int W, int Cin, int Cout, int KH, int KW, i
         return launch_tc2(ma, mb, p, grid, stream);
     }
     int bn = pick_bn(Cout, mtiles);
-    if (precision == 3 && bn == 256) bn = 128;
     CUtensorMap ma, malo, mb, mblo;
     {
         uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)Nimg};

@@ -225,9 +225,10 @@ __global__ void __launch_bounds__(128) attn_small_d32_kernel(const float* __rest
                                                             float* __restrict__ O, int64_t o_bs, int64_t o_ts,
                                                             const uint8_t* __restrict__ mask /*[B,Nq,Nk] 1 = masked*/, int B, int H, int Nq,
                                                             int Nk, float scale) {
-    const int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (wid >= B * H * Nq) return;
+    // one CTA (4 warps) per (batch, head, query); thread t owns keys t, t+128, ... with a private online softmax
+    __shared__ float s_m[4], s_l[4], s_acc[4][32];
+    const int wid = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q = wid % Nq;
     const int h = (wid / Nq) % H;
     const int b = wid / (Nq * H);
@@ -248,10 +249,10 @@ __global__ void __launch_bounds__(128) attn_small_d32_kernel(const float* __rest
         m = -INFINITY; l = 0.f;
 #pragma unroll
         for (int d = 0; d < 32; ++d) acc[d] = 0.f;
-        bool any = false;
-        for (int key = lane; key < Nk; key += 32) {
+        int any = 0;
+        for (int key = threadIdx.x; key < Nk; key += 128) {
             if (use_mask && mrow[key]) continue;
-            any = true;
+            any = 1;
             const float* kp = Kb + (int64_t)key * k_ts;
             float dot = 0.f;
 #pragma unroll
@@ -261,29 +262,41 @@ __global__ void __launch_bounds__(128) attn_small_d32_kernel(const float* __rest
             }
             dot *= scale;
             const float mn = fmaxf(m, dot);
-            const float corr = expf(m - mn), p = expf(dot - mn);
-            l = l * corr + p;
+            const float corr = expf(m - mn), pw = expf(dot - mn);
+            l = l * corr + pw;
             const float* vp = Vb + (int64_t)key * v_ts;
 #pragma unroll
             for (int d = 0; d < 32; d += 4) {
                 const float4 vv = *reinterpret_cast<const float4*>(vp + d);
-                acc[d] = acc[d] * corr + p * vv.x; acc[d + 1] = acc[d + 1] * corr + p * vv.y;
-                acc[d + 2] = acc[d + 2] * corr + p * vv.z; acc[d + 3] = acc[d + 3] * corr + p * vv.w;
+                acc[d] = acc[d] * corr + pw * vv.x; acc[d + 1] = acc[d + 1] * corr + pw * vv.y;
+                acc[d + 2] = acc[d + 2] * corr + pw * vv.z; acc[d + 3] = acc[d + 3] * corr + pw * vv.w;
             }
             m = mn;
         }
-        if (!use_mask || __any_sync(0xffffffffu, any)) break;  // fully masked row: redo without the mask
+        if (!use_mask || __syncthreads_or(any)) break;  // fully masked row: redo without the mask (video_seg_decoder.py:1306-1308)
     }
-    const float mall = warp_max(m);
-    const float f = (m == -INFINITY) ? 0.f : expf(m - mall);
+    // merge: warp level, then the 4 warps through shared memory
+    const float mw = warp_max(m);
+    const float f = (m == -INFINITY) ? 0.f : expf(m - mw);
     l = warp_sum(l * f);
-    float outv = 0.f;
 #pragma unroll
     for (int d = 0; d < 32; ++d) {
         const float v = warp_sum(acc[d] * f);
-        if (lane == d) outv = v;
+        if (lane == d) s_acc[warp][d] = v;
     }
-    O[(int64_t)b * o_bs + (int64_t)q * o_ts + h * 32 + lane] = outv / l;
+    if (lane == 0) { s_m[warp] = mw; s_l[warp] = l; }
+    __syncthreads();
+    if (warp == 0) {
+        const float M = fmaxf(fmaxf(s_m[0], s_m[1]), fmaxf(s_m[2], s_m[3]));
+        float L = 0.f, o = 0.f;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const float g = (s_m[w] == -INFINITY) ? 0.f : expf(s_m[w] - M);
+            L += s_l[w] * g;
+            o += s_acc[w][lane] * g;
+        }
+        O[(int64_t)b * o_bs + (int64_t)q * o_ts + h * 32 + lane] = o / L;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -397,8 +410,7 @@ int siu3r_attn_small_d32(const float* Q, int64_t q_bs, int64_t q_ts, const float
     cudaStream_t stream = (cudaStream_t)stream_;
     SIU3R_REQUIRE(Q && K && V && O && B > 0 && H > 0 && Nq > 0 && Nk > 0);
     SIU3R_REQUIRE(q_ts % 4 == 0 && k_ts % 4 == 0 && v_ts % 4 == 0 && q_bs % 4 == 0 && k_bs % 4 == 0 && v_bs % 4 == 0);
-    const int warps = B * H * Nq;
-    attn_small_d32_kernel<<<ceil_div(warps, 4), 128, 0, stream>>>(Q, q_bs, q_ts, K, k_bs, k_ts, V, v_bs, v_ts, O, o_bs, o_ts, mask, B, H, Nq, Nk,
+    attn_small_d32_kernel<<<B * H * Nq, 128, 0, stream>>>(Q, q_bs, q_ts, K, k_bs, k_ts, V, v_bs, v_ts, O, o_bs, o_ts, mask, B, H, Nq, Nk,
                                                                  scale);
     SIU3R_LAUNCH_CHECK();
     siu3r_note_launch(1);

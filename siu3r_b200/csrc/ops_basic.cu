@@ -74,17 +74,20 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 // One thread per (token, head, quarter index d<D/4, x/y half): rotates the pair (d, d+D/4) of its half.
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) rope2d_kernel(float* __restrict__ tokens, const int64_t* __restrict__ pos, int B, int N, int H, int D,
-                                                     int64_t batch_stride, int64_t token_stride, float base, float fwd) {
+                                                     int64_t batch_stride, int64_t token_stride, float base, float fwd, int nparts,
+                                                     int64_t part_stride) {
     const int Q = D >> 2;
-    const int64_t total = (int64_t)B * N * H * 2 * Q;
+    const int64_t total = (int64_t)B * N * nparts * H * 2 * Q;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     const int d = (int)(idx % Q);
     int64_t t = idx / Q;
     const int xh = (int)(t % 2); t /= 2;
     const int h = (int)(t % H); t /= H;
+    const int part = (int)(t % nparts); t /= nparts;
     const int n = (int)(t % N);
     const int b = (int)(t / N);
+    tokens += (int64_t)part * part_stride;
     const float inv_freq = fwd / powf(base, (float)d / (float)Q);
     const float f = (float)pos[((int64_t)b * N + n) * 2 + xh] * inv_freq;
     float s, c;
@@ -347,51 +350,59 @@ __global__ void __launch_bounds__(256) dwconv3x3_kernel(const float* __restrict_
     *reinterpret_cast<float4*>(y + (int64_t)n * batch_stride_y + ((int64_t)hh * W + ww) * ldy + c) = acc;
 }
 
-// GroupNorm over NHWC [N, HW, C]: one CTA per (n, group); two passes over the group's HW x (C/groups) slab.
-// (mask2former/video_seg_decoder.py:2004,2036,2048: GroupNorm(32, 256), eps 1e-5, optional fused ReLU)
-__global__ void __launch_bounds__(256) groupnorm_kernel(const float* __restrict__ x, int HW, int C, int groups, const float* __restrict__ w,
-                                                        const float* __restrict__ b, float eps, int relu, float* __restrict__ y) {
-    const int n = blockIdx.x / groups, g = blockIdx.x % groups;
+// GroupNorm over NHWC [N, HW, C] (mask2former/video_seg_decoder.py:2004,2036,2048: GroupNorm(32, 256), eps 1e-5, optional ReLU).
+// Pass 1: per-(n, group) sum and sum of squares, accumulated in fp64 (block partials -> atomicAdd(double)), grid over pixels;
+// pass 2: elementwise normalise.  (The former one-CTA-per-group kernel took 0.27 ms per call at 128x128.)
+__global__ void __launch_bounds__(256) groupnorm_stats_kernel(const float* __restrict__ x, int HW, int C, int groups, double* __restrict__ stats) {
+    // grid: (pixel chunks, N); each thread walks pixels of one channel-quad; C % 4 == 0 and (C/groups) % 4 == 0
+    const int n = blockIdx.y;
+    const int c4 = C >> 2;
+    const int cq = threadIdx.x % c4;                 // channel quad handled by this thread (blockDim.x multiple of c4)
+    const int prow = threadIdx.x / c4, pstep = blockDim.x / c4;
     const int cpg = C / groups;
-    const float* xb = x + (int64_t)n * HW * C + g * cpg;
-    float* yb = y + (int64_t)n * HW * C + g * cpg;
-    const int64_t cnt = (int64_t)HW * cpg;
-    __shared__ float s_red[32];
-    __shared__ float s_stat[2];
-    float s = 0.f;
-    for (int64_t i = threadIdx.x; i < cnt; i += blockDim.x) s += xb[(i / cpg) * C + (i % cpg)];
-    s = warp_sum(s);
-    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = s;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        float v = threadIdx.x < (blockDim.x >> 5) ? s_red[threadIdx.x] : 0.f;
-        v = warp_sum(v);
-        if (threadIdx.x == 0) s_stat[0] = v / (float)cnt;
+    const int g = (cq * 4) / cpg;
+    const int pix_per_block = (HW + gridDim.x - 1) / gridDim.x;
+    const int p0 = blockIdx.x * pix_per_block, p1 = min(HW, p0 + pix_per_block);
+    double s = 0.0, q = 0.0;
+    const float* xb = x + (int64_t)n * HW * C + cq * 4;
+    for (int p = p0 + prow; p < p1; p += pstep) {
+        const float4 v = *reinterpret_cast<const float4*>(xb + (int64_t)p * C);
+        s += (double)v.x + (double)v.y + (double)v.z + (double)v.w;
+        q += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
     }
+    __shared__ double sh_s[32], sh_q[32];
+    if (threadIdx.x < 32) { sh_s[threadIdx.x] = 0.0; sh_q[threadIdx.x] = 0.0; }
     __syncthreads();
-    const float mean = s_stat[0];
-    float q = 0.f;
-    for (int64_t i = threadIdx.x; i < cnt; i += blockDim.x) {
-        const float d = xb[(i / cpg) * C + (i % cpg)] - mean;
-        q += d * d;
-    }
-    q = warp_sum(q);
-    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = q;
+    atomicAdd(&sh_s[g], s);
+    atomicAdd(&sh_q[g], q);
     __syncthreads();
-    if (threadIdx.x < 32) {
-        float v = threadIdx.x < (blockDim.x >> 5) ? s_red[threadIdx.x] : 0.f;
-        v = warp_sum(v);
-        if (threadIdx.x == 0) s_stat[1] = rsqrtf(v / (float)cnt + eps);
+    if (threadIdx.x < groups) {
+        atomicAdd(&stats[((int64_t)n * groups + threadIdx.x) * 2], sh_s[threadIdx.x]);
+        atomicAdd(&stats[((int64_t)n * groups + threadIdx.x) * 2 + 1], sh_q[threadIdx.x]);
     }
-    __syncthreads();
-    const float rstd = s_stat[1];
-    for (int64_t i = threadIdx.x; i < cnt; i += blockDim.x) {
-        const int c = (int)(i % cpg);
-        const int64_t off = (i / cpg) * C + c;
-        float v = (xb[off] - mean) * rstd * w[g * cpg + c] + b[g * cpg + c];
-        if (relu) v = fmaxf(v, 0.f);
-        yb[off] = v;
-    }
+}
+
+__global__ void __launch_bounds__(256) groupnorm_apply_kernel(const float* __restrict__ x, int HW, int C, int groups, const double* __restrict__ stats,
+                                                              const float* __restrict__ w, const float* __restrict__ b, float eps, int relu,
+                                                              float* __restrict__ y, int64_t total4) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total4) return;
+    const int c4 = C >> 2;
+    const int c = (int)(i % c4) * 4;
+    const int64_t pix = i / c4;
+    const int n = (int)(pix / HW);
+    const int cpg = C / groups;
+    const int g = c / cpg;
+    const double cnt = (double)HW * cpg;
+    const double mean = stats[((int64_t)n * groups + g) * 2] / cnt;
+    const double var = stats[((int64_t)n * groups + g) * 2 + 1] / cnt - mean * mean;
+    const float mu = (float)mean, rstd = (float)(1.0 / sqrt(var + (double)eps));
+    float4 v = *reinterpret_cast<const float4*>(x + i * 4);
+    const float4 ww = *reinterpret_cast<const float4*>(w + c), bb = *reinterpret_cast<const float4*>(b + c);
+    v.x = (v.x - mu) * rstd * ww.x + bb.x; v.y = (v.y - mu) * rstd * ww.y + bb.y;
+    v.z = (v.z - mu) * rstd * ww.z + bb.z; v.w = (v.w - mu) * rstd * ww.w + bb.w;
+    if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    *reinterpret_cast<float4*>(y + i * 4) = v;
 }
 
 inline unsigned grid_for(int64_t n, int threads = 256) { return (unsigned)((n + threads - 1) / threads); }
@@ -419,12 +430,13 @@ int siu3r_layernorm(const float* x, int64_t ldx, const float* w, const float* b,
 }
 
 int siu3r_rope2d(float* tokens, const int64_t* positions, int B, int N, int H, int D, int64_t batch_stride, int64_t token_stride,
-                 float base, float fwd, void* stream_) {
+                 float base, float fwd, int nparts, int64_t part_stride, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     SIU3R_REQUIRE(tokens && positions && B > 0 && N > 0 && H > 0);
     SIU3R_REQUIRE(D % 4 == 0);  // "token dim must be multiple of 4" (kernels.cu:94)
-    const int64_t total = (int64_t)B * N * H * 2 * (D / 4);
-    rope2d_kernel<<<grid_for(total), 256, 0, stream>>>(tokens, positions, B, N, H, D, batch_stride, token_stride, base, fwd);
+    SIU3R_REQUIRE(nparts >= 1);
+    const int64_t total = (int64_t)B * N * nparts * H * 2 * (D / 4);
+    rope2d_kernel<<<grid_for(total), 256, 0, stream>>>(tokens, positions, B, N, H, D, batch_stride, token_stride, base, fwd, nparts, part_stride);
     SIU3R_LAUNCH_CHECK();
     siu3r_note_launch(1);
     return SIU3R_OK;
@@ -550,13 +562,19 @@ int siu3r_dwconv3x3_nhwc(const float* x, int64_t ldx, int64_t batch_stride_x, in
     return SIU3R_OK;
 }
 
+// stats_ws: device scratch of N*groups*2 doubles (zeroed here)
 int siu3r_groupnorm_nhwc(const float* x, int N, int HW, int C, int groups, const float* w, const float* b, float eps, int relu, float* y,
-                         void* stream_) {
+                         double* stats_ws, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    SIU3R_REQUIRE(x && y && w && b && groups > 0 && C % groups == 0);
-    groupnorm_kernel<<<N * groups, 256, 0, stream>>>(x, HW, C, groups, w, b, eps, relu, y);
+    SIU3R_REQUIRE(x && y && w && b && stats_ws && groups > 0 && groups <= 32 && C % groups == 0);
+    SIU3R_REQUIRE(C % 4 == 0 && (C / groups) % 4 == 0 && 256 % (C / 4) == 0);
+    SIU3R_CUDA_CHECK(cudaMemsetAsync(stats_ws, 0, sizeof(double) * 2 * N * groups, stream));
+    const int chunks = max(1, min(256, HW / 64));
+    groupnorm_stats_kernel<<<dim3(chunks, N), 256, 0, stream>>>(x, HW, C, groups, stats_ws);
+    const int64_t total4 = (int64_t)N * HW * (C / 4);
+    groupnorm_apply_kernel<<<grid_for(total4), 256, 0, stream>>>(x, HW, C, groups, stats_ws, w, b, eps, relu, y, total4);
     SIU3R_LAUNCH_CHECK();
-    siu3r_note_launch(1);
+    siu3r_note_launch(2);
     return SIU3R_OK;
 }
 

@@ -222,6 +222,27 @@ class SIU3RModel:
         self._cache[key] = k
         return k
 
+    def _par(self, fns):
+        """Run independent branches on side streams (fork/join with events; captured as parallel graph branches).
+        Every branch starts after all work enqueued so far and the caller's stream resumes after all of them."""
+        if not getattr(self, "_streams", None):
+            self._streams = [torch.cuda.Stream(device=self.dev) for _ in range(6)]
+        cur = torch.cuda.current_stream()
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        out = []
+        used = []
+        for i, fn in enumerate(fns):
+            st = self._streams[i % len(self._streams)]
+            if st not in used:
+                st.wait_event(fork)
+                used.append(st)
+            with torch.cuda.stream(st):
+                out.append(fn())
+        for st in used:
+            cur.wait_stream(st)
+        return out
+
     def _cap(self, name, t):
         if self.capture is not None:
             self.capture[name] = t
@@ -245,8 +266,7 @@ class SIU3RModel:
     def _self_attn(self, h, blk, pos, Bn, N, C, nh):
         M = Bn * N
         qkv = self._lin(h, blk.qkv, ar=True)
-        ops.rope2d_(qkv, 0, pos, Bn, N, nh, 64, N * 3 * C, 3 * C)
-        ops.rope2d_(qkv, C, pos, Bn, N, nh, 64, N * 3 * C, 3 * C)
+        ops.rope2d_(qkv, 0, pos, Bn, N, nh, 64, N * 3 * C, 3 * C, nparts=2, part_stride=C)  # q and k in one launch
         a = torch.empty(M, C, device=self.dev)
         ops.flash_attn_d64(qkv, 0, N * 3 * C, 3 * C, qkv, C, N * 3 * C, 3 * C, qkv, 2 * C, N * 3 * C, 3 * C, a, Bn, nh, N, N, 0.125, self.prec,
                            round_out=self.R)
@@ -651,8 +671,9 @@ class SIU3RModel:
         f1, f2 = f[:B * N], f[B * N:]
         dec1, dec2 = [feat[:B * N]], [feat[B * N:]]
         for l in range(c.dec_depth):
-            n1 = self._dec_block(w.dec[0][l], f1, f2, k.pos_dec, B, N)
-            n2 = self._dec_block(w.dec[1][l], f2, f1, k.pos_dec, B, N)
+            # the two views use different weights and only read the previous layer's pair: two parallel branches
+            n1, n2 = self._par([lambda: self._dec_block(w.dec[0][l], f1, f2, k.pos_dec, B, N),
+                                lambda: self._dec_block(w.dec[1][l], f2, f1, k.pos_dec, B, N)])
             f1, f2 = n1, n2
             dec1.append(f1)
             dec2.append(f2)
@@ -660,21 +681,21 @@ class SIU3RModel:
             self._cap(f"dec2_{l}", f2)
         dec1[-1] = ops.layernorm(dec1[-1], w.dec_norm[0], w.dec_norm[1], 1e-6)
         dec2[-1] = ops.layernorm(dec2[-1], w.dec_norm[0], w.dec_norm[1], 1e-6)
-        # ---- adapter (per view) -> multi-scale features [B*T, h, w, 1024] ----
+        # ---- adapter (per view) + the four DPT heads: six independent branches ----
         shapes = [(S0 // 4, S1 // 4), (S0 // 8, S1 // 8), (S0 // 16, S1 // 16), (S0 // 32, S1 // 32)]
         ms = [torch.empty(B * 2, h, w_, 1024, device=self.dev) for (h, w_) in shapes]
-        for v in range(2):
-            self._adapter(img4[v * B:(v + 1) * B], keep, k, B, N, gh, gw, ms, v)
-        self._cap("adapter_ms", ms)
-        # ---- Gaussian heads ----
         G1 = S0 * S1
         means = torch.empty(B, 2, G1, 3, device=self.dev)
         hooks = [0, c.dec_depth * 2 // 4, c.dec_depth * 3 // 4, c.dec_depth]
-        raws = []
-        for v, dec in enumerate((dec1, dec2)):
-            toks = [dec[hk] for hk in hooks]
-            self._center_head(w.heads[f"downstream_head{v + 1}"], toks, B, N, gh, gw, means, v)
-            raws.append(self._gs_head(w.heads[f"gaussian_param_head{v + 1}"], toks, img4[v * B:(v + 1) * B], B, N, gh, gw))
+        toks = [[dec1[hk] for hk in hooks], [dec2[hk] for hk in hooks]]
+        branches = []
+        for v in range(2):
+            branches.append(lambda v=v: self._adapter(img4[v * B:(v + 1) * B], keep, k, B, N, gh, gw, ms, v))
+            branches.append(lambda v=v: self._center_head(w.heads[f"downstream_head{v + 1}"], toks[v], B, N, gh, gw, means, v))
+            branches.append(lambda v=v: self._gs_head(w.heads[f"gaussian_param_head{v + 1}"], toks[v], img4[v * B:(v + 1) * B], B, N, gh, gw))
+        res = self._par(branches)
+        raws = [res[2], res[5]]
+        self._cap("adapter_ms", ms)
         self._cap("gs_raw", raws)
         cov = torch.empty(B, 2 * G1, 3, 3, device=self.dev)
         harm = torch.empty(B, 2 * G1, 3, 25, device=self.dev)

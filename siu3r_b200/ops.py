@@ -216,11 +216,11 @@ def layernorm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float, out
 
 
 def rope2d_(tokens_ptr_tensor: torch.Tensor, offset: int, positions: torch.Tensor, B: int, N: int, H: int, D: int, batch_stride: int,
-            token_stride: int, base: float = 100.0, fwd: float = 1.0):
+            token_stride: int, base: float = 100.0, fwd: float = 1.0, nparts: int = 1, part_stride: int = 0):
     """In-place 2-D RoPE on tokens[b,n,h,d] located at tokens.data_ptr() + 4*(offset + b*batch_stride + n*token_stride + h*D + d)."""
     assert positions.dtype == torch.int64 and positions.is_cuda and positions.is_contiguous()
     code = _lib.load().siu3r_rope2d(tokens_ptr_tensor.data_ptr() + 4 * offset, _p(positions), B, N, H, D, batch_stride, token_stride, base, fwd,
-                                    _stream())
+                                    nparts, part_stride, _stream())
     _lib.check(code, "rope2d")
 
 
@@ -338,7 +338,8 @@ def groupnorm(x: torch.Tensor, groups: int, w: torch.Tensor, b: torch.Tensor, ep
     N, HW, Cc = x.shape
     if out is None:
         out = torch.empty_like(x)
-    _lib.check(_lib.load().siu3r_groupnorm_nhwc(_p(x), N, HW, Cc, groups, _p(w), _p(b), eps, 1 if relu else 0, _p(out), _stream()), "groupnorm")
+    ws = torch.empty(N * groups * 2, device=x.device, dtype=torch.float64)
+    _lib.check(_lib.load().siu3r_groupnorm_nhwc(_p(x), N, HW, Cc, groups, _p(w), _p(b), eps, 1 if relu else 0, _p(out), _p(ws), _stream()), "groupnorm")
     return out
 
 

@@ -155,12 +155,11 @@ def test_rope2d_vs_oracle_and_torch(oracle_lib):
     k_ref = RO.rope2d(qkv[:, :, 1].contiguous().cpu().numpy(), pos.numpy())
     v_before = qkv[:, :, 2].clone()
     posd = pos.to(DEV)
-    ops.rope2d_(qkv, 0, posd, B, N, H, D, N * 3 * H * D, 3 * H * D)
-    ops.rope2d_(qkv, H * D, posd, B, N, H, D, N * 3 * H * D, 3 * H * D)
+    ops.rope2d_(qkv, 0, posd, B, N, H, D, N * 3 * H * D, 3 * H * D, nparts=2, part_stride=H * D)
     assert np.abs(qkv[:, :, 0].cpu().numpy() - q_ref).max() < 3e-5
     assert np.abs(qkv[:, :, 1].cpu().numpy() - k_ref).max() < 3e-5
     assert torch.equal(qkv[:, :, 2], v_before)
-    lib_err = __import__("siu3r_b200._lib", fromlist=["x"]).load().siu3r_rope2d(qkv.data_ptr(), posd.data_ptr(), 1, 1, 1, 6, 6, 6, 100.0, 1.0, None)
+    lib_err = __import__("siu3r_b200._lib", fromlist=["x"]).load().siu3r_rope2d(qkv.data_ptr(), posd.data_ptr(), 1, 1, 1, 6, 6, 6, 100.0, 1.0, 1, 0, None)
     assert lib_err == -1  # D % 4 != 0 -> invalid argument (kernels.cu:94 contract)
 
 

@@ -69,7 +69,7 @@ void siu3r_gemm_debug_set(long long* dev_buf);   /* profiling aid: per-CTA clock
  * [B,N,2] int64 (y, x); nparts > 1 rotates several tensors that share the positions in one launch (q and k
  * of the fused qkv buffer: part_stride = C).  Error contract: D % 4 != 0 -> -1 ("token dim must be multiple of 4", kernels.cu:94). */
 int siu3r_rope2d(float* tokens, const int64_t* positions, int B, int N, int H, int D, int64_t batch_stride,
-                 int64_t token_stride, float base, float fwd, int nparts, int64_t part_stride, void* stream);
+                 int64_t token_stride, float base, float fwd, int nparts, int64_t part_stride, int round_out, void* stream);
 /* nn.LayerNorm over the last dim (+ optional fused add of `add` rows): croco/blocks.py:119-125,176-184 */
 int siu3r_layernorm(const float* x, int64_t ldx, const float* w, const float* b, float* y, int64_t ldy, int rows, int C,
                     float eps, const float* add, int64_t ldadd, int round_out, void* stream);
@@ -77,6 +77,11 @@ int siu3r_layernorm(const float* x, int64_t ldx, const float* w, const float* b,
 int siu3r_flash_attn_d64(const float* Q, int64_t q_bs, int64_t q_ts, const float* K, int64_t k_bs, int64_t k_ts,
                          const float* V, int64_t v_bs, int64_t v_ts, float* O, int64_t o_bs, int64_t o_ts, int B, int H,
                          int Nq, int Nk, float scale, int precision, int round_out, void* stream);
+/* tcgen05 / TMEM flash attention (TF32 mode) and its V^T producer: same contract as siu3r_flash_attn_d64 */
+int siu3r_transpose_v(const float* V, int64_t v_bs, int64_t v_ts, int B, int N, int H, float* Vt, int64_t ld, void* stream);
+int siu3r_flash_attn_tc(const float* Q, int64_t q_bs, int64_t q_ts, int q_width, int q_col0, const float* K, int64_t k_bs,
+                        int64_t k_ts, int k_width, int k_col0, const float* Vt, int64_t vt_ld, float* O, int64_t o_bs,
+                        int64_t o_ts, int B, int H, int Nq, int Nk, float scale, int round_out, void* stream);
 /* masked / plain attention with head dim 32: mask2former/video_seg_decoder.py:975-983,994-999,1306-1308 */
 int siu3r_attn_small_d32(const float* Q, int64_t q_bs, int64_t q_ts, const float* K, int64_t k_bs, int64_t k_ts,
                          const float* V, int64_t v_bs, int64_t v_ts, float* O, int64_t o_bs, int64_t o_ts,

@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) rope2d_kernel(float* __restrict__ tokens, const int64_t* __restrict__ pos, int B, int N, int H, int D,
                                                      int64_t batch_stride, int64_t token_stride, float base, float fwd, int nparts,
-                                                     int64_t part_stride) {
+                                                     int64_t part_stride, int round_out) {
     const int Q = D >> 2;
     const int64_t total = (int64_t)B * N * nparts * H * 2 * Q;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -94,8 +94,9 @@ __global__ void __launch_bounds__(256) rope2d_kernel(float* __restrict__ tokens,
     sincosf(f, &s, &c);
     float* p = tokens + (int64_t)b * batch_stride + (int64_t)n * token_stride + (int64_t)h * D + xh * (D >> 1) + d;
     const float u = p[0], v = p[Q];
-    p[0] = u * c - v * s;
-    p[Q] = v * c + u * s;
+    const float o0 = u * c - v * s, o1 = v * c + u * s;
+    p[0] = round_out ? rn_tf32(o0) : o0;   // q / k only feed the TF32 attention: round to nearest here (the tensor core truncates)
+    p[Q] = round_out ? rn_tf32(o1) : o1;
 }
 
 // x = hi + lo with hi = RN_tf32(x), lo = RN_tf32(x - hi): operands of the 3xTF32 tensor-core path
@@ -430,13 +431,13 @@ int siu3r_layernorm(const float* x, int64_t ldx, const float* w, const float* b,
 }
 
 int siu3r_rope2d(float* tokens, const int64_t* positions, int B, int N, int H, int D, int64_t batch_stride, int64_t token_stride,
-                 float base, float fwd, int nparts, int64_t part_stride, void* stream_) {
+                 float base, float fwd, int nparts, int64_t part_stride, int round_out, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     SIU3R_REQUIRE(tokens && positions && B > 0 && N > 0 && H > 0);
     SIU3R_REQUIRE(D % 4 == 0);  // "token dim must be multiple of 4" (kernels.cu:94)
     SIU3R_REQUIRE(nparts >= 1);
     const int64_t total = (int64_t)B * N * nparts * H * 2 * (D / 4);
-    rope2d_kernel<<<grid_for(total), 256, 0, stream>>>(tokens, positions, B, N, H, D, batch_stride, token_stride, base, fwd, nparts, part_stride);
+    rope2d_kernel<<<grid_for(total), 256, 0, stream>>>(tokens, positions, B, N, H, D, batch_stride, token_stride, base, fwd, nparts, part_stride, round_out);
     SIU3R_LAUNCH_CHECK();
     siu3r_note_launch(1);
     return SIU3R_OK;

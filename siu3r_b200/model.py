@@ -266,10 +266,13 @@ class SIU3RModel:
     def _self_attn(self, h, blk, pos, Bn, N, C, nh):
         M = Bn * N
         qkv = self._lin(h, blk.qkv, ar=True)
-        ops.rope2d_(qkv, 0, pos, Bn, N, nh, 64, N * 3 * C, 3 * C, nparts=2, part_stride=C)  # q and k in one launch
+        ops.rope2d_(qkv, 0, pos, Bn, N, nh, 64, N * 3 * C, 3 * C, nparts=2, part_stride=C, round_out=self.R)  # q and k in one launch
         a = torch.empty(M, C, device=self.dev)
-        ops.flash_attn_d64(qkv, 0, N * 3 * C, 3 * C, qkv, C, N * 3 * C, 3 * C, qkv, 2 * C, N * 3 * C, 3 * C, a, Bn, nh, N, N, 0.125, self.prec,
-                           round_out=self.R)
+        if self.R:   # TF32 mode: tcgen05 / TMEM flash attention
+            ops.flash_attn_tc(qkv, 0, N * 3 * C, 3 * C, 3 * C, qkv, C, N * 3 * C, 3 * C, 3 * C, qkv, 2 * C, N * 3 * C, 3 * C, a, Bn, nh, N, N, 0.125,
+                              round_out=True)
+        else:        # 3xTF32 mode: mma.sync kernel with the register-level split
+            ops.flash_attn_d64(qkv, 0, N * 3 * C, 3 * C, qkv, C, N * 3 * C, 3 * C, qkv, 2 * C, N * 3 * C, 3 * C, a, Bn, nh, N, N, 0.125, self.prec)
         return a
 
     def _encoder(self, x, pos, Bn, N):
@@ -305,10 +308,13 @@ class SIU3RModel:
         h2 = self._ln(x1, blk.n2, 1e-6)
         q = self._lin(h2, blk.cq, ar=True)
         kv = self._lin(yn, blk.ckv, ar=True)
-        ops.rope2d_(q, 0, pos, B, N, nh, 64, N * C, C)
-        ops.rope2d_(kv, 0, pos, B, N, nh, 64, N * 2 * C, 2 * C)
+        ops.rope2d_(q, 0, pos, B, N, nh, 64, N * C, C, round_out=self.R)
+        ops.rope2d_(kv, 0, pos, B, N, nh, 64, N * 2 * C, 2 * C, round_out=self.R)
         a2 = torch.empty(B * N, C, device=self.dev)
-        ops.flash_attn_d64(q, 0, N * C, C, kv, 0, N * 2 * C, 2 * C, kv, C, N * 2 * C, 2 * C, a2, B, nh, N, N, 0.125, self.prec, round_out=self.R)
+        if self.R:
+            ops.flash_attn_tc(q, 0, N * C, C, C, kv, 0, N * 2 * C, 2 * C, 2 * C, kv, C, N * 2 * C, 2 * C, a2, B, nh, N, N, 0.125, round_out=True)
+        else:
+            ops.flash_attn_d64(q, 0, N * C, C, kv, 0, N * 2 * C, 2 * C, kv, C, N * 2 * C, 2 * C, a2, B, nh, N, N, 0.125, self.prec)
         self._lin(a2, blk.cproj, ar=True, residual=x1, out=x1)
         h3 = self._ln(x1, blk.n3, 1e-6)
         f = self._lin(h3, blk.fc1, ar=True, ro=True, act=ACT_GELU)

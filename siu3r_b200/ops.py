@@ -216,11 +216,11 @@ def layernorm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float, out
 
 
 def rope2d_(tokens_ptr_tensor: torch.Tensor, offset: int, positions: torch.Tensor, B: int, N: int, H: int, D: int, batch_stride: int,
-            token_stride: int, base: float = 100.0, fwd: float = 1.0, nparts: int = 1, part_stride: int = 0):
+            token_stride: int, base: float = 100.0, fwd: float = 1.0, nparts: int = 1, part_stride: int = 0, round_out: bool = False):
     """In-place 2-D RoPE on tokens[b,n,h,d] located at tokens.data_ptr() + 4*(offset + b*batch_stride + n*token_stride + h*D + d)."""
     assert positions.dtype == torch.int64 and positions.is_cuda and positions.is_contiguous()
     code = _lib.load().siu3r_rope2d(tokens_ptr_tensor.data_ptr() + 4 * offset, _p(positions), B, N, H, D, batch_stride, token_stride, base, fwd,
-                                    nparts, part_stride, _stream())
+                                    nparts, part_stride, 1 if round_out else 0, _stream())
     _lib.check(code, "rope2d")
 
 
@@ -232,6 +232,22 @@ def flash_attn_d64(q: torch.Tensor, q_off: int, q_bs: int, q_ts: int, k: torch.T
         code = _lib.load().siu3r_flash_attn_d64(q.data_ptr() + 4 * q_off, q_bs, q_ts, k.data_ptr() + 4 * k_off, k_bs, k_ts, v.data_ptr() + 4 * v_off,
                                                 v_bs, v_ts, _p(out), Nq * H * 64, H * 64, B, H, Nq, Nk, scale, precision, 1 if round_out else 0, _stream())
     _lib.check(code, "flash_attn_d64")
+    return out
+
+
+def flash_attn_tc(q: torch.Tensor, q_off: int, q_bs: int, q_ts: int, q_width: int, k: torch.Tensor, k_off: int, k_bs: int, k_ts: int, k_width: int,
+                  v: torch.Tensor, v_off: int, v_bs: int, v_ts: int, out: torch.Tensor, B: int, H: int, Nq: int, Nk: int, scale: float,
+                  round_out: bool = False):
+    """tcgen05 flash attention (TF32).  q/k: element (b, n, h, d) at tensor.data_ptr() + 4*(b*bs + n*ts + off + h*64 + d), `width` = row
+    width in floats; v likewise (transposed + rounded internally).  out [B, Nq, H*64] contiguous."""
+    lib = _lib.load()
+    ld = (Nk + 3) // 4 * 4
+    vt = torch.empty(B * H * 64, ld, device=out.device, dtype=torch.float32)
+    _lib.check(lib.siu3r_transpose_v(v.data_ptr() + 4 * v_off, v_bs, v_ts, B, Nk, H, _p(vt), ld, _stream()), "transpose_v")
+    with _Prof("flash_attn", 4.0 * B * H * Nq * Nk * 64):
+        code = lib.siu3r_flash_attn_tc(q.data_ptr(), q_bs, q_ts, q_width, q_off, k.data_ptr(), k_bs, k_ts, k_width, k_off, _p(vt), ld, _p(out),
+                                       Nq * H * 64, H * 64, B, H, Nq, Nk, scale, 1 if round_out else 0, _stream())
+    _lib.check(code, "flash_attn_tc")
     return out
 
 

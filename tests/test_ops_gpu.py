@@ -159,7 +159,7 @@ def test_rope2d_vs_oracle_and_torch(oracle_lib):
     assert np.abs(qkv[:, :, 0].cpu().numpy() - q_ref).max() < 3e-5
     assert np.abs(qkv[:, :, 1].cpu().numpy() - k_ref).max() < 3e-5
     assert torch.equal(qkv[:, :, 2], v_before)
-    lib_err = __import__("siu3r_b200._lib", fromlist=["x"]).load().siu3r_rope2d(qkv.data_ptr(), posd.data_ptr(), 1, 1, 1, 6, 6, 6, 100.0, 1.0, 1, 0, None)
+    lib_err = __import__("siu3r_b200._lib", fromlist=["x"]).load().siu3r_rope2d(qkv.data_ptr(), posd.data_ptr(), 1, 1, 1, 6, 6, 6, 100.0, 1.0, 1, 0, 0, None)
     assert lib_err == -1  # D % 4 != 0 -> invalid argument (kernels.cu:94 contract)
 
 
@@ -181,6 +181,29 @@ def test_flash_attn_d64(Nq, Nk, H, prec):
     ref = _attn_ref(q.permute(0, 2, 1, 3), k.permute(0, 2, 1, 3), v.permute(0, 2, 1, 3), D ** -0.5).permute(0, 2, 1, 3).reshape(B, Nq, H * D)
     tol = 3e-3 if prec == 1 else 3e-5
     assert rel_err(out, ref) < tol, rel_err(out, ref)
+
+
+@pytest.mark.parametrize("Nq,Nk,H", [(1025, 1025, 16), (257, 257, 12), (100, 3075, 12), (17, 17, 16), (128, 256, 2)])
+def test_flash_attn_tc(Nq, Nk, H):
+    from siu3r_b200 import ops
+    B, D = 2, 64
+    q, k, v = rnd(B, Nq, H, D, seed=58), rnd(B, Nk, H, D, seed=59), rnd(B, Nk, H, D, seed=60)
+    out = torch.empty(B, Nq, H * D, device=DEV)
+    ops.flash_attn_tc(q, 0, Nq * H * D, H * D, H * D, k, 0, Nk * H * D, H * D, H * D, v, 0, Nk * H * D, H * D, out, B, H, Nq, Nk, D ** -0.5)
+    ref = _attn_ref(q.permute(0, 2, 1, 3), k.permute(0, 2, 1, 3), v.permute(0, 2, 1, 3), D ** -0.5).permute(0, 2, 1, 3).reshape(B, Nq, H * D)
+    assert rel_err(out, ref) < 3e-3, rel_err(out, ref)
+
+
+def test_flash_attn_tc_inside_qkv_buffer():
+    from siu3r_b200 import ops
+    B, N, H, D = 2, 1025, 16, 64
+    C = H * D
+    qkv = rnd(B, N, 3, H, D, seed=61)
+    out = torch.empty(B, N, C, device=DEV)
+    ops.flash_attn_tc(qkv, 0, N * 3 * C, 3 * C, 3 * C, qkv, C, N * 3 * C, 3 * C, 3 * C, qkv, 2 * C, N * 3 * C, 3 * C, out, B, H, N, N, 0.125)
+    q, k, v = [qkv[:, :, i].permute(0, 2, 1, 3) for i in range(3)]
+    ref = _attn_ref(q, k, v, 0.125).permute(0, 2, 1, 3).reshape(B, N, C)
+    assert rel_err(out, ref) < 3e-3
 
 
 def test_flash_attn_inside_qkv_buffer():

@@ -151,7 +151,7 @@ def test_library_exports_every_declared_symbol():
     assert _lib.load().siu3r_abi_version() == 1
     # argument validation happens before any CUDA call: safe without a GPU
     assert _lib.load().siu3r_raster_workspace_bytes(0, 16, 16, 10) == -1
-    assert _lib.load().siu3r_rope2d(None, None, 1, 1, 1, 64, 64, 64, 100.0, 1.0, 1, 0, None) == -1
+    assert _lib.load().siu3r_rope2d(None, None, 1, 1, 1, 64, 64, 64, 100.0, 1.0, 1, 0, 0, None) == -1
 
 
 def test_product_path_has_no_oracle_or_torch_compute_dependency():

@@ -65,6 +65,13 @@ for prec in (1, 3):
         fl = 4 * B * H * N * N * 64
         res.append(dict(op="flash", prec=prec, B=B, H=H, N=N, ms=ms, tflops=fl / ms / 1e9))
         print(res[-1], flush=True)
+for (B, H, N) in [(2, 16, 1025), (1, 12, 1025), (8, 16, 1025)]:
+    C = H * 64
+    qkv = torch.randn(B, N, 3, H, 64, device=dev)
+    out = torch.empty(B, N, C, device=dev)
+    ms = timeit(lambda: ops.flash_attn_tc(qkv, 0, N * 3 * C, 3 * C, 3 * C, qkv, C, N * 3 * C, 3 * C, 3 * C, qkv, 2 * C, N * 3 * C, 3 * C, out, B, H, N, N, 0.125))
+    res.append(dict(op="flash_tc(+transpose)", B=B, H=H, N=N, ms=ms, tflops=4 * B * H * N * N * 64 / ms / 1e9))
+    print(res[-1], flush=True)
 # elementwise bandwidth sanity
 x = torch.randn(64 * 1024 * 1024, device=dev)
 ms = timeit(lambda: ops.eltwise(ops.ELT_RELU, x, out=x))

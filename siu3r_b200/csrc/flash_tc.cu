@@ -25,11 +25,11 @@ namespace {
 constexpr int FT_BM = 128, FT_BN = 128, FT_D = 64, FT_BK = 32;
 constexpr int FT_THREADS = 192;
 constexpr int FT_Q_BYTES = 2 * FT_BM * FT_BK * 4;        // 32 KB : 2 k-blocks [128 x 32]
-constexpr int FT_K_BYTES = 2 * FT_BN * FT_BK * 4;        // 32 KB
+constexpr int FT_K_BYTES = 2 * FT_BN * FT_BK * 4;        // 32 KB per buffer, double-buffered
 constexpr int FT_V_BYTES = 4 * FT_D * FT_BK * 4;         // 32 KB : 4 k-blocks [64 d x 32 keys]
 constexpr int FT_P_BYTES = 4 * FT_BM * FT_BK * 4;        // 64 KB : 4 k-blocks [128 q x 32 keys]
-constexpr int FT_SMEM = FT_Q_BYTES + FT_K_BYTES + FT_V_BYTES + FT_P_BYTES + 1024 + 256;
-constexpr int FT_TMEM_COLS = 256;                        // S: [0,128)  O: [128,192)
+constexpr int FT_SMEM = FT_Q_BYTES + 2 * FT_K_BYTES + FT_V_BYTES + FT_P_BYTES + 1024 + 256;
+constexpr int FT_TMEM_COLS = 512;                        // S0: [0,128)  S1: [128,256)  O: [256,320)
 
 struct FlashParams {
     int B, H, Nq, Nk;
@@ -120,8 +120,8 @@ __device__ __forceinline__ float4 lds_v4(uint32_t saddr) {
     return r;
 }
 
-// barrier indices
-enum { B_Q = 0, B_KFULL, B_KEMPTY, B_VFULL, B_VEMPTY, B_SFULL, B_SEMPTY, B_PFULL, B_OFULL, B_COUNT };
+// barrier indices (K / S barriers are double-buffered: index + buffer)
+enum { B_Q = 0, B_KFULL = 1, B_KEMPTY = 3, B_SFULL = 5, B_SEMPTY = 7, B_VFULL = 9, B_VEMPTY, B_PFULL, B_OFULL, B_COUNT };
 
 __global__ void __launch_bounds__(FT_THREADS, 1)
 flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmVt,
@@ -129,8 +129,8 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sQ = smem;
-    uint8_t* sK = sQ + FT_Q_BYTES;
-    uint8_t* sV = sK + FT_K_BYTES;
+    uint8_t* sK = sQ + FT_Q_BYTES;            // 2 buffers
+    uint8_t* sV = sK + 2 * FT_K_BYTES;
     uint8_t* sP = sV + FT_V_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sP + FT_P_BYTES);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_COUNT);
@@ -139,15 +139,18 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
     const int q0 = qt * FT_BM;
     const int ntiles = (p.Nk + FT_BN - 1) / FT_BN;
+    const int niter = 2 * ntiles;             // pass 1 (row maxima) then pass 2 (P, O)
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQ) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmK) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmVt) : "memory");
         mbar_init(&bars[B_Q], 1);
-        mbar_init(&bars[B_KFULL], 1); mbar_init(&bars[B_KEMPTY], 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bars[B_KFULL + i], 1); mbar_init(&bars[B_KEMPTY + i], 1);
+            mbar_init(&bars[B_SFULL + i], 1); mbar_init(&bars[B_SEMPTY + i], 4);   // one arrival per softmax warp
+        }
         mbar_init(&bars[B_VFULL], 1); mbar_init(&bars[B_VEMPTY], 1);
-        mbar_init(&bars[B_SFULL], 1); mbar_init(&bars[B_SEMPTY], 4);   // one arrival per softmax warp
         mbar_init(&bars[B_PFULL], 4);
         mbar_init(&bars[B_OFULL], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -160,7 +163,7 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
+    const uint32_t tmem_O = tmem_base + 256;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -168,113 +171,123 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             mbar_expect_tx(&bars[B_Q], FT_Q_BYTES);
             tma_load_3d(&tmQ, &bars[B_Q], sQ, p.q_col0 + h * FT_D, q0, b);
             tma_load_3d(&tmQ, &bars[B_Q], sQ + FT_BM * FT_BK * 4, p.q_col0 + h * FT_D + FT_BK, q0, b);
-            uint32_t kcnt = 0, vcnt = 0;
-            for (int pass = 0; pass < 2; ++pass)
-                for (int t = 0; t < ntiles; ++t) {
-                    mbar_wait(&bars[B_KEMPTY], (kcnt & 1) ^ 1);
-                    mbar_expect_tx(&bars[B_KFULL], FT_K_BYTES);
-                    tma_load_3d(&tmK, &bars[B_KFULL], sK, p.k_col0 + h * FT_D, t * FT_BN, b);
-                    tma_load_3d(&tmK, &bars[B_KFULL], sK + FT_BN * FT_BK * 4, p.k_col0 + h * FT_D + FT_BK, t * FT_BN, b);
-                    ++kcnt;
-                    if (pass == 1) {
-                        mbar_wait(&bars[B_VEMPTY], (vcnt & 1) ^ 1);
-                        mbar_expect_tx(&bars[B_VFULL], FT_V_BYTES);
+            uint32_t vcnt = 0;
+            for (int it = 0; it < niter; ++it) {
+                const int t = it < ntiles ? it : it - ntiles;
+                const int buf = it & 1;
+                const uint32_t use = (uint32_t)it >> 1;
+                mbar_wait(&bars[B_KEMPTY + buf], (use & 1) ^ 1);
+                uint8_t* dK = sK + buf * FT_K_BYTES;
+                mbar_expect_tx(&bars[B_KFULL + buf], FT_K_BYTES);
+                tma_load_3d(&tmK, &bars[B_KFULL + buf], dK, p.k_col0 + h * FT_D, t * FT_BN, b);
+                tma_load_3d(&tmK, &bars[B_KFULL + buf], dK + FT_BN * FT_BK * 4, p.k_col0 + h * FT_D + FT_BK, t * FT_BN, b);
+                if (it >= ntiles) {
+                    mbar_wait(&bars[B_VEMPTY], (vcnt & 1) ^ 1);
+                    mbar_expect_tx(&bars[B_VFULL], FT_V_BYTES);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            tma_load_2d(&tmVt, &bars[B_VFULL], sV + j * FT_D * FT_BK * 4, t * FT_BN + j * FT_BK, (b * p.H + h) * FT_D);
-                        ++vcnt;
-                    }
+                    for (int j = 0; j < 4; ++j)
+                        tma_load_2d(&tmVt, &bars[B_VFULL], sV + j * FT_D * FT_BK * 4, t * FT_BN + j * FT_BK, (b * p.H + h) * FT_D);
+                    ++vcnt;
                 }
+            }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
+        // ===================== MMA issuer (S of tile it+1 is issued before the P V of tile it) =====================
         if (lane == 0) {
             constexpr uint32_t idesc_s = make_idesc_tf32(FT_BM, FT_BN);
             constexpr uint32_t idesc_o = make_idesc_tf32(FT_BM, FT_D);
             mbar_wait(&bars[B_Q], 0);
-            uint32_t it = 0, vcnt = 0;
-            for (int pass = 0; pass < 2; ++pass)
-                for (int t = 0; t < ntiles; ++t, ++it) {
-                    mbar_wait(&bars[B_KFULL], it & 1);
-                    mbar_wait(&bars[B_SEMPTY], (it & 1) ^ 1);   // softmax finished reading the previous S
+            auto issue_s = [&](int it) {
+                const int buf = it & 1;
+                const uint32_t use = (uint32_t)it >> 1;
+                mbar_wait(&bars[B_KFULL + buf], use & 1);
+                mbar_wait(&bars[B_SEMPTY + buf], (use & 1) ^ 1);   // softmax finished reading the previous S in this buffer
+                tc_fence_after();
+                const uint32_t kb = smem_u32(sK + buf * FT_K_BYTES);
+#pragma unroll
+                for (int ks = 0; ks < FT_D / 8; ++ks) {
+                    const uint32_t blk = (ks >> 2), koff = (ks & 3) * 32;
+                    umma_tf32(tmem_base + (uint32_t)buf * 128, make_smem_desc(smem_u32(sQ) + blk * FT_BM * FT_BK * 4 + koff),
+                              make_smem_desc(kb + blk * FT_BN * FT_BK * 4 + koff), idesc_s, ks != 0);
+                }
+                umma_commit(&bars[B_KEMPTY + buf]);   // K buffer reusable
+                umma_commit(&bars[B_SFULL + buf]);    // S ready
+            };
+            issue_s(0);
+            uint32_t vcnt = 0;
+            for (int it = 0; it < niter; ++it) {
+                if (it + 1 < niter) issue_s(it + 1);
+                if (it >= ntiles) {
+                    mbar_wait(&bars[B_VFULL], vcnt & 1);
+                    mbar_wait(&bars[B_PFULL], vcnt & 1);   // P written (and fenced) by the softmax warps
                     tc_fence_after();
 #pragma unroll
-                    for (int ks = 0; ks < FT_D / 8; ++ks) {
+                    for (int ks = 0; ks < FT_BN / 8; ++ks) {
                         const uint32_t blk = (ks >> 2), koff = (ks & 3) * 32;
-                        umma_tf32(tmem_S, make_smem_desc(smem_u32(sQ) + blk * FT_BM * FT_BK * 4 + koff),
-                                  make_smem_desc(smem_u32(sK) + blk * FT_BN * FT_BK * 4 + koff), idesc_s, ks != 0);
+                        umma_tf32(tmem_O, make_smem_desc(smem_u32(sP) + blk * FT_BM * FT_BK * 4 + koff),
+                                  make_smem_desc(smem_u32(sV) + blk * FT_D * FT_BK * 4 + koff), idesc_o, (vcnt | ks) != 0);
                     }
-                    umma_commit(&bars[B_KEMPTY]);   // K tile reusable
-                    umma_commit(&bars[B_SFULL]);    // S ready
-                    if (pass == 1) {
-                        mbar_wait(&bars[B_VFULL], vcnt & 1);
-                        mbar_wait(&bars[B_PFULL], vcnt & 1);   // P written (and fenced) by the softmax warps
-                        tc_fence_after();
-#pragma unroll
-                        for (int ks = 0; ks < FT_BN / 8; ++ks) {
-                            const uint32_t blk = (ks >> 2), koff = (ks & 3) * 32;
-                            umma_tf32(tmem_O, make_smem_desc(smem_u32(sP) + blk * FT_BM * FT_BK * 4 + koff),
-                                      make_smem_desc(smem_u32(sV) + blk * FT_D * FT_BK * 4 + koff), idesc_o, (t | ks) != 0);
-                        }
-                        umma_commit(&bars[B_VEMPTY]);   // V tile and P buffer reusable once these MMAs are done
-                        ++vcnt;
-                    }
+                    umma_commit(&bars[B_VEMPTY]);   // V tile and P buffer reusable once these MMAs are done
+                    ++vcnt;
                 }
+            }
             umma_commit(&bars[B_OFULL]);
         }
     } else {
         // ===================== softmax / epilogue warps: thread = one query row =====================
         const int qd = warp & 3;                 // TMEM lane quarter
         const int r = qd * 32 + lane;            // row in the tile
-        const uint32_t tS = tmem_S + ((uint32_t)(qd * 32) << 16);
         float m = -INFINITY, l = 0.f;
-        uint32_t it = 0, vcnt = 0;
-        for (int pass = 0; pass < 2; ++pass)
-            for (int t = 0; t < ntiles; ++t, ++it) {
-                mbar_wait(&bars[B_SFULL], it & 1);
-                tc_fence_after();
-                const int kvalid = p.Nk - t * FT_BN;   // columns >= kvalid are padding
-                if (pass == 0) {
+        uint32_t vcnt = 0;
+        for (int it = 0; it < niter; ++it) {
+            const int t = it < ntiles ? it : it - ntiles;
+            const int buf = it & 1;
+            const uint32_t tS = tmem_base + (uint32_t)buf * 128 + ((uint32_t)(qd * 32) << 16);
+            mbar_wait(&bars[B_SFULL + buf], ((uint32_t)it >> 1) & 1);
+            tc_fence_after();
+            const int kvalid = p.Nk - t * FT_BN;   // columns >= kvalid are padding
+            if (it < ntiles) {
 #pragma unroll 1
-                    for (int c0 = 0; c0 < FT_BN; c0 += 32) {
-                        uint32_t v[32];
-                        tmem_ld32(tS + c0, v);
-                        tmem_ld_wait();
+                for (int c0 = 0; c0 < FT_BN; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(tS + c0, v);
+                    tmem_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (c0 + j < kvalid) m = fmaxf(m, __uint_as_float(v[j]));
-                    }
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&bars[B_SEMPTY]);
-                } else {
-                    if (vcnt > 0) mbar_wait(&bars[B_VEMPTY], (vcnt - 1) & 1);   // previous P consumed by the PV MMAs
-                    const float ms = m * p.scale_log2e;
-#pragma unroll 1
-                    for (int c0 = 0; c0 < FT_BN; c0 += 32) {
-                        uint32_t v[32];
-                        tmem_ld32(tS + c0, v);
-                        tmem_ld_wait();
-                        float pv[32];
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float e = (c0 + j < kvalid) ? exp2f(__uint_as_float(v[j]) * p.scale_log2e - ms) : 0.f;
-                            pv[j] = rn_tf32(e);
-                            l += pv[j];
-                        }
-                        // k-block c0/32 of P: row r, 128 B per row, 16-byte chunk c stored at chunk (c ^ (r & 7))
-                        const uint32_t rowaddr = smem_u32(sP) + (uint32_t)(c0 / 32) * FT_BM * FT_BK * 4 + (uint32_t)r * 128;
-#pragma unroll
-                        for (int c = 0; c < 8; ++c)
-                            sts_v4(rowaddr + (uint32_t)((c ^ (r & 7)) * 16), pv[4 * c], pv[4 * c + 1], pv[4 * c + 2], pv[4 * c + 3]);
-                    }
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA (async proxy)
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) { mbar_arrive(&bars[B_PFULL]); mbar_arrive(&bars[B_SEMPTY]); }
-                    ++vcnt;
+                    for (int j = 0; j < 32; ++j)
+                        if (c0 + j < kvalid) m = fmaxf(m, __uint_as_float(v[j]));
                 }
+            } else {
+                const float ms = m * p.scale_log2e;
+#pragma unroll 1
+                for (int c0 = 0; c0 < FT_BN; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(tS + c0, v);
+                    tmem_ld_wait();
+                    float pv[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float e = (c0 + j < kvalid) ? exp2f(__uint_as_float(v[j]) * p.scale_log2e - ms) : 0.f;
+                        pv[j] = rn_tf32(e);
+                        l += pv[j];
+                    }
+                    // the P buffer is shared by consecutive tiles: wait for the previous tile's P V only now, after the first exps
+                    if (c0 == 0 && vcnt > 0) mbar_wait(&bars[B_VEMPTY], (vcnt - 1) & 1);
+                    // k-block c0/32 of P: row r, 128 B per row, 16-byte chunk c stored at chunk (c ^ (r & 7))
+                    const uint32_t rowaddr = smem_u32(sP) + (uint32_t)(c0 / 32) * FT_BM * FT_BK * 4 + (uint32_t)r * 128;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        sts_v4(rowaddr + (uint32_t)((c ^ (r & 7)) * 16), pv[4 * c], pv[4 * c + 1], pv[4 * c + 2], pv[4 * c + 3]);
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA (async proxy)
+                ++vcnt;
             }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (it >= ntiles) mbar_arrive(&bars[B_PFULL]);
+                mbar_arrive(&bars[B_SEMPTY + buf]);
+            }
+        }
         // ---- epilogue: O / l -> global (transposed through the now idle P buffer for 128-byte coalesced stores) ----
         mbar_wait(&bars[B_OFULL], 0);
         tc_fence_after();

@@ -191,7 +191,7 @@ def test_flash_attn_tc(Nq, Nk, H):
     out = torch.empty(B, Nq, H * D, device=DEV)
     ops.flash_attn_tc(q, 0, Nq * H * D, H * D, H * D, k, 0, Nk * H * D, H * D, H * D, v, 0, Nk * H * D, H * D, out, B, H, Nq, Nk, D ** -0.5)
     ref = _attn_ref(q.permute(0, 2, 1, 3), k.permute(0, 2, 1, 3), v.permute(0, 2, 1, 3), D ** -0.5).permute(0, 2, 1, 3).reshape(B, Nq, H * D)
-    assert rel_err(out, ref) < 3e-3, rel_err(out, ref)
+    assert rel_err(out, ref) < 5e-3, rel_err(out, ref)  # raw fp32 operands: the tensor core truncates them (the engine rounds q, k, v first)
 
 
 def test_flash_attn_tc_inside_qkv_buffer():
@@ -203,7 +203,7 @@ def test_flash_attn_tc_inside_qkv_buffer():
     ops.flash_attn_tc(qkv, 0, N * 3 * C, 3 * C, 3 * C, qkv, C, N * 3 * C, 3 * C, 3 * C, qkv, 2 * C, N * 3 * C, 3 * C, out, B, H, N, N, 0.125)
     q, k, v = [qkv[:, :, i].permute(0, 2, 1, 3) for i in range(3)]
     ref = _attn_ref(q, k, v, 0.125).permute(0, 2, 1, 3).reshape(B, N, C)
-    assert rel_err(out, ref) < 3e-3
+    assert rel_err(out, ref) < 5e-3
 
 
 def test_flash_attn_inside_qkv_buffer():

@@ -227,9 +227,12 @@ def main():
 
     # ---- roofline of the dominant kernel family (instrumented pass, CUDA events on the launching stream) ----
     model.disable_cuda_graph()
+    model.serial = True   # no parallel branches: per-kernel CUDA-event durations are not inflated by co-running kernels
+    step()
     ops.PROFILE = []
     step()
     torch.cuda.synchronize()
+    model.serial = False
     fam = {}
     for f, work, s, e in ops.PROFILE:
         d = fam.setdefault(f, [0.0, 0.0, 0])

@@ -225,6 +225,8 @@ class SIU3RModel:
     def _par(self, fns):
         """Run independent branches on side streams (fork/join with events; captured as parallel graph branches).
         Every branch starts after all work enqueued so far and the caller's stream resumes after all of them."""
+        if getattr(self, "serial", False):   # profiling: one stream, clean per-kernel timings
+            return [fn() for fn in fns]
         if not getattr(self, "_streams", None):
             self._streams = [torch.cuda.Stream(device=self.dev) for _ in range(6)]
         cur = torch.cuda.current_stream()

@@ -245,6 +245,13 @@ class SIU3RModel:
             cur.wait_stream(st)
         return out
 
+    def _mark(self, name):
+        """Stage timing marks (tools/stage_times.py): external events so that they also become nodes of a captured graph."""
+        if getattr(self, "marks", None) is not None:
+            ev = torch.cuda.Event(enable_timing=True, external=True)
+            ev.record()
+            self.marks[name] = ev
+
     def _cap(self, name, t):
         if self.capture is not None:
             self.capture[name] = t
@@ -298,6 +305,9 @@ class SIU3RModel:
                 keep[i] = x
                 frozen = True
                 self._cap(f"enc{i}", x)
+                ev = torch.cuda.Event()
+                ev.record()
+                self._keep_ev[i] = ev   # the adapter stream starts interaction #k as soon as its ViT block is done
         return x, keep
 
     def _dec_block(self, blk, x, y, pos, B, N):
@@ -412,56 +422,67 @@ class SIU3RModel:
             off += cnt
         self._lin(dw, ex.fc2, residual=c, out=c)
 
-    def _adapter(self, img4, feats, k, B, N, gh, gw, out_slots, v):
-        """img4 [B,S0,S1,4]; feats: {block idx: [2B*N, 1024]} -> writes f1..f4 of view v into out_slots[l][b*2+v]."""
+    def _adapter_stem(self, img4):
+        """SpatialPriorModule convs (vit_adapter/blocks.py:200-262): depends on the image only."""
         a = self.w.adapter
-        P = gh * gw
         x = self._conv(img4, a.stem[0], 3, ro=True, stride=2, pad=1, act=ACT_RELU)
         x = self._conv(x, a.stem[1], 3, ar=True, ro=True, pad=1, act=ACT_RELU)
         x = self._conv(x, a.stem[2], 3, ar=True, ro=True, pad=1, act=ACT_RELU)
-        c1 = ops.maxpool3x3s2(x)                                           # [B, S/4, S/4, 64] (max of rounded values stays rounded)
+        c1 = ops.maxpool3x3s2(x)                                           # [Bn, S/4, S/4, 64] (max of rounded values stays rounded)
         c2 = self._conv(c1, a.conv2, 3, ro=True, stride=2, pad=1, act=ACT_RELU)     # S/8, 128
         c3 = self._conv(c2, a.conv3, 3, ro=True, stride=2, pad=1, act=ACT_RELU)     # S/16, 256
         c4 = self._conv(c3, a.conv4, 3, ro=True, stride=2, pad=1, act=ACT_RELU)     # S/32, 256
-        c1 = self._conv(c1, a.fc1, 1, ar=True)                             # [B, S/4, S/4, 1024]
+        c1 = self._conv(c1, a.fc1, 1, ar=True)                             # [Bn, S/4, S/4, 1024]
+        return c1, c2, c3, c4
+
+    def _adapter(self, img4, feats, k, B, N, gh, gw, out_slots):
+        """img4 [2B,S0,S1,4] view-major (image j = v*B + b); feats: {block idx: [2B*N, 1024]} -> f1..f4 of every image into
+        out_slots[l][b*2+v].  Both views go through every kernel as one batch."""
+        a = self.w.adapter
+        P = gh * gw
+        Bn = 2 * B
+        c1, c2, c3, c4 = self._adapter_stem(img4)
         n2, n3, n4 = 4 * P, P, P // 4
         Lq = n2 + n3 + n4
-        c = torch.empty(B, Lq, 1024, device=self.dev)
-        for b in range(B):  # fc2..4 (+ level embed folded into the bias) written straight into the concatenated query buffer
+        c = torch.empty(Bn, Lq, 1024, device=self.dev)
+        for b in range(Bn):  # fc2..4 (+ level embed folded into the bias) written straight into the concatenated query buffer
             self._lin(c2[b].view(n2, -1), a.fc[0], ar=True, out=c[b, :n2])
             self._lin(c3[b].view(n3, -1), a.fc[1], ar=True, out=c[b, n2:n2 + n3])
             self._lin(c4[b].view(n4, -1), a.fc[2], ar=True, out=c[b, n2 + n3:])
-        c = c.view(B * Lq, 1024)
+        c = c.view(Bn * Lq, 1024)
         for i, exs in enumerate(a.inter):
-            src = feats[self.cfg.interaction_indexes[i]][v * B * N:(v + 1) * B * N]
+            idx = self.cfg.interaction_indexes[i]
+            if idx in self._keep_ev:
+                torch.cuda.current_stream().wait_event(self._keep_ev[idx])
             for ex in exs:
-                self._extractor(ex, c, src, k, B, N, P, gh, gw)
-        c = c.view(B, Lq, 1024)
+                self._extractor(ex, c, feats[idx], k, Bn, N, P, gh, gw)
+        c = c.view(Bn, Lq, 1024)
         # c1 = up(c2) + c1
-        c2d = torch.empty(B, n2, 1024, device=self.dev)
-        for b in range(B):
+        c2d = torch.empty(Bn, n2, 1024, device=self.dev)
+        for b in range(Bn):
             ops.rows_affine(c[b, :n2], out=c2d[b])
-        g = self._lin(c2d.view(B * n2, 1024), a.up)
-        c1 = ops.pixel_shuffle(g, B, 2 * gh, 2 * gw, 1024, a.up_s, add=c1)
-        maps = [c1, c2d.view(B, 2 * gh, 2 * gw, 1024), None, None]
-        c3d = torch.empty(B, gh, gw, 1024, device=self.dev)
-        c4d = torch.empty(B, gh // 2, gw // 2, 1024, device=self.dev)
-        for b in range(B):
+        g = self._lin(c2d.view(Bn * n2, 1024), a.up)
+        c1 = ops.pixel_shuffle(g, Bn, 2 * gh, 2 * gw, 1024, a.up_s, add=c1)
+        maps = [c1, c2d.view(Bn, 2 * gh, 2 * gw, 1024), None, None]
+        c3d = torch.empty(Bn, gh, gw, 1024, device=self.dev)
+        c4d = torch.empty(Bn, gh // 2, gw // 2, 1024, device=self.dev)
+        for b in range(Bn):
             ops.rows_affine(c[b, n2:n2 + n3], out=c3d[b].view(n3, 1024))
             ops.rows_affine(c[b, n2 + n3:], out=c4d[b].view(n4, 1024))
         maps[2], maps[3] = c3d, c4d
         # + bilinear-resized ViT features (align_corners=False), then eval-mode BatchNorm
         for l, (scale_hw, idx) in enumerate(zip(((4 * gh, 4 * gw), (2 * gh, 2 * gw), (gh, gw), (gh // 2, gw // 2)), self.cfg.interaction_indexes)):
-            src = feats[idx][v * B * N:(v + 1) * B * N]
-            for b in range(B):
-                xb = src[b * N: b * N + P].view(1, gh, gw, 1024)
+            src = feats[idx]
+            for j in range(Bn):
+                v, b = divmod(j, B)
+                xb = src[j * N: j * N + P].view(1, gh, gw, 1024)
                 if l == 2:
-                    ops.eltwise(ELT_ADD, maps[l][b].view(P, 1024), xb.view(P, 1024).contiguous(), out=maps[l][b].view(P, 1024))
+                    ops.eltwise(ELT_ADD, maps[l][j].view(P, 1024), xb.view(P, 1024).contiguous(), out=maps[l][j].view(P, 1024))
                 else:
-                    ops.resize_bilinear(xb, scale_hw[0], scale_hw[1], False, out=maps[l][b:b + 1], accumulate=True)
+                    ops.resize_bilinear(xb, scale_hw[0], scale_hw[1], False, out=maps[l][j:j + 1], accumulate=True)
                 sc, sh = a.bn[l]
                 rows = scale_hw[0] * scale_hw[1]
-                ops.rows_affine(maps[l][b].view(rows, 1024), scale=sc, shift=sh, out=out_slots[l][b * 2 + v].view(rows, 1024))
+                ops.rows_affine(maps[l][j].view(rows, 1024), scale=sc, shift=sh, out=out_slots[l][b * 2 + v].view(rows, 1024))
 
     # ---- Mask2Former (mask2former/video_seg_decoder.py:2072-2196, 1506-1575, 1204-1360) ---------------------------------
     def _m2f(self, feats, k, B, S0, S1):
@@ -671,7 +692,34 @@ class SIU3RModel:
         Kflat = Kin.view(B, 18)
         for v in range(2):  # intrinsics token = Linear(9 -> 1024) on the flattened K (backbone_croco.py:278-280)
             ops.gemm_simt(Kflat[:, 9 * v: 9 * v + 9], w.intr_w, w.intr_b, out=x[v * B * N + P:: N][:B])
+        # DAG: the panoptic chain (adapter -> Mask2Former) only needs the image and the four kept encoder outputs, so it runs
+        # on its own stream next to the rest of the encoder, the decoder and the Gaussian heads (one graph branch when captured).
+        self._keep_ev = {}
+        serial = getattr(self, "serial", False)
+        main = torch.cuda.current_stream()
+        if not serial:
+            if getattr(self, "_seg_stream", None) is None:
+                self._seg_stream = torch.cuda.Stream(device=self.dev)
+            fork = torch.cuda.Event()
+            fork.record(main)
+        self._mark("start")
         x, keep = self._encoder(x, k.pos_enc, Bn, N)
+        self._mark("encoder")
+        shapes = [(S0 // 4, S1 // 4), (S0 // 8, S1 // 8), (S0 // 16, S1 // 16), (S0 // 32, S1 // 32)]
+        ms = [torch.empty(B * 2, h, w_, 1024, device=self.dev) for (h, w_) in shapes]
+
+        def seg_chain():
+            self._adapter(img4, keep, k, B, N, gh, gw, ms)
+            self._cap("adapter_ms", ms)
+            self._mark("adapter")
+            r = self._m2f(ms, k, B, S0, S1)
+            self._mark("m2f")
+            return r
+
+        if not serial:
+            self._seg_stream.wait_event(fork)
+            with torch.cuda.stream(self._seg_stream):
+                cls_logits, mask_logits = seg_chain()
         feat = ops.layernorm(x, w.enc_norm[0], w.enc_norm[1], 1e-6)  # [2B*N, 1024]
         self._cap("enc_norm", feat)
         # ---- decoder ----
@@ -689,21 +737,18 @@ class SIU3RModel:
             self._cap(f"dec2_{l}", f2)
         dec1[-1] = ops.layernorm(dec1[-1], w.dec_norm[0], w.dec_norm[1], 1e-6)
         dec2[-1] = ops.layernorm(dec2[-1], w.dec_norm[0], w.dec_norm[1], 1e-6)
-        # ---- adapter (per view) + the four DPT heads: six independent branches ----
-        shapes = [(S0 // 4, S1 // 4), (S0 // 8, S1 // 8), (S0 // 16, S1 // 16), (S0 // 32, S1 // 32)]
-        ms = [torch.empty(B * 2, h, w_, 1024, device=self.dev) for (h, w_) in shapes]
+        self._mark("decoder")
+        # ---- the four DPT heads: independent branches ----
         G1 = S0 * S1
         means = torch.empty(B, 2, G1, 3, device=self.dev)
         hooks = [0, c.dec_depth * 2 // 4, c.dec_depth * 3 // 4, c.dec_depth]
         toks = [[dec1[hk] for hk in hooks], [dec2[hk] for hk in hooks]]
         branches = []
         for v in range(2):
-            branches.append(lambda v=v: self._adapter(img4[v * B:(v + 1) * B], keep, k, B, N, gh, gw, ms, v))
             branches.append(lambda v=v: self._center_head(w.heads[f"downstream_head{v + 1}"], toks[v], B, N, gh, gw, means, v))
             branches.append(lambda v=v: self._gs_head(w.heads[f"gaussian_param_head{v + 1}"], toks[v], img4[v * B:(v + 1) * B], B, N, gh, gw))
         res = self._par(branches)
-        raws = [res[2], res[5]]
-        self._cap("adapter_ms", ms)
+        raws = [res[1], res[3]]
         self._cap("gs_raw", raws)
         cov = torch.empty(B, 2 * G1, 3, 3, device=self.dev)
         harm = torch.empty(B, 2 * G1, 3, 25, device=self.dev)
@@ -715,7 +760,12 @@ class SIU3RModel:
                 o = v * G1
                 ops._lib.check(lib.siu3r_gaussian_adapter(raws[v][b].data_ptr(), G1, cov[b, o:].data_ptr(), harm[b, o:].data_ptr(), opac[b, o:].data_ptr(),
                                                           scales[b, o:].data_ptr(), rots[b, o:].data_ptr(), ops._stream()), "gaussian_adapter")
-        cls_logits, mask_logits = self._m2f(ms, k, B, S0, S1)
+        self._mark("heads")
+        if serial:
+            cls_logits, mask_logits = seg_chain()
+        else:
+            main.wait_stream(self._seg_stream)
+        self._mark("end")
         return means.view(B, 2 * G1, 3), cov, harm, opac, scales, rots, cls_logits, mask_logits
 
     @torch.no_grad()

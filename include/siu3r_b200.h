@@ -53,6 +53,11 @@ int siu3r_raster_forward(int G, int H, int W, int sh_degree, int sh_coeffs, int 
 int siu3r_gemm_tc(int M, int N, int K, const float* A, const float* A_lo, int64_t lda, const float* Wt, const float* W_lo,
                   int64_t ldw, float* C, int64_t ldc, const float* bias, const float* residual, int64_t ldr, int act,
                   float alpha, int precision, void* stream);
+/* nn.Linear + curope.rope_2d on output columns [0, rope_cols) in one kernel (the q / k columns of the qkv, q and kv
+ * projections, croco/blocks.py:97-103,154-160); positions [M,2] int64, rope_tab from siu3r_rope2d_table (head dim 64) */
+int siu3r_gemm_tc_rope(int M, int N, int K, const float* A, const float* A_lo, int64_t lda, const float* Wt, const float* W_lo,
+                       int64_t ldw, float* C, int64_t ldc, const float* bias, int act, int precision, const int64_t* positions,
+                       const float* rope_tab, int rope_cols, void* stream);
 int siu3r_conv2d_tc(int Nimg, int H, int W, int Cin, int Cout, int KH, int KW, int pad, const float* x, const float* x_lo,
                     const float* Wt, const float* W_lo, float* y, int64_t ldc, const float* bias, const float* residual,
                     int64_t ldr, int act, int precision, void* stream);
@@ -70,6 +75,8 @@ void siu3r_gemm_debug_set(long long* dev_buf);   /* profiling aid: per-CTA clock
  * of the fused qkv buffer: part_stride = C).  Error contract: D % 4 != 0 -> -1 ("token dim must be multiple of 4", kernels.cu:94). */
 int siu3r_rope2d(float* tokens, const int64_t* positions, int B, int N, int H, int D, int64_t batch_stride,
                  int64_t token_stride, float base, float fwd, int nparts, int64_t part_stride, int round_out, void* stream);
+/* tab[maxpos][D/4] (cos, sin) float pairs of pos * fwd / base^(d/(D/4)): the per-position factors of kernels.cu:36-48 */
+int siu3r_rope2d_table(float* tab, int maxpos, int D, float base, float fwd, void* stream);
 /* nn.LayerNorm over the last dim (+ optional fused add of `add` rows): croco/blocks.py:119-125,176-184 */
 int siu3r_layernorm(const float* x, int64_t ldx, const float* w, const float* b, float* y, int64_t ldy, int rows, int C,
                     float eps, const float* add, int64_t ldadd, int round_out, void* stream);
@@ -82,10 +89,14 @@ int siu3r_transpose_v(const float* V, int64_t v_bs, int64_t v_ts, int B, int N, 
 int siu3r_flash_attn_tc(const float* Q, int64_t q_bs, int64_t q_ts, int q_width, int q_col0, const float* K, int64_t k_bs,
                         int64_t k_ts, int k_width, int k_col0, const float* Vt, int64_t vt_ld, float* O, int64_t o_bs,
                         int64_t o_ts, int B, int H, int Nq, int Nk, float scale, int round_out, void* stream);
-/* masked / plain attention with head dim 32: mask2former/video_seg_decoder.py:975-983,994-999,1306-1308 */
+/* masked / plain attention with head dim 32: mask2former/video_seg_decoder.py:975-983,994-999,1306-1308.
+ * Keys are split over CTAs (K/V staged once per head in shared memory); workspace = scratch for the row flags and the
+ * per-split softmax partials, at least siu3r_attn_small_d32_ws_bytes(B, H, Nq, Nk) bytes, 256-byte aligned. */
+int64_t siu3r_attn_small_d32_ws_bytes(int B, int H, int Nq, int Nk);
 int siu3r_attn_small_d32(const float* Q, int64_t q_bs, int64_t q_ts, const float* K, int64_t k_bs, int64_t k_ts,
                          const float* V, int64_t v_bs, int64_t v_ts, float* O, int64_t o_bs, int64_t o_ts,
-                         const uint8_t* mask, int B, int H, int Nq, int Nk, float scale, void* stream);
+                         const uint8_t* mask, int B, int H, int Nq, int Nk, float scale, void* workspace,
+                         int64_t workspace_bytes, void* stream);
 /* multi_scale_deformable_attention (vit_adapter/blocks.py:171-213,217-267; video_seg_decoder.py:1679-1720) */
 int siu3r_msdeform_attn(const float* value, int64_t ldv, int Lin, const float* ow, int64_t ldow, const float* ref,
                         const int* level_hw_host, int L, int P, int B, int Lq, int nH, int hd, float* out, int64_t ldo,

@@ -29,12 +29,15 @@ SIGNATURES = {
     "siu3r_gemm_simt": (_i, [_i, _i, _i, _p, _l, _p, _l, _p, _l, _p, _p, _l, _i, _f, _p]),
     "siu3r_split_tf32": (_i, [_p, _p, _p, _l, _p]),
     "siu3r_gemm_debug_set": (None, [_p]),
+    "siu3r_gemm_tc_rope": (_i, [_i, _i, _i, _p, _p, _l, _p, _p, _l, _p, _l, _p, _i, _i, _p, _p, _i, _p]),
+    "siu3r_rope2d_table": (_i, [_p, _i, _i, _f, _f, _p]),
     "siu3r_rope2d": (_i, [_p, _p, _i, _i, _i, _i, _l, _l, _f, _f, _i, _l, _i, _p]),
     "siu3r_transpose_v": (_i, [_p, _l, _l, _i, _i, _i, _p, _l, _p]),
     "siu3r_flash_attn_tc": (_i, [_p, _l, _l, _i, _i, _p, _l, _l, _i, _i, _p, _l, _p, _l, _l, _i, _i, _i, _i, _f, _i, _p]),
     "siu3r_layernorm": (_i, [_p, _l, _p, _p, _p, _l, _i, _i, _f, _p, _l, _i, _p]),
     "siu3r_flash_attn_d64": (_i, [_p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _l, _l, _i, _i, _i, _i, _f, _i, _i, _p]),
-    "siu3r_attn_small_d32": (_i, [_p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _i, _i, _i, _i, _f, _p]),
+    "siu3r_attn_small_d32_ws_bytes": (_l, [_i, _i, _i, _i]),
+    "siu3r_attn_small_d32": (_i, [_p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _i, _i, _i, _i, _f, _p, _l, _p]),
     "siu3r_msdeform_attn": (_i, [_p, _l, _i, _p, _l, _p, C.POINTER(C.c_int), _i, _i, _i, _i, _i, _i, _p, _l, _p]),
     "siu3r_eltwise": (_i, [_i, _p, _p, _p, _l, _p]),
     "siu3r_scale": (_i, [_p, _f, _p, _l, _p]),

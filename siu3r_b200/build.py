@@ -48,7 +48,7 @@ def build_extension(force: bool = False, verbose: bool = True) -> str:
     with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
         objs = list(ex.map(compile_one, SOURCES))
     if force or _stale(LIB, objs):
-        cmd = [nvcc, "-shared", "-o", LIB, *objs]
+        cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB, *objs]
         if verbose:
             print("[siu3r_b200.build]", " ".join(cmd), file=sys.stderr)
         subprocess.run(cmd, check=True)

@@ -49,6 +49,10 @@ struct GemmParams {
     int conv;                  // 0 = linear, 1 = conv (stride 1)
     int H, W, Cin, KH, KW, pad;
     int tiles_w, tiles_h;      // tiles per image row / column
+    // fused RoPE-2D on the output (q / k columns of a qkv projection; croco/blocks.py:101-103,158-160)
+    const long long* rope_pos; // [M, 2] (y, x) positions or null
+    const float* rope_tab;     // [maxpos][16] (cos, sin) pairs from siu3r_rope2d_table (head dim 64)
+    int rope_cols;             // columns [0, rope_cols) are rotated (multiple of 64)
     long long* dbg;            // optional: per-CTA clock64 stamps [cta][8] (tools/gemm_probe.py), null in production
 };
 
@@ -219,14 +223,34 @@ __device__ __forceinline__ void epi_emit(uint32_t tr_saddr, int lane, int q, int
     const bool full4 = col + 4 <= p.N;
     const bool c_vec = ((p.ldc & 3) == 0) && ((((uintptr_t)p.C) & 15) == 0) && full4 && ((col & 3) == 0);
     const bool r_vec = p.residual && ((p.ldr & 3) == 0) && ((((uintptr_t)p.residual) & 15) == 0) && full4 && ((col & 3) == 0);
+    // RoPE: a 32-column block is one (y or x) half of a 64-wide head; the pair (d, d+16) lives in lanes l and l^4 of the same row
+    const bool rope = p.rope_pos != nullptr && nbase < p.rope_cols;   // warp-uniform
+    const int axis = (nbase >> 5) & 1;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int r = rsub + 4 * i;
         const int64_t grow = rm.row(q * 32 + r);
         float4 x = lds_v4(tr_saddr + (uint32_t)(r * EPI_LD + c4) * 4);
-        if (grow < 0 || col >= p.N) continue;
         x.x = epi_act(x.x * p.alpha + bias.x, act); x.y = epi_act(x.y * p.alpha + bias.y, act);
         x.z = epi_act(x.z * p.alpha + bias.z, act); x.w = epi_act(x.w * p.alpha + bias.w, act);
+        if (rope) {
+            float4 y;
+            y.x = __shfl_xor_sync(0xffffffffu, x.x, 4); y.y = __shfl_xor_sync(0xffffffffu, x.y, 4);
+            y.z = __shfl_xor_sync(0xffffffffu, x.z, 4); y.w = __shfl_xor_sync(0xffffffffu, x.w, 4);
+            if (grow >= 0) {
+                const long long pp = p.rope_pos[grow * 2 + axis];
+                const float4* t = reinterpret_cast<const float4*>(p.rope_tab + (pp * 16 + (c4 & 15)) * 2);
+                const float4 t0 = __ldg(t), t1 = __ldg(t + 1);   // (cos, sin) of d = c4..c4+3 (mod 16)
+                if (c4 < 16) {   // first element of the pair: u*c - v*s
+                    x.x = x.x * t0.x - y.x * t0.y; x.y = x.y * t0.z - y.y * t0.w;
+                    x.z = x.z * t1.x - y.z * t1.y; x.w = x.w * t1.z - y.w * t1.w;
+                } else {         // second: v*c + u*s
+                    x.x = x.x * t0.x + y.x * t0.y; x.y = x.y * t0.z + y.y * t0.w;
+                    x.z = x.z * t1.x + y.z * t1.y; x.w = x.w * t1.z + y.w * t1.w;
+                }
+            }
+        }
+        if (grow < 0 || col >= p.N) continue;
         if (p.residual) {
             const float* rp = p.residual + grow * p.ldr + col;
             if (r_vec) { const float4 rr = *reinterpret_cast<const float4*>(rp); x.x += rr.x; x.y += rr.y; x.z += rr.z; x.w += rr.w; }
@@ -660,10 +684,11 @@ void siu3r_gemm_debug_set(long long* dev_buf) { g_gemm_dbg = dev_buf; }
 // fp32 storage; precision 1 = TF32, 3 = 3xTF32 (needs the *_lo planes: x = hi + lo with hi = tf32-rounded x).
 // Requirements: K % 4 == 0 handled by zero-filled TMA only if lda/ldw are multiples of 4 floats and all bases 16-byte aligned.
 // act: 0 none, 1 GELU(erf), 2 ReLU; +4 = store the result rounded to nearest TF32 (output only feeds TF32 GEMMs).  Replaces torch.nn.functional.linear (+ fused bias/activation/residual).
-int siu3r_gemm_tc(int M, int N, int K, const float* A, const float* A_lo, int64_t lda, const float* Wt, const float* W_lo, int64_t ldw,
-                  float* C, int64_t ldc, const float* bias, const float* residual, int64_t ldr, int act, float alpha, int precision,
-                  void* stream_) {
+static int gemm_tc_impl(int M, int N, int K, const float* A, const float* A_lo, int64_t lda, const float* Wt, const float* W_lo, int64_t ldw,
+                        float* C, int64_t ldc, const float* bias, const float* residual, int64_t ldr, int act, float alpha, int precision,
+                        const int64_t* rope_pos, const float* rope_tab, int rope_cols, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
+    if (rope_pos) SIU3R_REQUIRE(rope_tab && rope_cols > 0 && rope_cols % 64 == 0 && rope_cols <= N && ((uintptr_t)rope_tab & 15) == 0);
     SIU3R_REQUIRE(M > 0 && N > 0 && K > 0 && A && Wt && C);
     SIU3R_REQUIRE(precision == 1 || precision == 3);
     SIU3R_REQUIRE(precision == 1 || (A_lo && W_lo));
@@ -680,6 +705,7 @@ int siu3r_gemm_tc(int M, int N, int K, const float* A, const float* A_lo, int64_
         GemmParams p{};
         p.M = M; p.N = N; p.num_kb = ceil_div(K, BK); p.C = C; p.ldc = ldc; p.bias = bias; p.residual = residual; p.ldr = ldr;
         p.act = act; p.alpha = alpha; p.conv = 0;
+        p.rope_pos = (const long long*)rope_pos; p.rope_tab = rope_tab; p.rope_cols = rope_cols;
         dim3 grid((unsigned)(2 * ceil_div_i64(mtiles, 2)), (unsigned)(N / TC2_BN));
         return launch_tc2(ma, mb, p, grid, stream);
     }
@@ -700,6 +726,7 @@ int siu3r_gemm_tc(int M, int N, int K, const float* A, const float* A_lo, int64_
     GemmParams p{};
     p.M = M; p.N = N; p.num_kb = ceil_div(K, BK); p.C = C; p.ldc = ldc; p.bias = bias; p.residual = residual; p.ldr = ldr;
     p.act = act; p.alpha = alpha; p.conv = 0; p.dbg = g_gemm_dbg;
+    p.rope_pos = (const long long*)rope_pos; p.rope_tab = rope_tab; p.rope_cols = rope_cols;
     dim3 grid((unsigned)mtiles, (unsigned)ceil_div(N, bn));
     if (precision == 1) {
         if (bn == 256) return launch<256, 1>(ma, malo, mb, mblo, p, grid, stream);
@@ -708,6 +735,22 @@ int siu3r_gemm_tc(int M, int N, int K, const float* A, const float* A_lo, int64_
     }
     if (bn == 128) return launch<128, 3>(ma, malo, mb, mblo, p, grid, stream);
     return launch<64, 3>(ma, malo, mb, mblo, p, grid, stream);
+}
+
+int siu3r_gemm_tc(int M, int N, int K, const float* A, const float* A_lo, int64_t lda, const float* Wt, const float* W_lo, int64_t ldw,
+                  float* C, int64_t ldc, const float* bias, const float* residual, int64_t ldr, int act, float alpha, int precision,
+                  void* stream) {
+    return gemm_tc_impl(M, N, K, A, A_lo, lda, Wt, W_lo, ldw, C, ldc, bias, residual, ldr, act, alpha, precision, nullptr, nullptr, 0, stream);
+}
+
+// nn.Linear followed by RoPE-2D on output columns [0, rope_cols) (head dim 64), i.e. the qkv / q / kv projections of
+// croco/blocks.py:97-103,154-160 with curope.rope_2d folded into the epilogue.  positions [M, 2] int64 (row m = token m),
+// rope_tab from siu3r_rope2d_table.  Rotation happens after the bias and before the optional TF32 rounding.
+int siu3r_gemm_tc_rope(int M, int N, int K, const float* A, const float* A_lo, int64_t lda, const float* Wt, const float* W_lo, int64_t ldw,
+                       float* C, int64_t ldc, const float* bias, int act, int precision, const int64_t* positions, const float* rope_tab,
+                       int rope_cols, void* stream) {
+    SIU3R_REQUIRE(positions && rope_tab);
+    return gemm_tc_impl(M, N, K, A, A_lo, lda, Wt, W_lo, ldw, C, ldc, bias, nullptr, 0, act, 1.0f, precision, positions, rope_tab, rope_cols, stream);
 }
 
 // Stride-1 KHxKW convolution, NHWC fp32:  y[n,h,w,co] = act(sum x[n,h+kh-pad,w+kw-pad,ci] * Wt[co,kh,kw,ci] + bias) + residual

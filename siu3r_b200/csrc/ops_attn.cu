@@ -216,87 +216,140 @@ __global__ void __launch_bounds__(FA_THREADS) flash_attn_d64_kernel(const float*
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// (2) small attention, head dim 32: one warp per (batch, head, query); each lane owns a strided subset of the keys
-//     with a private online softmax that is merged across lanes at the end.  Exact fp32.
+// (2) small attention, head dim 32, few queries (Mask2Former's 100 object queries against up to 2*64*64 pixel keys).
+//     Exact fp32 FFMA (the boolean attention masks downstream are threshold decisions: no TF32 here).
+//     Split over the keys ("flash-decoding"): CTA (b, h, split) stages its <= 128 keys of K and V in shared memory ONCE
+//     and every thread owns one query, so K/V are read from L2 once per head instead of once per (head, query);
+//     the per-split (max, sum, acc[32]) partials are merged by a second tiny kernel.  Fully masked rows attend everywhere
+//     (video_seg_decoder.py:1306-1308): a row-flag pre-pass decides that before the split kernel runs.
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) attn_small_d32_kernel(const float* __restrict__ Q, int64_t q_bs, int64_t q_ts,
-                                                            const float* __restrict__ K, int64_t k_bs, int64_t k_ts,
-                                                            const float* __restrict__ V, int64_t v_bs, int64_t v_ts,
-                                                            float* __restrict__ O, int64_t o_bs, int64_t o_ts,
-                                                            const uint8_t* __restrict__ mask /*[B,Nq,Nk] 1 = masked*/, int B, int H, int Nq,
-                                                            int Nk, float scale) {
-    // one CTA (4 warps) per (batch, head, query); thread t owns keys t, t+128, ... with a private online softmax
-    __shared__ float s_m[4], s_l[4], s_acc[4][32];
-    const int wid = blockIdx.x;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q = wid % Nq;
-    const int h = (wid / Nq) % H;
-    const int b = wid / (Nq * H);
-    const float* qp = Q + (int64_t)b * q_bs + (int64_t)q * q_ts + h * 32;
-    float qr[32];
-#pragma unroll
-    for (int d = 0; d < 32; d += 4) {
-        const float4 v = *reinterpret_cast<const float4*>(qp + d);
-        qr[d] = v.x; qr[d + 1] = v.y; qr[d + 2] = v.z; qr[d + 3] = v.w;
-    }
-    const float* Kb = K + (int64_t)b * k_bs + h * 32;
-    const float* Vb = V + (int64_t)b * v_bs + h * 32;
-    const uint8_t* mrow = mask ? mask + ((int64_t)b * Nq + q) * Nk : nullptr;
+constexpr int AS_KEYS = 128;     // keys per split (K and V tiles: 2 x 16 KB of shared memory)
+constexpr int AS_QT = 128;       // queries per CTA = threads
+constexpr int AS_REC = 34;       // partial record: m, l, acc[32]
 
+__global__ void __launch_bounds__(256) attn_small_rowflags_kernel(const uint8_t* __restrict__ mask, int Nk, uint8_t* __restrict__ all_masked) {
+    // one CTA per (b, q) row: all_masked = 1 iff every key is masked
+    const uint8_t* row = mask + (int64_t)blockIdx.x * Nk;
+    int any = 0;
+    for (int i = threadIdx.x; i < Nk; i += blockDim.x) any |= (row[i] == 0);
+    any = __syncthreads_or(any);
+    if (threadIdx.x == 0) all_masked[blockIdx.x] = any ? 0 : 1;
+}
+
+__global__ void __launch_bounds__(AS_QT) attn_small_split_kernel(const float* __restrict__ Q, int64_t q_bs, int64_t q_ts,
+                                                                 const float* __restrict__ K, int64_t k_bs, int64_t k_ts,
+                                                                 const float* __restrict__ V, int64_t v_bs, int64_t v_ts,
+                                                                 float* __restrict__ O, int64_t o_bs, int64_t o_ts,
+                                                                 const uint8_t* __restrict__ mask, const uint8_t* __restrict__ all_masked,
+                                                                 float* __restrict__ part, int H, int Nq, int Nk, int keys_per_split,
+                                                                 int nsplit, float scale) {
+    __shared__ __align__(16) float sK[AS_KEYS * 32];
+    __shared__ __align__(16) float sV[AS_KEYS * 32];
+    const int split = blockIdx.x, bh = blockIdx.y, qt = blockIdx.z;
+    const int b = bh / H, h = bh % H;
+    const int key0 = split * keys_per_split;
+    const int nkeys = min(keys_per_split, Nk - key0);
+    // ---- stage K / V of this split (coalesced: 8 threads per 128-byte key row) ----
+    {
+        const float* Kb = K + (int64_t)b * k_bs + h * 32;
+        const float* Vb = V + (int64_t)b * v_bs + h * 32;
+        for (int i = threadIdx.x; i < nkeys * 8; i += AS_QT) {
+            const int key = i >> 3, c = (i & 7) * 4;
+            *reinterpret_cast<float4*>(sK + key * 32 + c) = *reinterpret_cast<const float4*>(Kb + (int64_t)(key0 + key) * k_ts + c);
+            *reinterpret_cast<float4*>(sV + key * 32 + c) = *reinterpret_cast<const float4*>(Vb + (int64_t)(key0 + key) * v_ts + c);
+        }
+    }
+    __syncthreads();
+    const int q = qt * AS_QT + threadIdx.x;
+    if (q >= Nq) return;
+    float qr[32];
+    {
+        const float* qp = Q + (int64_t)b * q_bs + (int64_t)q * q_ts + h * 32;
+#pragma unroll
+        for (int d = 0; d < 32; d += 4) {
+            const float4 v = *reinterpret_cast<const float4*>(qp + d);
+            qr[d] = v.x; qr[d + 1] = v.y; qr[d + 2] = v.z; qr[d + 3] = v.w;
+        }
+    }
+    const uint8_t* mrow = nullptr;
+    if (mask && !all_masked[b * Nq + q]) mrow = mask + ((int64_t)b * Nq + q) * Nk + key0;
     float m = -INFINITY, l = 0.f, acc[32];
-    for (int pass = 0; pass < 2; ++pass) {
-        const bool use_mask = (pass == 0) && (mrow != nullptr);
-        m = -INFINITY; l = 0.f;
 #pragma unroll
-        for (int d = 0; d < 32; ++d) acc[d] = 0.f;
-        int any = 0;
-        for (int key = threadIdx.x; key < Nk; key += 128) {
-            if (use_mask && mrow[key]) continue;
-            any = 1;
-            const float* kp = Kb + (int64_t)key * k_ts;
-            float dot = 0.f;
+    for (int d = 0; d < 32; ++d) acc[d] = 0.f;
+    for (int c0 = 0; c0 < nkeys; c0 += 32) {
+        const int cn = min(32, nkeys - c0);
+        float sc[32];
+        float cmax = -INFINITY;
 #pragma unroll
-            for (int d = 0; d < 32; d += 4) {
-                const float4 kv = *reinterpret_cast<const float4*>(kp + d);
-                dot += qr[d] * kv.x + qr[d + 1] * kv.y + qr[d + 2] * kv.z + qr[d + 3] * kv.w;
+        for (int j = 0; j < 32; ++j) {
+            float dot = -INFINITY;
+            if (j < cn && !(mrow && mrow[c0 + j])) {
+                const float* kp = sK + (c0 + j) * 32;
+                dot = 0.f;
+#pragma unroll
+                for (int d = 0; d < 32; d += 4) {
+                    const float4 kv = *reinterpret_cast<const float4*>(kp + d);   // broadcast read
+                    dot += qr[d] * kv.x + qr[d + 1] * kv.y + qr[d + 2] * kv.z + qr[d + 3] * kv.w;
+                }
+                dot *= scale;
             }
-            dot *= scale;
-            const float mn = fmaxf(m, dot);
-            const float corr = expf(m - mn), pw = expf(dot - mn);
-            l = l * corr + pw;
-            const float* vp = Vb + (int64_t)key * v_ts;
+            sc[j] = dot;
+            cmax = fmaxf(cmax, dot);
+        }
+        if (cmax == -INFINITY) continue;   // every key of this chunk masked for this query
+        const float mn = fmaxf(m, cmax);
+        const float corr = expf(m - mn);   // m = -inf -> 0
+        l *= corr;
+#pragma unroll
+        for (int d = 0; d < 32; ++d) acc[d] *= corr;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            if (sc[j] == -INFINITY) continue;
+            const float pw = expf(sc[j] - mn);
+            l += pw;
+            const float* vp = sV + (c0 + j) * 32;
 #pragma unroll
             for (int d = 0; d < 32; d += 4) {
                 const float4 vv = *reinterpret_cast<const float4*>(vp + d);
-                acc[d] = acc[d] * corr + pw * vv.x; acc[d + 1] = acc[d + 1] * corr + pw * vv.y;
-                acc[d + 2] = acc[d + 2] * corr + pw * vv.z; acc[d + 3] = acc[d + 3] * corr + pw * vv.w;
+                acc[d] += pw * vv.x; acc[d + 1] += pw * vv.y; acc[d + 2] += pw * vv.z; acc[d + 3] += pw * vv.w;
             }
-            m = mn;
         }
-        if (!use_mask || __syncthreads_or(any)) break;  // fully masked row: redo without the mask (video_seg_decoder.py:1306-1308)
+        m = mn;
     }
-    // merge: warp level, then the 4 warps through shared memory
-    const float mw = warp_max(m);
-    const float f = (m == -INFINITY) ? 0.f : expf(m - mw);
-    l = warp_sum(l * f);
+    if (nsplit == 1) {
+        float* op = O + (int64_t)b * o_bs + (int64_t)q * o_ts + h * 32;
+        const float inv = 1.0f / l;
 #pragma unroll
-    for (int d = 0; d < 32; ++d) {
-        const float v = warp_sum(acc[d] * f);
-        if (lane == d) s_acc[warp][d] = v;
+        for (int d = 0; d < 32; d += 4) *reinterpret_cast<float4*>(op + d) = make_float4(acc[d] * inv, acc[d + 1] * inv, acc[d + 2] * inv, acc[d + 3] * inv);
+        return;
     }
-    if (lane == 0) { s_m[warp] = mw; s_l[warp] = l; }
-    __syncthreads();
-    if (warp == 0) {
-        const float M = fmaxf(fmaxf(s_m[0], s_m[1]), fmaxf(s_m[2], s_m[3]));
-        float L = 0.f, o = 0.f;
+    float* rec = part + (((int64_t)bh * nsplit + split) * Nq + q) * AS_REC;
+    rec[0] = m; rec[1] = l;
 #pragma unroll
-        for (int w = 0; w < 4; ++w) {
-            const float g = (s_m[w] == -INFINITY) ? 0.f : expf(s_m[w] - M);
-            L += s_l[w] * g;
-            o += s_acc[w][lane] * g;
-        }
-        O[(int64_t)b * o_bs + (int64_t)q * o_ts + h * 32 + lane] = o / L;
+    for (int d = 0; d < 32; ++d) rec[2 + d] = acc[d];
+}
+
+// one warp per (b, h, q): lane = channel
+__global__ void __launch_bounds__(128) attn_small_merge_kernel(const float* __restrict__ part, float* __restrict__ O, int64_t o_bs, int64_t o_ts,
+                                                               int H, int Nq, int nsplit, int total) {
+    const int w = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (w >= total) return;
+    const int q = w % Nq, bh = w / Nq;
+    const int b = bh / H, h = bh % H;
+    const float* rec = part + ((int64_t)bh * nsplit * Nq + q) * AS_REC;
+    const int64_t step = (int64_t)Nq * AS_REC;
+    float M = -INFINITY;
+    for (int s = lane; s < nsplit; s += 32) M = fmaxf(M, rec[s * step]);
+    M = warp_max(M);
+    float L = 0.f, o = 0.f;
+    for (int s = 0; s < nsplit; ++s) {
+        const float ms = rec[s * step];
+        if (ms == -INFINITY) continue;
+        const float g = expf(ms - M);
+        L += rec[s * step + 1] * g;
+        o += rec[s * step + 2 + lane] * g;
     }
+    O[(int64_t)b * o_bs + (int64_t)q * o_ts + h * 32 + lane] = o / L;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -403,17 +456,51 @@ int siu3r_flash_attn_d64(const float* Q, int64_t q_bs, int64_t q_ts, const float
     return SIU3R_OK;
 }
 
+static void attn_small_plan(int Nk, int* keys_per_split, int* nsplit) {
+    int ks = AS_KEYS;
+    *nsplit = ceil_div(Nk, ks);
+    *keys_per_split = ks;
+}
+
+// bytes of scratch siu3r_attn_small_d32 needs for this problem (row flags + split partials)
+int64_t siu3r_attn_small_d32_ws_bytes(int B, int H, int Nq, int Nk) {
+    int ks, ns;
+    attn_small_plan(Nk, &ks, &ns);
+    const int64_t flags = ((int64_t)B * Nq + 255) / 256 * 256;
+    return flags + (ns > 1 ? (int64_t)B * H * ns * Nq * AS_REC * 4 : 0);
+}
+
 // Head dim 32; mask (optional) uint8 [B, Nq, Nk], non-zero = key not attended; rows that are fully masked attend everywhere.
+// workspace: >= siu3r_attn_small_d32_ws_bytes(B, H, Nq, Nk) bytes of device memory, 256-byte aligned.
 int siu3r_attn_small_d32(const float* Q, int64_t q_bs, int64_t q_ts, const float* K, int64_t k_bs, int64_t k_ts, const float* V, int64_t v_bs,
                          int64_t v_ts, float* O, int64_t o_bs, int64_t o_ts, const uint8_t* mask, int B, int H, int Nq, int Nk, float scale,
-                         void* stream_) {
+                         void* workspace, int64_t workspace_bytes, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     SIU3R_REQUIRE(Q && K && V && O && B > 0 && H > 0 && Nq > 0 && Nk > 0);
-    SIU3R_REQUIRE(q_ts % 4 == 0 && k_ts % 4 == 0 && v_ts % 4 == 0 && q_bs % 4 == 0 && k_bs % 4 == 0 && v_bs % 4 == 0);
-    attn_small_d32_kernel<<<B * H * Nq, 128, 0, stream>>>(Q, q_bs, q_ts, K, k_bs, k_ts, V, v_bs, v_ts, O, o_bs, o_ts, mask, B, H, Nq, Nk,
-                                                                 scale);
+    SIU3R_REQUIRE(q_ts % 4 == 0 && k_ts % 4 == 0 && v_ts % 4 == 0 && q_bs % 4 == 0 && k_bs % 4 == 0 && v_bs % 4 == 0 && o_ts % 4 == 0 && o_bs % 4 == 0);
+    SIU3R_REQUIRE((((uintptr_t)Q | (uintptr_t)K | (uintptr_t)V | (uintptr_t)O) & 15) == 0);
+    SIU3R_REQUIRE(workspace && workspace_bytes >= siu3r_attn_small_d32_ws_bytes(B, H, Nq, Nk) && ((uintptr_t)workspace & 255) == 0);
+    int ks, ns;
+    attn_small_plan(Nk, &ks, &ns);
+    uint8_t* flags = (uint8_t*)workspace;
+    float* part = (float*)((uint8_t*)workspace + ((int64_t)B * Nq + 255) / 256 * 256);
+    int launches = 1;
+    if (mask) {
+        attn_small_rowflags_kernel<<<B * Nq, 256, 0, stream>>>(mask, Nk, flags);
+        SIU3R_LAUNCH_CHECK();
+        ++launches;
+    }
+    dim3 grid((unsigned)ns, (unsigned)(B * H), (unsigned)ceil_div(Nq, AS_QT));
+    attn_small_split_kernel<<<grid, AS_QT, 0, stream>>>(Q, q_bs, q_ts, K, k_bs, k_ts, V, v_bs, v_ts, O, o_bs, o_ts, mask, flags, part, H, Nq, Nk, ks,
+                                                        ns, scale);
     SIU3R_LAUNCH_CHECK();
-    siu3r_note_launch(1);
+    if (ns > 1) {
+        const int total = B * H * Nq;
+        attn_small_merge_kernel<<<ceil_div(total, 4), 128, 0, stream>>>(part, O, o_bs, o_ts, H, Nq, ns, total);
+        SIU3R_LAUNCH_CHECK();
+        ++launches;
+    }
+    siu3r_note_launch(launches);
     return SIU3R_OK;
 }
 

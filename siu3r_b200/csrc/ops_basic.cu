@@ -99,6 +99,18 @@ __global__ void __launch_bounds__(256) rope2d_kernel(float* __restrict__ tokens,
     p[Q] = round_out ? rn_tf32(o1) : o1;
 }
 
+// (cos, sin)(pos * fwd / base^(d/Q)) for pos < maxpos, d < Q: the same expressions as rope2d_kernel, evaluated once
+__global__ void rope2d_table_kernel(float2* __restrict__ tab, int maxpos, int Q, float base, float fwd) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= maxpos * Q) return;
+    const int d = idx % Q, pos = idx / Q;
+    const float inv_freq = fwd / powf(base, (float)d / (float)Q);
+    const float f = (float)pos * inv_freq;
+    float s, c;
+    sincosf(f, &s, &c);
+    tab[idx] = make_float2(c, s);
+}
+
 // x = hi + lo with hi = RN_tf32(x), lo = RN_tf32(x - hi): operands of the 3xTF32 tensor-core path
 __global__ void __launch_bounds__(256) split_tf32_kernel(const float4* __restrict__ x, float4* __restrict__ hi, float4* __restrict__ lo, int64_t n4) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -438,6 +450,16 @@ int siu3r_rope2d(float* tokens, const int64_t* positions, int B, int N, int H, i
     SIU3R_REQUIRE(nparts >= 1);
     const int64_t total = (int64_t)B * N * nparts * H * 2 * (D / 4);
     rope2d_kernel<<<grid_for(total), 256, 0, stream>>>(tokens, positions, B, N, H, D, batch_stride, token_stride, base, fwd, nparts, part_stride, round_out);
+    SIU3R_LAUNCH_CHECK();
+    siu3r_note_launch(1);
+    return SIU3R_OK;
+}
+
+int siu3r_rope2d_table(float* tab, int maxpos, int D, float base, float fwd, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    SIU3R_REQUIRE(tab && maxpos > 0 && D > 0 && D % 4 == 0);
+    const int Q = D / 4;
+    rope2d_table_kernel<<<(unsigned)ceil_div(maxpos * Q, 256), 256, 0, stream>>>((float2*)tab, maxpos, Q, base, fwd);
     SIU3R_LAUNCH_CHECK();
     siu3r_note_launch(1);
     return SIU3R_OK;

@@ -207,6 +207,7 @@ class SIU3RModel:
         k = SimpleNamespace()
         k.pos_enc = pos[None].repeat(2 * B, 1, 1).contiguous().to(self.dev)
         k.pos_dec = pos[None].repeat(B, 1, 1).contiguous().to(self.dev)
+        k.rope_tab = ops.rope2d_table(int(pos.max()) + 1, 64, 100.0, 1.0, self.dev)   # RoPE factors for the fused projection epilogues
         ad_shapes = [(S0 // 8, S1 // 8), (S0 // 16, S1 // 16), (S0 // 32, S1 // 32)]
         k.ad_ref = reference_points(ad_shapes).to(self.dev)
         m = self.w.m2f
@@ -274,8 +275,7 @@ class SIU3RModel:
 
     def _self_attn(self, h, blk, pos, Bn, N, C, nh):
         M = Bn * N
-        qkv = self._lin(h, blk.qkv, ar=True)
-        ops.rope2d_(qkv, 0, pos, Bn, N, nh, 64, N * 3 * C, 3 * C, nparts=2, part_stride=C, round_out=self.R)  # q and k in one launch
+        qkv = self._lin(h, blk.qkv, ar=True, ro=True, rope=(pos, self._k.rope_tab, 2 * C))   # RoPE on q and k inside the epilogue
         a = torch.empty(M, C, device=self.dev)
         if self.R:   # TF32 mode: tcgen05 / TMEM flash attention
             ops.flash_attn_tc(qkv, 0, N * 3 * C, 3 * C, 3 * C, qkv, C, N * 3 * C, 3 * C, 3 * C, qkv, 2 * C, N * 3 * C, 3 * C, a, Bn, nh, N, N, 0.125,
@@ -318,10 +318,8 @@ class SIU3RModel:
         x1 = self._lin(a, blk.proj, ar=True, residual=x)
         yn = self._ln(y, blk.ny, 1e-6)
         h2 = self._ln(x1, blk.n2, 1e-6)
-        q = self._lin(h2, blk.cq, ar=True)
-        kv = self._lin(yn, blk.ckv, ar=True)
-        ops.rope2d_(q, 0, pos, B, N, nh, 64, N * C, C, round_out=self.R)
-        ops.rope2d_(kv, 0, pos, B, N, nh, 64, N * 2 * C, 2 * C, round_out=self.R)
+        q = self._lin(h2, blk.cq, ar=True, ro=True, rope=(pos, self._k.rope_tab, C))
+        kv = self._lin(yn, blk.ckv, ar=True, ro=True, rope=(pos, self._k.rope_tab, C))
         a2 = torch.empty(B * N, C, device=self.dev)
         if self.R:
             ops.flash_attn_tc(q, 0, N * C, C, C, kv, 0, N * 2 * C, 2 * C, 2 * C, kv, C, N * 2 * C, 2 * C, a2, B, nh, N, N, 0.125, round_out=True)
@@ -672,7 +670,7 @@ class SIU3RModel:
         """All device work of SIU3RModel.forward up to (and excluding) the host-assisted panoptic post-process."""
         B, V, _, S0, S1 = imgs.shape
         w, c = self.w, self.cfg
-        k = self._consts(B, S0, S1)
+        k = self._k = self._consts(B, S0, S1)
         gh, gw = S0 // 16, S1 // 16
         P, N = gh * gw, gh * gw + 1
         Bn = 2 * B

@@ -104,8 +104,9 @@ def round_tf32(x: torch.Tensor) -> torch.Tensor:
 
 def gemm(x: torch.Tensor, wt: Weight, out: torch.Tensor | None = None, act: int = ACT_NONE, residual: torch.Tensor | None = None,
          alpha: float = 1.0, precision: int = PREC_TF32, bias: torch.Tensor | None | bool = True, M: int | None = None,
-         a_rounded: bool = False, round_out: bool = False) -> torch.Tensor:
+         a_rounded: bool = False, round_out: bool = False, rope: tuple | None = None) -> torch.Tensor:
     """out[M,N] = act(alpha * x[M,K] @ W^T + bias) + residual.  x / out / residual are 2-D row-strided views.
+    rope = (positions [M,2] int64, table from rope2d_table, ncols): RoPE-2D on output columns [0, ncols) in the epilogue.
     TF32 mode: the A operand must be round-to-nearest TF32 (a_rounded=True if its producer already did that);
     round_out=True stores the result rounded because it only feeds further TF32 GEMMs."""
     _chk_f32(x, out, residual)
@@ -134,11 +135,26 @@ def gemm(x: torch.Tensor, wt: Weight, out: torch.Tensor | None = None, act: int 
             x = round_tf32(x)
         if round_out:
             act = act | ACT_ROUND_TF32
+    if rope is not None:
+        pos, tab, ncols = rope
+        assert residual is None and alpha == 1.0 and pos.dtype == torch.int64 and pos.is_contiguous() and pos.numel() == 2 * M
+        with _Prof("gemm_tc", 2.0 * M * wt.N * K):
+            code = _lib.load().siu3r_gemm_tc_rope(M, wt.N, K, _p(x), _p(x_lo), x.stride(0), _p(wt.w), _p(wt.w_lo), ldw, _p(out), out.stride(0),
+                                                  _p(b), act, precision, _p(pos), _p(tab), ncols, _stream())
+        _lib.check(code, "gemm_tc_rope")
+        return out
     with _Prof("gemm_tc", 2.0 * M * wt.N * K):
         code = _lib.load().siu3r_gemm_tc(M, wt.N, K, _p(x), _p(x_lo), x.stride(0), _p(wt.w), _p(wt.w_lo), ldw, _p(out), out.stride(0), _p(b),
                                          _p(residual), 0 if residual is None else residual.stride(0), act, alpha, precision, _stream())
     _lib.check(code, "gemm_tc")
     return out
+
+
+def rope2d_table(maxpos: int, D: int = 64, base: float = 100.0, fwd: float = 1.0, device="cuda") -> torch.Tensor:
+    """[maxpos, D/4, 2] (cos, sin) factors shared by every RoPE-fused projection (siu3r_gemm_tc_rope)."""
+    tab = torch.empty(maxpos, D // 4, 2, device=device, dtype=torch.float32)
+    _lib.check(_lib.load().siu3r_rope2d_table(_p(tab), maxpos, D, base, fwd, _stream()), "rope2d_table")
+    return tab
 
 
 def gemm_simt(x, w, bias=None, out=None, act=ACT_NONE, residual=None, alpha=1.0):
@@ -252,8 +268,11 @@ def flash_attn_tc(q: torch.Tensor, q_off: int, q_bs: int, q_ts: int, q_width: in
 
 
 def attn_small_d32(q, q_bs, q_ts, k, k_bs, k_ts, v, v_bs, v_ts, out, o_bs, o_ts, mask, B, H, Nq, Nk, scale):
-    code = _lib.load().siu3r_attn_small_d32(_p(q), q_bs, q_ts, _p(k), k_bs, k_ts, _p(v), v_bs, v_ts, _p(out), o_bs, o_ts, _p(mask), B, H, Nq, Nk,
-                                            scale, _stream())
+    lib = _lib.load()
+    nb = lib.siu3r_attn_small_d32_ws_bytes(B, H, Nq, Nk)
+    ws = torch.empty(nb, dtype=torch.uint8, device=q.device)
+    code = lib.siu3r_attn_small_d32(_p(q), q_bs, q_ts, _p(k), k_bs, k_ts, _p(v), v_bs, v_ts, _p(out), o_bs, o_ts, _p(mask), B, H, Nq, Nk,
+                                    scale, _p(ws), nb, _stream())
     _lib.check(code, "attn_small_d32")
     return out
 

@@ -153,3 +153,33 @@ def test_model_rejects_bad_inputs():
         m(torch.zeros(1, 2, 3, 64, 64), torch.zeros(1, 2, 3, 3))  # not loaded
     with pytest.raises(RuntimeError):
         m.cuda()
+
+
+def test_pair_pipeline_matches_direct_forward():
+    """serving.PairPipeline (overlapped download) returns exactly what forward() + detach_cpu_copy would, per pair, in order."""
+    from siu3r_b200 import synth
+    from siu3r_b200.model import ModelCfg, SIU3RModel
+    from siu3r_b200.serving import PairPipeline, GAUSSIAN_FIELDS
+    S = 64
+    model = SIU3RModel(ModelCfg(image_size=(S, S)), precision="tf32")
+    model.load_state_dict(synth.make_state_dict())
+    model.cuda()
+    model.enable_cuda_graph()
+    pairs = [synth.pair_inputs(1, 2, S, seed=s) for s in (0, 1, 2, 3, 4)]
+    direct = []
+    for img, K in pairs:
+        g = model(img.cuda(), K.cuda())[0]
+        torch.cuda.synchronize()
+        direct.append({n: getattr(g, n).detach().cpu().clone() for n in GAUSSIAN_FIELDS})
+    pipe = PairPipeline(model)
+    got = []
+    for img, K in pairs:
+        r = pipe.submit(img.pin_memory(), K.pin_memory())
+        if r is not None:
+            got.append({n: t.clone() for n, t in r[0].items()})
+    got.append({n: t.clone() for n, t in pipe.flush()[0].items()})
+    assert len(got) == len(direct)
+    for a, b in zip(got, direct):
+        for n in GAUSSIAN_FIELDS:
+            assert torch.equal(a[n], b[n]), n
+    assert pipe.h2d_bytes == 2 * 3 * S * S * 4 + 18 * 4 and pipe.d2h_bytes > 0

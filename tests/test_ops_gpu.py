@@ -163,6 +163,27 @@ def test_rope2d_vs_oracle_and_torch(oracle_lib):
     assert lib_err == -1  # D % 4 != 0 -> invalid argument (kernels.cu:94 contract)
 
 
+@pytest.mark.parametrize("M,N,K,cols", [(2050, 3072, 1024, 2048), (1025, 768, 768, 768), (1025, 1536, 768, 768), (2050, 4096, 256, 4096)])
+@pytest.mark.parametrize("prec", [1, 3])
+def test_gemm_rope_epilogue_matches_gemm_then_rope2d(M, N, K, cols, prec):
+    """siu3r_gemm_tc_rope == siu3r_gemm_tc followed by siu3r_rope2d on the first `cols` columns (all tile variants)."""
+    from siu3r_b200 import ops
+    x = rnd(M, K, seed=71)
+    wt = ops.Weight(rnd(N, K, seed=72) / K ** 0.5, rnd(N, seed=73), prec)
+    n_tok = M // 2 if M % 2 == 0 else M
+    Bn = M // n_tok
+    g = int((n_tok - 1) ** 0.5)
+    ys, xs = torch.meshgrid(torch.arange(g), torch.arange(g), indexing="ij")
+    pos = torch.cat([torch.stack([ys.flatten(), xs.flatten()], -1), torch.tensor([[g, 0]])], 0)[None].repeat(Bn, 1, 1).contiguous().to(DEV)
+    assert pos.shape[1] == n_tok
+    tab = ops.rope2d_table(g + 1)
+    ref = ops.gemm(x, wt, precision=prec)
+    ops.rope2d_(ref, 0, pos, Bn, n_tok, cols // 64, 64, n_tok * N, N)
+    got = ops.gemm(x, wt, precision=prec, rope=(pos.view(-1, 2), tab, cols))
+    assert float((got - ref).abs().max()) < 2e-5 * max(1.0, float(ref.abs().max()))
+    assert torch.equal(got[:, cols:], ref[:, cols:])
+
+
 def _attn_ref(q, k, v, scale, mask=None):
     s = torch.einsum("bhqd,bhkd->bhqk", q, k) * scale
     if mask is not None:
@@ -218,7 +239,7 @@ def test_flash_attn_inside_qkv_buffer():
     assert rel_err(out, ref) < 3e-5
 
 
-@pytest.mark.parametrize("Nk", [512, 2048, 100])
+@pytest.mark.parametrize("Nk", [512, 2048, 100, 8192, 333])
 def test_attn_small_d32_masked(Nk):
     from siu3r_b200 import ops
     B, H, Nq, D = 2, 8, 100, 32

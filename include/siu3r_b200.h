@@ -58,7 +58,7 @@ int siu3r_gemm_tc(int M, int N, int K, const float* A, const float* A_lo, int64_
 int siu3r_gemm_tc_rope(int M, int N, int K, const float* A, const float* A_lo, int64_t lda, const float* Wt, const float* W_lo,
                        int64_t ldw, float* C, int64_t ldc, const float* bias, int act, int precision, const int64_t* positions,
                        const float* rope_tab, int rope_cols, void* stream);
-int siu3r_conv2d_tc(int Nimg, int H, int W, int Cin, int Cout, int KH, int KW, int pad, const float* x, const float* x_lo,
+int siu3r_conv2d_tc(int Nimg, int H, int W, int Cin, int Cout, int KH, int KW, int pad_h, int pad_w, const float* x, const float* x_lo,
                     const float* Wt, const float* W_lo, float* y, int64_t ldc, const float* bias, const float* residual,
                     int64_t ldr, int act, int precision, void* stream);
 /* plain fp32 FFMA GEMM (tiny / odd shapes such as the K = 9 intrinsics encoder, backbone_croco.py:59,278) */
@@ -95,12 +95,12 @@ int siu3r_flash_attn_tc(const float* Q, int64_t q_bs, int64_t q_ts, int q_width,
 int64_t siu3r_attn_small_d32_ws_bytes(int B, int H, int Nq, int Nk);
 int siu3r_attn_small_d32(const float* Q, int64_t q_bs, int64_t q_ts, const float* K, int64_t k_bs, int64_t k_ts,
                          const float* V, int64_t v_bs, int64_t v_ts, float* O, int64_t o_bs, int64_t o_ts,
-                         const uint8_t* mask, int B, int H, int Nq, int Nk, float scale, void* workspace,
+                         const uint8_t* mask, int B, int H, int Nq, int Nk, float scale, int round_out, void* workspace,
                          int64_t workspace_bytes, void* stream);
 /* multi_scale_deformable_attention (vit_adapter/blocks.py:171-213,217-267; video_seg_decoder.py:1679-1720) */
 int siu3r_msdeform_attn(const float* value, int64_t ldv, int Lin, const float* ow, int64_t ldow, const float* ref,
                         const int* level_hw_host, int L, int P, int B, int Lq, int nH, int hd, float* out, int64_t ldo,
-                        void* stream);
+                        int round_out, void* stream);
 
 /* ---- HBM-bound elementwise / resampling ------------------------------------------------------------------------ */
 int siu3r_eltwise(int op, const float* a, const float* b, float* out, int64_t n, void* stream);
@@ -113,8 +113,11 @@ int siu3r_resize_bilinear_nhwc(const float* x, int N, int H, int W, int C, int64
                                int64_t ldy, int align_corners, int accumulate, void* stream);
 /* scatter half of nn.ConvTranspose2d(kernel = stride): heads/dpt_block.py:422-451; vit_adapter.py:356,425 */
 int siu3r_pixel_shuffle_nhwc(const float* g, int N, int H, int W, int C, int s, const float* add, float* y, void* stream);
-int siu3r_im2col_nhwc(const float* x, int N, int H, int W, int C, int KH, int KW, int stride, int pad, float* out,
-                      int64_t ldo, int round_out, void* stream);
+/* out[(n,oh,ow), (kh,kw,ci)] patches (row stride ldo, padding columns zeroed); pad_h / pad_w = zero padding per axis.
+ * KH = 1 packs the KW horizontal taps of a few-channel input (the RGB image) into one 32-wide "channel" vector so that a
+ * KHxKW conv becomes a KHx1 implicit-GEMM conv (heads/dpt_gs_head.py input_merger 7x7, Cin = 3). */
+int siu3r_im2col_nhwc(const float* x, int N, int H, int W, int C, int KH, int KW, int stride, int pad_h, int pad_w,
+                      float* out, int64_t ldo, int round_out, void* stream);
 int siu3r_nchw_to_nhwc(const float* x, float* y, int N, int C, int HW, int64_t ldy, void* stream);
 int siu3r_nhwc_to_nchw(const float* x, int64_t ldx, float* y, int N, int C, int HW, void* stream);
 int siu3r_maxpool3x3s2_nhwc(const float* x, int N, int H, int W, int C, float* y, void* stream);   /* vit_adapter.py:220 */

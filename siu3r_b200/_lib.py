@@ -25,7 +25,7 @@ SIGNATURES = {
     "siu3r_raster_forward": (_i, [_i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _l, _l,
                                   C.POINTER(C.c_int64), _p, _p, _p, _p, _p, _p]),
     "siu3r_gemm_tc": (_i, [_i, _i, _i, _p, _p, _l, _p, _p, _l, _p, _l, _p, _p, _l, _i, _f, _i, _p]),
-    "siu3r_conv2d_tc": (_i, [_i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _l, _p, _p, _l, _i, _i, _p]),
+    "siu3r_conv2d_tc": (_i, [_i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _l, _p, _p, _l, _i, _i, _p]),
     "siu3r_gemm_simt": (_i, [_i, _i, _i, _p, _l, _p, _l, _p, _l, _p, _p, _l, _i, _f, _p]),
     "siu3r_split_tf32": (_i, [_p, _p, _p, _l, _p]),
     "siu3r_gemm_debug_set": (None, [_p]),
@@ -37,14 +37,14 @@ SIGNATURES = {
     "siu3r_layernorm": (_i, [_p, _l, _p, _p, _p, _l, _i, _i, _f, _p, _l, _i, _p]),
     "siu3r_flash_attn_d64": (_i, [_p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _l, _l, _i, _i, _i, _i, _f, _i, _i, _p]),
     "siu3r_attn_small_d32_ws_bytes": (_l, [_i, _i, _i, _i]),
-    "siu3r_attn_small_d32": (_i, [_p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _i, _i, _i, _i, _f, _p, _l, _p]),
-    "siu3r_msdeform_attn": (_i, [_p, _l, _i, _p, _l, _p, C.POINTER(C.c_int), _i, _i, _i, _i, _i, _i, _p, _l, _p]),
+    "siu3r_attn_small_d32": (_i, [_p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _i, _i, _i, _i, _f, _i, _p, _l, _p]),
+    "siu3r_msdeform_attn": (_i, [_p, _l, _i, _p, _l, _p, C.POINTER(C.c_int), _i, _i, _i, _i, _i, _i, _p, _l, _i, _p]),
     "siu3r_eltwise": (_i, [_i, _p, _p, _p, _l, _p]),
     "siu3r_scale": (_i, [_p, _f, _p, _l, _p]),
     "siu3r_rows_affine": (_i, [_p, _l, _p, _p, _p, _l, _p, _l, _l, _i, _i, _p]),
     "siu3r_resize_bilinear_nhwc": (_i, [_p, _i, _i, _i, _i, _l, _p, _i, _i, _l, _i, _i, _p]),
     "siu3r_pixel_shuffle_nhwc": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p]),
-    "siu3r_im2col_nhwc": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _l, _i, _p]),
+    "siu3r_im2col_nhwc": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _l, _i, _p]),
     "siu3r_nchw_to_nhwc": (_i, [_p, _p, _i, _i, _i, _l, _p]),
     "siu3r_nhwc_to_nchw": (_i, [_p, _l, _p, _i, _i, _i, _p]),
     "siu3r_maxpool3x3s2_nhwc": (_i, [_p, _i, _i, _i, _i, _p, _p]),

@@ -47,7 +47,7 @@ struct GemmParams {
     float alpha;               // scales the accumulator before bias
     // conv mode
     int conv;                  // 0 = linear, 1 = conv (stride 1)
-    int H, W, Cin, KH, KW, pad;
+    int H, W, Cin, KH, KW, pad /* rows */, pad_w /* columns */;
     int tiles_w, tiles_h;      // tiles per image row / column
     // fused RoPE-2D on the output (q / k columns of a qkv projection; croco/blocks.py:101-103,158-160)
     const long long* rope_pos; // [M, 2] (y, x) positions or null
@@ -383,8 +383,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (p.conv) {
                     const int tap = kb / cblocks, cb = kb - tap * cblocks;
                     const int kh = tap / p.KW, kw = tap - kh * p.KW;
-                    tma_load_4d(&tmA, &full_bar[stage], sA, cb * BK, w0 + kw - p.pad, h0 + kh - p.pad, img);
-                    if (NSPLIT == 3) tma_load_4d(&tmAlo, &full_bar[stage], sA + C_::A_BYTES, cb * BK, w0 + kw - p.pad, h0 + kh - p.pad, img);
+                    tma_load_4d(&tmA, &full_bar[stage], sA, cb * BK, w0 + kw - p.pad_w, h0 + kh - p.pad, img);
+                    if (NSPLIT == 3) tma_load_4d(&tmAlo, &full_bar[stage], sA + C_::A_BYTES, cb * BK, w0 + kw - p.pad_w, h0 + kh - p.pad, img);
                 } else {
                     tma_load_2d(&tmA, &full_bar[stage], sA, kb * BK, m0);
                     if (NSPLIT == 3) tma_load_2d(&tmAlo, &full_bar[stage], sA + C_::A_BYTES, kb * BK, m0);
@@ -548,7 +548,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 if (p.conv) {
                     const int tap = kb / cblocks, cb = kb - tap * cblocks;
                     const int kh = tap / p.KW, kw = tap - kh * p.KW;
-                    tma2_load_4d(&tmA, lead_full, sA, cb * BK, w0 + kw - p.pad, h0 + kh - p.pad, img);
+                    tma2_load_4d(&tmA, lead_full, sA, cb * BK, w0 + kw - p.pad_w, h0 + kh - p.pad, img);
                 } else {
                     tma2_load_2d(&tmA, lead_full, sA, kb * BK, m0);
                 }
@@ -756,7 +756,7 @@ int siu3r_gemm_tc_rope(int M, int N, int K, const float* A, const float* A_lo, i
 // Stride-1 KHxKW convolution, NHWC fp32:  y[n,h,w,co] = act(sum x[n,h+kh-pad,w+kw-pad,ci] * Wt[co,kh,kw,ci] + bias) + residual
 // x [Nimg,H,W,Cin], Wt [Cout, KH*KW*Cin] (repacked from torch's [Cout,Cin,KH,KW]), y [Nimg,H,W,ldc>=Cout].
 // Requirements: Cin % 32 == 0, W % 16 == 0, H % 8 == 0.  Replaces nn.Conv2d(k, stride=1, padding=pad) on the DPT / FPN paths.
-int siu3r_conv2d_tc(int Nimg, int H, int W, int Cin, int Cout, int KH, int KW, int pad, const float* x, const float* x_lo,
+int siu3r_conv2d_tc(int Nimg, int H, int W, int Cin, int Cout, int KH, int KW, int pad_h, int pad_w, const float* x, const float* x_lo,
                     const float* Wt, const float* W_lo, float* y, int64_t ldc, const float* bias, const float* residual, int64_t ldr,
                     int act, int precision, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
@@ -779,7 +779,7 @@ int siu3r_conv2d_tc(int Nimg, int H, int W, int Cin, int Cout, int KH, int KW, i
         GemmParams p{};
         p.M = Nimg; /* image count: rows of the padded last pair are masked with it */ p.N = Cout; p.num_kb = KH * KW * (Cin / BK); p.C = y;
         p.ldc = ldc; p.bias = bias; p.residual = residual; p.ldr = ldr; p.act = act; p.alpha = 1.0f; p.conv = 1; p.H = H; p.W = W; p.Cin = Cin;
-        p.KH = KH; p.KW = KW; p.pad = pad; p.tiles_w = tiles_w; p.tiles_h = tiles_h;
+        p.KH = KH; p.KW = KW; p.pad = pad_h; p.pad_w = pad_w; p.tiles_w = tiles_w; p.tiles_h = tiles_h;
         dim3 grid((unsigned)(2 * ceil_div_i64(mtiles, 2)), (unsigned)(Cout / TC2_BN));
         return launch_tc2(ma, mb, p, grid, stream);
     }
@@ -801,7 +801,7 @@ int siu3r_conv2d_tc(int Nimg, int H, int W, int Cin, int Cout, int KH, int KW, i
     }
     GemmParams p{};
     p.M = (int)(mtiles * BM); p.N = Cout; p.num_kb = KH * KW * (Cin / BK); p.C = y; p.ldc = ldc; p.bias = bias; p.residual = residual;
-    p.ldr = ldr; p.act = act; p.alpha = 1.0f; p.conv = 1; p.H = H; p.W = W; p.Cin = Cin; p.KH = KH; p.KW = KW; p.pad = pad;
+    p.ldr = ldr; p.act = act; p.alpha = 1.0f; p.conv = 1; p.H = H; p.W = W; p.Cin = Cin; p.KH = KH; p.KW = KW; p.pad = pad_h; p.pad_w = pad_w;
     p.tiles_w = tiles_w; p.tiles_h = tiles_h;
     dim3 grid((unsigned)mtiles, (unsigned)ceil_div(Cout, bn));
     if (precision == 1) {

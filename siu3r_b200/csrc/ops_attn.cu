@@ -231,7 +231,15 @@ __global__ void __launch_bounds__(256) attn_small_rowflags_kernel(const uint8_t*
     // one CTA per (b, q) row: all_masked = 1 iff every key is masked
     const uint8_t* row = mask + (int64_t)blockIdx.x * Nk;
     int any = 0;
-    for (int i = threadIdx.x; i < Nk; i += blockDim.x) any |= (row[i] == 0);
+    if ((Nk & 15) == 0 && (((uintptr_t)row) & 15) == 0) {
+        const uint4* r4 = reinterpret_cast<const uint4*>(row);
+        for (int i = threadIdx.x; i < (Nk >> 4); i += blockDim.x) {
+            const uint4 v = r4[i];   // a byte is 0 (= attend) iff (x - 0x01010101) & ~x & 0x80808080 is non-zero
+            any |= (((v.x - 0x01010101u) & ~v.x) | ((v.y - 0x01010101u) & ~v.y) | ((v.z - 0x01010101u) & ~v.z) | ((v.w - 0x01010101u) & ~v.w)) & 0x80808080u;
+        }
+    } else {
+        for (int i = threadIdx.x; i < Nk; i += blockDim.x) any |= (row[i] == 0);
+    }
     any = __syncthreads_or(any);
     if (threadIdx.x == 0) all_masked[blockIdx.x] = any ? 0 : 1;
 }
@@ -242,7 +250,7 @@ __global__ void __launch_bounds__(AS_QT) attn_small_split_kernel(const float* __
                                                                  float* __restrict__ O, int64_t o_bs, int64_t o_ts,
                                                                  const uint8_t* __restrict__ mask, const uint8_t* __restrict__ all_masked,
                                                                  float* __restrict__ part, int H, int Nq, int Nk, int keys_per_split,
-                                                                 int nsplit, float scale) {
+                                                                 int nsplit, float scale, int round_out) {
     __shared__ __align__(16) float sK[AS_KEYS * 32];
     __shared__ __align__(16) float sV[AS_KEYS * 32];
     const int split = blockIdx.x, bh = blockIdx.y, qt = blockIdx.z;
@@ -285,13 +293,13 @@ __global__ void __launch_bounds__(AS_QT) attn_small_split_kernel(const float* __
             float dot = -INFINITY;
             if (j < cn && !(mrow && mrow[c0 + j])) {
                 const float* kp = sK + (c0 + j) * 32;
-                dot = 0.f;
+                float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;   // four independent chains (latency, not throughput, bounds this loop)
 #pragma unroll
                 for (int d = 0; d < 32; d += 4) {
                     const float4 kv = *reinterpret_cast<const float4*>(kp + d);   // broadcast read
-                    dot += qr[d] * kv.x + qr[d + 1] * kv.y + qr[d + 2] * kv.z + qr[d + 3] * kv.w;
+                    d0 += qr[d] * kv.x; d1 += qr[d + 1] * kv.y; d2 += qr[d + 2] * kv.z; d3 += qr[d + 3] * kv.w;
                 }
-                dot *= scale;
+                dot = ((d0 + d1) + (d2 + d3)) * scale;
             }
             sc[j] = dot;
             cmax = fmaxf(cmax, dot);
@@ -320,7 +328,9 @@ __global__ void __launch_bounds__(AS_QT) attn_small_split_kernel(const float* __
         float* op = O + (int64_t)b * o_bs + (int64_t)q * o_ts + h * 32;
         const float inv = 1.0f / l;
 #pragma unroll
-        for (int d = 0; d < 32; d += 4) *reinterpret_cast<float4*>(op + d) = make_float4(acc[d] * inv, acc[d + 1] * inv, acc[d + 2] * inv, acc[d + 3] * inv);
+        for (int d = 0; d < 32; ++d) { acc[d] *= inv; if (round_out) acc[d] = __uint_as_float(f2tf32(acc[d])); }
+#pragma unroll
+        for (int d = 0; d < 32; d += 4) *reinterpret_cast<float4*>(op + d) = make_float4(acc[d], acc[d + 1], acc[d + 2], acc[d + 3]);
         return;
     }
     float* rec = part + (((int64_t)bh * nsplit + split) * Nq + q) * AS_REC;
@@ -329,27 +339,36 @@ __global__ void __launch_bounds__(AS_QT) attn_small_split_kernel(const float* __
     for (int d = 0; d < 32; ++d) rec[2 + d] = acc[d];
 }
 
-// one warp per (b, h, q): lane = channel
+// one warp per (b, h, q): lane = channel.  The split weights exp(m_s - M) are computed once (lane s) and broadcast, so the
+// partial-record loads of all splits are independent and pipeline.
 __global__ void __launch_bounds__(128) attn_small_merge_kernel(const float* __restrict__ part, float* __restrict__ O, int64_t o_bs, int64_t o_ts,
-                                                               int H, int Nq, int nsplit, int total) {
+                                                               int H, int Nq, int nsplit, int total, int round_out) {
     const int w = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (w >= total) return;
     const int q = w % Nq, bh = w / Nq;
     const int b = bh / H, h = bh % H;
     const float* rec = part + ((int64_t)bh * nsplit * Nq + q) * AS_REC;
     const int64_t step = (int64_t)Nq * AS_REC;
+    float L = 0.f, o = 0.f;
     float M = -INFINITY;
     for (int s = lane; s < nsplit; s += 32) M = fmaxf(M, rec[s * step]);
     M = warp_max(M);
-    float L = 0.f, o = 0.f;
-    for (int s = 0; s < nsplit; ++s) {
-        const float ms = rec[s * step];
-        if (ms == -INFINITY) continue;
-        const float g = expf(ms - M);
-        L += rec[s * step + 1] * g;
-        o += rec[s * step + 2 + lane] * g;
+    for (int s0 = 0; s0 < nsplit; s0 += 32) {
+        const int s = s0 + lane;
+        float g = 0.f, lg = 0.f;
+        if (s < nsplit) {
+            const float ms = rec[s * step];
+            if (ms != -INFINITY) { g = expf(ms - M); lg = rec[s * step + 1] * g; }
+        }
+        L += lg;
+        const int n = min(32, nsplit - s0);
+#pragma unroll 8
+        for (int j = 0; j < n; ++j) o += rec[(s0 + j) * step + 2 + lane] * __shfl_sync(0xffffffffu, g, j);
     }
-    O[(int64_t)b * o_bs + (int64_t)q * o_ts + h * 32 + lane] = o / L;
+    L = warp_sum(L);
+    float r = o / L;
+    if (round_out) r = __uint_as_float(f2tf32(r));
+    O[(int64_t)b * o_bs + (int64_t)q * o_ts + h * 32 + lane] = r;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -428,6 +447,89 @@ __global__ void __launch_bounds__(256) msdeform_kernel(const float* __restrict__
 
 }  // namespace
 
+// ------------------------------------------------------------------------------------------------------------
+// (3b) deformable attention, vectorised: a warp serves one query and 32/(HD/4) heads at once (lane group = head, each lane
+//      4 channels -> every gather is a 16-byte load and one warp instruction moves 512 bytes).  The scalar work (softmax
+//      of the L*P logits, sampling coordinates, the 4 corner indices / bilinear weights) is computed ONCE per
+//      (head, point) by one lane and handed over through a small per-warp shared record, instead of redundantly by all
+//      32 lanes; out-of-range corners become weight 0 at a clamped address, so all loads of a point issue back to back.
+// ------------------------------------------------------------------------------------------------------------
+template <int HD>
+__global__ void __launch_bounds__(256) msdeform_vec_kernel(const float* __restrict__ value, int64_t ldv, int Lin, const float* __restrict__ ow,
+                                                          int64_t ldow, const float* __restrict__ ref, MsdaLevels lv, int B, int Lq, int nH, int L,
+                                                          int P, float* __restrict__ out, int64_t ldo, int round_out) {
+    constexpr int LPH = HD / 4;        // lanes per head
+    constexpr int HPW = 32 / LPH;      // heads per warp
+    __shared__ __align__(16) float s_rec[8][HPW * MSDA_MAX_LP][8];   // per warp: [item][w00 w01 w10 w11 | i00 i01 i10 i11]
+    const int wslot = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nHG = nH / HPW;
+    const int wid = blockIdx.x * 8 + wslot;
+    if (wid >= B * Lq * nHG) return;
+    const int hg = wid % nHG;
+    const int q = (wid / nHG) % Lq;
+    const int b = wid / (nHG * Lq);
+    const int LP = L * P;
+    const float* row = ow + ((int64_t)b * Lq + q) * ldow;
+    const float rx = ref[2 * q], ry = ref[2 * q + 1];
+    // ---- phase 1: one lane per (head, point) ----
+    for (int id = lane; id < HPW * LP; id += 32) {
+        const int hh = id / LP, i = id - hh * LP;
+        const int h = hg * HPW + hh;
+        const float* offs = row + (int64_t)h * LP * 2;
+        const float* logit = row + (int64_t)nH * LP * 2 + (int64_t)h * LP;
+        float mx = -INFINITY;
+        for (int j = 0; j < LP; ++j) mx = fmaxf(mx, logit[j]);
+        float sum = 0.f;
+        for (int j = 0; j < LP; ++j) sum += expf(logit[j] - mx);
+        const float inv = 1.f / sum;
+        const float w = expf(logit[i] - mx) * inv;
+        const int l = i / P;
+        const int Hl = lv.H[l], Wl = lv.W[l], st = lv.start[l];
+        const float locx = rx + offs[2 * i] / (float)Wl, locy = ry + offs[2 * i + 1] / (float)Hl;
+        const float gx = 2.f * locx - 1.f, gy = 2.f * locy - 1.f;
+        const float px = ((gx + 1.f) * (float)Wl - 1.f) * 0.5f, py = ((gy + 1.f) * (float)Hl - 1.f) * 0.5f;
+        const float fx = floorf(px), fy = floorf(py);
+        const int x0 = (int)fx, y0 = (int)fy;
+        const float ax = px - fx, ay = py - fy;
+        float* rec = s_rec[wslot][id];
+#pragma unroll
+        for (int cy = 0; cy < 2; ++cy)
+#pragma unroll
+            for (int cx = 0; cx < 2; ++cx) {
+                const int yy = y0 + cy, xx = x0 + cx;
+                const bool ok = yy >= 0 && yy < Hl && xx >= 0 && xx < Wl;
+                const float wy = cy ? ay : 1.f - ay, wx = cx ? ax : 1.f - ax;
+                rec[cy * 2 + cx] = ok ? w * wx * wy : 0.f;
+                rec[4 + cy * 2 + cx] = __int_as_float(ok ? st + yy * Wl + xx : st);
+            }
+    }
+    __syncwarp();
+    // ---- phase 2: lane group = head, lane = 4 channels ----
+    const int hh = lane / LPH;
+    const int h = hg * HPW + hh;
+    const float* vb = value + (int64_t)b * Lin * ldv + h * HD + (lane % LPH) * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* recs = s_rec[wslot][hh * LP];
+#pragma unroll 4
+    for (int i = 0; i < LP; ++i) {
+        const float4 wv = *reinterpret_cast<const float4*>(recs + i * 8);
+        const float4 iv = *reinterpret_cast<const float4*>(recs + i * 8 + 4);
+        const float4 v0 = __ldg(reinterpret_cast<const float4*>(vb + (int64_t)__float_as_int(iv.x) * ldv));
+        const float4 v1 = __ldg(reinterpret_cast<const float4*>(vb + (int64_t)__float_as_int(iv.y) * ldv));
+        const float4 v2 = __ldg(reinterpret_cast<const float4*>(vb + (int64_t)__float_as_int(iv.z) * ldv));
+        const float4 v3 = __ldg(reinterpret_cast<const float4*>(vb + (int64_t)__float_as_int(iv.w) * ldv));
+        acc.x += wv.x * v0.x; acc.y += wv.x * v0.y; acc.z += wv.x * v0.z; acc.w += wv.x * v0.w;
+        acc.x += wv.y * v1.x; acc.y += wv.y * v1.y; acc.z += wv.y * v1.z; acc.w += wv.y * v1.w;
+        acc.x += wv.z * v2.x; acc.y += wv.z * v2.y; acc.z += wv.z * v2.z; acc.w += wv.z * v2.w;
+        acc.x += wv.w * v3.x; acc.y += wv.w * v3.y; acc.z += wv.w * v3.z; acc.w += wv.w * v3.w;
+    }
+    if (round_out) {   // the sampled values only feed the output projection (a TF32 GEMM): round to nearest here
+        acc.x = __uint_as_float(f2tf32(acc.x)); acc.y = __uint_as_float(f2tf32(acc.y));
+        acc.z = __uint_as_float(f2tf32(acc.z)); acc.w = __uint_as_float(f2tf32(acc.w));
+    }
+    *reinterpret_cast<float4*>(out + ((int64_t)b * Lq + q) * ldo + h * HD + (lane % LPH) * 4) = acc;
+}
+
 extern "C" {
 
 // out[b, n, h*64 + d] = softmax(Q K^T * scale) V per (batch, head).  Element (b, n, h, d) of X lives at
@@ -456,8 +558,13 @@ int siu3r_flash_attn_d64(const float* Q, int64_t q_bs, int64_t q_ts, const float
     return SIU3R_OK;
 }
 
-static void attn_small_plan(int Nk, int* keys_per_split, int* nsplit) {
-    int ks = AS_KEYS;
+static void attn_small_plan(int B, int H, int Nq, int Nk, int* keys_per_split, int* nsplit) {
+    // enough CTAs for ~2 per SM: keys per split in [32, AS_KEYS], multiple of 32
+    const int64_t groups = (int64_t)B * H * ceil_div(Nq, AS_QT);
+    int ks = (int)ceil_div_i64((int64_t)Nk * groups, 296);
+    ks = ceil_div(ks, 32) * 32;
+    if (ks < 32) ks = 32;
+    if (ks > AS_KEYS) ks = AS_KEYS;
     *nsplit = ceil_div(Nk, ks);
     *keys_per_split = ks;
 }
@@ -465,7 +572,7 @@ static void attn_small_plan(int Nk, int* keys_per_split, int* nsplit) {
 // bytes of scratch siu3r_attn_small_d32 needs for this problem (row flags + split partials)
 int64_t siu3r_attn_small_d32_ws_bytes(int B, int H, int Nq, int Nk) {
     int ks, ns;
-    attn_small_plan(Nk, &ks, &ns);
+    attn_small_plan(B, H, Nq, Nk, &ks, &ns);
     const int64_t flags = ((int64_t)B * Nq + 255) / 256 * 256;
     return flags + (ns > 1 ? (int64_t)B * H * ns * Nq * AS_REC * 4 : 0);
 }
@@ -474,14 +581,14 @@ int64_t siu3r_attn_small_d32_ws_bytes(int B, int H, int Nq, int Nk) {
 // workspace: >= siu3r_attn_small_d32_ws_bytes(B, H, Nq, Nk) bytes of device memory, 256-byte aligned.
 int siu3r_attn_small_d32(const float* Q, int64_t q_bs, int64_t q_ts, const float* K, int64_t k_bs, int64_t k_ts, const float* V, int64_t v_bs,
                          int64_t v_ts, float* O, int64_t o_bs, int64_t o_ts, const uint8_t* mask, int B, int H, int Nq, int Nk, float scale,
-                         void* workspace, int64_t workspace_bytes, void* stream_) {
+                         int round_out, void* workspace, int64_t workspace_bytes, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     SIU3R_REQUIRE(Q && K && V && O && B > 0 && H > 0 && Nq > 0 && Nk > 0);
     SIU3R_REQUIRE(q_ts % 4 == 0 && k_ts % 4 == 0 && v_ts % 4 == 0 && q_bs % 4 == 0 && k_bs % 4 == 0 && v_bs % 4 == 0 && o_ts % 4 == 0 && o_bs % 4 == 0);
     SIU3R_REQUIRE((((uintptr_t)Q | (uintptr_t)K | (uintptr_t)V | (uintptr_t)O) & 15) == 0);
     SIU3R_REQUIRE(workspace && workspace_bytes >= siu3r_attn_small_d32_ws_bytes(B, H, Nq, Nk) && ((uintptr_t)workspace & 255) == 0);
     int ks, ns;
-    attn_small_plan(Nk, &ks, &ns);
+    attn_small_plan(B, H, Nq, Nk, &ks, &ns);
     uint8_t* flags = (uint8_t*)workspace;
     float* part = (float*)((uint8_t*)workspace + ((int64_t)B * Nq + 255) / 256 * 256);
     int launches = 1;
@@ -492,11 +599,11 @@ int siu3r_attn_small_d32(const float* Q, int64_t q_bs, int64_t q_ts, const float
     }
     dim3 grid((unsigned)ns, (unsigned)(B * H), (unsigned)ceil_div(Nq, AS_QT));
     attn_small_split_kernel<<<grid, AS_QT, 0, stream>>>(Q, q_bs, q_ts, K, k_bs, k_ts, V, v_bs, v_ts, O, o_bs, o_ts, mask, flags, part, H, Nq, Nk, ks,
-                                                        ns, scale);
+                                                        ns, scale, round_out);
     SIU3R_LAUNCH_CHECK();
     if (ns > 1) {
         const int total = B * H * Nq;
-        attn_small_merge_kernel<<<ceil_div(total, 4), 128, 0, stream>>>(part, O, o_bs, o_ts, H, Nq, ns, total);
+        attn_small_merge_kernel<<<ceil_div(total, 4), 128, 0, stream>>>(part, O, o_bs, o_ts, H, Nq, ns, total, round_out);
         SIU3R_LAUNCH_CHECK();
         ++launches;
     }
@@ -507,7 +614,7 @@ int siu3r_attn_small_d32(const float* Q, int64_t q_bs, int64_t q_ts, const float
 // value [B, Lin, nH*hd] (ldv), ow [B*Lq, ldow] = [sampling offsets | attention logits], ref [Lq, 2] normalised (x, y),
 // levels: level_hw [L][2] = (H_l, W_l) (host ints); out [B*Lq, ldo].  hd in {32, 64}; L*P <= 16.
 int siu3r_msdeform_attn(const float* value, int64_t ldv, int Lin, const float* ow, int64_t ldow, const float* ref, const int* level_hw, int L,
-                        int P, int B, int Lq, int nH, int hd, float* out, int64_t ldo, void* stream_) {
+                        int P, int B, int Lq, int nH, int hd, float* out, int64_t ldo, int round_out, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     SIU3R_REQUIRE(value && ow && ref && level_hw && out && L >= 1 && L <= 4 && P >= 1 && L * P <= MSDA_MAX_LP);
     SIU3R_REQUIRE(hd == 32 || hd == 64);
@@ -515,6 +622,17 @@ int siu3r_msdeform_attn(const float* value, int64_t ldv, int Lin, const float* o
     int start = 0;
     for (int l = 0; l < L; ++l) { lv.H[l] = level_hw[2 * l]; lv.W[l] = level_hw[2 * l + 1]; lv.start[l] = start; start += lv.H[l] * lv.W[l]; }
     SIU3R_REQUIRE(start == Lin);
+    SIU3R_REQUIRE(!round_out || (nH % (32 / (hd / 4)) == 0));   // rounding lives in the vectorised kernel
+    const bool vec = (ldv % 4 == 0) && (ldo % 4 == 0) && (((uintptr_t)value | (uintptr_t)out) & 15) == 0 && nH % (32 / (hd / 4)) == 0;
+    if (vec) {
+        const int hpw = 32 / (hd / 4);
+        const int nw = B * Lq * (nH / hpw);
+        if (hd == 64) msdeform_vec_kernel<64><<<ceil_div(nw, 8), 256, 0, stream>>>(value, ldv, Lin, ow, ldow, ref, lv, B, Lq, nH, L, P, out, ldo, round_out);
+        else msdeform_vec_kernel<32><<<ceil_div(nw, 8), 256, 0, stream>>>(value, ldv, Lin, ow, ldow, ref, lv, B, Lq, nH, L, P, out, ldo, round_out);
+        SIU3R_LAUNCH_CHECK();
+        siu3r_note_launch(1);
+        return SIU3R_OK;
+    }
     const int warps = B * Lq * nH;
     if (hd == 64)
         msdeform_kernel<2><<<ceil_div(warps, 8), 256, 0, stream>>>(value, ldv, Lin, ow, ldow, ref, lv, B, Lq, nH, L, P, out, ldo);

@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(256) split_tf32_kernel(const float4* __restric
 // ------------------------------------------------------------------------------------------------------------
 // Elementwise family (vectorised float4, n % 4 == 0 enforced by the host wrapper; tails handled scalar)
 // ------------------------------------------------------------------------------------------------------------
-enum EltOp { ELT_RELU = 0, ELT_ADD = 1, ELT_ADD_RELU = 2, ELT_GELU = 3, ELT_COPY = 4, ELT_SIGMOID = 5, ELT_CLAMP01 = 6, ELT_RELU_RN = 7, ELT_ROUND = 8 };
+enum EltOp { ELT_RELU = 0, ELT_ADD = 1, ELT_ADD_RELU = 2, ELT_GELU = 3, ELT_COPY = 4, ELT_SIGMOID = 5, ELT_CLAMP01 = 6, ELT_RELU_RN = 7, ELT_ROUND = 8, ELT_ADD_RN = 9 };
 
 __device__ __forceinline__ float elt_apply(int op, float a, float b) {
     switch (op) {
@@ -149,6 +149,7 @@ __device__ __forceinline__ float elt_apply(int op, float a, float b) {
         case ELT_CLAMP01: return fminf(fmaxf(a, 0.f), 1.f);
         case ELT_RELU_RN: return rn_tf32(fmaxf(a, 0.f));
         case ELT_ROUND: return rn_tf32(a);
+        case ELT_ADD_RN: return rn_tf32(a + b);
         default: return a;
     }
 }
@@ -264,7 +265,7 @@ __global__ void __launch_bounds__(256) pixel_shuffle_kernel(const float* __restr
 
 // im2col for NHWC input: out[(n,oh,ow), (kh,kw,ci)] (row stride ldo >= KH*KW*C, pad columns zeroed by caller's memset)
 __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ x, int N, int H, int W, int C, int KH, int KW, int stride, int pad,
-                                                     int OH, int OW, float* __restrict__ out, int64_t ldo, int round_out) {
+                                                     int pad_w, int OH, int OW, float* __restrict__ out, int64_t ldo, int round_out) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int K = KH * KW * C;
     const int64_t total = (int64_t)N * OH * OW * ldo;
@@ -280,7 +281,7 @@ __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ x
         const int ci = k % C;
         const int tap = k / C;
         const int kh = tap / KW, kw = tap % KW;
-        const int ih = oh * stride + kh - pad, iw = ow * stride + kw - pad;
+        const int ih = oh * stride + kh - pad, iw = ow * stride + kw - pad_w;
         if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = x[(((int64_t)n * H + ih) * W + iw) * C + ci];
     }
     out[idx] = round_out ? rn_tf32(v) : v;
@@ -474,10 +475,10 @@ int siu3r_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stre
     return SIU3R_OK;
 }
 
-// op: 0 relu(a), 1 a+b, 2 relu(a+b), 3 gelu(a), 4 copy, 5 sigmoid(a), 6 clamp(a, 0, 1), 7 RN_tf32(relu(a)), 8 RN_tf32(a)
+// op: 0 relu(a), 1 a+b, 2 relu(a+b), 3 gelu(a), 4 copy, 5 sigmoid(a), 6 clamp(a, 0, 1), 7 RN_tf32(relu(a)), 8 RN_tf32(a), 9 RN_tf32(a+b)
 int siu3r_eltwise(int op, const float* a, const float* b, float* out, int64_t n, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    SIU3R_REQUIRE(a && out && n > 0 && op >= 0 && op <= 8);
+    SIU3R_REQUIRE(a && out && n > 0 && op >= 0 && op <= 9);
     SIU3R_REQUIRE(((uintptr_t)a & 15) == 0 && ((uintptr_t)out & 15) == 0 && (!b || ((uintptr_t)b & 15) == 0));
     eltwise_kernel<<<grid_for(ceil_div_i64(n, 4)), 256, 0, stream>>>(op, a, b, out, n);
     SIU3R_LAUNCH_CHECK();
@@ -537,11 +538,11 @@ int siu3r_pixel_shuffle_nhwc(const float* g, int N, int H, int W, int C, int s, 
     return SIU3R_OK;
 }
 
-int siu3r_im2col_nhwc(const float* x, int N, int H, int W, int C, int KH, int KW, int stride, int pad, float* out, int64_t ldo, int round_out, void* stream_) {
+int siu3r_im2col_nhwc(const float* x, int N, int H, int W, int C, int KH, int KW, int stride, int pad, int pad_w, float* out, int64_t ldo, int round_out, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     SIU3R_REQUIRE(x && out && N > 0 && stride >= 1 && ldo >= (int64_t)KH * KW * C);
-    const int OH = (H + 2 * pad - KH) / stride + 1, OW = (W + 2 * pad - KW) / stride + 1;
-    im2col_kernel<<<grid_for((int64_t)N * OH * OW * ldo), 256, 0, stream>>>(x, N, H, W, C, KH, KW, stride, pad, OH, OW, out, ldo, round_out);
+    const int OH = (H + 2 * pad - KH) / stride + 1, OW = (W + 2 * pad_w - KW) / stride + 1;
+    im2col_kernel<<<grid_for((int64_t)N * OH * OW * ldo), 256, 0, stream>>>(x, N, H, W, C, KH, KW, stride, pad, pad_w, OH, OW, out, ldo, round_out);
     SIU3R_LAUNCH_CHECK();
     siu3r_note_launch(1);
     return SIU3R_OK;

@@ -408,8 +408,8 @@ class SIU3RModel:
         value = self._lin(fn, ex.value, ar=True)
         ow = self._lin(qn, ex.ow, ar=True)
         samp = torch.empty(B * Lq, C, device=self.dev)
-        ops.msdeform_attn(value, P, ow, k.ad_ref, [(gh, gw)], 4, B, Lq, 16, 64, samp)
-        self._lin(samp, ex.out, residual=c, out=c)
+        ops.msdeform_attn(value, P, ow, k.ad_ref, [(gh, gw)], 4, B, Lq, 16, 64, samp, round_out=self.R)
+        self._lin(samp, ex.out, ar=True, residual=c, out=c)
         t = self._ln(c, ex.ffn_norm, 1e-6)
         t1 = self._lin(t, ex.fc1, ar=True)  # [B*Lq, 256]
         dw = torch.empty_like(t1)
@@ -501,17 +501,18 @@ class SIU3RModel:
             for bt in range(BT):
                 ops.rows_affine(e[bt], out=x[bt, starts[i]:starts[i] + h * w_])
         x = x.view(BT * Ltot, E)
-        for lyr in m.enc:
-            q = ops.eltwise(ELT_ADD, x, k.m2f_pos)
-            value = self._lin(x, lyr.value)
-            ow = self._lin(q, lyr.ow)
+        ADD_RN = ops.ELT_ADD_RN if self.R else ELT_ADD   # sums that only feed a TF32 GEMM are rounded where they are produced
+        for li_, lyr in enumerate(m.enc):
+            q = ops.eltwise(ADD_RN, x, k.m2f_pos)
+            value = self._lin(x, lyr.value, ar=li_ > 0)   # x is a (rounded) LayerNorm output from the second layer on
+            ow = self._lin(q, lyr.ow, ar=True)
             samp = torch.empty(BT * Ltot, E, device=self.dev)
-            ops.msdeform_attn(value, Ltot, ow, k.m2f_ref, lv, 4, BT, Ltot, 8, 32, samp)
-            y = self._lin(samp, lyr.out, residual=x)
-            x = ops.layernorm(y, lyr.ln1[0], lyr.ln1[1], 1e-5)
-            f1 = self._lin(x, lyr.fc1, act=ACT_RELU)
-            y = self._lin(f1, lyr.fc2, residual=x)
-            x = ops.layernorm(y, lyr.ln2[0], lyr.ln2[1], 1e-5)
+            ops.msdeform_attn(value, Ltot, ow, k.m2f_ref, lv, 4, BT, Ltot, 8, 32, samp, round_out=self.R)
+            y = self._lin(samp, lyr.out, ar=True, residual=x)
+            x = self._ln(y, lyr.ln1, 1e-5)
+            f1 = self._lin(x, lyr.fc1, ar=True, ro=True, act=ACT_RELU)
+            y = self._lin(f1, lyr.fc2, ar=True, residual=x)
+            x = self._ln(y, lyr.ln2, 1e-5)
         x = x.view(BT, Ltot, E)
         # FPN level (stride 4)
         h4, w4 = S0 // 4, S1 // 4
@@ -523,7 +524,7 @@ class SIU3RModel:
         cw, gw_, gb_ = m.output
         o = self._conv(cur, cw, 3, pad=1)
         o = ops.groupnorm(o.view(BT, h4 * w4, E), 32, gw_, gb_, 1e-5, True).view(BT, h4, w4, E)
-        mask_feat = self._conv(o, m.mask_proj, 1)  # [BT, h4, w4, 256]
+        mask_feat = self._conv(o, m.mask_proj, 1, ro=True)  # [BT, h4, w4, 256]; only ever the A operand of the mask GEMMs
         self._cap("m2f_mask_features", mask_feat)
         self._cap("m2f_tokens", x)
         # transformer module: keys of level i for batch b = frames (t) x pixels, + level embedding
@@ -535,20 +536,20 @@ class SIU3RModel:
                 for t in range(T):
                     ops.rows_affine(x[b * T + t, starts[i]:starts[i] + n], shift=k.tm_lvl[i], out=s[b, t * n:(t + 1) * n])
             s = s.view(B * T * n, E)
-            src.append(s)
-            srcpos.append(ops.eltwise(ELT_ADD, s, k.tm_pos[i]))
+            srcpos.append(ops.eltwise(ADD_RN, s, k.tm_pos[i]))
+            src.append(ops.round_tf32(s) if self.R else s)   # keys / values of all 9 decoder layers: rounded once
         hidden, qpos = k.hidden0, k.qpos
         mf = mask_feat.view(B, T * h4 * w4, E)
 
         def predict(hid, target_hw):
-            inter = ops.layernorm(hid, m.dec_ln[0], m.dec_ln[1], 1e-5)
-            e = self._lin(inter, m.mask_mlp[0], act=ACT_RELU)
-            e = self._lin(e, m.mask_mlp[1], act=ACT_RELU)
-            e = self._lin(e, m.mask_mlp[2])  # [B*Q, 256]
+            inter = self._ln(hid, m.dec_ln, 1e-5)
+            e = self._lin(inter, m.mask_mlp[0], ar=True, ro=True, act=ACT_RELU)
+            e = self._lin(e, m.mask_mlp[1], ar=True, ro=True, act=ACT_RELU)
+            e = self._lin(e, m.mask_mlp[2], ar=True)  # [B*Q, 256]
             logits = torch.empty(B, T * h4 * w4, Q, device=self.dev)
             for b in range(B):  # einsum("bqc,btchw->bqthw") as a per-batch GEMM, pixel-major output
                 wq = ops.Weight(e[b * Q:(b + 1) * Q], None, self.prec)
-                self._lin(mf[b], wq, out=logits[b])
+                self._lin(mf[b], wq, ar=True, out=logits[b])
             amask = None
             if target_hw is not None:
                 amask = ops.attn_mask_from_logits(logits, B, T, h4, w4, Q, target_hw[0], target_hw[1])
@@ -560,29 +561,30 @@ class SIU3RModel:
             li = idx % 3
             n = lv[li][0] * lv[li][1] * T
             # masked cross-attention (post-norm)
-            qin = ops.eltwise(ELT_ADD, hidden, qpos)
-            qh = self._lin(qin, lyr.cq)
-            kh = self._lin(srcpos[li], lyr.ck)
-            vh = self._lin(src[li], lyr.cv)
+            qin = ops.eltwise(ADD_RN, hidden, qpos)
+            qh = self._lin(qin, lyr.cq, ar=True)
+            kh = self._lin(srcpos[li], lyr.ck, ar=True)
+            vh = self._lin(src[li], lyr.cv, ar=True)
             att = torch.empty(B * Q, E, device=self.dev)
-            ops.attn_small_d32(qh, Q * E, E, kh, n * E, E, vh, n * E, E, att, Q * E, E, amask, B, nh, Q, n, 32 ** -0.5)
-            y = self._lin(att, lyr.cout, residual=hidden)
-            hidden = ops.layernorm(y, lyr.cln[0], lyr.cln[1], 1e-5)
+            ops.attn_small_d32(qh, Q * E, E, kh, n * E, E, vh, n * E, E, att, Q * E, E, amask, B, nh, Q, n, 32 ** -0.5, round_out=self.R)
+            y = self._lin(att, lyr.cout, ar=True, residual=hidden)
+            hidden = self._ln(y, lyr.cln, 1e-5)
             # query self-attention
-            qin = ops.eltwise(ELT_ADD, hidden, qpos)
-            qk = self._lin(qin, lyr.sqk)          # [B*Q, 512] = [q | k]
-            vv = self._lin(hidden, lyr.sv)
+            qin = ops.eltwise(ADD_RN, hidden, qpos)
+            qk = self._lin(qin, lyr.sqk, ar=True)          # [B*Q, 512] = [q | k]
+            vv = self._lin(hidden, lyr.sv, ar=True)
             att = torch.empty(B * Q, E, device=self.dev)
-            ops.attn_small_d32(qk, Q * 2 * E, 2 * E, qk[:, E:], Q * 2 * E, 2 * E, vv, Q * E, E, att, Q * E, E, None, B, nh, Q, Q, 32 ** -0.5)
-            y = self._lin(att, lyr.sout, residual=hidden)
-            hidden = ops.layernorm(y, lyr.sln[0], lyr.sln[1], 1e-5)
+            ops.attn_small_d32(qk, Q * 2 * E, 2 * E, qk[:, E:], Q * 2 * E, 2 * E, vv, Q * E, E, att, Q * E, E, None, B, nh, Q, Q, 32 ** -0.5,
+                               round_out=self.R)
+            y = self._lin(att, lyr.sout, ar=True, residual=hidden)
+            hidden = self._ln(y, lyr.sln, 1e-5)
             # FFN
-            f1 = self._lin(hidden, lyr.fc1, act=ACT_RELU)
-            y = self._lin(f1, lyr.fc2, residual=hidden)
-            hidden = ops.layernorm(y, lyr.fln[0], lyr.fln[1], 1e-5)
+            f1 = self._lin(hidden, lyr.fc1, ar=True, ro=True, act=ACT_RELU)
+            y = self._lin(f1, lyr.fc2, ar=True, residual=hidden)
+            hidden = self._ln(y, lyr.fln, 1e-5)
             last = idx == len(m.dec) - 1
             inter, logits, amask = predict(hidden, None if last else lv[(idx + 1) % 3])
-        cls = self._lin(inter, m.cls)  # [B*Q, 21]
+        cls = self._lin(inter, m.cls, ar=True)  # [B*Q, 21]
         return cls.view(B, Q, -1), logits.view(B * T, h4, w4, Q)
 
     # ---- panoptic post-process (image_processing_video_mask2former.py:1238-1481, model.py:231-312) ------------------------
@@ -682,7 +684,7 @@ class SIU3RModel:
         # ---- encoder input: patch tokens + intrinsics token ----
         x = torch.empty(Bn, N, 1024, device=self.dev)
         cols = torch.empty(Bn * P, 1024, device=self.dev)
-        ops._lib.check(lib.siu3r_im2col_nhwc(img4.data_ptr(), Bn, S0, S1, 4, 16, 16, 16, 0, cols.data_ptr(), 1024, 1 if self.R else 0, ops._stream()),
+        ops._lib.check(lib.siu3r_im2col_nhwc(img4.data_ptr(), Bn, S0, S1, 4, 16, 16, 16, 0, 0, cols.data_ptr(), 1024, 1 if self.R else 0, ops._stream()),
                        "im2col")
         for i in range(Bn):
             self._lin(cols[i * P:(i + 1) * P], w.patch, ar=True, out=x[i, :P])

@@ -12,7 +12,7 @@ import torch
 from . import _lib
 
 ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
-ELT_RELU, ELT_ADD, ELT_ADD_RELU, ELT_GELU, ELT_COPY, ELT_SIGMOID, ELT_CLAMP01, ELT_RELU_RN, ELT_ROUND = 0, 1, 2, 3, 4, 5, 6, 7, 8
+ELT_RELU, ELT_ADD, ELT_ADD_RELU, ELT_GELU, ELT_COPY, ELT_SIGMOID, ELT_CLAMP01, ELT_RELU_RN, ELT_ROUND, ELT_ADD_RN = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9
 ACT_ROUND_TF32 = 4  # flag OR-ed into `act`: store RN_tf32(result)
 PREC_TF32, PREC_FP32X3 = 1, 3
 
@@ -75,7 +75,7 @@ def split_tf32(x: torch.Tensor):
 class Weight:
     """A [N, K] K-major matrix (nn.Linear.weight layout) prepared for the tensor-core path."""
 
-    __slots__ = ("w", "w_lo", "bias", "N", "K")
+    __slots__ = ("w", "w_lo", "bias", "N", "K", "_rows")
 
     def __init__(self, w: torch.Tensor, bias: torch.Tensor | None, precision: int):
         w = w.contiguous().float()
@@ -92,6 +92,25 @@ class Weight:
         else:
             self.w, self.w_lo = w, None
         self.bias = None if bias is None else bias.contiguous().float()
+        self._rows = None
+
+    def rowpacked(self, KH: int, KW: int, Cin: int) -> "Weight":
+        """[Cout, KH*KW*Cin] conv weight re-laid as [Cout, KH*32]: the KW*Cin <= 32 taps of one filter row become one
+        32-wide channel vector (zero padded), matching the activations packed by siu3r_im2col_nhwc(KH=1)."""
+        if self._rows is None:
+            assert KW * Cin <= 32 and self.K == KH * KW * Cin
+            r = object.__new__(Weight)
+            r.N, r.K, r.bias, r._rows = self.N, KH * 32, self.bias, None
+
+            def relay(w):
+                if w is None:
+                    return None
+                o = torch.zeros(self.N, KH, 32, device=w.device, dtype=torch.float32)
+                o[:, :, : KW * Cin] = w[:, : self.K].view(self.N, KH, KW * Cin)
+                return o.view(self.N, KH * 32)
+            r.w, r.w_lo = relay(self.w), relay(self.w_lo)
+            self._rows = r
+        return self._rows
 
 
 def round_tf32(x: torch.Tensor) -> torch.Tensor:
@@ -174,7 +193,7 @@ def conv2d_tc_supported(H: int, W: int, Cin: int) -> bool:
     return Cin % 32 == 0 and W % 16 == 0 and H % 8 == 0
 
 
-def conv2d(x: torch.Tensor, wt: Weight, KH: int, KW: int, stride: int = 1, pad: int = 0, act: int = ACT_NONE,
+def conv2d(x: torch.Tensor, wt: Weight, KH: int, KW: int, stride: int = 1, pad: int | tuple = 0, act: int = ACT_NONE,
            residual: torch.Tensor | None = None, out: torch.Tensor | None = None, precision: int = PREC_TF32, a_rounded: bool = False,
            round_out: bool = False) -> torch.Tensor:
     """NHWC convolution.  wt is [Cout, KH*KW*Cin] ((kh, kw, ci) fastest = ci).  Stride-1 convs with tensor-core friendly
@@ -183,14 +202,22 @@ def conv2d(x: torch.Tensor, wt: Weight, KH: int, KW: int, stride: int = 1, pad: 
     N, H, W, Cin = x.shape
     assert x.is_contiguous()
     Cout = wt.N
-    OH = (H + 2 * pad - KH) // stride + 1
-    OW = (W + 2 * pad - KW) // stride + 1
+    pad_h, pad_w = pad if isinstance(pad, tuple) else (pad, pad)
+    OH = (H + 2 * pad_h - KH) // stride + 1
+    OW = (W + 2 * pad_w - KW) // stride + 1
     if out is None:
         out = torch.empty(N, OH, OW, Cout, device=x.device, dtype=torch.float32)
-    if KH == 1 and KW == 1 and stride == 1 and pad == 0:
+    if KH == 1 and KW == 1 and stride == 1 and pad_h == 0 and pad_w == 0:
         gemm(x.view(-1, Cin), wt, out=out.view(-1, Cout), act=act, residual=None if residual is None else residual.view(-1, Cout),
              precision=precision, a_rounded=a_rounded, round_out=round_out)
         return out
+    if stride == 1 and KH > 1 and KW > 1 and KW * Cin <= 32 and conv2d_tc_supported(H, W, 32) and OH == H and OW == W:
+        # few input channels (the RGB image): pack the KW taps of a filter row into one 32-wide vector per pixel (a 1 x KW
+        # im2col, 32 floats per pixel instead of KH*KW*Cin) and run the KH x 1 remainder as implicit GEMM on the tensor cores
+        rows = torch.empty(N, H, W, 32, device=x.device, dtype=torch.float32)
+        rnd = 1 if precision == PREC_TF32 else 0
+        _lib.check(_lib.load().siu3r_im2col_nhwc(_p(x), N, H, W, Cin, 1, KW, 1, 0, pad_w, _p(rows), 32, rnd, _stream()), "im2col(rows)")
+        return conv2d(rows, wt.rowpacked(KH, KW, Cin), KH, 1, 1, (pad_h, 0), act, residual, out, precision, True, round_out)
     if stride == 1 and conv2d_tc_supported(H, W, Cin) and OH == H and OW == W:
         x_lo = None
         xx = x
@@ -202,7 +229,7 @@ def conv2d(x: torch.Tensor, wt: Weight, KH: int, KW: int, stride: int = 1, pad: 
             if round_out:
                 act = act | ACT_ROUND_TF32
         with _Prof("conv2d_tc", 2.0 * N * H * W * Cout * KH * KW * Cin):
-            code = _lib.load().siu3r_conv2d_tc(N, H, W, Cin, Cout, KH, KW, pad, _p(xx), _p(x_lo), _p(wt.w), _p(wt.w_lo), _p(out), Cout,
+            code = _lib.load().siu3r_conv2d_tc(N, H, W, Cin, Cout, KH, KW, pad_h, pad_w, _p(xx), _p(x_lo), _p(wt.w), _p(wt.w_lo), _p(out), Cout,
                                                _p(wt.bias), _p(residual), Cout, act, precision, _stream())
         _lib.check(code, "conv2d_tc")
         return out
@@ -210,7 +237,7 @@ def conv2d(x: torch.Tensor, wt: Weight, KH: int, KW: int, stride: int = 1, pad: 
     ldo = wt.w.shape[1]
     cols = torch.empty(N * OH * OW, ldo, device=x.device, dtype=torch.float32)
     rnd = 1 if precision == PREC_TF32 else 0  # the column matrix only feeds the GEMM: round it on the way out
-    code = _lib.load().siu3r_im2col_nhwc(_p(x), N, H, W, Cin, KH, KW, stride, pad, _p(cols), ldo, rnd, _stream())
+    code = _lib.load().siu3r_im2col_nhwc(_p(x), N, H, W, Cin, KH, KW, stride, pad_h, pad_w, _p(cols), ldo, rnd, _stream())
     _lib.check(code, "im2col")
     assert K <= ldo
     gemm(cols, wt, out=out.view(-1, Cout), act=act, residual=None if residual is None else residual.view(-1, Cout), precision=precision,
@@ -267,21 +294,21 @@ def flash_attn_tc(q: torch.Tensor, q_off: int, q_bs: int, q_ts: int, q_width: in
     return out
 
 
-def attn_small_d32(q, q_bs, q_ts, k, k_bs, k_ts, v, v_bs, v_ts, out, o_bs, o_ts, mask, B, H, Nq, Nk, scale):
+def attn_small_d32(q, q_bs, q_ts, k, k_bs, k_ts, v, v_bs, v_ts, out, o_bs, o_ts, mask, B, H, Nq, Nk, scale, round_out=False):
     lib = _lib.load()
     nb = lib.siu3r_attn_small_d32_ws_bytes(B, H, Nq, Nk)
     ws = torch.empty(nb, dtype=torch.uint8, device=q.device)
     code = lib.siu3r_attn_small_d32(_p(q), q_bs, q_ts, _p(k), k_bs, k_ts, _p(v), v_bs, v_ts, _p(out), o_bs, o_ts, _p(mask), B, H, Nq, Nk,
-                                    scale, _p(ws), nb, _stream())
+                                    scale, 1 if round_out else 0, _p(ws), nb, _stream())
     _lib.check(code, "attn_small_d32")
     return out
 
 
-def msdeform_attn(value, Lin, ow, ref, levels_hw, P, B, Lq, nH, hd, out):
+def msdeform_attn(value, Lin, ow, ref, levels_hw, P, B, Lq, nH, hd, out, round_out=False):
     L = len(levels_hw)
     arr = (C.c_int * (2 * L))(*[int(v) for hw in levels_hw for v in hw])
     code = _lib.load().siu3r_msdeform_attn(_p(value), value.stride(-2) if value.dim() > 1 else nH * hd, Lin, _p(ow), ow.stride(-2), _p(ref), arr, L,
-                                           P, B, Lq, nH, hd, _p(out), out.stride(-2), _stream())
+                                           P, B, Lq, nH, hd, _p(out), out.stride(-2), 1 if round_out else 0, _stream())
     _lib.check(code, "msdeform_attn")
     return out
 

@@ -116,6 +116,22 @@ def test_conv2d_im2col(cfg):
     assert rel_err(y, ref) < 1e-4  # K up to 6912: error grows with the MMA chain length (tools/acc_probe.py)
 
 
+@pytest.mark.parametrize("prec", [1, 3])
+def test_conv2d_rowpacked_7x7_image(prec):
+    """7x7 conv on a 3(+1)-channel image (dpt_gs_head input_merger): 1x7 row packing + 7x1 implicit GEMM, fused ReLU + residual."""
+    from siu3r_b200 import ops
+    N, H, W, Cin, Cout, k = 2, 40, 48, 4, 256, 7
+    x = rnd(N, H, W, Cin, seed=61)
+    x[..., 3] = 0
+    w = rnd(Cout, Cin, k, k, seed=62, scale=(Cin * k * k) ** -0.5)
+    b = rnd(Cout, seed=63)
+    res = rnd(N, H, W, Cout, seed=64)
+    wt = ops.Weight(w.permute(0, 2, 3, 1).reshape(Cout, -1), b, prec)
+    y = ops.conv2d(x, wt, k, k, pad=3, act=ops.ACT_RELU, residual=res, precision=prec)
+    ref = F.relu(F.conv2d(x.permute(0, 3, 1, 2), w, b, padding=3)).permute(0, 2, 3, 1) + res
+    assert rel_err(y, ref) < (3e-3 if prec == 1 else 3e-5)
+
+
 def test_conv_transpose_as_gemm_pixel_shuffle():
     from siu3r_b200 import ops
     N, H, W, Cin, Cout, s = 2, 8, 8, 96, 96, 4

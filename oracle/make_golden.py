@@ -1,6 +1,7 @@
 """ORACLE / TEST INFRASTRUCTURE: generate tests/golden/model_S*.npz from the UNMODIFIED reference (CPU, fp32).
 
-Run in the build container (needs /root/reference):   python oracle/make_golden.py 64 256
+Run in the build container (needs /root/reference):   python oracle/make_golden.py 64 256 512
+                                                       python oracle/make_golden.py --views=4 64 256 512   (multi-view model)
 Each fixture holds, per stage boundary of SIU3RModel.forward, the tensor's shape / mean / abs-mean / abs-max and
 2048 samples at fixed pseudo-random flat indices (oracle/ref_model.py:sample_indices), plus the full small outputs
 (class logits, segment infos, label histograms).  Inputs and weights are regenerated on the GPU box from seeds
@@ -22,18 +23,19 @@ from oracle import ref_model as R  # noqa: E402
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
 
-def main(sizes):
+def main(sizes, views=2):
+    """views == 2: SIU3RModel (model_S*.npz); views > 2: SIU3RMultiViewModel (model_V{views}_S*.npz, BASELINE config 4)."""
     os.makedirs(OUT, exist_ok=True)
     sd = R.make_state_dict()
     for S in sizes:
         t0 = time.time()
         torch.set_num_threads(os.cpu_count())
-        model = R.build_reference(S, sd)
-        img, K = R.synthetic_inputs(1, 2, S)
+        model = R.build_reference(S, sd, multiview=views > 2)
+        img, K = R.synthetic_inputs(1, views, S)
         t1 = time.time()
-        st = R.run_reference_stages(model, img, K)
+        st = (R.run_reference_stages_multi if views > 2 else R.run_reference_stages)(model, img, K)
         t2 = time.time()
-        arrays, meta = {}, {"size": S, "forward_s": t2 - t1, "threads": torch.get_num_threads()}
+        arrays, meta = {}, {"size": S, "views": views, "forward_s": t2 - t1, "threads": torch.get_num_threads()}
         for name, v in st.items():
             if torch.is_tensor(v):
                 sm = R.summarize(v)
@@ -51,9 +53,12 @@ def main(sizes):
         meta["qc0"] = s2
         meta["sem_hist"] = torch.bincount(st["g_semantic_labels"].flatten().long(), minlength=22).tolist()
         meta["inst_hist"] = torch.bincount(st["g_instance_labels"].flatten().long()).tolist()
-        np.savez_compressed(os.path.join(OUT, f"model_S{S}.npz"), meta=json.dumps(meta), **arrays)
+        name = f"model_S{S}.npz" if views == 2 else f"model_V{views}_S{S}.npz"
+        np.savez_compressed(os.path.join(OUT, name), meta=json.dumps(meta), **arrays)
         print(f"S={S}: build {t1 - t0:.1f}s forward {t2 - t1:.1f}s infos={st['seg_infos']}", flush=True)
 
 
 if __name__ == "__main__":
-    main([int(a) for a in sys.argv[1:]] or [64, 256])
+    args = [a for a in sys.argv[1:] if not a.startswith("--views=")]
+    nv = [int(a.split("=")[1]) for a in sys.argv[1:] if a.startswith("--views=")]
+    main([int(a) for a in args] or [64, 256], views=nv[0] if nv else 2)

@@ -79,7 +79,7 @@ def build_reference(size: int, state_dict: dict | None = None, multiview: bool =
     if state_dict is not None:
         missing, unexpected = model.load_state_dict(state_dict, strict=False)
         assert not unexpected, unexpected
-        assert all("criterion" in k for k in missing), missing
+        assert all("criterion" in k or k == "backbone.mask_token" for k in missing), missing   # mask_token: unused by forward
     return model
 
 
@@ -142,6 +142,70 @@ def run_reference_stages(model, img, K) -> dict:
     st["masks_queries_logits"] = seg_out.masks_queries_logits
     for name in ("means", "covariances", "harmonics", "opacities", "scales", "rotations",
                  "semantic_labels", "instance_labels"):
+        st["g_" + name] = getattr(g, name)
+    st["seg_masks"] = [m.clone() for m in seg_masks]
+    st["seg_infos"] = seg_infos
+    st["query_scores"] = q_scores
+    st["seg_query_class_logits"] = g.seg_query_class_logits
+    return st
+
+
+@torch.no_grad()
+def run_reference_stages_multi(model, img, K) -> dict:
+    """Run SIU3RMultiViewModel.forward (model_multi.py:310-392) and capture stage-boundary tensors with forward hooks.
+    Per-view modules are called once per view (head2 / gaussian_param_head2 V-1 times): their outputs are stored per call."""
+    st: dict = {}
+    hooks = []
+
+    def grab(name, idx=None):
+        def fn(_m, _inp, out):
+            o = out if idx is None else out[idx]
+            st[name] = o.detach().clone()
+        return fn
+
+    bb = model.backbone
+    for i in (0, 5, 11, 17, 23):
+        hooks.append(bb.enc_blocks[i].register_forward_hook(grab(f"enc{i}")))
+    hooks.append(bb.enc_norm.register_forward_hook(grab("enc_norm")))
+    for i in (0, 5, 11):
+        hooks.append(bb.dec_blocks[i].register_forward_hook(grab(f"dec1_{i}", 0)))
+        hooks.append(bb.dec_blocks2[i].register_forward_hook(grab(f"dec2_{i}", 0)))
+    counters = {"adapter": 0, "pts": 0, "raw": 0}
+
+    def adapter_hook(_m, _inp, out):
+        v = counters["adapter"]
+        for j, f in enumerate(out):
+            st[f"adapter_v{v}_f{j + 1}"] = f.detach().clone()
+        counters["adapter"] += 1
+
+    def pts_hook(_m, _inp, out):
+        st[f"pts3d_{counters['pts']}"] = out["pts3d"].detach().clone()
+        counters["pts"] += 1
+
+    def raw_hook(_m, _inp, out):
+        st[f"gs_raw_{counters['raw']}"] = out.detach().clone()
+        counters["raw"] += 1
+
+    hooks.append(model.adapter.register_forward_hook(adapter_hook))
+    hooks.append(model.downstream_head1.register_forward_hook(pts_hook))   # view 0 first, then views 1.. (model_multi.py:175-185)
+    hooks.append(model.downstream_head2.register_forward_hook(pts_hook))
+    hooks.append(model.gaussian_param_head1.register_forward_hook(raw_hook))
+    hooks.append(model.gaussian_param_head2.register_forward_hook(raw_hook))
+    pd = model.mask2former.model.pixel_decoder
+
+    def pd_hook(_m, _inp, out):
+        st["m2f_mask_features"] = out.mask_features.detach().clone()
+        for j, f in enumerate(out.multi_scale_features):
+            st[f"m2f_ms{j}"] = f.detach().clone()
+
+    hooks.append(pd.register_forward_hook(pd_hook))
+    out = model(img, K, enable_query_class_logit_lift=True)
+    for h in hooks:
+        h.remove()
+    g, seg_out, seg_masks, seg_infos, q_scores = out
+    st["class_queries_logits"] = seg_out.class_queries_logits
+    st["masks_queries_logits"] = seg_out.masks_queries_logits
+    for name in ("means", "covariances", "harmonics", "opacities", "scales", "rotations", "semantic_labels", "instance_labels"):
         st["g_" + name] = getattr(g, name)
     st["seg_masks"] = [m.clone() for m in seg_masks]
     st["seg_infos"] = seg_infos

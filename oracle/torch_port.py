@@ -116,6 +116,46 @@ def backbone(sd, images, intrinsics):
     return dict(all_feat=[strip(t) for t in all_feat], dec1=[strip(t) for t in dec1], dec2=[strip(t) for t in dec2], gh=gh, gw=gw)
 
 
+def backbone_multi(sd, images, intrinsics):
+    """AsymmetricCroCoMulti.forward (backbone_croco.py:537-590) + _decoder (:487-535): V >= 2 views.  View 0 runs dec_blocks,
+    views 1..V-1 run dec_blocks2; the cross-attention memory of view i is the concatenation (in view order) of the other
+    V-1 views' previous-layer tokens, intrinsics tokens included, with their own positions (generate_ctx_views :500-506)."""
+    B, V, _, H, W = images.shape
+    p = "backbone."
+    img = images.flatten(0, 1)                                    # (b v) ordering, :552
+    x = F.conv2d(img, sd[p + "patch_embed.proj.weight"], sd[p + "patch_embed.proj.bias"], stride=16)
+    gh, gw = x.shape[2], x.shape[3]
+    x = x.flatten(2).transpose(1, 2)
+    emb = F.linear(intrinsics.flatten(2), sd[p + "intrinsic_encoder.weight"], sd[p + "intrinsic_encoder.bias"])  # [B,V,1024]
+    x = torch.cat((x, emb.flatten(0, 1)[:, None]), dim=1)
+    pos = torch.cartesian_prod(torch.arange(gh), torch.arange(gw))
+    pos = torch.cat((pos, torch.tensor([[gh, 0]])), 0)[None].expand(B * V, -1, -1)
+    all_feat = []
+    for i in range(24):
+        x = _enc_block(x, pos, sd, p + f"enc_blocks.{i}")
+        all_feat.append(x)
+    N = x.shape[1]
+    feat = _ln(x, sd, p + "enc_norm", 1e-6).view(B, V, N, -1)
+    pose = pos.reshape(B, V, N, 2)
+
+    def ctx(t):  # [B,V,L,C] -> [B,V,(V-1)L,C]: for view i, all views j != i in order
+        return torch.stack([torch.cat([t[:, j] for j in range(V) if j != i], dim=1) for i in range(V)], dim=1)
+
+    pos_ctx = ctx(pose)
+    outs = [feat]
+    f = _lin(feat, sd, p + "decoder_embed")
+    for i in range(12):
+        c = ctx(f)
+        n1 = _dec_block(f[:, 0], c[:, 0], pose[:, 0], pos_ctx[:, 0], sd, p + f"dec_blocks.{i}")
+        n2 = _dec_block(f[:, 1:].flatten(0, 1), c[:, 1:].flatten(0, 1), pose[:, 1:].flatten(0, 1), pos_ctx[:, 1:].flatten(0, 1), sd,
+                        p + f"dec_blocks2.{i}")
+        f = torch.cat((n1[:, None], n2.view(B, V - 1, N, -1)), dim=1)
+        outs.append(f)
+    outs[-1] = _ln(outs[-1], sd, p + "dec_norm", 1e-6)
+    all_feat = [t.view(B, V, N, -1)[:, :, :-1] for t in all_feat]
+    return dict(all_feat=all_feat, dec=[t[:, :, :-1] for t in outs], gh=gh, gw=gw)
+
+
 # ---- DPT heads (heads/dpt_block.py, dpt_head.py:36-79, dpt_gs_head.py:121-171, postprocess.py:46-61) --------------------
 def _conv(x, sd, p, **kw):
     return F.conv2d(x, sd[p + ".weight"], sd.get(p + ".bias"), **kw)
@@ -476,4 +516,39 @@ def forward(sd, images, intrinsics, lift=True, stages=None):
     if stages is not None:
         stages.update(enc={i: bb["all_feat"][i] for i in (5, 11, 17, 23)}, dec1=bb["dec1"], dec2=bb["dec2"], adapter=[ms1, ms2], gs_raw=[r1, r2],
                       pts3d=[p1, p2], m2f=aux)
+    return out
+
+
+@torch.no_grad()
+def forward_multi(sd, images, intrinsics, lift=True, stages=None):
+    """SIU3RMultiViewModel.forward (model_multi.py:310-392): head1 / gaussian_param_head1 on view 0, head2 / gaussian_param_head2
+    on every other view (:175-215); adapter per view (:337), Mask2Former over the V frames (:355-359)."""
+    B, V, _, H, W = images.shape
+    bb = backbone_multi(sd, images, intrinsics)
+    gh, gw = bb["gh"], bb["gw"]
+    ms = [adapter(sd, images[:, v], [t[:, v] for t in bb["all_feat"]], gh, gw) for v in range(V)]
+    feats = [torch.stack([ms[v][l] for v in range(V)], dim=1).flatten(0, 1) for l in range(4)]
+    pts, raws = [], []
+    for v in range(V):
+        hn = "1" if v == 0 else "2"
+        dec = [t[:, v] for t in bb["dec"]]
+        pts.append(center_head(sd, "downstream_head" + hn, dec, gh, gw).reshape(B, -1, 3))
+        raws.append(gs_head(sd, "gaussian_param_head" + hn, dec, images[:, v], gh, gw).flatten(2).transpose(1, 2))
+    g = gaussian_adapter(torch.stack(pts, dim=1), torch.stack(raws, dim=1))
+    cls, masks, aux = mask2former(sd, feats, B, T=V)
+    res = post_process(cls, masks, H, W)
+    sem = torch.zeros(B, V, H, W, dtype=torch.int32)
+    inst = torch.zeros(B, V, H, W, dtype=torch.int32)
+    for b, r in enumerate(res):
+        for s in r["segments_info"]:
+            m = r["segmentation"] == s["id"]
+            sem[b][m] = s["label_id"] + 1
+            inst[b][m] = s["id"]
+    out = {k: v.flatten(1, 2) for k, v in g.items()}
+    out.update(class_queries_logits=cls, masks_queries_logits=masks, semantic_labels=sem.flatten(1), instance_labels=inst.flatten(1),
+               seg_masks=[r["segmentation"] for r in res], seg_infos=[r["segments_info"] for r in res],
+               query_scores=[r["query_scores"] for r in res],
+               seg_query_class_logits=[r["query_class_logits"].permute(0, 3, 4, 1, 2).flatten(0, 2) for r in res])
+    if stages is not None:
+        stages.update(enc={i: bb["all_feat"][i] for i in (5, 11, 17, 23)}, dec=bb["dec"], adapter=ms, gs_raw=raws, pts3d=pts, m2f=aux)
     return out

@@ -24,6 +24,7 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 METRIC = "image_pairs_per_s_512x512"
+FLOPS_PER_SAMPLE_512_V4 = 8.657e12  # same source: one 4-view 512^2 sample through SIU3RMultiViewModel
 FLOPS_PER_PAIR_512 = 4.059e12  # algorithmic 2*MAC FLOPs of one 512^2 pair (FlopCounterMode on the reference)
 
 
@@ -36,6 +37,8 @@ def parse():
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--batch", type=int, default=1, help="image pairs per GPU per step")
     ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32x3"])
+    ap.add_argument("--views", type=int, default=2, help="2 = SIU3RModel (headline, BASELINE configs[1]); > 2 = SIU3RMultiViewModel (configs[3])")
+    ap.add_argument("--no-multiview", action="store_true", help="skip the short 4-view (configs[3]) measurement appended at N = 1")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-raster", action="store_true")
     ap.add_argument("--graph", type=int, default=1, help="replay the device part of the forward from a CUDA graph")
@@ -158,17 +161,18 @@ def main():
         return
     import torch.distributed as dist
     from siu3r_b200 import ops, synth
-    from siu3r_b200.model import ModelCfg, SIU3RModel
+    from siu3r_b200.model import ModelCfg, SIU3RModel, SIU3RMultiViewModel
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback exists for the product path)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     S, B = args.size, args.batch
-    model = SIU3RModel(ModelCfg(image_size=(S, S)), precision=args.precision)
+    V = args.views
+    model = (SIU3RModel if V == 2 else SIU3RMultiViewModel)(ModelCfg(image_size=(S, S)), precision=args.precision)
     model.load_state_dict(synth.make_state_dict())
     model.cuda()
-    img_h, K_h = synth.pair_inputs(B, 2, S, seed=rank)
+    img_h, K_h = synth.pair_inputs(B, V, S, seed=rank)
     img_pin, K_pin = img_h.pin_memory(), K_h.pin_memory()
     img_d, K_d = img_pin.to(dev, non_blocking=True), K_pin.to(dev, non_blocking=True)
     if args.graph:
@@ -262,15 +266,35 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "tf32" if args.precision == "tf32" else "3xtf32", "data": "synthetic",
-            "config": {"workload": f"two-view {S}x{S} inference -> Gaussians + panoptic (SIU3RModel.forward), {B} pair(s) per GPU per step",
+            "config": {"workload": (f"two-view {S}x{S} inference -> Gaussians + panoptic (SIU3RModel.forward), {B} pair(s) per GPU per step" if V == 2 else
+                                    f"{V}-view {S}x{S} inference -> Gaussians + panoptic (SIU3RMultiViewModel.forward), {B} sample(s) per GPU per step"),
                        "weights": "seeded random init of the reference architecture (655.5 M params)", "parallelism": f"dp{world}",
                        "cuda_graph": bool(args.graph),
                        "l2": "no explicit flush: weights (2.6 GB) + activations per step exceed the 126 MB L2 many times over"},
             "clocks": clk,
             "e2e": {"value": e2e_v, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
-            "vit_tensor_pipe_frac": value / world * FLOPS_PER_PAIR_512 * (S / 512.0) ** 2 / 1e12 / tf32_peak,
+            "vit_tensor_pipe_frac": value / world * (FLOPS_PER_PAIR_512 if V == 2 else FLOPS_PER_SAMPLE_512_V4 * V / 4) * (S / 512.0) ** 2 / 1e12 / tf32_peak,
             "roofline": roofline}
+
+    # ---- BASELINE configs[3]: 4-view sample through SIU3RMultiViewModel (short, N = 1 only; not the headline) ----
+    if V == 2 and world == 1 and not args.no_multiview:
+        try:
+            del pipe
+            model._graphs = {}
+            mv = SIU3RMultiViewModel(ModelCfg(image_size=(S, S)), precision=args.precision)
+            mv.w, mv.dev, mv._ready = model.w, model.dev, True      # same packed weights (identical state_dict key set)
+            mv.enable_cuda_graph()
+            i4, K4 = synth.pair_inputs(1, 4, S, seed=rank)
+            i4, K4 = i4.to(dev), K4.to(dev)
+            for _ in range(2):
+                mv(i4, K4)
+            ms4 = timed(lambda: mv(i4, K4), 5) / 5
+            line["multiview"] = {"workload": f"4-view {S}x{S} sample (SIU3RMultiViewModel.forward), 1 per step", "samples_per_s": 1e3 / ms4, "ms_per_step": ms4,
+                                 "steps": 5, "tensor_pipe_frac": 1e3 / ms4 * FLOPS_PER_SAMPLE_512_V4 * (S / 512.0) ** 2 / 1e12 / tf32_peak}
+            del mv
+        except Exception as ex:  # never lose the headline line
+            line["multiview"] = {"error": repr(ex)}
 
     # ---- rasterizer sample (BASELINE config 5: 500k pixel-aligned Gaussians @512^2), HBM roofline ----
     if not args.no_raster and rank == 0:
@@ -297,23 +321,30 @@ def raster_bench(dev, peaks):
     view, full, campos, tx, ty = camera_matrices(sc["extrinsics"], sc["intrinsics"], sc["near"], sc["far"])
     a = [sc[k].to(dev) for k in ("means", "covariances", "harmonics", "opacities")]
     cam = [view[0].to(dev), full[0].to(dev), campos[0].to(dev), torch.zeros(3, device=dev)]
-    fn = lambda: ops.raster_forward(a[0], a[1], a[2], a[3], cam[0], cam[1], cam[2], cam[3], float(tx[0]), float(ty[0]), H, W, 4, sh_layout=1)
+    def fn(touched=True):
+        return ops.raster_forward(a[0], a[1], a[2], a[3], cam[0], cam[1], cam[2], cam[3], float(tx[0]), float(ty[0]), H, W, 4, sh_layout=1,
+                                  count_touched=touched)
     r = fn()
     D = r["num_rendered"]
-    for _ in range(3):
-        fn()
-    torch.cuda.synchronize()
-    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n = 20
-    s.record()
-    for _ in range(n):
-        fn()
-    e.record()
-    torch.cuda.synchronize()
-    ms = s.elapsed_time(e) / n
+
+    def run(touched):
+        for _ in range(3):
+            fn(touched)
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(n):
+            fn(touched)
+        e.record()
+        torch.cuda.synchronize()
+        return s.elapsed_time(e) / n
+    ms = run(True)          # full 5-tuple of the reference rasterizer (image, radii, depth, opacity, n_touched)
+    ms_rc = run(False)      # what render_cuda keeps (colour + depth): no n_touched counting
     algo_bytes = 388.0 * G + 68.0 * D + 20.0 * H * W  # preprocess + binning/blend + output
     hbm = peaks.get("hbm_gbs", 6650.0)
-    return {"workload": f"{G} pixel-aligned Gaussians @ {H}x{W}, 1 camera", "fps": 1e3 / ms, "ms": ms, "duplicates": D,
+    return {"workload": f"{G} pixel-aligned Gaussians @ {H}x{W}, 1 camera", "fps": 1e3 / ms, "ms": ms, "fps_render_cuda": 1e3 / ms_rc, "ms_render_cuda": ms_rc,
+            "duplicates": D,
             "roofline": {"bound": "hbm", "achieved": algo_bytes / (ms / 1e3) / 1e9, "peak": hbm, "unit": "GB/s", "frac": algo_bytes / (ms / 1e3) / 1e9 / hbm,
                          "traffic": None, "algorithmic_bytes": algo_bytes}}
 

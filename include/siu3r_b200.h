@@ -44,6 +44,10 @@ int siu3r_raster_forward(int G, int H, int W, int sh_degree, int sh_coeffs, int 
                          uint32_t* debug_offsets, uint64_t* debug_keys, uint32_t* debug_values, uint32_t* debug_ranges,
                          void* stream);
 
+/* testing aid: 0 disables the blend kernel's exact sub-tile culling (every pixel then evaluates every record of its tile, the
+ * literal loop of the reference rasterizer); results must be bit-identical either way (tests/test_ops_gpu.py) */
+void siu3r_raster_set_culling(int enabled);
+
 /* ---- dense contractions on the tcgen05 tensor cores ------------------------------------------------------------
  * siu3r_gemm_tc   : torch.nn.functional.linear (+bias, +GELU/ReLU, +residual): croco/blocks.py:74-77,97,110,154-156,167;
  *                   backbone_croco.py:87; vit_adapter/blocks.py:118-121; every nn.Linear / 1x1 Conv2d of

@@ -2,6 +2,7 @@
 
 Public surface (mirrors the reference):
   siu3r_b200.SIU3RModel        <-> /root/reference/src/models/model.py:31  (forward :314-389)
+  siu3r_b200.SIU3RMultiViewModel <-> /root/reference/src/models/model_multi.py:28 (forward :310-392; V >= 2 context views)
   siu3r_b200.SplattingCUDA     <-> /root/reference/src/models/gaussian_renderer.py:15 (forward :29-116)
   siu3r_b200.render_cuda       <-> /root/reference/src/models/cuda_splatting.py:46-122
   siu3r_b200.Gaussians         <-> /root/reference/src/utils/gaussians_types.py:4-38
@@ -11,7 +12,7 @@ from .gaussians import Gaussians  # noqa: F401
 
 
 def __getattr__(name):
-    if name in ("SIU3RModel", "ModelCfg"):
+    if name in ("SIU3RModel", "SIU3RMultiViewModel", "ModelCfg"):
         from . import model as _m
         return getattr(_m, name)
     if name in ("SplattingCUDA", "render_cuda"):

@@ -304,49 +304,98 @@ __global__ void __launch_bounds__(256) identify_tile_ranges_kernel(uint32_t D, c
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Blend: one CTA (16x16 threads) per tile, front-to-back over the tile's sorted list in batches of 256 records that
-// are staged once in shared memory (id, xy, conic+opacity, rgb+depth = 44 B) and then broadcast-read by all pixels.
+// Blend: one CTA (256 threads) per 16x16 tile, front-to-back over the tile's sorted list in batches of 256 records that
+// are staged once in shared memory (id, xy, conic+opacity, rgb+depth = 44 B) and then broadcast-read by the pixels.
+//
+// Sub-tile culling.  A warp owns an 8x4 pixel block of the tile.  A record can only change a pixel where
+//     power = -(a dx^2 + c dy^2)/2 - b dx dy  satisfies  power <= 0  and  o * exp(power) >= 1/255,
+// i.e. inside the ellipse  q(d) <= tau = ln(255 o).  The staging thread turns that into a conservative bounding box
+// (half extents sqrt(2 tau Sigma_xx), sqrt(2 tau Sigma_yy) with Sigma = conic^-1, widened by 0.02 in tau, 0.1 % and
+// 0.01 px against rounding of the per-pixel arithmetic and of ex2.approx); every warp then compacts, in list order, the
+// records whose box meets its block and blends only those.  Skipped records would have taken the `power > 0` or
+// `alpha < 1/255` exit at all 32 pixels, so colour, depth, opacity and n_touched are bit-identical to the unculled loop,
+// while a pixel-aligned splat (1-3 px) is evaluated by 1-3 warps instead of 8.
 // ---------------------------------------------------------------------------------------------------------------
+constexpr int RB = TILE_X * TILE_Y;   // records per batch = threads per CTA
+constexpr int SUB_W = 8, SUB_H = 4;   // pixel block of one warp
+
 template <bool COUNT_TOUCHED>
-__global__ void __launch_bounds__(TILE_X* TILE_Y) render_kernel(int W, int H, int gx, const uint2* __restrict__ ranges,
-                                                              const uint32_t* __restrict__ point_list, const float2* __restrict__ xy,
-                                                              const float4* __restrict__ conic_o, const float* __restrict__ rgb,
-                                                              const float* __restrict__ depths, const float* __restrict__ cam_dev,
-                                                              float* __restrict__ out_color, float* __restrict__ out_depth,
-                                                              float* __restrict__ out_opacity, int32_t* __restrict__ n_touched) {
-    constexpr int BS = TILE_X * TILE_Y;
-    __shared__ uint32_t s_id[BS];
-    __shared__ float2 s_xy[BS];
-    __shared__ float4 s_co[BS];
-    __shared__ float4 s_rgbd[BS];
-    __shared__ int s_cnt[COUNT_TOUCHED ? BS : 1];
+__global__ void __launch_bounds__(RB) render_kernel(int W, int H, int gx, const uint2* __restrict__ ranges,
+                                                    const uint32_t* __restrict__ point_list, const float2* __restrict__ xy,
+                                                    const float4* __restrict__ conic_o, const float* __restrict__ rgb,
+                                                    const float* __restrict__ depths, const float* __restrict__ cam_dev,
+                                                    float* __restrict__ out_color, float* __restrict__ out_depth,
+                                                    float* __restrict__ out_opacity, int32_t* __restrict__ n_touched, int cull) {
+    __shared__ uint32_t s_id[RB];
+    __shared__ float2 s_xy[RB];
+    __shared__ float4 s_co[RB];
+    __shared__ float4 s_rgbd[RB];
+    __shared__ float4 s_box[RB];                 // xmin, xmax, ymin, ymax of the contributing region
+    __shared__ uint8_t s_list[RB / 32][RB];      // per warp: batch slots that meet its pixel block, in list order
+    __shared__ int s_cnt[COUNT_TOUCHED ? RB : 1];
 
     const int tile_x = blockIdx.x, tile_y = blockIdx.y;
-    const int tid = threadIdx.y * TILE_X + threadIdx.x;
-    const int pxi = tile_x * TILE_X + threadIdx.x, pyi = tile_y * TILE_Y + threadIdx.y;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int bx0 = tile_x * TILE_X + (warp & 1) * SUB_W, by0 = tile_y * TILE_Y + (warp >> 1) * SUB_H;
+    const int pxi = bx0 + (lane & 7), pyi = by0 + (lane >> 3);
     const bool inside = pxi < W && pyi < H;
     const float pfx = (float)pxi, pfy = (float)pyi;
+    const float wx0 = (float)bx0, wx1 = (float)(bx0 + SUB_W - 1), wy0 = (float)by0, wy1 = (float)(by0 + SUB_H - 1);
     const uint2 range = ranges[tile_y * gx + tile_x];
-    const int rounds = (int)((range.y - range.x + BS - 1) / BS);
+    const int rounds = (int)((range.y - range.x + RB - 1) / RB);
     int todo = (int)(range.y - range.x);
     bool done = !inside;
     float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, Dz = 0.f;
+    uint8_t* my_list = s_list[warp];
 
-    for (int r = 0; r < rounds; ++r, todo -= BS) {
+    for (int r = 0; r < rounds; ++r, todo -= RB) {
         const int num_done = __syncthreads_count(done);
-        if (num_done == BS) break;
-        const uint32_t progress = range.x + (uint32_t)r * BS + tid;
+        if (num_done == RB) break;
+        const uint32_t progress = range.x + (uint32_t)r * RB + tid;
         if (progress < range.y) {
             const uint32_t id = point_list[progress];
+            const float2 p = xy[id];
+            const float4 co = conic_o[id];
             s_id[tid] = id;
-            s_xy[tid] = xy[id];
-            s_co[tid] = conic_o[id];
+            s_xy[tid] = p;
+            s_co[tid] = co;
             s_rgbd[tid] = make_float4(rgb[3 * (size_t)id], rgb[3 * (size_t)id + 1], rgb[3 * (size_t)id + 2], depths[id]);
+            const float det = co.x * co.z - co.y * co.y;
+            float ex = INFINITY, ey = INFINITY;   // not a proper ellipse: never cull
+            if (cull && det > 0.0f && co.x > 0.0f && co.z > 0.0f && co.w == co.w) {   // NaN opacity: fminf(0.99, NaN) blends -> keep
+                const float tau = __logf(255.0f * co.w) + 0.02f;
+                if (tau < 0.0f || !(co.w > 0.0f)) {
+                    ex = ey = -INFINITY;          // o < 1/255: alpha can never reach 1/255 -> empty box
+                } else {
+                    const float inv = 1.0f / det;
+                    ex = sqrtf(2.0f * tau * co.z * inv) * 1.001f + 0.01f;
+                    ey = sqrtf(2.0f * tau * co.x * inv) * 1.001f + 0.01f;
+                }
+            }
+            s_box[tid] = make_float4(p.x - ex, p.x + ex, p.y - ey, p.y + ey);
         }
         if (COUNT_TOUCHED) s_cnt[tid] = 0;
         __syncthreads();
-        const int nb = min(BS, todo);
-        for (int j = 0; j < nb; ++j) {
+        const int nb = min(RB, todo);
+        // ---- per-warp compaction of the batch (order preserving) ----
+        int nl = 0;
+        if (!__all_sync(0xffffffffu, done)) {
+#pragma unroll
+            for (int k = 0; k < RB / 32; ++k) {
+                const int j = k * 32 + lane;
+                bool hit = false;
+                if (j < nb) {
+                    const float4 b = s_box[j];
+                    hit = b.y >= wx0 && b.x <= wx1 && b.w >= wy0 && b.z <= wy1;
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, hit);
+                if (hit) my_list[nl + __popc(m & ((1u << lane) - 1u))] = (uint8_t)j;
+                nl += __popc(m);
+            }
+            __syncwarp();
+        }
+        for (int i = 0; i < nl; ++i) {
+            const int j = my_list[i];
             bool touch = false;
             if (!done) {
                 const float2 p = s_xy[j];
@@ -374,7 +423,7 @@ __global__ void __launch_bounds__(TILE_X* TILE_Y) render_kernel(int W, int H, in
             }
             if (COUNT_TOUCHED) {
                 const unsigned m = __ballot_sync(0xffffffffu, touch);
-                if (m != 0 && (tid & 31) == 0) atomicAdd(&s_cnt[j], __popc(m));
+                if (m != 0 && lane == 0) atomicAdd(&s_cnt[j], __popc(m));
             }
         }
         if (COUNT_TOUCHED) {
@@ -454,9 +503,13 @@ Workspace carve(void* base, int G, int H, int W, int64_t cap) {
     return w;
 }
 
+int g_cull = 1;   // testing aid: 0 blends every record of the tile at every pixel (the unculled reference loop)
+
 }  // namespace
 
 extern "C" {
+
+void siu3r_raster_set_culling(int enabled) { g_cull = enabled ? 1 : 0; }
 
 // Bytes of device scratch siu3r_raster_forward needs for G Gaussians, an HxW image and at most `dup_capacity`
 // (tile, Gaussian) duplicates.  Mirrors the resize-callback buffers of the reference rasterizer (geomBuffer,
@@ -539,13 +592,13 @@ int siu3r_raster_forward(int G, int H, int W, int sh_degree, int sh_coeffs, int 
         SIU3R_LAUNCH_CHECK();
         siu3r_note_launch(2);
     }
-    dim3 grid(gx, gy), block(TILE_X, TILE_Y);
+    dim3 grid(gx, gy), block(RB);
     if (n_touched)
         render_kernel<true><<<grid, block, 0, stream>>>(W, H, gx, w.ranges, sorted_vals, w.xy, w.conic_o, w.rgb, w.depths, w.cam,
-                                                        out_color, out_depth, out_opacity, n_touched);
+                                                        out_color, out_depth, out_opacity, n_touched, g_cull);
     else
         render_kernel<false><<<grid, block, 0, stream>>>(W, H, gx, w.ranges, sorted_vals, w.xy, w.conic_o, w.rgb, w.depths, w.cam,
-                                                         out_color, out_depth, out_opacity, nullptr);
+                                                         out_color, out_depth, out_opacity, nullptr, g_cull);
     SIU3R_LAUNCH_CHECK();
     siu3r_note_launch(1);
     if (D > 0) {

@@ -196,8 +196,8 @@ class SIU3RModel:
         self._ready = True
 
     # ---- shape-dependent constants (host-built once per image size) -------------------------------------------------
-    def _consts(self, B: int, S0: int, S1: int):
-        key = (B, S0, S1)
+    def _consts(self, B: int, S0: int, S1: int, V: int = 2):
+        key = (B, S0, S1, V)
         if key in self._cache:
             return self._cache[key]
         gh, gw = S0 // 16, S1 // 16
@@ -205,7 +205,7 @@ class SIU3RModel:
         pos = torch.stack([ys.flatten(), xs.flatten()], -1)
         pos = torch.cat([pos, torch.tensor([[gh, 0]])], 0)  # intrinsics token at (y_last + 1, 0): backbone_croco.py:148-150
         k = SimpleNamespace()
-        k.pos_enc = pos[None].repeat(2 * B, 1, 1).contiguous().to(self.dev)
+        k.pos_enc = pos[None].repeat(V * B, 1, 1).contiguous().to(self.dev)
         k.pos_dec = pos[None].repeat(B, 1, 1).contiguous().to(self.dev)
         k.rope_tab = ops.rope2d_table(int(pos.max()) + 1, 64, 100.0, 1.0, self.dev)   # RoPE factors for the fused projection epilogues
         ad_shapes = [(S0 // 8, S1 // 8), (S0 // 16, S1 // 16), (S0 // 32, S1 // 32)]
@@ -215,8 +215,8 @@ class SIU3RModel:
         k.m2f_shapes = lv
         k.m2f_ref = reference_points(lv).to(self.dev)
         pe = torch.cat([sine_pos_2d(h, w) + m.pd_level_embed[i][None] for i, (h, w) in enumerate(lv)], 0)
-        k.m2f_pos = pe[None].repeat(2 * B, 1, 1).reshape(-1, 256).contiguous().to(self.dev)
-        k.tm_pos = [sine_pos_3d(2, h, w)[None].repeat(B, 1, 1).reshape(-1, 256).contiguous().to(self.dev) for (h, w) in lv]
+        k.m2f_pos = pe[None].repeat(V * B, 1, 1).reshape(-1, 256).contiguous().to(self.dev)
+        k.tm_pos = [sine_pos_3d(V, h, w)[None].repeat(B, 1, 1).reshape(-1, 256).contiguous().to(self.dev) for (h, w) in lv]
         k.tm_lvl = [m.tm_level_embed[i].contiguous().to(self.dev) for i in range(3)]
         k.hidden0 = m.q_feat[None].repeat(B, 1, 1).view(-1, 256).contiguous()
         k.qpos = m.q_pos[None].repeat(B, 1, 1).view(-1, 256).contiguous()
@@ -372,7 +372,8 @@ class SIU3RModel:
         p1 = self._fusion(hw.refine[0], p2, layers[0], ro=True)  # path_1 only feeds a conv (centre head) or a resize (GS head)
         return p1
 
-    def _center_head(self, hw, toks, B, N, gh, gw, means_out, v):
+    def _center_head(self, hw, toks, B, N, gh, gw, dst):
+        """dst[i]: [S0*S1, 3] slice of Gaussians.means that receives the pts3d of batch entry i."""
         p1 = self._dpt_trunk(hw, toks, B, N, gh, gw)
         x = self._conv(p1, hw.head0, 3, ar=True, pad=1)
         n, h, w_, c = x.shape
@@ -382,7 +383,7 @@ class SIU3RModel:
         xyz = torch.empty(B * S0 * S1, 4, device=self.dev)
         self._lin(x.view(-1, x.shape[-1]), hw.head4, ar=True, out=xyz[:, :3])
         for b in range(B):  # pts3d written straight into Gaussians.means[b, v]
-            ops._lib.check(ops._lib.load().siu3r_depth_exp(xyz[b * S0 * S1:].data_ptr(), 4, means_out[b, v].data_ptr(), S0 * S1, ops._stream()),
+            ops._lib.check(ops._lib.load().siu3r_depth_exp(xyz[b * S0 * S1:].data_ptr(), 4, dst[b].data_ptr(), S0 * S1, ops._stream()),
                            "depth_exp")
 
     def _gs_head(self, hw, toks, img4, B, N, gh, gw):
@@ -433,12 +434,12 @@ class SIU3RModel:
         c1 = self._conv(c1, a.fc1, 1, ar=True)                             # [Bn, S/4, S/4, 1024]
         return c1, c2, c3, c4
 
-    def _adapter(self, img4, feats, k, B, N, gh, gw, out_slots):
-        """img4 [2B,S0,S1,4] view-major (image j = v*B + b); feats: {block idx: [2B*N, 1024]} -> f1..f4 of every image into
-        out_slots[l][b*2+v].  Both views go through every kernel as one batch."""
+    def _adapter(self, img4, feats, k, B, N, gh, gw, out_slots, V=2):
+        """img4 [V*B,S0,S1,4] view-major (image j = v*B + b); feats: {block idx: [V*B*N, 1024]} -> f1..f4 of every image into
+        out_slots[l][b*V+v].  All views go through every kernel as one batch."""
         a = self.w.adapter
         P = gh * gw
-        Bn = 2 * B
+        Bn = V * B
         c1, c2, c3, c4 = self._adapter_stem(img4)
         n2, n3, n4 = 4 * P, P, P // 4
         Lq = n2 + n3 + n4
@@ -480,14 +481,14 @@ class SIU3RModel:
                     ops.resize_bilinear(xb, scale_hw[0], scale_hw[1], False, out=maps[l][j:j + 1], accumulate=True)
                 sc, sh = a.bn[l]
                 rows = scale_hw[0] * scale_hw[1]
-                ops.rows_affine(maps[l][j].view(rows, 1024), scale=sc, shift=sh, out=out_slots[l][b * 2 + v].view(rows, 1024))
+                ops.rows_affine(maps[l][j].view(rows, 1024), scale=sc, shift=sh, out=out_slots[l][b * V + v].view(rows, 1024))
 
     # ---- Mask2Former (mask2former/video_seg_decoder.py:2072-2196, 1506-1575, 1204-1360) ---------------------------------
-    def _m2f(self, feats, k, B, S0, S1):
+    def _m2f(self, feats, k, B, S0, S1, T=2):
         """feats: 4 maps [B*T, h, w, 1024] at strides 4/8/16/32 (frame index bt = b*T + t).  Returns class logits [B,100,21],
         mask logits pixel-major [B*T, S0/4, S1/4, 100]."""
         m = self.w.m2f
-        T, E, Q = 2, 256, self.cfg.num_queries
+        E, Q = 256, self.cfg.num_queries
         BT = B * T
         lv = k.m2f_shapes
         Ltot = sum(h * w for h, w in lv)
@@ -588,9 +589,9 @@ class SIU3RModel:
         return cls.view(B, Q, -1), logits.view(B * T, h4, w4, Q)
 
     # ---- panoptic post-process (image_processing_video_mask2former.py:1238-1481, model.py:231-312) ------------------------
-    def _post_process(self, cls_logits, mask_logits, B, S0, S1, lift):
+    def _post_process(self, cls_logits, mask_logits, B, S0, S1, lift, T=2):
         cfg = self.cfg
-        T, Q = 2, cfg.num_queries
+        Q = cfg.num_queries
         num_labels = cls_logits.shape[-1] - 1
         h4, w4 = mask_logits.shape[1], mask_logits.shape[2]
         probs256 = ops.eltwise(ELT_SIGMOID, ops.resize_bilinear(mask_logits, 256, 256, False))  # [B*T,256,256,Q] (:1298-1312)
@@ -668,17 +669,63 @@ class SIU3RModel:
     def disable_cuda_graph(self):
         self._use_graph = False
 
+    def _dec_block_multi(self, blk, x, f_all, qviews, pos, B, N, V, out):
+        """DecoderBlock of the V-view decoder (backbone_croco.py:487-535).  x: rows of the query views `qviews` (view-major,
+        len(qviews)*B*N rows); f_all: previous-layer tokens of all V views [V*B*N, C].  The cross-attention memory of query
+        view i is the concatenation, in view order, of norm_y(tokens) of every view j != i (generate_ctx_views :500-506), each
+        key rotated with its own positions.  norm_y + the k|v projection are per token, so they run once per needed view and
+        the per-query-view memories are assembled by row copies."""
+        C, nh = 768, 12
+        nq = len(qviews)
+        Bq = nq * B
+        pos_q = pos[:Bq]
+        h = self._ln(x, blk.n1, 1e-6)
+        a = self._self_attn(h, blk, pos_q, Bq, N, C, nh)
+        x1 = self._lin(a, blk.proj, ar=True, residual=x, out=out)   # `out`: this branch's rows of the next layer's token buffer
+        need = [j for j in range(V) if any(j != i for i in qviews)]
+        lo, hi = need[0], need[-1] + 1   # contiguous view range (view 0 alone needs 1..V-1, views 1..V-1 need all)
+        yn = self._ln(f_all[lo * B * N: hi * B * N], blk.ny, 1e-6)
+        kv = self._lin(yn, blk.ckv, ar=True, ro=True, rope=(pos[:(hi - lo) * B], self._k.rope_tab, C))   # [(hi-lo)*B*N, 2C]
+        Nk = (V - 1) * N
+        if nq == 1 and B == 1:
+            ctx = kv       # views 1..V-1 of the single sample are already contiguous and in order
+        else:
+            ctx = torch.empty(Bq, Nk, 2 * C, device=self.dev)
+            for qi, i in enumerate(qviews):
+                for b in range(B):
+                    slot = 0
+                    for j in range(V):
+                        if j == i:
+                            continue
+                        r0 = ((j - lo) * B + b) * N
+                        ops.rows_affine(kv[r0:r0 + N], out=ctx[qi * B + b, slot * N:(slot + 1) * N])
+                        slot += 1
+        h2 = self._ln(x1, blk.n2, 1e-6)
+        q = self._lin(h2, blk.cq, ar=True, ro=True, rope=(pos_q, self._k.rope_tab, C))
+        a2 = torch.empty(Bq * N, C, device=self.dev)
+        if self.R:
+            ops.flash_attn_tc(q, 0, N * C, C, C, ctx, 0, Nk * 2 * C, 2 * C, 2 * C, ctx, C, Nk * 2 * C, 2 * C, a2, Bq, nh, N, Nk, 0.125, round_out=True)
+        else:
+            ops.flash_attn_d64(q, 0, N * C, C, ctx, 0, Nk * 2 * C, 2 * C, ctx, C, Nk * 2 * C, 2 * C, a2, Bq, nh, N, Nk, 0.125, self.prec)
+        self._lin(a2, blk.cproj, ar=True, residual=x1, out=x1)
+        h3 = self._ln(x1, blk.n3, 1e-6)
+        f = self._lin(h3, blk.fc1, ar=True, ro=True, act=ACT_GELU)
+        self._lin(f, blk.fc2, ar=True, residual=x1, out=x1)
+        return x1
+
     def _forward_device(self, imgs, Kin):
-        """All device work of SIU3RModel.forward up to (and excluding) the host-assisted panoptic post-process."""
+        """All device work of SIU3RModel.forward / SIU3RMultiViewModel.forward up to (and excluding) the host-assisted panoptic
+        post-process.  Images are batched view-major (image j = v*B + b) in both models."""
         B, V, _, S0, S1 = imgs.shape
         w, c = self.w, self.cfg
-        k = self._k = self._consts(B, S0, S1)
+        multi = self.multiview
+        k = self._k = self._consts(B, S0, S1, V)
         gh, gw = S0 // 16, S1 // 16
         P, N = gh * gw, gh * gw + 1
-        Bn = 2 * B
+        Bn = V * B
         img4 = torch.zeros(Bn, S0, S1, 4, device=self.dev)  # view-major NHWC, 4th channel = 0
         lib = ops._lib.load()
-        for v in range(2):
+        for v in range(V):
             for b in range(B):
                 ops._lib.check(lib.siu3r_nchw_to_nhwc(imgs[b, v].data_ptr(), img4[v * B + b].data_ptr(), 1, 3, S0 * S1, 4, ops._stream()), "nchw_to_nhwc")
         # ---- encoder input: patch tokens + intrinsics token ----
@@ -689,8 +736,8 @@ class SIU3RModel:
         for i in range(Bn):
             self._lin(cols[i * P:(i + 1) * P], w.patch, ar=True, out=x[i, :P])
         x = x.view(Bn * N, 1024)
-        Kflat = Kin.view(B, 18)
-        for v in range(2):  # intrinsics token = Linear(9 -> 1024) on the flattened K (backbone_croco.py:278-280)
+        Kflat = Kin.view(B, 9 * V)
+        for v in range(V):  # intrinsics token = Linear(9 -> 1024) on the flattened K (backbone_croco.py:278-280, :546-549)
             ops.gemm_simt(Kflat[:, 9 * v: 9 * v + 9], w.intr_w, w.intr_b, out=x[v * B * N + P:: N][:B])
         # DAG: the panoptic chain (adapter -> Mask2Former) only needs the image and the four kept encoder outputs, so it runs
         # on its own stream next to the rest of the encoder, the decoder and the Gaussian heads (one graph branch when captured).
@@ -706,13 +753,13 @@ class SIU3RModel:
         x, keep = self._encoder(x, k.pos_enc, Bn, N)
         self._mark("encoder")
         shapes = [(S0 // 4, S1 // 4), (S0 // 8, S1 // 8), (S0 // 16, S1 // 16), (S0 // 32, S1 // 32)]
-        ms = [torch.empty(B * 2, h, w_, 1024, device=self.dev) for (h, w_) in shapes]
+        ms = [torch.empty(B * V, h, w_, 1024, device=self.dev) for (h, w_) in shapes]
 
         def seg_chain():
-            self._adapter(img4, keep, k, B, N, gh, gw, ms)
+            self._adapter(img4, keep, k, B, N, gh, gw, ms, V)
             self._cap("adapter_ms", ms)
             self._mark("adapter")
-            r = self._m2f(ms, k, B, S0, S1)
+            r = self._m2f(ms, k, B, S0, S1, V)
             self._mark("m2f")
             return r
 
@@ -720,45 +767,66 @@ class SIU3RModel:
             self._seg_stream.wait_event(fork)
             with torch.cuda.stream(self._seg_stream):
                 cls_logits, mask_logits = seg_chain()
-        feat = ops.layernorm(x, w.enc_norm[0], w.enc_norm[1], 1e-6)  # [2B*N, 1024]
+        feat = ops.layernorm(x, w.enc_norm[0], w.enc_norm[1], 1e-6)  # [V*B*N, 1024]
         self._cap("enc_norm", feat)
         # ---- decoder ----
-        f = self._lin(feat, w.dec_embed)  # [2B*N, 768]
-        f1, f2 = f[:B * N], f[B * N:]
-        dec1, dec2 = [feat[:B * N]], [feat[B * N:]]
-        for l in range(c.dec_depth):
-            # the two views use different weights and only read the previous layer's pair: two parallel branches
-            n1, n2 = self._par([lambda: self._dec_block(w.dec[0][l], f1, f2, k.pos_dec, B, N),
-                                lambda: self._dec_block(w.dec[1][l], f2, f1, k.pos_dec, B, N)])
-            f1, f2 = n1, n2
-            dec1.append(f1)
-            dec2.append(f2)
-            self._cap(f"dec1_{l}", f1)
-            self._cap(f"dec2_{l}", f2)
-        dec1[-1] = ops.layernorm(dec1[-1], w.dec_norm[0], w.dec_norm[1], 1e-6)
-        dec2[-1] = ops.layernorm(dec2[-1], w.dec_norm[0], w.dec_norm[1], 1e-6)
+        f = self._lin(feat, w.dec_embed)  # [V*B*N, 768]
+        if not multi:
+            f1, f2 = f[:B * N], f[B * N:]
+            dec1, dec2 = [feat[:B * N]], [feat[B * N:]]
+            for l in range(c.dec_depth):
+                # the two views use different weights and only read the previous layer's pair: two parallel branches
+                n1, n2 = self._par([lambda: self._dec_block(w.dec[0][l], f1, f2, k.pos_dec, B, N),
+                                    lambda: self._dec_block(w.dec[1][l], f2, f1, k.pos_dec, B, N)])
+                f1, f2 = n1, n2
+                dec1.append(f1)
+                dec2.append(f2)
+                self._cap(f"dec1_{l}", f1)
+                self._cap(f"dec2_{l}", f2)
+            dec1[-1] = ops.layernorm(dec1[-1], w.dec_norm[0], w.dec_norm[1], 1e-6)
+            dec2[-1] = ops.layernorm(dec2[-1], w.dec_norm[0], w.dec_norm[1], 1e-6)
+            dec_first, dec_rest = dec1, dec2
+        else:
+            # V-view decoder: view 0 through dec_blocks, views 1..V-1 (one batch) through dec_blocks2; both read the previous
+            # layer's tokens of all views, so every layer writes into a fresh [V*B*N, 768] buffer
+            decs = [feat]
+            rest = list(range(1, V))
+            for l in range(c.dec_depth):
+                nxt = torch.empty(Bn * N, 768, device=self.dev)
+                fa = f
+                self._par([lambda: self._dec_block_multi(w.dec[0][l], fa[:B * N], fa, [0], k.pos_enc, B, N, V, nxt[:B * N]),
+                           lambda: self._dec_block_multi(w.dec[1][l], fa[B * N:], fa, rest, k.pos_enc, B, N, V, nxt[B * N:])])
+                f = nxt
+                decs.append(f)
+                self._cap(f"dec1_{l}", f[:B * N])
+                self._cap(f"dec2_{l}", f[B * N:])
+            decs[-1] = ops.layernorm(decs[-1], w.dec_norm[0], w.dec_norm[1], 1e-6)
+            dec_first, dec_rest = [t[:B * N] for t in decs], [t[B * N:] for t in decs]
         self._mark("decoder")
-        # ---- the four DPT heads: independent branches ----
+        # ---- DPT heads: head1 on view 0, head2 on the other views (one batch); independent branches ----
         G1 = S0 * S1
-        means = torch.empty(B, 2, G1, 3, device=self.dev)
+        means = torch.empty(B, V, G1, 3, device=self.dev)
         hooks = [0, c.dec_depth * 2 // 4, c.dec_depth * 3 // 4, c.dec_depth]
-        toks = [[dec1[hk] for hk in hooks], [dec2[hk] for hk in hooks]]
-        branches = []
-        for v in range(2):
-            branches.append(lambda v=v: self._center_head(w.heads[f"downstream_head{v + 1}"], toks[v], B, N, gh, gw, means, v))
-            branches.append(lambda v=v: self._gs_head(w.heads[f"gaussian_param_head{v + 1}"], toks[v], img4[v * B:(v + 1) * B], B, N, gh, gw))
+        toks = [[dec_first[hk] for hk in hooks], [dec_rest[hk] for hk in hooks]]
+        Br = (V - 1) * B
+        dst = [[means[b, 0] for b in range(B)], [means[b, v] for v in range(1, V) for b in range(B)]]
+        branches = [lambda: self._center_head(w.heads["downstream_head1"], toks[0], B, N, gh, gw, dst[0]),
+                    lambda: self._gs_head(w.heads["gaussian_param_head1"], toks[0], img4[:B], B, N, gh, gw),
+                    lambda: self._center_head(w.heads["downstream_head2"], toks[1], Br, N, gh, gw, dst[1]),
+                    lambda: self._gs_head(w.heads["gaussian_param_head2"], toks[1], img4[B:], Br, N, gh, gw)]
         res = self._par(branches)
-        raws = [res[1], res[3]]
+        raws = [res[1], res[3]]     # [B, G1, 83] (view 0), [(V-1)*B, G1, 83] (views 1.., view-major)
         self._cap("gs_raw", raws)
-        cov = torch.empty(B, 2 * G1, 3, 3, device=self.dev)
-        harm = torch.empty(B, 2 * G1, 3, 25, device=self.dev)
-        opac = torch.empty(B, 2 * G1, device=self.dev)
-        scales = torch.empty(B, 2 * G1, 3, device=self.dev)
-        rots = torch.empty(B, 2 * G1, 4, device=self.dev)
-        for v in range(2):
+        cov = torch.empty(B, V * G1, 3, 3, device=self.dev)
+        harm = torch.empty(B, V * G1, 3, 25, device=self.dev)
+        opac = torch.empty(B, V * G1, device=self.dev)
+        scales = torch.empty(B, V * G1, 3, device=self.dev)
+        rots = torch.empty(B, V * G1, 4, device=self.dev)
+        for v in range(V):
             for b in range(B):
                 o = v * G1
-                ops._lib.check(lib.siu3r_gaussian_adapter(raws[v][b].data_ptr(), G1, cov[b, o:].data_ptr(), harm[b, o:].data_ptr(), opac[b, o:].data_ptr(),
+                raw = raws[0][b] if v == 0 else raws[1][(v - 1) * B + b]
+                ops._lib.check(lib.siu3r_gaussian_adapter(raw.data_ptr(), G1, cov[b, o:].data_ptr(), harm[b, o:].data_ptr(), opac[b, o:].data_ptr(),
                                                           scales[b, o:].data_ptr(), rots[b, o:].data_ptr(), ops._stream()), "gaussian_adapter")
         self._mark("heads")
         if serial:
@@ -766,7 +834,9 @@ class SIU3RModel:
         else:
             main.wait_stream(self._seg_stream)
         self._mark("end")
-        return means.view(B, 2 * G1, 3), cov, harm, opac, scales, rots, cls_logits, mask_logits
+        return means.view(B, V * G1, 3), cov, harm, opac, scales, rots, cls_logits, mask_logits
+
+    multiview = False   # SIU3RMultiViewModel sets True
 
     @torch.no_grad()
     def forward(self, context_views_images, context_views_intrinsics, mask_labels=None, class_labels=None, enable_query_class_logit_lift=False):
@@ -774,14 +844,17 @@ class SIU3RModel:
         assert mask_labels is None and class_labels is None, "training losses are out of scope (SURVEY.md section 8)"
         imgs = context_views_images
         B, V, _, S0, S1 = imgs.shape
-        assert V == 2, "two-view path; the V-view model is SIU3RMultiViewModel (next)"
+        if self.multiview:
+            assert V >= 2, "SIU3RMultiViewModel needs at least two context views"
+        else:
+            assert V == 2, "two-view path; the V-view model is SIU3RMultiViewModel"
         assert S0 % 16 == 0 and S1 % 16 == 0, f"Input image size ({S0}x{S1}) is not a multiple of patch size (16)."
         assert (S0, S1) == tuple(self.cfg.image_size), "model was built for a different image_size (vit_adapter.py:328-329)"
         if getattr(self, "_use_graph", False) and self.capture is None:
-            key = (B, S0, S1)
+            key = (B, V, S0, S1)
             if key not in self._graphs:
-                si = torch.empty(B, 2, 3, S0, S1, device=self.dev)
-                sk = torch.empty(B, 2, 3, 3, device=self.dev)
+                si = torch.empty(B, V, 3, S0, S1, device=self.dev)
+                sk = torch.empty(B, V, 3, 3, device=self.dev)
                 si.copy_(imgs)
                 sk.copy_(context_views_intrinsics)
                 side = torch.cuda.Stream()
@@ -808,11 +881,18 @@ class SIU3RModel:
         gaussians = Gaussians(means=means, covariances=cov, harmonics=harm, opacities=opac, scales=scales, rotations=rots)
         h4, w4 = S0 // 4, S1 // 4
         seg_output = SimpleNamespace(class_queries_logits=cls_logits,
-                                     masks_queries_logits=mask_logits.view(B, 2, h4, w4, -1).permute(0, 4, 1, 2, 3))
-        seg_masks, seg_infos, qc_list, qscores, sem, inst = self._post_process(cls_logits, mask_logits, B, S0, S1, enable_query_class_logit_lift)
+                                     masks_queries_logits=mask_logits.view(B, V, h4, w4, -1).permute(0, 4, 1, 2, 3))
+        seg_masks, seg_infos, qc_list, qscores, sem, inst = self._post_process(cls_logits, mask_logits, B, S0, S1, enable_query_class_logit_lift, V)
         gaussians.semantic_labels = sem
         gaussians.instance_labels = inst
         if enable_query_class_logit_lift:
             gaussians.seg_query_class_logits = qc_list
             return gaussians, seg_output, seg_masks, seg_infos, qscores
         return gaussians, seg_output, seg_masks, seg_infos
+
+
+class SIU3RMultiViewModel(SIU3RModel):
+    """V-view model (src/models/model_multi.py:28-392, backbone AsymmetricCroCoMulti backbone_croco.py:350-590): same weights
+    and state_dict keys as SIU3RModel; view 0 is the reference view (dec_blocks / head1 / gaussian_param_head1), every other
+    view goes through dec_blocks2 / head2 / gaussian_param_head2 and cross-attends to the V-1 other views."""
+    multiview = True

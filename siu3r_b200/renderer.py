@@ -80,7 +80,8 @@ def render_cuda(extrinsics, intrinsics, near, far, image_shape, background_color
         gi = i if gaussian_means.shape[0] == b else 0
         res = ops.raster_forward(gaussian_means[gi].contiguous(), gaussian_covariances[gi].contiguous(), gaussian_sh_coefficients[gi].contiguous(),
                                  gaussian_opacities[gi].contiguous(), cam[i, 0:16], cam[i, 16:32], cam[i, 32:35], cam[i, 35:38], float(tan_x[i]),
-                                 float(tan_y[i]), h, w, degree, sh_layout=1)
+                                 float(tan_y[i]), h, w, degree, sh_layout=1,
+                                 count_touched=return_aux)   # the reference discards n_touched / radii / opacity here (cuda_splatting.py:109,122)
         colors.append(res["color"])
         depths.append(res["depth"])
         aux.append(res)

@@ -513,3 +513,19 @@ def test_raster_properties_large():
     res2 = ops.raster_forward(sc["means"].to(DEV), sc["covariances"].to(DEV), sc["harmonics"].to(DEV), sc["opacities"].to(DEV), view.to(DEV),
                               full.to(DEV), campos.to(DEV), bg, tx, ty, H, W, 4, sh_layout=1)
     assert torch.equal(res2["color"], res["color"]) and torch.equal(res2["depth"], res["depth"])
+    # exact sub-tile culling: bit-identical to the unculled per-pixel loop (colour, depth, opacity, n_touched)
+    from siu3r_b200 import _lib
+    lib = _lib.load()
+    for pa in (True, False):
+        sc, view, full, campos, tx, ty = _raster_case(G // 4 if not pa else G, H, W, 11, pa)
+        sc["opacities"][::7] *= 1e-3        # some records below the 1/255 floor
+        args = (sc["means"].to(DEV), sc["covariances"].to(DEV), sc["harmonics"].to(DEV), sc["opacities"].to(DEV), view.to(DEV), full.to(DEV),
+                campos.to(DEV), bg, tx, ty, H, W, 4)
+        a = ops.raster_forward(*args, sh_layout=1)
+        lib.siu3r_raster_set_culling(0)
+        try:
+            b = ops.raster_forward(*args, sh_layout=1)
+        finally:
+            lib.siu3r_raster_set_culling(1)
+        for kk in ("color", "depth", "opacity", "n_touched"):
+            assert torch.equal(a[kk], b[kk]), (pa, kk)

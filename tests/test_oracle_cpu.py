@@ -61,6 +61,42 @@ def test_torch_port_matches_reference_goldens(S, state_dict):
     assert list(qc.shape) == meta["qc0"]["shape"] and np.abs(_samples(qc) - z["qc0__samples"]).max() < 1e-5
 
 
+@pytest.mark.parametrize("S", [64, 256])
+def test_torch_port_multiview_matches_reference_goldens(S, state_dict):
+    """BASELINE config 4 (SIU3RMultiViewModel, V = 4): the port's forward_multi against goldens made from the unmodified reference
+    (oracle/make_golden.py --views=4)."""
+    from oracle import torch_port as TP
+    from siu3r_b200 import synth
+    V = 4
+    z = np.load(os.path.join(GOLD, f"model_V{V}_S{S}.npz"))
+    meta = json.loads(str(z["meta"]))
+    img, K = synth.pair_inputs(1, V, S)
+    st = {}
+    out = TP.forward_multi(state_dict, img, K, stages=st)
+    d = {"g_" + n: out[n] for n in ("means", "covariances", "harmonics", "opacities", "scales", "rotations")}
+    d["class_queries_logits"], d["masks_queries_logits"] = out["class_queries_logits"], out["masks_queries_logits"]
+    for v in range(V):
+        for l in range(4):
+            d[f"adapter_v{v}_f{l + 1}"] = st["adapter"][v][l]
+        d[f"gs_raw_{v}"] = st["gs_raw"][v].transpose(1, 2).reshape(1, 83, S, S)
+        d[f"pts3d_{v}"] = st["pts3d"][v].view(1, S, S, 3)
+    d["m2f_mask_features"] = st["m2f"]["mask_features"]
+    for j in range(3):
+        d[f"m2f_ms{j}"] = st["m2f"]["ms"][j]
+    for name, t in d.items():
+        assert list(t.shape) == meta[name]["shape"], (name, t.shape, meta[name]["shape"])
+        err = np.abs(_samples(t) - z[name + "__samples"]).max()
+        assert err <= 2e-5 * meta[name]["absmax"] + 1e-12, (name, err, meta[name]["absmax"])
+    assert len(out["seg_infos"][0]) == len(meta["seg_infos"][0])
+    for a, b in zip(out["seg_infos"][0], meta["seg_infos"][0]):
+        assert (a["id"], a["label_id"], a["was_fused"]) == (b["id"], b["label_id"], b["was_fused"]) and abs(a["score"] - b["score"]) < 1e-5
+    assert torch.bincount(out["semantic_labels"].flatten().long(), minlength=22).tolist() == meta["sem_hist"]
+    assert torch.bincount(out["instance_labels"].flatten().long()).tolist() == meta["inst_hist"]
+    assert np.array_equal(_samples(out["seg_masks"][0]).astype(np.int64), z["seg_mask0__samples"].astype(np.int64))
+    qc = out["seg_query_class_logits"][0]
+    assert list(qc.shape) == meta["qc0"]["shape"] and np.abs(_samples(qc) - z["qc0__samples"]).max() < 1e-5
+
+
 def test_post_process_crafted_logits_populated_branch():
     """Crafted logits drive the data-dependent branch (kept queries, stuff fusing of classes {0,1}, area test)."""
     from oracle import torch_port as TP

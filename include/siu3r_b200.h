@@ -69,7 +69,8 @@ int siu3r_conv2d_tc(int Nimg, int H, int W, int Cin, int Cout, int KH, int KW, i
 int siu3r_gemm_simt(int M, int N, int K, const float* A, int64_t lda, const float* W, int64_t ldw, float* C, int64_t ldc,
                     const float* bias, const float* residual, int64_t ldr, int act, float alpha, void* stream);
 int siu3r_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream);
-void siu3r_gemm_debug_set(long long* dev_buf);   /* profiling aid: per-CTA clock64 stamps of the 1-CTA linear kernel */
+void siu3r_gemm_debug_set(long long* dev_buf);
+void siu3r_gemm_force(int kernel);               /* tuning aid: 0 heuristic, 1 persistent swapped pair kernel (>= 16: that token tile width), 3 one-tile pair, 4 1-CTA */   /* profiling aid: per-CTA clock64 stamps of the 1-CTA linear kernel */
 
 /* ---- transformer pieces ----------------------------------------------------------------------------------------
  * siu3r_rope2d replaces curope.rope_2d(tokens, positions, base, fwd) (croco/curope/curope.cpp:49-65,

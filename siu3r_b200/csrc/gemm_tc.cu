@@ -21,7 +21,9 @@
 //                accuracy on the tensor cores; used for the strict parity tolerances of BASELINE.json's north_star.
 #include <cuda.h>
 
+#include <cmath>
 #include <cstdlib>
+#include <cstring>
 #include <mutex>
 #include <unordered_map>
 
@@ -267,11 +269,11 @@ __device__ __forceinline__ void epi_emit(uint32_t tr_saddr, int lane, int q, int
 // chunk c+1 and the bias of chunk c+1 are in flight while chunk c is emitted.  3xTF32 sums the 4 accumulators per chunk.
 template <int NCOLS, int NSPLIT>
 __device__ __forceinline__ void run_epilogue(uint32_t tmem_base, uint32_t tr, int lane, int q, int n0, const GemmParams& p, const EpiRowMap& rm,
-                                             uint64_t* acc_bar) {
+                                             uint64_t* acc_bar, uint32_t acc_parity = 0) {
     const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16);
     const int c4 = (lane & 7) * 4;
     float4 bias = epi_load_bias(p, n0 + c4);   // issued before the accumulator is ready: latency hidden behind the mainloop
-    mbar_wait(acc_bar, 0);
+    mbar_wait(acc_bar, acc_parity);
     tcgen05_fence_after();
     uint32_t v[32];
     if (NSPLIT == 1) tmem_ld_32x32b_x32(tq, v);
@@ -588,6 +590,255 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TC2_BN) : "memory");
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Persistent, operand-swapped 2-CTA kernel (linear mode, TF32):  C^T tile = W[256 rows] * X[tw tokens]^T.
+//
+// Why swapped.  The transformer GEMMs of one image pair have M = 2050 or 1025 token rows (1024 patches + the intrinsics
+// token per image) against N = 768..4096 weight rows.  With tokens on the 128-row MMA-M axis the last M tile holds 1-2
+// rows (6-20 % of the machine wasted) and the tile count (e.g. 9 x 12 pair tiles on 74 TPC pairs) quantises badly.  The
+// weight rows are multiples of 256, so THEY go on the MMA-M axis (256 per CTA pair, nothing wasted) and the tokens on the
+// MMA-N axis, whose tile width tw may be any multiple of 16 up to 256: the host picks tw so that (weight pair rows x
+// token tiles) fills whole rounds of the 74 resident clusters (2050 tokens x 3072 rows: tw = 176 -> 144 tiles = 1.95 rounds).
+// A second gain: TMEM lane = weight row n, TMEM column = token m, so one tcgen05.ld row-per-lane fragment already has 32
+// consecutive n for a fixed m across the warp -> every global store / residual load is a full 128-byte line of C without
+// the shared-memory transpose of the M-major kernels; bias is one register per thread, RoPE pairs (d, d+16) are lanes
+// l and l^16.
+//
+// Persistent: one cluster (CTA pair) per TPC walks over its tiles; two TMEM accumulators (2 x 256 fp32 columns) let the
+// epilogue of tile i run under the mainloop of tile i+1 and the 6-stage TMA ring stays full across tile boundaries.
+//   full[s]   (leader)      <- complete_tx of both CTAs' TMA loads
+//   empty[s]  (both CTAs)   <- tcgen05.commit multicast by the leader
+//   tfull[b]  (both CTAs)   <- tcgen05.commit multicast after the last k-block of a tile
+//   tempty[b] (leader, 16)  <- one arrive per epilogue warp of both CTAs once accumulator b has been drained
+// ------------------------------------------------------------------------------------------------------------
+struct Tc3 {
+    static constexpr int W_BYTES = BM * BK * 4;             // 128 weight rows per CTA
+    static constexpr int X_BYTES_MAX = 128 * BK * 4;        // up to 128 token rows per CTA (tw <= 256)
+    static constexpr int STAGE_BYTES = W_BYTES + X_BYTES_MAX;
+    static constexpr int STAGES = 6;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+    static constexpr int TMEM_COLS = 512;
+    static constexpr int CLUSTERS = 74;                     // TPC pairs of a B200 (148 SMs)
+};
+
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+
+// Epilogue of one warp: TMEM lanes [32q, 32q+32) = weight rows n, columns [c_lo, c_hi) = its share of the tile's tokens.
+// One 32-column fragment = 32 tokens x (this lane's n): every store / residual load below is one 128-byte line per warp.
+constexpr int TC3_EPI_WARPS = 8;                       // two warps per TMEM lane quarter (they split the token columns)
+constexpr int TC3_THREADS = 64 + 32 * TC3_EPI_WARPS;   // + TMA producer warp + MMA issuer warp
+
+template <int ACTK, bool ROPE, bool RES, bool RND>
+__device__ __forceinline__ void epi_chunk_swapped(const uint32_t (&v)[32], int jmax, int lane, int n, bool n_ok, float bias, int mrow, int axis,
+                                                  const GemmParams& p) {
+    float r[32];
+    const float* rp = RES ? p.residual + (int64_t)mrow * p.ldr + n : nullptr;
+    if (RES) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = (j < jmax && n_ok) ? rp[(int64_t)j * p.ldr] : 0.0f;   // all loads in flight before the math
+    }
+    long long pos_l = 0;
+    const float* tab = nullptr;
+    if (ROPE) {
+        pos_l = lane < jmax ? p.rope_pos[(int64_t)(mrow + lane) * 2 + axis] : 0;   // lane j holds the position of token j of the fragment
+        tab = p.rope_tab + (lane & 15) * 2;
+    }
+    float* cp = p.C + (int64_t)mrow * p.ldc + n;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        float x = __uint_as_float(v[j]) * p.alpha + bias;
+        if (ACTK == ACT_GELU) x = gelu_erf(x);
+        if (ACTK == ACT_RELU) x = fmaxf(x, 0.0f);
+        if (ROPE) {
+            const float y = __shfl_xor_sync(0xffffffffu, x, 16);
+            const int pj = __shfl_sync(0xffffffffu, (int)pos_l, j);
+            const float2 cs = __ldg(reinterpret_cast<const float2*>(tab + pj * 32));
+            x = (lane & 16) ? x * cs.x + y * cs.y : x * cs.x - y * cs.y;
+        }
+        if (RES) x += r[j];
+        if (RND) x = rn_tf32(x);
+        if (j < jmax && n_ok) cp[(int64_t)j * p.ldc] = x;
+    }
+}
+
+__device__ __forceinline__ void run_epilogue_swapped(uint32_t tmem_acc, int lane, int q, int c_lo, int c_hi, int n_cta, int m_base,
+                                                     const GemmParams& p, uint64_t* bar, uint32_t parity) {
+    const int nb = n_cta + q * 32;           // warp-uniform first weight row
+    const int n = nb + lane;
+    const bool n_ok = n < p.N;
+    const float bias = (p.bias && n_ok) ? __ldg(p.bias + n) : 0.0f;
+    const int act = p.act & ACT_MASK;
+    const bool rnd = (p.act & ACT_ROUND_TF32) != 0;
+    const bool rope = p.rope_pos != nullptr && nb < p.rope_cols;
+    const bool res = p.residual != nullptr;
+    const int axis = (nb >> 5) & 1;
+    // warp-uniform variant id: branches are hoisted out of the 32-element inner loops
+    const int variant = rope ? (rnd ? 1 : 0) : 2 + (act * 4 + (res ? 2 : 0) + (rnd ? 1 : 0));
+    mbar_wait(bar, parity);
+    tcgen05_fence_after();
+    if (nb >= p.N || c_lo >= c_hi) return;
+    const uint32_t tq = tmem_acc + ((uint32_t)(q * 32) << 16);
+    uint32_t v[32];
+#pragma unroll 1
+    for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
+        tmem_ld_32x32b_x32(tq + (uint32_t)c0, v);
+        tmem_ld_wait();
+        const int mrow = m_base + c0;
+        int jmax = c_hi - c0;
+        if (jmax > 32) jmax = 32;
+        if (jmax > p.M - mrow) jmax = p.M - mrow;
+        if (jmax <= 0) break;
+        switch (variant) {
+            case 0: epi_chunk_swapped<ACT_NONE, true, false, false>(v, jmax, lane, n, n_ok, bias, mrow, axis, p); break;
+            case 1: epi_chunk_swapped<ACT_NONE, true, false, true>(v, jmax, lane, n, n_ok, bias, mrow, axis, p); break;
+            case 2: epi_chunk_swapped<ACT_NONE, false, false, false>(v, jmax, lane, n, n_ok, bias, mrow, axis, p); break;
+            case 3: epi_chunk_swapped<ACT_NONE, false, false, true>(v, jmax, lane, n, n_ok, bias, mrow, axis, p); break;
+            case 4: epi_chunk_swapped<ACT_NONE, false, true, false>(v, jmax, lane, n, n_ok, bias, mrow, axis, p); break;
+            case 5: epi_chunk_swapped<ACT_NONE, false, true, true>(v, jmax, lane, n, n_ok, bias, mrow, axis, p); break;
+            case 6: epi_chunk_swapped<ACT_GELU, false, false, false>(v, jmax, lane, n, n_ok, bias, mrow, axis, p); break;
+            case 7: epi_chunk_swapped<ACT_GELU, false, false, true>(v, jmax, lane, n, n_ok, bias, mrow, axis, p); break;
+            case 8: epi_chunk_swapped<ACT_GELU, false, true, false>(v, jmax, lane, n, n_ok, bias, mrow, axis, p); break;
+            case 9: epi_chunk_swapped<ACT_GELU, false, true, true>(v, jmax, lane, n, n_ok, bias, mrow, axis, p); break;
+            case 10: epi_chunk_swapped<ACT_RELU, false, false, false>(v, jmax, lane, n, n_ok, bias, mrow, axis, p); break;
+            case 11: epi_chunk_swapped<ACT_RELU, false, false, true>(v, jmax, lane, n, n_ok, bias, mrow, axis, p); break;
+            case 12: epi_chunk_swapped<ACT_RELU, false, true, false>(v, jmax, lane, n, n_ok, bias, mrow, axis, p); break;
+            default: epi_chunk_swapped<ACT_RELU, false, true, true>(v, jmax, lane, n, n_ok, bias, mrow, axis, p); break;
+        }
+    }
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC3_THREADS, 1)
+gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX, const GemmParams p, int w_pairs, int num_tiles,
+                int tw) {
+    using C_ = Tc3;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C_::STAGES * C_::STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + C_::STAGES;
+    uint64_t* tfull_bar = empty_bar + C_::STAGES;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+    const int xrows = tw >> 1;                                  // token rows staged by each CTA
+    const uint32_t stage_tx = 2u * (uint32_t)(C_::W_BYTES + xrows * BK * 4);
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmW);
+        prefetch_tmap(&tmX);
+        for (int s = 0; s < C_::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 2 * TC3_EPI_WARPS); }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(C_::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs) =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+                const int n0 = (t % w_pairs) * 2 * BM + (int)rank * BM;       // this CTA's 128 weight rows
+                const int m0 = (t / w_pairs) * tw + (int)rank * xrows;        // this CTA's half of the token tile
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sW = smem + stage * C_::STAGE_BYTES;
+                    uint8_t* sX = sW + C_::W_BYTES;
+                    const uint32_t lead_full = mapa_to_cta(smem_u32(&full_bar[stage]), 0);
+                    if (leader) mbar_expect_tx(&full_bar[stage], stage_tx);
+                    tma2_load_2d(&tmW, lead_full, sW, kb * BK, n0);
+                    tma2_load_2d(&tmX, lead_full, sX, kb * BK, m0);
+                    if (++stage == C_::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA, one lane) =====================
+        if (leader && lane == 0) {
+            const uint32_t idesc = make_idesc_tf32(2 * BM, tw);
+            int stage = 0; uint32_t phase = 0;
+            int it = 0;
+            for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
+                const int buf = it & 1;
+                mbar_wait(&tempty_bar[buf], (((uint32_t)it >> 1) & 1u) ^ 1u);   // both CTAs' epilogues have drained this accumulator
+                tcgen05_fence_after();
+                const uint32_t acc = tmem_base + (uint32_t)(buf * 256);
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tcgen05_fence_after();
+                    const uint32_t sW = smem_u32(smem + stage * C_::STAGE_BYTES);
+                    const uint32_t sX = sW + C_::W_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint32_t koff = k * UMMA_K * 4;
+                        umma2_tf32(acc, make_smem_desc(sW + koff), make_smem_desc(sX + koff), idesc, (kb | k) != 0);
+                    }
+                    umma2_commit_mc(&empty_bar[stage]);
+                    if (++stage == C_::STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma2_commit_mc(&tfull_bar[buf]);
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..9 of both CTAs) =====================
+        const int q = warp & 3;                         // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;               // which half of the tile's 32-column fragments
+        const int nfrag = (tw + 31) >> 5;
+        const int c_lo = half == 0 ? 0 : ((nfrag + 1) >> 1) * 32;
+        const int c_hi = half == 0 ? min(tw, ((nfrag + 1) >> 1) * 32) : tw;
+        const uint32_t lead_tempty0 = mapa_to_cta(smem_u32(&tempty_bar[0]), 0);
+        int it = 0;
+        for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
+            const int buf = it & 1;
+            const int n_cta = (t % w_pairs) * 2 * BM + (int)rank * BM;
+            const int m_base = (t / w_pairs) * tw;
+            run_epilogue_swapped(tmem_base + (uint32_t)(buf * 256), lane, q, c_lo, c_hi, n_cta, m_base, p, &tfull_bar[buf], ((uint32_t)it >> 1) & 1u);
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(lead_tempty0 + (uint32_t)(buf * 8));
+        }
+    }
+    __syncwarp();
+    tcgen05_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C_::TMEM_COLS) : "memory");
+}
+
+int launch_tc3(const CUtensorMap& w, const CUtensorMap& x, const GemmParams& p, int w_pairs, int num_tiles, int tw, cudaStream_t stream) {
+    using C_ = Tc3;
+    static int max_clusters = 0;
+    if (max_clusters == 0) {
+        SIU3R_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM_BYTES));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * C_::CLUSTERS); cfg.blockDim = dim3(TC3_THREADS); cfg.dynamicSmemBytes = C_::SMEM_BYTES;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, gemm_tc3_kernel, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = 64; }
+        max_clusters = n;
+        if (getenv("SIU3R_GEMM_VERBOSE")) fprintf(stderr, "[siu3r_b200] gemm_tc3: %d resident clusters, %d stages, %d B smem\n", n, C_::STAGES, C_::SMEM_BYTES);
+    }
+    const int clusters = num_tiles < max_clusters ? num_tiles : max_clusters;
+    gemm_tc3_kernel<<<dim3((unsigned)(2 * clusters)), TC3_THREADS, C_::SMEM_BYTES, stream>>>(w, x, p, w_pairs, num_tiles, tw);
+    SIU3R_LAUNCH_CHECK();
+    siu3r_note_launch(1);
+    return SIU3R_OK;
+}
+
 int launch_tc2(const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, dim3 grid, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
@@ -668,6 +919,45 @@ bool use_tc2(int N, int64_t mtiles) {
     return 2 * ceil_div_i64(mtiles, 2) * (N / TC2_BN) >= kFillCtas;
 }
 
+// forced kernel choice for tools/bench_ops.py sweeps: SIU3R_GEMM_FORCE = tc3 | tc2 | tc1 (unset = heuristic)
+int g_force = -1;
+int forced_kernel() {
+    int& v = g_force;
+    if (v < 0) {
+        const char* e = getenv("SIU3R_GEMM_FORCE");
+        v = 0;
+        if (e) {
+            if (!strcmp(e, "tc3")) v = 1; else if (!strcmp(e, "tc2")) v = 3; else if (!strcmp(e, "tc1")) v = 4;
+        }
+    }
+    return v;
+}
+
+// Persistent swapped pair kernel: returns the token tile width tw (multiple of 16, <= 256) or 0 = use the one-tile kernels.
+// Cost model per cluster (clocks): rounds x (k-blocks x max(tensor time, operand bytes per CTA / L2->SM share) + tile overhead);
+// TF32 tensor rate 4096 flop/clk/SM -> a 128 x tw x 32 k-block takes 2*tw clocks; the chip-wide L2->SM cap (~6300 B/clk, measured
+// on the 3x3 convs) gives each SM ~42 B/clk.
+int pick_tc3(int M, int N, int K, double* est_clk = nullptr) {
+    const int f = forced_kernel();
+    if (f == 3 || f == 4 || !tc2_enabled()) return 0;
+    if (f == 0 && (N < 256 || K < 128 || M < 256)) return 0;
+    const int tw_env = f >= 16 ? f : 0;   // siu3r_gemm_force(tw): this token tile width (sweeps)
+    const int w_pairs = ceil_div(N, 256);
+    const int num_kb = ceil_div(K, BK);
+    int best = 0; double best_t = 1e30;
+    for (int tw = 32; tw <= 256; tw += 16) {
+        if (tw_env && tw != tw_env) continue;
+        const int T = ceil_div(M, tw);
+        const int64_t tiles = (int64_t)w_pairs * T;
+        const int64_t rounds = ceil_div_i64(tiles, Tc3::CLUSTERS);
+        const double kb = fmax(2.0 * tw, (16384.0 + 64.0 * tw) / 42.0);
+        const double t = (double)rounds * (num_kb * kb + 700.0 + 6.0 * tw);
+        if (t < best_t * 0.999) { best_t = t; best = tw; }
+    }
+    if (est_clk) *est_clk = best_t;
+    return best;
+}
+
 int pick_bn(int N, int64_t mtiles) {
     if (N <= 64) return 64;
     return mtiles * ceil_div(N, 128) >= 148 ? 128 : 64;   // BN = 64 when 128-wide tiles would leave SMs idle
@@ -679,6 +969,9 @@ extern "C" {
 
 // debugging aid (not part of the product ABI): device buffer [16][8] of clock64 stamps written by the 1-CTA linear kernel
 void siu3r_gemm_debug_set(long long* dev_buf) { g_gemm_dbg = dev_buf; }
+// tuning aid: 0 = heuristic, 1 = persistent swapped pair kernel wherever it is legal (>= 16: with that token tile width),
+// 3 = one-tile pair kernel, 4 = 1-CTA kernels only
+void siu3r_gemm_force(int kernel) { g_force = kernel; }
 
 // C[M,N] (ldc) = act(alpha * A[M,K] (lda) @ W[N,K]^T (ldw) + bias[N]) + residual[M,N] (ldr)
 // fp32 storage; precision 1 = TF32, 3 = 3xTF32 (needs the *_lo planes: x = hi + lo with hi = tf32-rounded x).
@@ -695,7 +988,21 @@ static int gemm_tc_impl(int M, int N, int K, const float* A, const float* A_lo, 
     SIU3R_REQUIRE(lda % 4 == 0 && ldw % 4 == 0 && lda >= K && ldw >= K);
     SIU3R_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)Wt & 15) == 0);
     const int64_t mtiles = ceil_div_i64(M, BM);
-    if (precision == 1 && use_tc2(N, mtiles)) {
+    if (const int tw = (precision == 1 ? pick_tc3(M, N, K) : 0)) {
+        // persistent swapped pair kernel: weights on the MMA-M axis, tokens on the MMA-N axis
+        CUtensorMap mw, mx;
+        uint64_t dimsW[2] = {(uint64_t)K, (uint64_t)N}; uint64_t strW[1] = {(uint64_t)ldw * 4}; uint32_t boxW[2] = {BK, BM};
+        int r = make_map(&mw, Wt, 2, dimsW, strW, boxW); if (r) return r;
+        uint64_t dimsX[2] = {(uint64_t)K, (uint64_t)M}; uint64_t strX[1] = {(uint64_t)lda * 4}; uint32_t boxX[2] = {BK, (uint32_t)(tw / 2)};
+        r = make_map(&mx, A, 2, dimsX, strX, boxX); if (r) return r;
+        GemmParams p{};
+        p.M = M; p.N = N; p.num_kb = ceil_div(K, BK); p.C = C; p.ldc = ldc; p.bias = bias; p.residual = residual; p.ldr = ldr;
+        p.act = act; p.alpha = alpha; p.conv = 0;
+        p.rope_pos = (const long long*)rope_pos; p.rope_tab = rope_tab; p.rope_cols = rope_cols;
+        const int w_pairs = ceil_div(N, 256);
+        return launch_tc3(mw, mx, p, w_pairs, w_pairs * ceil_div(M, tw), tw, stream);
+    }
+    if (precision == 1 && forced_kernel() != 4 && use_tc2(N, mtiles)) {
         // 2-CTA path: pairs of consecutive 128-row tiles share one 256 x 256 MMA
         CUtensorMap ma, mb;
         uint64_t dimsA[2] = {(uint64_t)K, (uint64_t)M}; uint64_t strA[1] = {(uint64_t)lda * 4}; uint32_t boxA[2] = {BK, BM};

@@ -232,6 +232,12 @@ def main():
     host_out = pipe.slots[0]["host"]
     h2d = img_pin.numel() * 4 + K_pin.numel() * 4
     d2h = sum(t.numel() * t.element_size() for t in host_out.values())
+    # PCIe download rate of this box (explains e2e vs value: ~200 MB of Gaussians leave the GPU per pair)
+    big = max(pipe.slots[0]["dev"].values(), key=lambda t: t.numel())
+    big_h = torch.empty(big.shape, dtype=big.dtype, pin_memory=True)
+    big_h.copy_(big); torch.cuda.synchronize()
+    ms_copy = timed(lambda: big_h.copy_(big, non_blocking=True), 3) / 3
+    d2h_gbs = big.numel() * big.element_size() / ms_copy / 1e6
 
     # ---- roofline of the dominant kernel family (instrumented pass, CUDA events on the launching stream) ----
     model.disable_cuda_graph()
@@ -256,11 +262,19 @@ def main():
     tf32_peak = bf16_peak / 2
     dom = max(fam.items(), key=lambda kv: kv[1][0]) if fam else None
     roofline = None
+    # DRAM traffic per launch of the dominant family, from the committed ncu pass over the same forward (profiles/r01_ncu_traffic.json,
+    # made by tools/summarize_launches.py --traffic from `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum`); null if absent
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))
+    except Exception:
+        pass
     if dom:
         name, (tms, work, n) = dom
         ach = work / (tms / 1e3) / 1e12
+        tr = traffic.get(name, {}).get("dram_bytes_per_launch") if S == 512 and B == 1 and V == 2 else None
         roofline = {"kernel": name, "bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak,
-                    "traffic": None, "launches": n, "ms_per_launch": tms / n, "share_of_step_ms": tms, "peak_source": peak_src,
+                    "traffic": tr, "traffic_unit": "bytes of DRAM read+write per launch (ncu)", "algorithmic_flop_per_launch": work / n, "launches": n, "ms_per_launch": tms / n, "share_of_step_ms": tms, "peak_source": peak_src,
                     "families": {k: {"ms": v[0], "tflops": v[1] / (v[0] / 1e3) / 1e12, "launches": v[2]} for k, v in fam.items()}}
 
     line = {"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -272,7 +286,8 @@ def main():
                        "cuda_graph": bool(args.graph),
                        "l2": "no explicit flush: weights (2.6 GB) + activations per step exceed the 126 MB L2 many times over"},
             "clocks": clk,
-            "e2e": {"value": e2e_v, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+            "e2e": {"value": e2e_v, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
+                    "d2h_pinned_GBs": d2h_gbs},
             "gpu_launches": launches,
             "vit_tensor_pipe_frac": value / world * (FLOPS_PER_PAIR_512 if V == 2 else FLOPS_PER_SAMPLE_512_V4 * V / 4) * (S / 512.0) ** 2 / 1e12 / tf32_peak,
             "roofline": roofline}
@@ -295,6 +310,25 @@ def main():
             del mv
         except Exception as ex:  # never lose the headline line
             line["multiview"] = {"error": repr(ex)}
+
+    # ---- the parity-grade precision mode (3xTF32: north-star tolerances, tests/test_model_gpu.py) timed on the same workload ----
+    if V == 2 and world == 1 and not args.no_multiview and args.precision == "tf32":
+        try:
+            del model
+            torch.cuda.empty_cache()
+            m3 = SIU3RModel(ModelCfg(image_size=(S, S)), precision="fp32x3")
+            m3.load_state_dict(synth.make_state_dict())
+            m3.cuda()
+            m3.enable_cuda_graph()
+            for _ in range(2):
+                m3(img_d, K_d)
+            ms3 = timed(lambda: m3(img_d, K_d), 5) / 5
+            line["fp32x3"] = {"value": B * 1e3 / ms3, "unit": "pairs/s", "ms_per_step": ms3, "steps": 5,
+                              "note": "3xTF32 split on the tensor cores: Gaussians within 1e-3 abs, seg logits within 1e-4 rel of the fp32 reference"}
+            del m3
+            torch.cuda.empty_cache()
+        except Exception as ex:
+            line["fp32x3"] = {"error": repr(ex)}
 
     # ---- rasterizer sample (BASELINE config 5: 500k pixel-aligned Gaussians @512^2), HBM roofline ----
     if not args.no_raster and rank == 0:

@@ -62,6 +62,12 @@ int siu3r_gemm_tc(int M, int N, int K, const float* A, const float* A_lo, int64_
 int siu3r_gemm_tc_rope(int M, int N, int K, const float* A, const float* A_lo, int64_t lda, const float* Wt, const float* W_lo,
                        int64_t ldw, float* C, int64_t ldc, const float* bias, int act, int precision, const int64_t* positions,
                        const float* rope_tab, int rope_cols, void* stream);
+/* two same-shape linear layers with different operands in one persistent launch (TF32 only): the two decoder streams of
+ * AsymmetricCroCo (dec_blocks / dec_blocks2, backbone_croco.py:244-250, 514-531).  *_host = host arrays of 2 device pointers (bias_host /
+ * residual_host may be null); M_host[2] rows per problem.  -4 when the shape is not eligible (issue two siu3r_gemm_tc instead). */
+int siu3r_gemm_tc_group2(const int* M_host, int N, int K, const float* const* A_host, int64_t lda, const float* const* W_host, int64_t ldw,
+                         float* const* C_host, int64_t ldc, const float* const* bias_host, const float* const* residual_host, int64_t ldr,
+                         int act, float alpha, const int64_t* positions, const float* rope_tab, int rope_cols, void* stream);
 int siu3r_conv2d_tc(int Nimg, int H, int W, int Cin, int Cout, int KH, int KW, int pad_h, int pad_w, const float* x, const float* x_lo,
                     const float* Wt, const float* W_lo, float* y, int64_t ldc, const float* bias, const float* residual,
                     int64_t ldr, int act, int precision, void* stream);
@@ -148,6 +154,15 @@ int siu3r_label_lut(const int32_t* labels, int64_t npix, const int32_t* seg_lut,
                     int32_t* sem, int32_t* inst, void* stream);
 int siu3r_qc_logits(const float* probs, int64_t npix, int nq, const int* keep, int nk, const float* cls, int ncls,
                     float* out, void* stream);
+
+/* ---- output wire format ------------------------------------------------------------------------------------------
+ * Packed little-endian PLY vertex records of export_ply (src/utils/ply_export.py:12-97; field order :12-27, log(scales) :74,
+ * rotations re-ordered xyzw -> wxyz :52-53, i4 labels :62-64, flattened seg_query_class_logits :65-71): the device buffer copied to
+ * the host is the body of the file written by inference.py:137-150. */
+int siu3r_ply_record_words(int d_sh, int dc_only, int has_labels, int qc_words);
+int siu3r_ply_pack(const float* means, const float* scales, const float* rotations, const float* harmonics, const float* opacities,
+                   const int32_t* semantic_labels, const int32_t* instance_labels, const float* qc_logits, int64_t G, int d_sh, int dc_only,
+                   int qc_words, uint32_t* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -630,11 +630,22 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
 constexpr int TC3_EPI_WARPS = 8;                       // two warps per TMEM lane quarter (they split the token columns)
 constexpr int TC3_THREADS = 64 + 32 * TC3_EPI_WARPS;   // + TMA producer warp + MMA issuer warp
 
+struct Tc3Problem {      // what differs between the problems of a grouped launch (same N, K, leading dimensions, epilogue)
+    float* C;
+    const float* bias;
+    const float* residual;
+    int M;
+};
+struct Tc3Group {
+    Tc3Problem prob[2];
+    int tiles0;          // tiles of problem 0 (tile t >= tiles0 belongs to problem 1)
+};
+
 template <int ACTK, bool ROPE, bool RES, bool RND>
 __device__ __forceinline__ void epi_chunk_swapped(const uint32_t (&v)[32], int jmax, int lane, int n, bool n_ok, float bias, int mrow, int axis,
-                                                  const GemmParams& p) {
+                                                  const GemmParams& p, const Tc3Problem& pr) {
     float r[32];
-    const float* rp = RES ? p.residual + (int64_t)mrow * p.ldr + n : nullptr;
+    const float* rp = RES ? pr.residual + (int64_t)mrow * p.ldr + n : nullptr;
     if (RES) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) r[j] = (j < jmax && n_ok) ? rp[(int64_t)j * p.ldr] : 0.0f;   // all loads in flight before the math
@@ -645,7 +656,7 @@ __device__ __forceinline__ void epi_chunk_swapped(const uint32_t (&v)[32], int j
         pos_l = lane < jmax ? p.rope_pos[(int64_t)(mrow + lane) * 2 + axis] : 0;   // lane j holds the position of token j of the fragment
         tab = p.rope_tab + (lane & 15) * 2;
     }
-    float* cp = p.C + (int64_t)mrow * p.ldc + n;
+    float* cp = pr.C + (int64_t)mrow * p.ldc + n;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
         float x = __uint_as_float(v[j]) * p.alpha + bias;
@@ -664,15 +675,15 @@ __device__ __forceinline__ void epi_chunk_swapped(const uint32_t (&v)[32], int j
 }
 
 __device__ __forceinline__ void run_epilogue_swapped(uint32_t tmem_acc, int lane, int q, int c_lo, int c_hi, int n_cta, int m_base,
-                                                     const GemmParams& p, uint64_t* bar, uint32_t parity) {
+                                                     const GemmParams& p, const Tc3Problem& pr, uint64_t* bar, uint32_t parity) {
     const int nb = n_cta + q * 32;           // warp-uniform first weight row
     const int n = nb + lane;
     const bool n_ok = n < p.N;
-    const float bias = (p.bias && n_ok) ? __ldg(p.bias + n) : 0.0f;
+    const float bias = (pr.bias && n_ok) ? __ldg(pr.bias + n) : 0.0f;
     const int act = p.act & ACT_MASK;
     const bool rnd = (p.act & ACT_ROUND_TF32) != 0;
     const bool rope = p.rope_pos != nullptr && nb < p.rope_cols;
-    const bool res = p.residual != nullptr;
+    const bool res = pr.residual != nullptr;
     const int axis = (nb >> 5) & 1;
     // warp-uniform variant id: branches are hoisted out of the 32-element inner loops
     const int variant = rope ? (rnd ? 1 : 0) : 2 + (act * 4 + (res ? 2 : 0) + (rnd ? 1 : 0));
@@ -688,30 +699,30 @@ __device__ __forceinline__ void run_epilogue_swapped(uint32_t tmem_acc, int lane
         const int mrow = m_base + c0;
         int jmax = c_hi - c0;
         if (jmax > 32) jmax = 32;
-        if (jmax > p.M - mrow) jmax = p.M - mrow;
+        if (jmax > pr.M - mrow) jmax = pr.M - mrow;
         if (jmax <= 0) break;
         switch (variant) {
-            case 0: epi_chunk_swapped<ACT_NONE, true, false, false>(v, jmax, lane, n, n_ok, bias, mrow, axis, p); break;
-            case 1: epi_chunk_swapped<ACT_NONE, true, false, true>(v, jmax, lane, n, n_ok, bias, mrow, axis, p); break;
-            case 2: epi_chunk_swapped<ACT_NONE, false, false, false>(v, jmax, lane, n, n_ok, bias, mrow, axis, p); break;
-            case 3: epi_chunk_swapped<ACT_NONE, false, false, true>(v, jmax, lane, n, n_ok, bias, mrow, axis, p); break;
-            case 4: epi_chunk_swapped<ACT_NONE, false, true, false>(v, jmax, lane, n, n_ok, bias, mrow, axis, p); break;
-            case 5: epi_chunk_swapped<ACT_NONE, false, true, true>(v, jmax, lane, n, n_ok, bias, mrow, axis, p); break;
-            case 6: epi_chunk_swapped<ACT_GELU, false, false, false>(v, jmax, lane, n, n_ok, bias, mrow, axis, p); break;
-            case 7: epi_chunk_swapped<ACT_GELU, false, false, true>(v, jmax, lane, n, n_ok, bias, mrow, axis, p); break;
-            case 8: epi_chunk_swapped<ACT_GELU, false, true, false>(v, jmax, lane, n, n_ok, bias, mrow, axis, p); break;
-            case 9: epi_chunk_swapped<ACT_GELU, false, true, true>(v, jmax, lane, n, n_ok, bias, mrow, axis, p); break;
-            case 10: epi_chunk_swapped<ACT_RELU, false, false, false>(v, jmax, lane, n, n_ok, bias, mrow, axis, p); break;
-            case 11: epi_chunk_swapped<ACT_RELU, false, false, true>(v, jmax, lane, n, n_ok, bias, mrow, axis, p); break;
-            case 12: epi_chunk_swapped<ACT_RELU, false, true, false>(v, jmax, lane, n, n_ok, bias, mrow, axis, p); break;
-            default: epi_chunk_swapped<ACT_RELU, false, true, true>(v, jmax, lane, n, n_ok, bias, mrow, axis, p); break;
+            case 0: epi_chunk_swapped<ACT_NONE, true, false, false>(v, jmax, lane, n, n_ok, bias, mrow, axis, p, pr); break;
+            case 1: epi_chunk_swapped<ACT_NONE, true, false, true>(v, jmax, lane, n, n_ok, bias, mrow, axis, p, pr); break;
+            case 2: epi_chunk_swapped<ACT_NONE, false, false, false>(v, jmax, lane, n, n_ok, bias, mrow, axis, p, pr); break;
+            case 3: epi_chunk_swapped<ACT_NONE, false, false, true>(v, jmax, lane, n, n_ok, bias, mrow, axis, p, pr); break;
+            case 4: epi_chunk_swapped<ACT_NONE, false, true, false>(v, jmax, lane, n, n_ok, bias, mrow, axis, p, pr); break;
+            case 5: epi_chunk_swapped<ACT_NONE, false, true, true>(v, jmax, lane, n, n_ok, bias, mrow, axis, p, pr); break;
+            case 6: epi_chunk_swapped<ACT_GELU, false, false, false>(v, jmax, lane, n, n_ok, bias, mrow, axis, p, pr); break;
+            case 7: epi_chunk_swapped<ACT_GELU, false, false, true>(v, jmax, lane, n, n_ok, bias, mrow, axis, p, pr); break;
+            case 8: epi_chunk_swapped<ACT_GELU, false, true, false>(v, jmax, lane, n, n_ok, bias, mrow, axis, p, pr); break;
+            case 9: epi_chunk_swapped<ACT_GELU, false, true, true>(v, jmax, lane, n, n_ok, bias, mrow, axis, p, pr); break;
+            case 10: epi_chunk_swapped<ACT_RELU, false, false, false>(v, jmax, lane, n, n_ok, bias, mrow, axis, p, pr); break;
+            case 11: epi_chunk_swapped<ACT_RELU, false, false, true>(v, jmax, lane, n, n_ok, bias, mrow, axis, p, pr); break;
+            case 12: epi_chunk_swapped<ACT_RELU, false, true, false>(v, jmax, lane, n, n_ok, bias, mrow, axis, p, pr); break;
+            default: epi_chunk_swapped<ACT_RELU, false, true, true>(v, jmax, lane, n, n_ok, bias, mrow, axis, p, pr); break;
         }
     }
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC3_THREADS, 1)
-gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX, const GemmParams p, int w_pairs, int num_tiles,
-                int tw) {
+gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
+                const __grid_constant__ CUtensorMap tmX1, const GemmParams p, const Tc3Group grp, int w_pairs, int num_tiles, int tw) {
     using C_ = Tc3;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -731,6 +742,7 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmW);
         prefetch_tmap(&tmX);
+        if (grp.tiles0 < num_tiles) { prefetch_tmap(&tmW1); prefetch_tmap(&tmX1); }
         for (int s = 0; s < C_::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 2 * TC3_EPI_WARPS); }
         fence_barrier_init();
@@ -750,16 +762,20 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             for (int t = cluster_id; t < num_tiles; t += num_clusters) {
-                const int n0 = (t % w_pairs) * 2 * BM + (int)rank * BM;       // this CTA's 128 weight rows
-                const int m0 = (t / w_pairs) * tw + (int)rank * xrows;        // this CTA's half of the token tile
+                const int g = t >= grp.tiles0;
+                const int tl = g ? t - grp.tiles0 : t;
+                const CUtensorMap* mw = g ? &tmW1 : &tmW;
+                const CUtensorMap* mx = g ? &tmX1 : &tmX;
+                const int n0 = (tl % w_pairs) * 2 * BM + (int)rank * BM;       // this CTA's 128 weight rows
+                const int m0 = (tl / w_pairs) * tw + (int)rank * xrows;        // this CTA's half of the token tile
                 for (int kb = 0; kb < p.num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sW = smem + stage * C_::STAGE_BYTES;
                     uint8_t* sX = sW + C_::W_BYTES;
                     const uint32_t lead_full = mapa_to_cta(smem_u32(&full_bar[stage]), 0);
                     if (leader) mbar_expect_tx(&full_bar[stage], stage_tx);
-                    tma2_load_2d(&tmW, lead_full, sW, kb * BK, n0);
-                    tma2_load_2d(&tmX, lead_full, sX, kb * BK, m0);
+                    tma2_load_2d(mw, lead_full, sW, kb * BK, n0);
+                    tma2_load_2d(mx, lead_full, sX, kb * BK, m0);
                     if (++stage == C_::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -802,9 +818,12 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         int it = 0;
         for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
             const int buf = it & 1;
-            const int n_cta = (t % w_pairs) * 2 * BM + (int)rank * BM;
-            const int m_base = (t / w_pairs) * tw;
-            run_epilogue_swapped(tmem_base + (uint32_t)(buf * 256), lane, q, c_lo, c_hi, n_cta, m_base, p, &tfull_bar[buf], ((uint32_t)it >> 1) & 1u);
+            const int g = t >= grp.tiles0;
+            const int tl = g ? t - grp.tiles0 : t;
+            const int n_cta = (tl % w_pairs) * 2 * BM + (int)rank * BM;
+            const int m_base = (tl / w_pairs) * tw;
+            run_epilogue_swapped(tmem_base + (uint32_t)(buf * 256), lane, q, c_lo, c_hi, n_cta, m_base, p, grp.prob[g], &tfull_bar[buf],
+                                 ((uint32_t)it >> 1) & 1u);
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(lead_tempty0 + (uint32_t)(buf * 8));
@@ -817,7 +836,8 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C_::TMEM_COLS) : "memory");
 }
 
-int launch_tc3(const CUtensorMap& w, const CUtensorMap& x, const GemmParams& p, int w_pairs, int num_tiles, int tw, cudaStream_t stream) {
+int launch_tc3(const CUtensorMap& w, const CUtensorMap& x, const CUtensorMap& w1, const CUtensorMap& x1, const GemmParams& p, const Tc3Group& grp,
+               int w_pairs, int num_tiles, int tw, cudaStream_t stream) {
     using C_ = Tc3;
     static int max_clusters = 0;
     if (max_clusters == 0) {
@@ -833,7 +853,7 @@ int launch_tc3(const CUtensorMap& w, const CUtensorMap& x, const GemmParams& p, 
         if (getenv("SIU3R_GEMM_VERBOSE")) fprintf(stderr, "[siu3r_b200] gemm_tc3: %d resident clusters, %d stages, %d B smem\n", n, C_::STAGES, C_::SMEM_BYTES);
     }
     const int clusters = num_tiles < max_clusters ? num_tiles : max_clusters;
-    gemm_tc3_kernel<<<dim3((unsigned)(2 * clusters)), TC3_THREADS, C_::SMEM_BYTES, stream>>>(w, x, p, w_pairs, num_tiles, tw);
+    gemm_tc3_kernel<<<dim3((unsigned)(2 * clusters)), TC3_THREADS, C_::SMEM_BYTES, stream>>>(w, x, w1, x1, p, grp, w_pairs, num_tiles, tw);
     SIU3R_LAUNCH_CHECK();
     siu3r_note_launch(1);
     return SIU3R_OK;
@@ -937,17 +957,17 @@ int forced_kernel() {
 // Cost model per cluster (clocks): rounds x (k-blocks x max(tensor time, operand bytes per CTA / L2->SM share) + tile overhead);
 // TF32 tensor rate 4096 flop/clk/SM -> a 128 x tw x 32 k-block takes 2*tw clocks; the chip-wide L2->SM cap (~6300 B/clk, measured
 // on the 3x3 convs) gives each SM ~42 B/clk.
-int pick_tc3(int M, int N, int K, double* est_clk = nullptr) {
+int pick_tc3(int M, int N, int K, int M1 = 0, double* est_clk = nullptr) {
     const int f = forced_kernel();
     if (f == 3 || f == 4 || !tc2_enabled()) return 0;
-    if (f == 0 && (N < 256 || K < 128 || M < 256)) return 0;
+    if (f == 0 && (N < 256 || K < 128 || M + M1 < 256)) return 0;
     const int tw_env = f >= 16 ? f : 0;   // siu3r_gemm_force(tw): this token tile width (sweeps)
     const int w_pairs = ceil_div(N, 256);
     const int num_kb = ceil_div(K, BK);
     int best = 0; double best_t = 1e30;
     for (int tw = 32; tw <= 256; tw += 16) {
         if (tw_env && tw != tw_env) continue;
-        const int T = ceil_div(M, tw);
+        const int T = ceil_div(M, tw) + (M1 > 0 ? ceil_div(M1, tw) : 0);
         const int64_t tiles = (int64_t)w_pairs * T;
         const int64_t rounds = ceil_div_i64(tiles, Tc3::CLUSTERS);
         const double kb = fmax(2.0 * tw, (16384.0 + 64.0 * tw) / 42.0);
@@ -1000,7 +1020,11 @@ static int gemm_tc_impl(int M, int N, int K, const float* A, const float* A_lo, 
         p.act = act; p.alpha = alpha; p.conv = 0;
         p.rope_pos = (const long long*)rope_pos; p.rope_tab = rope_tab; p.rope_cols = rope_cols;
         const int w_pairs = ceil_div(N, 256);
-        return launch_tc3(mw, mx, p, w_pairs, w_pairs * ceil_div(M, tw), tw, stream);
+        Tc3Group grp{};
+        grp.prob[0] = Tc3Problem{C, bias, residual, M};
+        grp.prob[1] = grp.prob[0];
+        grp.tiles0 = w_pairs * ceil_div(M, tw);
+        return launch_tc3(mw, mx, mw, mx, p, grp, w_pairs, grp.tiles0, tw, stream);
     }
     if (precision == 1 && forced_kernel() != 4 && use_tc2(N, mtiles)) {
         // 2-CTA path: pairs of consecutive 128-row tiles share one 256 x 256 MMA
@@ -1048,6 +1072,40 @@ int siu3r_gemm_tc(int M, int N, int K, const float* A, const float* A_lo, int64_
                   float* C, int64_t ldc, const float* bias, const float* residual, int64_t ldr, int act, float alpha, int precision,
                   void* stream) {
     return gemm_tc_impl(M, N, K, A, A_lo, lda, Wt, W_lo, ldw, C, ldc, bias, residual, ldr, act, alpha, precision, nullptr, nullptr, 0, stream);
+}
+
+// Two independent linear layers of the same shape class in ONE persistent launch (TF32):  C_g = act(alpha * A_g W_g^T + bias_g) + R_g,
+// g = 0, 1, with M_g rows each and common N, K, leading dimensions and epilogue.  This is how the two decoder streams of
+// AsymmetricCroCo (dec_blocks on view 1, dec_blocks2 on view 2: backbone_croco.py:244-250, :514-531) share the machine: each
+// stream alone has M = 1025 rows, i.e. too few tiles to fill 148 SMs.  Pointer arrays are HOST arrays of device pointers.
+// Returns SIU3R_ERR_UNSUPPORTED when the shape is not eligible for the persistent kernel (caller then issues two siu3r_gemm_tc).
+int siu3r_gemm_tc_group2(const int* M_host, int N, int K, const float* const* A_host, int64_t lda, const float* const* W_host, int64_t ldw,
+                         float* const* C_host, int64_t ldc, const float* const* bias_host, const float* const* residual_host, int64_t ldr,
+                         int act, float alpha, const int64_t* positions, const float* rope_tab, int rope_cols, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    SIU3R_REQUIRE(M_host && A_host && W_host && C_host && N > 0 && K > 0 && M_host[0] > 0 && M_host[1] > 0);
+    SIU3R_REQUIRE(lda % 4 == 0 && ldw % 4 == 0 && lda >= K && ldw >= K);
+    for (int g = 0; g < 2; ++g) SIU3R_REQUIRE(A_host[g] && W_host[g] && C_host[g] && ((uintptr_t)A_host[g] & 15) == 0 && ((uintptr_t)W_host[g] & 15) == 0);
+    if (positions) SIU3R_REQUIRE(rope_tab && rope_cols > 0 && rope_cols % 64 == 0 && rope_cols <= N && ((uintptr_t)rope_tab & 15) == 0 && !residual_host);
+    const int tw = pick_tc3(M_host[0], N, K, M_host[1]);
+    if (tw == 0) return SIU3R_ERR_UNSUPPORTED;
+    CUtensorMap mw[2], mx[2];
+    for (int g = 0; g < 2; ++g) {
+        uint64_t dimsW[2] = {(uint64_t)K, (uint64_t)N}; uint64_t strW[1] = {(uint64_t)ldw * 4}; uint32_t boxW[2] = {BK, BM};
+        int r = make_map(&mw[g], W_host[g], 2, dimsW, strW, boxW); if (r) return r;
+        uint64_t dimsX[2] = {(uint64_t)K, (uint64_t)M_host[g]}; uint64_t strX[1] = {(uint64_t)lda * 4}; uint32_t boxX[2] = {BK, (uint32_t)(tw / 2)};
+        r = make_map(&mx[g], A_host[g], 2, dimsX, strX, boxX); if (r) return r;
+    }
+    GemmParams p{};
+    p.M = M_host[0]; p.N = N; p.num_kb = ceil_div(K, BK); p.C = C_host[0]; p.ldc = ldc; p.ldr = ldr; p.act = act; p.alpha = alpha; p.conv = 0;
+    p.rope_pos = (const long long*)positions; p.rope_tab = rope_tab; p.rope_cols = rope_cols;
+    const int w_pairs = ceil_div(N, 256);
+    Tc3Group grp{};
+    for (int g = 0; g < 2; ++g)
+        grp.prob[g] = Tc3Problem{C_host[g], bias_host ? bias_host[g] : nullptr, residual_host ? residual_host[g] : nullptr, M_host[g]};
+    grp.tiles0 = w_pairs * ceil_div(M_host[0], tw);
+    const int tiles = grp.tiles0 + w_pairs * ceil_div(M_host[1], tw);
+    return launch_tc3(mw[0], mx[0], mw[1], mx[1], p, grp, w_pairs, tiles, tw, stream);
 }
 
 // nn.Linear followed by RoPE-2D on output columns [0, rope_cols) (head dim 64), i.e. the qkv / q / kv projections of

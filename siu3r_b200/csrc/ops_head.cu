@@ -217,6 +217,43 @@ inline unsigned grid_for(int64_t n, int threads = 256) { return (unsigned)((n + 
 
 }  // namespace
 
+// ---- PLY vertex records (src/utils/ply_export.py:30-97): one 32-bit word per thread, record-major so that the D2H copy of the
+//      packed buffer IS the file body.  Field order: x y z | nx ny nz (0) | f_dc_0..2 | f_rest (harmonics[..., 1:] flattened
+//      channel-major, omitted when dc_only) | opacity | log(scale_0..2) | rot w x y z (stored xyzw) | semantic_label i4 |
+//      instance_label i4 | seg_query_class_logits (q*c floats).  HBM-bound: ~(95 + qc) words read, F words written per Gaussian.
+__global__ void __launch_bounds__(256) ply_pack_kernel(const float* __restrict__ means, const float* __restrict__ scales,
+                                                       const float* __restrict__ rot, const float* __restrict__ harm,
+                                                       const float* __restrict__ opac, const int32_t* __restrict__ sem,
+                                                       const int32_t* __restrict__ inst, const float* __restrict__ qc, int64_t G, int d_sh,
+                                                       int n_rest, int has_labels, int qc_words, int F, uint32_t* __restrict__ out) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= G * F) return;
+    const int64_t g = t / F;
+    int f = (int)(t - g * F);
+    uint32_t w;
+    if (f < 3) w = __float_as_uint(means[3 * g + f]);
+    else if (f < 6) w = 0u;
+    else if (f < 9) w = __float_as_uint(harm[(3 * g + (f - 6)) * d_sh]);
+    else {
+        f -= 9;
+        if (f < n_rest) {
+            const int ch = f / (d_sh - 1), k = f - ch * (d_sh - 1) + 1;
+            w = __float_as_uint(harm[(3 * g + ch) * d_sh + k]);
+        } else {
+            f -= n_rest;
+            if (f == 0) w = __float_as_uint(opac[g]);
+            else if (f < 4) w = __float_as_uint(logf(scales[3 * g + (f - 1)]));
+            else if (f < 8) w = __float_as_uint(rot[4 * g + ((f - 4 + 3) & 3)]);   // (w, x, y, z) from (x, y, z, w)
+            else {
+                f -= 8;
+                if (has_labels && f < 2) w = (uint32_t)(f == 0 ? sem[g] : inst[g]);
+                else w = __float_as_uint(qc[g * qc_words + (f - (has_labels ? 2 : 0))]);
+            }
+        }
+    }
+    out[t] = w;
+}
+
 extern "C" {
 
 int siu3r_depth_exp(const float* xyz, int64_t ldx, float* pts, int64_t n, void* stream_) {
@@ -296,6 +333,28 @@ int siu3r_gemm_simt(int M, int N, int K, const float* A, int64_t lda, const floa
     SIU3R_REQUIRE(M > 0 && N > 0 && K > 0 && A && W && C);
     dim3 grid(ceil_div(N, SG_T), ceil_div(M, SG_T));
     gemm_simt_kernel<<<grid, SG_T * SG_T, 0, stream>>>(M, N, K, A, lda, W, ldw, C, ldc, bias, residual, ldr, act, alpha);
+    SIU3R_LAUNCH_CHECK();
+    siu3r_note_launch(1);
+    return SIU3R_OK;
+}
+
+
+// Packed PLY vertex records for export_ply (src/utils/ply_export.py:30-97).  out: G records of F = siu3r_ply_record_words(...) 32-bit words.
+int siu3r_ply_record_words(int d_sh, int dc_only, int has_labels, int qc_words) {
+    return 9 + (dc_only ? 0 : 3 * (d_sh - 1)) + 8 + (has_labels ? 2 : 0) + qc_words;
+}
+int siu3r_ply_pack(const float* means, const float* scales, const float* rotations, const float* harmonics, const float* opacities,
+                   const int32_t* semantic_labels, const int32_t* instance_labels, const float* qc_logits, int64_t G, int d_sh, int dc_only,
+                   int qc_words, uint32_t* out, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    SIU3R_REQUIRE(means && scales && rotations && harmonics && opacities && out && G > 0 && d_sh >= 1 && qc_words >= 0);
+    SIU3R_REQUIRE((semantic_labels == nullptr) == (instance_labels == nullptr));
+    SIU3R_REQUIRE(qc_words == 0 || qc_logits);
+    const int has_labels = semantic_labels ? 1 : 0;
+    const int n_rest = dc_only ? 0 : 3 * (d_sh - 1);
+    const int F = siu3r_ply_record_words(d_sh, dc_only, has_labels, qc_words);
+    ply_pack_kernel<<<grid_for(G * F), 256, 0, stream>>>(means, scales, rotations, harmonics, opacities, semantic_labels, instance_labels, qc_logits,
+                                                         G, d_sh, n_rest, has_labels, qc_words, F, out);
     SIU3R_LAUNCH_CHECK();
     siu3r_note_launch(1);
     return SIU3R_OK;

@@ -310,27 +310,6 @@ class SIU3RModel:
                 self._keep_ev[i] = ev   # the adapter stream starts interaction #k as soon as its ViT block is done
         return x, keep
 
-    def _dec_block(self, blk, x, y, pos, B, N):
-        """DecoderBlock.forward (croco/blocks.py:186-191): self-attn, cross-attn on norm_y(y), MLP.  Returns a new buffer."""
-        C, nh = 768, 12
-        h = self._ln(x, blk.n1, 1e-6)
-        a = self._self_attn(h, blk, pos, B, N, C, nh)
-        x1 = self._lin(a, blk.proj, ar=True, residual=x)
-        yn = self._ln(y, blk.ny, 1e-6)
-        h2 = self._ln(x1, blk.n2, 1e-6)
-        q = self._lin(h2, blk.cq, ar=True, ro=True, rope=(pos, self._k.rope_tab, C))
-        kv = self._lin(yn, blk.ckv, ar=True, ro=True, rope=(pos, self._k.rope_tab, C))
-        a2 = torch.empty(B * N, C, device=self.dev)
-        if self.R:
-            ops.flash_attn_tc(q, 0, N * C, C, C, kv, 0, N * 2 * C, 2 * C, 2 * C, kv, C, N * 2 * C, 2 * C, a2, B, nh, N, N, 0.125, round_out=True)
-        else:
-            ops.flash_attn_d64(q, 0, N * C, C, kv, 0, N * 2 * C, 2 * C, kv, C, N * 2 * C, 2 * C, a2, B, nh, N, N, 0.125, self.prec)
-        self._lin(a2, blk.cproj, ar=True, residual=x1, out=x1)
-        h3 = self._ln(x1, blk.n3, 1e-6)
-        f = self._lin(h3, blk.fc1, ar=True, ro=True, act=ACT_GELU)
-        self._lin(f, blk.fc2, ar=True, residual=x1, out=x1)
-        return x1
-
     # ---- DPT heads (heads/dpt_head.py:36-79, dpt_gs_head.py:121-171, dpt_block.py) ------------------------------------
     def _rcu(self, x, unit):
         r = ops.eltwise(ops.ELT_RELU_RN if self.R else ELT_RELU, x)
@@ -669,48 +648,81 @@ class SIU3RModel:
     def disable_cuda_graph(self):
         self._use_graph = False
 
-    def _dec_block_multi(self, blk, x, f_all, qviews, pos, B, N, V, out):
-        """DecoderBlock of the V-view decoder (backbone_croco.py:487-535).  x: rows of the query views `qviews` (view-major,
-        len(qviews)*B*N rows); f_all: previous-layer tokens of all V views [V*B*N, C].  The cross-attention memory of query
-        view i is the concatenation, in view order, of norm_y(tokens) of every view j != i (generate_ctx_views :500-506), each
-        key rotated with its own positions.  norm_y + the k|v projection are per token, so they run once per needed view and
-        the per-query-view memories are assembled by row copies."""
+    def _lin2(self, xs, wts, ar=False, ro=False, **kw):
+        """Two same-shape linear layers (the two decoder streams) in one grouped launch."""
+        return ops.gemm_group2(xs, wts, precision=self.prec, a_rounded=ar and self.R, round_out=ro and self.R, **kw)
+
+    def _dec_layer(self, l, f, B, N, V):
+        """One decoder layer for ALL views (backbone_croco.py:244-250 for V = 2, :514-531 for V > 2).  f: previous-layer tokens
+        [V*B*N, 768], view-major.  Stream 0 = view 0 through dec_blocks[l], stream 1 = views 1..V-1 (one batch) through
+        dec_blocks2[l]; every projection of the two streams is ONE grouped GEMM launch, self- and cross-attention run as one flash
+        launch over all V*B images.  The cross-attention memory of an image of view i is the concatenation, in view order, of
+        norm_y(tokens) of the same sample's other views (generate_ctx_views :500-506), keys rotated with their own positions;
+        norm_y + the k|v projection are per token, so they run once per (stream weights, needed view).  Returns a new buffer."""
         C, nh = 768, 12
-        nq = len(qviews)
-        Bq = nq * B
-        pos_q = pos[:Bq]
-        h = self._ln(x, blk.n1, 1e-6)
-        a = self._self_attn(h, blk, pos_q, Bq, N, C, nh)
-        x1 = self._lin(a, blk.proj, ar=True, residual=x, out=out)   # `out`: this branch's rows of the next layer's token buffer
-        need = [j for j in range(V) if any(j != i for i in qviews)]
-        lo, hi = need[0], need[-1] + 1   # contiguous view range (view 0 alone needs 1..V-1, views 1..V-1 need all)
-        yn = self._ln(f_all[lo * B * N: hi * B * N], blk.ny, 1e-6)
-        kv = self._lin(yn, blk.ckv, ar=True, ro=True, rope=(pos[:(hi - lo) * B], self._k.rope_tab, C))   # [(hi-lo)*B*N, 2C]
-        Nk = (V - 1) * N
-        if nq == 1 and B == 1:
-            ctx = kv       # views 1..V-1 of the single sample are already contiguous and in order
+        blks = (self.w.dec[0][l], self.w.dec[1][l])
+        R0, R = B * N, V * B * N
+        rows = ((0, R0), (R0, R))
+        pos, tab = self._k.pos_enc, self._k.rope_tab        # positions are the same for every image
+        split = lambda t: [t[a:b] for a, b in rows]
+        # ---- self-attention ----
+        h = torch.empty(R, C, device=self.dev)
+        for g, (a, b) in enumerate(rows):
+            self._ln(f[a:b], blks[g].n1, 1e-6, out=h[a:b])
+        qkv = torch.empty(R, 3 * C, device=self.dev)
+        self._lin2(split(h), [bk.qkv for bk in blks], outs=split(qkv), ar=True, ro=True, rope=(pos, tab, 2 * C))
+        att = torch.empty(R, C, device=self.dev)
+        if self.R:
+            ops.flash_attn_tc(qkv, 0, N * 3 * C, 3 * C, 3 * C, qkv, C, N * 3 * C, 3 * C, 3 * C, qkv, 2 * C, N * 3 * C, 3 * C, att, V * B, nh, N, N, 0.125,
+                              round_out=True)
         else:
-            ctx = torch.empty(Bq, Nk, 2 * C, device=self.dev)
-            for qi, i in enumerate(qviews):
+            ops.flash_attn_d64(qkv, 0, N * 3 * C, 3 * C, qkv, C, N * 3 * C, 3 * C, qkv, 2 * C, N * 3 * C, 3 * C, att, V * B, nh, N, N, 0.125, self.prec)
+        x1 = torch.empty(R, C, device=self.dev)
+        self._lin2(split(att), [bk.proj for bk in blks], outs=split(x1), ar=True, residuals=split(f))
+        # ---- cross-attention memory: k|v of the other views ----
+        if V == 2:
+            # stream 0 (view 0) attends to view 1, stream 1 (view 1) to view 0: memory rows are already image-aligned
+            yn = torch.empty(R, C, device=self.dev)
+            self._ln(f[R0:], blks[0].ny, 1e-6, out=yn[:R0])
+            self._ln(f[:R0], blks[1].ny, 1e-6, out=yn[R0:])
+            ctx = torch.empty(R, 2 * C, device=self.dev)
+            self._lin2(split(yn), [bk.ckv for bk in blks], outs=split(ctx), ar=True, ro=True, rope=(pos, tab, C))
+            Nk = N
+        else:
+            yn0 = self._ln(f[R0:], blks[0].ny, 1e-6)          # views 1..V-1 under stream-0 weights
+            yn1 = self._ln(f, blks[1].ny, 1e-6)               # all views under stream-1 weights
+            kv0 = torch.empty(R - R0, 2 * C, device=self.dev)
+            kv1 = torch.empty(R, 2 * C, device=self.dev)
+            self._lin2([yn0, yn1], [bk.ckv for bk in blks], outs=[kv0, kv1], ar=True, ro=True, rope=(pos, tab, C))
+            Nk = (V - 1) * N
+            ctx = torch.empty(V * B, Nk, 2 * C, device=self.dev)
+            for i in range(V):
                 for b in range(B):
                     slot = 0
                     for j in range(V):
                         if j == i:
                             continue
-                        r0 = ((j - lo) * B + b) * N
-                        ops.rows_affine(kv[r0:r0 + N], out=ctx[qi * B + b, slot * N:(slot + 1) * N])
+                        src = kv0[((j - 1) * B + b) * N:][:N] if i == 0 else kv1[(j * B + b) * N:][:N]
+                        ops.rows_affine(src, out=ctx[i * B + b, slot * N:(slot + 1) * N])
                         slot += 1
-        h2 = self._ln(x1, blk.n2, 1e-6)
-        q = self._lin(h2, blk.cq, ar=True, ro=True, rope=(pos_q, self._k.rope_tab, C))
-        a2 = torch.empty(Bq * N, C, device=self.dev)
+        h2 = torch.empty(R, C, device=self.dev)
+        for g, (a, b) in enumerate(rows):
+            self._ln(x1[a:b], blks[g].n2, 1e-6, out=h2[a:b])
+        q = torch.empty(R, C, device=self.dev)
+        self._lin2(split(h2), [bk.cq for bk in blks], outs=split(q), ar=True, ro=True, rope=(pos, tab, C))
+        a2 = torch.empty(R, C, device=self.dev)
         if self.R:
-            ops.flash_attn_tc(q, 0, N * C, C, C, ctx, 0, Nk * 2 * C, 2 * C, 2 * C, ctx, C, Nk * 2 * C, 2 * C, a2, Bq, nh, N, Nk, 0.125, round_out=True)
+            ops.flash_attn_tc(q, 0, N * C, C, C, ctx, 0, Nk * 2 * C, 2 * C, 2 * C, ctx, C, Nk * 2 * C, 2 * C, a2, V * B, nh, N, Nk, 0.125, round_out=True)
         else:
-            ops.flash_attn_d64(q, 0, N * C, C, ctx, 0, Nk * 2 * C, 2 * C, ctx, C, Nk * 2 * C, 2 * C, a2, Bq, nh, N, Nk, 0.125, self.prec)
-        self._lin(a2, blk.cproj, ar=True, residual=x1, out=x1)
-        h3 = self._ln(x1, blk.n3, 1e-6)
-        f = self._lin(h3, blk.fc1, ar=True, ro=True, act=ACT_GELU)
-        self._lin(f, blk.fc2, ar=True, residual=x1, out=x1)
+            ops.flash_attn_d64(q, 0, N * C, C, ctx, 0, Nk * 2 * C, 2 * C, ctx, C, Nk * 2 * C, 2 * C, a2, V * B, nh, N, Nk, 0.125, self.prec)
+        self._lin2(split(a2), [bk.cproj for bk in blks], outs=split(x1), ar=True, residuals=split(x1))
+        # ---- MLP ----
+        h3 = torch.empty(R, C, device=self.dev)
+        for g, (a, b) in enumerate(rows):
+            self._ln(x1[a:b], blks[g].n3, 1e-6, out=h3[a:b])
+        m = torch.empty(R, 4 * C, device=self.dev)
+        self._lin2(split(h3), [bk.fc1 for bk in blks], outs=split(m), ar=True, ro=True, act=ACT_GELU)
+        self._lin2(split(m), [bk.fc2 for bk in blks], outs=split(x1), ar=True, residuals=split(x1))
         return x1
 
     def _forward_device(self, imgs, Kin):
@@ -718,7 +730,6 @@ class SIU3RModel:
         post-process.  Images are batched view-major (image j = v*B + b) in both models."""
         B, V, _, S0, S1 = imgs.shape
         w, c = self.w, self.cfg
-        multi = self.multiview
         k = self._k = self._consts(B, S0, S1, V)
         gh, gw = S0 // 16, S1 // 16
         P, N = gh * gw, gh * gw + 1
@@ -771,37 +782,15 @@ class SIU3RModel:
         self._cap("enc_norm", feat)
         # ---- decoder ----
         f = self._lin(feat, w.dec_embed)  # [V*B*N, 768]
-        if not multi:
-            f1, f2 = f[:B * N], f[B * N:]
-            dec1, dec2 = [feat[:B * N]], [feat[B * N:]]
-            for l in range(c.dec_depth):
-                # the two views use different weights and only read the previous layer's pair: two parallel branches
-                n1, n2 = self._par([lambda: self._dec_block(w.dec[0][l], f1, f2, k.pos_dec, B, N),
-                                    lambda: self._dec_block(w.dec[1][l], f2, f1, k.pos_dec, B, N)])
-                f1, f2 = n1, n2
-                dec1.append(f1)
-                dec2.append(f2)
-                self._cap(f"dec1_{l}", f1)
-                self._cap(f"dec2_{l}", f2)
-            dec1[-1] = ops.layernorm(dec1[-1], w.dec_norm[0], w.dec_norm[1], 1e-6)
-            dec2[-1] = ops.layernorm(dec2[-1], w.dec_norm[0], w.dec_norm[1], 1e-6)
-            dec_first, dec_rest = dec1, dec2
-        else:
-            # V-view decoder: view 0 through dec_blocks, views 1..V-1 (one batch) through dec_blocks2; both read the previous
-            # layer's tokens of all views, so every layer writes into a fresh [V*B*N, 768] buffer
-            decs = [feat]
-            rest = list(range(1, V))
-            for l in range(c.dec_depth):
-                nxt = torch.empty(Bn * N, 768, device=self.dev)
-                fa = f
-                self._par([lambda: self._dec_block_multi(w.dec[0][l], fa[:B * N], fa, [0], k.pos_enc, B, N, V, nxt[:B * N]),
-                           lambda: self._dec_block_multi(w.dec[1][l], fa[B * N:], fa, rest, k.pos_enc, B, N, V, nxt[B * N:])])
-                f = nxt
-                decs.append(f)
-                self._cap(f"dec1_{l}", f[:B * N])
-                self._cap(f"dec2_{l}", f[B * N:])
-            decs[-1] = ops.layernorm(decs[-1], w.dec_norm[0], w.dec_norm[1], 1e-6)
-            dec_first, dec_rest = [t[:B * N] for t in decs], [t[B * N:] for t in decs]
+        # both decoder streams advance together: one grouped launch per projection, one flash launch per attention
+        decs = [feat]
+        for l in range(c.dec_depth):
+            f = self._dec_layer(l, f, B, N, V)
+            decs.append(f)
+            self._cap(f"dec1_{l}", f[:B * N])
+            self._cap(f"dec2_{l}", f[B * N:])
+        decs[-1] = ops.layernorm(decs[-1], w.dec_norm[0], w.dec_norm[1], 1e-6)
+        dec_first, dec_rest = [t[:B * N] for t in decs], [t[B * N:] for t in decs]
         self._mark("decoder")
         # ---- DPT heads: head1 on view 0, head2 on the other views (one batch); independent branches ----
         G1 = S0 * S1

@@ -169,6 +169,55 @@ def gemm(x: torch.Tensor, wt: Weight, out: torch.Tensor | None = None, act: int 
     return out
 
 
+def gemm_group2(xs, wts, outs=None, act: int = ACT_NONE, residuals=None, precision: int = PREC_TF32, a_rounded: bool = False,
+                round_out: bool = False, rope: tuple | None = None):
+    """Two linear layers of the same shape class (same N, K, strides, epilogue; rows may differ) in ONE persistent launch:
+    outs[g] = act(xs[g] @ wts[g]^T + bias_g) + residuals[g].  Falls back to two gemm() calls when the shape / precision is not
+    eligible for the grouped kernel (3xTF32 mode, tiny N or K, mismatching strides)."""
+    assert len(xs) == 2 and len(wts) == 2
+    if outs is None:
+        outs = [torch.empty(x.shape[0], w.N, device=x.device, dtype=torch.float32) for x, w in zip(xs, wts)]
+    residuals = residuals or [None, None]
+
+    def fallback():
+        for g in range(2):
+            r = None if rope is None else (rope[0].view(-1, 2)[: xs[g].shape[0]], rope[1], rope[2])   # positions repeat per image
+            gemm(xs[g], wts[g], out=outs[g], act=act, residual=residuals[g], precision=precision, a_rounded=a_rounded, round_out=round_out, rope=r)
+        return outs
+
+    w0, w1 = wts
+    ok = (precision == PREC_TF32 and w0.N == w1.N and w0.w.shape[1] == w1.w.shape[1] and xs[0].shape[1] == xs[1].shape[1]
+          and xs[0].stride(0) == xs[1].stride(0) and outs[0].stride(0) == outs[1].stride(0) and (w0.bias is None) == (w1.bias is None)
+          and (residuals[0] is None) == (residuals[1] is None) and xs[0].shape[1] % 4 == 0 and xs[0].stride(0) % 4 == 0
+          and all(x.data_ptr() % 16 == 0 and x.stride(1) == 1 for x in xs) and all(o.stride(1) == 1 for o in outs))
+    if ok and residuals[0] is not None:
+        ok = residuals[0].stride(0) == residuals[1].stride(0)
+    if not ok:
+        return fallback()
+    _chk_f32(*xs, *outs, *[r for r in residuals if r is not None])
+    if not a_rounded:
+        xs = [round_tf32(x) for x in xs]
+    a = act | (ACT_ROUND_TF32 if round_out else 0)
+    K = xs[0].shape[1]
+    Ms = (C.c_int * 2)(xs[0].shape[0], xs[1].shape[0])
+    arr = lambda ts: (C.c_void_p * 2)(*[t.data_ptr() for t in ts])
+    pos = tab = None
+    ncols = 0
+    if rope is not None:
+        pos, tab, ncols = rope[0], rope[1], rope[2]
+        assert residuals[0] is None and pos.dtype == torch.int64 and pos.is_contiguous() and pos.numel() >= 2 * max(Ms[0], Ms[1])
+    work = 2.0 * (Ms[0] + Ms[1]) * w0.N * K
+    with _Prof("gemm_tc", work):
+        code = _lib.load().siu3r_gemm_tc_group2(Ms, w0.N, K, arr(xs), xs[0].stride(0), arr([w0.w, w1.w]), w0.w.shape[1], arr(outs), outs[0].stride(0),
+                                                None if w0.bias is None else arr([w0.bias, w1.bias]),
+                                                None if residuals[0] is None else arr(residuals),
+                                                0 if residuals[0] is None else residuals[0].stride(0), a, 1.0, _p(pos), _p(tab), ncols, _stream())
+    if code == -4:
+        return fallback()
+    _lib.check(code, "gemm_tc_group2")
+    return outs
+
+
 def rope2d_table(maxpos: int, D: int = 64, base: float = 100.0, fwd: float = 1.0, device="cuda") -> torch.Tensor:
     """[maxpos, D/4, 2] (cos, sin) factors shared by every RoPE-fused projection (siu3r_gemm_tc_rope)."""
     tab = torch.empty(maxpos, D // 4, 2, device=device, dtype=torch.float32)

@@ -38,6 +38,17 @@ def main():
     for n, a in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
         extra = f" {a['dram'] / a['launches'] / 1e6:.2f} | {a['dram'] / max(a['ms'], 1e-9) / 1e6:.0f} |" if has_dram else ""
         print(f"| `{n}` | {a['launches']} | {a['ms']:.3f} | {100 * a['ms'] / tot:.1f}% |{extra}")
+    if "--traffic" in sys.argv:   # per-family DRAM bytes per launch -> profiles/r01_ncu_traffic.json (read by bench.py)
+        fams = {"gemm_tc": ("gemm_tc",), "flash_attn": ("flash_tc", "flash_attn"), "conv2d_tc": ()}
+        out = {}
+        for fam, keys in fams.items():
+            sel = [a for n, a in agg.items() if any(k in n for k in keys)]
+            if sel:
+                nl = sum(a["launches"] for a in sel)
+                out[fam] = {"dram_bytes_per_launch": sum(a["dram"] for a in sel) / nl, "launches": nl, "ms": sum(a["ms"] for a in sel),
+                            "source": "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum over tools/one_forward.py 512 tf32 "
+                                      "(all gemm_tc* launches: linear GEMMs and implicit-GEMM convs share the kernels)"}
+        json.dump(out, open(sys.argv[sys.argv.index("--traffic") + 1], "w"), indent=1)
     if "--json" in sys.argv:
         json.dump({"total_ms": tot, "kernels": agg}, open(sys.argv[sys.argv.index("--json") + 1], "w"), indent=1)
 

@@ -3,15 +3,14 @@
 //   O[b, n, h*64 + d] = softmax_k( Q K^T * scale ) V        replaces croco/blocks.py:105-109 (Attention) and :162-166
 //                                                            (CrossAttention) without materialising the N x N matrix.
 //
-// One CTA = 128 queries of one (batch, head); keys are visited in tiles of 128.
-//   warp 0   : TMA producer   Q tile once; per key tile K [128 keys x 64 d] and V^T [64 d x 128 keys] (both K-major, 128B-swizzled)
-//   warp 1   : MMA issuer     S = Q K^T   : tcgen05.mma kind::tf32 M=128 N=128 K=8 x 8   -> TMEM columns [0,128)
-//                             O += P V    : M=128 N=64 K=8 x 16 (A = P from shared memory)  -> TMEM columns [128,192)
-//   warps 2-5: softmax        one query row per thread (tcgen05.ld 32x32b gives exactly that: no shuffles);
-//                             P = exp2((S - m) * scale*log2e) rounded to TF32 and written into the swizzled K-major A-operand
-//                             layout in shared memory; finally O / l -> global through a shared-memory transpose.
-// Two passes over the key tiles: pass 1 only computes the row maxima m (S is recomputed in pass 2), so the O accumulator in
-// TMEM never needs rescaling -- QK^T is cheap on the tensor cores, a TMEM read-modify-write of O per tile is not.
+// One CTA = 128 queries of one (batch, head); keys are visited in tiles of 64, ONE pass (online softmax with lazy rescaling).
+//   warp 0   : TMA producer   Q tile once; per key tile K [64 keys x 64 d] and V^T [64 d x 64 keys] (K-major, 128B-swizzled), double-buffered
+//   warp 1   : MMA issuer     S = Q K^T   : tcgen05.mma kind::tf32 M=128 N=64 K=8 x 8    -> TMEM S/P buffer t % 3 (64 columns)
+//                             O += P V    : M=128 N=64 K=8 x 8, A = P read straight from TMEM -> TMEM columns [192,256)
+//   warps 2-5: softmax        one query row per thread (tcgen05.ld 32x32b gives exactly that: no shuffles); P = exp2(S*scale*log2e - m_ref)
+//                             written back over S in place with tcgen05.st (no shared-memory round trip); finally O / l -> global
+//                             through a shared-memory transpose.
+// 96 KB of shared memory + 256 TMEM columns per CTA -> two CTAs per SM.  See the comment above flash_tc_kernel for the rescaling rule.
 // V must be supplied transposed ([b*H + h][d][key], row pitch vt_ld) so that every UMMA operand is K-major:
 // siu3r_transpose_v produces it (and rounds it to TF32) from the fused qkv / kv buffer.
 #include <cuda.h>
@@ -22,14 +21,14 @@
 
 namespace {
 
-constexpr int FT_BM = 128, FT_BN = 128, FT_D = 64, FT_BK = 32;
+constexpr int FT_BM = 128, FT_BN = 64, FT_D = 64, FT_BK = 32;
 constexpr int FT_THREADS = 192;
-constexpr int FT_Q_BYTES = 2 * FT_BM * FT_BK * 4;        // 32 KB : 2 k-blocks [128 x 32]
-constexpr int FT_K_BYTES = 2 * FT_BN * FT_BK * 4;        // 32 KB per buffer, double-buffered
-constexpr int FT_V_BYTES = 4 * FT_D * FT_BK * 4;         // 32 KB : 4 k-blocks [64 d x 32 keys]
-constexpr int FT_P_BYTES = 4 * FT_BM * FT_BK * 4;        // 64 KB : 4 k-blocks [128 q x 32 keys]
-constexpr int FT_SMEM = FT_Q_BYTES + 2 * FT_K_BYTES + FT_V_BYTES + FT_P_BYTES + 1024 + 256;
-constexpr int FT_TMEM_COLS = 512;                        // S0: [0,128)  S1: [128,256)  O: [256,320)
+constexpr int FT_Q_BYTES = 2 * FT_BM * FT_BK * 4;        // 32 KB : 2 k-blocks [128 q x 32 d]
+constexpr int FT_K_BYTES = 2 * FT_BN * FT_BK * 4;        // 16 KB per buffer : 2 k-blocks [64 keys x 32 d], double-buffered
+constexpr int FT_V_BYTES = (FT_BN / FT_BK) * FT_D * FT_BK * 4;   // 16 KB per buffer : 2 k-blocks [64 d x 32 keys], double-buffered
+constexpr int FT_SMEM = FT_Q_BYTES + 2 * FT_K_BYTES + 2 * FT_V_BYTES + 1024 + 256;   // 97.3 KB -> two CTAs per SM
+constexpr int FT_TMEM_COLS = 256;                        // S/P 0..2: [0,64) [64,128) [128,192)   O: [192,256)
+static_assert(2 * FT_K_BYTES >= 4 * 32 * 36 * 4, "the epilogue transpose tiles alias the K buffers");
 
 struct FlashParams {
     int B, H, Nq, Nk;
@@ -120,26 +119,63 @@ __device__ __forceinline__ float4 lds_v4(uint32_t saddr) {
     return r;
 }
 
-// barrier indices (K / S barriers are double-buffered: index + buffer)
-enum { B_Q = 0, B_KFULL = 1, B_KEMPTY = 3, B_SFULL = 5, B_SEMPTY = 7, B_VFULL = 9, B_VEMPTY, B_PFULL, B_OFULL, B_COUNT };
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+        "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]),
+        "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] * B[smem desc]: the A operand (P, one query row per lane, one key per 32-bit column) stays in tensor memory
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
-__global__ void __launch_bounds__(FT_THREADS, 1)
+// barrier indices (double-buffered ones: index + buffer)
+// K / V tiles are double-buffered, the S/P accumulator is TRIPLE-buffered: P(t) aliases S(t), so with two buffers S(t+1) could only be
+// issued after P(t-1) V(t-1) had completed, i.e. the softmax warps waited one full MMA round trip per tile (ncu: 15 % of all stall samples on the
+// S-ready wait).  With three, S(t+1) only needs P(t-2) V(t-2), which finished a whole tile earlier.
+enum { B_Q = 0, B_KFULL = 1, B_KEMPTY = 3, B_SFULL = 5, B_PFULL = 8, B_VFULL = 11, B_VFREE = 13, B_SFREE = 15, B_OFULL = 18, B_COUNT };
+
+// Single pass, online softmax with LAZY rescaling: the running reference maximum m_ref (log2 domain) of a row is only raised when the
+// tile maximum exceeds it by more than 8, so P = exp2(s - m_ref) <= 256 stays exact in fp32 / TF32 and the O accumulator in TMEM
+// is read-modify-written only when some row of the warp actually moves its reference (first tile aside, almost never).
+// softmax is shift invariant, so the result is the exact softmax(QK^T)V -- O and l carry the same factor.
+//   S(t) = Q K_t^T        -> TMEM buffer t&1 (64 fp32 columns)
+//   P(t) overwrites S(t) in place (thread = query row = TMEM lane), RN-TF32, and is the A operand of O += P(t) V_t straight from TMEM
+//   K / V^T tiles of 64 keys by TMA, both double-buffered; 96 KB of shared memory and 256 TMEM columns -> two CTAs per SM, so one
+//   CTA's exponentials (MUFU-bound: 64 per row and tile) overlap the other's MMAs.
+__global__ void __launch_bounds__(FT_THREADS, 2)
 flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmVt,
                 const FlashParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sQ = smem;
     uint8_t* sK = sQ + FT_Q_BYTES;            // 2 buffers
-    uint8_t* sV = sK + 2 * FT_K_BYTES;
-    uint8_t* sP = sV + FT_V_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + FT_P_BYTES);
+    uint8_t* sV = sK + 2 * FT_K_BYTES;        // 2 buffers
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * FT_V_BYTES);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_COUNT);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
     const int q0 = qt * FT_BM;
     const int ntiles = (p.Nk + FT_BN - 1) / FT_BN;
-    const int niter = 2 * ntiles;             // pass 1 (row maxima) then pass 2 (P, O)
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQ) : "memory");
@@ -148,10 +184,12 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_init(&bars[B_Q], 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&bars[B_KFULL + i], 1); mbar_init(&bars[B_KEMPTY + i], 1);
-            mbar_init(&bars[B_SFULL + i], 1); mbar_init(&bars[B_SEMPTY + i], 4);   // one arrival per softmax warp
+            mbar_init(&bars[B_VFULL + i], 1); mbar_init(&bars[B_VFREE + i], 1);
         }
-        mbar_init(&bars[B_VFULL], 1); mbar_init(&bars[B_VEMPTY], 1);
-        mbar_init(&bars[B_PFULL], 4);
+        for (int i = 0; i < 3; ++i) {
+            mbar_init(&bars[B_SFULL + i], 1); mbar_init(&bars[B_PFULL + i], 4);     // one arrival per softmax warp
+            mbar_init(&bars[B_SFREE + i], 1);
+        }
         mbar_init(&bars[B_OFULL], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -163,7 +201,7 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_O = tmem_base + 256;
+    const uint32_t tmem_O = tmem_base + 3 * FT_BN;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -171,129 +209,139 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             mbar_expect_tx(&bars[B_Q], FT_Q_BYTES);
             tma_load_3d(&tmQ, &bars[B_Q], sQ, p.q_col0 + h * FT_D, q0, b);
             tma_load_3d(&tmQ, &bars[B_Q], sQ + FT_BM * FT_BK * 4, p.q_col0 + h * FT_D + FT_BK, q0, b);
-            uint32_t vcnt = 0;
-            for (int it = 0; it < niter; ++it) {
-                const int t = it < ntiles ? it : it - ntiles;
-                const int buf = it & 1;
-                const uint32_t use = (uint32_t)it >> 1;
+            for (int t = 0; t < ntiles; ++t) {
+                const int buf = t & 1;
+                const uint32_t use = (uint32_t)t >> 1;
                 mbar_wait(&bars[B_KEMPTY + buf], (use & 1) ^ 1);
                 uint8_t* dK = sK + buf * FT_K_BYTES;
                 mbar_expect_tx(&bars[B_KFULL + buf], FT_K_BYTES);
                 tma_load_3d(&tmK, &bars[B_KFULL + buf], dK, p.k_col0 + h * FT_D, t * FT_BN, b);
                 tma_load_3d(&tmK, &bars[B_KFULL + buf], dK + FT_BN * FT_BK * 4, p.k_col0 + h * FT_D + FT_BK, t * FT_BN, b);
-                if (it >= ntiles) {
-                    mbar_wait(&bars[B_VEMPTY], (vcnt & 1) ^ 1);
-                    mbar_expect_tx(&bars[B_VFULL], FT_V_BYTES);
+                mbar_wait(&bars[B_VFREE + buf], (use & 1) ^ 1);      // P V of tile t-2 has read this V buffer
+                uint8_t* dV = sV + buf * FT_V_BYTES;
+                mbar_expect_tx(&bars[B_VFULL + buf], FT_V_BYTES);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        tma_load_2d(&tmVt, &bars[B_VFULL], sV + j * FT_D * FT_BK * 4, t * FT_BN + j * FT_BK, (b * p.H + h) * FT_D);
-                    ++vcnt;
-                }
+                for (int j = 0; j < FT_BN / FT_BK; ++j)
+                    tma_load_2d(&tmVt, &bars[B_VFULL + buf], dV + j * FT_D * FT_BK * 4, t * FT_BN + j * FT_BK, (b * p.H + h) * FT_D);
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer (S of tile it+1 is issued before the P V of tile it) =====================
+        // ===================== MMA issuer: S(t+1) is issued before P(t) V(t) =====================
         if (lane == 0) {
             constexpr uint32_t idesc_s = make_idesc_tf32(FT_BM, FT_BN);
             constexpr uint32_t idesc_o = make_idesc_tf32(FT_BM, FT_D);
             mbar_wait(&bars[B_Q], 0);
-            auto issue_s = [&](int it) {
-                const int buf = it & 1;
-                const uint32_t use = (uint32_t)it >> 1;
+            auto issue_s = [&](int t) {
+                const int buf = t & 1, sb = t % 3;
+                const uint32_t use = (uint32_t)t >> 1;
                 mbar_wait(&bars[B_KFULL + buf], use & 1);
-                mbar_wait(&bars[B_SEMPTY + buf], (use & 1) ^ 1);   // softmax finished reading the previous S in this buffer
+                mbar_wait(&bars[B_SFREE + sb], (((uint32_t)t / 3) & 1) ^ 1);   // P(t-3) (aliasing this S buffer) has been consumed
                 tc_fence_after();
                 const uint32_t kb = smem_u32(sK + buf * FT_K_BYTES);
 #pragma unroll
                 for (int ks = 0; ks < FT_D / 8; ++ks) {
                     const uint32_t blk = (ks >> 2), koff = (ks & 3) * 32;
-                    umma_tf32(tmem_base + (uint32_t)buf * 128, make_smem_desc(smem_u32(sQ) + blk * FT_BM * FT_BK * 4 + koff),
+                    umma_tf32(tmem_base + (uint32_t)(sb * FT_BN), make_smem_desc(smem_u32(sQ) + blk * FT_BM * FT_BK * 4 + koff),
                               make_smem_desc(kb + blk * FT_BN * FT_BK * 4 + koff), idesc_s, ks != 0);
                 }
                 umma_commit(&bars[B_KEMPTY + buf]);   // K buffer reusable
-                umma_commit(&bars[B_SFULL + buf]);    // S ready
+                umma_commit(&bars[B_SFULL + sb]);     // S ready
             };
             issue_s(0);
-            uint32_t vcnt = 0;
-            for (int it = 0; it < niter; ++it) {
-                if (it + 1 < niter) issue_s(it + 1);
-                if (it >= ntiles) {
-                    mbar_wait(&bars[B_VFULL], vcnt & 1);
-                    mbar_wait(&bars[B_PFULL], vcnt & 1);   // P written (and fenced) by the softmax warps
-                    tc_fence_after();
+            for (int t = 0; t < ntiles; ++t) {
+                if (t + 1 < ntiles) issue_s(t + 1);
+                const int buf = t & 1, sb = t % 3;
+                const uint32_t use = (uint32_t)t >> 1;
+                mbar_wait(&bars[B_VFULL + buf], use & 1);
+                mbar_wait(&bars[B_PFULL + sb], ((uint32_t)t / 3) & 1);   // P written (and, if needed, O rescaled) by the softmax warps
+                tc_fence_after();
+                const uint32_t vb = smem_u32(sV + buf * FT_V_BYTES);
 #pragma unroll
-                    for (int ks = 0; ks < FT_BN / 8; ++ks) {
-                        const uint32_t blk = (ks >> 2), koff = (ks & 3) * 32;
-                        umma_tf32(tmem_O, make_smem_desc(smem_u32(sP) + blk * FT_BM * FT_BK * 4 + koff),
-                                  make_smem_desc(smem_u32(sV) + blk * FT_D * FT_BK * 4 + koff), idesc_o, (vcnt | ks) != 0);
-                    }
-                    umma_commit(&bars[B_VEMPTY]);   // V tile and P buffer reusable once these MMAs are done
-                    ++vcnt;
+                for (int ks = 0; ks < FT_BN / 8; ++ks) {
+                    const uint32_t blk = (ks >> 2), koff = (ks & 3) * 32;
+                    umma_tf32_ts(tmem_O, tmem_base + (uint32_t)(sb * FT_BN + ks * 8), make_smem_desc(vb + blk * FT_D * FT_BK * 4 + koff), idesc_o,
+                                 (t | ks) != 0);
                 }
+                umma_commit(&bars[B_VFREE + buf]);    // V buffer ...
+                umma_commit(&bars[B_SFREE + sb]);     // ... and the S/P buffer reusable once these MMAs are done
             }
             umma_commit(&bars[B_OFULL]);
         }
     } else {
         // ===================== softmax / epilogue warps: thread = one query row =====================
         const int qd = warp & 3;                 // TMEM lane quarter
-        const int r = qd * 32 + lane;            // row in the tile
-        float m = -INFINITY, l = 0.f;
-        uint32_t vcnt = 0;
-        for (int it = 0; it < niter; ++it) {
-            const int t = it < ntiles ? it : it - ntiles;
-            const int buf = it & 1;
-            const uint32_t tS = tmem_base + (uint32_t)buf * 128 + ((uint32_t)(qd * 32) << 16);
-            mbar_wait(&bars[B_SFULL + buf], ((uint32_t)it >> 1) & 1);
+        const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
+        float m_ref = -INFINITY, l = 0.f;        // m_ref in the log2 domain (already multiplied by scale * log2 e)
+        for (int t = 0; t < ntiles; ++t) {
+            const int sb = t % 3;
+            const uint32_t tS = tmem_base + (uint32_t)(sb * FT_BN) + lane_off;
+            mbar_wait(&bars[B_SFULL + sb], ((uint32_t)t / 3) & 1);
             tc_fence_after();
-            const int kvalid = p.Nk - t * FT_BN;   // columns >= kvalid are padding
-            if (it < ntiles) {
-#pragma unroll 1
-                for (int c0 = 0; c0 < FT_BN; c0 += 32) {
-                    uint32_t v[32];
-                    tmem_ld32(tS + c0, v);
-                    tmem_ld_wait();
+            uint32_t v0[32], v1[32];
+            tmem_ld32(tS, v0);
+            tmem_ld32(tS + 32, v1);
+            tmem_ld_wait();
+            const int kvalid = p.Nk - t * FT_BN;   // columns >= kvalid are padding (only ever on the last tile)
+            if (kvalid < FT_BN) {                   // -inf scores: they drop out of the maximum and exponentiate to exactly 0
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (c0 + j < kvalid) m = fmaxf(m, __uint_as_float(v[j]));
+                for (int j = 0; j < 32; ++j) {
+                    if (j >= kvalid) v0[j] = 0xff800000u;
+                    if (32 + j >= kvalid) v1[j] = 0xff800000u;
                 }
-            } else {
-                const float ms = m * p.scale_log2e;
-#pragma unroll 1
-                for (int c0 = 0; c0 < FT_BN; c0 += 32) {
-                    uint32_t v[32];
-                    tmem_ld32(tS + c0, v);
-                    tmem_ld_wait();
-                    float pv[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float e = (c0 + j < kvalid) ? exp2f(__uint_as_float(v[j]) * p.scale_log2e - ms) : 0.f;
-                        pv[j] = rn_tf32(e);
-                        l += pv[j];
-                    }
-                    // the P buffer is shared by consecutive tiles: wait for the previous tile's P V only now, after the first exps
-                    if (c0 == 0 && vcnt > 0) mbar_wait(&bars[B_VEMPTY], (vcnt - 1) & 1);
-                    // k-block c0/32 of P: row r, 128 B per row, 16-byte chunk c stored at chunk (c ^ (r & 7))
-                    const uint32_t rowaddr = smem_u32(sP) + (uint32_t)(c0 / 32) * FT_BM * FT_BK * 4 + (uint32_t)r * 128;
-#pragma unroll
-                    for (int c = 0; c < 8; ++c)
-                        sts_v4(rowaddr + (uint32_t)((c ^ (r & 7)) * 16), pv[4 * c], pv[4 * c + 1], pv[4 * c + 2], pv[4 * c + 3]);
-                }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA (async proxy)
-                ++vcnt;
             }
+            float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // four independent chains
+#pragma unroll
+            for (int j = 0; j < 32; ++j) mx[j & 3] = fmaxf(mx[j & 3], fmaxf(__uint_as_float(v0[j]), __uint_as_float(v1[j])));
+            const float mt = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+            const float m_new = fmaxf(m_ref, mt * p.scale_log2e);
+            const bool need = m_new > m_ref + 8.0f;          // also true on the first tile (m_ref = -inf)
+            if (__any_sync(0xffffffffu, need)) {
+                const float factor = need ? ex2_approx(m_ref - m_new) : 1.0f;   // 0 on the first tile (l = 0, O not yet written)
+                if (t > 0) {
+                    // O is about to be rescaled: P(t-1) V(t-1) (and every earlier MMA into O) must have completed
+                    mbar_wait(&bars[B_SFREE + ((t - 1) % 3)], ((uint32_t)(t - 1) / 3) & 1);
+                    tc_fence_after();
+                    const uint32_t tO = tmem_O + lane_off;
+#pragma unroll 1
+                    for (int c0 = 0; c0 < FT_D; c0 += 32) {
+                        uint32_t o[32];
+                        tmem_ld32(tO + c0, o);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * factor);
+                        tmem_st32(tO + c0, o);
+                    }
+                    tmem_st_wait();
+                }
+                l *= factor;
+                if (need) m_ref = m_new;
+            }
+            // P = exp2(s * scale*log2e - m_ref) in (0, 256].  The tensor core truncates its fp32 A operand to TF32, so adding half a
+            // TF32 ulp (0x1000) to the bit pattern here makes that truncation a round-to-nearest (what cvt.rna.tf32 does, minus its
+            // inf / NaN guard: P is finite).  l sums the unrounded values: the difference is an unbiased 2^-12 relative noise.
+            float ls[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float e0 = ex2_approx(__uint_as_float(v0[j]) * p.scale_log2e - m_ref);
+                const float e1 = ex2_approx(__uint_as_float(v1[j]) * p.scale_log2e - m_ref);
+                ls[j & 3] += e0 + e1;
+                v0[j] = __float_as_uint(e0) + 0x1000u;
+                v1[j] = __float_as_uint(e1) + 0x1000u;
+            }
+            l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
+            tmem_st32(tS, v0);          // P(t) over S(t): same lane, same columns
+            tmem_st32(tS + 32, v1);
+            tmem_st_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) {
-                if (it >= ntiles) mbar_arrive(&bars[B_PFULL]);
-                mbar_arrive(&bars[B_SEMPTY + buf]);
-            }
+            if (lane == 0) mbar_arrive(&bars[B_PFULL + sb]);
         }
-        // ---- epilogue: O / l -> global (transposed through the now idle P buffer for 128-byte coalesced stores) ----
+        // ---- epilogue: O / l -> global (transposed through the now idle K buffers for 128-byte coalesced stores) ----
         mbar_wait(&bars[B_OFULL], 0);
         tc_fence_after();
         const float inv = 1.f / l;
-        const uint32_t tO = tmem_O + ((uint32_t)(qd * 32) << 16);
-        const uint32_t tr = smem_u32(sP) + (uint32_t)qd * (32 * 36 * 4);
+        const uint32_t tO = tmem_O + lane_off;
+        const uint32_t tr = smem_u32(sK) + (uint32_t)qd * (32 * 36 * 4);
         float* Ob = p.O + (int64_t)b * p.o_bs + (int64_t)h * FT_D;
 #pragma unroll 1
         for (int c0 = 0; c0 < FT_D; c0 += 32) {

@@ -24,8 +24,9 @@ elif which == "flash":
     qkv = torch.randn(B, N, 3, H, 64, device=dev)
     out = torch.empty(B, N, H * 64, device=dev)
     bs, ts = N * 3 * H * 64, 3 * H * 64
+    C_ = H * 64
     for _ in range(3):
-        ops.flash_attn_d64(qkv, 0, bs, ts, qkv, H * 64, bs, ts, qkv, 2 * H * 64, bs, ts, out, B, H, N, N, 0.125, 1)
+        ops.flash_attn_tc(qkv, 0, bs, ts, 3 * C_, qkv, C_, bs, ts, 3 * C_, qkv, 2 * C_, bs, ts, out, B, H, N, N, 0.125)
 elif which == "raster":
     G, H, W = 500000, 512, 512
     sc = synth.raster_scene(G, H, W, seed=0, pixel_aligned=True)

@@ -310,7 +310,10 @@ __device__ __forceinline__ void run_epilogue(uint32_t tmem_base, uint32_t tr, in
     }
 }
 
-template <int BN, int NSPLIT>
+// DEEP: one CTA per SM with the whole shared memory as pipeline (TF32 mode).  Used when the grid has fewer CTAs than SMs anyway
+// (the 3x3 convs of the DPT fusion stages at 16^2 .. 64^2: 8-64 CTAs x 72 k-blocks each): such launches are bound by the TMA round
+// trip per stage, so twice the stages in flight is close to twice the speed.
+template <int BN, int NSPLIT, bool DEEP = false>
 struct Cfg {
     static constexpr int NOPER = NSPLIT == 1 ? 1 : 2;  // hi (+ lo) planes per operand
     static constexpr int A_BYTES = BM * BK * 4;
@@ -318,9 +321,9 @@ struct Cfg {
     static constexpr int STAGE_BYTES = NOPER * (A_BYTES + B_BYTES);
     // TF32: <= 96 KB of stages so that TWO CTAs fit per SM (one CTA's epilogue overlaps the other's mainloop; 2 x 256 TMEM
     // columns).  3xTF32 needs all 512 TMEM columns -> one CTA per SM, deeper pipeline.
-    static constexpr int BUDGET = NSPLIT == 1 ? 96 * 1024 : 208 * 1024;
-    static constexpr int STAGES = BUDGET / STAGE_BYTES > 8 ? 8 : BUDGET / STAGE_BYTES;
-    static constexpr int CTAS_PER_SM = NSPLIT == 1 ? 2 : 1;
+    static constexpr int BUDGET = (NSPLIT == 1 && !DEEP) ? 96 * 1024 : 208 * 1024;
+    static constexpr int STAGES = BUDGET / STAGE_BYTES > 10 ? 10 : BUDGET / STAGE_BYTES;
+    static constexpr int CTAS_PER_SM = (NSPLIT == 1 && !DEEP) ? 2 : 1;
     // the epilogue's transpose tiles (4 x 4.5 KB) alias the pipeline stages: the mainloop is over when the accumulator is ready
     static_assert(STAGES * STAGE_BYTES >= 4 * EPI_TR_FLOATS * 4, "stage memory must cover the epilogue tiles");
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
@@ -331,11 +334,11 @@ struct Cfg {
     static constexpr int TMEM_COLS = NACC * BN < 32 ? 32 : NACC * BN;
 };
 
-template <int BN, int NSPLIT>
-__global__ void __launch_bounds__(NUM_THREADS, (NSPLIT == 1 ? 2 : 1))
+template <int BN, int NSPLIT, bool DEEP = false>
+__global__ void __launch_bounds__(NUM_THREADS, ((NSPLIT == 1 && !DEEP) ? 2 : 1))
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo, const GemmParams p) {
-    using C_ = Cfg<BN, NSPLIT>;
+    using C_ = Cfg<BN, NSPLIT, DEEP>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C_::STAGES * C_::STAGE_BYTES);
@@ -913,16 +916,16 @@ int make_map(CUtensorMap* map, const float* base, int rank, const uint64_t* dims
     return SIU3R_OK;
 }
 
-template <int BN, int NSPLIT>
+template <int BN, int NSPLIT, bool DEEP = false>
 int launch(const CUtensorMap& a, const CUtensorMap& alo, const CUtensorMap& b, const CUtensorMap& blo, const GemmParams& p, dim3 grid,
            cudaStream_t stream) {
-    using C_ = Cfg<BN, NSPLIT>;
+    using C_ = Cfg<BN, NSPLIT, DEEP>;
     static bool attr_set = false;
     if (!attr_set) {
-        SIU3R_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM_BYTES));
+        SIU3R_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, NSPLIT, DEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM_BYTES));
         attr_set = true;
     }
-    gemm_tc_kernel<BN, NSPLIT><<<grid, NUM_THREADS, C_::SMEM_BYTES, stream>>>(a, alo, b, blo, p);
+    gemm_tc_kernel<BN, NSPLIT, DEEP><<<grid, NUM_THREADS, C_::SMEM_BYTES, stream>>>(a, alo, b, blo, p);
     SIU3R_LAUNCH_CHECK();
     siu3r_note_launch(1);
     return SIU3R_OK;
@@ -1060,9 +1063,10 @@ static int gemm_tc_impl(int M, int N, int K, const float* A, const float* A_lo, 
     p.rope_pos = (const long long*)rope_pos; p.rope_tab = rope_tab; p.rope_cols = rope_cols;
     dim3 grid((unsigned)mtiles, (unsigned)ceil_div(N, bn));
     if (precision == 1) {
+        const bool deep = (int64_t)grid.x * grid.y <= 148 && p.num_kb >= 16;   // under-filled, long K loop: latency-bound
         if (bn == 256) return launch<256, 1>(ma, malo, mb, mblo, p, grid, stream);
-        if (bn == 128) return launch<128, 1>(ma, malo, mb, mblo, p, grid, stream);
-        return launch<64, 1>(ma, malo, mb, mblo, p, grid, stream);
+        if (bn == 128) return deep ? launch<128, 1, true>(ma, malo, mb, mblo, p, grid, stream) : launch<128, 1>(ma, malo, mb, mblo, p, grid, stream);
+        return deep ? launch<64, 1, true>(ma, malo, mb, mblo, p, grid, stream) : launch<64, 1>(ma, malo, mb, mblo, p, grid, stream);
     }
     if (bn == 128) return launch<128, 3>(ma, malo, mb, mblo, p, grid, stream);
     return launch<64, 3>(ma, malo, mb, mblo, p, grid, stream);
@@ -1170,9 +1174,10 @@ int siu3r_conv2d_tc(int Nimg, int H, int W, int Cin, int Cout, int KH, int KW, i
     p.tiles_w = tiles_w; p.tiles_h = tiles_h;
     dim3 grid((unsigned)mtiles, (unsigned)ceil_div(Cout, bn));
     if (precision == 1) {
+        const bool deep = (int64_t)grid.x * grid.y <= 148 && p.num_kb >= 16;   // under-filled, long K loop: latency-bound
         if (bn == 256) return launch<256, 1>(ma, malo, mb, mblo, p, grid, stream);
-        if (bn == 128) return launch<128, 1>(ma, malo, mb, mblo, p, grid, stream);
-        return launch<64, 1>(ma, malo, mb, mblo, p, grid, stream);
+        if (bn == 128) return deep ? launch<128, 1, true>(ma, malo, mb, mblo, p, grid, stream) : launch<128, 1>(ma, malo, mb, mblo, p, grid, stream);
+        return deep ? launch<64, 1, true>(ma, malo, mb, mblo, p, grid, stream) : launch<64, 1>(ma, malo, mb, mblo, p, grid, stream);
     }
     if (bn == 128) return launch<128, 3>(ma, malo, mb, mblo, p, grid, stream);
     return launch<64, 3>(ma, malo, mb, mblo, p, grid, stream);

@@ -182,34 +182,61 @@ __global__ void __launch_bounds__(256) attn_mask_kernel(const float* __restrict_
     mask[(((int64_t)bidx * Q + q) * T + tt) * oh_ * ow_ + (int64_t)oh * ow_ + ow] = sg < 0.5f ? 1 : 0;
 }
 
-// Plain fp32 (FFMA) GEMM: C = act(alpha * A W^T + bias) + residual.  Shape-agnostic fallback for tiny / odd shapes
-// (K = 9 intrinsics encoder, backbone_croco.py:59) and the on-device cross-check of the tensor-core path.
-constexpr int SG_T = 16;
-__global__ void __launch_bounds__(SG_T* SG_T) gemm_simt_kernel(int M, int N, int K, const float* __restrict__ A, int64_t lda,
-                                                              const float* __restrict__ W, int64_t ldw, float* __restrict__ C, int64_t ldc,
-                                                              const float* __restrict__ bias, const float* __restrict__ res, int64_t ldr, int act,
-                                                              float alpha) {
-    __shared__ float sA[SG_T][SG_T + 1], sW[SG_T][SG_T + 1];
-    const int tx = threadIdx.x % SG_T, ty = threadIdx.x / SG_T;
-    const int m = blockIdx.y * SG_T + ty, n = blockIdx.x * SG_T + tx;
-    float acc = 0.f;
-    for (int k0 = 0; k0 < K; k0 += SG_T) {
-        const int ka = k0 + tx;
-        sA[ty][tx] = (m < M && ka < K) ? A[(int64_t)m * lda + ka] : 0.f;
-        const int nw = blockIdx.x * SG_T + ty;
-        sW[ty][tx] = (nw < N && ka < K) ? W[(int64_t)nw * ldw + ka] : 0.f;
+// Plain fp32 (FFMA) GEMM: C = act(alpha * A W^T + bias) + residual.  Shape-agnostic path for tiny / odd shapes: the K = 9 intrinsics
+// encoder (backbone_croco.py:59) and the ~80 GEMMs per pair with M <= 128 rows (the 100 Mask2Former queries,
+// video_seg_decoder.py:957-1025,1423-1480), whose cost on the tensor-core kernels is pure launch / TMEM / TMA set-up latency.
+// 32 x 64 output tile per CTA, 2 x 4 outputs per thread, operands staged K-major-transposed in shared memory.
+constexpr int SG_M = 32, SG_N = 64, SG_K = 16;
+__global__ void __launch_bounds__(256) gemm_simt_kernel(int M, int N, int K, const float* __restrict__ A, int64_t lda,
+                                                        const float* __restrict__ W, int64_t ldw, float* __restrict__ C, int64_t ldc,
+                                                        const float* __restrict__ bias, const float* __restrict__ res, int64_t ldr, int act,
+                                                        float alpha) {
+    __shared__ float sA[SG_K][SG_M + 4];
+    __shared__ __align__(16) float sW[SG_K][SG_N + 4];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int m0 = blockIdx.y * SG_M, n0 = blockIdx.x * SG_N;
+    float acc[2][4] = {};
+    const int ar = tid >> 3, ak = (tid & 7) * 2;        // A tile: 32 rows x 16 k, two k per thread
+    const int wr = tid >> 2, wk = (tid & 3) * 4;        // W tile: 64 rows x 16 k, four k per thread
+    for (int k0 = 0; k0 < K; k0 += SG_K) {
+        {
+            const int m = m0 + ar;
+            const float* ap = A + (int64_t)m * lda + k0 + ak;
+            sA[ak][ar] = (m < M && k0 + ak < K) ? ap[0] : 0.f;
+            sA[ak + 1][ar] = (m < M && k0 + ak + 1 < K) ? ap[1] : 0.f;
+            const int n = n0 + wr;
+            const float* wp = W + (int64_t)n * ldw + k0 + wk;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) sW[wk + j][wr] = (n < N && k0 + wk + j < K) ? wp[j] : 0.f;
+        }
         __syncthreads();
 #pragma unroll
-        for (int k = 0; k < SG_T; ++k) acc = fmaf(sA[ty][k], sW[tx][k], acc);
+        for (int k = 0; k < SG_K; ++k) {
+            const float a0 = sA[k][ty * 2], a1 = sA[k][ty * 2 + 1];
+            const float4 w = *reinterpret_cast<const float4*>(&sW[k][tx * 4]);
+            acc[0][0] = fmaf(a0, w.x, acc[0][0]); acc[0][1] = fmaf(a0, w.y, acc[0][1]); acc[0][2] = fmaf(a0, w.z, acc[0][2]); acc[0][3] = fmaf(a0, w.w, acc[0][3]);
+            acc[1][0] = fmaf(a1, w.x, acc[1][0]); acc[1][1] = fmaf(a1, w.y, acc[1][1]); acc[1][2] = fmaf(a1, w.z, acc[1][2]); acc[1][3] = fmaf(a1, w.w, acc[1][3]);
+        }
         __syncthreads();
     }
-    if (m < M && n < N) {
-        float x = acc * alpha;
-        if (bias) x += bias[n];
-        if (act == 1) x = 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
-        else if (act == 2) x = fmaxf(x, 0.f);
-        if (res) x += res[(int64_t)m * ldr + n];
-        C[(int64_t)m * ldc + n] = x;
+    const bool rnd = (act & 4) != 0;
+    const int a = act & 3;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int m = m0 + ty * 2 + i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n >= N) continue;
+            float x = acc[i][j] * alpha;
+            if (bias) x += bias[n];
+            if (a == 1) x = 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+            else if (a == 2) x = fmaxf(x, 0.f);
+            if (res) x += res[(int64_t)m * ldr + n];
+            if (rnd) { uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); x = __uint_as_float(r); }
+            C[(int64_t)m * ldc + n] = x;
+        }
     }
 }
 
@@ -331,8 +358,8 @@ int siu3r_gemm_simt(int M, int N, int K, const float* A, int64_t lda, const floa
                     const float* residual, int64_t ldr, int act, float alpha, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     SIU3R_REQUIRE(M > 0 && N > 0 && K > 0 && A && W && C);
-    dim3 grid(ceil_div(N, SG_T), ceil_div(M, SG_T));
-    gemm_simt_kernel<<<grid, SG_T * SG_T, 0, stream>>>(M, N, K, A, lda, W, ldw, C, ldc, bias, residual, ldr, act, alpha);
+    dim3 grid(ceil_div(N, SG_N), ceil_div(M, SG_M));
+    gemm_simt_kernel<<<grid, 256, 0, stream>>>(M, N, K, A, lda, W, ldw, C, ldc, bias, residual, ldr, act, alpha);
     SIU3R_LAUNCH_CHECK();
     siu3r_note_launch(1);
     return SIU3R_OK;

@@ -44,6 +44,13 @@ int siu3r_raster_forward(int G, int H, int W, int sh_degree, int sh_coeffs, int 
                          uint32_t* debug_offsets, uint64_t* debug_keys, uint32_t* debug_values, uint32_t* debug_ranges,
                          void* stream);
 
+/* N-channel feature splatting: replaces gsplat.rasterization(means, quats=None, scales=None, covars, opacities, colors[N,C], viewmats,
+ * Ks, width, height, sh_degree=None, near_plane, far_plane) as called at src/models/gaussian_renderer.py:92-106 (one camera per call).
+ * viewmat = world-to-camera 4x4 row-major (device); intr_host = (fx, fy, cx, cy) in pixels (host); out_features [H,W,C], out_alpha [H,W]. */
+int siu3r_raster_features_forward(int G, int H, int W, int C, int cov_stride, const float* means3D, const float* cov, const float* opacities,
+                                  const float* features, const float* viewmat, const float* intr_host, float near_plane, float far_plane,
+                                  float* out_features, float* out_alpha, int32_t* radii_xy, void* workspace, int64_t workspace_bytes,
+                                  int64_t dup_capacity, int64_t* num_rendered_host, void* stream);
 /* testing aid: 0 disables the blend kernel's exact sub-tile culling (every pixel then evaluates every record of its tile, the
  * literal loop of the reference rasterizer); results must be bit-identical either way (tests/test_ops_gpu.py) */
 void siu3r_raster_set_culling(int enabled);

@@ -443,6 +443,203 @@ __global__ void __launch_bounds__(RB) render_kernel(int W, int H, int gx, const 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// N-channel ("feature") splatting: what the reference obtains from gsplat.rasterization(means, covars, opacities, colors[N,C],
+// viewmats, Ks, width, height, near_plane, far_plane) at src/models/gaussian_renderer.py:92-106 to render the per-Gaussian
+// query x class logits.  gsplat (1.5.2, un-vendored) is NOT available offline: this follows its published classic-mode algorithm
+// (projection with the 0.3-px blur, opacity-aware 3.33-sigma extents, 16x16 tiles, alpha = min(0.999, o exp(-sigma)), alpha < 1/255
+// skipped, stop before T <= 1e-4, pixel centres at +0.5) -- PARITY UNPINNED, see oracle/gsplat_ref.py.  Binning, scan, sort and tile
+// ranges are shared with the colour rasterizer above.
+// ---------------------------------------------------------------------------------------------------------------
+struct FeatCam { float V[16]; float fx, fy, cx, cy, near_plane, far_plane; };
+
+__global__ void __launch_bounds__(128) preprocess_feat_kernel(int G, int H, int W, int gx, int gy, int cov_stride, const float* __restrict__ means,
+                                                              const float* __restrict__ cov, const float* __restrict__ opac,
+                                                              const float* __restrict__ cam_dev, float* __restrict__ depths,
+                                                              float2* __restrict__ xy, float4* __restrict__ conic_o, uint32_t* __restrict__ tiles,
+                                                              ushort4* __restrict__ rects, int32_t* __restrict__ radii, int32_t* __restrict__ radii_xy) {
+    __shared__ FeatCam s_cam;
+    if (threadIdx.x < (int)(sizeof(FeatCam) / sizeof(float))) reinterpret_cast<float*>(&s_cam)[threadIdx.x] = cam_dev[threadIdx.x];
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= G) return;
+    const float* V = s_cam.V;   // world-to-camera, row-major
+    const float px = means[3 * (size_t)i], py = means[3 * (size_t)i + 1], pz = means[3 * (size_t)i + 2];
+    const float x = ADD(ADD(ADD(MUL(V[0], px), MUL(V[1], py)), MUL(V[2], pz)), V[3]);
+    const float y = ADD(ADD(ADD(MUL(V[4], px), MUL(V[5], py)), MUL(V[6], pz)), V[7]);
+    const float z = ADD(ADD(ADD(MUL(V[8], px), MUL(V[9], py)), MUL(V[10], pz)), V[11]);
+    if (z < s_cam.near_plane || z > s_cam.far_plane) return;      // radii / tiles were zeroed by the host wrapper
+    float S[3][3];
+    {
+        const float* c = cov + (size_t)i * cov_stride;
+        if (cov_stride == 6) { S[0][0] = c[0]; S[0][1] = S[1][0] = c[1]; S[0][2] = S[2][0] = c[2]; S[1][1] = c[3]; S[1][2] = S[2][1] = c[4]; S[2][2] = c[5]; }
+        else { for (int r = 0; r < 3; ++r) for (int q = 0; q < 3; ++q) S[r][q] = c[3 * r + q]; }
+    }
+    float RS[3][3], Cc[3][3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int q = 0; q < 3; ++q) RS[r][q] = ADD(ADD(MUL(V[4 * r], S[0][q]), MUL(V[4 * r + 1], S[1][q])), MUL(V[4 * r + 2], S[2][q]));
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int q = 0; q < 3; ++q) Cc[r][q] = ADD(ADD(MUL(RS[r][0], V[4 * q]), MUL(RS[r][1], V[4 * q + 1])), MUL(RS[r][2], V[4 * q + 2]));
+    const float fx = s_cam.fx, fy = s_cam.fy, cx = s_cam.cx, cy = s_cam.cy;
+    const float tanx = DIV(MUL(0.5f, (float)W), fx), tany = DIV(MUL(0.5f, (float)H), fy);
+    const float lxp = ADD(DIV(SUB((float)W, cx), fx), MUL(0.3f, tanx)), lxn = ADD(DIV(cx, fx), MUL(0.3f, tanx));
+    const float lyp = ADD(DIV(SUB((float)H, cy), fy), MUL(0.3f, tany)), lyn = ADD(DIV(cy, fy), MUL(0.3f, tany));
+    const float rz = DIV(1.0f, z), rz2 = MUL(rz, rz);
+    const float tx = MUL(z, fminf(lxp, fmaxf(-lxn, MUL(x, rz)))), ty = MUL(z, fminf(lyp, fmaxf(-lyn, MUL(y, rz))));
+    const float ja = MUL(fx, rz), jb = -MUL(MUL(fx, tx), rz2), jc = MUL(fy, rz), jd = -MUL(MUL(fy, ty), rz2);
+    float JC0[3], JC1[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) { JC0[q] = ADD(MUL(ja, Cc[0][q]), MUL(jb, Cc[2][q])); JC1[q] = ADD(MUL(jc, Cc[1][q]), MUL(jd, Cc[2][q])); }
+    float c00 = ADD(MUL(JC0[0], ja), MUL(JC0[2], jb));
+    const float c01 = ADD(MUL(JC0[1], jc), MUL(JC0[2], jd));
+    float c11 = ADD(MUL(JC1[1], jc), MUL(JC1[2], jd));
+    const float mx = ADD(MUL(MUL(fx, x), rz), cx), my = ADD(MUL(MUL(fy, y), rz), cy);
+    c00 = ADD(c00, 0.3f); c11 = ADD(c11, 0.3f);
+    const float det = SUB(MUL(c00, c11), MUL(c01, c01));
+    if (!(det > 0.0f)) return;
+    const float o = opac[i];
+    const float thr = 1.0f / 255.0f;
+    if (o < thr) return;
+    const float ext = fminf(3.33f, __fsqrt_rn(MUL(2.0f, logf(DIV(o, thr)))));
+    const float bb = MUL(0.5f, ADD(c00, c11));
+    const float v1 = ADD(bb, __fsqrt_rn(fmaxf(0.01f, SUB(MUL(bb, bb), det))));
+    const float r1 = MUL(ext, __fsqrt_rn(v1));
+    const float rx = ceilf(fminf(MUL(ext, __fsqrt_rn(c00)), r1)), ry = ceilf(fminf(MUL(ext, __fsqrt_rn(c11)), r1));
+    if (rx <= 0.0f && ry <= 0.0f) return;
+    if (ADD(mx, rx) <= 0.0f || SUB(mx, rx) >= (float)W || ADD(my, ry) <= 0.0f || SUB(my, ry) >= (float)H) return;
+    const float tsx = DIV(mx, 16.0f), tsy = DIV(my, 16.0f), trx = DIV(rx, 16.0f), try_ = DIV(ry, 16.0f);
+    const int rminx = min(gx, max(0, (int)floorf(SUB(tsx, trx)))), rmaxx = min(gx, max(0, (int)ceilf(ADD(tsx, trx))));
+    const int rminy = min(gy, max(0, (int)floorf(SUB(tsy, try_)))), rmaxy = min(gy, max(0, (int)ceilf(ADD(tsy, try_))));
+    const int nt = (rmaxx - rminx) * (rmaxy - rminy);
+    if (nt <= 0) return;
+    const float inv = DIV(1.0f, det);
+    depths[i] = z;
+    xy[i] = make_float2(mx, my);
+    conic_o[i] = make_float4(MUL(c11, inv), MUL(-c01, inv), MUL(c00, inv), o);
+    tiles[i] = (uint32_t)nt;
+    rects[i] = make_ushort4((unsigned short)rminx, (unsigned short)rminy, (unsigned short)rmaxx, (unsigned short)rmaxy);
+    radii[i] = (int32_t)fmaxf(rx, ry);
+    if (radii_xy) { radii_xy[2 * (size_t)i] = (int32_t)rx; radii_xy[2 * (size_t)i + 1] = (int32_t)ry; }
+}
+
+// Blend of one 32-channel slice of the features: grid (tiles_x, tiles_y, ceil(C / 32)); same 256-record batches and exact per-warp
+// (8x4 pixel) culling as render_kernel; the slice of every staged record's feature row sits in shared memory (32 KB per batch).
+constexpr int FCH = 32;
+__global__ void __launch_bounds__(RB) render_feat_kernel(int W, int H, int gx, const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
+                                                         const float2* __restrict__ xy, const float4* __restrict__ conic_o,
+                                                         const float* __restrict__ feats, int C, float* __restrict__ out, float* __restrict__ out_alpha) {
+    __shared__ float2 s_xy[RB];
+    __shared__ float4 s_co[RB];
+    __shared__ float4 s_box[RB];
+    __shared__ uint8_t s_list[RB / 32][RB];
+    __shared__ __align__(16) float s_f[RB][FCH];
+    const int tile_x = blockIdx.x, tile_y = blockIdx.y, c0 = blockIdx.z * FCH;
+    const int nch = min(FCH, C - c0);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int bx0 = tile_x * TILE_X + (warp & 1) * SUB_W, by0 = tile_y * TILE_Y + (warp >> 1) * SUB_H;
+    const int pxi = bx0 + (lane & 7), pyi = by0 + (lane >> 3);
+    const bool inside = pxi < W && pyi < H;
+    const float pfx = (float)pxi + 0.5f, pfy = (float)pyi + 0.5f;
+    const float wx0 = (float)bx0 + 0.5f, wx1 = (float)(bx0 + SUB_W - 1) + 0.5f, wy0 = (float)by0 + 0.5f, wy1 = (float)(by0 + SUB_H - 1) + 0.5f;
+    const uint2 range = ranges[tile_y * gx + tile_x];
+    const int rounds = (int)((range.y - range.x + RB - 1) / RB);
+    int todo = (int)(range.y - range.x);
+    bool done = !inside;
+    float T = 1.0f;
+    float acc[FCH];
+#pragma unroll
+    for (int k = 0; k < FCH; ++k) acc[k] = 0.f;
+    uint8_t* my_list = s_list[warp];
+    const bool vec = (C % 4 == 0) && nch == FCH && ((((uintptr_t)feats) & 15) == 0);
+
+    for (int r = 0; r < rounds; ++r, todo -= RB) {
+        const int num_done = __syncthreads_count(done);
+        if (num_done == RB) break;
+        const uint32_t progress = range.x + (uint32_t)r * RB + tid;
+        if (progress < range.y) {
+            const uint32_t id = point_list[progress];
+            const float2 p = xy[id];
+            const float4 co = conic_o[id];
+            s_xy[tid] = p;
+            s_co[tid] = co;
+            const float* f = feats + (size_t)id * C + c0;
+            if (vec) {
+#pragma unroll
+                for (int k = 0; k < FCH; k += 4) *reinterpret_cast<float4*>(&s_f[tid][k]) = __ldg(reinterpret_cast<const float4*>(f + k));
+            } else {
+                for (int k = 0; k < FCH; ++k) s_f[tid][k] = k < nch ? __ldg(f + k) : 0.f;
+            }
+            const float det = co.x * co.z - co.y * co.y;
+            float ex = INFINITY, ey = INFINITY;
+            if (det > 0.0f && co.x > 0.0f && co.z > 0.0f && co.w == co.w) {
+                const float tau = __logf(255.0f * co.w) + 0.02f;
+                if (tau < 0.0f || !(co.w > 0.0f)) {
+                    ex = ey = -INFINITY;
+                } else {
+                    const float inv = 1.0f / det;
+                    ex = sqrtf(2.0f * tau * co.z * inv) * 1.001f + 0.01f;
+                    ey = sqrtf(2.0f * tau * co.x * inv) * 1.001f + 0.01f;
+                }
+            }
+            s_box[tid] = make_float4(p.x - ex, p.x + ex, p.y - ey, p.y + ey);
+        }
+        __syncthreads();
+        const int nb = min(RB, todo);
+        int nl = 0;
+        if (!__all_sync(0xffffffffu, done)) {
+#pragma unroll
+            for (int k = 0; k < RB / 32; ++k) {
+                const int j = k * 32 + lane;
+                bool hit = false;
+                if (j < nb) {
+                    const float4 b = s_box[j];
+                    hit = b.y >= wx0 && b.x <= wx1 && b.w >= wy0 && b.z <= wy1;
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, hit);
+                if (hit) my_list[nl + __popc(m & ((1u << lane) - 1u))] = (uint8_t)j;
+                nl += __popc(m);
+            }
+            __syncwarp();
+        }
+        for (int i = 0; i < nl; ++i) {
+            const int j = my_list[i];
+            if (done) continue;
+            const float2 p = s_xy[j];
+            const float4 co = s_co[j];
+            const float dx = p.x - pfx, dy = p.y - pfy;
+            const float sigma = 0.5f * (co.x * dx * dx + co.z * dy * dy) + co.y * dx * dy;
+            const float alpha = fminf(0.999f, co.w * __expf(-sigma));
+            if (sigma < 0.0f || alpha < 1.0f / 255.0f) continue;
+            const float next_T = T * (1.0f - alpha);
+            if (next_T <= 1e-4f) { done = true; continue; }
+            const float vis = alpha * T;
+            const float4* f4 = reinterpret_cast<const float4*>(s_f[j]);
+#pragma unroll
+            for (int k = 0; k < FCH / 4; ++k) {
+                const float4 f = f4[k];
+                acc[4 * k] += f.x * vis; acc[4 * k + 1] += f.y * vis; acc[4 * k + 2] += f.z * vis; acc[4 * k + 3] += f.w * vis;
+            }
+            T = next_T;
+        }
+    }
+    if (inside) {
+        float* o = out + ((size_t)pyi * W + pxi) * C + c0;
+        if (vec) {
+#pragma unroll
+            for (int k = 0; k < FCH; k += 4) *reinterpret_cast<float4*>(o + k) = make_float4(acc[k], acc[k + 1], acc[k + 2], acc[k + 3]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < FCH; ++k)
+                if (k < nch) o[k] = acc[k];
+        }
+        if (blockIdx.z == 0 && out_alpha) out_alpha[(size_t)pyi * W + pxi] = 1.0f - T;
+    }
+}
+
 __global__ void pack_camera_kernel(const float* __restrict__ view, const float* __restrict__ proj, const float* __restrict__ campos,
                                    const float* __restrict__ bg, float* __restrict__ cam) {
     const int t = threadIdx.x;
@@ -606,6 +803,61 @@ int siu3r_raster_forward(int G, int H, int W, int sh_degree, int sh_coeffs, int 
         if (debug_values) SIU3R_CUDA_CHECK(cudaMemcpyAsync(debug_values, sorted_vals, sizeof(uint32_t) * D, cudaMemcpyDeviceToDevice, stream));
     }
     if (debug_ranges) SIU3R_CUDA_CHECK(cudaMemcpyAsync(debug_ranges, w.ranges, sizeof(uint2) * gx * gy, cudaMemcpyDeviceToDevice, stream));
+    return SIU3R_OK;
+}
+
+
+// N-channel feature rasterization of one camera (gsplat.rasterization semantics, see render_feat_kernel).  viewmat: world-to-camera
+// 4x4 row-major; intr_host = (fx, fy, cx, cy) in pixels; features [G, C]; out_features [H, W, C]; out_alpha [H, W] (may be null);
+// radii_xy [G, 2] int32 (may be null).  Workspace / capacity protocol as siu3r_raster_forward.
+int siu3r_raster_features_forward(int G, int H, int W, int C, int cov_stride, const float* means3D, const float* cov, const float* opacities,
+                                  const float* features, const float* viewmat, const float* intr_host, float near_plane, float far_plane,
+                                  float* out_features, float* out_alpha, int32_t* radii_xy, void* workspace, int64_t workspace_bytes,
+                                  int64_t dup_capacity, int64_t* num_rendered_host, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    SIU3R_REQUIRE(G > 0 && H > 0 && W > 0 && C > 0 && (cov_stride == 6 || cov_stride == 9));
+    SIU3R_REQUIRE(means3D && cov && opacities && features && viewmat && intr_host && out_features && workspace);
+    SIU3R_REQUIRE(dup_capacity > 0 && dup_capacity < (1ll << 31));
+    const int gx = ceil_div(W, TILE_X), gy = ceil_div(H, TILE_Y);
+    SIU3R_REQUIRE(gx < 65536 && gy < 65536 && ceil_div(C, FCH) < 65536);
+    Workspace w = carve(workspace, G, H, W, dup_capacity);
+    if ((int64_t)w.bytes > workspace_bytes) return SIU3R_ERR_CAPACITY;
+    int32_t* radii = reinterpret_cast<int32_t*>(w.rgb);   // the colour slot of the shared workspace is free on this path
+    SIU3R_CUDA_CHECK(cudaMemsetAsync(radii, 0, sizeof(int32_t) * G, stream));
+    SIU3R_CUDA_CHECK(cudaMemsetAsync(w.tiles, 0, sizeof(uint32_t) * G, stream));
+    SIU3R_CUDA_CHECK(cudaMemsetAsync(w.ranges, 0, sizeof(uint2) * gx * gy, stream));
+    if (radii_xy) SIU3R_CUDA_CHECK(cudaMemsetAsync(radii_xy, 0, sizeof(int32_t) * 2 * G, stream));
+    // camera block: V (device) + 6 host scalars -> one small device buffer
+    SIU3R_CUDA_CHECK(cudaMemcpyAsync(w.cam, viewmat, 16 * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+    const float scal[6] = {intr_host[0], intr_host[1], intr_host[2], intr_host[3], near_plane, far_plane};
+    SIU3R_CUDA_CHECK(cudaMemcpyAsync(w.cam + 16, scal, sizeof(scal), cudaMemcpyHostToDevice, stream));
+    preprocess_feat_kernel<<<ceil_div(G, 128), 128, 0, stream>>>(G, H, W, gx, gy, cov_stride, means3D, cov, opacities, w.cam, w.depths, w.xy,
+                                                                w.conic_o, w.tiles, w.rects, radii, radii_xy);
+    const int nsb = ceil_div(G, SCAN_TILE);
+    scan_local_kernel<<<nsb, SCAN_THREADS, 0, stream>>>(w.tiles, w.offsets, w.block_sums, G);
+    scan_sums_kernel<<<1, SCAN_THREADS, 0, stream>>>(w.block_sums, nsb, w.total);
+    scan_add_kernel<<<nsb, SCAN_THREADS, 0, stream>>>(w.offsets, w.block_sums, G);
+    SIU3R_LAUNCH_CHECK();
+    siu3r_note_launch(4);
+    uint32_t D32 = 0;
+    SIU3R_CUDA_CHECK(cudaMemcpyAsync(&D32, w.total, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    SIU3R_CUDA_CHECK(cudaStreamSynchronize(stream));   // also covers the pageable `scal` upload above
+    const int64_t D = (int64_t)D32;
+    if (num_rendered_host) *num_rendered_host = D;
+    if (D > dup_capacity) return SIU3R_ERR_CAPACITY;
+    if (D > 0) {
+        duplicate_with_keys_kernel<<<ceil_div(G, 256), 256, 0, stream>>>(G, gx, radii, w.offsets, w.depths, w.rects, w.keys, w.vals);
+        const int end_bit = 32 + higher_msb((uint32_t)(gx * gy));
+        size_t tb = w.cub_bytes;
+        SIU3R_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(w.cub_temp, tb, w.keys, w.keys_sorted, w.vals, w.vals_sorted, (int)D, 0, end_bit, stream));
+        identify_tile_ranges_kernel<<<(unsigned)ceil_div_i64(D, 256), 256, 0, stream>>>((uint32_t)D, w.keys_sorted, w.ranges);
+        SIU3R_LAUNCH_CHECK();
+        siu3r_note_launch(2);
+    }
+    dim3 grid(gx, gy, ceil_div(C, FCH));
+    render_feat_kernel<<<grid, RB, 0, stream>>>(W, H, gx, w.ranges, w.vals_sorted, w.xy, w.conic_o, features, C, out_features, out_alpha);
+    SIU3R_LAUNCH_CHECK();
+    siu3r_note_launch(1);
     return SIU3R_OK;
 }
 

@@ -563,3 +563,32 @@ def raster_forward(means, cov, shs, opac, viewmatrix, projmatrix, campos, bg, ta
     res = dict(color=color, depth=depth, opacity=opacity, radii=radii, n_touched=n_touched, num_rendered=int(nren.value))
     res.update(dbg)
     return res
+
+
+def raster_features_forward(means, cov, opac, feats, viewmat, intr, near, far, H, W, dup_capacity=None, want_alpha=True, want_radii=False):
+    """N-channel feature splatting of one camera (gsplat.rasterization semantics).  means [G,3]; cov [G,3,3] or [G,6]; opac [G];
+    feats [G,C]; viewmat [4,4] world-to-camera (device); intr = (fx, fy, cx, cy) in pixels.  -> dict(features [H,W,C], alpha [H,W], ...)."""
+    lib = _lib.load()
+    _chk_f32(means, cov, opac, feats, viewmat)
+    assert means.is_contiguous() and cov.is_contiguous() and opac.is_contiguous() and feats.is_contiguous() and viewmat.is_contiguous()
+    G, Cc = means.shape[0], feats.shape[1]
+    cov_stride = 6 if cov.shape[-1] == 6 else 9
+    dev = means.device
+    if dup_capacity is None:
+        dup_capacity = max(1 << 16, 8 * G)
+    intr_arr = (C.c_float * 4)(*[float(v) for v in intr])
+    while True:
+        ws_bytes = int(lib.siu3r_raster_workspace_bytes(G, H, W, dup_capacity))
+        ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+        out = torch.empty(H, W, Cc, device=dev)
+        alpha = torch.empty(H, W, device=dev) if want_alpha else None
+        radii = torch.empty(G, 2, device=dev, dtype=torch.int32) if want_radii else None
+        nren = C.c_int64(0)
+        code = lib.siu3r_raster_features_forward(G, H, W, Cc, cov_stride, _p(means), _p(cov), _p(opac), _p(feats), _p(viewmat), intr_arr, float(near),
+                                                 float(far), _p(out), _p(alpha), _p(radii), _p(ws), ws_bytes, dup_capacity, C.byref(nren), _stream())
+        if code == -2 and nren.value > dup_capacity:
+            dup_capacity = int(nren.value * 1.05) + 1024
+            continue
+        _lib.check(code, "raster_features_forward")
+        break
+    return dict(features=out, alpha=alpha, radii=radii, num_rendered=int(nren.value))

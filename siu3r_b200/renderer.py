@@ -5,7 +5,8 @@
   get_projection_matrix  <-> cuda_splatting.py:16-43 ;  get_fov <-> src/utils/projection.py:247-261
 
 Camera set-up is host-side float32 arithmetic on tiny [b,4,4] matrices (plumbing); all per-Gaussian / per-pixel work
-runs in the sm_100a rasterizer (csrc/raster.cu) through the C ABI.  Differences from the reference, by design:
+runs in the sm_100a rasterizer (csrc/raster.cu) through the C ABI.  `render_qc_logits=True` splats the per-Gaussian query x class
+logits with the N-channel kernel that replaces gsplat.rasterization (gaussian_renderer.py:92-106).  Differences from the reference, by design:
   * no per-camera copy of the Gaussians (the reference `repeat`s them per view, gaussian_renderer.py:57-60);
   * covariances are consumed as the full [g,3,3] tensor and harmonics as [g,3,d_sh] -- the upper-triangle gather
     (cuda_splatting.py:107,115) and the SH transpose (:65) happen inside the preprocess kernel's loads.
@@ -110,8 +111,6 @@ class SplattingCUDA:
     def forward(self, gaussians: Gaussians, extrinsics, intrinsics, image_shape, render_color: bool = True, render_feature: bool = False,
                 render_id: bool = False, render_qc_logits: bool = False, cam_rot_delta=None, cam_trans_delta=None):
         assert cam_rot_delta is None and cam_trans_delta is None, "pose deltas are a training-only (backward) feature"
-        if render_qc_logits:
-            raise NotImplementedError("N-channel logit rasterisation (gsplat path) is SURVEY.md section 8(f)-1: next, not built yet")
         b, v = extrinsics.shape[:2]
         E = extrinsics.detach().float().cpu().clone()
         E[..., :3, 3] = E[..., :3, 3] * self.scale_factor
@@ -132,4 +131,22 @@ class SplattingCUDA:
             color = torch.stack(cols)
             depth = torch.stack(deps)
             color = ops.eltwise(ops.ELT_CLAMP01, color.contiguous())
-        return {"render_color": color, "render_depth": depth, "render_qc_logits": None}
+        qc = None
+        if render_qc_logits:
+            # gaussian_renderer.py:75-110: per sample, splat the [n, q*c] query-class logits into every target view (gsplat semantics)
+            h, w = image_shape
+            qc = []
+            for bi in range(b):
+                logits = gaussians.seg_query_class_logits[bi]            # [n, q, c]
+                n, q, c = logits.shape
+                feats = logits.reshape(n, q * c).contiguous()
+                Ks = intrinsics[bi].detach().float().cpu()
+                viewmats = torch.linalg.inv(E[bi]).contiguous().to(gaussians.means.device)
+                outs = []
+                for vi in range(v):
+                    intr = (float(Ks[vi, 0, 0]) * w, float(Ks[vi, 1, 1]) * h, float(Ks[vi, 0, 2]) * w, float(Ks[vi, 1, 2]) * h)
+                    r = ops.raster_features_forward(gaussians.means[bi].contiguous(), gaussians.covariances[bi].contiguous(),
+                                                    gaussians.opacities[bi].contiguous(), feats, viewmats[vi], intr, near, far, h, w, want_alpha=False)
+                    outs.append(r["features"])
+                qc.append(torch.stack(outs).view(v, h, w, q, c).permute(0, 3, 4, 1, 2))     # "n h w (q c) -> n q c h w" as a view
+        return {"render_color": color, "render_depth": depth, "render_qc_logits": qc}

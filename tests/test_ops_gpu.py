@@ -529,3 +529,69 @@ def test_raster_properties_large():
             lib.siu3r_raster_set_culling(1)
         for kk in ("color", "depth", "opacity", "n_touched"):
             assert torch.equal(a[kk], b[kk]), (pa, kk)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# N-channel feature splatting (gsplat.rasterization semantics; oracle/gsplat_ref.py, parity unpinned vs gsplat itself)
+def _feature_scene(G, H, W, C, seed):
+    rng = np.random.default_rng(seed)
+    z = rng.uniform(1.5, 30.0, G)
+    means = np.stack([rng.uniform(-1, 1, G) * z * 0.5, rng.uniform(-1, 1, G) * z * 0.5, z], -1).astype("f4")
+    A = (rng.standard_normal((G, 3, 3)) * (0.02 * z)[:, None, None]).astype("f4")
+    cov = (A @ A.transpose(0, 2, 1) + 1e-6 * np.eye(3, dtype="f4")).astype("f4")
+    op = rng.random(G).astype("f4")
+    op[::11] = 0.001                                  # below the 1/255 floor
+    means[::13, 2] = 0.5                              # in front of the near plane (1.0)
+    feats = rng.standard_normal((G, C)).astype("f4")
+    ang = 0.2
+    V = np.eye(4, dtype="f4")
+    V[:3, :3] = np.array([[np.cos(ang), 0, np.sin(ang)], [0, 1, 0], [-np.sin(ang), 0, np.cos(ang)]], dtype="f4")
+    V[:3, 3] = [0.1, -0.05, 0.3]
+    return means, cov, op, feats, V
+
+
+@pytest.mark.parametrize("G,H,W,C", [(3000, 64, 64, 42), (8000, 96, 160, 21), (500, 48, 80, 70), (1, 32, 32, 5)])
+def test_raster_features_vs_oracle(G, H, W, C):
+    from siu3r_b200 import ops
+    from oracle import gsplat_ref as GR
+    means, cov, op, feats, V = _feature_scene(G, H, W, C, 5)
+    fx, fy, cx, cy = 1.242 * W, 1.242 * H, 0.5 * W, 0.47 * H
+    ref, ref_alpha, pr = GR.rasterize(means, cov, op, feats, V, fx, fy, cx, cy, W, H, 1.0, 1000.0)
+    t = lambda a: torch.from_numpy(a).to(DEV)
+    res = ops.raster_features_forward(t(means), t(cov), t(op), t(feats), t(V), (fx, fy, cx, cy), 1.0, 1000.0, H, W, want_radii=True)
+    radii = res["radii"].cpu().numpy()
+    # extents go through log(): CUDA logf and numpy log may differ in the last bit -> allow isolated off-by-one radii
+    assert (np.abs(radii - pr["radii"]).max() <= 1) and (radii != pr["radii"]).mean() < 2e-3
+    scale = max(1.0, float(np.abs(ref).max()))
+    assert np.abs(res["features"].cpu().numpy() - ref).max() < 1e-3 * scale
+    assert np.abs(res["alpha"].cpu().numpy() - ref_alpha).max() < 1e-3
+    # cov6 layout gives the identical result; so does a second call (idempotence)
+    row, col = np.triu_indices(3)
+    res2 = ops.raster_features_forward(t(means), t(np.ascontiguousarray(cov[:, row, col])), t(op), t(feats), t(V), (fx, fy, cx, cy), 1.0, 1000.0, H, W)
+    assert torch.equal(res2["features"], res["features"])
+    # linearity in the features (the blend weights do not depend on them)
+    res3 = ops.raster_features_forward(t(means), t(cov), t(op), t(2 * feats), t(V), (fx, fy, cx, cy), 1.0, 1000.0, H, W)
+    assert float((res3["features"] - 2 * res["features"]).abs().max()) < 1e-4 * scale
+
+
+def test_splatting_render_qc_logits_surface():
+    """SplattingCUDA.forward(render_qc_logits=True): list over the batch of [V, q, c, H, W] (gaussian_renderer.py:75-110), consistent with a
+    direct call of the feature rasterizer, colour path unchanged."""
+    from siu3r_b200 import ops
+    from siu3r_b200.gaussians import Gaussians
+    from siu3r_b200.renderer import SplattingCUDA
+    means, cov, op, feats, V = _feature_scene(4000, 64, 64, 42, 9)
+    t = lambda a: torch.from_numpy(a).to(DEV)
+    g = Gaussians(means=t(means)[None] / 10, covariances=t(cov)[None] / 100, harmonics=torch.randn(1, 4000, 3, 25, device=DEV) * 0.1, opacities=t(op)[None])
+    g.seg_query_class_logits = [t(feats).view(4000, 2, 21)]
+    E = torch.eye(4)[None, None].repeat(1, 2, 1, 1)
+    E[0, 1, 0, 3] = 0.02
+    K = torch.tensor([[1.242, 0, 0.5], [0, 1.242, 0.5], [0, 0, 1.0]])[None, None].repeat(1, 2, 1, 1)
+    out = SplattingCUDA()(g, E, K, (64, 64), render_color=True, render_qc_logits=True)
+    qc = out["render_qc_logits"]
+    assert len(qc) == 1 and tuple(qc[0].shape) == (2, 2, 21, 64, 64) and tuple(out["render_color"].shape) == (1, 2, 3, 64, 64)
+    # the renderer rescaled the scene x10 in place (gaussian_renderer.py:43-46); view 0 has the identity pose
+    direct = ops.raster_features_forward(g.means[0].contiguous(), g.covariances[0].contiguous(), g.opacities[0].contiguous(), t(feats),
+                                         torch.eye(4, device=DEV), (1.242 * 64, 1.242 * 64, 32.0, 32.0), 1.0, 1000.0, 64, 64)
+    assert torch.equal(qc[0][0], direct["features"].view(64, 64, 2, 21).permute(2, 3, 0, 1))
+    assert torch.isfinite(qc[0]).all() and float(qc[0].abs().max()) > 0

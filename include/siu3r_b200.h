@@ -98,6 +98,10 @@ int siu3r_rope2d_table(float* tab, int maxpos, int D, float base, float fwd, voi
 /* nn.LayerNorm over the last dim (+ optional fused add of `add` rows): croco/blocks.py:119-125,176-184 */
 int siu3r_layernorm(const float* x, int64_t ldx, const float* w, const float* b, float* y, int64_t ldy, int rows, int C,
                     float eps, const float* add, int64_t ldadd, int round_out, void* stream);
+/* two LayerNorms with different affine parameters / buffers in one launch (the two decoder streams: norm1, norm2, norm3, norm_y of
+ * dec_blocks[l] and dec_blocks2[l], croco/blocks.py:186-190); same C, pitches and eps; segment g has rows_g rows */
+int siu3r_layernorm_group2(const float* x0, const float* x1, int64_t ldx, const float* w0, const float* b0, const float* w1, const float* b1,
+                           float* y0, float* y1, int64_t ldy, int rows0, int rows1, int C, float eps, int round_out, void* stream);
 /* softmax(Q K^T * scale) V, head dim 64: croco/blocks.py:105-109 (Attention), :162-166 (CrossAttention) */
 int siu3r_flash_attn_d64(const float* Q, int64_t q_bs, int64_t q_ts, const float* K, int64_t k_bs, int64_t k_ts,
                          const float* V, int64_t v_bs, int64_t v_ts, float* O, int64_t o_bs, int64_t o_ts, int B, int H,

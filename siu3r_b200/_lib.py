@@ -40,6 +40,7 @@ SIGNATURES = {
     "siu3r_rope2d": (_i, [_p, _p, _i, _i, _i, _i, _l, _l, _f, _f, _i, _l, _i, _p]),
     "siu3r_transpose_v": (_i, [_p, _l, _l, _i, _i, _i, _p, _l, _p]),
     "siu3r_flash_attn_tc": (_i, [_p, _l, _l, _i, _i, _p, _l, _l, _i, _i, _p, _l, _p, _l, _l, _i, _i, _i, _i, _f, _i, _p]),
+    "siu3r_layernorm_group2": (_i, [_p, _p, _l, _p, _p, _p, _p, _p, _p, _l, _i, _i, _i, _f, _i, _p]),
     "siu3r_layernorm": (_i, [_p, _l, _p, _p, _p, _l, _i, _i, _f, _p, _l, _i, _p]),
     "siu3r_flash_attn_d64": (_i, [_p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _l, _l, _i, _i, _i, _i, _f, _i, _i, _p]),
     "siu3r_attn_small_d32_ws_bytes": (_l, [_i, _i, _i, _i]),

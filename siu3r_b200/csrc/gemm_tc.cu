@@ -642,16 +642,20 @@ struct Tc3Problem {      // what differs between the problems of a grouped launc
 struct Tc3Group {
     Tc3Problem prob[2];
     int tiles0;          // tiles of problem 0 (tile t >= tiles0 belongs to problem 1)
+    int nsplit;          // split-K factor (work unit u = split * num_tiles + tile; splits of a tile are serialised through `flags`)
+    int kb_per_split;    // k-blocks per split
+    int* flags;          // [num_tiles][2 * TC3_EPI_WARPS] progress words, zero between launches (null when nsplit == 1)
 };
 
 template <int ACTK, bool ROPE, bool RES, bool RND>
 __device__ __forceinline__ void epi_chunk_swapped(const uint32_t (&v)[32], int jmax, int lane, int n, bool n_ok, float bias, int mrow, int axis,
-                                                  const GemmParams& p, const Tc3Problem& pr) {
+                                                  const GemmParams& p, const Tc3Problem& pr, int64_t ldr) {
     float r[32];
-    const float* rp = RES ? pr.residual + (int64_t)mrow * p.ldr + n : nullptr;
+    const float* rp = RES ? pr.residual + (int64_t)mrow * ldr + n : nullptr;
     if (RES) {
+        // all loads in flight before the math; .cg (L2) because with split-K this is C as written by another SM a moment ago
 #pragma unroll
-        for (int j = 0; j < 32; ++j) r[j] = (j < jmax && n_ok) ? rp[(int64_t)j * p.ldr] : 0.0f;   // all loads in flight before the math
+        for (int j = 0; j < 32; ++j) r[j] = (j < jmax && n_ok) ? __ldcg(rp + (int64_t)j * ldr) : 0.0f;
     }
     long long pos_l = 0;
     const float* tab = nullptr;
@@ -677,14 +681,22 @@ __device__ __forceinline__ void epi_chunk_swapped(const uint32_t (&v)[32], int j
     }
 }
 
+// split / nsplit / flag: split-K.  Split 0 writes C = alpha*acc + bias + residual, split s > 0 waits until the SAME warp slot of split s-1 has
+// published its part of the tile (flag == s), then accumulates C += alpha*acc (the last split applies the TF32 rounding) and publishes s+1
+// (the last split resets the word to 0 for the next launch).  One writer per flag word and phase: plain release / acquire, no atomics, and a
+// fixed summation order -> bit-reproducible results.
 __device__ __forceinline__ void run_epilogue_swapped(uint32_t tmem_acc, int lane, int q, int c_lo, int c_hi, int n_cta, int m_base,
-                                                     const GemmParams& p, const Tc3Problem& pr, uint64_t* bar, uint32_t parity) {
+                                                     const GemmParams& p, const Tc3Problem& pr_in, uint64_t* bar, uint32_t parity, int split,
+                                                     int nsplit, int* flag) {
     const int nb = n_cta + q * 32;           // warp-uniform first weight row
     const int n = nb + lane;
     const bool n_ok = n < p.N;
+    Tc3Problem pr = pr_in;
+    int64_t ldr = p.ldr;
+    if (split > 0) { pr.bias = nullptr; pr.residual = pr_in.C; ldr = p.ldc; }
     const float bias = (pr.bias && n_ok) ? __ldg(pr.bias + n) : 0.0f;
     const int act = p.act & ACT_MASK;
-    const bool rnd = (p.act & ACT_ROUND_TF32) != 0;
+    const bool rnd = (p.act & ACT_ROUND_TF32) != 0 && split == nsplit - 1;
     const bool rope = p.rope_pos != nullptr && nb < p.rope_cols;
     const bool res = pr.residual != nullptr;
     const int axis = (nb >> 5) & 1;
@@ -692,11 +704,17 @@ __device__ __forceinline__ void run_epilogue_swapped(uint32_t tmem_acc, int lane
     const int variant = rope ? (rnd ? 1 : 0) : 2 + (act * 4 + (res ? 2 : 0) + (rnd ? 1 : 0));
     mbar_wait(bar, parity);
     tcgen05_fence_after();
-    if (nb >= p.N || c_lo >= c_hi) return;
+    if (split > 0) {   // the previous split's partial sums of this warp's block must be visible
+        if (lane == 0) {
+            int f;
+            do { asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(f) : "l"(flag) : "memory"); } while (f != split);
+        }
+        __syncwarp();
+    }
     const uint32_t tq = tmem_acc + ((uint32_t)(q * 32) << 16);
     uint32_t v[32];
 #pragma unroll 1
-    for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
+    for (int c0 = c_lo; c0 < c_hi && nb < p.N; c0 += 32) {
         tmem_ld_32x32b_x32(tq + (uint32_t)c0, v);
         tmem_ld_wait();
         const int mrow = m_base + c0;
@@ -705,20 +723,27 @@ __device__ __forceinline__ void run_epilogue_swapped(uint32_t tmem_acc, int lane
         if (jmax > pr.M - mrow) jmax = pr.M - mrow;
         if (jmax <= 0) break;
         switch (variant) {
-            case 0: epi_chunk_swapped<ACT_NONE, true, false, false>(v, jmax, lane, n, n_ok, bias, mrow, axis, p, pr); break;
-            case 1: epi_chunk_swapped<ACT_NONE, true, false, true>(v, jmax, lane, n, n_ok, bias, mrow, axis, p, pr); break;
-            case 2: epi_chunk_swapped<ACT_NONE, false, false, false>(v, jmax, lane, n, n_ok, bias, mrow, axis, p, pr); break;
-            case 3: epi_chunk_swapped<ACT_NONE, false, false, true>(v, jmax, lane, n, n_ok, bias, mrow, axis, p, pr); break;
-            case 4: epi_chunk_swapped<ACT_NONE, false, true, false>(v, jmax, lane, n, n_ok, bias, mrow, axis, p, pr); break;
-            case 5: epi_chunk_swapped<ACT_NONE, false, true, true>(v, jmax, lane, n, n_ok, bias, mrow, axis, p, pr); break;
-            case 6: epi_chunk_swapped<ACT_GELU, false, false, false>(v, jmax, lane, n, n_ok, bias, mrow, axis, p, pr); break;
-            case 7: epi_chunk_swapped<ACT_GELU, false, false, true>(v, jmax, lane, n, n_ok, bias, mrow, axis, p, pr); break;
-            case 8: epi_chunk_swapped<ACT_GELU, false, true, false>(v, jmax, lane, n, n_ok, bias, mrow, axis, p, pr); break;
-            case 9: epi_chunk_swapped<ACT_GELU, false, true, true>(v, jmax, lane, n, n_ok, bias, mrow, axis, p, pr); break;
-            case 10: epi_chunk_swapped<ACT_RELU, false, false, false>(v, jmax, lane, n, n_ok, bias, mrow, axis, p, pr); break;
-            case 11: epi_chunk_swapped<ACT_RELU, false, false, true>(v, jmax, lane, n, n_ok, bias, mrow, axis, p, pr); break;
-            case 12: epi_chunk_swapped<ACT_RELU, false, true, false>(v, jmax, lane, n, n_ok, bias, mrow, axis, p, pr); break;
-            default: epi_chunk_swapped<ACT_RELU, false, true, true>(v, jmax, lane, n, n_ok, bias, mrow, axis, p, pr); break;
+            case 0: epi_chunk_swapped<ACT_NONE, true, false, false>(v, jmax, lane, n, n_ok, bias, mrow, axis, p, pr, ldr); break;
+            case 1: epi_chunk_swapped<ACT_NONE, true, false, true>(v, jmax, lane, n, n_ok, bias, mrow, axis, p, pr, ldr); break;
+            case 2: epi_chunk_swapped<ACT_NONE, false, false, false>(v, jmax, lane, n, n_ok, bias, mrow, axis, p, pr, ldr); break;
+            case 3: epi_chunk_swapped<ACT_NONE, false, false, true>(v, jmax, lane, n, n_ok, bias, mrow, axis, p, pr, ldr); break;
+            case 4: epi_chunk_swapped<ACT_NONE, false, true, false>(v, jmax, lane, n, n_ok, bias, mrow, axis, p, pr, ldr); break;
+            case 5: epi_chunk_swapped<ACT_NONE, false, true, true>(v, jmax, lane, n, n_ok, bias, mrow, axis, p, pr, ldr); break;
+            case 6: epi_chunk_swapped<ACT_GELU, false, false, false>(v, jmax, lane, n, n_ok, bias, mrow, axis, p, pr, ldr); break;
+            case 7: epi_chunk_swapped<ACT_GELU, false, false, true>(v, jmax, lane, n, n_ok, bias, mrow, axis, p, pr, ldr); break;
+            case 8: epi_chunk_swapped<ACT_GELU, false, true, false>(v, jmax, lane, n, n_ok, bias, mrow, axis, p, pr, ldr); break;
+            case 9: epi_chunk_swapped<ACT_GELU, false, true, true>(v, jmax, lane, n, n_ok, bias, mrow, axis, p, pr, ldr); break;
+            case 10: epi_chunk_swapped<ACT_RELU, false, false, false>(v, jmax, lane, n, n_ok, bias, mrow, axis, p, pr, ldr); break;
+            case 11: epi_chunk_swapped<ACT_RELU, false, false, true>(v, jmax, lane, n, n_ok, bias, mrow, axis, p, pr, ldr); break;
+            case 12: epi_chunk_swapped<ACT_RELU, false, true, false>(v, jmax, lane, n, n_ok, bias, mrow, axis, p, pr, ldr); break;
+            default: epi_chunk_swapped<ACT_RELU, false, true, true>(v, jmax, lane, n, n_ok, bias, mrow, axis, p, pr, ldr); break;
+        }
+    }
+    if (nsplit > 1) {
+        __syncwarp();
+        if (lane == 0) {
+            const int nf = split == nsplit - 1 ? 0 : split + 1;
+            asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(nf) : "memory");
         }
     }
 }
@@ -739,6 +764,7 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
     const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+    const int num_units = num_tiles * grp.nsplit;               // split-major: every split-0 unit precedes the split-1 units
     const int xrows = tw >> 1;                                  // token rows staged by each CTA
     const uint32_t stage_tx = 2u * (uint32_t)(C_::W_BYTES + xrows * BK * 4);
 
@@ -764,14 +790,16 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         // ===================== TMA producer (both CTAs) =====================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+            for (int u = cluster_id; u < num_units; u += num_clusters) {
+                const int split = u / num_tiles, t = u - split * num_tiles;
                 const int g = t >= grp.tiles0;
                 const int tl = g ? t - grp.tiles0 : t;
                 const CUtensorMap* mw = g ? &tmW1 : &tmW;
                 const CUtensorMap* mx = g ? &tmX1 : &tmX;
                 const int n0 = (tl % w_pairs) * 2 * BM + (int)rank * BM;       // this CTA's 128 weight rows
                 const int m0 = (tl / w_pairs) * tw + (int)rank * xrows;        // this CTA's half of the token tile
-                for (int kb = 0; kb < p.num_kb; ++kb) {
+                const int kb1 = min(p.num_kb, (split + 1) * grp.kb_per_split);
+                for (int kb = split * grp.kb_per_split; kb < kb1; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sW = smem + stage * C_::STAGE_BYTES;
                     uint8_t* sX = sW + C_::W_BYTES;
@@ -789,12 +817,14 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             const uint32_t idesc = make_idesc_tf32(2 * BM, tw);
             int stage = 0; uint32_t phase = 0;
             int it = 0;
-            for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
+            for (int u = cluster_id; u < num_units; u += num_clusters, ++it) {
                 const int buf = it & 1;
                 mbar_wait(&tempty_bar[buf], (((uint32_t)it >> 1) & 1u) ^ 1u);   // both CTAs' epilogues have drained this accumulator
                 tcgen05_fence_after();
                 const uint32_t acc = tmem_base + (uint32_t)(buf * 256);
-                for (int kb = 0; kb < p.num_kb; ++kb) {
+                const int split = u / num_tiles;
+                const int kb0 = split * grp.kb_per_split, kb1 = min(p.num_kb, kb0 + grp.kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tcgen05_fence_after();
                     const uint32_t sW = smem_u32(smem + stage * C_::STAGE_BYTES);
@@ -802,7 +832,7 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         const uint32_t koff = k * UMMA_K * 4;
-                        umma2_tf32(acc, make_smem_desc(sW + koff), make_smem_desc(sX + koff), idesc, (kb | k) != 0);
+                        umma2_tf32(acc, make_smem_desc(sW + koff), make_smem_desc(sX + koff), idesc, ((kb - kb0) | k) != 0);
                     }
                     umma2_commit_mc(&empty_bar[stage]);
                     if (++stage == C_::STAGES) { stage = 0; phase ^= 1; }
@@ -819,14 +849,16 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         const int c_hi = half == 0 ? min(tw, ((nfrag + 1) >> 1) * 32) : tw;
         const uint32_t lead_tempty0 = mapa_to_cta(smem_u32(&tempty_bar[0]), 0);
         int it = 0;
-        for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
+        for (int u = cluster_id; u < num_units; u += num_clusters, ++it) {
             const int buf = it & 1;
+            const int split = u / num_tiles, t = u - split * num_tiles;
             const int g = t >= grp.tiles0;
             const int tl = g ? t - grp.tiles0 : t;
             const int n_cta = (tl % w_pairs) * 2 * BM + (int)rank * BM;
             const int m_base = (tl / w_pairs) * tw;
+            int* flag = grp.flags ? grp.flags + ((size_t)t * 2 + rank) * TC3_EPI_WARPS + (warp - 2) : nullptr;
             run_epilogue_swapped(tmem_base + (uint32_t)(buf * 256), lane, q, c_lo, c_hi, n_cta, m_base, p, grp.prob[g], &tfull_bar[buf],
-                                 ((uint32_t)it >> 1) & 1u);
+                                 ((uint32_t)it >> 1) & 1u, split, grp.nsplit, flag);
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(lead_tempty0 + (uint32_t)(buf * 8));
@@ -855,7 +887,8 @@ int launch_tc3(const CUtensorMap& w, const CUtensorMap& x, const CUtensorMap& w1
         max_clusters = n;
         if (getenv("SIU3R_GEMM_VERBOSE")) fprintf(stderr, "[siu3r_b200] gemm_tc3: %d resident clusters, %d stages, %d B smem\n", n, C_::STAGES, C_::SMEM_BYTES);
     }
-    const int clusters = num_tiles < max_clusters ? num_tiles : max_clusters;
+    const int units = num_tiles * grp.nsplit;
+    const int clusters = units < max_clusters ? units : max_clusters;
     gemm_tc3_kernel<<<dim3((unsigned)(2 * clusters)), TC3_THREADS, C_::SMEM_BYTES, stream>>>(w, x, w1, x1, p, grp, w_pairs, num_tiles, tw);
     SIU3R_LAUNCH_CHECK();
     siu3r_note_launch(1);
@@ -936,6 +969,7 @@ long long* g_gemm_dbg = nullptr;
 // Tile selection (TF32 mode).  148 SMs x 2 resident CTAs: prefer the 2-CTA 256x256 pair tile when it still fills the
 // machine, otherwise fall back to smaller 1-CTA tiles so that small problems (M = 1025 / 2050 rows) launch enough CTAs.
 constexpr int kFillCtas = 222;  // ~1.5 CTAs per SM
+constexpr int kFlagSlotInts = 1 << 15, kFlagSlots = 32;   // split-K progress words: 32 slots x 128 KB
 
 bool use_tc2(int N, int64_t mtiles) {
     if (!tc2_enabled() || N % TC2_BN != 0 || mtiles < 2) return false;
@@ -960,25 +994,50 @@ int forced_kernel() {
 // Cost model per cluster (clocks): rounds x (k-blocks x max(tensor time, operand bytes per CTA / L2->SM share) + tile overhead);
 // TF32 tensor rate 4096 flop/clk/SM -> a 128 x tw x 32 k-block takes 2*tw clocks; the chip-wide L2->SM cap (~6300 B/clk, measured
 // on the 3x3 convs) gives each SM ~42 B/clk.
-int pick_tc3(int M, int N, int K, int M1 = 0, double* est_clk = nullptr) {
+int pick_tc3(int M, int N, int K, int M1 = 0, bool allow_split = false, int* nsplit_out = nullptr) {
+    if (nsplit_out) *nsplit_out = 1;
     const int f = forced_kernel();
     if (f == 3 || f == 4 || !tc2_enabled()) return 0;
     if (f == 0 && (N < 256 || K < 128 || M + M1 < 256)) return 0;
     const int tw_env = f >= 16 ? f : 0;   // siu3r_gemm_force(tw): this token tile width (sweeps)
+    static int split_env = -1;            // SIU3R_TC3_SPLITK=0 disables split-K, =n forces n where legal
+    if (split_env < 0) { const char* e = getenv("SIU3R_TC3_SPLITK"); split_env = e ? atoi(e) + 1 : 0; }
     const int w_pairs = ceil_div(N, 256);
     const int num_kb = ceil_div(K, BK);
-    int best = 0; double best_t = 1e30;
-    for (int tw = 32; tw <= 256; tw += 16) {
-        if (tw_env && tw != tw_env) continue;
-        const int T = ceil_div(M, tw) + (M1 > 0 ? ceil_div(M1, tw) : 0);
-        const int64_t tiles = (int64_t)w_pairs * T;
-        const int64_t rounds = ceil_div_i64(tiles, Tc3::CLUSTERS);
-        const double kb = fmax(2.0 * tw, (16384.0 + 64.0 * tw) / 42.0);
-        const double t = (double)rounds * (num_kb * kb + 700.0 + 6.0 * tw);
-        if (t < best_t * 0.999) { best_t = t; best = tw; }
+    int best = 0, best_s = 1; double best_t = 1e30;
+    const int smax = (allow_split && nsplit_out && split_env != 1) ? 4 : 1;
+    for (int S = 1; S <= smax; ++S) {
+        if (split_env > 1 && smax > 1 && S != split_env - 1 && (split_env - 1) <= 4) continue;
+        const int kbs = ceil_div(num_kb, S);
+        if (S > 1 && (kbs < 8 || (S - 1) * kbs >= num_kb)) continue;      // every split needs work; short splits are all prologue
+        for (int tw = 32; tw <= 256; tw += 16) {
+            if (tw_env && tw != tw_env) continue;
+            const int T = ceil_div(M, tw) + (M1 > 0 ? ceil_div(M1, tw) : 0);
+            const int64_t tiles = (int64_t)w_pairs * T;
+            if (S > 1 && tiles * 2 * TC3_EPI_WARPS > kFlagSlotInts) continue;
+            const int64_t rounds = ceil_div_i64(tiles * S, Tc3::CLUSTERS);
+            const double kb = fmax(2.0 * tw, (16384.0 + 64.0 * tw) / 42.0);
+            // split-K: the splits' epilogues are serialised (flag hop + membar + C read-back), measured ~8 us on top of the model
+            const double t = (double)rounds * (kbs * kb + 700.0 + 6.0 * tw) + (S > 1 ? 16000.0 : 0.0);
+            if (t < best_t * 0.999) { best_t = t; best = tw; best_s = S; }
+        }
     }
-    if (est_clk) *est_clk = best_t;
+    if (nsplit_out) *nsplit_out = best_s;
     return best;
+}
+
+// Split-K progress flags: one device buffer for the life of the library, used as a ring of slots so that launches that may run
+// concurrently (parallel graph branches) never share words; every kernel leaves its words at zero.
+int* g_flag_ring = nullptr;
+unsigned g_flag_next = 0;
+int* next_flag_slot(cudaStream_t stream) {
+    if (!g_flag_ring) {
+        cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(stream, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) { cudaGetLastError(); return nullptr; }
+        if (cudaMalloc(&g_flag_ring, sizeof(int) * kFlagSlotInts * kFlagSlots) != cudaSuccess) { cudaGetLastError(); g_flag_ring = nullptr; return nullptr; }
+        cudaMemset(g_flag_ring, 0, sizeof(int) * kFlagSlotInts * kFlagSlots);
+    }
+    return g_flag_ring + (size_t)(g_flag_next++ % kFlagSlots) * kFlagSlotInts;
 }
 
 int pick_bn(int N, int64_t mtiles) {
@@ -1011,7 +1070,15 @@ static int gemm_tc_impl(int M, int N, int K, const float* A, const float* A_lo, 
     SIU3R_REQUIRE(lda % 4 == 0 && ldw % 4 == 0 && lda >= K && ldw >= K);
     SIU3R_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)Wt & 15) == 0);
     const int64_t mtiles = ceil_div_i64(M, BM);
-    if (const int tw = (precision == 1 ? pick_tc3(M, N, K) : 0)) {
+    int nsplit = 1;
+    const bool can_split = (act & ACT_MASK) == ACT_NONE && rope_pos == nullptr;
+    int tw = precision == 1 ? pick_tc3(M, N, K, 0, can_split, &nsplit) : 0;
+    int* fl = nullptr;
+    if (tw && nsplit > 1) {
+        fl = next_flag_slot(stream);
+        if (!fl) { nsplit = 1; tw = pick_tc3(M, N, K); }     // no flag buffer yet and the stream is capturing: plain schedule
+    }
+    if (tw) {
         // persistent swapped pair kernel: weights on the MMA-M axis, tokens on the MMA-N axis
         CUtensorMap mw, mx;
         uint64_t dimsW[2] = {(uint64_t)K, (uint64_t)N}; uint64_t strW[1] = {(uint64_t)ldw * 4}; uint32_t boxW[2] = {BK, BM};
@@ -1027,6 +1094,8 @@ static int gemm_tc_impl(int M, int N, int K, const float* A, const float* A_lo, 
         grp.prob[0] = Tc3Problem{C, bias, residual, M};
         grp.prob[1] = grp.prob[0];
         grp.tiles0 = w_pairs * ceil_div(M, tw);
+        grp.nsplit = 1; grp.kb_per_split = p.num_kb; grp.flags = nullptr;
+        if (nsplit > 1) { grp.nsplit = nsplit; grp.kb_per_split = ceil_div(p.num_kb, nsplit); grp.flags = fl; }
         return launch_tc3(mw, mx, mw, mx, p, grp, w_pairs, grp.tiles0, tw, stream);
     }
     if (precision == 1 && forced_kernel() != 4 && use_tc2(N, mtiles)) {
@@ -1091,8 +1160,12 @@ int siu3r_gemm_tc_group2(const int* M_host, int N, int K, const float* const* A_
     SIU3R_REQUIRE(lda % 4 == 0 && ldw % 4 == 0 && lda >= K && ldw >= K);
     for (int g = 0; g < 2; ++g) SIU3R_REQUIRE(A_host[g] && W_host[g] && C_host[g] && ((uintptr_t)A_host[g] & 15) == 0 && ((uintptr_t)W_host[g] & 15) == 0);
     if (positions) SIU3R_REQUIRE(rope_tab && rope_cols > 0 && rope_cols % 64 == 0 && rope_cols <= N && ((uintptr_t)rope_tab & 15) == 0 && !residual_host);
-    const int tw = pick_tc3(M_host[0], N, K, M_host[1]);
+    int nsplit = 1;
+    const bool can_split = (act & ACT_MASK) == ACT_NONE && positions == nullptr;
+    int tw = pick_tc3(M_host[0], N, K, M_host[1], can_split, &nsplit);
     if (tw == 0) return SIU3R_ERR_UNSUPPORTED;
+    int* fl = nsplit > 1 ? next_flag_slot(stream) : nullptr;
+    if (nsplit > 1 && !fl) { nsplit = 1; tw = pick_tc3(M_host[0], N, K, M_host[1]); }
     CUtensorMap mw[2], mx[2];
     for (int g = 0; g < 2; ++g) {
         uint64_t dimsW[2] = {(uint64_t)K, (uint64_t)N}; uint64_t strW[1] = {(uint64_t)ldw * 4}; uint32_t boxW[2] = {BK, BM};
@@ -1108,6 +1181,7 @@ int siu3r_gemm_tc_group2(const int* M_host, int N, int K, const float* const* A_
     for (int g = 0; g < 2; ++g)
         grp.prob[g] = Tc3Problem{C_host[g], bias_host ? bias_host[g] : nullptr, residual_host ? residual_host[g] : nullptr, M_host[g]};
     grp.tiles0 = w_pairs * ceil_div(M_host[0], tw);
+    grp.nsplit = nsplit; grp.kb_per_split = ceil_div(p.num_kb, nsplit); grp.flags = fl;
     const int tiles = grp.tiles0 + w_pairs * ceil_div(M_host[1], tw);
     return launch_tc3(mw[0], mx[0], mw[1], mx[1], p, grp, w_pairs, tiles, tw, stream);
 }

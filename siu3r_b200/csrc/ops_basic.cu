@@ -15,13 +15,17 @@ __device__ __forceinline__ float rn_tf32(float x) {
 // like ATen.  Replaces nn.LayerNorm in croco/blocks.py:119,123,176,180-184 (eps 1e-6, croco/croco.py:35),
 // vit_adapter/vit_adapter.py:74-93, mask2former/video_seg_decoder.py:945-952,1738-1744 (eps 1e-5).
 // ------------------------------------------------------------------------------------------------------------
+// Second segment of a grouped launch (siu3r_layernorm_group2): rows >= rows0 read x1 / w1 / b1 and write y1 (row index rebased).
+struct LnSeg2 { const float* x1; const float* w1; const float* b1; float* y1; int rows0; };
+
 template <int VEC_PER_LANE>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ w,
                                                         const float* __restrict__ b, float* __restrict__ y, int64_t ldy, int rows, int C,
-                                                        float eps, const float* __restrict__ add, int64_t ldadd, int round_out) {
-    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+                                                        float eps, const float* __restrict__ add, int64_t ldadd, int round_out, LnSeg2 g) {
+    int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
+    if (g.x1 && row >= g.rows0) { row -= g.rows0; x = g.x1; w = g.w1; b = g.b1; y = g.y1; }
     const float4* xr = reinterpret_cast<const float4*>(x + (int64_t)row * ldx);
     const int nvec = C >> 2;
     float4 v[VEC_PER_LANE];
@@ -425,8 +429,8 @@ inline unsigned grid_for(int64_t n, int threads = 256) { return (unsigned)((n + 
 
 extern "C" {
 
-int siu3r_layernorm(const float* x, int64_t ldx, const float* w, const float* b, float* y, int64_t ldy, int rows, int C, float eps,
-                    const float* add, int64_t ldadd, int round_out, void* stream_) {
+static int layernorm_impl(const float* x, int64_t ldx, const float* w, const float* b, float* y, int64_t ldy, int rows, int C,
+                          float eps, const float* add, int64_t ldadd, int round_out, LnSeg2 g, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     SIU3R_REQUIRE(x && w && b && y && rows > 0 && C > 0 && C % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0);
     SIU3R_REQUIRE(C <= 4096);
@@ -434,14 +438,28 @@ int siu3r_layernorm(const float* x, int64_t ldx, const float* w, const float* b,
     const int vpl = ceil_div(nvec, 32);
     const int wpb = 8;
     dim3 grid(ceil_div(rows, wpb));
-    if (vpl <= 2) layernorm_kernel<2><<<grid, wpb * 32, 0, stream>>>(x, ldx, w, b, y, ldy, rows, C, eps, add, ldadd, round_out);
-    else if (vpl <= 6) layernorm_kernel<6><<<grid, wpb * 32, 0, stream>>>(x, ldx, w, b, y, ldy, rows, C, eps, add, ldadd, round_out);
-    else if (vpl <= 8) layernorm_kernel<8><<<grid, wpb * 32, 0, stream>>>(x, ldx, w, b, y, ldy, rows, C, eps, add, ldadd, round_out);
-    else layernorm_kernel<32><<<grid, wpb * 32, 0, stream>>>(x, ldx, w, b, y, ldy, rows, C, eps, add, ldadd, round_out);
+    if (vpl <= 2) layernorm_kernel<2><<<grid, wpb * 32, 0, stream>>>(x, ldx, w, b, y, ldy, rows, C, eps, add, ldadd, round_out, g);
+    else if (vpl <= 6) layernorm_kernel<6><<<grid, wpb * 32, 0, stream>>>(x, ldx, w, b, y, ldy, rows, C, eps, add, ldadd, round_out, g);
+    else if (vpl <= 8) layernorm_kernel<8><<<grid, wpb * 32, 0, stream>>>(x, ldx, w, b, y, ldy, rows, C, eps, add, ldadd, round_out, g);
+    else layernorm_kernel<32><<<grid, wpb * 32, 0, stream>>>(x, ldx, w, b, y, ldy, rows, C, eps, add, ldadd, round_out, g);
     SIU3R_LAUNCH_CHECK();
     siu3r_note_launch(1);
     return SIU3R_OK;
 }
+int siu3r_layernorm(const float* x, int64_t ldx, const float* w, const float* b, float* y, int64_t ldy, int rows, int C, float eps,
+                    const float* add, int64_t ldadd, int round_out, void* stream) {
+    return layernorm_impl(x, ldx, w, b, y, ldy, rows, C, eps, add, ldadd, round_out, LnSeg2{nullptr, nullptr, nullptr, nullptr, 0}, stream);
+}
+
+// Two LayerNorms with different affine parameters (and possibly different source / destination buffers) in one launch: the norm1 / norm2 /
+// norm3 / norm_y pairs of the two decoder streams (croco/blocks.py:186-190 under dec_blocks and dec_blocks2).  Same C, pitch and eps.
+int siu3r_layernorm_group2(const float* x0, const float* x1, int64_t ldx, const float* w0, const float* b0, const float* w1, const float* b1,
+                           float* y0, float* y1, int64_t ldy, int rows0, int rows1, int C, float eps, int round_out, void* stream) {
+    SIU3R_REQUIRE(x1 && w1 && b1 && y1 && rows0 > 0 && rows1 > 0);
+    SIU3R_REQUIRE(((uintptr_t)x1 & 15) == 0 && ((uintptr_t)y1 & 15) == 0 && ((uintptr_t)w1 & 15) == 0 && ((uintptr_t)b1 & 15) == 0);
+    return layernorm_impl(x0, ldx, w0, b0, y0, ldy, rows0 + rows1, C, eps, nullptr, 0, round_out, LnSeg2{x1, w1, b1, y1, rows0}, stream);
+}
+
 
 int siu3r_rope2d(float* tokens, const int64_t* positions, int B, int N, int H, int D, int64_t batch_stride, int64_t token_stride,
                  float base, float fwd, int nparts, int64_t part_stride, int round_out, void* stream_) {

@@ -666,9 +666,9 @@ class SIU3RModel:
         pos, tab = self._k.pos_enc, self._k.rope_tab        # positions are the same for every image
         split = lambda t: [t[a:b] for a, b in rows]
         # ---- self-attention ----
+        ln2 = lambda xs, wbs, outs: ops.layernorm_group2(xs, wbs, 1e-6, outs, round_out=self.R)   # both streams' norms in one launch
         h = torch.empty(R, C, device=self.dev)
-        for g, (a, b) in enumerate(rows):
-            self._ln(f[a:b], blks[g].n1, 1e-6, out=h[a:b])
+        ln2(split(f), [bk.n1 for bk in blks], split(h))
         qkv = torch.empty(R, 3 * C, device=self.dev)
         self._lin2(split(h), [bk.qkv for bk in blks], outs=split(qkv), ar=True, ro=True, rope=(pos, tab, 2 * C))
         att = torch.empty(R, C, device=self.dev)
@@ -683,14 +683,14 @@ class SIU3RModel:
         if V == 2:
             # stream 0 (view 0) attends to view 1, stream 1 (view 1) to view 0: memory rows are already image-aligned
             yn = torch.empty(R, C, device=self.dev)
-            self._ln(f[R0:], blks[0].ny, 1e-6, out=yn[:R0])
-            self._ln(f[:R0], blks[1].ny, 1e-6, out=yn[R0:])
+            ln2([f[R0:], f[:R0]], [bk.ny for bk in blks], split(yn))
             ctx = torch.empty(R, 2 * C, device=self.dev)
             self._lin2(split(yn), [bk.ckv for bk in blks], outs=split(ctx), ar=True, ro=True, rope=(pos, tab, C))
             Nk = N
         else:
-            yn0 = self._ln(f[R0:], blks[0].ny, 1e-6)          # views 1..V-1 under stream-0 weights
-            yn1 = self._ln(f, blks[1].ny, 1e-6)               # all views under stream-1 weights
+            yn0 = torch.empty(R - R0, C, device=self.dev)     # views 1..V-1 under stream-0 weights
+            yn1 = torch.empty(R, C, device=self.dev)          # all views under stream-1 weights
+            ln2([f[R0:], f], [bk.ny for bk in blks], [yn0, yn1])
             kv0 = torch.empty(R - R0, 2 * C, device=self.dev)
             kv1 = torch.empty(R, 2 * C, device=self.dev)
             self._lin2([yn0, yn1], [bk.ckv for bk in blks], outs=[kv0, kv1], ar=True, ro=True, rope=(pos, tab, C))
@@ -706,8 +706,7 @@ class SIU3RModel:
                         ops.rows_affine(src, out=ctx[i * B + b, slot * N:(slot + 1) * N])
                         slot += 1
         h2 = torch.empty(R, C, device=self.dev)
-        for g, (a, b) in enumerate(rows):
-            self._ln(x1[a:b], blks[g].n2, 1e-6, out=h2[a:b])
+        ln2(split(x1), [bk.n2 for bk in blks], split(h2))
         q = torch.empty(R, C, device=self.dev)
         self._lin2(split(h2), [bk.cq for bk in blks], outs=split(q), ar=True, ro=True, rope=(pos, tab, C))
         a2 = torch.empty(R, C, device=self.dev)
@@ -718,8 +717,7 @@ class SIU3RModel:
         self._lin2(split(a2), [bk.cproj for bk in blks], outs=split(x1), ar=True, residuals=split(x1))
         # ---- MLP ----
         h3 = torch.empty(R, C, device=self.dev)
-        for g, (a, b) in enumerate(rows):
-            self._ln(x1[a:b], blks[g].n3, 1e-6, out=h3[a:b])
+        ln2(split(x1), [bk.n3 for bk in blks], split(h3))
         m = torch.empty(R, 4 * C, device=self.dev)
         self._lin2(split(h3), [bk.fc1 for bk in blks], outs=split(m), ar=True, ro=True, act=ACT_GELU)
         self._lin2(split(m), [bk.fc2 for bk in blks], outs=split(x1), ar=True, residuals=split(x1))

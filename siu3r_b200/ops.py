@@ -311,6 +311,19 @@ def layernorm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float, out
     return out
 
 
+def layernorm_group2(xs, wbs, eps: float, outs, round_out: bool = False):
+    """outs[g] = LayerNorm(xs[g]; wbs[g]) for two row blocks with different affine parameters in one launch."""
+    _chk_f32(*xs, *outs, *wbs[0], *wbs[1])
+    Cc = xs[0].shape[1]
+    assert xs[1].shape[1] == Cc and xs[0].stride(0) == xs[1].stride(0) and outs[0].stride(0) == outs[1].stride(0)
+    assert all(t.stride(1) == 1 for t in (*xs, *outs))
+    code = _lib.load().siu3r_layernorm_group2(_p(xs[0]), _p(xs[1]), xs[0].stride(0), _p(wbs[0][0]), _p(wbs[0][1]), _p(wbs[1][0]), _p(wbs[1][1]),
+                                              _p(outs[0]), _p(outs[1]), outs[0].stride(0), xs[0].shape[0], xs[1].shape[0], Cc, eps,
+                                              1 if round_out else 0, _stream())
+    _lib.check(code, "layernorm_group2")
+    return outs
+
+
 def rope2d_(tokens_ptr_tensor: torch.Tensor, offset: int, positions: torch.Tensor, B: int, N: int, H: int, D: int, batch_stride: int,
             token_stride: int, base: float = 100.0, fwd: float = 1.0, nparts: int = 1, part_stride: int = 0, round_out: bool = False):
     """In-place 2-D RoPE on tokens[b,n,h,d] located at tokens.data_ptr() + 4*(offset + b*batch_stride + n*token_stride + h*D + d)."""

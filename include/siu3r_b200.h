@@ -54,6 +54,9 @@ int siu3r_raster_features_forward(int G, int H, int W, int C, int cov_stride, co
 /* testing aid: 0 disables the blend kernel's exact sub-tile culling (every pixel then evaluates every record of its tile, the
  * literal loop of the reference rasterizer); results must be bit-identical either way (tests/test_ops_gpu.py) */
 void siu3r_raster_set_culling(int enabled);
+/* testing aid: 0 = always bin / sort the duplicates the way the reference pipeline does (prefix scan over Gaussians, duplicateWithKeys, global
+ * 64-bit radix sort, identifyTileRanges) instead of the per-tile binned sort; both give the identical sorted list */
+void siu3r_raster_set_binning(int enabled);
 
 /* ---- dense contractions on the tcgen05 tensor cores ------------------------------------------------------------
  * siu3r_gemm_tc   : torch.nn.functional.linear (+bias, +GELU/ReLU, +residual): croco/blocks.py:74-77,97,110,154-156,167;

@@ -304,6 +304,144 @@ __global__ void __launch_bounds__(256) identify_tile_ranges_kernel(uint32_t D, c
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Binned fast path (replaces: scan over Gaussians -> duplicateWithKeys -> 6-pass global radix sort -> identifyTileRanges).
+// The global sort only ever orders records WITHIN a tile (the tile id is the high key word), so it is done per tile in shared memory:
+//   preprocess counts the duplicates of every tile (atomics on <= 8160 counters);
+//   tile_scan_kernel  : exclusive scan of the tile counts -> ranges[t] = (begin, end), total D, largest tile;
+//   bin_scatter_kernel: every Gaussian appends (depth bits << 32 | id) to the segments of its tiles (arbitrary order inside a segment);
+//   tile_sort_kernel  : one CTA per tile loads its segment into shared memory, bitonic-sorts the 64-bit words and writes the ids back.
+// (depth, id) is exactly the order the stable radix sort of (tile << 32 | depth) produces from records emitted in id order, so the
+// sorted list -- and everything downstream -- is bit-identical to the reference pipeline (tests/test_ops_gpu.py).  Tiles with more than
+// TS_CAP records fall back to the global sort for the whole frame.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int TS_CAP = 8192;          // records per tile that fit the shared-memory sort (64 KB)
+constexpr int TS_THREADS = 256;
+
+__global__ void __launch_bounds__(1024) tile_scan_kernel(const uint32_t* __restrict__ counts, int ntiles, uint2* __restrict__ ranges,
+                                                         uint32_t* __restrict__ cursors, uint32_t* __restrict__ total_max) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry, s_max;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) { s_carry = 0; s_max = 0; }
+    __syncthreads();
+    uint32_t mymax = 0;
+    for (int start = 0; start < ntiles; start += 1024) {
+        const int i = start + threadIdx.x;
+        const uint32_t c = i < ntiles ? counts[i] : 0u;
+        mymax = max(mymax, c);
+        uint32_t v = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t n = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += n; }
+        if (lane == 31) s_warp[warp] = v;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = s_warp[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t n = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += n; }
+            s_warp[lane] = w;
+        }
+        __syncthreads();
+        const uint32_t excl = s_carry + (warp > 0 ? s_warp[warp - 1] : 0u) + v - c;
+        if (i < ntiles) { ranges[i] = make_uint2(excl, excl + c); cursors[i] = excl; }
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry += s_warp[31];
+        __syncthreads();
+    }
+    atomicMax(&s_max, mymax);
+    __syncthreads();
+    if (threadIdx.x == 0) { total_max[0] = s_carry; total_max[1] = s_max; }
+}
+
+// Counting and scattering go through a per-CTA shared-memory histogram of the tiles: a CTA walks BIN_CHUNK Gaussians, so a tile that is hit k
+// times by the chunk costs one global atomic instead of k (500k splats @512^2: ~9x fewer, and far less same-address serialisation).
+constexpr int BIN_THREADS = 256, BIN_CHUNK = 4096;
+
+__global__ void __launch_bounds__(BIN_THREADS) bin_count_kernel(int G, int gx, int ntiles, const int32_t* __restrict__ radii,
+                                                               const ushort4* __restrict__ rects, uint32_t* __restrict__ tile_counts) {
+    extern __shared__ uint32_t s_cnt[];
+    for (int t = threadIdx.x; t < ntiles; t += BIN_THREADS) s_cnt[t] = 0;
+    __syncthreads();
+    const int g0 = blockIdx.x * BIN_CHUNK, g1 = min(G, g0 + BIN_CHUNK);
+    for (int i = g0 + threadIdx.x; i < g1; i += BIN_THREADS) {
+        if (radii[i] <= 0) continue;
+        const ushort4 r = rects[i];
+        for (uint32_t y = r.y; y < r.w; ++y)
+            for (uint32_t x = r.x; x < r.z; ++x) atomicAdd(&s_cnt[y * (uint32_t)gx + x], 1u);
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < ntiles; t += BIN_THREADS) {
+        const uint32_t c = s_cnt[t];
+        if (c) atomicAdd(&tile_counts[t], c);
+    }
+}
+
+__global__ void __launch_bounds__(BIN_THREADS) bin_scatter_kernel(int G, int gx, int ntiles, const int32_t* __restrict__ radii,
+                                                                 const float* __restrict__ depths, const ushort4* __restrict__ rects,
+                                                                 uint32_t* __restrict__ cursors, uint64_t* __restrict__ list) {
+    extern __shared__ uint32_t s_bin[];          // [ntiles] count, then local cursor | [ntiles] base of this CTA's run inside the tile segment
+    uint32_t* s_cnt = s_bin;
+    uint32_t* s_base = s_bin + ntiles;
+    for (int t = threadIdx.x; t < ntiles; t += BIN_THREADS) s_cnt[t] = 0;
+    __syncthreads();
+    const int g0 = blockIdx.x * BIN_CHUNK, g1 = min(G, g0 + BIN_CHUNK);
+    for (int i = g0 + threadIdx.x; i < g1; i += BIN_THREADS) {
+        if (radii[i] <= 0) continue;
+        const ushort4 r = rects[i];
+        for (uint32_t y = r.y; y < r.w; ++y)
+            for (uint32_t x = r.x; x < r.z; ++x) atomicAdd(&s_cnt[y * (uint32_t)gx + x], 1u);
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < ntiles; t += BIN_THREADS) {
+        const uint32_t c = s_cnt[t];
+        s_base[t] = c ? atomicAdd(&cursors[t], c) : 0u;   // reserve a contiguous run for this CTA
+        s_cnt[t] = 0;
+    }
+    __syncthreads();
+    for (int i = g0 + threadIdx.x; i < g1; i += BIN_THREADS) {
+        if (radii[i] <= 0) continue;
+        const ushort4 r = rects[i];
+        const uint64_t word = ((uint64_t)__float_as_uint(depths[i]) << 32) | (uint32_t)i;
+        for (uint32_t y = r.y; y < r.w; ++y)
+            for (uint32_t x = r.x; x < r.z; ++x) {
+                const uint32_t t = y * (uint32_t)gx + x;
+                list[s_base[t] + atomicAdd(&s_cnt[t], 1u)] = word;
+            }
+    }
+}
+
+// One CTA per tile: bitonic sort of the tile's (depth bits << 32 | id) words in shared memory.  Every thread keeps TS_ITEMS consecutive
+// elements, so the sub-passes with stride < TS_ITEMS stay in registers-by-way-of-private-smem without barriers.
+__global__ void __launch_bounds__(TS_THREADS) tile_sort_kernel(const uint2* __restrict__ ranges, const uint64_t* __restrict__ list,
+                                                               uint32_t* __restrict__ sorted_ids, uint64_t* __restrict__ sorted_words) {
+    extern __shared__ uint64_t s_w[];
+    const uint2 rg = ranges[blockIdx.x];
+    const int n = (int)(rg.y - rg.x);
+    if (n <= 0 || n > TS_CAP) return;
+    int P = 1;
+    while (P < n) P <<= 1;
+    for (int i = threadIdx.x; i < P; i += TS_THREADS) s_w[i] = i < n ? list[rg.x + i] : ~0ull;
+    __syncthreads();
+    const int half = P >> 1;
+    for (int k = 2; k <= P; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const int jm = j - 1;
+            for (int t = threadIdx.x; t < half; t += TS_THREADS) {
+                const int lo = ((t & ~jm) << 1) | (t & jm), hi = lo + j;     // j is a power of two
+                const bool up = (lo & k) == 0;
+                const uint64_t a = s_w[lo], b = s_w[hi];
+                if ((a > b) == up) { s_w[lo] = b; s_w[hi] = a; }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = threadIdx.x; i < n; i += TS_THREADS) {
+        const uint64_t w = s_w[i];
+        sorted_ids[rg.x + i] = (uint32_t)w;
+        if (sorted_words) sorted_words[rg.x + i] = w;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Blend: one CTA (256 threads) per 16x16 tile, front-to-back over the tile's sorted list in batches of 256 records that
 // are staged once in shared memory (id, xy, conic+opacity, rgb+depth = 44 B) and then broadcast-read by the pixels.
 //
@@ -651,7 +789,7 @@ __global__ void pack_camera_kernel(const float* __restrict__ view, const float* 
 
 struct Workspace {
     float* depths; float2* xy; float4* conic_o; float* rgb; uint32_t* tiles; ushort4* rects; uint32_t* offsets;
-    uint32_t* block_sums; uint32_t* total; float* cam; uint2* ranges;
+    uint32_t* block_sums; uint32_t* total; float* cam; uint2* ranges; uint32_t* tile_counts; uint32_t* tile_cursors;
     uint64_t* keys; uint64_t* keys_sorted; uint32_t* vals; uint32_t* vals_sorted; void* cub_temp; size_t cub_bytes;
     size_t bytes;
 };
@@ -690,6 +828,8 @@ Workspace carve(void* base, int G, int H, int W, int64_t cap) {
     w.total = (uint32_t*)take(256);
     w.cam = (float*)take(256);
     w.ranges = (uint2*)take(sizeof(uint2) * gx * gy);
+    w.tile_counts = (uint32_t*)take(sizeof(uint32_t) * gx * gy);
+    w.tile_cursors = (uint32_t*)take(sizeof(uint32_t) * gx * gy);
     w.keys = (uint64_t*)take(sizeof(uint64_t) * cap);
     w.keys_sorted = (uint64_t*)take(sizeof(uint64_t) * cap);
     w.vals = (uint32_t*)take(sizeof(uint32_t) * cap);
@@ -700,6 +840,7 @@ Workspace carve(void* base, int G, int H, int W, int64_t cap) {
     return w;
 }
 
+int g_binned = 1; // 0: always use the reference-shaped global radix sort (testing aid, see siu3r_raster_set_binning)
 int g_cull = 1;   // testing aid: 0 blends every record of the tile at every pixel (the unculled reference loop)
 
 }  // namespace
@@ -707,6 +848,7 @@ int g_cull = 1;   // testing aid: 0 blends every record of the tile at every pix
 extern "C" {
 
 void siu3r_raster_set_culling(int enabled) { g_cull = enabled ? 1 : 0; }
+void siu3r_raster_set_binning(int enabled) { g_binned = enabled ? 1 : 0; }
 
 // Bytes of device scratch siu3r_raster_forward needs for G Gaussians, an HxW image and at most `dup_capacity`
 // (tile, Gaussian) duplicates.  Mirrors the resize-callback buffers of the reference rasterizer (geomBuffer,
@@ -751,9 +893,15 @@ int siu3r_raster_forward(int G, int H, int W, int sh_degree, int sh_coeffs, int 
     const int deg = sh_degree > 3 ? 3 : sh_degree;  // the reference kernel evaluates SH bands 0..3 only
     const float focal_y = (float)H / (2.0f * tan_fovy), focal_x = (float)W / (2.0f * tan_fovx);
 
+    // The binned fast path produces the same sorted list and ranges; the debug exports of the reference pipeline's intermediate
+    // arrays (per-Gaussian offsets, 64-bit keys) only exist on the global-sort path.
+    const bool want_debug = debug_tiles_touched || debug_offsets || debug_keys || debug_values || debug_ranges;
+    bool binned = g_binned && !want_debug;
+
     SIU3R_CUDA_CHECK(cudaMemsetAsync(radii, 0, sizeof(int32_t) * G, stream));
     SIU3R_CUDA_CHECK(cudaMemsetAsync(w.tiles, 0, sizeof(uint32_t) * G, stream));
     SIU3R_CUDA_CHECK(cudaMemsetAsync(w.ranges, 0, sizeof(uint2) * gx * gy, stream));
+    if (binned) SIU3R_CUDA_CHECK(cudaMemsetAsync(w.tile_counts, 0, sizeof(uint32_t) * gx * gy, stream));
     if (n_touched) SIU3R_CUDA_CHECK(cudaMemsetAsync(n_touched, 0, sizeof(int32_t) * G, stream));
 
     pack_camera_kernel<<<1, 64, 0, stream>>>(viewmatrix, projmatrix, campos, bg, w.cam);
@@ -761,33 +909,73 @@ int siu3r_raster_forward(int G, int H, int W, int sh_degree, int sh_coeffs, int 
     preprocess_kernel<<<ceil_div(G, PRE_THREADS), PRE_THREADS, 0, stream>>>(G, H, W, gx, gy, deg, sh_coeffs, sh_layout, cov_stride,
                                                                             means3D, cov, shs, opacities, w.cam, tan_fovx, tan_fovy,
                                                                             focal_x, focal_y, po, radii);
-    const int nsb = ceil_div(G, SCAN_TILE);
-    scan_local_kernel<<<nsb, SCAN_THREADS, 0, stream>>>(w.tiles, w.offsets, w.block_sums, G);
-    scan_sums_kernel<<<1, SCAN_THREADS, 0, stream>>>(w.block_sums, nsb, w.total);
-    scan_add_kernel<<<nsb, SCAN_THREADS, 0, stream>>>(w.offsets, w.block_sums, G);
     SIU3R_LAUNCH_CHECK();
-    siu3r_note_launch(5);
-
-    uint32_t D32 = 0;
-    SIU3R_CUDA_CHECK(cudaMemcpyAsync(&D32, w.total, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-    SIU3R_CUDA_CHECK(cudaStreamSynchronize(stream));
-    const int64_t D = (int64_t)D32;
-    if (num_rendered_host) *num_rendered_host = D;
-    if (debug_tiles_touched) SIU3R_CUDA_CHECK(cudaMemcpyAsync(debug_tiles_touched, w.tiles, sizeof(uint32_t) * G, cudaMemcpyDeviceToDevice, stream));
-    if (debug_offsets) SIU3R_CUDA_CHECK(cudaMemcpyAsync(debug_offsets, w.offsets, sizeof(uint32_t) * G, cudaMemcpyDeviceToDevice, stream));
-    if (D > dup_capacity) return SIU3R_ERR_CAPACITY;
-
+    siu3r_note_launch(2);
     const uint64_t* sorted_keys = w.keys_sorted;
     const uint32_t* sorted_vals = w.vals_sorted;
-    if (D > 0) {
-        duplicate_with_keys_kernel<<<ceil_div(G, 256), 256, 0, stream>>>(G, gx, radii, w.offsets, w.depths, w.rects, w.keys, w.vals);
-        const int end_bit = 32 + higher_msb((uint32_t)(gx * gy));
-        size_t tb = w.cub_bytes;
-        SIU3R_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(w.cub_temp, tb, w.keys, w.keys_sorted, w.vals, w.vals_sorted, (int)D, 0,
-                                                         end_bit, stream));
-        identify_tile_ranges_kernel<<<(unsigned)ceil_div_i64(D, 256), 256, 0, stream>>>((uint32_t)D, sorted_keys, w.ranges);
+    int64_t D = 0;
+    const int ntiles = gx * gy;
+    if (binned && (size_t)ntiles * 8 > 200 * 1024) binned = false;        // per-CTA tile histograms must fit shared memory (<= 25600 tiles)
+    if (binned) {
+        static bool attr_bin = false;
+        if (!attr_bin) {
+            SIU3R_CUDA_CHECK(cudaFuncSetAttribute(bin_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            SIU3R_CUDA_CHECK(cudaFuncSetAttribute(bin_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr_bin = true;
+        }
+        bin_count_kernel<<<ceil_div(G, BIN_CHUNK), BIN_THREADS, (size_t)ntiles * 4, stream>>>(G, gx, ntiles, radii, w.rects, w.tile_counts);
+        tile_scan_kernel<<<1, 1024, 0, stream>>>(w.tile_counts, ntiles, w.ranges, w.tile_cursors, w.total);
         SIU3R_LAUNCH_CHECK();
         siu3r_note_launch(2);
+        uint32_t tm[2] = {0, 0};
+        SIU3R_CUDA_CHECK(cudaMemcpyAsync(tm, w.total, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+        SIU3R_CUDA_CHECK(cudaStreamSynchronize(stream));
+        D = (int64_t)tm[0];
+        if (num_rendered_host) *num_rendered_host = D;
+        if (D > dup_capacity) return SIU3R_ERR_CAPACITY;
+        if (tm[1] > (uint32_t)TS_CAP) {
+            binned = false;                                   // a tile too large for the shared-memory sort: global sort for this frame
+            SIU3R_CUDA_CHECK(cudaMemsetAsync(w.ranges, 0, sizeof(uint2) * gx * gy, stream));
+        } else if (D > 0) {
+            static bool attr = false;
+            if (!attr) {
+                SIU3R_CUDA_CHECK(cudaFuncSetAttribute(tile_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_CAP * 8));
+                attr = true;
+            }
+            bin_scatter_kernel<<<ceil_div(G, BIN_CHUNK), BIN_THREADS, (size_t)ntiles * 8, stream>>>(G, gx, ntiles, radii, w.depths, w.rects,
+                                                                                                  w.tile_cursors, w.keys);
+            int P = 1;
+            while (P < (int)tm[1]) P <<= 1;                   // shared memory for the largest tile of this frame
+            tile_sort_kernel<<<gx * gy, TS_THREADS, (size_t)P * 8, stream>>>(w.ranges, w.keys, w.vals_sorted, nullptr);
+            SIU3R_LAUNCH_CHECK();
+            siu3r_note_launch(2);
+        }
+    }
+    if (!binned) {
+        const int nsb = ceil_div(G, SCAN_TILE);
+        scan_local_kernel<<<nsb, SCAN_THREADS, 0, stream>>>(w.tiles, w.offsets, w.block_sums, G);
+        scan_sums_kernel<<<1, SCAN_THREADS, 0, stream>>>(w.block_sums, nsb, w.total);
+        scan_add_kernel<<<nsb, SCAN_THREADS, 0, stream>>>(w.offsets, w.block_sums, G);
+        SIU3R_LAUNCH_CHECK();
+        siu3r_note_launch(3);
+        uint32_t D32 = 0;
+        SIU3R_CUDA_CHECK(cudaMemcpyAsync(&D32, w.total, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+        SIU3R_CUDA_CHECK(cudaStreamSynchronize(stream));
+        D = (int64_t)D32;
+        if (num_rendered_host) *num_rendered_host = D;
+        if (debug_tiles_touched) SIU3R_CUDA_CHECK(cudaMemcpyAsync(debug_tiles_touched, w.tiles, sizeof(uint32_t) * G, cudaMemcpyDeviceToDevice, stream));
+        if (debug_offsets) SIU3R_CUDA_CHECK(cudaMemcpyAsync(debug_offsets, w.offsets, sizeof(uint32_t) * G, cudaMemcpyDeviceToDevice, stream));
+        if (D > dup_capacity) return SIU3R_ERR_CAPACITY;
+        if (D > 0) {
+            duplicate_with_keys_kernel<<<ceil_div(G, 256), 256, 0, stream>>>(G, gx, radii, w.offsets, w.depths, w.rects, w.keys, w.vals);
+            const int end_bit = 32 + higher_msb((uint32_t)(gx * gy));
+            size_t tb = w.cub_bytes;
+            SIU3R_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(w.cub_temp, tb, w.keys, w.keys_sorted, w.vals, w.vals_sorted, (int)D, 0,
+                                                             end_bit, stream));
+            identify_tile_ranges_kernel<<<(unsigned)ceil_div_i64(D, 256), 256, 0, stream>>>((uint32_t)D, sorted_keys, w.ranges);
+            SIU3R_LAUNCH_CHECK();
+            siu3r_note_launch(2);
+        }
     }
     dim3 grid(gx, gy), block(RB);
     if (n_touched)

@@ -248,9 +248,17 @@ def main():
     torch.cuda.synchronize()
     model.serial = False
     fam = {}
-    for f, work, s, e in ops.PROFILE:
+    shapes = {}
+    for f, work, s, e, tag in ops.PROFILE:
         d = fam.setdefault(f, [0.0, 0.0, 0])
-        d[0] += s.elapsed_time(e); d[1] += work; d[2] += 1
+        t_ = s.elapsed_time(e)
+        d[0] += t_; d[1] += work; d[2] += 1
+        if tag is not None:
+            sh = shapes.setdefault(tag, [0.0, 0.0, 0])
+            sh[0] += t_; sh[1] += work; sh[2] += 1
+    if os.environ.get("SIU3R_BENCH_SHAPES") and rank == 0:   # per-shape table of the tensor-core launches (stderr)
+        for tag, (t_, wk, n_) in sorted(shapes.items(), key=lambda kv: -kv[1][0])[:40]:
+            print(f"{str(tag):44s} x{n_:4d} {t_:8.3f} ms  {wk / (t_ / 1e3) / 1e12:7.1f} TFLOP/s  {1e3 * t_ / n_:7.1f} us/launch", file=sys.stderr)
     ops.PROFILE = None
     peaks = {}
     try:

@@ -81,6 +81,10 @@ int siu3r_gemm_tc_group2(const int* M_host, int N, int K, const float* const* A_
 int siu3r_conv2d_tc(int Nimg, int H, int W, int Cin, int Cout, int KH, int KW, int pad_h, int pad_w, const float* x, const float* x_lo,
                     const float* Wt, const float* W_lo, float* y, int64_t ldc, const float* bias, const float* residual,
                     int64_t ldr, int act, int precision, void* stream);
+/* input_merger step of the Gaussian-parameter head (heads/dpt_gs_head.py:113-119,155-164) fused: KH x 1 conv over the row-packed image
+ * (siu3r_im2col_nhwc with KH = 1) + bias + act + bilinear x2 (align_corners=True) upsampling of `low` [H/2, W/2, Cout] as residual; one image */
+int siu3r_conv_rows_up2x_tc(int H, int W, int KH, int pad, int Cout, const float* rows, const float* Wt, const float* bias, const float* low,
+                            float* out, int64_t ldc, int act, void* stream);
 /* plain fp32 FFMA GEMM (tiny / odd shapes such as the K = 9 intrinsics encoder, backbone_croco.py:59,278) */
 int siu3r_gemm_simt(int M, int N, int K, const float* A, int64_t lda, const float* W, int64_t ldw, float* C, int64_t ldc,
                     const float* bias, const float* residual, int64_t ldr, int act, float alpha, void* stream);

@@ -56,6 +56,12 @@ struct GemmParams {
     const float* rope_tab;     // [maxpos][16] (cos, sin) pairs from siu3r_rope2d_table (head dim 64)
     int rope_cols;             // columns [0, rope_cols) are rotated (multiple of 64)
     long long* dbg;            // optional: per-CTA clock64 stamps [cta][8] (tools/gemm_probe.py), null in production
+    // gemm_tc3 "rows" mode: KH x 1 convolution over a flattened [H*W, 32] row-packed image (one k-block = one vertical tap):
+    // k-block kb reads the X operand rows m + (kb - rows_pad) * rows_W at K offset 0 (TMA zero-fills above / below the image)
+    int rows_W, rows_pad;
+    // ... with the residual taken from a bilinear x2 (align_corners) upsampling of a [up_h, up_w, N] map computed in the epilogue
+    int up_h, up_w;
+    float up_sh, up_sw;
 };
 
 // ------------------------------------------------------------------------------------------------------------
@@ -681,19 +687,60 @@ __device__ __forceinline__ void epi_chunk_swapped(const uint32_t (&v)[32], int j
     }
 }
 
+// Epilogue fragment of the fused "7x7 image conv + ReLU + bilinear x2 upsampled trunk" step of the Gaussian-parameter head
+// (heads/dpt_gs_head.py:162-164 after :155-160): x = act(acc + bias) + bilinear(low)[pixel m, channel n], align_corners = True, same source
+// index arithmetic as siu3r_resize_bilinear_nhwc.  The 4 taps of a pixel are 128-byte lines across the warp (lane = channel).
+template <bool RND>
+__device__ __forceinline__ void epi_chunk_swapped_up2x(const uint32_t (&v)[32], int jmax, int n, bool n_ok, float bias, int mrow, const GemmParams& p,
+                                                       const Tc3Problem& pr) {
+    const int W = 2 * p.up_w;
+    const int act = p.act & ACT_MASK;
+    int y = mrow / W, x = mrow - y * W;
+    const float* __restrict__ low = pr.residual + n;
+    float* __restrict__ cp = pr.C + (int64_t)mrow * p.ldc + n;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {            // 16 pixels at a time: all 64 tap loads are issued before any of them is consumed
+        float t00[16], t01[16], t10[16], t11[16], wy[16], wx[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const float sy = p.up_sh * (float)y, sx = p.up_sw * (float)x;
+            int y0 = (int)sy, x0 = (int)sx;
+            if (y0 > p.up_h - 1) y0 = p.up_h - 1;
+            if (x0 > p.up_w - 1) x0 = p.up_w - 1;
+            const int y1 = y0 + (y0 < p.up_h - 1 ? 1 : 0), x1 = x0 + (x0 < p.up_w - 1 ? 1 : 0);
+            wy[j] = sy - (float)y0; wx[j] = sx - (float)x0;
+            const bool ok = (h * 16 + j) < jmax && n_ok;
+            const float* r0 = low + (int64_t)y0 * p.up_w * p.N;
+            const float* r1 = low + (int64_t)y1 * p.up_w * p.N;
+            t00[j] = ok ? __ldg(r0 + (int64_t)x0 * p.N) : 0.f; t01[j] = ok ? __ldg(r0 + (int64_t)x1 * p.N) : 0.f;
+            t10[j] = ok ? __ldg(r1 + (int64_t)x0 * p.N) : 0.f; t11[j] = ok ? __ldg(r1 + (int64_t)x1 * p.N) : 0.f;
+            if (++x == W) { x = 0; ++y; }
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int jj = h * 16 + j;
+            const float up = (1.f - wy[j]) * ((1.f - wx[j]) * t00[j] + wx[j] * t01[j]) + wy[j] * ((1.f - wx[j]) * t10[j] + wx[j] * t11[j]);
+            float r = epi_act(__uint_as_float(v[jj]) * p.alpha + bias, act) + up;
+            if (RND) r = rn_tf32(r);
+            if (jj < jmax && n_ok) cp[(int64_t)jj * p.ldc] = r;
+        }
+    }
+}
+
 // split / nsplit / flag: split-K.  Split 0 writes C = alpha*acc + bias + residual, split s > 0 waits until the SAME warp slot of split s-1 has
 // published its part of the tile (flag == s), then accumulates C += alpha*acc (the last split applies the TF32 rounding) and publishes s+1
 // (the last split resets the word to 0 for the next launch).  One writer per flag word and phase: plain release / acquire, no atomics, and a
 // fixed summation order -> bit-reproducible results.
+template <bool UP2X>
 __device__ __forceinline__ void run_epilogue_swapped(uint32_t tmem_acc, int lane, int q, int c_lo, int c_hi, int n_cta, int m_base,
                                                      const GemmParams& p, const Tc3Problem& pr_in, uint64_t* bar, uint32_t parity, int split,
                                                      int nsplit, int* flag) {
     const int nb = n_cta + q * 32;           // warp-uniform first weight row
     const int n = nb + lane;
     const bool n_ok = n < p.N;
-    Tc3Problem pr = pr_in;
-    int64_t ldr = p.ldr;
-    if (split > 0) { pr.bias = nullptr; pr.residual = pr_in.C; ldr = p.ldc; }
+    // split s > 0 accumulates into C: "residual" = C itself (pitch ldc), no bias
+    const Tc3Problem pr{pr_in.C, split > 0 ? nullptr : pr_in.bias, split > 0 ? (const float*)pr_in.C : pr_in.residual, pr_in.M};
+    const int64_t ldr = split > 0 ? p.ldc : p.ldr;
     const float bias = (pr.bias && n_ok) ? __ldg(pr.bias + n) : 0.0f;
     const int act = p.act & ACT_MASK;
     const bool rnd = (p.act & ACT_ROUND_TF32) != 0 && split == nsplit - 1;
@@ -722,6 +769,11 @@ __device__ __forceinline__ void run_epilogue_swapped(uint32_t tmem_acc, int lane
         if (jmax > 32) jmax = 32;
         if (jmax > pr.M - mrow) jmax = pr.M - mrow;
         if (jmax <= 0) break;
+        if (UP2X) {
+            if (rnd) epi_chunk_swapped_up2x<true>(v, jmax, n, n_ok, bias, mrow, p, pr);
+            else epi_chunk_swapped_up2x<false>(v, jmax, n, n_ok, bias, mrow, p, pr);
+            continue;
+        }
         switch (variant) {
             case 0: epi_chunk_swapped<ACT_NONE, true, false, false>(v, jmax, lane, n, n_ok, bias, mrow, axis, p, pr, ldr); break;
             case 1: epi_chunk_swapped<ACT_NONE, true, false, true>(v, jmax, lane, n, n_ok, bias, mrow, axis, p, pr, ldr); break;
@@ -748,7 +800,8 @@ __device__ __forceinline__ void run_epilogue_swapped(uint32_t tmem_acc, int lane
     }
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC3_THREADS, 1)
+template <bool UP2X>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC3_THREADS, 1)   // 168 registers: 10 warps are allocated as 12
 gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
                 const __grid_constant__ CUtensorMap tmX1, const GemmParams p, const Tc3Group grp, int w_pairs, int num_tiles, int tw) {
     using C_ = Tc3;
@@ -806,7 +859,8 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                     const uint32_t lead_full = mapa_to_cta(smem_u32(&full_bar[stage]), 0);
                     if (leader) mbar_expect_tx(&full_bar[stage], stage_tx);
                     tma2_load_2d(mw, lead_full, sW, kb * BK, n0);
-                    tma2_load_2d(mx, lead_full, sX, kb * BK, m0);
+                    if (UP2X) tma2_load_2d(mx, lead_full, sX, 0, m0 + (kb - p.rows_pad) * p.rows_W);
+                    else tma2_load_2d(mx, lead_full, sX, kb * BK, m0);
                     if (++stage == C_::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -857,8 +911,11 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             const int n_cta = (tl % w_pairs) * 2 * BM + (int)rank * BM;
             const int m_base = (tl / w_pairs) * tw;
             int* flag = grp.flags ? grp.flags + ((size_t)t * 2 + rank) * TC3_EPI_WARPS + (warp - 2) : nullptr;
-            run_epilogue_swapped(tmem_base + (uint32_t)(buf * 256), lane, q, c_lo, c_hi, n_cta, m_base, p, grp.prob[g], &tfull_bar[buf],
-                                 ((uint32_t)it >> 1) & 1u, split, grp.nsplit, flag);
+            // (static member selection: a runtime index into the kernel-parameter struct would force a local copy of it)
+            const Tc3Problem prob{g ? grp.prob[1].C : grp.prob[0].C, g ? grp.prob[1].bias : grp.prob[0].bias,
+                                  g ? grp.prob[1].residual : grp.prob[0].residual, g ? grp.prob[1].M : grp.prob[0].M};
+            run_epilogue_swapped<UP2X>(tmem_base + (uint32_t)(buf * 256), lane, q, c_lo, c_hi, n_cta, m_base, p, prob, &tfull_bar[buf],
+                                       ((uint32_t)it >> 1) & 1u, split, grp.nsplit, flag);
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(lead_tempty0 + (uint32_t)(buf * 8));
@@ -871,25 +928,26 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C_::TMEM_COLS) : "memory");
 }
 
+template <bool UP2X = false>
 int launch_tc3(const CUtensorMap& w, const CUtensorMap& x, const CUtensorMap& w1, const CUtensorMap& x1, const GemmParams& p, const Tc3Group& grp,
                int w_pairs, int num_tiles, int tw, cudaStream_t stream) {
     using C_ = Tc3;
     static int max_clusters = 0;
     if (max_clusters == 0) {
-        SIU3R_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM_BYTES));
+        SIU3R_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc3_kernel<UP2X>, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM_BYTES));
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(2 * C_::CLUSTERS); cfg.blockDim = dim3(TC3_THREADS); cfg.dynamicSmemBytes = C_::SMEM_BYTES;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
         int n = 0;
-        if (cudaOccupancyMaxActiveClusters(&n, gemm_tc3_kernel, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = 64; }
+        if (cudaOccupancyMaxActiveClusters(&n, gemm_tc3_kernel<UP2X>, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = 64; }
         max_clusters = n;
         if (getenv("SIU3R_GEMM_VERBOSE")) fprintf(stderr, "[siu3r_b200] gemm_tc3: %d resident clusters, %d stages, %d B smem\n", n, C_::STAGES, C_::SMEM_BYTES);
     }
     const int units = num_tiles * grp.nsplit;
     const int clusters = units < max_clusters ? units : max_clusters;
-    gemm_tc3_kernel<<<dim3((unsigned)(2 * clusters)), TC3_THREADS, C_::SMEM_BYTES, stream>>>(w, x, w1, x1, p, grp, w_pairs, num_tiles, tw);
+    gemm_tc3_kernel<UP2X><<<dim3((unsigned)(2 * clusters)), TC3_THREADS, C_::SMEM_BYTES, stream>>>(w, x, w1, x1, p, grp, w_pairs, num_tiles, tw);
     SIU3R_LAUNCH_CHECK();
     siu3r_note_launch(1);
     return SIU3R_OK;
@@ -1184,6 +1242,39 @@ int siu3r_gemm_tc_group2(const int* M_host, int N, int K, const float* const* A_
     grp.nsplit = nsplit; grp.kb_per_split = ceil_div(p.num_kb, nsplit); grp.flags = fl;
     const int tiles = grp.tiles0 + w_pairs * ceil_div(M_host[1], tw);
     return launch_tc3(mw[0], mx[0], mw[1], mx[1], p, grp, w_pairs, tiles, tw, stream);
+}
+
+// KH x 1 convolution over a row-packed image + activation + bilinear x2 (align_corners) upsampled residual, one image per call:
+//   out[(y, x), co] = act( sum_kh rows[(y + kh - pad, x), :] . Wt[co, kh*32 : kh*32+32] + bias[co] ) + up2x(low)[(y, x), co]
+// rows [H*W, 32] is siu3r_im2col_nhwc(KH = 1, KW) of the image (the KW horizontal taps of <= 32/KW channels packed per pixel), Wt
+// [Cout, KH*32] the matching row-packed filter, low [H/2, W/2, Cout].  This is the input_merger step of the Gaussian-parameter head
+// (heads/dpt_gs_head.py:113-119,155-164: F.interpolate(path_1, x2, bilinear, align_corners=True) + ReLU(Conv7x7(image))) in ONE
+// persistent tensor-core launch: the [H, W, Cout] upsampled map is never materialised.  TF32 only; -4 when the shape is not eligible.
+int siu3r_conv_rows_up2x_tc(int H, int W, int KH, int pad, int Cout, const float* rows, const float* Wt, const float* bias, const float* low,
+                            float* out, int64_t ldc, int act, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    SIU3R_REQUIRE(H > 0 && W > 0 && KH > 0 && pad >= 0 && Cout > 0 && rows && Wt && low && out && H % 2 == 0 && W % 2 == 0);
+    SIU3R_REQUIRE(((uintptr_t)rows & 15) == 0 && ((uintptr_t)Wt & 15) == 0);
+    const int M = H * W, K = KH * BK;
+    const int tw = pick_tc3(M, Cout, K);
+    if (tw == 0 || Cout % 32 != 0) return SIU3R_ERR_UNSUPPORTED;
+    CUtensorMap mw, mx;
+    uint64_t dimsW[2] = {(uint64_t)K, (uint64_t)Cout}; uint64_t strW[1] = {(uint64_t)K * 4}; uint32_t boxW[2] = {BK, BM};
+    int r = make_map(&mw, Wt, 2, dimsW, strW, boxW); if (r) return r;
+    uint64_t dimsX[2] = {(uint64_t)BK, (uint64_t)M}; uint64_t strX[1] = {(uint64_t)BK * 4}; uint32_t boxX[2] = {BK, (uint32_t)(tw / 2)};
+    r = make_map(&mx, rows, 2, dimsX, strX, boxX); if (r) return r;
+    GemmParams p{};
+    p.M = M; p.N = Cout; p.num_kb = KH; p.C = out; p.ldc = ldc; p.bias = bias; p.act = act; p.alpha = 1.0f; p.conv = 0;
+    p.rows_W = W; p.rows_pad = pad; p.up_h = H / 2; p.up_w = W / 2;
+    p.up_sh = H > 1 ? (float)(H / 2 - 1) / (float)(H - 1) : 0.f;
+    p.up_sw = W > 1 ? (float)(W / 2 - 1) / (float)(W - 1) : 0.f;
+    const int w_pairs = ceil_div(Cout, 256);
+    Tc3Group grp{};
+    grp.prob[0] = Tc3Problem{out, bias, low, M};
+    grp.prob[1] = grp.prob[0];
+    grp.tiles0 = w_pairs * ceil_div(M, tw);
+    grp.nsplit = 1; grp.kb_per_split = p.num_kb; grp.flags = nullptr;
+    return launch_tc3<true>(mw, mx, mw, mx, p, grp, w_pairs, grp.tiles0, tw, stream);
 }
 
 // nn.Linear followed by RoPE-2D on output columns [0, rope_cols) (head dim 64), i.e. the qkv / q / kv projections of

@@ -369,8 +369,10 @@ class SIU3RModel:
         """-> raw Gaussian parameters [B, S*S, 83] (model.py:195-210)."""
         p1 = self._dpt_trunk(hw, toks, B, N, gh, gw)
         n, h, w_, c = p1.shape
-        up = ops.resize_bilinear(p1, 2 * h, 2 * w_, True)
-        s = self._conv(img4, hw.merger, 7, ro=True, pad=3, act=ACT_RELU, residual=up)
+        s = ops.conv_kxk_up2x(img4, hw.merger, 7, 7, p1, act=ACT_RELU, round_out=True) if self.R else None   # fused: no [S,S,256] upsampled map
+        if s is None:
+            up = ops.resize_bilinear(p1, 2 * h, 2 * w_, True)
+            s = self._conv(img4, hw.merger, 7, ro=True, pad=3, act=ACT_RELU, residual=up)
         t = self._conv(s, hw.head0, 3, ar=True, ro=True, pad=1, act=ACT_RELU)
         raw = torch.empty(B, 4 * h * w_, 83, device=self.dev)
         self._lin(t.view(-1, 256), hw.head4, ar=True, out=raw.view(-1, 83))

@@ -28,10 +28,10 @@ PROFILE = None
 
 
 class _Prof:
-    __slots__ = ("fam", "work", "s")
+    __slots__ = ("fam", "work", "s", "tag")
 
-    def __init__(self, fam, work):
-        self.fam, self.work = fam, work
+    def __init__(self, fam, work, tag=None):
+        self.fam, self.work, self.tag = fam, work, tag
         self.s = None
 
     def __enter__(self):
@@ -44,7 +44,7 @@ class _Prof:
         if self.s is not None:
             e = torch.cuda.Event(enable_timing=True)
             e.record()
-            PROFILE.append((self.fam, self.work, self.s, e))
+            PROFILE.append((self.fam, self.work, self.s, e, self.tag))
 
 
 def _p(t):
@@ -161,12 +161,12 @@ def gemm(x: torch.Tensor, wt: Weight, out: torch.Tensor | None = None, act: int 
     if rope is not None:
         pos, tab, ncols = rope
         assert residual is None and alpha == 1.0 and pos.dtype == torch.int64 and pos.is_contiguous() and pos.numel() == 2 * M
-        with _Prof("gemm_tc", 2.0 * M * wt.N * K):
+        with _Prof("gemm_tc", 2.0 * M * wt.N * K, ("rope", M, wt.N, K)):
             code = _lib.load().siu3r_gemm_tc_rope(M, wt.N, K, _p(x), _p(x_lo), x.stride(0), _p(wt.w), _p(wt.w_lo), ldw, _p(out), out.stride(0),
                                                   _p(b), act, precision, _p(pos), _p(tab), ncols, _stream())
         _lib.check(code, "gemm_tc_rope")
         return out
-    with _Prof("gemm_tc", 2.0 * M * wt.N * K):
+    with _Prof("gemm_tc", 2.0 * M * wt.N * K, ("lin", M, wt.N, K)):
         code = _lib.load().siu3r_gemm_tc(M, wt.N, K, _p(x), _p(x_lo), x.stride(0), _p(wt.w), _p(wt.w_lo), ldw, _p(out), out.stride(0), _p(b),
                                          _p(residual), 0 if residual is None else residual.stride(0), act, alpha, precision, _stream())
     _lib.check(code, "gemm_tc")
@@ -211,7 +211,7 @@ def gemm_group2(xs, wts, outs=None, act: int = ACT_NONE, residuals=None, precisi
         pos, tab, ncols = rope[0], rope[1], rope[2]
         assert residuals[0] is None and pos.dtype == torch.int64 and pos.is_contiguous() and pos.numel() >= 2 * max(Ms[0], Ms[1])
     work = 2.0 * (Ms[0] + Ms[1]) * w0.N * K
-    with _Prof("gemm_tc", work):
+    with _Prof("gemm_tc", work, ("grp2", Ms[0] + Ms[1], w0.N, K)):
         code = _lib.load().siu3r_gemm_tc_group2(Ms, w0.N, K, arr(xs), xs[0].stride(0), arr([w0.w, w1.w]), w0.w.shape[1], arr(outs), outs[0].stride(0),
                                                 None if w0.bias is None else arr([w0.bias, w1.bias]),
                                                 None if residuals[0] is None else arr(residuals),
@@ -281,7 +281,7 @@ def conv2d(x: torch.Tensor, wt: Weight, KH: int, KW: int, stride: int = 1, pad: 
                 xx = round_tf32(x)
             if round_out:
                 act = act | ACT_ROUND_TF32
-        with _Prof("conv2d_tc", 2.0 * N * H * W * Cout * KH * KW * Cin):
+        with _Prof("conv2d_tc", 2.0 * N * H * W * Cout * KH * KW * Cin, ("conv", N * H * W, Cout, KH * KW * Cin)):
             code = _lib.load().siu3r_conv2d_tc(N, H, W, Cin, Cout, KH, KW, pad_h, pad_w, _p(xx), _p(x_lo), _p(wt.w), _p(wt.w_lo), _p(out), Cout,
                                                _p(wt.bias), _p(residual), Cout, act, precision, _stream())
         _lib.check(code, "conv2d_tc")
@@ -295,6 +295,32 @@ def conv2d(x: torch.Tensor, wt: Weight, KH: int, KW: int, stride: int = 1, pad: 
     assert K <= ldo
     gemm(cols, wt, out=out.view(-1, Cout), act=act, residual=None if residual is None else residual.view(-1, Cout), precision=precision,
          a_rounded=True, round_out=round_out)
+    return out
+
+
+def conv_kxk_up2x(x: torch.Tensor, wt: Weight, KH: int, KW: int, low: torch.Tensor, act: int = ACT_NONE, round_out: bool = False,
+                  out: torch.Tensor | None = None):
+    """out = act(conv_{KH x KW, stride 1, same padding}(x) + bias) + bilinear_x2_align_corners(low), TF32, for a few-channel image x
+    [N,H,W,Cin] with KW*Cin <= 32 (the RGB(+pad) image of the Gaussian-parameter head's input_merger) and low [N,H/2,W/2,Cout]:
+    the horizontal taps are packed per pixel (1 x KW im2col, 32 floats), the vertical taps + the upsampled residual run in one persistent
+    tensor-core launch per image.  Returns None when the shape is not eligible (caller uses resize_bilinear + conv2d)."""
+    N, H, W, Cin = x.shape
+    Cout = wt.N
+    if KW * Cin > 32 or H % 2 or W % 2 or tuple(low.shape) != (N, H // 2, W // 2, Cout) or not low.is_contiguous():
+        return None
+    lib = _lib.load()
+    rows = torch.empty(N, H, W, 32, device=x.device, dtype=torch.float32)
+    _lib.check(lib.siu3r_im2col_nhwc(_p(x), N, H, W, Cin, 1, KW, 1, 0, KW // 2, _p(rows), 32, 1, _stream()), "im2col(rows)")
+    wr = wt.rowpacked(KH, KW, Cin)
+    if out is None:
+        out = torch.empty(N, H, W, Cout, device=x.device, dtype=torch.float32)
+    a = act | (ACT_ROUND_TF32 if round_out else 0)
+    for n in range(N):
+        with _Prof("conv2d_tc", 2.0 * H * W * Cout * KH * KW * Cin, ("rows_up2x", H * W, Cout, KH * 32)):
+            code = lib.siu3r_conv_rows_up2x_tc(H, W, KH, KH // 2, Cout, _p(rows[n]), _p(wr.w), _p(wr.bias), _p(low[n]), _p(out[n]), Cout, a, _stream())
+        if code == -4:
+            return None
+        _lib.check(code, "conv_rows_up2x_tc")
     return out
 
 

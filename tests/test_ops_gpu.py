@@ -618,3 +618,29 @@ def test_raster_binned_sort_equals_global_sort(G, H, W, pa):
     assert a["num_rendered"] == b["num_rendered"]
     for kk in ("color", "depth", "opacity", "radii", "n_touched"):
         assert torch.equal(a[kk], b[kk]), kk
+
+
+@pytest.mark.parametrize("H,W", [(64, 64), (96, 160), (512, 512)])
+def test_conv_rows_up2x_fused_matches_unfused(H, W):
+    """input_merger of the GS head fused (7x7 image conv + ReLU + bilinear x2 of the trunk output in one launch) against the unfused
+    resize_bilinear + conv2d path and against torch (fp32, TF32-rounded operands)."""
+    import torch.nn.functional as F
+    from siu3r_b200 import ops
+    torch.manual_seed(H)
+    N, Cout = 1, 256
+    x = torch.zeros(N, H, W, 4, device=DEV)
+    x[..., :3] = torch.rand(N, H, W, 3, device=DEV)
+    low = torch.randn(N, H // 2, W // 2, Cout, device=DEV)
+    w = torch.randn(Cout, 7, 7, 4, device=DEV) / 12
+    w[..., 3] = 0
+    b = torch.randn(Cout, device=DEV) * 0.1
+    wt = ops.Weight(w.reshape(Cout, -1), b, ops.PREC_TF32)
+    fused = ops.conv_kxk_up2x(x, wt, 7, 7, low, act=ops.ACT_RELU, round_out=False)
+    assert fused is not None
+    up = ops.resize_bilinear(low, H, W, True)
+    unfused = ops.conv2d(x, wt, 7, 7, pad=3, act=ops.ACT_RELU, residual=up)
+    assert float((fused - unfused).abs().max()) < 2e-4 * max(1.0, float(unfused.abs().max()))
+    xr, wr = ops.round_tf32(x.contiguous()), wt.w[:, :196].reshape(Cout, 7, 7, 4)
+    ref = F.relu(F.conv2d(xr.permute(0, 3, 1, 2), wr.permute(0, 3, 1, 2), b, padding=3)) + F.interpolate(low.permute(0, 3, 1, 2), size=(H, W),
+                                                                                                        mode="bilinear", align_corners=True)
+    assert float((fused - ref.permute(0, 2, 3, 1)).abs().max()) < 2e-3 * max(1.0, float(ref.abs().max()))

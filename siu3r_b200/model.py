@@ -827,11 +827,8 @@ class SIU3RModel:
 
     multiview = False   # SIU3RMultiViewModel sets True
 
-    @torch.no_grad()
-    def forward(self, context_views_images, context_views_intrinsics, mask_labels=None, class_labels=None, enable_query_class_logit_lift=False):
+    def _check_inputs(self, imgs):
         assert self._ready, "call load_state_dict(...).cuda() first"
-        assert mask_labels is None and class_labels is None, "training losses are out of scope (SURVEY.md section 8)"
-        imgs = context_views_images
         B, V, _, S0, S1 = imgs.shape
         if self.multiview:
             assert V >= 2, "SIU3RMultiViewModel needs at least two context views"
@@ -839,33 +836,56 @@ class SIU3RModel:
             assert V == 2, "two-view path; the V-view model is SIU3RMultiViewModel"
         assert S0 % 16 == 0 and S1 % 16 == 0, f"Input image size ({S0}x{S1}) is not a multiple of patch size (16)."
         assert (S0, S1) == tuple(self.cfg.image_size), "model was built for a different image_size (vit_adapter.py:328-329)"
+        return B, V, S0, S1
+
+    @torch.no_grad()
+    def forward_async(self, context_views_images, context_views_intrinsics, slot: int = 0):
+        """Enqueue the device part of forward() without waiting for it and return a handle for forward_finish().  With
+        enable_cuda_graph() every `slot` has its own captured graph, static buffers and stream, so the forwards of consecutive pairs
+        overlap on the GPU (serving.PairPipeline, bench.py): slot s may be re-submitted once its previous handle has been finished."""
+        imgs = context_views_images
+        B, V, S0, S1 = self._check_inputs(imgs)
+        cur = torch.cuda.current_stream()
         if getattr(self, "_use_graph", False) and self.capture is None:
-            key = (B, V, S0, S1)
+            key = (B, V, S0, S1, slot)
             if key not in self._graphs:
                 si = torch.empty(B, V, 3, S0, S1, device=self.dev)
                 sk = torch.empty(B, V, 3, 3, device=self.dev)
                 si.copy_(imgs)
                 sk.copy_(context_views_intrinsics)
                 side = torch.cuda.Stream()
-                side.wait_stream(torch.cuda.current_stream())
+                side.wait_stream(cur)
                 with torch.cuda.stream(side):
                     self._forward_device(si, sk)  # warm-up: builds host tables, sets kernel attributes
-                torch.cuda.current_stream().wait_stream(side)
+                cur.wait_stream(side)
                 torch.cuda.synchronize()
                 graph = torch.cuda.CUDAGraph()
                 n0 = ops.launch_count()
                 with torch.cuda.graph(graph):
                     outs = self._forward_device(si, sk)
-                self._graphs[key] = (graph, si, sk, outs, ops.launch_count() - n0)  # kernels of ours per replay
-            graph, si, sk, outs, nlaunch = self._graphs[key]
-            si.copy_(imgs, non_blocking=True)
-            sk.copy_(context_views_intrinsics, non_blocking=True)
-            graph.replay()
+                self._graphs[key] = (graph, si, sk, outs, ops.launch_count() - n0, torch.cuda.Stream(device=self.dev))  # kernels of ours per replay
+            graph, si, sk, outs, nlaunch, st = self._graphs[key]
+            st.wait_stream(cur)            # inputs produced / previous results of this slot consumed on the caller's stream
+            with torch.cuda.stream(st):
+                si.copy_(imgs, non_blocking=True)
+                sk.copy_(context_views_intrinsics, non_blocking=True)
+                graph.replay()
+                done = torch.cuda.Event()
+                done.record(st)
             ops._lib.load().siu3r_note_launch(nlaunch)
         else:
             imgs = imgs.to(self.dev, torch.float32).contiguous()
             Kin = context_views_intrinsics.to(self.dev, torch.float32).contiguous()
             outs = self._forward_device(imgs, Kin)
+            done = None
+        return (outs, done, (B, V, S0, S1))
+
+    @torch.no_grad()
+    def forward_finish(self, handle, enable_query_class_logit_lift=False):
+        """Second half of forward(): waits for the device part of `handle` and runs the panoptic post-process (host decisions)."""
+        outs, done, (B, V, S0, S1) = handle
+        if done is not None:
+            torch.cuda.current_stream().wait_event(done)
         means, cov, harm, opac, scales, rots, cls_logits, mask_logits = outs
         gaussians = Gaussians(means=means, covariances=cov, harmonics=harm, opacities=opac, scales=scales, rotations=rots)
         h4, w4 = S0 // 4, S1 // 4
@@ -878,6 +898,11 @@ class SIU3RModel:
             gaussians.seg_query_class_logits = qc_list
             return gaussians, seg_output, seg_masks, seg_infos, qscores
         return gaussians, seg_output, seg_masks, seg_infos
+
+    @torch.no_grad()
+    def forward(self, context_views_images, context_views_intrinsics, mask_labels=None, class_labels=None, enable_query_class_logit_lift=False):
+        assert mask_labels is None and class_labels is None, "training losses are out of scope (SURVEY.md section 8)"
+        return self.forward_finish(self.forward_async(context_views_images, context_views_intrinsics), enable_query_class_logit_lift)
 
 
 class SIU3RMultiViewModel(SIU3RModel):

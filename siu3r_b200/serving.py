@@ -14,18 +14,20 @@ GAUSSIAN_FIELDS = ("means", "covariances", "harmonics", "opacities", "scales", "
 
 
 class PairPipeline:
-    """submit(images, intrinsics) -> result of the PREVIOUS submit (or None); flush() -> result of the last one.
+    """submit(images, intrinsics) -> finished result of the pair submitted two calls earlier (or None); flush() -> the remaining results.
+    Pair n computes (graph slot n % 2) while pair n-1 is post-processed / snapshotted and pair n-2 is being downloaded.
 
     A result is (host_gaussians: dict[str, pinned tensor], seg_masks, seg_infos).  The pinned tensors of a slot are
     reused `depth` submits later: consume (or copy) them before that.
     """
 
-    def __init__(self, model, depth: int = 2, fields=GAUSSIAN_FIELDS):
-        assert depth >= 2
+    def __init__(self, model, depth: int = 3, fields=GAUSSIAN_FIELDS):
+        assert depth >= 3, "one slot downloading, one being post-processed, one being overwritten"
         self.model, self.depth, self.fields = model, depth, tuple(fields)
         self.copy_stream = torch.cuda.Stream(device=model.dev)
         self.slots = [dict(dev={}, host={}, snap=torch.cuda.Event(), done=torch.cuda.Event(), meta=None) for _ in range(depth)]
         self.n = 0
+        self._pending = None
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
@@ -34,14 +36,27 @@ class PairPipeline:
         return slot["host"], *slot["meta"]
 
     def submit(self, images: torch.Tensor, intrinsics: torch.Tensor):
-        cur = torch.cuda.current_stream()
-        slot = self.slots[self.n % self.depth]
-        prev = self.slots[(self.n - 1) % self.depth] if self.n > 0 else None
-        if images.device.type == "cpu":   # forward() uploads (pinned -> device, asynchronous) itself
+        """Enqueue pair n; returns the finished result of pair n-1 (None for the first call).  The forward of pair n (graph slot n % 2) is
+        already running on the GPU while pair n-1 is post-processed, snapshotted and downloaded."""
+        if images.device.type == "cpu":   # forward_async() uploads (pinned -> device, asynchronous) itself
             self.h2d_bytes = images.numel() * images.element_size() + intrinsics.numel() * intrinsics.element_size()
-        out = self.model(images, intrinsics)
+        handle = self.model.forward_async(images, intrinsics, slot=self.n % 2)
+        prev = self._retire()
+        self._pending = (self.n, handle)
+        self.n += 1
+        return prev
+
+    def _retire(self):
+        """Finish the pending forward: post-process, device-side snapshot, asynchronous download; returns the PREVIOUS finished result."""
+        if self._pending is None:
+            return None
+        idx, handle = self._pending
+        self._pending = None
+        cur = torch.cuda.current_stream()
+        slot = self.slots[idx % self.depth]
+        out = self.model.forward_finish(handle)
         g, seg_masks, seg_infos = out[0], out[2], out[3]
-        if self.n >= self.depth:
+        if idx >= self.depth:
             cur.wait_event(slot["done"])   # the slot's previous download has left the snapshot buffers
         nbytes = 0
         for name in self.fields:
@@ -59,10 +74,19 @@ class PairPipeline:
                 slot["host"][name].copy_(slot["dev"][name], non_blocking=True)
             slot["done"].record(self.copy_stream)
         slot["meta"] = (seg_masks, seg_infos)
-        self.n += 1
-        return self._collect(prev) if prev is not None else None
+        prev_idx = idx - 1
+        ready = self._collect(self.slots[prev_idx % self.depth]) if prev_idx >= 0 else None
+        self._last = idx
+        return ready
 
-    def flush(self):
+    def flush(self) -> list:
+        """Drain: returns the results that submit() has not handed out yet (at most two), in submission order."""
         if self.n == 0:
-            return None
-        return self._collect(self.slots[(self.n - 1) % self.depth])
+            return []
+        out = []
+        if self._pending is not None:
+            r = self._retire()
+            if r is not None:
+                out.append(r)
+        out.append(self._collect(self.slots[(self.n - 1) % self.depth]))
+        return out

@@ -177,7 +177,8 @@ def test_pair_pipeline_matches_direct_forward():
         r = pipe.submit(img.pin_memory(), K.pin_memory())
         if r is not None:
             got.append({n: t.clone() for n, t in r[0].items()})
-    got.append({n: t.clone() for n, t in pipe.flush()[0].items()})
+    for r in pipe.flush():
+        got.append({n: t.clone() for n, t in r[0].items()})
     assert len(got) == len(direct)
     for a, b in zip(got, direct):
         for n in GAUSSIAN_FIELDS:

@@ -24,6 +24,7 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 METRIC = "image_pairs_per_s_512x512"
+NSLOTS = int(os.environ.get("SIU3R_BENCH_SLOTS", "2"))   # graph slots alternated by the timed loop
 FLOPS_PER_SAMPLE_512_V4 = 8.657e12  # same source: one 4-view 512^2 sample through SIU3RMultiViewModel
 FLOPS_PER_PAIR_512 = 4.059e12  # algorithmic 2*MAC FLOPs of one 512^2 pair (FlopCounterMode on the reference)
 
@@ -210,7 +211,7 @@ def main():
             return
         pend = None
         for i in range(n):
-            h = model.forward_async(img_d, K_d, slot=i % 2)
+            h = model.forward_async(img_d, K_d, slot=i % NSLOTS)
             if pend is not None:
                 model.forward_finish(pend)
             pend = h

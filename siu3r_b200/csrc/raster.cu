@@ -316,6 +316,7 @@ __global__ void __launch_bounds__(256) identify_tile_ranges_kernel(uint32_t D, c
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int TS_CAP = 8192;          // records per tile that fit the shared-memory sort (64 KB)
 constexpr int TS_THREADS = 256;
+constexpr int TS_FAST = 2048;         // largest tile for which the binned path is used (measured: above it the global radix sort is faster)
 
 __global__ void __launch_bounds__(1024) tile_scan_kernel(const uint32_t* __restrict__ counts, int ntiles, uint2* __restrict__ ranges,
                                                          uint32_t* __restrict__ cursors, uint32_t* __restrict__ total_max) {
@@ -933,8 +934,8 @@ int siu3r_raster_forward(int G, int H, int W, int sh_degree, int sh_coeffs, int 
         D = (int64_t)tm[0];
         if (num_rendered_host) *num_rendered_host = D;
         if (D > dup_capacity) return SIU3R_ERR_CAPACITY;
-        if (tm[1] > (uint32_t)TS_CAP) {
-            binned = false;                                   // a tile too large for the shared-memory sort: global sort for this frame
+        if (tm[1] > (uint32_t)TS_FAST) {
+            binned = false;                                   // big tiles: the O(n log^2 n) shared-memory sort loses to the global radix sort
             SIU3R_CUDA_CHECK(cudaMemsetAsync(w.ranges, 0, sizeof(uint2) * gx * gy, stream));
         } else if (D > 0) {
             static bool attr = false;

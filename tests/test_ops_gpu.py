@@ -602,7 +602,7 @@ def test_splatting_render_qc_logits_surface():
 def test_raster_binned_sort_equals_global_sort(G, H, W, pa):
     """The per-tile binned sort (tile counts -> scatter -> shared-memory bitonic sort of (depth bits, id)) must reproduce the sorted list of the
     reference-shaped pipeline (global stable radix sort of (tile << 32 | depth)): identical images, depth, opacity, radii and n_touched.
-    The last case puts ~26 000 records per tile (> the shared-memory capacity) and exercises the fallback."""
+    The last case puts ~26 000 records per tile (above the binned path's tile limit) and exercises the fallback to the global sort."""
     from siu3r_b200 import _lib, ops
     lib = _lib.load()
     sc, view, full, campos, tx, ty = _raster_case(G, H, W, 21, pa)

@@ -316,6 +316,24 @@ def main():
             "vit_tensor_pipe_frac": value / world * (FLOPS_PER_PAIR_512 if V == 2 else FLOPS_PER_SAMPLE_512_V4 * V / 4) * (S / 512.0) ** 2 / 1e12 / tf32_peak,
             "roofline": roofline}
 
+    # ---- BASELINE configs[2]: the one collective of the path -- all-gather of the packed render records (88 fp32 per Gaussian) so that every
+    #      rank holds the Gaussians of all pairs for joint-scene rasterisation (N > 1 only; not part of `value`) ----
+    if world > 1:
+        try:
+            from siu3r_b200 import parallel
+            g0 = model(img_d, K_d)[0]
+            rec = parallel.pack_render_record(g0)
+            for _ in range(2):
+                parallel.all_gather_gaussians(rec)
+            ms_ag = timed(lambda: parallel.all_gather_gaussians(rec), 5) / 5
+            nbytes = rec.numel() * 4
+            line["allgather"] = {"what": "NCCL all_gather_into_tensor of the packed render records (means 3 + cov 9 + SH 75 + opacity 1 fp32 per Gaussian)",
+                                 "bytes_contributed_per_rank": nbytes, "bytes_gathered_per_rank": nbytes * world, "ms": ms_ag,
+                                 "algbw_GBs": nbytes * world / ms_ag / 1e6, "busbw_GBs": nbytes * (world - 1) / ms_ag / 1e6}
+            del g0, rec
+        except Exception as ex:
+            line["allgather"] = {"error": repr(ex)}
+
     # ---- BASELINE configs[3]: 4-view sample through SIU3RMultiViewModel (short, N = 1 only; not the headline) ----
     if V == 2 and world == 1 and not args.no_multiview:
         try:

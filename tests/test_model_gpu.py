@@ -184,3 +184,41 @@ def test_pair_pipeline_matches_direct_forward():
         for n in GAUSSIAN_FIELDS:
             assert torch.equal(a[n], b[n]), n
     assert pipe.h2d_bytes == 2 * 3 * S * S * 4 + 18 * 4 and pipe.d2h_bytes > 0
+
+
+def test_pair_model_batch2_matches_oracle_port():
+    """Two pairs per call (the per-GPU shard of BASELINE configs[2] is 4 pairs): every sample against the oracle port."""
+    from oracle import torch_port as TP
+    from siu3r_b200 import synth
+    from siu3r_b200.model import ModelCfg, SIU3RModel
+    S, B = 64, 2
+    img, K = synth.pair_inputs(B, 2, S, seed=11)
+    K = K.clone()
+    K[1, :, 0, 0] *= 1.07
+    ref = TP.forward(synth.make_state_dict(), img, K)
+    model = SIU3RModel(ModelCfg(image_size=(S, S)), precision="fp32x3")
+    model.load_state_dict(synth.make_state_dict())
+    model.cuda()
+    g, seg_out, seg_masks, seg_infos = model(img.cuda(), K.cuda())
+    for n in ("means", "covariances", "harmonics", "opacities", "scales", "rotations"):
+        got, want = getattr(g, n).cpu(), ref[n]
+        assert got.shape == want.shape and float((got - want).abs().max()) < 1e-3, n
+    ml, rl = seg_out.masks_queries_logits.cpu(), ref["masks_queries_logits"]
+    assert ml.shape == rl.shape and float((ml - rl).abs().max()) < 1e-4 * float(rl.abs().max())
+    assert [len(s) for s in seg_infos] == [len(s) for s in ref["seg_infos"]]
+    # the overlapped two-slot execution returns the same results as plain forward() calls, in order
+    model2 = SIU3RModel(ModelCfg(image_size=(S, S)), precision="tf32")
+    model2.load_state_dict(synth.make_state_dict())
+    model2.cuda()
+    model2.enable_cuda_graph()
+    ins = [synth.pair_inputs(1, 2, S, seed=s) for s in (1, 2, 3, 4)]
+    plain = [model2(i.cuda(), k.cuda())[0].means.clone() for i, k in ins]
+    outs, pend = [], None
+    for n, (i, k) in enumerate(ins):
+        h = model2.forward_async(i.cuda(), k.cuda(), slot=n % 2)
+        if pend is not None:
+            outs.append(model2.forward_finish(pend)[0].means.clone())
+        pend = h
+    outs.append(model2.forward_finish(pend)[0].means.clone())
+    for a, b in zip(plain, outs):
+        assert float((a - b).abs().max()) < 1e-5

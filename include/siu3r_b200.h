@@ -77,7 +77,14 @@ int siu3r_gemm_tc_rope(int M, int N, int K, const float* A, const float* A_lo, i
  * residual_host may be null); M_host[2] rows per problem.  -4 when the shape is not eligible (issue two siu3r_gemm_tc instead). */
 int siu3r_gemm_tc_group2(const int* M_host, int N, int K, const float* const* A_host, int64_t lda, const float* const* W_host, int64_t ldw,
                          float* const* C_host, int64_t ldc, const float* const* bias_host, const float* const* residual_host, int64_t ldr,
-                         int act, float alpha, const int64_t* positions, const float* rope_tab, int rope_cols, void* stream);
+                         int act, float alpha, const int64_t* positions, const float* rope_tab, int rope_cols, float* const* vt_host,
+                         const int* vt_cols_host, int64_t vt_ld, int vt_col0, void* stream);
+/* siu3r_gemm_tc_rope with the output columns >= vt_col0 (the V third of a qkv projection) written as V^T [(n - vt_col0)][m] (pitch vt_ld)
+ * instead of C: the operand siu3r_flash_attn_tc consumes with vt_batch_cols = tokens per image (no siu3r_transpose_v pass).  In the grouped
+ * call vt_host[g] / vt_cols_host[g] give each problem's (16-byte aligned) column window inside the V^T rows. */
+int siu3r_gemm_tc_rope_vt(int M, int N, int K, const float* A, int64_t lda, const float* Wt, int64_t ldw, float* C, int64_t ldc, const float* bias,
+                          int act, const int64_t* positions, const float* rope_tab, int rope_cols, float* vt, int64_t vt_ld, int vt_col0,
+                          void* stream);
 int siu3r_conv2d_tc(int Nimg, int H, int W, int Cin, int Cout, int KH, int KW, int pad_h, int pad_w, const float* x, const float* x_lo,
                     const float* Wt, const float* W_lo, float* y, int64_t ldc, const float* bias, const float* residual,
                     int64_t ldr, int act, int precision, void* stream);
@@ -116,8 +123,10 @@ int siu3r_flash_attn_d64(const float* Q, int64_t q_bs, int64_t q_ts, const float
 /* tcgen05 / TMEM flash attention (TF32 mode) and its V^T producer: same contract as siu3r_flash_attn_d64 */
 int siu3r_transpose_v(const float* V, int64_t v_bs, int64_t v_ts, int B, int N, int H, float* Vt, int64_t ld, void* stream);
 int siu3r_flash_attn_tc(const float* Q, int64_t q_bs, int64_t q_ts, int q_width, int q_col0, const float* K, int64_t k_bs,
-                        int64_t k_ts, int k_width, int k_col0, const float* Vt, int64_t vt_ld, float* O, int64_t o_bs,
+                        int64_t k_ts, int k_width, int k_col0, const float* Vt, int64_t vt_ld, int64_t vt_batch_cols, float* O, int64_t o_bs,
                         int64_t o_ts, int B, int H, int Nq, int Nk, float scale, int round_out, void* stream);
+/* vt_batch_cols = 0: Vt rows are (b*H + h)*64 + d, columns = keys of image b (siu3r_transpose_v layout);
+ * vt_batch_cols > 0: Vt rows are h*64 + d, image b's keys start at column b * vt_batch_cols (layout written by siu3r_gemm_tc_rope_vt) */
 /* masked / plain attention with head dim 32: mask2former/video_seg_decoder.py:975-983,994-999,1306-1308.
  * Keys are split over CTAs (K/V staged once per head in shared memory); workspace = scratch for the row flags and the
  * per-split softmax partials, at least siu3r_attn_small_d32_ws_bytes(B, H, Nq, Nk) bytes, 256-byte aligned. */

@@ -36,12 +36,13 @@ SIGNATURES = {
     "siu3r_conv_rows_up2x_tc": (_i, [_i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _l, _i, _p]),
     "siu3r_ply_record_words": (_i, [_i, _i, _i, _i]),
     "siu3r_ply_pack": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _l, _i, _i, _i, _p, _p]),
-    "siu3r_gemm_tc_group2": (_i, [_p, _i, _i, _p, _l, _p, _l, _p, _l, _p, _p, _l, _i, _f, _p, _p, _i, _p]),
+    "siu3r_gemm_tc_group2": (_i, [_p, _i, _i, _p, _l, _p, _l, _p, _l, _p, _p, _l, _i, _f, _p, _p, _i, _p, _p, _l, _i, _p]),
+    "siu3r_gemm_tc_rope_vt": (_i, [_i, _i, _i, _p, _l, _p, _l, _p, _l, _p, _i, _p, _p, _i, _p, _l, _i, _p]),
     "siu3r_gemm_tc_rope": (_i, [_i, _i, _i, _p, _p, _l, _p, _p, _l, _p, _l, _p, _i, _i, _p, _p, _i, _p]),
     "siu3r_rope2d_table": (_i, [_p, _i, _i, _f, _f, _p]),
     "siu3r_rope2d": (_i, [_p, _p, _i, _i, _i, _i, _l, _l, _f, _f, _i, _l, _i, _p]),
     "siu3r_transpose_v": (_i, [_p, _l, _l, _i, _i, _i, _p, _l, _p]),
-    "siu3r_flash_attn_tc": (_i, [_p, _l, _l, _i, _i, _p, _l, _l, _i, _i, _p, _l, _p, _l, _l, _i, _i, _i, _i, _f, _i, _p]),
+    "siu3r_flash_attn_tc": (_i, [_p, _l, _l, _i, _i, _p, _l, _l, _i, _i, _p, _l, _l, _p, _l, _l, _i, _i, _i, _i, _f, _i, _p]),
     "siu3r_layernorm_group2": (_i, [_p, _p, _l, _p, _p, _p, _p, _p, _p, _l, _i, _i, _i, _f, _i, _p]),
     "siu3r_layernorm": (_i, [_p, _l, _p, _p, _p, _l, _i, _i, _f, _p, _l, _i, _p]),
     "siu3r_flash_attn_d64": (_i, [_p, _l, _l, _p, _l, _l, _p, _l, _l, _p, _l, _l, _i, _i, _i, _i, _f, _i, _i, _p]),

@@ -36,6 +36,7 @@ struct FlashParams {
     float scale_log2e;
     float* O; int64_t o_bs, o_ts;
     int round_out;
+    long long vt_batch_cols;     // 0: V^T rows indexed by (b, h, d); > 0: rows (h, d), image b at column offset b * vt_batch_cols
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -175,7 +176,11 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
     const int q0 = qt * FT_BM;
-    const int ntiles = (p.Nk + FT_BN - 1) / FT_BN;
+    // TMA needs a 16-byte aligned start in the innermost (key) dimension of V^T.  When image b's keys start at an unaligned column
+    // (vt_batch_cols = tokens per image, e.g. 1025) the key tiling is shifted down by kshift = start & 3 keys: tile t covers keys
+    // [t*64 - kshift, ...), the (at most 3) phantom keys in front of key 0 are masked like the padding behind key Nk-1.
+    const int kshift = p.vt_batch_cols ? (int)(((long long)b * p.vt_batch_cols) & 3) : 0;
+    const int ntiles = (p.Nk + kshift + FT_BN - 1) / FT_BN;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQ) : "memory");
@@ -215,14 +220,16 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 mbar_wait(&bars[B_KEMPTY + buf], (use & 1) ^ 1);
                 uint8_t* dK = sK + buf * FT_K_BYTES;
                 mbar_expect_tx(&bars[B_KFULL + buf], FT_K_BYTES);
-                tma_load_3d(&tmK, &bars[B_KFULL + buf], dK, p.k_col0 + h * FT_D, t * FT_BN, b);
-                tma_load_3d(&tmK, &bars[B_KFULL + buf], dK + FT_BN * FT_BK * 4, p.k_col0 + h * FT_D + FT_BK, t * FT_BN, b);
+                tma_load_3d(&tmK, &bars[B_KFULL + buf], dK, p.k_col0 + h * FT_D, t * FT_BN - kshift, b);
+                tma_load_3d(&tmK, &bars[B_KFULL + buf], dK + FT_BN * FT_BK * 4, p.k_col0 + h * FT_D + FT_BK, t * FT_BN - kshift, b);
                 mbar_wait(&bars[B_VFREE + buf], (use & 1) ^ 1);      // P V of tile t-2 has read this V buffer
                 uint8_t* dV = sV + buf * FT_V_BYTES;
                 mbar_expect_tx(&bars[B_VFULL + buf], FT_V_BYTES);
 #pragma unroll
                 for (int j = 0; j < FT_BN / FT_BK; ++j)
-                    tma_load_2d(&tmVt, &bars[B_VFULL + buf], dV + j * FT_D * FT_BK * 4, t * FT_BN + j * FT_BK, (b * p.H + h) * FT_D);
+                    tma_load_2d(&tmVt, &bars[B_VFULL + buf], dV + j * FT_D * FT_BK * 4,
+                                (int)(p.vt_batch_cols ? b * p.vt_batch_cols : 0) + t * FT_BN - kshift + j * FT_BK,
+                                (p.vt_batch_cols ? h : b * p.H + h) * FT_D);
             }
         }
     } else if (warp == 1) {
@@ -281,11 +288,12 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             tmem_ld32(tS, v0);
             tmem_ld32(tS + 32, v1);
             tmem_ld_wait();
-            const int kvalid = p.Nk - t * FT_BN;   // columns >= kvalid are padding (only ever on the last tile)
-            if (kvalid < FT_BN) {                   // -inf scores: they drop out of the maximum and exponentiate to exactly 0
+            const int kvalid = p.Nk - (t * FT_BN - kshift);    // columns >= kvalid are padding (only ever on the last tile)
+            const int klo = t == 0 ? kshift : 0;               // columns < klo are the phantom keys of a shifted tiling (first tile only)
+            if (kvalid < FT_BN || klo > 0) {                   // -inf scores: they drop out of the maximum and exponentiate to exactly 0
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    if (j >= kvalid) v0[j] = 0xff800000u;
+                    if (j >= kvalid || j < klo) v0[j] = 0xff800000u;
                     if (32 + j >= kvalid) v1[j] = 0xff800000u;
                 }
             }
@@ -438,13 +446,13 @@ int siu3r_transpose_v(const float* V, int64_t v_bs, int64_t v_ts, int B, int N, 
 // Q: rows [B][Nq] of width q_width floats (token pitch q_ts, batch pitch q_bs), head h at columns q_col0 + 64 h .. ; K likewise.
 // Vt from siu3r_transpose_v.  O [B][Nq][H*64] (pitches o_bs / o_ts).  Q / K should already be RN-TF32 (the tensor core truncates).
 int siu3r_flash_attn_tc(const float* Q, int64_t q_bs, int64_t q_ts, int q_width, int q_col0, const float* K, int64_t k_bs, int64_t k_ts,
-                        int k_width, int k_col0, const float* Vt, int64_t vt_ld, float* O, int64_t o_bs, int64_t o_ts, int B, int H, int Nq,
-                        int Nk, float scale, int round_out, void* stream_) {
+                        int k_width, int k_col0, const float* Vt, int64_t vt_ld, int64_t vt_batch_cols, float* O, int64_t o_bs, int64_t o_ts, int B,
+                        int H, int Nq, int Nk, float scale, int round_out, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     SIU3R_REQUIRE(Q && K && Vt && O && B > 0 && H > 0 && Nq > 0 && Nk > 0);
     SIU3R_REQUIRE(q_ts % 4 == 0 && k_ts % 4 == 0 && q_bs % 4 == 0 && k_bs % 4 == 0 && vt_ld % 4 == 0 && o_ts % 4 == 0 && o_bs % 4 == 0);
     SIU3R_REQUIRE(((uintptr_t)Q & 15) == 0 && ((uintptr_t)K & 15) == 0 && ((uintptr_t)Vt & 15) == 0 && ((uintptr_t)O & 15) == 0);
-    SIU3R_REQUIRE(q_col0 % 4 == 0 && k_col0 % 4 == 0 && q_width >= q_col0 + H * 64 && k_width >= k_col0 + H * 64 && vt_ld >= Nk);
+    SIU3R_REQUIRE(q_col0 % 4 == 0 && k_col0 % 4 == 0 && q_width >= q_col0 + H * 64 && k_width >= k_col0 + H * 64 && vt_ld >= Nk && vt_batch_cols >= 0);
     CUtensorMap mq, mk, mv;
     {
         uint64_t dims[3] = {(uint64_t)q_width, (uint64_t)Nq, (uint64_t)B};
@@ -459,7 +467,7 @@ int siu3r_flash_attn_tc(const float* Q, int64_t q_bs, int64_t q_ts, int q_width,
         int r = make_map(&mk, K, 3, dims, str, box); if (r) return r;
     }
     {
-        uint64_t dims[2] = {(uint64_t)vt_ld, (uint64_t)B * H * 64};
+        uint64_t dims[2] = {(uint64_t)vt_ld, (uint64_t)(vt_batch_cols ? 1 : B) * H * 64};
         uint64_t str[1] = {(uint64_t)vt_ld * 4};
         uint32_t box[2] = {FT_BK, FT_D};
         int r = make_map(&mv, Vt, 2, dims, str, box); if (r) return r;
@@ -467,7 +475,7 @@ int siu3r_flash_attn_tc(const float* Q, int64_t q_bs, int64_t q_ts, int q_width,
     FlashParams p{};
     p.B = B; p.H = H; p.Nq = Nq; p.Nk = Nk; p.q_col0 = q_col0; p.k_col0 = k_col0;
     p.scale_log2e = scale * 1.4426950408889634f;
-    p.O = O; p.o_bs = o_bs; p.o_ts = o_ts; p.round_out = round_out;
+    p.O = O; p.o_bs = o_bs; p.o_ts = o_ts; p.round_out = round_out; p.vt_batch_cols = vt_batch_cols;
     static bool attr = false;
     if (!attr) {
         SIU3R_CUDA_CHECK(cudaFuncSetAttribute(flash_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM));

@@ -56,6 +56,9 @@ struct GemmParams {
     const float* rope_tab;     // [maxpos][16] (cos, sin) pairs from siu3r_rope2d_table (head dim 64)
     int rope_cols;             // columns [0, rope_cols) are rotated (multiple of 64)
     long long* dbg;            // optional: per-CTA clock64 stamps [cta][8] (tools/gemm_probe.py), null in production
+    // gemm_tc3: output columns >= vt_col0 (the V part of a qkv / k|v projection) are written TRANSPOSED into Vt[(n - vt_col0)][m] (row pitch
+    // vt_ld) instead of C: the K-major V^T operand of the flash-attention P.V product, without a separate transpose pass
+    int vt_col0; long long vt_ld;
     // gemm_tc3 "rows" mode: KH x 1 convolution over a flattened [H*W, 32] row-packed image (one k-block = one vertical tap):
     // k-block kb reads the X operand rows m + (kb - rows_pad) * rows_W at K offset 0 (TMA zero-fills above / below the image)
     int rows_W, rows_pad;
@@ -644,6 +647,8 @@ struct Tc3Problem {      // what differs between the problems of a grouped launc
     const float* bias;
     const float* residual;
     int M;
+    float* vt;           // V^T destination of this problem's rows (null: everything goes to C); 16-byte aligned
+    int vt_cols;         // columns of a V^T row this problem owns (>= M, multiple of 4): [M, vt_cols) is zero-filled
 };
 struct Tc3Group {
     Tc3Problem prob[2];
@@ -690,6 +695,24 @@ __device__ __forceinline__ void epi_chunk_swapped(const uint32_t (&v)[32], int j
 // Epilogue fragment of the fused "7x7 image conv + ReLU + bilinear x2 upsampled trunk" step of the Gaussian-parameter head
 // (heads/dpt_gs_head.py:162-164 after :155-160): x = act(acc + bias) + bilinear(low)[pixel m, channel n], align_corners = True, same source
 // index arithmetic as siu3r_resize_bilinear_nhwc.  The 4 taps of a pixel are 128-byte lines across the warp (lane = channel).
+// V columns of a fused qkv / k|v projection: this lane's output column n is one row of V^T, the fragment's 32 tokens are 128 contiguous
+// bytes of it (8 x 16-byte stores; m and vt_ld are multiples of 4).  Tokens past M up to the padded pitch are zero-filled so that the
+// attention kernel's TMA never stages uninitialised memory.  Values are stored round-to-nearest TF32 like siu3r_transpose_v does.
+__device__ __forceinline__ void epi_chunk_swapped_vt(const uint32_t (&v)[32], int jmax, int n, bool n_ok, float bias, int mrow, const GemmParams& p,
+                                                     const Tc3Problem& pr) {
+    if (!n_ok) return;
+    float* dst = pr.vt + (int64_t)(n - p.vt_col0) * p.vt_ld + mrow;
+    float x[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) x[j] = j < jmax ? rn_tf32(__uint_as_float(v[j]) * p.alpha + bias) : 0.0f;
+    // a fragment cut by the END OF THE PROBLEM (mrow + jmax == M) also zero-fills the pad columns [M, vt_cols); one cut by the tile edge (tw is a
+    // multiple of 16, not of 32) must stop there: the next columns belong to the neighbouring tile
+    const int lim = (mrow + jmax == pr.M) ? min(32, pr.vt_cols - mrow) : jmax;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4)
+        if (j < lim) *reinterpret_cast<float4*>(dst + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
+}
+
 template <bool RND>
 __device__ __forceinline__ void epi_chunk_swapped_up2x(const uint32_t (&v)[32], int jmax, int n, bool n_ok, float bias, int mrow, const GemmParams& p,
                                                        const Tc3Problem& pr) {
@@ -739,7 +762,8 @@ __device__ __forceinline__ void run_epilogue_swapped(uint32_t tmem_acc, int lane
     const int n = nb + lane;
     const bool n_ok = n < p.N;
     // split s > 0 accumulates into C: "residual" = C itself (pitch ldc), no bias
-    const Tc3Problem pr{pr_in.C, split > 0 ? nullptr : pr_in.bias, split > 0 ? (const float*)pr_in.C : pr_in.residual, pr_in.M};
+    const Tc3Problem pr{pr_in.C, split > 0 ? nullptr : pr_in.bias, split > 0 ? (const float*)pr_in.C : pr_in.residual, pr_in.M, pr_in.vt,
+                        pr_in.vt_cols};
     const int64_t ldr = split > 0 ? p.ldc : p.ldr;
     const float bias = (pr.bias && n_ok) ? __ldg(pr.bias + n) : 0.0f;
     const int act = p.act & ACT_MASK;
@@ -769,6 +793,10 @@ __device__ __forceinline__ void run_epilogue_swapped(uint32_t tmem_acc, int lane
         if (jmax > 32) jmax = 32;
         if (jmax > pr.M - mrow) jmax = pr.M - mrow;
         if (jmax <= 0) break;
+        if (!UP2X && pr.vt != nullptr && nb >= p.vt_col0) {        // warp-uniform: a 32-column block never straddles vt_col0 (multiple of 64)
+            epi_chunk_swapped_vt(v, jmax, n, n_ok, bias, mrow, p, pr);
+            continue;
+        }
         if (UP2X) {
             if (rnd) epi_chunk_swapped_up2x<true>(v, jmax, n, n_ok, bias, mrow, p, pr);
             else epi_chunk_swapped_up2x<false>(v, jmax, n, n_ok, bias, mrow, p, pr);
@@ -913,7 +941,8 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             int* flag = grp.flags ? grp.flags + ((size_t)t * 2 + rank) * TC3_EPI_WARPS + (warp - 2) : nullptr;
             // (static member selection: a runtime index into the kernel-parameter struct would force a local copy of it)
             const Tc3Problem prob{g ? grp.prob[1].C : grp.prob[0].C, g ? grp.prob[1].bias : grp.prob[0].bias,
-                                  g ? grp.prob[1].residual : grp.prob[0].residual, g ? grp.prob[1].M : grp.prob[0].M};
+                                  g ? grp.prob[1].residual : grp.prob[0].residual, g ? grp.prob[1].M : grp.prob[0].M,
+                                  g ? grp.prob[1].vt : grp.prob[0].vt, g ? grp.prob[1].vt_cols : grp.prob[0].vt_cols};
             run_epilogue_swapped<UP2X>(tmem_base + (uint32_t)(buf * 256), lane, q, c_lo, c_hi, n_cta, m_base, p, prob, &tfull_bar[buf],
                                        ((uint32_t)it >> 1) & 1u, split, grp.nsplit, flag);
             tcgen05_fence_before();
@@ -1119,7 +1148,8 @@ void siu3r_gemm_force(int kernel) { g_force = kernel; }
 // act: 0 none, 1 GELU(erf), 2 ReLU; +4 = store the result rounded to nearest TF32 (output only feeds TF32 GEMMs).  Replaces torch.nn.functional.linear (+ fused bias/activation/residual).
 static int gemm_tc_impl(int M, int N, int K, const float* A, const float* A_lo, int64_t lda, const float* Wt, const float* W_lo, int64_t ldw,
                         float* C, int64_t ldc, const float* bias, const float* residual, int64_t ldr, int act, float alpha, int precision,
-                        const int64_t* rope_pos, const float* rope_tab, int rope_cols, void* stream_) {
+                        const int64_t* rope_pos, const float* rope_tab, int rope_cols, void* stream_, float* vt = nullptr, int64_t vt_ld = 0,
+                        int vt_col0 = 0) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (rope_pos) SIU3R_REQUIRE(rope_tab && rope_cols > 0 && rope_cols % 64 == 0 && rope_cols <= N && ((uintptr_t)rope_tab & 15) == 0);
     SIU3R_REQUIRE(M > 0 && N > 0 && K > 0 && A && Wt && C);
@@ -1136,6 +1166,7 @@ static int gemm_tc_impl(int M, int N, int K, const float* A, const float* A_lo, 
         fl = next_flag_slot(stream);
         if (!fl) { nsplit = 1; tw = pick_tc3(M, N, K); }     // no flag buffer yet and the stream is capturing: plain schedule
     }
+    if (vt && (!tw || nsplit > 1)) return SIU3R_ERR_UNSUPPORTED;   // V^T emission exists in the persistent kernel's epilogue only
     if (tw) {
         // persistent swapped pair kernel: weights on the MMA-M axis, tokens on the MMA-N axis
         CUtensorMap mw, mx;
@@ -1147,9 +1178,10 @@ static int gemm_tc_impl(int M, int N, int K, const float* A, const float* A_lo, 
         p.M = M; p.N = N; p.num_kb = ceil_div(K, BK); p.C = C; p.ldc = ldc; p.bias = bias; p.residual = residual; p.ldr = ldr;
         p.act = act; p.alpha = alpha; p.conv = 0;
         p.rope_pos = (const long long*)rope_pos; p.rope_tab = rope_tab; p.rope_cols = rope_cols;
+        p.vt_col0 = vt_col0; p.vt_ld = vt_ld;
         const int w_pairs = ceil_div(N, 256);
         Tc3Group grp{};
-        grp.prob[0] = Tc3Problem{C, bias, residual, M};
+        grp.prob[0] = Tc3Problem{C, bias, residual, M, vt, (int)vt_ld};
         grp.prob[1] = grp.prob[0];
         grp.tiles0 = w_pairs * ceil_div(M, tw);
         grp.nsplit = 1; grp.kb_per_split = p.num_kb; grp.flags = nullptr;
@@ -1212,7 +1244,8 @@ int siu3r_gemm_tc(int M, int N, int K, const float* A, const float* A_lo, int64_
 // Returns SIU3R_ERR_UNSUPPORTED when the shape is not eligible for the persistent kernel (caller then issues two siu3r_gemm_tc).
 int siu3r_gemm_tc_group2(const int* M_host, int N, int K, const float* const* A_host, int64_t lda, const float* const* W_host, int64_t ldw,
                          float* const* C_host, int64_t ldc, const float* const* bias_host, const float* const* residual_host, int64_t ldr,
-                         int act, float alpha, const int64_t* positions, const float* rope_tab, int rope_cols, void* stream_) {
+                         int act, float alpha, const int64_t* positions, const float* rope_tab, int rope_cols, float* const* vt_host,
+                         const int* vt_cols_host, int64_t vt_ld, int vt_col0, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     SIU3R_REQUIRE(M_host && A_host && W_host && C_host && N > 0 && K > 0 && M_host[0] > 0 && M_host[1] > 0);
     SIU3R_REQUIRE(lda % 4 == 0 && ldw % 4 == 0 && lda >= K && ldw >= K);
@@ -1222,6 +1255,11 @@ int siu3r_gemm_tc_group2(const int* M_host, int N, int K, const float* const* A_
     const bool can_split = (act & ACT_MASK) == ACT_NONE && positions == nullptr;
     int tw = pick_tc3(M_host[0], N, K, M_host[1], can_split, &nsplit);
     if (tw == 0) return SIU3R_ERR_UNSUPPORTED;
+    if (vt_host) {
+        SIU3R_REQUIRE(vt_cols_host && vt_ld % 4 == 0 && vt_col0 % 64 == 0 && vt_col0 < N && (((uintptr_t)vt_host[0] | (uintptr_t)vt_host[1]) & 15) == 0);
+        SIU3R_REQUIRE(vt_cols_host[0] % 4 == 0 && vt_cols_host[1] % 4 == 0 && vt_cols_host[0] >= M_host[0] && vt_cols_host[1] >= M_host[1]);
+        if (nsplit > 1) { nsplit = 1; tw = pick_tc3(M_host[0], N, K, M_host[1]); }
+    }
     int* fl = nsplit > 1 ? next_flag_slot(stream) : nullptr;
     if (nsplit > 1 && !fl) { nsplit = 1; tw = pick_tc3(M_host[0], N, K, M_host[1]); }
     CUtensorMap mw[2], mx[2];
@@ -1234,10 +1272,12 @@ int siu3r_gemm_tc_group2(const int* M_host, int N, int K, const float* const* A_
     GemmParams p{};
     p.M = M_host[0]; p.N = N; p.num_kb = ceil_div(K, BK); p.C = C_host[0]; p.ldc = ldc; p.ldr = ldr; p.act = act; p.alpha = alpha; p.conv = 0;
     p.rope_pos = (const long long*)positions; p.rope_tab = rope_tab; p.rope_cols = rope_cols;
+    p.vt_col0 = vt_col0; p.vt_ld = vt_ld;
     const int w_pairs = ceil_div(N, 256);
     Tc3Group grp{};
     for (int g = 0; g < 2; ++g)
-        grp.prob[g] = Tc3Problem{C_host[g], bias_host ? bias_host[g] : nullptr, residual_host ? residual_host[g] : nullptr, M_host[g]};
+        grp.prob[g] = Tc3Problem{C_host[g], bias_host ? bias_host[g] : nullptr, residual_host ? residual_host[g] : nullptr, M_host[g],
+                                 vt_host ? vt_host[g] : nullptr, vt_cols_host ? vt_cols_host[g] : 0};
     grp.tiles0 = w_pairs * ceil_div(M_host[0], tw);
     grp.nsplit = nsplit; grp.kb_per_split = ceil_div(p.num_kb, nsplit); grp.flags = fl;
     const int tiles = grp.tiles0 + w_pairs * ceil_div(M_host[1], tw);
@@ -1270,7 +1310,7 @@ int siu3r_conv_rows_up2x_tc(int H, int W, int KH, int pad, int Cout, const float
     p.up_sw = W > 1 ? (float)(W / 2 - 1) / (float)(W - 1) : 0.f;
     const int w_pairs = ceil_div(Cout, 256);
     Tc3Group grp{};
-    grp.prob[0] = Tc3Problem{out, bias, low, M};
+    grp.prob[0] = Tc3Problem{out, bias, low, M, nullptr, 0};
     grp.prob[1] = grp.prob[0];
     grp.tiles0 = w_pairs * ceil_div(M, tw);
     grp.nsplit = 1; grp.kb_per_split = p.num_kb; grp.flags = nullptr;
@@ -1285,6 +1325,18 @@ int siu3r_gemm_tc_rope(int M, int N, int K, const float* A, const float* A_lo, i
                        int rope_cols, void* stream) {
     SIU3R_REQUIRE(positions && rope_tab);
     return gemm_tc_impl(M, N, K, A, A_lo, lda, Wt, W_lo, ldw, C, ldc, bias, nullptr, 0, act, 1.0f, precision, positions, rope_tab, rope_cols, stream);
+}
+
+// siu3r_gemm_tc_rope whose output columns >= vt_col0 (the V third of a qkv projection) are written as V^T [(n - vt_col0)][m] (pitch vt_ld,
+// multiple of 4, >= M; columns [M, vt_ld) zero-filled) instead of C -- the operand layout siu3r_flash_attn_tc consumes with
+// vt_batch_cols = tokens per image.  TF32 only; -4 when the shape is not run by the persistent kernel (use siu3r_transpose_v then).
+int siu3r_gemm_tc_rope_vt(int M, int N, int K, const float* A, int64_t lda, const float* Wt, int64_t ldw, float* C, int64_t ldc, const float* bias,
+                          int act, const int64_t* positions, const float* rope_tab, int rope_cols, float* vt, int64_t vt_ld, int vt_col0,
+                          void* stream) {
+    SIU3R_REQUIRE(vt && vt_ld % 4 == 0 && vt_ld >= M && vt_col0 % 64 == 0 && vt_col0 < N && ((uintptr_t)vt & 15) == 0);
+    SIU3R_REQUIRE(positions == nullptr || rope_cols <= vt_col0);
+    return gemm_tc_impl(M, N, K, A, nullptr, lda, Wt, nullptr, ldw, C, ldc, bias, nullptr, 0, act, 1.0f, 1, positions, rope_tab, rope_cols, stream,
+                        vt, vt_ld, vt_col0);
 }
 
 // Stride-1 KHxKW convolution, NHWC fp32:  y[n,h,w,co] = act(sum x[n,h+kh-pad,w+kw-pad,ci] * Wt[co,kh,kw,ci] + bias) + residual

@@ -275,11 +275,15 @@ class SIU3RModel:
 
     def _self_attn(self, h, blk, pos, Bn, N, C, nh):
         M = Bn * N
-        qkv = self._lin(h, blk.qkv, ar=True, ro=True, rope=(pos, self._k.rope_tab, 2 * C))   # RoPE on q and k inside the epilogue
+        vt = st = None
+        if self.R:   # the V third of the projection is written as V^T by the GEMM epilogue (no transpose pass)
+            vt, st = torch.empty(C, (M + 3) // 4 * 4, device=self.dev), {}
+        qkv = self._lin(h, blk.qkv, ar=True, ro=True, rope=(pos, self._k.rope_tab, 2 * C),   # RoPE on q and k inside the epilogue
+                        **({"vt": (vt, 2 * C, st)} if vt is not None else {}))
         a = torch.empty(M, C, device=self.dev)
         if self.R:   # TF32 mode: tcgen05 / TMEM flash attention
             ops.flash_attn_tc(qkv, 0, N * 3 * C, 3 * C, 3 * C, qkv, C, N * 3 * C, 3 * C, 3 * C, qkv, 2 * C, N * 3 * C, 3 * C, a, Bn, nh, N, N, 0.125,
-                              round_out=True)
+                              round_out=True, vt=(vt, N) if st.get("ok") else None)
         else:        # 3xTF32 mode: mma.sync kernel with the register-level split
             ops.flash_attn_d64(qkv, 0, N * 3 * C, 3 * C, qkv, C, N * 3 * C, 3 * C, qkv, 2 * C, N * 3 * C, 3 * C, a, Bn, nh, N, N, 0.125, self.prec)
         return a
@@ -671,12 +675,28 @@ class SIU3RModel:
         ln2 = lambda xs, wbs, outs: ops.layernorm_group2(xs, wbs, 1e-6, outs, round_out=self.R)   # both streams' norms in one launch
         h = torch.empty(R, C, device=self.dev)
         ln2(split(f), [bk.n1 for bk in blks], split(h))
+        def vt_windows():
+            """V^T buffer [C, ld] for the grouped projections: stream g owns a 16-byte aligned column window; all images must end up at one
+            uniform column stride (possible for B = 1 with a padded stride, or when B*N is a multiple of 4)."""
+            if not self.R:
+                return None
+            if V == 2 and B == 1:
+                stride = (N + 3) // 4 * 4
+                buf = torch.empty(C, 2 * stride, device=self.dev)
+                return buf, [buf[:, :stride], buf[:, stride:]], [stride, stride], stride
+            if V == 2 and (B * N) % 4 == 0:
+                buf = torch.empty(C, 2 * B * N, device=self.dev)
+                return buf, [buf[:, :B * N], buf[:, B * N:]], [B * N, B * N], N
+            return None
+
         qkv = torch.empty(R, 3 * C, device=self.dev)
-        self._lin2(split(h), [bk.qkv for bk in blks], outs=split(qkv), ar=True, ro=True, rope=(pos, tab, 2 * C))
+        vw, st = vt_windows(), {}
+        self._lin2(split(h), [bk.qkv for bk in blks], outs=split(qkv), ar=True, ro=True, rope=(pos, tab, 2 * C),
+                   **({"vt": (vw[1], vw[2], 2 * C, st)} if vw else {}))
         att = torch.empty(R, C, device=self.dev)
         if self.R:
             ops.flash_attn_tc(qkv, 0, N * 3 * C, 3 * C, 3 * C, qkv, C, N * 3 * C, 3 * C, 3 * C, qkv, 2 * C, N * 3 * C, 3 * C, att, V * B, nh, N, N, 0.125,
-                              round_out=True)
+                              round_out=True, vt=(vw[0], vw[3]) if st.get("ok") else None)
         else:
             ops.flash_attn_d64(qkv, 0, N * 3 * C, 3 * C, qkv, C, N * 3 * C, 3 * C, qkv, 2 * C, N * 3 * C, 3 * C, att, V * B, nh, N, N, 0.125, self.prec)
         x1 = torch.empty(R, C, device=self.dev)
@@ -687,7 +707,9 @@ class SIU3RModel:
             yn = torch.empty(R, C, device=self.dev)
             ln2([f[R0:], f[:R0]], [bk.ny for bk in blks], split(yn))
             ctx = torch.empty(R, 2 * C, device=self.dev)
-            self._lin2(split(yn), [bk.ckv for bk in blks], outs=split(ctx), ar=True, ro=True, rope=(pos, tab, C))
+            vw2, st2 = vt_windows(), {}
+            self._lin2(split(yn), [bk.ckv for bk in blks], outs=split(ctx), ar=True, ro=True, rope=(pos, tab, C),
+                       **({"vt": (vw2[1], vw2[2], C, st2)} if vw2 else {}))
             Nk = N
         else:
             yn0 = torch.empty(R - R0, C, device=self.dev)     # views 1..V-1 under stream-0 weights
@@ -697,6 +719,7 @@ class SIU3RModel:
             kv1 = torch.empty(R, 2 * C, device=self.dev)
             self._lin2([yn0, yn1], [bk.ckv for bk in blks], outs=[kv0, kv1], ar=True, ro=True, rope=(pos, tab, C))
             Nk = (V - 1) * N
+            vw2, st2 = None, {}
             ctx = torch.empty(V * B, Nk, 2 * C, device=self.dev)
             for i in range(V):
                 for b in range(B):
@@ -713,7 +736,8 @@ class SIU3RModel:
         self._lin2(split(h2), [bk.cq for bk in blks], outs=split(q), ar=True, ro=True, rope=(pos, tab, C))
         a2 = torch.empty(R, C, device=self.dev)
         if self.R:
-            ops.flash_attn_tc(q, 0, N * C, C, C, ctx, 0, Nk * 2 * C, 2 * C, 2 * C, ctx, C, Nk * 2 * C, 2 * C, a2, V * B, nh, N, Nk, 0.125, round_out=True)
+            ops.flash_attn_tc(q, 0, N * C, C, C, ctx, 0, Nk * 2 * C, 2 * C, 2 * C, ctx, C, Nk * 2 * C, 2 * C, a2, V * B, nh, N, Nk, 0.125, round_out=True,
+                              vt=(vw2[0], vw2[3]) if (vw2 and st2.get("ok")) else None)
         else:
             ops.flash_attn_d64(q, 0, N * C, C, ctx, 0, Nk * 2 * C, 2 * C, ctx, C, Nk * 2 * C, 2 * C, a2, V * B, nh, N, Nk, 0.125, self.prec)
         self._lin2(split(a2), [bk.cproj for bk in blks], outs=split(x1), ar=True, residuals=split(x1))

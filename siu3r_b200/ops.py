@@ -125,7 +125,7 @@ def round_tf32(x: torch.Tensor) -> torch.Tensor:
 
 def gemm(x: torch.Tensor, wt: Weight, out: torch.Tensor | None = None, act: int = ACT_NONE, residual: torch.Tensor | None = None,
          alpha: float = 1.0, precision: int = PREC_TF32, bias: torch.Tensor | None | bool = True, M: int | None = None,
-         a_rounded: bool = False, round_out: bool = False, rope: tuple | None = None) -> torch.Tensor:
+         a_rounded: bool = False, round_out: bool = False, rope: tuple | None = None, vt: tuple | None = None) -> torch.Tensor:
     """out[M,N] = act(alpha * x[M,K] @ W^T + bias) + residual.  x / out / residual are 2-D row-strided views.
     rope = (positions [M,2] int64, table from rope2d_table, ncols): RoPE-2D on output columns [0, ncols) in the epilogue.
     TF32 mode: the A operand must be round-to-nearest TF32 (a_rounded=True if its producer already did that);
@@ -158,6 +158,21 @@ def gemm(x: torch.Tensor, wt: Weight, out: torch.Tensor | None = None, act: int 
             x = round_tf32(x)
         if round_out:
             act = act | ACT_ROUND_TF32
+    if vt is not None:
+        # vt = (tensor [rows, ld], col0, state): columns >= col0 of the result go to V^T (see siu3r_gemm_tc_rope_vt); state["ok"] tells the caller
+        # whether that happened (False: plain GEMM was run, use the transpose pass)
+        vt_t, vt_col0, state = vt
+        state["ok"] = False
+        if precision == PREC_TF32 and residual is None and alpha == 1.0 and x.stride(0) % 4 == 0 and K % 4 == 0 and x.data_ptr() % 16 == 0:
+            pos, tab, ncols = rope if rope is not None else (None, None, 0)
+            with _Prof("gemm_tc", 2.0 * M * wt.N * K, ("vt", M, wt.N, K)):
+                code = _lib.load().siu3r_gemm_tc_rope_vt(M, wt.N, K, _p(x), x.stride(0), _p(wt.w), ldw, _p(out), out.stride(0), _p(b), act, _p(pos),
+                                                         _p(tab), ncols, _p(vt_t), vt_t.stride(0), vt_col0, _stream())
+            if code == 0:
+                state["ok"] = True
+                return out
+            if code != -4:
+                _lib.check(code, "gemm_tc_rope_vt")
     if rope is not None:
         pos, tab, ncols = rope
         assert residual is None and alpha == 1.0 and pos.dtype == torch.int64 and pos.is_contiguous() and pos.numel() == 2 * M
@@ -174,7 +189,7 @@ def gemm(x: torch.Tensor, wt: Weight, out: torch.Tensor | None = None, act: int 
 
 
 def gemm_group2(xs, wts, outs=None, act: int = ACT_NONE, residuals=None, precision: int = PREC_TF32, a_rounded: bool = False,
-                round_out: bool = False, rope: tuple | None = None):
+                round_out: bool = False, rope: tuple | None = None, vt: tuple | None = None):
     """Two linear layers of the same shape class (same N, K, strides, epilogue; rows may differ) in ONE persistent launch:
     outs[g] = act(xs[g] @ wts[g]^T + bias_g) + residuals[g].  Falls back to two gemm() calls when the shape / precision is not
     eligible for the grouped kernel (3xTF32 mode, tiny N or K, mismatching strides)."""
@@ -182,6 +197,9 @@ def gemm_group2(xs, wts, outs=None, act: int = ACT_NONE, residuals=None, precisi
     if outs is None:
         outs = [torch.empty(x.shape[0], w.N, device=x.device, dtype=torch.float32) for x, w in zip(xs, wts)]
     residuals = residuals or [None, None]
+
+    if vt is not None:
+        vt[3]["ok"] = False   # vt = ([vt0, vt1] column windows of one V^T buffer, [cols0, cols1], col0, state)
 
     def fallback():
         for g in range(2):
@@ -211,14 +229,21 @@ def gemm_group2(xs, wts, outs=None, act: int = ACT_NONE, residuals=None, precisi
         pos, tab, ncols = rope[0], rope[1], rope[2]
         assert residuals[0] is None and pos.dtype == torch.int64 and pos.is_contiguous() and pos.numel() >= 2 * max(Ms[0], Ms[1])
     work = 2.0 * (Ms[0] + Ms[1]) * w0.N * K
+    vts = vcols = None
+    vt_ld = vt_col0 = 0
+    if vt is not None:
+        vts, vcols, vt_ld, vt_col0 = arr(vt[0]), (C.c_int * 2)(*vt[1]), vt[0][0].stride(0), vt[2]
     with _Prof("gemm_tc", work, ("grp2", Ms[0] + Ms[1], w0.N, K)):
         code = _lib.load().siu3r_gemm_tc_group2(Ms, w0.N, K, arr(xs), xs[0].stride(0), arr([w0.w, w1.w]), w0.w.shape[1], arr(outs), outs[0].stride(0),
                                                 None if w0.bias is None else arr([w0.bias, w1.bias]),
                                                 None if residuals[0] is None else arr(residuals),
-                                                0 if residuals[0] is None else residuals[0].stride(0), a, 1.0, _p(pos), _p(tab), ncols, _stream())
+                                                0 if residuals[0] is None else residuals[0].stride(0), a, 1.0, _p(pos), _p(tab), ncols, vts, vcols,
+                                                vt_ld, vt_col0, _stream())
     if code == -4:
         return fallback()
     _lib.check(code, "gemm_tc_group2")
+    if vt is not None:
+        vt[3]["ok"] = True
     return outs
 
 
@@ -372,15 +397,20 @@ def flash_attn_d64(q: torch.Tensor, q_off: int, q_bs: int, q_ts: int, k: torch.T
 
 def flash_attn_tc(q: torch.Tensor, q_off: int, q_bs: int, q_ts: int, q_width: int, k: torch.Tensor, k_off: int, k_bs: int, k_ts: int, k_width: int,
                   v: torch.Tensor, v_off: int, v_bs: int, v_ts: int, out: torch.Tensor, B: int, H: int, Nq: int, Nk: int, scale: float,
-                  round_out: bool = False):
+                  round_out: bool = False, vt: tuple | None = None):
     """tcgen05 flash attention (TF32).  q/k: element (b, n, h, d) at tensor.data_ptr() + 4*(b*bs + n*ts + off + h*64 + d), `width` = row
-    width in floats; v likewise (transposed + rounded internally).  out [B, Nq, H*64] contiguous."""
+    width in floats; v likewise (transposed + rounded internally), unless vt = (V^T tensor [H*64, ld], image column stride) written by the
+    projection GEMM itself is given.  out [B, Nq, H*64] contiguous."""
     lib = _lib.load()
-    ld = (Nk + 3) // 4 * 4
-    vt = torch.empty(B * H * 64, ld, device=out.device, dtype=torch.float32)
-    _lib.check(lib.siu3r_transpose_v(v.data_ptr() + 4 * v_off, v_bs, v_ts, B, Nk, H, _p(vt), ld, _stream()), "transpose_v")
+    if vt is None:
+        ld, bcols = (Nk + 3) // 4 * 4, 0
+        vt_t = torch.empty(B * H * 64, ld, device=out.device, dtype=torch.float32)
+        _lib.check(lib.siu3r_transpose_v(v.data_ptr() + 4 * v_off, v_bs, v_ts, B, Nk, H, _p(vt_t), ld, _stream()), "transpose_v")
+    else:
+        vt_t, bcols = vt
+        ld = vt_t.stride(0)
     with _Prof("flash_attn", 4.0 * B * H * Nq * Nk * 64):
-        code = lib.siu3r_flash_attn_tc(q.data_ptr(), q_bs, q_ts, q_width, q_off, k.data_ptr(), k_bs, k_ts, k_width, k_off, _p(vt), ld, _p(out),
+        code = lib.siu3r_flash_attn_tc(q.data_ptr(), q_bs, q_ts, q_width, q_off, k.data_ptr(), k_bs, k_ts, k_width, k_off, _p(vt_t), ld, bcols, _p(out),
                                        Nq * H * 64, H * 64, B, H, Nq, Nk, scale, 1 if round_out else 0, _stream())
     _lib.check(code, "flash_attn_tc")
     return out

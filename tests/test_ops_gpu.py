@@ -644,3 +644,30 @@ def test_conv_rows_up2x_fused_matches_unfused(H, W):
     ref = F.relu(F.conv2d(xr.permute(0, 3, 1, 2), wr.permute(0, 3, 1, 2), b, padding=3)) + F.interpolate(low.permute(0, 3, 1, 2), size=(H, W),
                                                                                                         mode="bilinear", align_corners=True)
     assert float((fused - ref.permute(0, 2, 3, 1)).abs().max()) < 2e-3 * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("M0,M1,N,K,col0", [(1025, 1025, 2304, 768, 1536), (257, 257, 2304, 768, 1536), (1025, 1025, 1536, 768, 768), (2050, 0, 3072, 1024, 2048)])
+def test_gemm_vt_emission(M0, M1, N, K, col0):
+    """V columns of a qkv / k|v projection written as V^T by the persistent kernel's epilogue (single and grouped launch): exact against the
+    row-major result, pad columns zero, C untouched for those columns, tile-edge fragments do not clobber their neighbours."""
+    from siu3r_b200 import ops
+    torch.manual_seed(M0 + N)
+    Ms = [M0] + ([M1] if M1 else [])
+    xs = [ops.round_tf32(torch.randn(m, K, device=DEV)) for m in Ms]
+    ws = [ops.Weight(torch.randn(N, K, device=DEV) / K ** 0.5, torch.randn(N, device=DEV), 1) for _ in Ms]
+    outs = [torch.zeros(m, N, device=DEV) for m in Ms]
+    stride = (M0 + 3) // 4 * 4
+    buf = torch.full((N - col0, len(Ms) * stride), float("nan"), device=DEV)
+    st = {}
+    if M1:
+        ops.gemm_group2(xs, ws, outs=outs, a_rounded=True, round_out=True, vt=([buf[:, :stride], buf[:, stride:]], [stride, stride], col0, st))
+    else:
+        ops.gemm(xs[0], ws[0], out=outs[0], a_rounded=True, round_out=True, vt=(buf, col0, st))
+    assert st["ok"]
+    for g, m in enumerate(Ms):
+        ref = (xs[g].double() @ ws[g].w.double().t() + ws[g].bias.double()).float()
+        assert float((outs[g][:, :col0] - ref[:, :col0]).abs().max()) < 4e-3
+        w = buf[:, g * stride: g * stride + m]
+        assert float((w - ref[:, col0:].t()).abs().max()) < 4e-3
+        assert float(buf[:, g * stride + m: (g + 1) * stride].abs().sum()) == 0.0
+        assert float(outs[g][:, col0:].abs().max()) == 0.0

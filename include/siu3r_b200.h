@@ -95,6 +95,9 @@ int siu3r_conv_rows_up2x_tc(int H, int W, int KH, int pad, int Cout, const float
 /* plain fp32 FFMA GEMM (tiny / odd shapes such as the K = 9 intrinsics encoder, backbone_croco.py:59,278) */
 int siu3r_gemm_simt(int M, int N, int K, const float* A, int64_t lda, const float* W, int64_t ldw, float* C, int64_t ldc,
                     const float* bias, const float* residual, int64_t ldr, int act, float alpha, void* stream);
+/* skinny fp32 GEMM (M <= ~128 rows: the 100 Mask2Former queries, video_seg_decoder.py:957-1025,1423-1480): 32x32 tiles, 8-way in-CTA split-K */
+int siu3r_gemm_skinny(int M, int N, int K, const float* A, int64_t lda, const float* W, int64_t ldw, float* C, int64_t ldc, const float* bias,
+                      const float* residual, int64_t ldr, int act, float alpha, void* stream);
 int siu3r_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream);
 void siu3r_gemm_debug_set(long long* dev_buf);
 void siu3r_gemm_force(int kernel);               /* tuning aid: 0 heuristic, 1 persistent swapped pair kernel (>= 16: that token tile width), 3 one-tile pair, 4 1-CTA */   /* profiling aid: per-CTA clock64 stamps of the 1-CTA linear kernel */

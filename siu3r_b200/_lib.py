@@ -30,6 +30,7 @@ SIGNATURES = {
     "siu3r_gemm_tc": (_i, [_i, _i, _i, _p, _p, _l, _p, _p, _l, _p, _l, _p, _p, _l, _i, _f, _i, _p]),
     "siu3r_conv2d_tc": (_i, [_i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _l, _p, _p, _l, _i, _i, _p]),
     "siu3r_gemm_simt": (_i, [_i, _i, _i, _p, _l, _p, _l, _p, _l, _p, _p, _l, _i, _f, _p]),
+    "siu3r_gemm_skinny": (_i, [_i, _i, _i, _p, _l, _p, _l, _p, _l, _p, _p, _l, _i, _f, _p]),
     "siu3r_split_tf32": (_i, [_p, _p, _p, _l, _p]),
     "siu3r_gemm_debug_set": (None, [_p]),
     "siu3r_gemm_force": (None, [_i]),

@@ -240,6 +240,73 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(int M, int N, int K, con
     }
 }
 
+// Skinny GEMM for M <= 128 rows (the 100 Mask2Former queries: ~85 linear layers per pair with 256..2048 columns, video_seg_decoder.py:957-1025,
+// 1423-1480).  On the tensor-core kernels these are pure set-up latency (TMEM allocation, barrier init, TMA descriptor fetch, one CTA row).
+// Here: 32 x 32 output tile per CTA, the 8 warps split K 8 ways (K = 256 -> one 32-wide chunk per warp, all of its loads in flight at once),
+// each lane accumulates a 4 x 8 register block, partial tiles are reduced through shared memory in a fixed order.  fp32 FFMA (exact products).
+constexpr int SK_T = 32, SK_WARPS = 8;
+__global__ void __launch_bounds__(SK_WARPS * 32) gemm_skinny_kernel(int M, int N, int K, const float* __restrict__ A, int64_t lda,
+                                                                    const float* __restrict__ W, int64_t ldw, float* __restrict__ C, int64_t ldc,
+                                                                    const float* __restrict__ bias, const float* __restrict__ res, int64_t ldr,
+                                                                    int act, float alpha) {
+    extern __shared__ float sk_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* sA = sk_smem + warp * (2 * SK_T * (SK_T + 1));     // [32 rows][33]
+    float* sW = sA + SK_T * (SK_T + 1);                       // [32 cols][33]
+    const int m0 = blockIdx.y * SK_T, n0 = blockIdx.x * SK_T;
+    const int kper = ((K + SK_WARPS - 1) / SK_WARPS + 31) / 32 * 32;      // K slice of this warp, multiple of 32
+    const int kbeg = warp * kper, kend = min(K, kbeg + kper);
+    const int rg = lane >> 2, cg = lane & 3;                  // lane block: rows rg*4 .. +3, columns cg*8 .. +7
+    float acc[4][8] = {};
+    for (int k0 = kbeg; k0 < kend; k0 += 32) {
+        const int k = k0 + lane;
+#pragma unroll 8
+        for (int r = 0; r < SK_T; ++r) {
+            const int m = m0 + r, n = n0 + r;
+            sA[r * (SK_T + 1) + lane] = (m < M && k < kend) ? __ldg(A + (int64_t)m * lda + k) : 0.f;
+            sW[r * (SK_T + 1) + lane] = (n < N && k < kend) ? __ldg(W + (int64_t)n * ldw + k) : 0.f;
+        }
+        __syncwarp();
+#pragma unroll 4
+        for (int kk = 0; kk < 32; ++kk) {
+            float a[4], w[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = sA[(rg * 4 + i) * (SK_T + 1) + kk];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) w[j] = sW[(cg * 8 + j) * (SK_T + 1) + kk];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+        }
+        __syncwarp();
+    }
+    __syncthreads();                       // every warp is done with its staging tiles: reuse the shared memory for the partial tiles
+    float* part = sk_smem + warp * (SK_T * SK_T);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) part[(rg * 4 + i) * SK_T + cg * 8 + j] = acc[i][j];
+    __syncthreads();
+    const bool rnd = (act & 4) != 0;
+    const int a_ = act & 3;
+    for (int e = threadIdx.x; e < SK_T * SK_T; e += SK_WARPS * 32) {
+        const int r = e >> 5, c = e & 31;
+        const int m = m0 + r, n = n0 + c;
+        if (m >= M || n >= N) continue;
+        float x = 0.f;
+#pragma unroll
+        for (int w8 = 0; w8 < SK_WARPS; ++w8) x += sk_smem[w8 * (SK_T * SK_T) + e];
+        x *= alpha;
+        if (bias) x += bias[n];
+        if (a_ == 1) x = 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+        else if (a_ == 2) x = fmaxf(x, 0.f);
+        if (res) x += res[(int64_t)m * ldr + n];
+        if (rnd) { uint32_t q; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(q) : "f"(x)); x = __uint_as_float(q); }
+        C[(int64_t)m * ldc + n] = x;
+    }
+}
+
 inline unsigned grid_for(int64_t n, int threads = 256) { return (unsigned)((n + threads - 1) / threads); }
 
 }  // namespace
@@ -382,6 +449,25 @@ int siu3r_ply_pack(const float* means, const float* scales, const float* rotatio
     const int F = siu3r_ply_record_words(d_sh, dc_only, has_labels, qc_words);
     ply_pack_kernel<<<grid_for(G * F), 256, 0, stream>>>(means, scales, rotations, harmonics, opacities, semantic_labels, instance_labels, qc_logits,
                                                          G, d_sh, n_rest, has_labels, qc_words, F, out);
+    SIU3R_LAUNCH_CHECK();
+    siu3r_note_launch(1);
+    return SIU3R_OK;
+}
+
+
+// act: 0 none, 1 GELU(erf), 2 ReLU; +4 = store RN_tf32(result).  Any alignment / K.
+int siu3r_gemm_skinny(int M, int N, int K, const float* A, int64_t lda, const float* W, int64_t ldw, float* C, int64_t ldc, const float* bias,
+                      const float* residual, int64_t ldr, int act, float alpha, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    SIU3R_REQUIRE(M > 0 && N > 0 && K > 0 && A && W && C);
+    constexpr int smem = SK_WARPS * 2 * SK_T * (SK_T + 1) * 4;   // 67.6 KB (staging) >= 32 KB (partials)
+    static bool attr = false;
+    if (!attr) {
+        SIU3R_CUDA_CHECK(cudaFuncSetAttribute(gemm_skinny_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr = true;
+    }
+    dim3 grid(ceil_div(N, SK_T), ceil_div(M, SK_T));
+    gemm_skinny_kernel<<<grid, SK_WARPS * 32, smem, stream>>>(M, N, K, A, lda, W, ldw, C, ldc, bias, residual, ldr, act, alpha);
     SIU3R_LAUNCH_CHECK();
     siu3r_note_launch(1);
     return SIU3R_OK;

@@ -15,6 +15,8 @@ ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
 ELT_RELU, ELT_ADD, ELT_ADD_RELU, ELT_GELU, ELT_COPY, ELT_SIGMOID, ELT_CLAMP01, ELT_RELU_RN, ELT_ROUND, ELT_ADD_RN = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9
 ACT_ROUND_TF32 = 4  # flag OR-ed into `act`: store RN_tf32(result)
 PREC_TF32, PREC_FP32X3 = 1, 3
+SKINNY = False   # route M <= SMALL_M GEMMs (TF32 mode) to siu3r_gemm_skinny: measured no faster than the tensor-core kernel inside the
+#                  captured graph (Mask2Former stage 3.85 vs 3.5 ms) -> off; the kernel stays available through the C ABI
 SMALL_M, SMALL_NK = 128, 0   # GEMMs with at most SMALL_M rows and N*K <= SMALL_NK would run on the fp32 FFMA kernel; measured slower than
 #                              the tensor-core kernel on the Mask2Former query GEMMs (few CTAs, serial K loop) -> disabled (0)
 
@@ -140,6 +142,14 @@ def gemm(x: torch.Tensor, wt: Weight, out: torch.Tensor | None = None, act: int 
     assert out.stride(1) == 1
     b = wt.bias if bias is True else (None if bias in (False, None) else bias)
     ldw = wt.w.shape[1]
+    if M <= SMALL_M and rope is None and vt is None and precision == PREC_TF32 and SKINNY:
+        # the ~85 GEMMs per pair with at most 128 rows (the 100 Mask2Former queries): set-up latency on the tensor-core kernels
+        a = act | (ACT_ROUND_TF32 if round_out else 0)
+        with _Prof("gemm_skinny", 2.0 * M * wt.N * K, ("skinny", M, wt.N, K)):
+            code = _lib.load().siu3r_gemm_skinny(M, wt.N, K, _p(x), x.stride(0), _p(wt.w), ldw, _p(out), out.stride(0), _p(b), _p(residual),
+                                                 0 if residual is None else residual.stride(0), a, alpha, _stream())
+        _lib.check(code, "gemm_skinny")
+        return out
     if x.stride(0) % 4 != 0 or K % 4 != 0 or x.data_ptr() % 16 != 0 or (M <= SMALL_M and wt.N * K <= SMALL_NK and rope is None and precision == PREC_TF32):
         # odd shapes (K or the row pitch not a multiple of 4 floats: no TMA) -> fp32 FFMA kernel
         a = act | (ACT_ROUND_TF32 if (round_out and precision == PREC_TF32) else 0)

@@ -671,3 +671,28 @@ def test_gemm_vt_emission(M0, M1, N, K, col0):
         assert float((w - ref[:, col0:].t()).abs().max()) < 4e-3
         assert float(buf[:, g * stride + m: (g + 1) * stride].abs().sum()) == 0.0
         assert float(outs[g][:, col0:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("M,N,K", [(100, 256, 256), (100, 2048, 256), (100, 256, 2048), (100, 21, 256), (7, 83, 100), (128, 512, 260)])
+def test_gemm_skinny(M, N, K):
+    from siu3r_b200 import _lib, ops
+    torch.manual_seed(M + N + K)
+    x = torch.randn(M, K, device=DEV)
+    w = torch.randn(N, K, device=DEV) / K ** 0.5
+    b = torch.randn(N, device=DEV)
+    r = torch.randn(M, N, device=DEV)
+    lib = _lib.load()
+    for act, res in ((0, None), (1, r), (2, None), (2 | 4, r)):
+        out = torch.empty(M, N, device=DEV)
+        code = lib.siu3r_gemm_skinny(M, N, K, x.data_ptr(), K, w.data_ptr(), K, out.data_ptr(), N, b.data_ptr(), None if res is None else res.data_ptr(),
+                                     N, act, 1.0, ops._stream())
+        assert code == 0
+        ref = (x.double() @ w.double().t() + b.double()).float()
+        if act & 3 == 1:
+            ref = torch.nn.functional.gelu(ref)
+        elif act & 3 == 2:
+            ref = torch.relu(ref)
+        if res is not None:
+            ref = ref + res
+        tol = 3e-3 if act & 4 else 2e-5
+        assert float((out - ref).abs().max()) < tol * max(1.0, float(ref.abs().max())), (act, float((out - ref).abs().max()))

@@ -1087,8 +1087,12 @@ int pick_tc3(int M, int N, int K, int M1 = 0, bool allow_split = false, int* nsp
     if (f == 3 || f == 4 || !tc2_enabled()) return 0;
     if (f == 0 && (N < 256 || K < 128 || M + M1 < 256)) return 0;
     const int tw_env = f >= 16 ? f : 0;   // siu3r_gemm_force(tw): this token tile width (sweeps)
-    static int split_env = -1;            // SIU3R_TC3_SPLITK=0 disables split-K, =n forces n where legal
-    if (split_env < 0) { const char* e = getenv("SIU3R_TC3_SPLITK"); split_env = e ? atoi(e) + 1 : 0; }
+    // Split-K is OFF unless SIU3R_TC3_SPLITK is set (1 = cost model decides, n >= 2 = force n where legal).  Its progress words live in a ring of
+    // 32 slots handed out per launch; two forwards that overlap on the GPU (the two graph slots of forward_async) can be handed the same slot for
+    // launches that run at the same time, which corrupts the words and leaves a warp spinning.  Until the words are owned per graph instance the
+    // 1 % it gains on the K = 3072 / 4096 layers is not worth that risk.
+    static int split_env = -1;
+    if (split_env < 0) { const char* e = getenv("SIU3R_TC3_SPLITK"); const int v = e ? atoi(e) : 0; split_env = v <= 0 ? 1 : (v == 1 ? 0 : v + 1); }
     const int w_pairs = ceil_div(N, 256);
     const int num_kb = ceil_div(K, BK);
     int best = 0, best_s = 1; double best_t = 1e30;

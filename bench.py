@@ -87,6 +87,28 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+class AuxWatchdog:
+    """The headline numbers (value, e2e, roofline) are measured first; the sections after them (all-gather, 4-view model, 3xTF32 mode, rasterizer
+    sample, CPU baseline) are auxiliary.  If they do not finish within `seconds` (a wedged GPU kernel cannot be interrupted from Python), this
+    thread prints the line as it stands -- marked with "aux_timeout" -- and ends the process, so the measured headline is never lost."""
+
+    def __init__(self, line: dict, seconds: float, enabled: bool = True):
+        self.line, self.seconds, self._stop = line, seconds, threading.Event()
+        if enabled:
+            threading.Thread(target=self._run, daemon=True).start()
+
+    def _run(self):
+        if not self._stop.wait(self.seconds):
+            self.line["aux_timeout"] = f"auxiliary sections exceeded {self.seconds:.0f} s; printed without the missing ones"
+            try:
+                print(json.dumps(self.line), flush=True)
+            finally:
+                os._exit(0)
+
+    def cancel(self):
+        self._stop.set()
+
+
 def host_threads() -> int:
     """Usable host threads: min(affinity mask, cgroup CPU quota) -- os.cpu_count() over-reports inside containers."""
     n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
@@ -315,6 +337,7 @@ def main():
             "gpu_launches": launches,
             "vit_tensor_pipe_frac": value / world * (FLOPS_PER_PAIR_512 if V == 2 else FLOPS_PER_SAMPLE_512_V4 * V / 4) * (S / 512.0) ** 2 / 1e12 / tf32_peak,
             "roofline": roofline}
+    watchdog = AuxWatchdog(line, float(os.environ.get("SIU3R_BENCH_AUX_TIMEOUT", "420")), enabled=(rank == 0))
 
     # ---- BASELINE configs[2]: the one collective of the path -- all-gather of the packed render records (88 fp32 per Gaussian) so that every
     #      rank holds the Gaussians of all pairs for joint-scene rasterisation (N > 1 only; not part of `value`) ----
@@ -383,6 +406,7 @@ def main():
         t = cpu_port_forward(S, 1, threads)
         line["cpu_baseline"] = {"value": 1.0 / t, "unit": "pairs/s", "cores": threads, "kind": "port",
                                 "sample": f"1 x one {S}x{S} pair (no warm-up), oracle/torch_port.py (torch CPU fp32, restatement pinned to reference goldens)"}
+    watchdog.cancel()
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

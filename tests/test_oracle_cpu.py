@@ -252,3 +252,17 @@ def test_gloo_world2_shard_and_all_gather():
     assert res[0][1] == [0, 1, 2] and res[1][1] == [3, 4]
     for r in res:
         assert tuple(r[2]) == (6, 7, 88) and r[3] == 0.0 and r[4] == 1.0 and r[5] == 2.0 and r[6] == 74.0
+
+
+def test_bench_aux_watchdog_prints_headline_and_exits():
+    """bench.AuxWatchdog: if the auxiliary sections wedge, the already measured headline line is printed and the process exits 0."""
+    code = ("import sys, time, json; sys.path.insert(0, %r); import bench; line = {'metric': 'm', 'value': 1.5}; "
+            "w = bench.AuxWatchdog(line, 0.3); time.sleep(30); print('not reached')") % ROOT
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "not reached" not in r.stdout
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out["value"] == 1.5 and "aux_timeout" in out
+    code2 = ("import sys, time, json; sys.path.insert(0, %r); import bench; line = {'value': 2}; w = bench.AuxWatchdog(line, 5.0); w.cancel(); "
+             "time.sleep(0.2); print(json.dumps(line))") % ROOT
+    r2 = subprocess.run([sys.executable, "-c", code2], capture_output=True, text=True, timeout=120)
+    assert r2.returncode == 0 and json.loads(r2.stdout.strip().splitlines()[-1]) == {"value": 2}

@@ -266,3 +266,36 @@ def test_bench_aux_watchdog_prints_headline_and_exits():
              "time.sleep(0.2); print(json.dumps(line))") % ROOT
     r2 = subprocess.run([sys.executable, "-c", code2], capture_output=True, text=True, timeout=120)
     assert r2.returncode == 0 and json.loads(r2.stdout.strip().splitlines()[-1]) == {"value": 2}
+
+
+def test_gsplat_oracle_invariants():
+    """oracle/gsplat_ref.py (parity unpinned vs gsplat itself): properties the published algorithm guarantees -- linear in the features,
+    alpha in [0, 1), culling of Gaussians behind the near plane / below the 1/255 opacity floor, depth ordering (an opaque near splat hides a far one)."""
+    from oracle import gsplat_ref as GR
+    rng = np.random.default_rng(0)
+    G, H, W, C = 400, 48, 64, 5
+    z = rng.uniform(2, 20, G)
+    means = np.stack([rng.uniform(-1, 1, G) * z * 0.4, rng.uniform(-1, 1, G) * z * 0.4, z], -1).astype("f4")
+    A = (rng.standard_normal((G, 3, 3)) * (0.03 * z)[:, None, None]).astype("f4")
+    cov = (A @ A.transpose(0, 2, 1) + 1e-6 * np.eye(3, dtype="f4")).astype("f4")
+    op = rng.random(G).astype("f4")
+    feats = rng.standard_normal((G, C)).astype("f4")
+    V = np.eye(4, dtype="f4")
+    args = (V, 1.2 * W, 1.2 * H, W / 2, H / 2, W, H, 1.0, 1000.0)
+    out, alpha, pr = GR.rasterize(means, cov, op, feats, *args)
+    out2, alpha2, _ = GR.rasterize(means, cov, op, 3 * feats, *args)
+    assert np.allclose(out2, 3 * out, atol=1e-5) and np.array_equal(alpha, alpha2)
+    assert alpha.min() >= 0 and alpha.max() < 1
+    means_b = means.copy(); means_b[:50, 2] = 0.5          # in front of the near plane
+    op_b = op.copy(); op_b[50:100] = 1e-3                   # below 1/255
+    _, _, prb = GR.rasterize(means_b, cov, op_b, feats, *args)
+    assert not prb["valid"][:100].any() and (prb["radii"][:100] == 0).all()
+    # two splats on the optical axis: the near, (almost) opaque one dominates the centre pixel
+    m2 = np.array([[0, 0, 3.0], [0, 0, 9.0]], "f4")
+    c2 = np.stack([np.eye(3, dtype="f4") * 0.05, np.eye(3, dtype="f4") * 0.5])
+    f2 = np.array([[1.0], [10.0]], "f4")
+    o2, a2, _ = GR.rasterize(m2, c2, np.array([0.999, 0.999], "f4"), f2, *args)
+    # (pixel centres sit at +0.5: alpha of the near splat is ~0.99 there, so ~1 % of the far splat's feature 10 leaks through)
+    assert 0.95 < o2[H // 2, W // 2, 0] < 1.3 and a2[H // 2, W // 2] > 0.99
+    far_only, _, _ = GR.rasterize(m2[1:], c2[1:], np.array([0.999], "f4"), f2[1:], *args)
+    assert far_only[H // 2, W // 2, 0] > 9.0

@@ -100,6 +100,8 @@ int siu3r_gemm_skinny(int M, int N, int K, const float* A, int64_t lda, const fl
                       const float* residual, int64_t ldr, int act, float alpha, void* stream);
 int siu3r_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream);
 void siu3r_gemm_debug_set(long long* dev_buf);
+/* host-only: what the tile planner of the persistent kernel decides for a shape (tw = 0: one-tile kernels) */
+int siu3r_gemm_plan(int M, int N, int K, int M1, int allow_split, int* tw_out, int* nsplit_out, int* tiles_out, int* rounds_out);
 void siu3r_gemm_force(int kernel);               /* tuning aid: 0 heuristic, 1 persistent swapped pair kernel (>= 16: that token tile width), 3 one-tile pair, 4 1-CTA */   /* profiling aid: per-CTA clock64 stamps of the 1-CTA linear kernel */
 
 /* ---- transformer pieces ----------------------------------------------------------------------------------------

@@ -34,6 +34,7 @@ SIGNATURES = {
     "siu3r_split_tf32": (_i, [_p, _p, _p, _l, _p]),
     "siu3r_gemm_debug_set": (None, [_p]),
     "siu3r_gemm_force": (None, [_i]),
+    "siu3r_gemm_plan": (_i, [_i, _i, _i, _i, _i, _p, _p, _p, _p]),
     "siu3r_conv_rows_up2x_tc": (_i, [_i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _l, _i, _p]),
     "siu3r_ply_record_words": (_i, [_i, _i, _i, _i]),
     "siu3r_ply_pack": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _l, _i, _i, _i, _p, _p]),

@@ -1145,6 +1145,18 @@ void siu3r_gemm_debug_set(long long* dev_buf) { g_gemm_dbg = dev_buf; }
 // tuning aid: 0 = heuristic, 1 = persistent swapped pair kernel wherever it is legal (>= 16: with that token tile width),
 // 3 = one-tile pair kernel, 4 = 1-CTA kernels only
 void siu3r_gemm_force(int kernel) { g_force = kernel; }
+// Host-only view of the tile planner (no CUDA call): token tile width chosen for the persistent kernel (0 = the one-tile kernels run this shape),
+// split-K factor, number of 256 x tw tiles and rounds over the 74 resident CTA pairs.  M1 > 0 = second problem of a grouped launch.
+int siu3r_gemm_plan(int M, int N, int K, int M1, int allow_split, int* tw_out, int* nsplit_out, int* tiles_out, int* rounds_out) {
+    SIU3R_REQUIRE(M > 0 && N > 0 && K > 0 && M1 >= 0 && tw_out && nsplit_out && tiles_out && rounds_out);
+    int ns = 1;
+    const int tw = pick_tc3(M, N, K, M1, allow_split != 0, &ns);
+    *tw_out = tw; *nsplit_out = ns;
+    const int tiles = tw ? ceil_div(N, 256) * (ceil_div(M, tw) + (M1 > 0 ? ceil_div(M1, tw) : 0)) : 0;
+    *tiles_out = tiles;
+    *rounds_out = tw ? ceil_div(tiles * ns, Tc3::CLUSTERS) : 0;
+    return SIU3R_OK;
+}
 
 // C[M,N] (ldc) = act(alpha * A[M,K] (lda) @ W[N,K]^T (ldw) + bias[N]) + residual[M,N] (ldr)
 // fp32 storage; precision 1 = TF32, 3 = 3xTF32 (needs the *_lo planes: x = hi + lo with hi = tf32-rounded x).

@@ -299,3 +299,26 @@ def test_gsplat_oracle_invariants():
     assert 0.95 < o2[H // 2, W // 2, 0] < 1.3 and a2[H // 2, W // 2] > 0.99
     far_only, _, _ = GR.rasterize(m2[1:], c2[1:], np.array([0.999], "f4"), f2[1:], *args)
     assert far_only[H // 2, W // 2, 0] > 9.0
+
+
+def test_gemm_tile_planner_host_logic():
+    """siu3r_gemm_plan (no GPU needed): the persistent kernel's token tile width is a multiple of 16 in [32, 256], the model's transformer shapes
+    fill whole rounds of the 74 CTA pairs, tiny shapes stay on the one-tile kernels, split-K is off unless SIU3R_TC3_SPLITK asks for it."""
+    from siu3r_b200 import _lib
+    lib = _lib.load()
+
+    def plan(M, N, K, M1=0, split=1):
+        o = [ctypes.c_int(0) for _ in range(4)]
+        assert lib.siu3r_gemm_plan(M, N, K, M1, split, *[ctypes.byref(x) for x in o]) == 0
+        return tuple(x.value for x in o)
+
+    for (M, N, K, M1) in [(2050, 3072, 1024, 0), (2050, 4096, 1024, 0), (2050, 1024, 4096, 0), (1025, 2304, 768, 1025), (1025, 768, 3072, 1025),
+                          (10752, 1024, 1024, 0), (8200, 3072, 1024, 0), (4100, 3072, 1024, 0)]:
+        tw, ns, tiles, rounds = plan(M, N, K, M1)
+        assert 32 <= tw <= 256 and tw % 16 == 0, (M, N, K, tw)
+        assert ns == 1                                              # split-K disabled by default
+        assert tiles == -(-N // 256) * (-(-M // tw) + (-(-M1 // tw) if M1 else 0)) and rounds == -(-tiles // 74)
+        assert tiles / (rounds * 74) >= 0.7, (M, N, K, tw, tiles)   # whole rounds are (nearly) full
+    assert plan(2050, 3072, 1024)[0] == 176                         # the case worked through in DESIGN.md: 144 tiles = 1.95 rounds
+    for (M, N, K) in [(100, 256, 256), (34, 3072, 1024), (262144, 83, 256), (2050, 1024, 64)]:
+        assert plan(M, N, K)[0] == 0

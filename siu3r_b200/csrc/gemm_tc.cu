@@ -1089,8 +1089,10 @@ int pick_tc3(int M, int N, int K, int M1 = 0, bool allow_split = false, int* nsp
     const int tw_env = f >= 16 ? f : 0;   // siu3r_gemm_force(tw): this token tile width (sweeps)
     // Split-K is OFF unless SIU3R_TC3_SPLITK is set (1 = cost model decides, n >= 2 = force n where legal).  Its progress words live in a ring of
     // 32 slots handed out per launch; two forwards that overlap on the GPU (the two graph slots of forward_async) can be handed the same slot for
-    // launches that run at the same time, which corrupts the words and leaves a warp spinning.  Until the words are owned per graph instance the
-    // 1 % it gains on the K = 3072 / 4096 layers is not worth that risk.
+    // launches that run at the same time, which corrupts the words and leaves a warp spinning.  A second hazard is co-residency: split s spins
+    // on split s-1 of its tile, which may belong to a CTA pair that is not resident yet when another persistent kernel (a parallel graph branch or
+    // the other slot) holds part of the SMs and itself waits the same way.  Until the words are owned per graph instance and a waiter only ever
+    // depends on work units with a lower index (dispatched first), the 1 % it gains on the K = 3072 / 4096 layers is not worth that risk.
     static int split_env = -1;
     if (split_env < 0) { const char* e = getenv("SIU3R_TC3_SPLITK"); const int v = e ? atoi(e) : 0; split_env = v <= 0 ? 1 : (v == 1 ? 0 : v + 1); }
     const int w_pairs = ceil_div(N, 256);

@@ -92,18 +92,23 @@ class AuxWatchdog:
     sample, CPU baseline) are auxiliary.  If they do not finish within `seconds` (a wedged GPU kernel cannot be interrupted from Python), this
     thread prints the line as it stands -- marked with "aux_timeout" -- and ends the process, so the measured headline is never lost."""
 
-    def __init__(self, line: dict, seconds: float, enabled: bool = True):
+    def __init__(self, line: dict, seconds: float, enabled: bool = True, key: str = "aux_timeout",
+                 note: str = "auxiliary sections exceeded {s:.0f} s; printed without the missing ones", exit_code: int = 0):
         self.line, self.seconds, self._stop = line, seconds, threading.Event()
+        self.key, self.note, self.exit_code = key, note, exit_code
         if enabled:
             threading.Thread(target=self._run, daemon=True).start()
 
     def _run(self):
         if not self._stop.wait(self.seconds):
-            self.line["aux_timeout"] = f"auxiliary sections exceeded {self.seconds:.0f} s; printed without the missing ones"
+            self.line[self.key] = self.note.format(s=self.seconds)
             try:
+                if self.exit_code:   # a wedged headline: leave the Python stacks of all threads on stderr for the post-mortem
+                    import faulthandler
+                    faulthandler.dump_traceback(file=sys.stderr, all_threads=True)
                 print(json.dumps(self.line), flush=True)
             finally:
-                os._exit(0)
+                os._exit(self.exit_code)
 
     def cancel(self):
         self._stop.set()
@@ -221,6 +226,11 @@ def main():
             ms = float(t)
         return ms
 
+    # A GPU kernel that never ends cannot be interrupted from Python: rather than sit until the caller's limit, report where the headline stopped.
+    phase = {"metric": METRIC, "value": None, "unit": "pairs/s", "n_gpus": world, "phase": "warm-up / graph capture"}
+    guard = AuxWatchdog(phase, float(os.environ.get("SIU3R_BENCH_HANG_TIMEOUT", "600")), enabled=(rank == 0), key="error",
+                        note="headline section did not finish within {s:.0f} s (see `phase`); no number was measured", exit_code=3)
+
     # ---- device-resident throughput (`value`) ----
     step = lambda: model(img_d, K_d, enable_query_class_logit_lift=False)
 
@@ -240,6 +250,7 @@ def main():
         model.forward_finish(pend)
 
     run_steps(max(args.warmup, 2))
+    phase["phase"] = "timed device-resident steps"
     clocks = ClockSampler(local)
     clocks.start()
     ops.reset_launch_count()
@@ -253,6 +264,7 @@ def main():
     # memory; the download of step i overlaps the forward of step i+1 (siu3r_b200.serving.PairPipeline) and the last
     # one is drained inside the timed region.
     from siu3r_b200.serving import PairPipeline
+    phase["phase"] = "end-to-end steps (PairPipeline)"
     pipe = PairPipeline(model)
 
     def e2e_step():
@@ -278,6 +290,7 @@ def main():
     d2h_gbs = big.numel() * big.element_size() / ms_copy / 1e6
 
     # ---- roofline of the dominant kernel family (instrumented pass, CUDA events on the launching stream) ----
+    phase["phase"] = "instrumented eager pass (roofline)"
     model.disable_cuda_graph()
     model.serial = True   # no parallel branches: per-kernel CUDA-event durations are not inflated by co-running kernels
     step()
@@ -337,6 +350,7 @@ def main():
             "gpu_launches": launches,
             "vit_tensor_pipe_frac": value / world * (FLOPS_PER_PAIR_512 if V == 2 else FLOPS_PER_SAMPLE_512_V4 * V / 4) * (S / 512.0) ** 2 / 1e12 / tf32_peak,
             "roofline": roofline}
+    guard.cancel()
     watchdog = AuxWatchdog(line, float(os.environ.get("SIU3R_BENCH_AUX_TIMEOUT", "420")), enabled=(rank == 0))
 
     # ---- BASELINE configs[2]: the one collective of the path -- all-gather of the packed render records (88 fp32 per Gaussian) so that every

@@ -322,3 +322,13 @@ def test_gemm_tile_planner_host_logic():
     assert plan(2050, 3072, 1024)[0] == 176                         # the case worked through in DESIGN.md: 144 tiles = 1.95 rounds
     for (M, N, K) in [(100, 256, 256), (34, 3072, 1024), (262144, 83, 256), (2050, 1024, 64)]:
         assert plan(M, N, K)[0] == 0
+
+
+def test_bench_headline_guard_reports_phase_and_fails():
+    """The guard around bench.py's headline: on a wedge it prints a line without a value that names the phase and exits non-zero."""
+    code = ("import sys, time, json; sys.path.insert(0, %r); import bench; ph = {'metric': 'm', 'value': None, 'phase': 'timed'}; "
+            "w = bench.AuxWatchdog(ph, 0.3, key='error', note='stopped after {s:.0f} s', exit_code=3); time.sleep(30)") % ROOT
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    assert r.returncode == 3 and out["value"] is None and out["phase"] == "timed" and "error" in out
+    assert "Thread" in r.stderr or "File" in r.stderr          # the stack dump

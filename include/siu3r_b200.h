@@ -196,6 +196,18 @@ int siu3r_ply_pack(const float* means, const float* scales, const float* rotatio
                    const int32_t* semantic_labels, const int32_t* instance_labels, const float* qc_logits, int64_t G, int d_sh, int dc_only,
                    int qc_words, uint32_t* out, void* stream);
 
+/* ---- 2-D labels from rendered query-class logits ---------------------------------------------------------------
+ * Replaces the tensor code of src/pipeline.py:132-164,182-186 (validation / test step; duplicated in viewer.py:404-446) for ONE sample:
+ * logits = render_qc_logits [V, Q, C, H, W] given by element strides (the rasteriser's memory is [V, H, W, Q*C]); C = classes + void,
+ * void last.  Per pixel: max over queries, class axis rotated void-first, max over classes, sem_logit < threshold -> 0, instance id =
+ * argmax query + 1 (0 where sem = 0); pixels whose semantic id equals fuse_sem[i] get instance id fuse_ins[i] (pipeline.py:182-186:
+ * stuff + 1 -> num_queries + stuff + 1; viewer.py:433-434: 1 -> 102, 2 -> 103), n_fuse <= 8, host arrays.  sem_id / ins_id: [V, H, W] int64 (torch.max
+ * indices).  first_sem [Q] (device, int32): semantic id of the first pixel (v, h, w order) a query owns before fusing, -1 = none --
+ * what pipeline.py:166-180 reads with q_sem_ids[0]; first_pix [Q] int32 is workspace. */
+int siu3r_labels_from_qc_logits(const float* logits, int V, int Q, int C, int H, int W, int64_t sv, int64_t sq, int64_t sc, int64_t sh,
+                                int64_t sw, float threshold, const int* fuse_sem, const int* fuse_ins, int n_fuse, int64_t* sem_id,
+                                int64_t* ins_id, int32_t* first_pix, int32_t* first_sem, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -332,3 +332,47 @@ def test_bench_headline_guard_reports_phase_and_fails():
     out = json.loads(r.stdout.strip().splitlines()[-1])
     assert r.returncode == 3 and out["value"] is None and out["phase"] == "timed" and "error" in out
     assert "Thread" in r.stderr or "File" in r.stderr          # the stack dump
+
+
+def _labels2d_cases():
+    z = np.load(os.path.join(GOLD, "labels2d_cases.npz"), allow_pickle=False)
+    meta = json.loads(str(z["meta"]))
+    return z, meta
+
+
+def test_labels2d_oracle_matches_reference_goldens():
+    """oracle/labels2d_ref.py against outputs of the reference's own statements (src/pipeline.py:132-193, oracle/make_golden_labels2d.py)."""
+    from oracle import labels2d_ref as LR
+    z, meta = _labels2d_cases()
+    assert set(meta) >= {"small", "ties", "onequery", "manyclasses", "allvoid"}
+    for name, m in meta.items():
+        sem, ins, infos = LR.labels_from_qc_logits(z[name + "__logits"], m["scores"], m["label_ids_to_fuse"], m["num_queries"])
+        assert np.array_equal(sem, z[name + "__sem"]) and np.array_equal(ins, z[name + "__ins"]), name
+        assert infos == m["infos"], (name, infos, m["infos"])
+
+
+def test_labels2d_kernel_arithmetic_on_host_matches_goldens(tmp_path):
+    """The per-pixel functions of csrc/labels2d_core.h (shared by the CUDA kernel) compiled for the host, with the warp emulated:
+    bit-exact label maps and per-query first labels on the goldens, for the channel-last layout the rasteriser emits and the contiguous one."""
+    so = str(tmp_path / "liblabels2d_host.so")
+    subprocess.run(["g++", "-O2", "-shared", "-fPIC", "-std=c++17", "-I", os.path.join(ROOT, "siu3r_b200", "csrc"),
+                    os.path.join(ROOT, "tests", "host_core", "labels2d_host.cpp"), "-o", so], check=True)
+    lib = ctypes.CDLL(so)
+    z, meta = _labels2d_cases()
+    I64, P = ctypes.c_int64, ctypes.c_void_p
+    lib.labels2d_host.argtypes = [P] + [ctypes.c_int] * 5 + [I64] * 5 + [ctypes.c_float, P, P, ctypes.c_int, P, P, P]
+    for name, m in meta.items():
+        v, q, c, h, w = m["shape"]
+        for layout in ("vqchw", "vhwqc"):
+            x = np.ascontiguousarray(z[name + "__logits"]) if layout == "vqchw" else np.ascontiguousarray(z[name + "__logits"].transpose(0, 3, 4, 1, 2))
+            st = [s // 4 for s in x.strides]
+            sv, sq, sc, sh, sw = st if layout == "vqchw" else (st[0], st[3], st[4], st[1], st[2])
+            fs = np.array([s + 1 for s in m["label_ids_to_fuse"]], np.int32)
+            fi = np.array([m["num_queries"] + s + 1 for s in m["label_ids_to_fuse"]], np.int32)
+            sem, ins, first = np.empty((v, h, w), np.int64), np.empty((v, h, w), np.int64), np.empty(q, np.int32)
+            rc = lib.labels2d_host(x.ctypes.data, v, q, c, h, w, sv, sq, sc, sh, sw, 0.3, fs.ctypes.data, fi.ctypes.data, len(fs),
+                                   sem.ctypes.data, ins.ctypes.data, first.ctypes.data)
+            assert rc == 0, (name, layout, rc)
+            assert np.array_equal(sem, z[name + "__sem"]) and np.array_equal(ins, z[name + "__ins"]), (name, layout)
+            got_infos = [(qi + 1, int(first[qi])) for qi in range(q) if first[qi] >= 0]
+            assert [l for _, l in got_infos] == [i["label_id"] for i in m["infos"]], (name, layout, got_infos, m["infos"])

@@ -376,3 +376,35 @@ def test_labels2d_kernel_arithmetic_on_host_matches_goldens(tmp_path):
             assert np.array_equal(sem, z[name + "__sem"]) and np.array_equal(ins, z[name + "__ins"]), (name, layout)
             got_infos = [(qi + 1, int(first[qi])) for qi in range(q) if first[qi] >= 0]
             assert [l for _, l in got_infos] == [i["label_id"] for i in m["infos"]], (name, layout, got_infos, m["infos"])
+
+
+def test_model_input_checks_and_no_cpu_fallback():
+    """Host-side contract of SIU3RModel / SIU3RMultiViewModel: the reference's input errors (patch_embed.py:22-23 multiples of 16, model.py:314-320
+    exactly two views, vit_adapter.py:328-329 fixed image_size) are raised before any kernel runs, and without a CUDA device the forward raises
+    instead of computing on the CPU."""
+    from siu3r_b200.model import ModelCfg, SIU3RModel, SIU3RMultiViewModel
+    m = SIU3RModel(ModelCfg(image_size=(64, 64)))
+    with pytest.raises(AssertionError):
+        m._check_inputs(torch.zeros(1, 2, 3, 64, 64))              # weights not loaded
+    with pytest.raises(AssertionError):
+        m(torch.zeros(1, 2, 3, 64, 64), torch.eye(3).repeat(1, 2, 1, 1), mask_labels=[0])     # training inputs are out of scope
+    m._ready = True
+    assert m._check_inputs(torch.zeros(3, 2, 3, 64, 64)) == (3, 2, 64, 64)
+    for shape in [(1, 3, 3, 64, 64), (1, 1, 3, 64, 64), (1, 2, 3, 128, 128)]:
+        with pytest.raises(AssertionError):
+            m._check_inputs(torch.zeros(*shape))
+    with pytest.raises(AssertionError, match="multiple of 32"):
+        SIU3RModel(ModelCfg(image_size=(60, 64)))                  # refused at construction (patch 16, adapter stride 32)
+    with pytest.raises(AssertionError, match="multiple of patch size"):
+        m._check_inputs(torch.zeros(1, 2, 3, 60, 64))
+    mv = SIU3RMultiViewModel(ModelCfg(image_size=(64, 64)))
+    mv._ready = True
+    assert mv._check_inputs(torch.zeros(1, 5, 3, 64, 64)) == (1, 5, 64, 64)
+    with pytest.raises(AssertionError):
+        mv._check_inputs(torch.zeros(1, 1, 3, 64, 64))
+    if not torch.cuda.is_available():
+        with pytest.raises(Exception):
+            m(torch.zeros(1, 2, 3, 64, 64), torch.eye(3).repeat(1, 2, 1, 1))
+        fresh = SIU3RModel(ModelCfg(image_size=(64, 64)))
+        with pytest.raises(Exception):
+            fresh.cuda()                                           # no device, no weights: refuses either way

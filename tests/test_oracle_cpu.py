@@ -408,3 +408,19 @@ def test_model_input_checks_and_no_cpu_fallback():
         fresh = SIU3RModel(ModelCfg(image_size=(64, 64)))
         with pytest.raises(Exception):
             fresh.cuda()                                           # no device, no weights: refuses either way
+
+
+def test_every_entry_point_refuses_null_arguments():
+    """Error behaviour at the C-ABI: no exception crosses it and nothing is dereferenced or launched before the arguments are checked --
+    every pointer-taking entry point returns SIU3R_ERR_INVALID (-1) for null pointers / zero sizes (the reference's TORCH_CHECKs,
+    curope.cpp:52-60, kernels.cu:91-94, raise at the same place: before any work)."""
+    from siu3r_b200 import _lib
+    lib = _lib.load()
+    checked = 0
+    for name, (res, args) in _lib.SIGNATURES.items():
+        if res is not _lib._i or not any(a is _lib._p or hasattr(a, "contents") for a in args):
+            continue
+        vals = [0.0 if a is _lib._f else (0 if a in (_lib._i, _lib._l) else None) for a in args]
+        assert getattr(lib, name)(*vals) == -1, name
+        checked += 1
+    assert checked >= 40

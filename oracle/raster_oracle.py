@@ -69,11 +69,11 @@ def rasterize(means, cov6, shs, opacities, viewmatrix, projmatrix, campos, tan_f
                 ranges=ranges, num_rendered=D)
 
 
-def rope2d(tokens: np.ndarray, pos: np.ndarray, base: float = 100.0, fwd: float = 1.0) -> np.ndarray:
-    """tokens [B,N,H,D] float32 (copied), pos [B,N,2] int64."""
+def rope2d(tokens: np.ndarray, pos: np.ndarray, base: float = 100.0, fwd: float = 1.0, cpu_order: bool = False) -> np.ndarray:
+    """tokens [B,N,H,D] float32 (copied), pos [B,N,2] int64.  cpu_order: angle formed as in curope.cpp:36 instead of kernels.cu:44-53."""
     t = np.ascontiguousarray(tokens, dtype=np.float32).copy()
     p = np.ascontiguousarray(pos, dtype=np.int64)
     B, N, H, D = t.shape
-    lib().siu3r_oracle_rope2d(t.ctypes.data_as(C.c_void_p), p.ctypes.data_as(C.c_void_p), C.c_int(B), C.c_int(N), C.c_int(H), C.c_int(D),
-                              C.c_float(base), C.c_float(fwd))
+    fn = lib().siu3r_oracle_rope2d_cpu if cpu_order else lib().siu3r_oracle_rope2d
+    fn(t.ctypes.data_as(C.c_void_p), p.ctypes.data_as(C.c_void_p), C.c_int(B), C.c_int(N), C.c_int(H), C.c_int(D), C.c_float(base), C.c_float(fwd))
     return t

@@ -288,10 +288,13 @@ int siu3r_oracle_rasterize(int G, int H, int W, int sh_degree, int sh_coeffs, co
 
 /* ----------------------------------------------------------------------------------------------
  * cuRoPE2D CPU restatement (reference: src/models/croco/curope/curope.cpp:11-47 rope_2d_cpu).
- * tokens [B,N,H,D] (in place), pos [B,N,2] int64.  Pinned against the reference's own PyTorch
- * fallback (croco/pos_embed.py:126-179) in tests/test_oracle_cpu.py.
+ * tokens [B,N,H,D] (in place), pos [B,N,2] int64.  Pinned in tests/test_oracle_cpu.py: the CPU-order variant is bit-identical to the
+ * reference's own curope.cpp compiled here (oracle/_ref/curope_ref.so, oracle/build_ref.py); both are within 2e-5 of its PyTorch
+ * fallback (croco/pos_embed.py:126-179).
  * -------------------------------------------------------------------------------------------- */
-void siu3r_oracle_rope2d(float* tokens, const int64_t* pos, int B, int N, int Hh, int D, float base, float fwd) {
+/* cpu_order = 0: angle = p * (fwd / base^(d/Q))   -- the reference's CUDA kernel (kernels.cu:44-53: inv_freq staged per block, then pos * inv_freq)
+ * cpu_order = 1: angle = (fwd * p) / base^(d/Q)   -- the reference's CPU function (curope.cpp:36); the two differ by one rounding of the angle */
+static void rope2d_impl(float* tokens, const int64_t* pos, int B, int N, int Hh, int D, float base, float fwd, int cpu_order) {
     const int Q = D / 4;
     for (int b = 0; b < B; ++b)
         for (int x = 0; x < 2; ++x)
@@ -300,8 +303,14 @@ void siu3r_oracle_rope2d(float* tokens, const int64_t* pos, int B, int N, int Hh
                 for (int h = 0; h < Hh; ++h) {
                     float* t = tokens + (((size_t)b * N + n) * Hh + h) * D + x * (D / 2);
                     for (int d = 0; d < Q; ++d) {
-                        const float inv_freq = fwd / powf(base, (float)d / (float)Q);
-                        const float f = (float)p * inv_freq;
+                        const float pw = powf(base, (float)d / (float)Q);
+                        float f;
+                        if (cpu_order) {
+                            f = (fwd * (float)(int)p) / pw;
+                        } else {
+                            const float inv_freq = fwd / pw;
+                            f = (float)p * inv_freq;
+                        }
                         const float c = cosf(f), s = sinf(f);
                         const float u = t[d], v = t[d + Q];
                         t[d] = u * c - v * s;
@@ -309,4 +318,11 @@ void siu3r_oracle_rope2d(float* tokens, const int64_t* pos, int B, int N, int Hh
                     }
                 }
             }
+}
+void siu3r_oracle_rope2d(float* tokens, const int64_t* pos, int B, int N, int Hh, int D, float base, float fwd) {
+    rope2d_impl(tokens, pos, B, N, Hh, D, base, fwd, 0);
+}
+/* bit-identical to the reference's curope.cpp compiled in this container (oracle/_ref/curope_ref.so): tests/test_oracle_cpu.py */
+void siu3r_oracle_rope2d_cpu(float* tokens, const int64_t* pos, int B, int N, int Hh, int D, float base, float fwd) {
+    rope2d_impl(tokens, pos, B, N, Hh, D, base, fwd, 1);
 }

@@ -134,6 +134,36 @@ def test_rope_c_oracle_matches_pytorch_form(oracle_lib):
         assert torch.equal(RoPE2D(100.0)(tok, pos), ref)
 
 
+def test_rope_c_oracle_bit_identical_to_compiled_reference(oracle_lib):
+    """oracle/_ref/curope_ref.so = the reference's own curope.cpp built by oracle/build_ref.py (rope_2d -> rope_2d_cpu, curope.cpp:11-65).
+    The CPU-order C restatement must reproduce it bit for bit (forward and inverse rotation, incl. the intrinsics token at (32, 0)); the
+    CUDA-order variant (kernels.cu:44-53, what the GPU tests compare with) differs from it by one rounding of the angle only.  Also the
+    reference's argument checks (TORCH_CHECK, curope.cpp:54-59), which our C-ABI mirrors with SIU3R_ERR_INVALID."""
+    from oracle import build_ref
+    from oracle import raster_oracle as RO
+    if os.path.isdir("/root/reference/src"):
+        build_ref.build_ref(verbose=False)
+    ref = build_ref.load_ref()
+    if ref is None:
+        pytest.skip("oracle/_ref/curope_ref.so not built (no /root/reference on this box)")
+    g = torch.Generator().manual_seed(0)
+    tok = torch.randn(2, 1025, 16, 64, generator=g)               # [B, N, H, D]
+    ys, xs = torch.meshgrid(torch.arange(32), torch.arange(32), indexing="ij")
+    pos = torch.cat([torch.stack([ys.flatten(), xs.flatten()], -1), torch.tensor([[32, 0]])], 0)[None].repeat(2, 1, 1)
+    for fwd in (1.0, -1.0):
+        want = tok.clone()
+        ref.rope_2d(want, pos, 100.0, fwd)
+        assert np.array_equal(RO.rope2d(tok.numpy(), pos.numpy(), fwd=fwd, cpu_order=True), want.numpy())
+        assert np.abs(RO.rope2d(tok.numpy(), pos.numpy(), fwd=fwd) - want.numpy()).max() < 2e-5
+    back = want.clone()
+    ref.rope_2d(back, pos, 100.0, 1.0)                            # inverse of the fwd = -1 rotation
+    assert float((back - tok).abs().max()) < 5e-6
+    with pytest.raises(RuntimeError, match="seq_length"):
+        ref.rope_2d(tok.clone(), pos[:, :100], 100.0, 1.0)
+    with pytest.raises(RuntimeError, match="4 dimensions"):
+        ref.rope_2d(tok[0].clone(), pos, 100.0, 1.0)
+
+
 def test_raster_oracle_invariants_and_regression(oracle_lib):
     from oracle import raster_oracle as RO
     from siu3r_b200 import synth

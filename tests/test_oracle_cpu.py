@@ -381,16 +381,51 @@ def test_labels2d_oracle_matches_reference_goldens():
         assert infos == m["infos"], (name, infos, m["infos"])
 
 
-def test_labels2d_kernel_arithmetic_on_host_matches_goldens(tmp_path):
-    """The per-pixel functions of csrc/labels2d_core.h (shared by the CUDA kernel) compiled for the host, with the warp emulated:
-    bit-exact label maps and per-query first labels on the goldens, for the channel-last layout the rasteriser emits and the contiguous one."""
+def _labels2d_host_lib(tmp_path):
     so = str(tmp_path / "liblabels2d_host.so")
     subprocess.run(["g++", "-O2", "-shared", "-fPIC", "-std=c++17", "-I", os.path.join(ROOT, "siu3r_b200", "csrc"),
                     os.path.join(ROOT, "tests", "host_core", "labels2d_host.cpp"), "-o", so], check=True)
     lib = ctypes.CDLL(so)
-    z, meta = _labels2d_cases()
     I64, P = ctypes.c_int64, ctypes.c_void_p
     lib.labels2d_host.argtypes = [P] + [ctypes.c_int] * 5 + [I64] * 5 + [ctypes.c_float, P, P, ctypes.c_int, P, P, P]
+    return lib
+
+
+def test_labels2d_kernel_arithmetic_on_host_random_cases(tmp_path):
+    """60 seeded random shapes (1..9 queries, 2..70 classes, coarse values -> many ties, random memory order of the five axes, random stuff
+    sets and thresholds): the kernel's per-pixel functions against the oracle restatement."""
+    from oracle import labels2d_ref as LR
+    lib = _labels2d_host_lib(tmp_path)
+    rng = np.random.default_rng(123)
+    for case in range(60):
+        v, q, c, h, w = (int(rng.integers(1, 4)), int(rng.integers(1, 10)), int(rng.integers(2, 71)), int(rng.integers(1, 12)), int(rng.integers(1, 12)))
+        levels = int(rng.choice([2, 4, 16, 1000]))
+        x = np.round(rng.random((v, q, c, h, w), dtype=np.float32) * levels) / np.float32(levels)
+        if case % 7 == 0:
+            x[:, :, :, : h // 2] = -np.inf                         # rows without any finite logit
+        perm = rng.permutation(5)                                  # memory order of (v, q, c, h, w)
+        mem = np.ascontiguousarray(x.transpose(perm))
+        st = [0] * 5
+        for pos_, ax in enumerate(perm):
+            st[ax] = mem.strides[pos_] // 4
+        thr = float(rng.choice([0.3, 0.0, 0.75]))
+        fuse = sorted(set(int(i) for i in rng.integers(0, c, size=int(rng.integers(0, 4)))))
+        nq = int(rng.integers(q, 120))
+        fs, fi = np.array([f + 1 for f in fuse] + [0], np.int32), np.array([nq + f + 1 for f in fuse] + [0], np.int32)
+        sem, ins, first = np.empty((v, h, w), np.int64), np.empty((v, h, w), np.int64), np.empty(q, np.int32)
+        rc = lib.labels2d_host(mem.ctypes.data, v, q, c, h, w, *st, thr, fs.ctypes.data, fi.ctypes.data, len(fuse), sem.ctypes.data, ins.ctypes.data,
+                               first.ctypes.data)
+        assert rc == 0, case
+        rs, ri, rinfo = LR.labels_from_qc_logits(x, list(range(q)), fuse, nq, thr)
+        assert np.array_equal(sem, rs) and np.array_equal(ins, ri), (case, (v, q, c, h, w), perm, thr, fuse)
+        assert [int(first[i["score"]]) for i in rinfo] == [i["label_id"] for i in rinfo] and int((first >= 0).sum()) == len(rinfo), case
+
+
+def test_labels2d_kernel_arithmetic_on_host_matches_goldens(tmp_path):
+    """The per-pixel functions of csrc/labels2d_core.h (shared by the CUDA kernel) compiled for the host, with the warp emulated:
+    bit-exact label maps and per-query first labels on the goldens, for the channel-last layout the rasteriser emits and the contiguous one."""
+    lib = _labels2d_host_lib(tmp_path)
+    z, meta = _labels2d_cases()
     for name, m in meta.items():
         v, q, c, h, w = m["shape"]
         for layout in ("vqchw", "vhwqc"):

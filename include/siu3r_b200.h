@@ -208,6 +208,18 @@ int siu3r_labels_from_qc_logits(const float* logits, int V, int Q, int C, int H,
                                 int64_t sw, float threshold, const int* fuse_sem, const int* fuse_ins, int n_fuse, int64_t* sem_id,
                                 int64_t* ins_id, int32_t* first_pix, int32_t* first_sem, void* stream);
 
+/* ---- image ingest ---------------------------------------------------------------------------------------------------
+ * preprocess_image (inference.py:13-38): PIL Image.resize((out_w, out_h), LANCZOS) of an 8-bit RGB frame [H, W, 3] (src_pitch bytes per
+ * row), crop of the window (crop_x, crop_y, cw, ch) of the resized image, /255 -> out [3, ch, cw] float32.  The resampling is Pillow's
+ * fixed-point algorithm (libImaging/Resample.c; two 8-bit passes, horizontal first), bit-exact.  bounds_* [out][2] = (first tap, tap count),
+ * k* [out][ksize] = round(coefficient * 2^22): device tables built by the host exactly as Pillow's precompute_coeffs /
+ * normalize_coeffs_8bpc do (siu3r_b200/io.py: lanczos_tables).  Only source rows [row0, row0 + rows) -- those the cropped output rows
+ * touch -- go through the horizontal pass; tmp = rows * cw * 3 bytes of workspace.  Parts of the crop window outside the resized image
+ * come out black (0.0), as PIL's Image.crop fills them. */
+int siu3r_resize_lanczos_u8(const uint8_t* src, int H, int W, int64_t src_pitch, const int32_t* bounds_x, const int32_t* kx, int ksize_x,
+                            int out_w, const int32_t* bounds_y, const int32_t* ky, int ksize_y, int out_h, int crop_x, int crop_y, int cw,
+                            int ch, int row0, int rows, uint8_t* tmp, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

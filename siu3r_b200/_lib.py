@@ -38,6 +38,7 @@ SIGNATURES = {
     "siu3r_conv_rows_up2x_tc": (_i, [_i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _l, _i, _p]),
     "siu3r_ply_record_words": (_i, [_i, _i, _i, _i]),
     "siu3r_labels_from_qc_logits": (_i, [_p, _i, _i, _i, _i, _i, _l, _l, _l, _l, _l, _f, _p, _p, _i, _p, _p, _p, _p, _p]),
+    "siu3r_resize_lanczos_u8": (_i, [_p, _i, _i, _l, _p, _p, _i, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
     "siu3r_ply_pack": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _l, _i, _i, _i, _p, _p]),
     "siu3r_gemm_tc_group2": (_i, [_p, _i, _i, _p, _l, _p, _l, _p, _l, _p, _p, _l, _i, _f, _p, _p, _i, _p, _p, _l, _i, _p]),
     "siu3r_gemm_tc_rope_vt": (_i, [_i, _i, _i, _p, _l, _p, _l, _p, _l, _p, _i, _p, _p, _i, _p, _l, _i, _p]),

@@ -27,6 +27,7 @@ def main(argv=None):
     ap.add_argument("--fy", type=float, default=318.0)
     ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32x3"])
     ap.add_argument("--synthetic_weights", action="store_true")
+    ap.add_argument("--gpu_ingest", action="store_true", help="resize / crop the decoded frames on the GPU (bit-identical to the PIL recipe)")
     args = ap.parse_args(argv)
     out = Path(args.output_path)
     out.mkdir(parents=True, exist_ok=True)
@@ -41,7 +42,11 @@ def main(argv=None):
             raise FileNotFoundError(f"Model file {args.model_path} does not exist.")
         sd = load_checkpoint(args.model_path)
     from .model import ModelCfg, SIU3RModel
-    images = torch.stack([preprocess_image(args.image_path1), preprocess_image(args.image_path2)], dim=0).unsqueeze(0)   # [1, 2, 3, 256, 256]
+    if args.gpu_ingest:
+        from .io import preprocess_views_cuda
+        images = preprocess_views_cuda([args.image_path1, args.image_path2])                                                # [1, 2, 3, 256, 256] on the device
+    else:
+        images = torch.stack([preprocess_image(args.image_path1), preprocess_image(args.image_path2)], dim=0).unsqueeze(0)   # [1, 2, 3, 256, 256]
     intrinsics = default_intrinsics(args.fx, args.fy, args.cx, args.cy)
     model = SIU3RModel(ModelCfg(image_size=(256, 256)), precision=args.precision)
     model.load_state_dict(sd)

@@ -117,3 +117,110 @@ def export_ply(means, scales, rotations, harmonics, opacities, semantic_labels, 
         f.write(ply_header(means.shape[0], attrs))
         f.write(host.numpy().tobytes())
     return path
+
+
+# ---- image ingest on the GPU ---------------------------------------------------------------------------
+import functools
+import math
+
+
+@functools.lru_cache(maxsize=256)
+def lanczos_tables(in_size: int, out_size: int):
+    """Window bounds [out, 2] (first tap, tap count), fixed-point coefficients [out, ksize] (int32, 22 fractional bits) and ksize of one
+    LANCZOS pass, computed as Pillow does (libImaging/Resample.c: precompute_coeffs with support 3 + normalize_coeffs_8bpc; double
+    precision, libm sin through math.sin).  in_size == out_size -> the identity pass (Pillow skips a pass that does not change the size)."""
+    if in_size == out_size:
+        bounds = np.stack([np.arange(out_size), np.ones(out_size, np.int64)], 1).astype(np.int32)
+        return bounds, np.full((out_size, 1), 1 << 22, np.int32), 1
+    scale = in_size / out_size
+    filterscale = max(scale, 1.0)
+    support = 3.0 * filterscale
+    ksize = int(math.ceil(support)) * 2 + 1
+    ss = 1.0 / filterscale
+
+    def sinc(x):
+        if x == 0.0:
+            return 1.0
+        x = x * math.pi
+        return math.sin(x) / x
+
+    def lanczos(x):
+        return sinc(x) * sinc(x / 3) if -3.0 <= x < 3.0 else 0.0
+
+    bounds = np.zeros((out_size, 2), np.int32)
+    kk = np.zeros((out_size, ksize), np.int32)
+    for xx in range(out_size):
+        center = 0.0 + (xx + 0.5) * scale
+        xmin = max(int(center - support + 0.5), 0)
+        xmax = min(int(center + support + 0.5), in_size) - xmin
+        w = [lanczos((x + xmin - center + 0.5) * ss) for x in range(xmax)]
+        ww = 0.0
+        for v in w:
+            ww += v
+        for x, v in enumerate(w):
+            if ww != 0.0:
+                v = v / ww
+            kk[xx, x] = int(-0.5 + v * (1 << 22)) if v < 0 else int(0.5 + v * (1 << 22))
+        bounds[xx] = (xmin, xmax)
+    return bounds, kk, ksize
+
+
+def resize_plan(W: int, H: int, size: int = 256):
+    """(new_W, new_H, crop_left, crop_top) of the reference recipe (inference.py:16-33), including its float rounding of the long side."""
+    if W < H:
+        new_W, new_H = size, int(H * (size / W))
+        return new_W, new_H, 0, (new_H - size) // 2
+    new_H, new_W = size, int(W * (size / H))
+    return new_W, new_H, (new_W - size) // 2, 0
+
+
+_DEVICE_TABLES = {}
+
+
+def _device_tables(in_size, out_size, dev):
+    key = (in_size, out_size, str(dev))
+    if key not in _DEVICE_TABLES:
+        b, k, ksize = lanczos_tables(in_size, out_size)
+        _DEVICE_TABLES[key] = (torch.from_numpy(b).to(dev), torch.from_numpy(np.ascontiguousarray(k)).to(dev), ksize, b)
+    return _DEVICE_TABLES[key]
+
+
+def preprocess_image_cuda(image, size: int = 256, device=None, out: torch.Tensor = None) -> torch.Tensor:
+    """GPU form of preprocess_image: the decoded 8-bit RGB frame is uploaded as it is ([H, W, 3] uint8: a path, a PIL image, a numpy array or
+    a torch uint8 tensor, host or device) and resized / cropped / scaled on the device -> [3, size, size] float32, bit-identical to
+    preprocess_image (csrc/resize.cu).  `out` (optional): a [3, size, size] float32 CUDA view to fill, e.g. a slot of a [B, V, 3, S, S] batch."""
+    lib = _lib.load()
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if isinstance(image, torch.Tensor):
+        frame = image
+    else:
+        if not isinstance(image, np.ndarray):
+            from PIL import Image
+            pil = image if isinstance(image, Image.Image) else Image.open(image)
+            image = np.array(pil.convert("RGB"))
+        frame = torch.from_numpy(np.ascontiguousarray(image))
+    assert frame.dtype == torch.uint8 and frame.dim() == 3 and frame.shape[2] == 3, "expected an [H, W, 3] uint8 RGB frame"
+    frame = frame.to(dev, non_blocking=True).contiguous()
+    H, W = int(frame.shape[0]), int(frame.shape[1])
+    new_W, new_H, cx, cy = resize_plan(W, H, size)
+    bx, kx, ksx, _ = _device_tables(W, new_W, dev)
+    by, ky, ksy, by_host = _device_tables(H, new_H, dev)
+    y_first, y_last = max(cy, 0), min(cy + size, new_H) - 1               # output rows of the crop window that exist in the resized image
+    row0 = int(by_host[y_first, 0])
+    rows = int(by_host[y_last, 0] + by_host[y_last, 1]) - row0
+    tmp = torch.empty(rows, size, 3, device=dev, dtype=torch.uint8)
+    if out is None:
+        out = torch.empty(3, size, size, device=dev, dtype=torch.float32)
+    assert out.shape == (3, size, size) and out.dtype == torch.float32 and out.is_cuda and out.is_contiguous()
+    _lib.check(lib.siu3r_resize_lanczos_u8(frame.data_ptr(), H, W, W * 3, bx.data_ptr(), kx.data_ptr(), ksx, new_W, by.data_ptr(), ky.data_ptr(), ksy,
+                                           new_H, cx, cy, size, size, row0, rows, tmp.data_ptr(), out.data_ptr(), ops._stream()), "resize_lanczos_u8")
+    return out
+
+
+def preprocess_views_cuda(images, size: int = 256, device=None) -> torch.Tensor:
+    """Batched ingest: V frames -> [1, V, 3, size, size] (the `images` tensor of inference.py:101-105) without a host-side resize."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    batch = torch.empty(1, len(images), 3, size, size, device=dev, dtype=torch.float32)
+    for v, im in enumerate(images):
+        preprocess_image_cuda(im, size, dev, out=batch[0, v])
+    return batch

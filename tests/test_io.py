@@ -116,3 +116,52 @@ def test_inference_cli_end_to_end(tmp_path):
     assert len(data) == hl + 131072 * 4 * nprops
     with pytest.raises(FileNotFoundError):
         inference.main(["--image_path1", str(tmp_path / "missing.jpg"), "--image_path2", str(p2), "--synthetic_weights"])
+
+
+# ---- GPU ingest (csrc/resize.cu): tables + integer passes checked on the host against PIL -------------------------------------------------
+INGEST_SIZES = [(1296, 968), (640, 480), (480, 640), (100, 80), (61, 97), (300, 300), (206, 206), (256, 256), (256, 300), (333, 256), (513, 777), (1920, 1080)]
+
+
+def _test_frame(W, H, seed):
+    rng = np.random.default_rng(seed)
+    img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    if seed % 2:
+        img[::3] = 255                                   # hard edges: LANCZOS ringing runs into the 0 / 255 clipping
+        img[1::3] = 0
+    return img
+
+
+@pytest.mark.parametrize("size", [256, 512])
+def test_ingest_tables_and_integer_passes_match_pil_on_host(tmp_path, size):
+    """siu3r_b200.io.lanczos_tables / resize_plan + the per-sample functions of csrc/resize_core.h (compiled for the host, driven with the
+    kernels' index arithmetic) reproduce preprocess_image (PIL LANCZOS resize + crop + /255, inference.py:13-38) bit for bit -- including
+    up-scaling, passes Pillow skips, and the square sizes whose resized side comes out one pixel short (black column from Image.crop)."""
+    import ctypes
+    import subprocess
+    from PIL import Image
+    from siu3r_b200 import io as sio
+    so = str(tmp_path / "libresize_host.so")
+    subprocess.run(["g++", "-O2", "-shared", "-fPIC", "-std=c++17", "-I", os.path.join(ROOT, "siu3r_b200", "csrc"),
+                    os.path.join(ROOT, "tests", "host_core", "resize_host.cpp"), "-o", so], check=True)
+    lib = ctypes.CDLL(so)
+    P, I = ctypes.c_void_p, ctypes.c_int
+    lib.resize_host.argtypes = [P, I, I, ctypes.c_int64, P, P, I, I, P, P, I, I, I, I, I, I, I, I, P]
+    short = False
+    for n, (W, H) in enumerate(INGEST_SIZES):
+        img = _test_frame(W, H, n)
+        want = sio.preprocess_image(Image.fromarray(img), size).numpy()
+        if size == 256:
+            assert np.array_equal(want, _reference_preprocess(Image.fromarray(img)).numpy())
+        new_W, new_H, cx, cy = sio.resize_plan(W, H, size)
+        short |= cx < 0
+        bx, kx, ksx = sio.lanczos_tables(W, new_W)
+        by, ky, ksy = sio.lanczos_tables(H, new_H)
+        y_first, y_last = max(cy, 0), min(cy + size, new_H) - 1
+        row0 = int(by[y_first, 0])
+        rows = int(by[y_last, 0] + by[y_last, 1]) - row0
+        got = np.empty((3, size, size), np.float32)
+        kx, ky = np.ascontiguousarray(kx), np.ascontiguousarray(ky)
+        rc = lib.resize_host(img.ctypes.data, H, W, W * 3, bx.ctypes.data, kx.ctypes.data, ksx, new_W, by.ctypes.data, ky.ctypes.data, ksy, new_H,
+                             cx, cy, size, size, row0, rows, got.ctypes.data)
+        assert rc == 0 and np.array_equal(got, want), (W, H, size, float(np.abs(got - want).max()))
+    assert short or size != 256                          # 206 x 206 -> 255 wide at size 256: the out-of-image crop column was exercised

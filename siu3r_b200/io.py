@@ -45,9 +45,41 @@ def default_intrinsics(fx: float = 318.0, fy: float = 318.0, cx: float = 128.0, 
     return K.repeat(1, views, 1, 1)
 
 
+class _Placeholder:
+    """Stands in for a class of the reference's own packages that a checkpoint pickled by reference (the Lightning checkpoint stores
+    hyper_parameters["cfg"] = RootCfg from src.config, with members from src.data.config etc.: pipeline.py:26,39): keeps whatever state it is given."""
+
+    def __init__(self, *args, **kwargs):
+        self._args, self._kwargs = args, kwargs
+
+    def __setstate__(self, state):
+        if isinstance(state, dict):
+            self.__dict__.update(state)
+        else:
+            self._state = state
+
+
+class _TolerantPickle:
+    """pickle_module for torch.load: classes that cannot be imported (the reference tree is not on sys.path) become _Placeholder subclasses
+    instead of failing the whole load -- only the tensors of "state_dict" are wanted."""
+    import pickle as _pickle
+    __name__ = "siu3r_b200_tolerant_pickle"
+    load, loads, dump, dumps = _pickle.load, _pickle.loads, _pickle.dump, _pickle.dumps
+    HIGHEST_PROTOCOL, DEFAULT_PROTOCOL = _pickle.HIGHEST_PROTOCOL, _pickle.DEFAULT_PROTOCOL
+    PickleError, PicklingError, UnpicklingError, Pickler = _pickle.PickleError, _pickle.PicklingError, _pickle.UnpicklingError, _pickle.Pickler
+
+    class Unpickler(_pickle.Unpickler):
+        def find_class(self, module, name):
+            try:
+                return super().find_class(module, name)
+            except (ImportError, AttributeError):
+                return type(name, (_Placeholder,), {"__module__": module})
+
+
 def load_checkpoint(path) -> dict:
-    """State dict of the model from a Lightning checkpoint (keys prefixed "model.") or a plain state_dict file."""
-    ckpt = torch.load(path, map_location="cpu", weights_only=False)
+    """State dict of the model from a Lightning checkpoint (keys prefixed "model.") or a plain state_dict file.  The reference's checkpoint
+    also pickles its config dataclasses (src.config.RootCfg, ...); they are not needed and are tolerated when that package is absent."""
+    ckpt = torch.load(path, map_location="cpu", weights_only=False, pickle_module=_TolerantPickle)
     sd = ckpt.get("state_dict", ckpt) if isinstance(ckpt, dict) else ckpt
     if any(k.startswith("model.") for k in sd):
         sd = {k[len("model."):]: v for k, v in sd.items() if k.startswith("model.")}

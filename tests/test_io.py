@@ -165,3 +165,45 @@ def test_ingest_tables_and_integer_passes_match_pil_on_host(tmp_path, size):
                              cx, cy, size, size, row0, rows, got.ctypes.data)
         assert rc == 0 and np.array_equal(got, want), (W, H, size, float(np.abs(got - want).max()))
     assert short or size != 256                          # 206 x 206 -> 255 wide at size 256: the out-of-image crop column was exercised
+
+
+def test_load_checkpoint_tolerates_pickled_reference_config(tmp_path):
+    """The reference's Lightning checkpoint pickles hyper_parameters["cfg"] = src.config.RootCfg (dataclasses from src.config / src.data.config,
+    pipeline.py:26,39; SURVEY.md section 8b).  Without the reference tree on sys.path a plain torch.load raises ModuleNotFoundError;
+    load_checkpoint must still return the "model."-stripped tensors (and drop non-model entries such as the lpips weights)."""
+    import dataclasses
+    import enum
+    import pathlib
+    import types
+    from siu3r_b200.io import load_checkpoint
+    mods = {n: types.ModuleType(n) for n in ("src", "src.config", "src.data", "src.data.config")}
+    sys.modules.update(mods)
+    try:
+        @dataclasses.dataclass
+        class DataCfg:
+            root: pathlib.Path
+            views: int = 2
+
+        class Mode(enum.Enum):
+            A = 1
+
+        @dataclasses.dataclass
+        class RootCfg:
+            data: DataCfg
+            mode: Mode
+            name: str = "x"
+        for cls, mod in ((DataCfg, "src.data.config"), (Mode, "src.config"), (RootCfg, "src.config")):
+            cls.__module__, cls.__qualname__ = mod, cls.__name__
+            setattr(mods[mod], cls.__name__, cls)
+        ck = {"state_dict": {"model.backbone.w": torch.arange(6.0).view(2, 3), "lpips.net.x": torch.zeros(1)},
+              "hyper_parameters": {"cfg": RootCfg(DataCfg(pathlib.Path("/d")), Mode.A)}, "epoch": 100}
+        torch.save(ck, tmp_path / "fake.ckpt")
+    finally:
+        for n in mods:
+            sys.modules.pop(n, None)
+    with pytest.raises(ModuleNotFoundError):
+        torch.load(tmp_path / "fake.ckpt", weights_only=False)
+    sd = load_checkpoint(tmp_path / "fake.ckpt")
+    assert list(sd) == ["backbone.w"] and torch.equal(sd["backbone.w"], torch.arange(6.0).view(2, 3))
+    torch.save({"a": torch.ones(2)}, tmp_path / "plain.pt")
+    assert torch.equal(load_checkpoint(tmp_path / "plain.pt")["a"], torch.ones(2))

@@ -7,6 +7,7 @@ Public surface (mirrors the reference):
   siu3r_b200.render_cuda       <-> /root/reference/src/models/cuda_splatting.py:46-122
   siu3r_b200.Gaussians         <-> /root/reference/src/utils/gaussians_types.py:4-38
   siu3r_b200.labels_from_qc_logits <-> the 2-D label extraction of /root/reference/src/pipeline.py:132-193 (viewer.py:422-435: viewer_labels)
+  siu3r_b200.curope.{rope_2d, cuRoPE2D} <-> /root/reference/src/models/croco/curope/{curope.cpp:49-65, curope2d.py:32-40}
   siu3r_b200.PairPipeline      <-> the upload / forward / detach_cpu_copy loop of /root/reference/inference.py:119-141, overlapped
 """
 from .gaussians import Gaussians  # noqa: F401

@@ -489,3 +489,14 @@ def test_every_entry_point_refuses_null_arguments():
         assert getattr(lib, name)(*vals) == -1, name
         checked += 1
     assert checked >= 40
+
+
+def test_curope_dropin_argument_checks_on_host():
+    """siu3r_b200.curope.rope_2d raises the reference's own messages (curope.cpp:54-59) before touching the device, and refuses host tensors
+    (the reference would rotate them on the CPU; this library has no CPU path)."""
+    from siu3r_b200.curope import rope_2d
+    tok, pos = torch.zeros(1, 4, 2, 8), torch.zeros(1, 4, 2, dtype=torch.int64)
+    for bt, bp, msg in [(tok[0], pos, "tokens must have 4 dimensions"), (tok, pos[0], "positions must have 3 dimensions"),
+                        (tok, pos[:, :3], "seq_length differs"), (tok, pos[..., :1], "must be equal to 2"), (tok, pos, "no CPU path")]:
+        with pytest.raises(RuntimeError, match=msg):
+            rope_2d(bt, bp, 100.0, 1.0)

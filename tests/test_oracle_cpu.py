@@ -500,3 +500,22 @@ def test_curope_dropin_argument_checks_on_host():
                         (tok, pos[:, :3], "seq_length differs"), (tok, pos[..., :1], "must be equal to 2"), (tok, pos, "no CPU path")]:
         with pytest.raises(RuntimeError, match=msg):
             rope_2d(bt, bp, 100.0, 1.0)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the driver's reference arm): one JSON line with the base contract's keys plus impl / cpu_baseline / e2e,
+    measured on the host cores with the oracle port; under torchrun only rank 0 works, the other ranks exit 0 silently.  Small size here."""
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--size", "64"],
+                       capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config"):
+        assert k in line, k
+    assert line["impl"] == "reference" and line["unit"] == "pairs/s" and line["value"] > 0 and line["vs_baseline"] is None
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["value"] == line["value"]
+    assert line["e2e"] == {"value": line["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in line["config"] and "model" not in line["config"]
+    r1 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0", "--size", "64"],
+                        capture_output=True, text=True, timeout=600, env=dict(env, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2"))
+    assert r1.returncode == 0 and r1.stdout.strip() == ""

@@ -44,9 +44,28 @@ class ModelCfg:
     sh_degree: int = 4
     interaction_indexes: tuple = (5, 11, 17, 23)
 
+    @classmethod
+    def from_reference(cls, cfg) -> "ModelCfg":
+        """Accepts the reference's nested ModelCfg (src/config.py:46-80: .croco, .mask2former, .gaussian_head, .image_size) -- the object
+        SIU3RModel(cfg) is built from in pipeline.py:31 -- and checks that it describes the architecture this engine implements
+        (ViT-L/16 encoder, 12-layer 768-wide decoder, 64-wide heads, RoPE100, SH degree 4); anything else is refused, not approximated."""
+        c, m, g = cfg.croco, cfg.mask2former, cfg.gaussian_head
+        ref = cls()
+        got = dict(enc_depth=c.enc_depth, dec_depth=c.dec_depth, enc_embed_dim=c.enc_embed_dim, dec_embed_dim=c.dec_embed_dim,
+                   enc_num_heads=c.enc_num_heads, dec_num_heads=c.dec_num_heads, patch_size=c.patch_size, sh_degree=g.sh_degree)
+        bad = {k: v for k, v in got.items() if v != getattr(ref, k)}
+        if getattr(c, "pos_embed", "RoPE100") != "RoPE100":
+            bad["pos_embed"] = c.pos_embed
+        if bad:
+            raise ValueError(f"siu3r_b200 implements the published SIU3R architecture only; unsupported configuration values: {bad}")
+        return cls(image_size=tuple(cfg.image_size), num_queries=m.num_queries, seg_threshold=m.seg_threshold, id2label=dict(m.id2label),
+                   label_ids_to_fuse=list(m.label_ids_to_fuse), **got)
+
 
 class SIU3RModel:
     def __init__(self, cfg: ModelCfg | None = None, precision: str = "tf32"):
+        if cfg is not None and hasattr(cfg, "croco") and hasattr(cfg, "mask2former"):
+            cfg = ModelCfg.from_reference(cfg)        # the reference's own nested config object
         self.cfg = cfg or ModelCfg()
         assert precision in ("tf32", "fp32x3")
         self.prec = ops.PREC_TF32 if precision == "tf32" else ops.PREC_FP32X3

@@ -519,3 +519,35 @@ def test_bench_reference_arm_contract():
     r1 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0", "--size", "64"],
                         capture_output=True, text=True, timeout=600, env=dict(env, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2"))
     assert r1.returncode == 0 and r1.stdout.strip() == ""
+
+
+def test_model_accepts_the_reference_config_object():
+    """SIU3RModel(cfg) takes the reference's nested ModelCfg (src/config.py:46-80, the object pipeline.py:31 passes) -- checked with the
+    reference's own dataclasses when /root/reference is present, and with a duck-typed stand-in otherwise -- and refuses architectures the
+    engine does not implement."""
+    from types import SimpleNamespace as NS
+    from siu3r_b200.model import ModelCfg, SIU3RModel, SIU3RMultiViewModel
+
+    def duck(**over):
+        croco = dict(enc_depth=24, dec_depth=12, enc_embed_dim=1024, dec_embed_dim=768, enc_num_heads=16, dec_num_heads=12, pos_embed="RoPE100",
+                     patch_size=16, freeze="encoder")
+        croco.update(over)
+        return NS(croco=NS(**croco), mask2former=NS(id2label={1: "wall", 2: "floor"}, seg_threshold=0.4, label_ids_to_fuse=[0], num_queries=100),
+                  gaussian_head=NS(gaussian_scale_min=0.5, gaussian_scale_max=15.0, sh_degree=4), image_size=[512, 512], pretrained_weights_path=None)
+
+    cfgs = [duck()]
+    if os.path.isdir("/root/reference/src"):
+        sys.path.insert(0, "/root/reference")
+        sys.path.append(os.path.join(ROOT, "oracle", "stubs"))
+        from src.config import CrocoCfg, GaussianHeadCfg, Mask2formerCfg
+        from src.config import ModelCfg as RefModelCfg
+        cfgs.append(RefModelCfg(croco=CrocoCfg(), gaussian_head=GaussianHeadCfg(), image_size=[512, 512],
+                                mask2former=Mask2formerCfg(id2label={1: "wall", 2: "floor"}, seg_threshold=0.4, label_ids_to_fuse=[0])))
+    for ref_cfg in cfgs:
+        for cls in (SIU3RModel, SIU3RMultiViewModel):
+            m = cls(ref_cfg)
+            assert isinstance(m.cfg, ModelCfg) and m.cfg.image_size == (512, 512) and m.cfg.seg_threshold == 0.4
+            assert m.cfg.label_ids_to_fuse == [0] and m.cfg.id2label == {1: "wall", 2: "floor"} and m.cfg.num_queries == 100
+    for over in (dict(enc_depth=12), dict(dec_embed_dim=512), dict(pos_embed="cosine"), dict(patch_size=14)):
+        with pytest.raises(ValueError, match="unsupported configuration"):
+            SIU3RModel(duck(**over))

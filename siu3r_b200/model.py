@@ -79,9 +79,23 @@ class SIU3RModel:
 
     # ---- nn.Module-like surface -------------------------------------------------------------------------------
     def load_state_dict(self, sd: dict, strict: bool = False):
+        """nn.Module.load_state_dict semantics against the reference key set (state_shapes.json: the 1660 entries of SIU3RModel.state_dict()):
+        returns (missing_keys, unexpected_keys); strict=True raises on either; a tensor of the wrong shape always raises, as torch does.
+        The reference loads with strict=False (inference.py:119-121), so e.g. the lpips.* entries of a Lightning checkpoint are ignored."""
+        from .synth import load_state_shapes
+        expected = load_state_shapes()
+        missing = [k for k in expected if k not in sd]
+        unexpected = [k for k in sd if k not in expected]
+        wrong = [f"{k}: checkpoint {list(sd[k].shape)} vs model {expected[k][0]}" for k in expected
+                 if k in sd and hasattr(sd[k], "shape") and list(sd[k].shape) != list(expected[k][0])]
+        if wrong:
+            raise RuntimeError("Error(s) in loading state_dict for SIU3RModel: size mismatch for " + "; ".join(wrong[:8]) + (" ..." if len(wrong) > 8 else ""))
+        if strict and (missing or unexpected):
+            raise RuntimeError(f"Error(s) in loading state_dict for SIU3RModel: {len(missing)} missing key(s) {missing[:4]}, "
+                               f"{len(unexpected)} unexpected key(s) {unexpected[:4]}")
         self._sd = sd
         self._ready = False
-        return SimpleNamespace(missing_keys=[], unexpected_keys=[])
+        return SimpleNamespace(missing_keys=missing, unexpected_keys=unexpected)
 
     def eval(self):
         return self

@@ -551,3 +551,22 @@ def test_model_accepts_the_reference_config_object():
     for over in (dict(enc_depth=12), dict(dec_embed_dim=512), dict(pos_embed="cosine"), dict(patch_size=14)):
         with pytest.raises(ValueError, match="unsupported configuration"):
             SIU3RModel(duck(**over))
+
+
+def test_load_state_dict_semantics(state_dict):
+    """load_state_dict mirrors nn.Module: key report with strict=False (what inference.py:119-121 uses), errors with strict=True and on shapes."""
+    from siu3r_b200.model import ModelCfg, SIU3RModel
+    m = SIU3RModel(ModelCfg(image_size=(64, 64)))
+    r = m.load_state_dict(state_dict, strict=True)
+    assert r.missing_keys == [] and r.unexpected_keys == []
+    sd = dict(state_dict)
+    sd["lpips.net.scaling_layer.shift"] = torch.zeros(1, 3, 1, 1)
+    del sd["backbone.enc_norm.weight"]
+    r = m.load_state_dict(sd)
+    assert r.missing_keys == ["backbone.enc_norm.weight"] and r.unexpected_keys == ["lpips.net.scaling_layer.shift"]
+    with pytest.raises(RuntimeError, match="missing key"):
+        m.load_state_dict(sd, strict=True)
+    sd = dict(state_dict)
+    sd["backbone.enc_norm.weight"] = torch.zeros(7)
+    with pytest.raises(RuntimeError, match="size mismatch"):
+        m.load_state_dict(sd)

@@ -206,15 +206,31 @@ def resize_plan(W: int, H: int, size: int = 256):
     return new_W, new_H, (new_W - size) // 2, 0
 
 
-_DEVICE_TABLES = {}
+def ingest_plan(W: int, H: int, size: int = 256) -> dict:
+    """Everything siu3r_resize_lanczos_u8 needs for a W x H frame, as host values: resized size, crop origin (may be negative: resize_plan),
+    the two coefficient tables, and the range of source rows [row0, row0 + rows) that the cropped output rows read -- only those go through
+    the horizontal pass (Pillow makes the same cut, ImagingResample's ybox_first / ybox_last)."""
+    new_W, new_H, cx, cy = resize_plan(W, H, size)
+    bx, kx, ksx = lanczos_tables(W, new_W)
+    by, ky, ksy = lanczos_tables(H, new_H)
+    y_first, y_last = max(cy, 0), min(cy + size, new_H) - 1               # output rows of the crop window that exist in the resized image
+    row0 = int(by[y_first, 0])
+    rows = int(by[y_last, 0] + by[y_last, 1]) - row0
+    return dict(new_W=new_W, new_H=new_H, crop_x=cx, crop_y=cy, row0=row0, rows=rows, bounds_x=bx, kx=np.ascontiguousarray(kx), ksize_x=ksx,
+                bounds_y=by, ky=np.ascontiguousarray(ky), ksize_y=ksy)
 
 
-def _device_tables(in_size, out_size, dev):
-    key = (in_size, out_size, str(dev))
-    if key not in _DEVICE_TABLES:
-        b, k, ksize = lanczos_tables(in_size, out_size)
-        _DEVICE_TABLES[key] = (torch.from_numpy(b).to(dev), torch.from_numpy(np.ascontiguousarray(k)).to(dev), ksize, b)
-    return _DEVICE_TABLES[key]
+_DEVICE_PLANS = {}
+
+
+def _device_plan(W, H, size, dev):
+    key = (W, H, size, str(dev))
+    if key not in _DEVICE_PLANS:
+        plan = ingest_plan(W, H, size)
+        for k in ("bounds_x", "kx", "bounds_y", "ky"):
+            plan[k] = torch.from_numpy(plan[k]).to(dev)
+        _DEVICE_PLANS[key] = plan
+    return _DEVICE_PLANS[key]
 
 
 def preprocess_image_cuda(image, size: int = 256, device=None, out: torch.Tensor = None) -> torch.Tensor:
@@ -234,18 +250,14 @@ def preprocess_image_cuda(image, size: int = 256, device=None, out: torch.Tensor
     assert frame.dtype == torch.uint8 and frame.dim() == 3 and frame.shape[2] == 3, "expected an [H, W, 3] uint8 RGB frame"
     frame = frame.to(dev, non_blocking=True).contiguous()
     H, W = int(frame.shape[0]), int(frame.shape[1])
-    new_W, new_H, cx, cy = resize_plan(W, H, size)
-    bx, kx, ksx, _ = _device_tables(W, new_W, dev)
-    by, ky, ksy, by_host = _device_tables(H, new_H, dev)
-    y_first, y_last = max(cy, 0), min(cy + size, new_H) - 1               # output rows of the crop window that exist in the resized image
-    row0 = int(by_host[y_first, 0])
-    rows = int(by_host[y_last, 0] + by_host[y_last, 1]) - row0
-    tmp = torch.empty(rows, size, 3, device=dev, dtype=torch.uint8)
+    p = _device_plan(W, H, size, dev)
+    tmp = torch.empty(p["rows"], size, 3, device=dev, dtype=torch.uint8)
     if out is None:
         out = torch.empty(3, size, size, device=dev, dtype=torch.float32)
     assert out.shape == (3, size, size) and out.dtype == torch.float32 and out.is_cuda and out.is_contiguous()
-    _lib.check(lib.siu3r_resize_lanczos_u8(frame.data_ptr(), H, W, W * 3, bx.data_ptr(), kx.data_ptr(), ksx, new_W, by.data_ptr(), ky.data_ptr(), ksy,
-                                           new_H, cx, cy, size, size, row0, rows, tmp.data_ptr(), out.data_ptr(), ops._stream()), "resize_lanczos_u8")
+    _lib.check(lib.siu3r_resize_lanczos_u8(frame.data_ptr(), H, W, W * 3, p["bounds_x"].data_ptr(), p["kx"].data_ptr(), p["ksize_x"], p["new_W"],
+                                           p["bounds_y"].data_ptr(), p["ky"].data_ptr(), p["ksize_y"], p["new_H"], p["crop_x"], p["crop_y"], size, size,
+                                           p["row0"], p["rows"], tmp.data_ptr(), out.data_ptr(), ops._stream()), "resize_lanczos_u8")
     return out
 
 

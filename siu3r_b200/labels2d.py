@@ -56,21 +56,24 @@ def labels_from_qc_logits(render_qc_logits, context_seg_query_scores, label_ids_
     all_ins = torch.empty(b, v, h, w, device=dev, dtype=torch.int64)
     firsts = [_extract(logits, pairs, threshold, all_sem[bi], all_ins[bi])[2]      # launches for the whole batch first, downloads afterwards
               for bi, logits in enumerate(render_qc_logits)]
-    seg_infos = []
-    for f, q_score in zip(firsts, context_seg_query_scores):
-        first_sem = f.cpu().tolist()
-        info = []
-        for q_idx, q_score_i in enumerate(q_score):
-            if first_sem[q_idx] < 0:                      # the query owns no pixel (:168-169)
-                continue
-            info.append({"id": q_idx + 1, "label_id": first_sem[q_idx], "was_fused": False, "score": q_score_i})
-        for sem_value, ins_value in pairs:                # :182-191 (a stuff label in an info implies that some pixel carries it)
-            for i in info:
-                if i["label_id"] == sem_value:
-                    i["was_fused"] = True
-                    i["id"] = ins_value
-        seg_infos.append(info)
+    seg_infos = [seg_infos_from_first_labels(f.cpu().tolist(), q_score, pairs) for f, q_score in zip(firsts, context_seg_query_scores)]
     return all_sem, all_ins, seg_infos
+
+
+def seg_infos_from_first_labels(first_sem, q_score, fuse_pairs):
+    """pipeline.py:165-191 on the host: first_sem[q] = semantic id of the first pixel query q owns (-1: none, the query is dropped, :168-169);
+    infos whose label is a fused stuff class take that class's instance id (a stuff label in an info implies that some pixel carries it)."""
+    info = []
+    for q_idx, q_score_i in enumerate(q_score):
+        if first_sem[q_idx] < 0:
+            continue
+        info.append({"id": q_idx + 1, "label_id": first_sem[q_idx], "was_fused": False, "score": q_score_i})
+    for sem_value, ins_value in fuse_pairs:
+        for i in info:
+            if i["label_id"] == sem_value:
+                i["was_fused"] = True
+                i["id"] = ins_value
+    return info
 
 
 def viewer_labels(render_qc_logit: torch.Tensor, semantic_threshold: float = 0.3):

@@ -152,17 +152,13 @@ def test_ingest_tables_and_integer_passes_match_pil_on_host(tmp_path, size):
         want = sio.preprocess_image(Image.fromarray(img), size).numpy()
         if size == 256:
             assert np.array_equal(want, _reference_preprocess(Image.fromarray(img)).numpy())
-        new_W, new_H, cx, cy = sio.resize_plan(W, H, size)
-        short |= cx < 0
-        bx, kx, ksx = sio.lanczos_tables(W, new_W)
-        by, ky, ksy = sio.lanczos_tables(H, new_H)
-        y_first, y_last = max(cy, 0), min(cy + size, new_H) - 1
-        row0 = int(by[y_first, 0])
-        rows = int(by[y_last, 0] + by[y_last, 1]) - row0
+        p = sio.ingest_plan(W, H, size)                   # the same host plan preprocess_image_cuda hands to siu3r_resize_lanczos_u8
+        short |= p["crop_x"] < 0
+        assert 0 <= p["row0"] and p["row0"] + p["rows"] <= H
         got = np.empty((3, size, size), np.float32)
-        kx, ky = np.ascontiguousarray(kx), np.ascontiguousarray(ky)
-        rc = lib.resize_host(img.ctypes.data, H, W, W * 3, bx.ctypes.data, kx.ctypes.data, ksx, new_W, by.ctypes.data, ky.ctypes.data, ksy, new_H,
-                             cx, cy, size, size, row0, rows, got.ctypes.data)
+        rc = lib.resize_host(img.ctypes.data, H, W, W * 3, p["bounds_x"].ctypes.data, p["kx"].ctypes.data, p["ksize_x"], p["new_W"],
+                             p["bounds_y"].ctypes.data, p["ky"].ctypes.data, p["ksize_y"], p["new_H"], p["crop_x"], p["crop_y"], size, size,
+                             p["row0"], p["rows"], got.ctypes.data)
         assert rc == 0 and np.array_equal(got, want), (W, H, size, float(np.abs(got - want).max()))
     assert short or size != 256                          # 206 x 206 -> 255 wide at size 256: the out-of-image crop column was exercised
 

@@ -439,8 +439,9 @@ def test_labels2d_kernel_arithmetic_on_host_matches_goldens(tmp_path):
                                    sem.ctypes.data, ins.ctypes.data, first.ctypes.data)
             assert rc == 0, (name, layout, rc)
             assert np.array_equal(sem, z[name + "__sem"]) and np.array_equal(ins, z[name + "__ins"]), (name, layout)
-            got_infos = [(qi + 1, int(first[qi])) for qi in range(q) if first[qi] >= 0]
-            assert [l for _, l in got_infos] == [i["label_id"] for i in m["infos"]], (name, layout, got_infos, m["infos"])
+            from siu3r_b200.labels2d import seg_infos_from_first_labels     # the host half of labels_from_qc_logits
+            infos = seg_infos_from_first_labels(first.tolist(), m["scores"], list(zip(fs.tolist(), fi.tolist())))
+            assert infos == m["infos"], (name, layout, infos, m["infos"])
 
 
 def test_model_input_checks_and_no_cpu_fallback():

@@ -11,6 +11,8 @@ instead downloads every attribute, concatenates them in float64 and converts G r
 """
 from __future__ import annotations
 
+import functools
+import math
 from pathlib import Path
 
 import numpy as np
@@ -152,10 +154,6 @@ def export_ply(means, scales, rotations, harmonics, opacities, semantic_labels, 
 
 
 # ---- image ingest on the GPU ---------------------------------------------------------------------------
-import functools
-import math
-
-
 @functools.lru_cache(maxsize=256)
 def lanczos_tables(in_size: int, out_size: int):
     """Window bounds [out, 2] (first tap, tap count), fixed-point coefficients [out, ksize] (int32, 22 fractional bits) and ksize of one

@@ -76,6 +76,9 @@ class SIU3RModel:
         self.capture = None  # set to a dict to record stage-boundary tensors (tests)
         S0, S1 = self.cfg.image_size
         assert S0 % 32 == 0 and S1 % 32 == 0, "image size must be a multiple of 32 (patch 16, adapter stride 32)"
+        if S0 > S1:
+            # the reference's heads run portrait batches transposed (transpose_to_landscape, croco/misc.py:71-113); not implemented here
+            raise NotImplementedError(f"portrait image_size {S0}x{S1}: only landscape / square sizes (H <= W) are implemented")
 
     # ---- nn.Module-like surface -------------------------------------------------------------------------------
     def load_state_dict(self, sd: dict, strict: bool = False):

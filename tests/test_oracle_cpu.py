@@ -463,6 +463,8 @@ def test_model_input_checks_and_no_cpu_fallback():
         SIU3RModel(ModelCfg(image_size=(60, 64)))                  # refused at construction (patch 16, adapter stride 32)
     with pytest.raises(AssertionError, match="multiple of patch size"):
         m._check_inputs(torch.zeros(1, 2, 3, 60, 64))
+    with pytest.raises(NotImplementedError, match="portrait"):
+        SIU3RModel(ModelCfg(image_size=(96, 64)))                  # the heads' transpose_to_landscape branch (croco/misc.py:71-113) is not implemented
     mv = SIU3RMultiViewModel(ModelCfg(image_size=(64, 64)))
     mv._ready = True
     assert mv._check_inputs(torch.zeros(1, 5, 3, 64, 64)) == (1, 5, 64, 64)

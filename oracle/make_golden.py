@@ -2,6 +2,7 @@
 
 Run in the build container (needs /root/reference):   python oracle/make_golden.py 64 256 512
                                                        python oracle/make_golden.py --views=4 64 256 512   (multi-view model)
+                                                       python oracle/make_golden.py 64x96                   (rectangular H x W frame)
 Each fixture holds, per stage boundary of SIU3RModel.forward, the tensor's shape / mean / abs-mean / abs-max and
 2048 samples at fixed pseudo-random flat indices (oracle/ref_model.py:sample_indices), plus the full small outputs
 (class logits, segment infos, label histograms).  Inputs and weights are regenerated on the GPU box from seeds
@@ -53,7 +54,8 @@ def main(sizes, views=2):
         meta["qc0"] = s2
         meta["sem_hist"] = torch.bincount(st["g_semantic_labels"].flatten().long(), minlength=22).tolist()
         meta["inst_hist"] = torch.bincount(st["g_instance_labels"].flatten().long()).tolist()
-        name = f"model_S{S}.npz" if views == 2 else f"model_V{views}_S{S}.npz"
+        tag = S if isinstance(S, int) else f"{S[0]}x{S[1]}"
+        name = f"model_S{tag}.npz" if views == 2 else f"model_V{views}_S{tag}.npz"
         np.savez_compressed(os.path.join(OUT, name), meta=json.dumps(meta), **arrays)
         print(f"S={S}: build {t1 - t0:.1f}s forward {t2 - t1:.1f}s infos={st['seg_infos']}", flush=True)
 
@@ -61,4 +63,4 @@ def main(sizes, views=2):
 if __name__ == "__main__":
     args = [a for a in sys.argv[1:] if not a.startswith("--views=")]
     nv = [int(a.split("=")[1]) for a in sys.argv[1:] if a.startswith("--views=")]
-    main([int(a) for a in args] or [64, 256], views=nv[0] if nv else 2)
+    main([tuple(int(x) for x in a.split("x")) if "x" in a else int(a) for a in args] or [64, 256], views=nv[0] if nv else 2)

@@ -45,11 +45,12 @@ def _import_reference():
 from siu3r_b200.synth import SHAPES_JSON, load_state_shapes, make_state_dict  # noqa: E402,F401  (reference-free generator)
 
 
-def synthetic_inputs(batch: int, views: int, size: int, seed: int = 0):
-    """images = rand(B,V,3,S,S) seeded; K = inference.py defaults (318/256, .5)."""
+def synthetic_inputs(batch: int, views: int, size, seed: int = 0):
+    """images = rand(B,V,3,H,W) seeded (size = S or (H, W)); K = inference.py defaults (318/256, .5)."""
     g = torch.Generator(device="cpu")
     g.manual_seed(1000 + seed)
-    img = torch.rand(batch, views, 3, size, size, generator=g)
+    H, W = (size, size) if isinstance(size, int) else size
+    img = torch.rand(batch, views, 3, H, W, generator=g)
     K = torch.tensor([[318 / 256, 0, 0.5], [0, 318 / 256, 0.5], [0, 0, 1.0]])
     K = K[None, None].repeat(batch, views, 1, 1).contiguous()
     return img, K
@@ -58,7 +59,7 @@ def synthetic_inputs(batch: int, views: int, size: int, seed: int = 0):
 # --------------------------------------------------------------------------------------
 # Reference construction + staged forward
 # --------------------------------------------------------------------------------------
-def build_reference(size: int, state_dict: dict | None = None, multiview: bool = False):
+def build_reference(size, state_dict: dict | None = None, multiview: bool = False):
     _import_reference()
     from src.config import CrocoCfg, GaussianHeadCfg, Mask2formerCfg, ModelCfg
     from src.utils.scannet_constant import PANOPTIC_SEMANTIC2NAME, STUFF_CLASSES
@@ -66,7 +67,7 @@ def build_reference(size: int, state_dict: dict | None = None, multiview: bool =
     cfg = ModelCfg(
         croco=CrocoCfg(),
         gaussian_head=GaussianHeadCfg(),
-        image_size=[size, size],
+        image_size=[size, size] if isinstance(size, int) else list(size),
         pretrained_weights_path=None,
         mask2former=Mask2formerCfg(id2label=PANOPTIC_SEMANTIC2NAME, label_ids_to_fuse=STUFF_CLASSES),
     )

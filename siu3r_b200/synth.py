@@ -10,11 +10,12 @@ import torch
 SHAPES_JSON = os.path.join(os.path.dirname(os.path.abspath(__file__)), "state_shapes.json")  # reference state_dict key set: name -> [shape, dtype]
 
 
-def pair_inputs(batch: int, views: int, size: int, seed: int = 0):
-    """images rand(B,V,3,S,S) in [0,1]; K = inference.py defaults (fx = fy = 318/256, cx = cy = 0.5) normalised."""
+def pair_inputs(batch: int, views: int, size, seed: int = 0):
+    """images rand(B,V,3,H,W) in [0,1] (size = S for square frames or (H, W)); K = inference.py defaults (fx = fy = 318/256, cx = cy = 0.5) normalised."""
     g = torch.Generator(device="cpu")
     g.manual_seed(1000 + seed)
-    img = torch.rand(batch, views, 3, size, size, generator=g)
+    H, W = (size, size) if isinstance(size, int) else size
+    img = torch.rand(batch, views, 3, H, W, generator=g)
     K = torch.tensor([[318 / 256, 0, 0.5], [0, 318 / 256, 0.5], [0, 0, 1.0]])
     return img, K[None, None].repeat(batch, views, 1, 1).contiguous()
 

@@ -28,11 +28,12 @@ def state_dict():
     return synth.make_state_dict()
 
 
-@pytest.mark.parametrize("S", [64, 256])
+@pytest.mark.parametrize("S", [64, 256, (64, 96)])
 def test_torch_port_matches_reference_goldens(S, state_dict):
+    """(64, 96): a rectangular landscape frame -- pins the oracle there; the GPU engine has no test at that shape yet."""
     from oracle import torch_port as TP
     from siu3r_b200 import synth
-    z = np.load(os.path.join(GOLD, f"model_S{S}.npz"))
+    z = np.load(os.path.join(GOLD, f"model_S{S}.npz" if isinstance(S, int) else f"model_S{S[0]}x{S[1]}.npz"))
     meta = json.loads(str(z["meta"]))
     img, K = synth.pair_inputs(1, 2, S)
     st = {}

@@ -574,3 +574,13 @@ def test_load_state_dict_semantics(state_dict):
     sd["backbone.enc_norm.weight"] = torch.zeros(7)
     with pytest.raises(RuntimeError, match="size mismatch"):
         m.load_state_dict(sd)
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/siu3r_b200.h is the C-ABI a foreign-language binding (cgo / JNI / ctypes) would consume: it must compile as C99 on its own
+    (no C++ or torch types in any signature)."""
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "siu3r_b200.h"\nint main(void) { return 0; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr

@@ -163,12 +163,13 @@ def run_reference(args, rank):
     if rank != 0:
         return
     threads = host_threads()
-    for _ in range(min(args.warmup, 1)):
+    warm = min(args.warmup, 3)              # ~7 s each at 512^2: bounded so that the arm ends within a few minutes
+    for _ in range(warm):
         cpu_port_forward(args.size, 1, threads)
     ts = [cpu_port_forward(args.size, 1, threads) for _ in range(args.steps)]
     total = sum(ts)
     v = args.steps / total
-    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1),
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": warm,
             "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": f"two-view {args.size}x{args.size} inference -> Gaussians + panoptic (SIU3RModel.forward), 1 pair per step",

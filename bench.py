@@ -229,7 +229,7 @@ def main():
 
     # A GPU kernel that never ends cannot be interrupted from Python: rather than sit until the caller's limit, report where the headline stopped.
     phase = {"metric": METRIC, "value": None, "unit": "pairs/s", "n_gpus": world, "phase": "warm-up / graph capture"}
-    guard = AuxWatchdog(phase, float(os.environ.get("SIU3R_BENCH_HANG_TIMEOUT", "600")), enabled=(rank == 0), key="error",
+    guard = AuxWatchdog(phase, float(os.environ.get("SIU3R_BENCH_HANG_TIMEOUT", "300")), enabled=(rank == 0), key="error",
                         note="headline section did not finish within {s:.0f} s (see `phase`); no number was measured", exit_code=3)
 
     # ---- device-resident throughput (`value`) ----

@@ -352,7 +352,7 @@ def main():
             "vit_tensor_pipe_frac": value / world * (FLOPS_PER_PAIR_512 if V == 2 else FLOPS_PER_SAMPLE_512_V4 * V / 4) * (S / 512.0) ** 2 / 1e12 / tf32_peak,
             "roofline": roofline}
     guard.cancel()
-    watchdog = AuxWatchdog(line, float(os.environ.get("SIU3R_BENCH_AUX_TIMEOUT", "420")), enabled=(rank == 0))
+    watchdog = AuxWatchdog(line, float(os.environ.get("SIU3R_BENCH_AUX_TIMEOUT", "300")), enabled=(rank == 0))
 
     # ---- BASELINE configs[2]: the one collective of the path -- all-gather of the packed render records (88 fp32 per Gaussian) so that every
     #      rank holds the Gaussians of all pairs for joint-scene rasterisation (N > 1 only; not part of `value`) ----

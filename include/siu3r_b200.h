@@ -220,6 +220,44 @@ int siu3r_resize_lanczos_u8(const uint8_t* src, int H, int W, int64_t src_pitch,
                             int out_w, const int32_t* bounds_y, const int32_t* ky, int ksize_y, int out_h, int crop_x, int crop_y, int cw,
                             int ch, int row0, int rows, uint8_t* tmp, float* out, void* stream);
 
+/* ---- "h3" mode: fp32-grade results on the fp16 tensor-core path ----------------------------------------------------
+ * The mode that meets the north-star tolerances (Gaussians 1e-3 abs, segmentation logits 1e-4 rel) at about the cost of the
+ * TF32 mode.  A tensor that only feeds tensor-core operands is stored as an fp16 PLANE PAIR: hi = fp16(x) and
+ * lo = fp16((x - hi) * 2^11), the lo plane `plane` elements after the hi plane, both with the same row pitch (pointers 16-byte
+ * aligned, pitches / plane distances multiples of 8 elements).  Products are evaluated as hi.hi + (lo.hi + hi.lo) * 2^-11 with
+ * kind::f16 tcgen05 MMAs and fp32 accumulation (22 significand bits per operand, like a 3xTF32 split).  The attention kernel takes
+ * plane pairs with an UNSCALED lo plane (lo = fp16(x - hi)); the projection GEMM writes them when asked to (unscaled_lo).
+ * These entry points replace the same reference ops as their TF32 counterparts above (nn.Linear / Conv2d / Attention /
+ * CrossAttention / LayerNorm / F.interpolate in croco/blocks.py, heads/dpt_block.py, vit_adapter/, mask2former/). */
+int siu3r_split_h3(const float* x, int64_t ldx, int64_t rows, int cols, void* out, int64_t ldo, int64_t plane, int unscaled_lo, void* stream);
+int siu3r_merge_h3(const void* in, int64_t ldi, int64_t plane, int64_t rows, int cols, float* y, int64_t ldy, void* stream);
+/* one (ngroups = 1) or two same-shape linear layers in one persistent launch; *_host = host arrays of ngroups device pointers */
+int siu3r_gemm_h3(int ngroups, const int* M_host, int N, int K, const void* const* X_host, int64_t lda, int64_t a_plane, const void* const* W_host,
+                  int64_t ldw, int64_t w_plane, float* const* C_host, int64_t ldc, void* const* Ch_host, int64_t ldh, int64_t h_plane,
+                  const float* const* bias_host, const float* const* residual_host, int64_t ldr, int act, float alpha, const int64_t* positions,
+                  const float* rope_tab, int rope_cols, void* const* vt_host, const int* vt_cols_host, int64_t vt_ld, int64_t vt_plane, int vt_col0,
+                  int unscaled_lo, void* stream);
+int siu3r_conv2d_h3(int Nimg, int H, int W, int Cin, int Cout, int KH, int KW, int pad_h, int pad_w, const void* x, int64_t ldx, int64_t x_plane,
+                    const void* Wt, int64_t ldw, int64_t w_plane, float* y, int64_t ldc, void* yh, int64_t ldh, int64_t h_plane, const float* bias,
+                    const float* residual, int64_t ldr, int act, void* stream);
+int siu3r_flash_attn_h3(const void* Q, int64_t q_bs, int64_t q_ts, int64_t q_plane, int q_width, int q_col0, const void* K, int64_t k_bs,
+                        int64_t k_ts, int64_t k_plane, int k_width, int k_col0, const void* Vt, int64_t vt_ld, int64_t vt_plane,
+                        int64_t vt_batch_cols, int vt_b_split, int64_t vt_extra, float* O, int64_t o_bs, int64_t o_ts, void* Oh, int64_t oh_bs,
+                        int64_t oh_ts, int64_t oh_plane, int B, int H, int Nq, int Nk, float scale, void* stream);
+int siu3r_transpose_v_h3(const float* V, int64_t v_bs, int64_t v_ts, int B, int N, int H, void* Vt, int64_t ld, int64_t plane, void* stream);
+int siu3r_layernorm_h3(const float* x0, const float* x1, int64_t ldx, const float* w0, const float* b0, const float* w1, const float* b1, float* y0,
+                       float* y1, int64_t ldy, void* yh0, void* yh1, int64_t ldh, int64_t plane, int rows0, int rows1, int C, float eps,
+                       void* stream);
+int siu3r_eltwise_h3(int op, const float* a, const float* b, void* outh, int64_t plane, int64_t n, void* stream);
+int siu3r_resize_bilinear_nhwc_h3(const float* x, int N, int H, int W, int C, int64_t ldx, void* yh, int OH, int OW, int64_t ldh, int64_t plane,
+                                  int align_corners, void* stream);
+int siu3r_im2col_nhwc_h3(const float* x, int N, int H, int W, int C, int KH, int KW, int stride, int pad, int pad_w, void* outh, int64_t ldo,
+                         int64_t plane, void* stream);
+/* tuning / debugging aids */
+void siu3r_gemm_h3_force(int tw);
+int siu3r_gemm_h3_plan(int M, int N, int K, int M1, int* tw_out, int* tiles_out, int* rounds_out);
+void siu3r_flash_h3_debug_swap(int swap);
+
 #ifdef __cplusplus
 }
 #endif

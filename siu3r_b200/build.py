@@ -9,7 +9,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB = os.path.join(CSRC, "libsiu3r_b200.so")
-SOURCES = ["api.cu", "raster.cu", "gemm_tc.cu", "flash_tc.cu", "ops_basic.cu", "ops_attn.cu", "ops_head.cu", "labels2d.cu", "resize.cu"]
+SOURCES = ["api.cu", "raster.cu", "gemm_tc.cu", "flash_tc.cu", "ops_basic.cu", "ops_attn.cu", "ops_head.cu", "labels2d.cu", "resize.cu", "gemm_h3.cu", "flash_h3.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-diag-suppress", "177",

@@ -1,0 +1,233 @@
+// Shared device helpers of the "h3" precision mode: fp32-grade GEMM / attention on the fp16 tensor-core path.
+//
+// A tensor x that only feeds tensor-core operands is stored as TWO fp16 planes
+//     hi = fp16(x)                     (round to nearest, saturated to +-65504)
+//     lo = fp16((x - hi) * 2^11)       (the rounding residue of hi, exact in fp32, scaled back into the fp16 normal range)
+// so that x = hi + lo * 2^-11 to ~2^-22 relative -- the same 22 significand bits a 3xTF32 split keeps -- while the tensor cores
+// run kind::f16 MMAs (K = 16 per instruction, twice the TF32 rate) on operands that cost 4 bytes per element, exactly what the
+// plain fp32 / TF32 storage costs.  A product a.b is evaluated as
+//     a_hi.b_hi                         -> accumulator "hh"
+//     a_lo.b_hi + a_hi.b_lo             -> accumulator "x"   (both carry the 2^11 factor)
+//     result = hh + x * 2^-11           (epilogue; the dropped a_lo.b_lo term is 2^-22 relative)
+// Two accumulators because the tensor core truncates its fp32 accumulator on every MMA (tools/acc_probe.py): the error of a
+// chain grows with its length, and the 2K/16 cross-term MMAs would triple the chain of the hh sum for no benefit.
+//
+// Plane addressing convention used by every h3 entry point: `base` points at the hi plane, the lo plane starts `plane`
+// ELEMENTS later, both share the row pitch.  base is 16-byte aligned, pitch and plane are multiples of 8 elements (TMA).
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+#define H3_LO_SCALE 2048.0f
+#define H3_LO_INV 4.8828125e-4f   // 2^-11
+
+__device__ __forceinline__ void h3_split(float x, __half& hi, __half& lo) {
+    const float xc = fminf(fmaxf(x, -65504.0f), 65504.0f);
+    hi = __float2half_rn(xc);
+    lo = __float2half_rn((xc - __half2float(hi)) * H3_LO_SCALE);
+}
+__device__ __forceinline__ void h3_split_s(float x, float lo_scale, __half& hi, __half& lo) {
+    const float xc = fminf(fmaxf(x, -65504.0f), 65504.0f);
+    hi = __float2half_rn(xc);
+    lo = __float2half_rn((xc - __half2float(hi)) * lo_scale);
+}
+// two consecutive elements -> packed (low half = first element)
+__device__ __forceinline__ void h3_split2(float x0, float x1, uint32_t& hi2, uint32_t& lo2) {
+    __half h0, l0, h1, l1;
+    h3_split(x0, h0, l0);
+    h3_split(x1, h1, l1);
+    hi2 = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+    lo2 = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+}
+
+__device__ __forceinline__ void h3_split2_s(float x0, float x1, float lo_scale, uint32_t& hi2, uint32_t& lo2) {
+    __half h0, l0, h1, l1;
+    h3_split_s(x0, lo_scale, h0, l0);
+    h3_split_s(x1, lo_scale, h1, l1);
+    hi2 = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+    lo2 = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+}
+
+namespace h3 {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) { asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_to_cta(uint32_t local_saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_saddr), "r"(rank));
+    return r;
+}
+
+// ---- TMA (1-CTA forms: the mbarrier is a local shared address) ----
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+                 "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
+                 "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+// ---- TMA (CTA-pair forms: complete_tx lands on the LEADER's barrier, given as a shared::cluster address) ----
+__device__ __forceinline__ void tma2_load_3d(const CUtensorMap* map, uint32_t bar_cluster_addr, void* dst, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
+        "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma2_load_5d(const CUtensorMap* map, uint32_t bar_cluster_addr, void* dst, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+
+// ---- tcgen05.mma kind::f16 (fp16 x fp16 -> fp32), K = 16 per instruction ----
+// cute::UMMA::InstrDescriptor: D fp32 (bit 4), A / B formats F16 (0 at bits 7 / 10), both K-major, N>>3 at bit 17, M>>4 at bit 24
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) { return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24); }
+// K-major, SWIZZLE_128B operand tile: start >> 4 | LBO(1) << 16 | SBO(1024 B >> 4) << 32 | version(1) << 46 | SWIZZLE_128B(2) << 61
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// A operand from tensor memory (two fp16 per 32-bit column: K = 16 -> 8 columns)
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma2_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma2_commit_mc(uint64_t* bar) {  // arrive on `bar` (same smem offset) in BOTH CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+        "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]),
+        "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+// ---- host: tensor maps over fp16 planes (driver entry point resolved at run time: no link-time libcuda dependency) ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)ptr;
+        tried = true;
+    }
+    return fn;
+}
+// dims / box: innermost first; strides_bytes[i] = pitch of dimension i + 1.  fp16 elements, 128-byte swizzle, OOB elements read as 0.
+inline int make_map_f16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) { fprintf(stderr, "[siu3r_b200] cuTensorMapEncodeTiled unavailable\n"); return SIU3R_ERR_CUDA; }
+    cuuint64_t d[5]; cuuint64_t s[5]; cuuint32_t b[5]; cuuint32_t e[5];
+    for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; e[i] = 1; }
+    for (int i = 0; i + 1 < rank; ++i) s[i] = strides_bytes[i];
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), d, s, b, e, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        fprintf(stderr, "[siu3r_b200] cuTensorMapEncodeTiled(f16) failed: %d (rank %d dims %llu %llu %llu box %u %u %u strides %llu %llu)\n", (int)r, rank,
+                (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)(rank > 2 ? dims[2] : 0), box[0], box[1],
+                rank > 2 ? box[2] : 0, (unsigned long long)strides_bytes[0], (unsigned long long)(rank > 2 ? strides_bytes[1] : 0));
+        return SIU3R_ERR_INVALID;
+    }
+    return SIU3R_OK;
+}
+
+}  // namespace h3

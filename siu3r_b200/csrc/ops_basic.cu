@@ -1,8 +1,19 @@
 // HBM-bound supporting kernels of the per-pair hot path (fp32, token-major / NHWC layouts).
 // Each entry point cites the reference op it replaces (paths relative to /root/reference).
 #include "common.cuh"
+#include "h3.cuh"
 
 namespace {
+
+// optional fp16 plane-pair destination (h3 mode, see h3.cuh) next to / instead of the fp32 one: p == nullptr -> unused
+struct H3Out { __half* p; int64_t ld; int64_t plane; };
+__device__ __forceinline__ void h3_store4(const H3Out& o, int64_t off, float4 v) {
+    uint2 hi, lo;
+    h3_split2(v.x, v.y, hi.x, lo.x);
+    h3_split2(v.z, v.w, hi.y, lo.y);
+    *reinterpret_cast<uint2*>(o.p + off) = hi;
+    *reinterpret_cast<uint2*>(o.p + o.plane + off) = lo;
+}
 
 __device__ __forceinline__ float rn_tf32(float x) {
     uint32_t r;
@@ -16,16 +27,16 @@ __device__ __forceinline__ float rn_tf32(float x) {
 // vit_adapter/vit_adapter.py:74-93, mask2former/video_seg_decoder.py:945-952,1738-1744 (eps 1e-5).
 // ------------------------------------------------------------------------------------------------------------
 // Second segment of a grouped launch (siu3r_layernorm_group2): rows >= rows0 read x1 / w1 / b1 and write y1 (row index rebased).
-struct LnSeg2 { const float* x1; const float* w1; const float* b1; float* y1; int rows0; };
+struct LnSeg2 { const float* x1; const float* w1; const float* b1; float* y1; int rows0; __half* yh1; };
 
 template <int VEC_PER_LANE>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ w,
                                                         const float* __restrict__ b, float* __restrict__ y, int64_t ldy, int rows, int C,
-                                                        float eps, const float* __restrict__ add, int64_t ldadd, int round_out, LnSeg2 g) {
+                                                        float eps, const float* __restrict__ add, int64_t ldadd, int round_out, LnSeg2 g, H3Out yh) {
     int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
-    if (g.x1 && row >= g.rows0) { row -= g.rows0; x = g.x1; w = g.w1; b = g.b1; y = g.y1; }
+    if (g.x1 && row >= g.rows0) { row -= g.rows0; x = g.x1; w = g.w1; b = g.b1; y = g.y1; yh.p = g.yh1; }
     const float4* xr = reinterpret_cast<const float4*>(x + (int64_t)row * ldx);
     const int nvec = C >> 2;
     float4 v[VEC_PER_LANE];
@@ -67,7 +78,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
             o.w = (v[i].w - mean) * rstd * ww.w + bb.w;
             if (a4) { const float4 aa = a4[idx]; o.x += aa.x; o.y += aa.y; o.z += aa.z; o.w += aa.w; }
             if (round_out) { o.x = rn_tf32(o.x); o.y = rn_tf32(o.y); o.z = rn_tf32(o.z); o.w = rn_tf32(o.w); }
-            yr[idx] = o;
+            if (y) yr[idx] = o;
+            if (yh.p) h3_store4(yh, (int64_t)row * yh.ld + idx * 4, o);
         }
     }
 }
@@ -158,7 +170,8 @@ __device__ __forceinline__ float elt_apply(int op, float a, float b) {
     }
 }
 
-__global__ void __launch_bounds__(256) eltwise_kernel(int op, const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int64_t n) {
+__global__ void __launch_bounds__(256) eltwise_kernel(int op, const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int64_t n,
+                                                      H3Out oh) {
     const int64_t i4 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (i4 >= n) return;
     if (i4 + 4 <= n) {
@@ -168,9 +181,14 @@ __global__ void __launch_bounds__(256) eltwise_kernel(int op, const float* __res
         float4 o;
         o.x = elt_apply(op, va.x, vb.x); o.y = elt_apply(op, va.y, vb.y);
         o.z = elt_apply(op, va.z, vb.z); o.w = elt_apply(op, va.w, vb.w);
-        *reinterpret_cast<float4*>(out + i4) = o;
+        if (out) *reinterpret_cast<float4*>(out + i4) = o;
+        if (oh.p) h3_store4(oh, i4, o);
     } else {
-        for (int64_t i = i4; i < n; ++i) out[i] = elt_apply(op, a[i], b ? b[i] : 0.f);
+        for (int64_t i = i4; i < n; ++i) {
+            const float v = elt_apply(op, a[i], b ? b[i] : 0.f);
+            if (out) out[i] = v;
+            if (oh.p) h3_split(v, oh.p[i], oh.p[oh.plane + i]);
+        }
     }
 }
 
@@ -216,7 +234,7 @@ __device__ __forceinline__ void src_index(int o, int in_size, int out_size, bool
 
 __global__ void __launch_bounds__(256) resize_bilinear_kernel(const float* __restrict__ x, int N, int H, int W, int C, int64_t ldx,
                                                               float* __restrict__ y, int OH, int OW, int64_t ldy, int align, float sh,
-                                                              float sw, int accumulate) {
+                                                              float sw, int accumulate, H3Out yh) {
     const int c4 = C >> 2;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t total = (int64_t)N * OH * OW * c4;
@@ -240,6 +258,7 @@ __global__ void __launch_bounds__(256) resize_bilinear_kernel(const float* __res
     o.y = h0l * (w0l * v00.y + lw * v01.y) + lh * (w0l * v10.y + lw * v11.y);
     o.z = h0l * (w0l * v00.z + lw * v01.z) + lh * (w0l * v10.z + lw * v11.z);
     o.w = h0l * (w0l * v00.w + lw * v01.w) + lh * (w0l * v10.w + lw * v11.w);
+    if (yh.p) { h3_store4(yh, (((int64_t)n * OH + oh) * OW + ow) * yh.ld + c, o); return; }
     float4* yp = reinterpret_cast<float4*>(y + (((int64_t)n * OH + oh) * OW + ow) * ldy + c);
     if (accumulate & 1) { const float4 p = *yp; o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
     if (accumulate & 2) { o.x = rn_tf32(o.x); o.y = rn_tf32(o.y); o.z = rn_tf32(o.z); o.w = rn_tf32(o.w); }
@@ -269,7 +288,7 @@ __global__ void __launch_bounds__(256) pixel_shuffle_kernel(const float* __restr
 
 // im2col for NHWC input: out[(n,oh,ow), (kh,kw,ci)] (row stride ldo >= KH*KW*C, pad columns zeroed by caller's memset)
 __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ x, int N, int H, int W, int C, int KH, int KW, int stride, int pad,
-                                                     int pad_w, int OH, int OW, float* __restrict__ out, int64_t ldo, int round_out) {
+                                                     int pad_w, int OH, int OW, float* __restrict__ out, int64_t ldo, int round_out, H3Out oh) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int K = KH * KW * C;
     const int64_t total = (int64_t)N * OH * OW * ldo;
@@ -288,6 +307,7 @@ __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ x
         const int ih = oh * stride + kh - pad, iw = ow * stride + kw - pad_w;
         if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = x[(((int64_t)n * H + ih) * W + iw) * C + ci];
     }
+    if (oh.p) { h3_split(v, oh.p[idx], oh.p[oh.plane + idx]); return; }
     out[idx] = round_out ? rn_tf32(v) : v;
 }
 
@@ -430,25 +450,26 @@ inline unsigned grid_for(int64_t n, int threads = 256) { return (unsigned)((n + 
 extern "C" {
 
 static int layernorm_impl(const float* x, int64_t ldx, const float* w, const float* b, float* y, int64_t ldy, int rows, int C,
-                          float eps, const float* add, int64_t ldadd, int round_out, LnSeg2 g, void* stream_) {
+                          float eps, const float* add, int64_t ldadd, int round_out, LnSeg2 g, void* stream_, H3Out yh = H3Out{nullptr, 0, 0}) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    SIU3R_REQUIRE(x && w && b && y && rows > 0 && C > 0 && C % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0);
+    SIU3R_REQUIRE(x && w && b && (y || yh.p) && rows > 0 && C > 0 && C % 4 == 0 && ldx % 4 == 0 && (!y || ldy % 4 == 0));
+    if (yh.p) SIU3R_REQUIRE(((uintptr_t)yh.p & 7) == 0 && yh.ld % 4 == 0 && yh.plane % 4 == 0);
     SIU3R_REQUIRE(C <= 4096);
     const int nvec = C / 4;
     const int vpl = ceil_div(nvec, 32);
     const int wpb = 8;
     dim3 grid(ceil_div(rows, wpb));
-    if (vpl <= 2) layernorm_kernel<2><<<grid, wpb * 32, 0, stream>>>(x, ldx, w, b, y, ldy, rows, C, eps, add, ldadd, round_out, g);
-    else if (vpl <= 6) layernorm_kernel<6><<<grid, wpb * 32, 0, stream>>>(x, ldx, w, b, y, ldy, rows, C, eps, add, ldadd, round_out, g);
-    else if (vpl <= 8) layernorm_kernel<8><<<grid, wpb * 32, 0, stream>>>(x, ldx, w, b, y, ldy, rows, C, eps, add, ldadd, round_out, g);
-    else layernorm_kernel<32><<<grid, wpb * 32, 0, stream>>>(x, ldx, w, b, y, ldy, rows, C, eps, add, ldadd, round_out, g);
+    if (vpl <= 2) layernorm_kernel<2><<<grid, wpb * 32, 0, stream>>>(x, ldx, w, b, y, ldy, rows, C, eps, add, ldadd, round_out, g, yh);
+    else if (vpl <= 6) layernorm_kernel<6><<<grid, wpb * 32, 0, stream>>>(x, ldx, w, b, y, ldy, rows, C, eps, add, ldadd, round_out, g, yh);
+    else if (vpl <= 8) layernorm_kernel<8><<<grid, wpb * 32, 0, stream>>>(x, ldx, w, b, y, ldy, rows, C, eps, add, ldadd, round_out, g, yh);
+    else layernorm_kernel<32><<<grid, wpb * 32, 0, stream>>>(x, ldx, w, b, y, ldy, rows, C, eps, add, ldadd, round_out, g, yh);
     SIU3R_LAUNCH_CHECK();
     siu3r_note_launch(1);
     return SIU3R_OK;
 }
 int siu3r_layernorm(const float* x, int64_t ldx, const float* w, const float* b, float* y, int64_t ldy, int rows, int C, float eps,
                     const float* add, int64_t ldadd, int round_out, void* stream) {
-    return layernorm_impl(x, ldx, w, b, y, ldy, rows, C, eps, add, ldadd, round_out, LnSeg2{nullptr, nullptr, nullptr, nullptr, 0}, stream);
+    return layernorm_impl(x, ldx, w, b, y, ldy, rows, C, eps, add, ldadd, round_out, LnSeg2{nullptr, nullptr, nullptr, nullptr, 0, nullptr}, stream);
 }
 
 // Two LayerNorms with different affine parameters (and possibly different source / destination buffers) in one launch: the norm1 / norm2 /
@@ -457,7 +478,17 @@ int siu3r_layernorm_group2(const float* x0, const float* x1, int64_t ldx, const 
                            float* y0, float* y1, int64_t ldy, int rows0, int rows1, int C, float eps, int round_out, void* stream) {
     SIU3R_REQUIRE(x1 && w1 && b1 && y1 && rows0 > 0 && rows1 > 0);
     SIU3R_REQUIRE(((uintptr_t)x1 & 15) == 0 && ((uintptr_t)y1 & 15) == 0 && ((uintptr_t)w1 & 15) == 0 && ((uintptr_t)b1 & 15) == 0);
-    return layernorm_impl(x0, ldx, w0, b0, y0, ldy, rows0 + rows1, C, eps, nullptr, 0, round_out, LnSeg2{x1, w1, b1, y1, rows0}, stream);
+    return layernorm_impl(x0, ldx, w0, b0, y0, ldy, rows0 + rows1, C, eps, nullptr, 0, round_out, LnSeg2{x1, w1, b1, y1, rows0, nullptr}, stream);
+}
+
+// LayerNorm whose result goes to an fp16 plane pair yh (h3 mode: the row only feeds tensor-core operands) and / or to fp32 y (either may be
+// null, not both).  x1 != null: second segment of a grouped launch as in siu3r_layernorm_group2 (rows >= rows0 use x1 / w1 / b1 / y1 / yh1).
+int siu3r_layernorm_h3(const float* x0, const float* x1, int64_t ldx, const float* w0, const float* b0, const float* w1, const float* b1, float* y0,
+                       float* y1, int64_t ldy, void* yh0, void* yh1, int64_t ldh, int64_t plane, int rows0, int rows1, int C, float eps,
+                       void* stream) {
+    SIU3R_REQUIRE(rows0 > 0 && rows1 >= 0 && (rows1 == 0 || (x1 && w1 && b1 && (y1 || yh1))));
+    return layernorm_impl(x0, ldx, w0, b0, y0, ldy, rows0 + rows1, C, eps, nullptr, 0, 0,
+                          LnSeg2{rows1 > 0 ? x1 : nullptr, w1, b1, y1, rows0, (__half*)yh1}, stream, H3Out{(__half*)yh0, ldh, plane});
 }
 
 
@@ -498,7 +529,18 @@ int siu3r_eltwise(int op, const float* a, const float* b, float* out, int64_t n,
     cudaStream_t stream = (cudaStream_t)stream_;
     SIU3R_REQUIRE(a && out && n > 0 && op >= 0 && op <= 9);
     SIU3R_REQUIRE(((uintptr_t)a & 15) == 0 && ((uintptr_t)out & 15) == 0 && (!b || ((uintptr_t)b & 15) == 0));
-    eltwise_kernel<<<grid_for(ceil_div_i64(n, 4)), 256, 0, stream>>>(op, a, b, out, n);
+    eltwise_kernel<<<grid_for(ceil_div_i64(n, 4)), 256, 0, stream>>>(op, a, b, out, n, H3Out{nullptr, 0, 0});
+    SIU3R_LAUNCH_CHECK();
+    siu3r_note_launch(1);
+    return SIU3R_OK;
+}
+
+// siu3r_eltwise whose result is stored as an fp16 plane pair (contiguous, lo plane `plane` elements after the hi plane); ops 0..6
+int siu3r_eltwise_h3(int op, const float* a, const float* b, void* outh, int64_t plane, int64_t n, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    SIU3R_REQUIRE(a && outh && n > 0 && op >= 0 && op <= 6 && plane >= n && plane % 4 == 0);
+    SIU3R_REQUIRE(((uintptr_t)a & 15) == 0 && ((uintptr_t)outh & 7) == 0 && (!b || ((uintptr_t)b & 15) == 0));
+    eltwise_kernel<<<grid_for(ceil_div_i64(n, 4)), 256, 0, stream>>>(op, a, b, nullptr, n, H3Out{(__half*)outh, 0, plane});
     SIU3R_LAUNCH_CHECK();
     siu3r_note_launch(1);
     return SIU3R_OK;
@@ -526,10 +568,10 @@ int siu3r_rows_affine(const float* x, int64_t ldx, const float* scale, const flo
     return SIU3R_OK;
 }
 
-int siu3r_resize_bilinear_nhwc(const float* x, int N, int H, int W, int C, int64_t ldx, float* y, int OH, int OW, int64_t ldy,
-                               int align_corners, int accumulate, void* stream_) {
+static int resize_impl(const float* x, int N, int H, int W, int C, int64_t ldx, float* y, int OH, int OW, int64_t ldy, int align_corners,
+                       int accumulate, void* stream_, H3Out yh) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    SIU3R_REQUIRE(x && y && N > 0 && H > 0 && W > 0 && OH > 0 && OW > 0 && C % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0);
+    SIU3R_REQUIRE(x && (y || yh.p) && N > 0 && H > 0 && W > 0 && OH > 0 && OW > 0 && C % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0);
     float sh, sw;
     if (align_corners) {
         sh = OH > 1 ? (float)(H - 1) / (float)(OH - 1) : 0.f;
@@ -541,10 +583,21 @@ int siu3r_resize_bilinear_nhwc(const float* x, int N, int H, int W, int C, int64
         sw = (float)W / (float)OW;
     }
     resize_bilinear_kernel<<<grid_for((int64_t)N * OH * OW * (C / 4)), 256, 0, stream>>>(x, N, H, W, C, ldx, y, OH, OW, ldy, align_corners, sh,
-                                                                                         sw, accumulate);
+                                                                                         sw, accumulate, yh);
     SIU3R_LAUNCH_CHECK();
     siu3r_note_launch(1);
     return SIU3R_OK;
+}
+int siu3r_resize_bilinear_nhwc(const float* x, int N, int H, int W, int C, int64_t ldx, float* y, int OH, int OW, int64_t ldy,
+                               int align_corners, int accumulate, void* stream) {
+    SIU3R_REQUIRE(y != nullptr);
+    return resize_impl(x, N, H, W, C, ldx, y, OH, OW, ldy, align_corners, accumulate, stream, H3Out{nullptr, 0, 0});
+}
+// ... with the result stored as an fp16 plane pair [N, OH, OW, ldh] (h3 mode: the resized map only feeds a convolution)
+int siu3r_resize_bilinear_nhwc_h3(const float* x, int N, int H, int W, int C, int64_t ldx, void* yh, int OH, int OW, int64_t ldh, int64_t plane,
+                                  int align_corners, void* stream) {
+    SIU3R_REQUIRE(yh && ((uintptr_t)yh & 7) == 0 && ldh % 4 == 0 && plane % 4 == 0);
+    return resize_impl(x, N, H, W, C, ldx, nullptr, OH, OW, 4, align_corners, 0, stream, H3Out{(__half*)yh, ldh, plane});
 }
 
 int siu3r_pixel_shuffle_nhwc(const float* g, int N, int H, int W, int C, int s, const float* add, float* y, void* stream_) {
@@ -556,14 +609,25 @@ int siu3r_pixel_shuffle_nhwc(const float* g, int N, int H, int W, int C, int s, 
     return SIU3R_OK;
 }
 
-int siu3r_im2col_nhwc(const float* x, int N, int H, int W, int C, int KH, int KW, int stride, int pad, int pad_w, float* out, int64_t ldo, int round_out, void* stream_) {
+static int im2col_impl(const float* x, int N, int H, int W, int C, int KH, int KW, int stride, int pad, int pad_w, float* out, int64_t ldo, int round_out,
+                       void* stream_, H3Out oh) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    SIU3R_REQUIRE(x && out && N > 0 && stride >= 1 && ldo >= (int64_t)KH * KW * C);
+    SIU3R_REQUIRE(x && (out || oh.p) && N > 0 && stride >= 1 && ldo >= (int64_t)KH * KW * C);
     const int OH = (H + 2 * pad - KH) / stride + 1, OW = (W + 2 * pad_w - KW) / stride + 1;
-    im2col_kernel<<<grid_for((int64_t)N * OH * OW * ldo), 256, 0, stream>>>(x, N, H, W, C, KH, KW, stride, pad, pad_w, OH, OW, out, ldo, round_out);
+    im2col_kernel<<<grid_for((int64_t)N * OH * OW * ldo), 256, 0, stream>>>(x, N, H, W, C, KH, KW, stride, pad, pad_w, OH, OW, out, ldo, round_out, oh);
     SIU3R_LAUNCH_CHECK();
     siu3r_note_launch(1);
     return SIU3R_OK;
+}
+int siu3r_im2col_nhwc(const float* x, int N, int H, int W, int C, int KH, int KW, int stride, int pad, int pad_w, float* out, int64_t ldo, int round_out, void* stream) {
+    SIU3R_REQUIRE(out != nullptr);
+    return im2col_impl(x, N, H, W, C, KH, KW, stride, pad, pad_w, out, ldo, round_out, stream, H3Out{nullptr, 0, 0});
+}
+// ... with the column matrix stored as an fp16 plane pair [rows, ldo] (pad columns K..ldo-1 are zero)
+int siu3r_im2col_nhwc_h3(const float* x, int N, int H, int W, int C, int KH, int KW, int stride, int pad, int pad_w, void* outh, int64_t ldo, int64_t plane,
+                         void* stream) {
+    SIU3R_REQUIRE(outh != nullptr && plane > 0);
+    return im2col_impl(x, N, H, W, C, KH, KW, stride, pad, pad_w, nullptr, ldo, 0, stream, H3Out{(__half*)outh, ldo, plane});
 }
 
 int siu3r_nchw_to_nhwc(const float* x, float* y, int N, int C, int HW, int64_t ldy, void* stream_) {

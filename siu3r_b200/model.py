@@ -67,8 +67,8 @@ class SIU3RModel:
         if cfg is not None and hasattr(cfg, "croco") and hasattr(cfg, "mask2former"):
             cfg = ModelCfg.from_reference(cfg)        # the reference's own nested config object
         self.cfg = cfg or ModelCfg()
-        assert precision in ("tf32", "fp32x3")
-        self.prec = ops.PREC_TF32 if precision == "tf32" else ops.PREC_FP32X3
+        assert precision in ("tf32", "fp32x3", "h3")
+        self.prec = {"tf32": ops.PREC_TF32, "fp32x3": ops.PREC_FP32X3, "h3": ops.PREC_H3}[precision]
         self.precision = precision
         self._sd = None
         self._ready = False
@@ -291,26 +291,59 @@ class SIU3RModel:
 
     def _cap(self, name, t):
         if self.capture is not None:
+            if isinstance(t, ops.Split):   # plane pair -> fp32 copy in the logical shape
+                t = t.view(-1, t.shape[-1]).float().view(*t.shape)
             self.capture[name] = t
 
     # ---- building blocks ------------------------------------------------------------------------------------------
     # TF32 mode: tensors that ONLY feed GEMM / conv A operands are stored round-to-nearest by their producer (R = True);
     # `ar=` tells the consumer its A operand is already rounded, `ro=` asks a GEMM / conv to round its own output.
+    # h3 mode (S = True): the same tensors are stored as fp16 (hi, lo) plane pairs (ops.Split) by their producer; consumers that are handed a
+    # plain fp32 tensor split it themselves (one extra pass).  `ro=` therefore means "this result only feeds tensor-core operands".
     @property
     def R(self):
         return self.prec == ops.PREC_TF32
 
+    @property
+    def S(self):
+        return self.prec == ops.PREC_H3
+
     def _lin(self, x, wt, ar=False, ro=False, **kw):
-        return ops.gemm(x, wt, precision=self.prec, a_rounded=ar and self.R, round_out=ro and self.R, **kw)
+        return ops.gemm(x, wt, precision=self.prec, a_rounded=ar and self.R, round_out=ro and (self.R or self.S), **kw)
 
     def _conv(self, x, wt, k, ar=False, ro=False, **kw):
-        return ops.conv2d(x, wt, k, k, precision=self.prec, a_rounded=ar and self.R, round_out=ro and self.R, **kw)
+        return ops.conv2d(x, wt, k, k, precision=self.prec, a_rounded=ar and self.R, round_out=ro and (self.R or self.S), **kw)
 
-    def _ln(self, x, wb, eps, ro=True, **kw):
-        return ops.layernorm(x, wb[0], wb[1], eps, round_out=ro and self.R, **kw)
+    def _ln(self, x, wb, eps, ro=True, out=None, **kw):
+        if self.S and ro:
+            return ops.layernorm_h3([x], [wb], eps, outs=None if out is None else [out])[0]
+        return ops.layernorm(x, wb[0], wb[1], eps, round_out=ro and self.R, out=out, **kw)
+
+    def _relu_op(self, x):
+        """ReLU whose result only feeds a convolution."""
+        if self.S:
+            return ops.eltwise_h3(ELT_RELU, x)
+        return ops.eltwise(ops.ELT_RELU_RN if self.R else ELT_RELU, x)
+
+    def _add_op(self, a, b):
+        """a + b whose result only feeds GEMM operands."""
+        if self.S:
+            return ops.eltwise_h3(ELT_ADD, a, b)
+        return ops.eltwise(ops.ELT_ADD_RN if self.R else ELT_ADD, a, b)
+
+    def _resize_op(self, x, OH, OW, align):
+        """Bilinear resize whose result only feeds a convolution."""
+        if self.S:
+            return ops.resize_bilinear_h3(x, OH, OW, align)
+        return ops.resize_bilinear(x, OH, OW, align, round_out=self.R)
 
     def _self_attn(self, h, blk, pos, Bn, N, C, nh):
         M = Bn * N
+        if self.S:   # h3: q | k as an unscaled plane pair (RoPE in the epilogue), V^T plane pair written by the same launch, plane-pair output
+            qkv = ops.Split.empty(M, 3 * C, device=self.dev, unscaled=True)
+            vth = ops.Split.empty(C, (M + 7) // 8 * 8, device=self.dev, unscaled=True)
+            self._lin(h, blk.qkv, ro=True, out=qkv, rope=(pos, self._k.rope_tab, 2 * C), vt=(vth, 2 * C, {}), unscaled=True)
+            return ops.flash_attn_h3(qkv, 0, qkv, C, vth, N, Bn, nh, N, N, 0.125, split_out=True)
         vt = st = None
         if self.R:   # the V third of the projection is written as V^T by the GEMM epilogue (no transpose pass)
             vt, st = torch.empty(C, (M + 3) // 4 * 4, device=self.dev), {}
@@ -352,7 +385,7 @@ class SIU3RModel:
 
     # ---- DPT heads (heads/dpt_head.py:36-79, dpt_gs_head.py:121-171, dpt_block.py) ------------------------------------
     def _rcu(self, x, unit):
-        r = ops.eltwise(ops.ELT_RELU_RN if self.R else ELT_RELU, x)
+        r = self._relu_op(x)
         t = self._conv(r, unit[0], 3, ar=True, ro=True, pad=1, act=ACT_RELU)
         return self._conv(t, unit[1], 3, ar=True, pad=1, residual=x)
 
@@ -363,19 +396,20 @@ class SIU3RModel:
             out = ops.eltwise(ELT_ADD, out, res)
         out = self._rcu(out, rf.r2)
         n, h, w_, c = out.shape
-        out = ops.resize_bilinear(out, 2 * h, 2 * w_, True, round_out=self.R)
+        out = self._resize_op(out, 2 * h, 2 * w_, True)
         return self._conv(out, rf.out_conv, 1, ar=True, ro=ro)
 
-    def _dpt_trunk(self, hw, toks, B, N, gh, gw):
+    def _dpt_trunk(self, hw, toks, B, N, gh, gw, p1_ro=True):
         """toks: 4 token tensors [B*N, C] (trailing intrinsics token per image is skipped) -> path_1 [B, 8gh, 8gw, 256]."""
         P = gh * gw
         layers = []
         for i in range(4):
             C_in = toks[i].shape[1]
             cw = hw.act_conv[i]
-            o = torch.empty(B, gh, gw, cw.N, device=self.dev)
+            # (h3: layer 3 goes through a strided conv, whose im2col reads fp32)
+            o = ops.Split.empty(B, gh, gw, cw.N, device=self.dev) if (self.S and i != 3) else torch.empty(B, gh, gw, cw.N, device=self.dev)
             for b in range(B):
-                self._lin(toks[i][b * N: b * N + P], cw, ro=True, out=o[b].view(P, cw.N))
+                self._lin(toks[i][b * N: b * N + P], cw, ro=not (self.S and i == 3), out=o[b].view(P, cw.N))
             del C_in
             layers.append(o)
         # act_postprocess tails
@@ -388,7 +422,7 @@ class SIU3RModel:
         p4 = self._fusion(hw.refine[3], layers[3])
         p3 = self._fusion(hw.refine[2], p4, layers[2])
         p2 = self._fusion(hw.refine[1], p3, layers[1])
-        p1 = self._fusion(hw.refine[0], p2, layers[0], ro=True)  # path_1 only feeds a conv (centre head) or a resize (GS head)
+        p1 = self._fusion(hw.refine[0], p2, layers[0], ro=p1_ro)  # path_1 only feeds a conv (centre head) or a resize (GS head)
         return p1
 
     def _center_head(self, hw, toks, B, N, gh, gw, dst):
@@ -396,7 +430,7 @@ class SIU3RModel:
         p1 = self._dpt_trunk(hw, toks, B, N, gh, gw)
         x = self._conv(p1, hw.head0, 3, ar=True, pad=1)
         n, h, w_, c = x.shape
-        x = ops.resize_bilinear(x, 2 * h, 2 * w_, True, round_out=self.R)
+        x = self._resize_op(x, 2 * h, 2 * w_, True)
         x = self._conv(x, hw.head2, 3, ar=True, ro=True, pad=1, act=ACT_RELU)
         S0, S1 = 2 * h, 2 * w_
         xyz = torch.empty(B * S0 * S1, 4, device=self.dev)
@@ -407,7 +441,7 @@ class SIU3RModel:
 
     def _gs_head(self, hw, toks, img4, B, N, gh, gw):
         """-> raw Gaussian parameters [B, S*S, 83] (model.py:195-210)."""
-        p1 = self._dpt_trunk(hw, toks, B, N, gh, gw)
+        p1 = self._dpt_trunk(hw, toks, B, N, gh, gw, p1_ro=not self.S)   # h3: the bilinear upsampling below reads fp32
         n, h, w_, c = p1.shape
         s = ops.conv_kxk_up2x(img4, hw.merger, 7, 7, p1, act=ACT_RELU, round_out=True) if self.R else None   # fused: no [S,S,256] upsampled map
         if s is None:
@@ -424,7 +458,7 @@ class SIU3RModel:
         C = 1024
         Lq = c.shape[0] // B
         qn = self._ln(c, ex.qn, 1e-6)
-        fn = torch.empty(B * P, C, device=self.dev)
+        fn = ops.Split.empty(B * P, C, device=self.dev) if self.S else torch.empty(B * P, C, device=self.dev)
         for b in range(B):
             self._ln(featn_src[b * N: b * N + P], ex.fn, 1e-6, out=fn[b * P:(b + 1) * P])
         value = self._lin(fn, ex.value, ar=True)
@@ -447,11 +481,12 @@ class SIU3RModel:
         a = self.w.adapter
         x = self._conv(img4, a.stem[0], 3, ro=True, stride=2, pad=1, act=ACT_RELU)
         x = self._conv(x, a.stem[1], 3, ar=True, ro=True, pad=1, act=ACT_RELU)
-        x = self._conv(x, a.stem[2], 3, ar=True, ro=True, pad=1, act=ACT_RELU)
+        f32 = not self.S    # h3: max-pool and the strided convs (im2col) read fp32, so their inputs stay fp32
+        x = self._conv(x, a.stem[2], 3, ar=True, ro=f32, pad=1, act=ACT_RELU)
         c1 = ops.maxpool3x3s2(x)                                           # [Bn, S/4, S/4, 64] (max of rounded values stays rounded)
-        c2 = self._conv(c1, a.conv2, 3, ro=True, stride=2, pad=1, act=ACT_RELU)     # S/8, 128
-        c3 = self._conv(c2, a.conv3, 3, ro=True, stride=2, pad=1, act=ACT_RELU)     # S/16, 256
-        c4 = self._conv(c3, a.conv4, 3, ro=True, stride=2, pad=1, act=ACT_RELU)     # S/32, 256
+        c2 = self._conv(c1, a.conv2, 3, ro=f32, stride=2, pad=1, act=ACT_RELU)     # S/8, 128
+        c3 = self._conv(c2, a.conv3, 3, ro=f32, stride=2, pad=1, act=ACT_RELU)     # S/16, 256
+        c4 = self._conv(c3, a.conv4, 3, ro=f32, stride=2, pad=1, act=ACT_RELU)     # S/32, 256
         c1 = self._conv(c1, a.fc1, 1, ar=True)                             # [Bn, S/4, S/4, 1024]
         return c1, c2, c3, c4
 
@@ -523,18 +558,19 @@ class SIU3RModel:
             for bt in range(BT):
                 ops.rows_affine(e[bt], out=x[bt, starts[i]:starts[i] + h * w_])
         x = x.view(BT * Ltot, E)
-        ADD_RN = ops.ELT_ADD_RN if self.R else ELT_ADD   # sums that only feed a TF32 GEMM are rounded where they are produced
+        # h3: LayerNorm outputs that are also residuals stay fp32 (their GEMM consumers split them)
+        lnro = not self.S
         for li_, lyr in enumerate(m.enc):
-            q = ops.eltwise(ADD_RN, x, k.m2f_pos)
+            q = self._add_op(x, k.m2f_pos)
             value = self._lin(x, lyr.value, ar=li_ > 0)   # x is a (rounded) LayerNorm output from the second layer on
             ow = self._lin(q, lyr.ow, ar=True)
             samp = torch.empty(BT * Ltot, E, device=self.dev)
             ops.msdeform_attn(value, Ltot, ow, k.m2f_ref, lv, 4, BT, Ltot, 8, 32, samp, round_out=self.R)
             y = self._lin(samp, lyr.out, ar=True, residual=x)
-            x = self._ln(y, lyr.ln1, 1e-5)
+            x = self._ln(y, lyr.ln1, 1e-5, ro=lnro)
             f1 = self._lin(x, lyr.fc1, ar=True, ro=True, act=ACT_RELU)
             y = self._lin(f1, lyr.fc2, ar=True, residual=x)
-            x = self._ln(y, lyr.ln2, 1e-5)
+            x = self._ln(y, lyr.ln2, 1e-5, ro=lnro)
         x = x.view(BT, Ltot, E)
         # FPN level (stride 4)
         h4, w4 = S0 // 4, S1 // 4
@@ -558,8 +594,8 @@ class SIU3RModel:
                 for t in range(T):
                     ops.rows_affine(x[b * T + t, starts[i]:starts[i] + n], shift=k.tm_lvl[i], out=s[b, t * n:(t + 1) * n])
             s = s.view(B * T * n, E)
-            srcpos.append(ops.eltwise(ADD_RN, s, k.tm_pos[i]))
-            src.append(ops.round_tf32(s) if self.R else s)   # keys / values of all 9 decoder layers: rounded once
+            srcpos.append(self._add_op(s, k.tm_pos[i]))
+            src.append(ops.split(s) if self.S else (ops.round_tf32(s) if self.R else s))   # keys / values of all 9 decoder layers: rounded / split once
         hidden, qpos = k.hidden0, k.qpos
         mf = mask_feat.view(B, T * h4 * w4, E)
 
@@ -583,27 +619,27 @@ class SIU3RModel:
             li = idx % 3
             n = lv[li][0] * lv[li][1] * T
             # masked cross-attention (post-norm)
-            qin = ops.eltwise(ADD_RN, hidden, qpos)
+            qin = self._add_op(hidden, qpos)
             qh = self._lin(qin, lyr.cq, ar=True)
             kh = self._lin(srcpos[li], lyr.ck, ar=True)
             vh = self._lin(src[li], lyr.cv, ar=True)
             att = torch.empty(B * Q, E, device=self.dev)
             ops.attn_small_d32(qh, Q * E, E, kh, n * E, E, vh, n * E, E, att, Q * E, E, amask, B, nh, Q, n, 32 ** -0.5, round_out=self.R)
             y = self._lin(att, lyr.cout, ar=True, residual=hidden)
-            hidden = self._ln(y, lyr.cln, 1e-5)
+            hidden = self._ln(y, lyr.cln, 1e-5, ro=lnro)
             # query self-attention
-            qin = ops.eltwise(ADD_RN, hidden, qpos)
+            qin = self._add_op(hidden, qpos)
             qk = self._lin(qin, lyr.sqk, ar=True)          # [B*Q, 512] = [q | k]
             vv = self._lin(hidden, lyr.sv, ar=True)
             att = torch.empty(B * Q, E, device=self.dev)
             ops.attn_small_d32(qk, Q * 2 * E, 2 * E, qk[:, E:], Q * 2 * E, 2 * E, vv, Q * E, E, att, Q * E, E, None, B, nh, Q, Q, 32 ** -0.5,
                                round_out=self.R)
             y = self._lin(att, lyr.sout, ar=True, residual=hidden)
-            hidden = self._ln(y, lyr.sln, 1e-5)
+            hidden = self._ln(y, lyr.sln, 1e-5, ro=lnro)
             # FFN
             f1 = self._lin(hidden, lyr.fc1, ar=True, ro=True, act=ACT_RELU)
             y = self._lin(f1, lyr.fc2, ar=True, residual=hidden)
-            hidden = self._ln(y, lyr.fln, 1e-5)
+            hidden = self._ln(y, lyr.fln, 1e-5, ro=lnro)
             last = idx == len(m.dec) - 1
             inter, logits, amask = predict(hidden, None if last else lv[(idx + 1) % 3])
         cls = self._lin(inter, m.cls, ar=True)  # [B*Q, 21]
@@ -701,6 +737,8 @@ class SIU3RModel:
         launch over all V*B images.  The cross-attention memory of an image of view i is the concatenation, in view order, of
         norm_y(tokens) of the same sample's other views (generate_ctx_views :500-506), keys rotated with their own positions;
         norm_y + the k|v projection are per token, so they run once per (stream weights, needed view).  Returns a new buffer."""
+        if self.S:
+            return self._dec_layer_h3(l, f, B, N, V)
         C, nh = 768, 12
         blks = (self.w.dec[0][l], self.w.dec[1][l])
         R0, R = B * N, V * B * N
@@ -785,6 +823,80 @@ class SIU3RModel:
         self._lin2(split(m), [bk.fc2 for bk in blks], outs=split(x1), ar=True, residuals=split(x1))
         return x1
 
+    def _dec_layer_h3(self, l, f, B, N, V):
+        """_dec_layer in h3 mode: every GEMM operand is an fp16 plane pair written by its producer (LayerNorm, projection epilogue, attention
+        epilogue); q / k / V^T of both attentions are unscaled plane pairs (flash_h3.cu)."""
+        C, nh = 768, 12
+        dev = self.dev
+        blks = (self.w.dec[0][l], self.w.dec[1][l])
+        R0, R = B * N, V * B * N
+        rows = ((0, R0), (R0, R))
+        pos, tab = self._k.pos_enc, self._k.rope_tab
+        sp = lambda t: [t[a:b] for a, b in rows]
+        W0 = (R0 + 7) // 8 * 8                 # V^T window of stream 0; stream 1 starts there (16-byte aligned)
+        W1 = (R - R0 + 7) // 8 * 8
+
+        def vt_buf():
+            buf = ops.Split.empty(C, W0 + W1, device=dev, unscaled=True)
+            return buf, [buf[:, :W0], buf[:, W0:]]
+        # ---- self-attention ----
+        h = ops.Split.empty(R, C, device=dev)
+        ops.layernorm_h3(sp(f), [bk.n1 for bk in blks], 1e-6, outs=sp(h))
+        qkv = ops.Split.empty(R, 3 * C, device=dev, unscaled=True)
+        vb, wins = vt_buf()
+        self._lin2(sp(h), [bk.qkv for bk in blks], outs=sp(qkv), ro=True, rope=(pos, tab, 2 * C), vt=(wins, [W0, W1], 2 * C, {}), unscaled=True)
+        att = ops.flash_attn_h3(qkv, 0, qkv, C, vb, N, V * B, nh, N, N, 0.125, split_out=True, vt_b_split=B, vt_extra=W0 - R0)
+        x1 = torch.empty(R, C, device=dev)
+        self._lin2(sp(att), [bk.proj for bk in blks], outs=sp(x1), residuals=sp(f))
+        # ---- cross-attention memory: k | v of the other views under the attending stream's weights ----
+        if V == 2:
+            yn = ops.Split.empty(R, C, device=dev)
+            ops.layernorm_h3([f[R0:], f[:R0]], [bk.ny for bk in blks], 1e-6, outs=sp(yn))
+            ctx = ops.Split.empty(R, 2 * C, device=dev, unscaled=True)
+            vb2, wins2 = vt_buf()
+            self._lin2(sp(yn), [bk.ckv for bk in blks], outs=sp(ctx), ro=True, rope=(pos, tab, C), vt=(wins2, [W0, W1], C, {}), unscaled=True)
+            Nk = N
+            kctx, vt2, vt_cols, vsplit, vextra = ctx, vb2, N, B, W0 - R0
+        else:
+            # V > 2: the memory of an image is the concatenation of V-1 views; it is assembled in fp32 (row copies), then split once
+            yn0 = ops.Split.empty(R - R0, C, device=dev)
+            yn1 = ops.Split.empty(R, C, device=dev)
+            ops.layernorm_h3([f[R0:]], [blks[0].ny], 1e-6, outs=[yn0])
+            ops.layernorm_h3([f], [blks[1].ny], 1e-6, outs=[yn1])
+            kv0 = torch.empty(R - R0, 2 * C, device=dev)
+            kv1 = torch.empty(R, 2 * C, device=dev)
+            pos_all = pos.view(-1, 2)
+            self._lin(yn0, blks[0].ckv, out=kv0, rope=(pos_all[:R - R0], tab, C))
+            self._lin(yn1, blks[1].ckv, out=kv1, rope=(pos_all, tab, C))
+            Nk = (V - 1) * N
+            ctxf = torch.empty(V * B, Nk, 2 * C, device=dev)
+            for i in range(V):
+                for b in range(B):
+                    slot = 0
+                    for j in range(V):
+                        if j == i:
+                            continue
+                        src = kv0[((j - 1) * B + b) * N:][:N] if i == 0 else kv1[(j * B + b) * N:][:N]
+                        ops.rows_affine(src, out=ctxf[i * B + b, slot * N:(slot + 1) * N])
+                        slot += 1
+            ctxf = ctxf.view(V * B * Nk, 2 * C)
+            kctx = ops.split(ctxf[:, :C], unscaled=True)
+            vt2 = ops.transpose_v_h3(ctxf, C, Nk * 2 * C, 2 * C, V * B, Nk, nh)
+            vt_cols, vsplit, vextra = 0, 0, 0
+        h2 = ops.Split.empty(R, C, device=dev)
+        ops.layernorm_h3(sp(x1), [bk.n2 for bk in blks], 1e-6, outs=sp(h2))
+        q = ops.Split.empty(R, C, device=dev, unscaled=True)
+        self._lin2(sp(h2), [bk.cq for bk in blks], outs=sp(q), ro=True, rope=(pos, tab, C), unscaled=True)
+        a2 = ops.flash_attn_h3(q, 0, kctx, 0, vt2, vt_cols, V * B, nh, N, Nk, 0.125, split_out=True, vt_b_split=vsplit, vt_extra=vextra)
+        self._lin2(sp(a2), [bk.cproj for bk in blks], outs=sp(x1), residuals=sp(x1))
+        # ---- MLP ----
+        h3_ = ops.Split.empty(R, C, device=dev)
+        ops.layernorm_h3(sp(x1), [bk.n3 for bk in blks], 1e-6, outs=sp(h3_))
+        m = ops.Split.empty(R, 4 * C, device=dev)
+        self._lin2(sp(h3_), [bk.fc1 for bk in blks], outs=sp(m), ro=True, act=ACT_GELU)
+        self._lin2(sp(m), [bk.fc2 for bk in blks], outs=sp(x1), residuals=sp(x1))
+        return x1
+
     def _forward_device(self, imgs, Kin):
         """All device work of SIU3RModel.forward / SIU3RMultiViewModel.forward up to (and excluding) the host-assisted panoptic
         post-process.  Images are batched view-major (image j = v*B + b) in both models."""
@@ -801,9 +913,12 @@ class SIU3RModel:
                 ops._lib.check(lib.siu3r_nchw_to_nhwc(imgs[b, v].data_ptr(), img4[v * B + b].data_ptr(), 1, 3, S0 * S1, 4, ops._stream()), "nchw_to_nhwc")
         # ---- encoder input: patch tokens + intrinsics token ----
         x = torch.empty(Bn, N, 1024, device=self.dev)
-        cols = torch.empty(Bn * P, 1024, device=self.dev)
-        ops._lib.check(lib.siu3r_im2col_nhwc(img4.data_ptr(), Bn, S0, S1, 4, 16, 16, 16, 0, 0, cols.data_ptr(), 1024, 1 if self.R else 0, ops._stream()),
-                       "im2col")
+        if self.S:
+            cols = ops.im2col_h3(img4, 16, 16, 16, 0, 0, 1024)
+        else:
+            cols = torch.empty(Bn * P, 1024, device=self.dev)
+            ops._lib.check(lib.siu3r_im2col_nhwc(img4.data_ptr(), Bn, S0, S1, 4, 16, 16, 16, 0, 0, cols.data_ptr(), 1024, 1 if self.R else 0, ops._stream()),
+                           "im2col")
         for i in range(Bn):
             self._lin(cols[i * P:(i + 1) * P], w.patch, ar=True, out=x[i, :P])
         x = x.view(Bn * N, 1024)

@@ -14,7 +14,7 @@ from . import _lib
 ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
 ELT_RELU, ELT_ADD, ELT_ADD_RELU, ELT_GELU, ELT_COPY, ELT_SIGMOID, ELT_CLAMP01, ELT_RELU_RN, ELT_ROUND, ELT_ADD_RN = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9
 ACT_ROUND_TF32 = 4  # flag OR-ed into `act`: store RN_tf32(result)
-PREC_TF32, PREC_FP32X3 = 1, 3
+PREC_TF32, PREC_FP32X3, PREC_H3 = 1, 3, 4   # 4 = fp32-grade on the fp16 tensor-core path (fp16 hi / lo plane pairs, csrc/h3.cuh)
 SKINNY = False   # route M <= SMALL_M GEMMs (TF32 mode) to siu3r_gemm_skinny: measured no faster than the tensor-core kernel inside the
 #                  captured graph (Mask2Former stage 3.85 vs 3.5 ms) -> off; the kernel stays available through the C ABI
 SMALL_M, SMALL_NK = 128, 0   # GEMMs with at most SMALL_M rows and N*K <= SMALL_NK would run on the fp32 FFMA kernel; measured slower than
@@ -59,6 +59,72 @@ def _chk_f32(*ts):
             assert t.is_cuda and t.dtype == torch.float32, (t.device, t.dtype)
 
 
+class Split:
+    """fp16 plane pair of the h3 mode (csrc/h3.cuh): t = [2, *shape] half tensor, t[0] = hi = fp16(x), t[1] = lo = fp16((x - hi) * 2^11)
+    (or the unscaled fp16(x - hi) when `unscaled`: operands of the attention kernel).  Slicing / views apply to the logical dims."""
+
+    __slots__ = ("t", "unscaled")
+
+    def __init__(self, t: torch.Tensor, unscaled: bool = False):
+        assert t.dtype == torch.float16 and t.shape[0] == 2 and t.is_cuda
+        self.t, self.unscaled = t, unscaled
+
+    @staticmethod
+    def empty(*shape, device, unscaled: bool = False) -> "Split":
+        return Split(torch.empty(2, *shape, device=device, dtype=torch.float16), unscaled)
+
+    shape = property(lambda self: self.t.shape[1:])
+    plane = property(lambda self: self.t.stride(0))
+    device = property(lambda self: self.t.device)
+
+    def dim(self):
+        return self.t.dim() - 1
+
+    def stride(self, i):
+        return self.t.stride(i + 1 if i >= 0 else i)
+
+    def data_ptr(self):
+        return self.t.data_ptr()
+
+    def __getitem__(self, idx):
+        idx = idx if isinstance(idx, tuple) else (idx,)
+        return Split(self.t[(slice(None),) + idx], self.unscaled)
+
+    def view(self, *shape):
+        return Split(self.t.view(2, *shape), self.unscaled)
+
+    def is_contiguous(self):
+        return self.t[0].is_contiguous()
+
+    def float(self) -> torch.Tensor:
+        """hi + lo * 2^-11 as fp32 (tests / debugging)."""
+        assert self.dim() == 2 and self.stride(1) == 1
+        y = torch.empty(self.shape[0], self.shape[1], device=self.device, dtype=torch.float32)
+        lib = _lib.load()
+        _lib.check(lib.siu3r_merge_h3(self.data_ptr(), self.stride(0), self.plane, self.shape[0], self.shape[1], _p(y), y.stride(0), _stream()), "merge_h3")
+        if self.unscaled:
+            hi = self.t[0].float()
+            return hi + (y - hi) * 2048.0
+        return y
+
+
+def split(x, out: "Split | None" = None, unscaled: bool = False) -> "Split":
+    """fp32 [rows, cols] (row-strided) or any contiguous fp32 tensor -> plane pair of the same logical shape."""
+    if isinstance(x, Split):
+        return x
+    _chk_f32(x)
+    if x.dim() != 2 or x.stride(1) != 1:
+        assert x.is_contiguous()
+        o = split(x.view(-1, x.shape[-1]), None if out is None else out.view(-1, x.shape[-1]), unscaled)
+        return o.view(*x.shape) if out is None else out
+    if out is None:
+        out = Split.empty(x.shape[0], x.shape[1], device=x.device, unscaled=unscaled)
+    assert out.dim() == 2 and out.stride(1) == 1 and tuple(out.shape) == tuple(x.shape) and out.unscaled == unscaled
+    _lib.check(_lib.load().siu3r_split_h3(_p(x), x.stride(0), x.shape[0], x.shape[1], out.data_ptr(), out.stride(0), out.plane, 1 if unscaled else 0,
+                                          _stream()), "split_h3")
+    return out
+
+
 def launch_count() -> int:
     return int(_lib.load().siu3r_launch_count())
 
@@ -79,7 +145,7 @@ def split_tf32(x: torch.Tensor):
 class Weight:
     """A [N, K] K-major matrix (nn.Linear.weight layout) prepared for the tensor-core path."""
 
-    __slots__ = ("w", "w_lo", "bias", "N", "K", "_rows")
+    __slots__ = ("w", "w_lo", "bias", "N", "K", "_rows", "h3")
 
     def __init__(self, w: torch.Tensor, bias: torch.Tensor | None, precision: int):
         w = w.contiguous().float()
@@ -89,7 +155,9 @@ class Weight:
             wp = torch.zeros(self.N, kp, device=w.device, dtype=torch.float32)
             wp[:, : self.K] = w
             w = wp
-        if w.is_cuda and w.numel() % 4 == 0:
+        if precision == PREC_H3:
+            self.w, self.w_lo = w, None   # exact fp32 copy for the SIMT fallback; the tensor cores read the fp16 plane pair below
+        elif w.is_cuda and w.numel() % 4 == 0:
             hi, lo = split_tf32(w)
             self.w = hi  # round-to-nearest TF32 once at load (the tensor core would otherwise truncate)
             self.w_lo = lo if precision == PREC_FP32X3 else None
@@ -97,6 +165,11 @@ class Weight:
             self.w, self.w_lo = w, None
         self.bias = None if bias is None else bias.contiguous().float()
         self._rows = None
+        self.h3 = None
+        if precision == PREC_H3 and w.is_cuda:
+            kp = (w.shape[1] + 7) // 8 * 8   # 16-byte row pitch in fp16
+            self.h3 = Split(torch.zeros(2, self.N, kp, device=w.device, dtype=torch.float16))
+            split(w, self.h3[:, : w.shape[1]])
 
     def rowpacked(self, KH: int, KW: int, Cin: int) -> "Weight":
         """[Cout, KH*KW*Cin] conv weight re-laid as [Cout, KH*32]: the KW*Cin <= 32 taps of one filter row become one
@@ -113,6 +186,10 @@ class Weight:
                 o[:, :, : KW * Cin] = w[:, : self.K].view(self.N, KH, KW * Cin)
                 return o.view(self.N, KH * 32)
             r.w, r.w_lo = relay(self.w), relay(self.w_lo)
+            r.h3 = None
+            if self.h3 is not None:
+                r.h3 = Split(torch.zeros(2, self.N, KH * 32, device=self.w.device, dtype=torch.float16))
+                r.h3.t.view(2, self.N, KH, 32)[..., : KW * Cin] = self.h3.t[:, :, : self.K].reshape(2, self.N, KH, KW * Cin)
             self._rows = r
         return self._rows
 
@@ -127,11 +204,16 @@ def round_tf32(x: torch.Tensor) -> torch.Tensor:
 
 def gemm(x: torch.Tensor, wt: Weight, out: torch.Tensor | None = None, act: int = ACT_NONE, residual: torch.Tensor | None = None,
          alpha: float = 1.0, precision: int = PREC_TF32, bias: torch.Tensor | None | bool = True, M: int | None = None,
-         a_rounded: bool = False, round_out: bool = False, rope: tuple | None = None, vt: tuple | None = None) -> torch.Tensor:
+         a_rounded: bool = False, round_out: bool = False, rope: tuple | None = None, vt: tuple | None = None, unscaled: bool = False):
     """out[M,N] = act(alpha * x[M,K] @ W^T + bias) + residual.  x / out / residual are 2-D row-strided views.
     rope = (positions [M,2] int64, table from rope2d_table, ncols): RoPE-2D on output columns [0, ncols) in the epilogue.
     TF32 mode: the A operand must be round-to-nearest TF32 (a_rounded=True if its producer already did that);
     round_out=True stores the result rounded because it only feeds further TF32 GEMMs."""
+    if precision == PREC_H3:
+        b_ = wt.bias if bias is True else (None if bias in (False, None) else bias)
+        if M is not None and M != x.shape[0]:
+            x = x[:M]
+        return _h3_linear([x], [wt], [out], act, [residual], alpha, [b_], rope, vt, round_out, unscaled)[0]
     _chk_f32(x, out, residual)
     assert x.dim() == 2 and x.stride(1) == 1
     M = x.shape[0] if M is None else M
@@ -199,11 +281,17 @@ def gemm(x: torch.Tensor, wt: Weight, out: torch.Tensor | None = None, act: int 
 
 
 def gemm_group2(xs, wts, outs=None, act: int = ACT_NONE, residuals=None, precision: int = PREC_TF32, a_rounded: bool = False,
-                round_out: bool = False, rope: tuple | None = None, vt: tuple | None = None):
+                round_out: bool = False, rope: tuple | None = None, vt: tuple | None = None, unscaled: bool = False):
     """Two linear layers of the same shape class (same N, K, strides, epilogue; rows may differ) in ONE persistent launch:
     outs[g] = act(xs[g] @ wts[g]^T + bias_g) + residuals[g].  Falls back to two gemm() calls when the shape / precision is not
     eligible for the grouped kernel (3xTF32 mode, tiny N or K, mismatching strides)."""
     assert len(xs) == 2 and len(wts) == 2
+    if precision == PREC_H3:
+        v = None
+        if vt is not None:   # vt = ([window Splits], [cols], col0, state)
+            v = (vt[0], vt[2], vt[3])
+        return _h3_linear(list(xs), list(wts), list(outs) if outs is not None else [None, None], act, list(residuals or [None, None]), 1.0,
+                          [w.bias for w in wts], rope, v, round_out, unscaled)
     if outs is None:
         outs = [torch.empty(x.shape[0], w.N, device=x.device, dtype=torch.float32) for x, w in zip(xs, wts)]
     residuals = residuals or [None, None]
@@ -257,6 +345,92 @@ def gemm_group2(xs, wts, outs=None, act: int = ACT_NONE, residuals=None, precisi
     return outs
 
 
+def _ptr_arr(ts):
+    return (C.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
+
+
+def _h3_linear(xs, wts, outs, act, residuals, alpha, biases, rope, vt, split_out, unscaled):
+    """h3 mode: outs[g] = act(alpha * xs[g] @ wts[g]^T + bias_g) [RoPE] + residuals[g] for 1 or 2 same-shape problems in one launch
+    (siu3r_gemm_h3).  xs: Split plane pairs or fp32 tensors (split here, one extra pass); outs[g]: fp32 tensor, Split, or None (allocated:
+    Split if split_out else fp32).  vt = (Split [rows, ld] or [window Splits], col0, state): columns >= col0 go to V^T."""
+    G = len(xs)
+    lib = _lib.load()
+    Ms = [x.shape[0] for x in xs]
+    K = xs[0].shape[1]
+    N = wts[0].N
+    assert all(x.dim() == 2 and x.shape[1] == K for x in xs) and all(w.N == N and w.K == K and w.h3 is not None for w in wts), (K, N, [w.K for w in wts])
+    if not all(isinstance(x, Split) for x in xs):
+        kp = (K + 7) // 8 * 8
+        parent = Split.empty(sum(Ms), kp, device=xs[0].device)
+        r0, sl = 0, []
+        for x, m in zip(xs, Ms):
+            dst = parent[r0:r0 + m, :K]
+            if isinstance(x, Split):   # mixed: re-pack under the common parent (rare)
+                dst.t.copy_(x.t)
+            else:
+                assert x.stride(1) == 1
+                split(x, dst)
+            sl.append(dst)
+            r0 += m
+        xs = sl
+    assert all(not x.unscaled and x.stride(1) == 1 and x.stride(0) % 8 == 0 and x.plane % 8 == 0 and x.data_ptr() % 16 == 0 for x in xs)
+    assert len({(x.stride(0), x.plane) for x in xs}) == 1, "grouped h3 operands must share pitch and plane distance (slices of one buffer)"
+    assert len({(w.h3.stride(0), w.h3.plane) for w in wts}) == 1
+    want_split = split_out or any(isinstance(o, Split) for o in outs)
+    dev = xs[0].device
+    if all(o is None for o in outs):
+        if want_split:
+            parent = Split.empty(sum(Ms), N, device=dev, unscaled=unscaled)
+            r0, outs = 0, []
+            for m in Ms:
+                outs.append(parent[r0:r0 + m])
+                r0 += m
+        else:
+            outs = [torch.empty(m, N, device=dev, dtype=torch.float32) for m in Ms]
+    assert all(o is not None for o in outs)
+    is_split = isinstance(outs[0], Split)
+    assert all(isinstance(o, Split) == is_split for o in outs) and (is_split or not want_split)
+    Cf = Ch = None
+    ldc = ldh = hpl = 0
+    if is_split:
+        assert all(o.stride(1) == 1 and o.unscaled == unscaled for o in outs) and len({(o.stride(0), o.plane) for o in outs}) == 1
+        Ch, ldh, hpl = _ptr_arr(outs), outs[0].stride(0), outs[0].plane
+    else:
+        _chk_f32(*outs)
+        assert all(o.stride(1) == 1 for o in outs) and len({o.stride(0) for o in outs}) == 1
+        Cf, ldc = _ptr_arr(outs), outs[0].stride(0)
+    has_b = biases[0] is not None
+    assert all((b is not None) == has_b for b in biases)
+    has_r = residuals[0] is not None
+    assert all((r is not None) == has_r for r in residuals)
+    if has_r:
+        _chk_f32(*residuals)
+        assert len({r.stride(0) for r in residuals}) == 1 and all(r.stride(1) == 1 for r in residuals)
+    pos = tab = None
+    ncols = 0
+    if rope is not None:
+        pos, tab, ncols = rope
+        assert not has_r and pos.dtype == torch.int64 and pos.is_contiguous() and pos.numel() >= 2 * max(Ms)
+    vts = vcols = None
+    vt_ld = vt_pl = vt_col0 = 0
+    if vt is not None:
+        vt_t, vt_col0, state = vt
+        wins = vt_t if isinstance(vt_t, (list, tuple)) else [vt_t]
+        assert len(wins) == G and all(isinstance(w_, Split) and w_.unscaled == unscaled and w_.stride(1) == 1 for w_ in wins)
+        assert len({(w_.stride(0), w_.plane) for w_ in wins}) == 1
+        vts, vcols = _ptr_arr(wins), (C.c_int * G)(*[w_.shape[1] for w_ in wins])
+        vt_ld, vt_pl = wins[0].stride(0), wins[0].plane
+        state["ok"] = True
+    Mh = (C.c_int * G)(*Ms)
+    with _Prof("gemm_h3", 2.0 * sum(Ms) * N * K, ("h3", sum(Ms), N, K)):
+        code = lib.siu3r_gemm_h3(G, Mh, N, K, _ptr_arr(xs), xs[0].stride(0), xs[0].plane, _ptr_arr([w.h3 for w in wts]), wts[0].h3.stride(0),
+                                 wts[0].h3.plane, Cf, ldc, Ch, ldh, hpl, _ptr_arr(biases) if has_b else None,
+                                 _ptr_arr(residuals) if has_r else None, residuals[0].stride(0) if has_r else 0, act & 3, alpha, _p(pos), _p(tab),
+                                 ncols, vts, vcols, vt_ld, vt_pl, vt_col0, 1 if unscaled else 0, _stream())
+    _lib.check(code, "gemm_h3")
+    return outs
+
+
 def rope2d_table(maxpos: int, D: int = 64, base: float = 100.0, fwd: float = 1.0, device="cuda") -> torch.Tensor:
     """[maxpos, D/4, 2] (cos, sin) factors shared by every RoPE-fused projection (siu3r_gemm_tc_rope)."""
     tab = torch.empty(maxpos, D // 4, 2, device=device, dtype=torch.float32)
@@ -286,6 +460,8 @@ def conv2d(x: torch.Tensor, wt: Weight, KH: int, KW: int, stride: int = 1, pad: 
            round_out: bool = False) -> torch.Tensor:
     """NHWC convolution.  wt is [Cout, KH*KW*Cin] ((kh, kw, ci) fastest = ci).  Stride-1 convs with tensor-core friendly
     shapes run as implicit GEMM (4-D TMA); everything else as im2col + tensor-core GEMM."""
+    if precision == PREC_H3:
+        return _h3_conv2d(x, wt, KH, KW, stride, pad, act, residual, out, round_out)
     _chk_f32(x, residual, out)
     N, H, W, Cin = x.shape
     assert x.is_contiguous()
@@ -330,6 +506,62 @@ def conv2d(x: torch.Tensor, wt: Weight, KH: int, KW: int, stride: int = 1, pad: 
     assert K <= ldo
     gemm(cols, wt, out=out.view(-1, Cout), act=act, residual=None if residual is None else residual.view(-1, Cout), precision=precision,
          a_rounded=True, round_out=round_out)
+    return out
+
+
+def im2col_h3(x: torch.Tensor, KH: int, KW: int, stride: int, pad_h: int, pad_w: int, ldo: int) -> Split:
+    """NHWC fp32 image -> column matrix [(n, oh, ow), ldo] as a plane pair ((kh, kw, ci) order, zero pad columns)."""
+    _chk_f32(x)
+    N, H, W, Cin = x.shape
+    assert x.is_contiguous() and ldo % 8 == 0
+    OH, OW = (H + 2 * pad_h - KH) // stride + 1, (W + 2 * pad_w - KW) // stride + 1
+    cols = Split.empty(N * OH * OW, ldo, device=x.device)
+    _lib.check(_lib.load().siu3r_im2col_nhwc_h3(_p(x), N, H, W, Cin, KH, KW, stride, pad_h, pad_w, cols.data_ptr(), ldo, cols.plane, _stream()),
+               "im2col_h3")
+    return cols
+
+
+def _h3_conv2d(x, wt: Weight, KH, KW, stride, pad, act, residual, out, split_out):
+    """h3-mode NHWC convolution.  x: fp32 [N,H,W,Cin] or Split of that shape; out: fp32 tensor / Split / None."""
+    N, H, W, Cin = x.shape
+    Cout = wt.N
+    pad_h, pad_w = pad if isinstance(pad, tuple) else (pad, pad)
+    OH = (H + 2 * pad_h - KH) // stride + 1
+    OW = (W + 2 * pad_w - KW) // stride + 1
+    want_split = split_out or isinstance(out, Split)
+    if out is None:
+        out = Split.empty(N, OH, OW, Cout, device=x.device) if want_split else torch.empty(N, OH, OW, Cout, device=x.device, dtype=torch.float32)
+    o2 = out.view(-1, Cout)
+    r2 = None if residual is None else residual.view(-1, Cout)
+    if KH == 1 and KW == 1 and stride == 1 and pad_h == 0 and pad_w == 0:
+        assert x.is_contiguous()
+        _h3_linear([x.view(-1, Cin)], [wt], [o2], act, [r2], 1.0, [wt.bias], None, None, want_split, False)
+        return out
+    same = stride == 1 and OH == H and OW == W and 2 * pad_h == KH - 1 and 2 * pad_w == KW - 1
+    if same and KH > 1 and KW > 1 and KW * Cin <= 32 and W % 16 == 0 and not isinstance(x, Split):
+        # few input channels (the RGB image): pack the KW taps of a filter row into one 32-wide vector per pixel and run the KH x 1 remainder
+        # as implicit GEMM (the 64-wide channel block is half zero fill)
+        rows = im2col_h3(x, 1, KW, 1, 0, pad_w, 32).view(N, H, W, 32)
+        return _h3_conv2d(rows, wt.rowpacked(KH, KW, Cin), KH, 1, 1, (pad_h, 0), act, residual, out, split_out)
+    if same and W % 16 == 0 and Cin % 8 == 0:
+        xs = x if isinstance(x, Split) else split(x)
+        assert xs.is_contiguous() and xs.data_ptr() % 16 == 0 and xs.plane % 8 == 0 and wt.h3 is not None and wt.K == KH * KW * Cin
+        if residual is not None:
+            _chk_f32(residual)
+            assert residual.is_contiguous()
+        is_split = isinstance(out, Split)
+        assert out.is_contiguous()
+        with _Prof("conv2d_h3", 2.0 * N * H * W * Cout * KH * KW * Cin, ("conv", N * H * W, Cout, KH * KW * Cin)):
+            code = _lib.load().siu3r_conv2d_h3(N, H, W, Cin, Cout, KH, KW, pad_h, pad_w, xs.data_ptr(), Cin, xs.plane, wt.h3.data_ptr(), wt.h3.stride(0),
+                                               wt.h3.plane, None if is_split else _p(out), Cout, out.data_ptr() if is_split else None, Cout,
+                                               out.plane if is_split else 0, _p(wt.bias), _p(residual), Cout, act & 3, _stream())
+        _lib.check(code, "conv2d_h3")
+        return out
+    # strided / odd shapes: im2col (plane pair written directly) + tensor-core GEMM; im2col reads fp32
+    if isinstance(x, Split):
+        x = x.view(-1, Cin).float().view(N, H, W, Cin)
+    cols = im2col_h3(x, KH, KW, stride, pad_h, pad_w, wt.h3.shape[1])
+    _h3_linear([cols[:, : wt.K]], [wt], [o2], act, [r2], 1.0, [wt.bias], None, None, want_split, False)
     return out
 
 
@@ -383,6 +615,69 @@ def layernorm_group2(xs, wbs, eps: float, outs, round_out: bool = False):
                                               1 if round_out else 0, _stream())
     _lib.check(code, "layernorm_group2")
     return outs
+
+
+def layernorm_h3(xs, wbs, eps: float, outs=None, outs_f32=None):
+    """h3 mode LayerNorm of one or two row blocks (different affine parameters) in one launch, result as plane pairs `outs` (allocated as
+    slices of one buffer when None) and / or fp32 `outs_f32`.  Returns the list of plane pairs (or of fp32 tensors when only those)."""
+    G = len(xs)
+    assert G in (1, 2) and len(wbs) == G
+    _chk_f32(*xs, *[t for wb in wbs for t in wb])
+    Cc = xs[0].shape[1]
+    assert all(x.dim() == 2 and x.shape[1] == Cc and x.stride(1) == 1 for x in xs) and len({x.stride(0) for x in xs}) == 1
+    rows = [x.shape[0] for x in xs]
+    if outs is None and outs_f32 is None:
+        parent = Split.empty(sum(rows), Cc, device=xs[0].device)
+        outs, r0 = [], 0
+        for r in rows:
+            outs.append(parent[r0:r0 + r])
+            r0 += r
+    ldy = ldh = pl = 0
+    if outs is not None:
+        assert all(isinstance(o, Split) and not o.unscaled and o.stride(1) == 1 for o in outs) and len({(o.stride(0), o.plane) for o in outs}) == 1
+        ldh, pl = outs[0].stride(0), outs[0].plane
+    if outs_f32 is not None:
+        _chk_f32(*outs_f32)
+        assert len({o.stride(0) for o in outs_f32}) == 1
+        ldy = outs_f32[0].stride(0)
+    g1 = G == 2
+    code = _lib.load().siu3r_layernorm_h3(_p(xs[0]), _p(xs[1]) if g1 else None, xs[0].stride(0), _p(wbs[0][0]), _p(wbs[0][1]),
+                                          _p(wbs[1][0]) if g1 else None, _p(wbs[1][1]) if g1 else None,
+                                          _p(outs_f32[0]) if outs_f32 is not None else None, _p(outs_f32[1]) if (outs_f32 is not None and g1) else None,
+                                          ldy, outs[0].data_ptr() if outs is not None else None, outs[1].data_ptr() if (outs is not None and g1) else None,
+                                          ldh, pl, rows[0], rows[1] if g1 else 0, Cc, eps, _stream())
+    _lib.check(code, "layernorm_h3")
+    return outs if outs is not None else outs_f32
+
+
+def flash_attn_h3(q: Split, q_col0: int, k: Split, k_col0: int, vt: Split, vt_batch_cols: int, B: int, H: int, Nq: int, Nk: int, scale: float,
+                  out=None, split_out: bool = True, vt_b_split: int = 0, vt_extra: int = 0):
+    """tcgen05 flash attention at fp32-grade accuracy (csrc/flash_h3.cu).  q [B*Nq, wq] / k [B*Nk, wk]: UNSCALED plane pairs, head h at columns
+    col0 + 64 h; vt: unscaled V^T plane pair [H*64, ld] with image b at column b * vt_batch_cols (+ vt_extra for b >= vt_b_split > 0), or
+    [(B*H)*64, ld] when vt_batch_cols == 0.  out: Split / fp32 [B*Nq, H*64] (allocated when None)."""
+    assert q.unscaled and k.unscaled and vt.unscaled and q.dim() == 2 and k.dim() == 2 and vt.dim() == 2
+    assert q.stride(1) == 1 and k.stride(1) == 1 and vt.stride(1) == 1
+    dev = q.device
+    if out is None:
+        out = Split.empty(B * Nq, H * 64, device=dev) if split_out else torch.empty(B * Nq, H * 64, device=dev, dtype=torch.float32)
+    is_split = isinstance(out, Split)
+    assert out.stride(1) == 1 and tuple(out.shape) == (B * Nq, H * 64)
+    with _Prof("flash_attn", 4.0 * B * H * Nq * Nk * 64):
+        code = _lib.load().siu3r_flash_attn_h3(q.data_ptr(), Nq * q.stride(0), q.stride(0), q.plane, q.shape[1], q_col0, k.data_ptr(), Nk * k.stride(0),
+                                               k.stride(0), k.plane, k.shape[1], k_col0, vt.data_ptr(), vt.stride(0), vt.plane, vt_batch_cols,
+                                               vt_b_split, vt_extra, None if is_split else _p(out), Nq * out.stride(0), out.stride(0),
+                                               out.data_ptr() if is_split else None, Nq * out.stride(0), out.stride(0), out.plane if is_split else 0,
+                                               B, H, Nq, Nk, scale, _stream())
+    _lib.check(code, "flash_attn_h3")
+    return out
+
+
+def transpose_v_h3(v: torch.Tensor, v_off: int, v_bs: int, v_ts: int, B: int, N: int, H: int) -> Split:
+    """fp32 V inside a fused buffer -> unscaled V^T plane pair [(B*H)*64, roundup8(N)] (fallback when the projection could not write V^T)."""
+    ld = (N + 7) // 8 * 8
+    vt = Split.empty(B * H * 64, ld, device=v.device, unscaled=True)
+    _lib.check(_lib.load().siu3r_transpose_v_h3(v.data_ptr() + 4 * v_off, v_bs, v_ts, B, N, H, vt.data_ptr(), ld, vt.plane, _stream()), "transpose_v_h3")
+    return vt
 
 
 def rope2d_(tokens_ptr_tensor: torch.Tensor, offset: int, positions: torch.Tensor, B: int, N: int, H: int, D: int, batch_stride: int,
@@ -454,6 +749,15 @@ def eltwise(op: int, a: torch.Tensor, b: torch.Tensor | None = None, out: torch.
     return out
 
 
+def eltwise_h3(op: int, a: torch.Tensor, b: torch.Tensor | None = None) -> Split:
+    """eltwise (ops 0..6) whose result is stored as a plane pair of a's shape."""
+    _chk_f32(a, b)
+    assert a.is_contiguous() and (b is None or b.is_contiguous()) and a.numel() % 4 == 0
+    out = Split.empty(*a.shape, device=a.device)
+    _lib.check(_lib.load().siu3r_eltwise_h3(op, _p(a), _p(b), out.data_ptr(), out.plane, a.numel(), _stream()), "eltwise_h3")
+    return out
+
+
 def scale_(x: torch.Tensor, alpha: float):
     """x *= alpha in place."""
     _chk_f32(x)
@@ -486,6 +790,17 @@ def resize_bilinear(x: torch.Tensor, OH: int, OW: int, align_corners: bool, out:
     code = _lib.load().siu3r_resize_bilinear_nhwc(_p(x), N, H, W, Cc, ldx, _p(out), OH, OW, out.stride(2), 1 if align_corners else 0,
                                                   (1 if accumulate else 0) | (2 if round_out else 0), _stream())
     _lib.check(code, "resize_bilinear")
+    return out
+
+
+def resize_bilinear_h3(x: torch.Tensor, OH: int, OW: int, align_corners: bool) -> Split:
+    """resize_bilinear whose result [N,OH,OW,C] is stored as a plane pair (it only feeds a convolution)."""
+    _chk_f32(x)
+    N, H, W, Cc = x.shape
+    out = Split.empty(N, OH, OW, Cc, device=x.device)
+    code = _lib.load().siu3r_resize_bilinear_nhwc_h3(_p(x), N, H, W, Cc, x.stride(2), out.data_ptr(), OH, OW, Cc, out.plane, 1 if align_corners else 0,
+                                                     _stream())
+    _lib.check(code, "resize_bilinear_h3")
     return out
 
 

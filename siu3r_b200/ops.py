@@ -102,9 +102,8 @@ class Split:
         y = torch.empty(self.shape[0], self.shape[1], device=self.device, dtype=torch.float32)
         lib = _lib.load()
         _lib.check(lib.siu3r_merge_h3(self.data_ptr(), self.stride(0), self.plane, self.shape[0], self.shape[1], _p(y), y.stride(0), _stream()), "merge_h3")
-        if self.unscaled:
-            hi = self.t[0].float()
-            return hi + (y - hi) * 2048.0
+        if self.unscaled:   # (the merge kernel applies the 2^-11 factor: undo it exactly on the lo plane instead of on the rounded sum)
+            return self.t[0].float() + self.t[1].float()
         return y
 
 

@@ -21,9 +21,11 @@ class PairPipeline:
     reused `depth` submits later: consume (or copy) them before that.
     """
 
-    def __init__(self, model, depth: int = 3, fields=GAUSSIAN_FIELDS):
+    def __init__(self, model, depth: int = 3, fields=GAUSSIAN_FIELDS, lift: bool = False):
         assert depth >= 3, "one slot downloading, one being post-processed, one being overwritten"
         self.model, self.depth, self.fields = model, depth, tuple(fields)
+        self.lift = lift   # enable_query_class_logit_lift (inference.py:132-136); the lifted logits stay on the device like in the reference
+        #                    (Gaussians.detach_cpu_copy only moves tensor attributes; seg_query_class_logits is a list)
         self.copy_stream = torch.cuda.Stream(device=model.dev)
         self.slots = [dict(dev={}, host={}, snap=torch.cuda.Event(), done=torch.cuda.Event(), meta=None) for _ in range(depth)]
         self.n = 0
@@ -54,7 +56,7 @@ class PairPipeline:
         self._pending = None
         cur = torch.cuda.current_stream()
         slot = self.slots[idx % self.depth]
-        out = self.model.forward_finish(handle)
+        out = self.model.forward_finish(handle, enable_query_class_logit_lift=self.lift)
         g, seg_masks, seg_infos = out[0], out[2], out[3]
         if idx >= self.depth:
             cur.wait_event(slot["done"])   # the slot's previous download has left the snapshot buffers

@@ -119,6 +119,18 @@ def make_state_dict(shapes: dict | None = None, seed: int = 0) -> dict:
                 gain = 0.12 if key.startswith("downstream") else 0.3
             if leaf in ("level_embed",) or "queries_" in key or "level_embed" in key:
                 gain = 1.0
+            # Mask2Former decoder: with unit-gain sublayers the 27 post-norm residual steps wash the query identity out (every query ends up with
+            # the same class logits: all void, the panoptic post-process empty).  Unit-variance learned queries + damped sublayer outputs keep the 100
+            # queries distinct, which -- with the class bias below -- populates the post-process: at 512^2 19 queries pass the score test, 13 of
+            # them are rejected by the area test and 6 survive, four of them fused into one "floor" segment.
+            if "queries_features" in key:
+                gain = 16.0
+            if "transformer_module.decoder.layers" in key and (".out_proj." in key or ".fc2." in key):
+                gain = 0.3
             t = gain * torch.randn(shape, generator=g) / (fan_in ** 0.5)
+        if key == "mask2former.class_predictor.bias":
+            t[20] += 30.0   # most queries void ...
+            t[0] += 8.0     # ... and the two stuff classes (wall, floor) favoured so that fused segments occur
+            t[1] += 8.0
         sd[key] = t.to(torch.float32)
     return sd

@@ -158,7 +158,7 @@ def cpu_port_forward(size: int, batch: int, threads: int):
     from oracle import torch_port as TP
     from siu3r_b200 import synth
     torch.set_num_threads(threads)
-    sd = cpu_port_forward.sd if hasattr(cpu_port_forward, "sd") else synth.make_state_dict()
+    sd = cpu_port_forward.sd if hasattr(cpu_port_forward, "sd") else synth.make_state_dict(populated=True)
     cpu_port_forward.sd = sd
     img, K = synth.pair_inputs(batch, 2, size)
     t0 = time.perf_counter()
@@ -182,7 +182,7 @@ def run_reference(args, rank):
             "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": workload_name(args.size, 1, 2),
-                       "weights": "seeded random init of the reference architecture (655.5 M params)"},
+                       "weights": "seeded random init of the reference architecture (655.5 M params), populated-panoptic preset (siu3r_b200/synth.py)"},
             "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": threads, "kind": "port",
                              "sample": f"{args.steps} x one {args.size}x{args.size} pair, oracle/torch_port.py (torch CPU fp32)"},
             "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
@@ -208,7 +208,7 @@ def main():
     S, B = args.size, args.batch
     V = args.views
     model = (SIU3RModel if V == 2 else SIU3RMultiViewModel)(ModelCfg(image_size=(S, S)), precision=args.precision)
-    model.load_state_dict(synth.make_state_dict())
+    model.load_state_dict(synth.make_state_dict(populated=True))
     model.cuda()
     img_h, K_h = synth.pair_inputs(B, V, S, seed=rank)
     img_pin, K_pin = img_h.pin_memory(), K_h.pin_memory()
@@ -362,7 +362,7 @@ def main():
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {"tf32": "tf32", "fp32x3": "3xtf32", "h3": "f32 (fp16 hi+lo operand pairs, fp32 accumulate)"}[args.precision], "data": "synthetic",
             "config": {"workload": workload_name(S, B, V), "precision": args.precision,
-                       "weights": "seeded random init of the reference architecture (655.5 M params)", "parallelism": f"dp{world}",
+                       "weights": "seeded random init of the reference architecture (655.5 M params), populated-panoptic preset (siu3r_b200/synth.py)", "parallelism": f"dp{world}",
                        "cuda_graph": bool(args.graph), "overlap": "two graph slots: the device part of step i+1 runs while step i is post-processed" if args.graph else "none",
                        "l2": "no explicit flush: weights (2.6 GB) + activations per step exceed the 126 MB L2 many times over"},
             "clocks": clk,
@@ -417,7 +417,7 @@ def main():
             del model
             torch.cuda.empty_cache()
             m3 = SIU3RModel(ModelCfg(image_size=(S, S)), precision="tf32")
-            m3.load_state_dict(synth.make_state_dict())
+            m3.load_state_dict(synth.make_state_dict(populated=True))
             m3.cuda()
             m3.enable_cuda_graph()
             for _ in range(2):
@@ -481,14 +481,30 @@ def raster_bench(dev, peaks):
         e.record()
         torch.cuda.synchronize()
         return s.elapsed_time(e) / n
-    ms = run(True)          # full 5-tuple of the reference rasterizer (image, radii, depth, opacity, n_touched)
-    ms_rc = run(False)      # what render_cuda keeps (colour + depth): no n_touched counting
+    ms5 = run(True)         # full 5-tuple of the reference rasterizer (image, radii, depth, opacity, n_touched), host sync per frame to return the duplicate count
+    # what render_cuda runs: colour + depth, no n_touched, NO host round trip (siu3r_raster_forward_nosync: status word checked after the batch)
+    status = torch.zeros(4, device=dev, dtype=torch.int32)
+    st = {"ws": None}
+
+    def fn_ns():
+        r_ = ops.raster_forward_nosync(a[0], a[1], a[2], a[3], cam[0], cam[1], cam[2], cam[3], float(tx[0]), float(ty[0]), H, W, 4, sh_layout=1,
+                                       status=status, ws=st["ws"], out=st.get("out"))
+        st["ws"], st["out"] = r_["ws"], {k: r_[k] for k in ("color", "depth", "opacity", "radii", "n_touched")}
+    fn = lambda touched=False: fn_ns()
+    ms = run(False)
+    assert status.cpu().tolist()[2] == 0
     algo_bytes = 388.0 * G + 68.0 * D + 20.0 * H * W  # preprocess + binning/blend + output
     hbm = peaks.get("hbm_gbs", 6650.0)
-    return {"workload": f"{G} pixel-aligned Gaussians @ {H}x{W}, 1 camera", "fps": 1e3 / ms, "ms": ms, "fps_render_cuda": 1e3 / ms_rc, "ms_render_cuda": ms_rc,
-            "duplicates": D,
+    traffic = None
+    for cand in ("r02_ncu_raster_traffic.json",):
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", cand))).get("dram_bytes_per_frame")
+        except Exception:
+            pass
+    return {"workload": f"{G} pixel-aligned Gaussians @ {H}x{W}, 1 camera (render_cuda path: colour + depth, no host synchronisation)", "fps": 1e3 / ms, "ms": ms,
+            "fps_5tuple_sync": 1e3 / ms5, "ms_5tuple_sync": ms5, "duplicates": D,
             "roofline": {"bound": "hbm", "achieved": algo_bytes / (ms / 1e3) / 1e9, "peak": hbm, "unit": "GB/s", "frac": algo_bytes / (ms / 1e3) / 1e9 / hbm,
-                         "traffic": None, "algorithmic_bytes": algo_bytes}}
+                         "traffic": traffic, "traffic_unit": "DRAM bytes read+write per frame, all kernels of the frame (ncu)", "algorithmic_bytes": algo_bytes}}
 
 
 def labels2d_bench(dev, peaks):

@@ -44,6 +44,18 @@ int siu3r_raster_forward(int G, int H, int W, int sh_degree, int sh_coeffs, int 
                          uint32_t* debug_offsets, uint64_t* debug_keys, uint32_t* debug_values, uint32_t* debug_ranges,
                          void* stream);
 
+/* The same frame without the host synchronisation and without debug exports: the duplicate count stays on the device; status_dev [4] uint32 =
+ * {duplicates D, largest tile, flags, 0}, flags bit 0 = D > dup_capacity, bit 1 = a tile holds more than 8192 records -- in either case the later
+ * kernels return at once and the outputs are undefined: the caller reads status_dev when convenient (once for all cameras of a
+ * SplattingCUDA.forward) and re-renders flagged cameras through siu3r_raster_forward.  Capturable in a CUDA graph. */
+int siu3r_raster_forward_nosync(int G, int H, int W, int sh_degree, int sh_coeffs, int sh_layout, int cov_stride, const float* means3D,
+                                const float* cov, const float* shs, const float* opacities, const float* viewmatrix, const float* projmatrix,
+                                const float* campos, const float* bg, float tan_fovx, float tan_fovy, float* out_color, float* out_depth,
+                                float* out_opacity, int32_t* radii, int32_t* n_touched, void* workspace, int64_t workspace_bytes,
+                                int64_t dup_capacity, uint32_t* status_dev, void* stream);
+/* testing aid: 0 = the shared-memory bitonic tile sort of round 1 (tiles <= 2048 records) instead of the register-resident one */
+void siu3r_raster_set_regsort(int enabled);
+
 /* N-channel feature splatting: replaces gsplat.rasterization(means, quats=None, scales=None, covars, opacities, colors[N,C], viewmats,
  * Ks, width, height, sh_degree=None, near_plane, far_plane) as called at src/models/gaussian_renderer.py:92-106 (one camera per call).
  * viewmat = world-to-camera 4x4 row-major (device); intr_host = (fx, fy, cx, cy) in pixels (host); out_features [H,W,C], out_alpha [H,W]. */

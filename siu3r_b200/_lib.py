@@ -24,6 +24,8 @@ SIGNATURES = {
     "siu3r_raster_workspace_bytes": (_l, [_i, _i, _i, _l]),
     "siu3r_raster_forward": (_i, [_i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _l, _l,
                                   C.POINTER(C.c_int64), _p, _p, _p, _p, _p, _p]),
+    "siu3r_raster_forward_nosync": (_i, [_i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _l, _l, _p, _p]),
+    "siu3r_raster_set_regsort": (None, [_i]),
     "siu3r_raster_set_culling": (None, [_i]),
     "siu3r_raster_set_binning": (None, [_i]),
     "siu3r_raster_features_forward": (_i, [_i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _l, _l, C.POINTER(C.c_int64), _p]),

@@ -319,7 +319,8 @@ constexpr int TS_THREADS = 256;
 constexpr int TS_FAST = 2048;         // largest tile for which the binned path is used (measured: above it the global radix sort is faster)
 
 __global__ void __launch_bounds__(1024) tile_scan_kernel(const uint32_t* __restrict__ counts, int ntiles, uint2* __restrict__ ranges,
-                                                         uint32_t* __restrict__ cursors, uint32_t* __restrict__ total_max) {
+                                                         uint32_t* __restrict__ cursors, uint32_t* __restrict__ total_max, uint32_t capacity,
+                                                         uint32_t* __restrict__ status) {
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_carry, s_max;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -350,7 +351,13 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(const uint32_t* __restr
     }
     atomicMax(&s_max, mymax);
     __syncthreads();
-    if (threadIdx.x == 0) { total_max[0] = s_carry; total_max[1] = s_max; }
+    if (threadIdx.x == 0) {
+        total_max[0] = s_carry; total_max[1] = s_max;
+        if (status) {   // no-sync protocol: the later kernels of the frame read the flags and skip their work; the host looks at them once per batch of cameras
+            status[0] = s_carry; status[1] = s_max;
+            status[2] = (s_carry > capacity ? 1u : 0u) | (s_max > (uint32_t)TS_CAP ? 2u : 0u);
+        }
+    }
 }
 
 // Counting and scattering go through a per-CTA shared-memory histogram of the tiles: a CTA walks BIN_CHUNK Gaussians, so a tile that is hit k
@@ -378,7 +385,9 @@ __global__ void __launch_bounds__(BIN_THREADS) bin_count_kernel(int G, int gx, i
 
 __global__ void __launch_bounds__(BIN_THREADS) bin_scatter_kernel(int G, int gx, int ntiles, const int32_t* __restrict__ radii,
                                                                  const float* __restrict__ depths, const ushort4* __restrict__ rects,
-                                                                 uint32_t* __restrict__ cursors, uint64_t* __restrict__ list) {
+                                                                 uint32_t* __restrict__ cursors, uint64_t* __restrict__ list,
+                                                                 const uint32_t* __restrict__ status) {
+    if (status && status[2]) return;
     extern __shared__ uint32_t s_bin[];          // [ntiles] count, then local cursor | [ntiles] base of this CTA's run inside the tile segment
     uint32_t* s_cnt = s_bin;
     uint32_t* s_base = s_bin + ntiles;
@@ -442,6 +451,74 @@ __global__ void __launch_bounds__(TS_THREADS) tile_sort_kernel(const uint2* __re
     }
 }
 
+// Register-resident variant: every thread keeps ITEMS consecutive elements of the (padded) tile list, P = 256 * ITEMS.  Bitonic sub-stages
+// with stride j < ITEMS are compare-exchanges inside a thread, ITEMS <= j < 32 ITEMS are warp shuffles (partner lane = lane ^ j/ITEMS, same
+// register), only j >= 32 ITEMS goes through shared memory (element-major layout s[r * 256 + tid]: conflict free): for P = 2048 that is 6 of
+// the 66 sub-stages and 12 CTA barriers instead of 66.  Handles the tiles with n_lo < n <= n_hi; one launch per size class.
+__device__ __forceinline__ uint64_t shfl_xor_u64(uint64_t v, int m) {
+    const uint32_t lo = __shfl_xor_sync(0xffffffffu, (uint32_t)v, m), hi = __shfl_xor_sync(0xffffffffu, (uint32_t)(v >> 32), m);
+    return ((uint64_t)hi << 32) | lo;
+}
+
+template <int ITEMS>
+__global__ void __launch_bounds__(TS_THREADS) tile_sort_reg_kernel(const uint2* __restrict__ ranges, const uint64_t* __restrict__ list,
+                                                                   uint32_t* __restrict__ sorted_ids, int n_lo, int n_hi,
+                                                                   const uint32_t* __restrict__ status) {
+    extern __shared__ uint64_t s_w[];
+    if (status && status[2]) return;
+    const uint2 rg = ranges[blockIdx.x];
+    const int n = (int)(rg.y - rg.x);
+    if (n <= n_lo || n > n_hi) return;
+    constexpr int P = TS_THREADS * ITEMS;
+    const int tid = threadIdx.x;
+    const int e0 = tid * ITEMS;
+    uint64_t v[ITEMS];
+#pragma unroll
+    for (int r = 0; r < ITEMS; ++r) v[r] = (e0 + r) < n ? list[rg.x + e0 + r] : ~0ull;
+    for (int k = 2; k <= P; k <<= 1) {
+        for (int j = k >> 1; j >= 32 * ITEMS; j >>= 1) {            // partner in another warp
+            const int m = j / ITEMS;
+#pragma unroll
+            for (int r = 0; r < ITEMS; ++r) s_w[r * TS_THREADS + tid] = v[r];
+            __syncthreads();
+#pragma unroll
+            for (int r = 0; r < ITEMS; ++r) {
+                const uint64_t o = s_w[r * TS_THREADS + (tid ^ m)];
+                const int e = e0 + r;
+                const bool keep_min = ((e & j) == 0) == ((e & k) == 0);
+                v[r] = keep_min ? (o < v[r] ? o : v[r]) : (o > v[r] ? o : v[r]);
+            }
+            __syncthreads();
+        }
+        for (int j = min(k >> 1, 16 * ITEMS); j >= ITEMS; j >>= 1) {   // partner lane in the same warp
+            const int m = j / ITEMS;
+#pragma unroll
+            for (int r = 0; r < ITEMS; ++r) {
+                const uint64_t o = shfl_xor_u64(v[r], m);
+                const int e = e0 + r;
+                const bool keep_min = ((e & j) == 0) == ((e & k) == 0);
+                v[r] = keep_min ? (o < v[r] ? o : v[r]) : (o > v[r] ? o : v[r]);
+            }
+        }
+#pragma unroll
+        for (int J = ITEMS / 2; J >= 1; J >>= 1) {                   // partner register in the same thread
+            if (J <= (k >> 1)) {
+#pragma unroll
+                for (int r = 0; r < ITEMS; ++r) {
+                    if ((r & J) == 0) {
+                        const bool up = ((e0 + r) & k) == 0;
+                        const uint64_t a = v[r], b = v[r | J];
+                        if ((a > b) == up) { v[r] = b; v[r | J] = a; }
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < ITEMS; ++r)
+        if (e0 + r < n) sorted_ids[rg.x + e0 + r] = (uint32_t)v[r];
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Blend: one CTA (256 threads) per 16x16 tile, front-to-back over the tile's sorted list in batches of 256 records that
 // are staged once in shared memory (id, xy, conic+opacity, rgb+depth = 44 B) and then broadcast-read by the pixels.
@@ -464,7 +541,9 @@ __global__ void __launch_bounds__(RB) render_kernel(int W, int H, int gx, const 
                                                     const float4* __restrict__ conic_o, const float* __restrict__ rgb,
                                                     const float* __restrict__ depths, const float* __restrict__ cam_dev,
                                                     float* __restrict__ out_color, float* __restrict__ out_depth,
-                                                    float* __restrict__ out_opacity, int32_t* __restrict__ n_touched, int cull) {
+                                                    float* __restrict__ out_opacity, int32_t* __restrict__ n_touched, int cull,
+                                                    const uint32_t* __restrict__ status) {
+    if (status && status[2]) return;   // no-sync protocol: capacity overflow flagged by tile_scan_kernel (the caller retries with more room)
     __shared__ uint32_t s_id[RB];
     __shared__ float2 s_xy[RB];
     __shared__ float4 s_co[RB];
@@ -841,6 +920,26 @@ Workspace carve(void* base, int G, int H, int W, int64_t cap) {
     return w;
 }
 
+int g_regsort = 1; // testing aid: 0 = the round-1 shared-memory bitonic tile sort (tiles <= 2048 records) instead of the register-resident one
+
+// Per-tile sorts of one frame: one launch per size class that can occur (max_tile = largest tile if the host knows it, else TS_CAP).
+int launch_tile_sorts(int ntiles, const uint2* ranges, const uint64_t* list, uint32_t* sorted_ids, int max_tile, const uint32_t* status,
+                      cudaStream_t stream) {
+    static bool attr[64] = {false};
+    int dev = 0;
+    SIU3R_CUDA_CHECK(cudaGetDevice(&dev));
+    if (!attr[dev & 63]) {
+        SIU3R_CUDA_CHECK(cudaFuncSetAttribute(tile_sort_reg_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_THREADS * 32 * 8));
+        attr[dev & 63] = true;
+    }
+    tile_sort_reg_kernel<2><<<ntiles, TS_THREADS, TS_THREADS * 2 * 8, stream>>>(ranges, list, sorted_ids, 0, 512, status);
+    siu3r_note_launch(1);
+    if (max_tile > 512) { tile_sort_reg_kernel<8><<<ntiles, TS_THREADS, TS_THREADS * 8 * 8, stream>>>(ranges, list, sorted_ids, 512, 2048, status); siu3r_note_launch(1); }
+    if (max_tile > 2048) { tile_sort_reg_kernel<32><<<ntiles, TS_THREADS, TS_THREADS * 32 * 8, stream>>>(ranges, list, sorted_ids, 2048, TS_CAP, status); siu3r_note_launch(1); }
+    SIU3R_LAUNCH_CHECK();
+    return SIU3R_OK;
+}
+
 int g_binned = 1; // 0: always use the reference-shaped global radix sort (testing aid, see siu3r_raster_set_binning)
 int g_cull = 1;   // testing aid: 0 blends every record of the tile at every pixel (the unculled reference loop)
 
@@ -850,6 +949,7 @@ extern "C" {
 
 void siu3r_raster_set_culling(int enabled) { g_cull = enabled ? 1 : 0; }
 void siu3r_raster_set_binning(int enabled) { g_binned = enabled ? 1 : 0; }
+void siu3r_raster_set_regsort(int enabled) { g_regsort = enabled ? 1 : 0; }
 
 // Bytes of device scratch siu3r_raster_forward needs for G Gaussians, an HxW image and at most `dup_capacity`
 // (tile, Gaussian) duplicates.  Mirrors the resize-callback buffers of the reference rasterizer (geomBuffer,
@@ -925,7 +1025,7 @@ int siu3r_raster_forward(int G, int H, int W, int sh_degree, int sh_coeffs, int 
             attr_bin = true;
         }
         bin_count_kernel<<<ceil_div(G, BIN_CHUNK), BIN_THREADS, (size_t)ntiles * 4, stream>>>(G, gx, ntiles, radii, w.rects, w.tile_counts);
-        tile_scan_kernel<<<1, 1024, 0, stream>>>(w.tile_counts, ntiles, w.ranges, w.tile_cursors, w.total);
+        tile_scan_kernel<<<1, 1024, 0, stream>>>(w.tile_counts, ntiles, w.ranges, w.tile_cursors, w.total, (uint32_t)dup_capacity, nullptr);
         SIU3R_LAUNCH_CHECK();
         siu3r_note_launch(2);
         uint32_t tm[2] = {0, 0};
@@ -934,7 +1034,7 @@ int siu3r_raster_forward(int G, int H, int W, int sh_degree, int sh_coeffs, int 
         D = (int64_t)tm[0];
         if (num_rendered_host) *num_rendered_host = D;
         if (D > dup_capacity) return SIU3R_ERR_CAPACITY;
-        if (tm[1] > (uint32_t)TS_FAST) {
+        if (tm[1] > (uint32_t)(g_regsort ? TS_CAP : TS_FAST)) {
             binned = false;                                   // big tiles: the O(n log^2 n) shared-memory sort loses to the global radix sort
             SIU3R_CUDA_CHECK(cudaMemsetAsync(w.ranges, 0, sizeof(uint2) * gx * gy, stream));
         } else if (D > 0) {
@@ -944,12 +1044,17 @@ int siu3r_raster_forward(int G, int H, int W, int sh_degree, int sh_coeffs, int 
                 attr = true;
             }
             bin_scatter_kernel<<<ceil_div(G, BIN_CHUNK), BIN_THREADS, (size_t)ntiles * 8, stream>>>(G, gx, ntiles, radii, w.depths, w.rects,
-                                                                                                  w.tile_cursors, w.keys);
-            int P = 1;
-            while (P < (int)tm[1]) P <<= 1;                   // shared memory for the largest tile of this frame
-            tile_sort_kernel<<<gx * gy, TS_THREADS, (size_t)P * 8, stream>>>(w.ranges, w.keys, w.vals_sorted, nullptr);
-            SIU3R_LAUNCH_CHECK();
-            siu3r_note_launch(2);
+                                                                                                  w.tile_cursors, w.keys, nullptr);
+            if (g_regsort) {
+                int r = launch_tile_sorts(gx * gy, w.ranges, w.keys, w.vals_sorted, (int)tm[1], nullptr, stream); if (r) return r;
+            } else {
+                int P = 1;
+                while (P < (int)tm[1]) P <<= 1;                   // shared memory for the largest tile of this frame
+                tile_sort_kernel<<<gx * gy, TS_THREADS, (size_t)P * 8, stream>>>(w.ranges, w.keys, w.vals_sorted, nullptr);
+                SIU3R_LAUNCH_CHECK();
+                siu3r_note_launch(1);
+            }
+            siu3r_note_launch(1);
         }
     }
     if (!binned) {
@@ -981,10 +1086,10 @@ int siu3r_raster_forward(int G, int H, int W, int sh_degree, int sh_coeffs, int 
     dim3 grid(gx, gy), block(RB);
     if (n_touched)
         render_kernel<true><<<grid, block, 0, stream>>>(W, H, gx, w.ranges, sorted_vals, w.xy, w.conic_o, w.rgb, w.depths, w.cam,
-                                                        out_color, out_depth, out_opacity, n_touched, g_cull);
+                                                        out_color, out_depth, out_opacity, n_touched, g_cull, nullptr);
     else
         render_kernel<false><<<grid, block, 0, stream>>>(W, H, gx, w.ranges, sorted_vals, w.xy, w.conic_o, w.rgb, w.depths, w.cam,
-                                                         out_color, out_depth, out_opacity, nullptr, g_cull);
+                                                         out_color, out_depth, out_opacity, nullptr, g_cull, nullptr);
     SIU3R_LAUNCH_CHECK();
     siu3r_note_launch(1);
     if (D > 0) {
@@ -995,6 +1100,63 @@ int siu3r_raster_forward(int G, int H, int W, int sh_degree, int sh_coeffs, int 
     return SIU3R_OK;
 }
 
+// siu3r_raster_forward WITHOUT the host synchronisation (and without the debug exports): the duplicate count stays on the device.  All
+// kernels of the frame are enqueued unconditionally; if the frame needs more than dup_capacity duplicates, or one tile holds more than 8192
+// records, tile_scan_kernel raises a flag in status_dev[2] (bit 0 / bit 1) and the later kernels return at once, leaving the outputs undefined.
+// status_dev [4] uint32 (device): {duplicates D, largest tile, flags, 0}; the caller reads it whenever convenient -- e.g. once for all the
+// cameras of a SplattingCUDA.forward call -- and re-renders a flagged camera through siu3r_raster_forward.  Capturable in a CUDA graph.
+int siu3r_raster_forward_nosync(int G, int H, int W, int sh_degree, int sh_coeffs, int sh_layout, int cov_stride, const float* means3D,
+                                const float* cov, const float* shs, const float* opacities, const float* viewmatrix, const float* projmatrix,
+                                const float* campos, const float* bg, float tan_fovx, float tan_fovy, float* out_color, float* out_depth,
+                                float* out_opacity, int32_t* radii, int32_t* n_touched, void* workspace, int64_t workspace_bytes,
+                                int64_t dup_capacity, uint32_t* status_dev, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    SIU3R_REQUIRE(G > 0 && H > 0 && W > 0 && status_dev);
+    SIU3R_REQUIRE(sh_coeffs >= 1 && sh_coeffs * 3 <= MAX_SH_FLOATS && (sh_degree + 1) * (sh_degree + 1) <= sh_coeffs);
+    SIU3R_REQUIRE((sh_layout == 0 || sh_layout == 1) && (cov_stride == 6 || cov_stride == 9));
+    SIU3R_REQUIRE(means3D && cov && shs && opacities && viewmatrix && projmatrix && campos && bg);
+    SIU3R_REQUIRE(out_color && out_depth && out_opacity && radii && workspace && dup_capacity > 0 && dup_capacity < (1ll << 31));
+    const int gx = ceil_div(W, TILE_X), gy = ceil_div(H, TILE_Y), ntiles = gx * gy;
+    SIU3R_REQUIRE(gx < 65536 && gy < 65536);
+    if ((size_t)ntiles * 8 > 200 * 1024) return SIU3R_ERR_UNSUPPORTED;   // per-CTA tile histograms must fit shared memory
+    Workspace w = carve(workspace, G, H, W, dup_capacity);
+    if ((int64_t)w.bytes > workspace_bytes) return SIU3R_ERR_CAPACITY;
+    const int deg = sh_degree > 3 ? 3 : sh_degree;
+    const float focal_y = (float)H / (2.0f * tan_fovy), focal_x = (float)W / (2.0f * tan_fovx);
+    static bool attr_bin[64] = {false};
+    int dev = 0;
+    SIU3R_CUDA_CHECK(cudaGetDevice(&dev));
+    if (!attr_bin[dev & 63]) {
+        SIU3R_CUDA_CHECK(cudaFuncSetAttribute(bin_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        SIU3R_CUDA_CHECK(cudaFuncSetAttribute(bin_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_bin[dev & 63] = true;
+    }
+    SIU3R_CUDA_CHECK(cudaMemsetAsync(radii, 0, sizeof(int32_t) * G, stream));
+    SIU3R_CUDA_CHECK(cudaMemsetAsync(w.tiles, 0, sizeof(uint32_t) * G, stream));
+    SIU3R_CUDA_CHECK(cudaMemsetAsync(w.tile_counts, 0, sizeof(uint32_t) * ntiles, stream));
+    if (n_touched) SIU3R_CUDA_CHECK(cudaMemsetAsync(n_touched, 0, sizeof(int32_t) * G, stream));
+    pack_camera_kernel<<<1, 64, 0, stream>>>(viewmatrix, projmatrix, campos, bg, w.cam);
+    PreOut po{w.depths, w.xy, w.conic_o, w.rgb, w.tiles, w.rects};
+    preprocess_kernel<<<ceil_div(G, PRE_THREADS), PRE_THREADS, 0, stream>>>(G, H, W, gx, gy, deg, sh_coeffs, sh_layout, cov_stride, means3D, cov, shs,
+                                                                            opacities, w.cam, tan_fovx, tan_fovy, focal_x, focal_y, po, radii);
+    bin_count_kernel<<<ceil_div(G, BIN_CHUNK), BIN_THREADS, (size_t)ntiles * 4, stream>>>(G, gx, ntiles, radii, w.rects, w.tile_counts);
+    tile_scan_kernel<<<1, 1024, 0, stream>>>(w.tile_counts, ntiles, w.ranges, w.tile_cursors, w.total, (uint32_t)dup_capacity, status_dev);
+    bin_scatter_kernel<<<ceil_div(G, BIN_CHUNK), BIN_THREADS, (size_t)ntiles * 8, stream>>>(G, gx, ntiles, radii, w.depths, w.rects, w.tile_cursors,
+                                                                                          w.keys, status_dev);
+    SIU3R_LAUNCH_CHECK();
+    siu3r_note_launch(5);
+    int r = launch_tile_sorts(ntiles, w.ranges, w.keys, w.vals_sorted, TS_CAP, status_dev, stream); if (r) return r;
+    dim3 grid(gx, gy), block(RB);
+    if (n_touched)
+        render_kernel<true><<<grid, block, 0, stream>>>(W, H, gx, w.ranges, w.vals_sorted, w.xy, w.conic_o, w.rgb, w.depths, w.cam, out_color, out_depth,
+                                                        out_opacity, n_touched, g_cull, status_dev);
+    else
+        render_kernel<false><<<grid, block, 0, stream>>>(W, H, gx, w.ranges, w.vals_sorted, w.xy, w.conic_o, w.rgb, w.depths, w.cam, out_color, out_depth,
+                                                         out_opacity, nullptr, g_cull, status_dev);
+    SIU3R_LAUNCH_CHECK();
+    siu3r_note_launch(1);
+    return SIU3R_OK;
+}
 
 // N-channel feature rasterization of one camera (gsplat.rasterization semantics, see render_feat_kernel).  viewmat: world-to-camera
 // 4x4 row-major; intr_host = (fx, fy, cx, cy) in pixels; features [G, C]; out_features [H, W, C]; out_alpha [H, W] (may be null);

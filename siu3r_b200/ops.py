@@ -116,8 +116,8 @@ def split(x, out: "Split | None" = None, unscaled: bool = False) -> "Split":
         assert x.is_contiguous()
         o = split(x.view(-1, x.shape[-1]), None if out is None else out.view(-1, x.shape[-1]), unscaled)
         return o.view(*x.shape) if out is None else out
-    if out is None:
-        out = Split.empty(x.shape[0], x.shape[1], device=x.device, unscaled=unscaled)
+    if out is None:   # row pitch padded to a multiple of 8 elements (16 bytes: TMA)
+        out = Split.empty(x.shape[0], (x.shape[1] + 7) // 8 * 8, device=x.device, unscaled=unscaled)[:, : x.shape[1]]
     assert out.dim() == 2 and out.stride(1) == 1 and tuple(out.shape) == tuple(x.shape) and out.unscaled == unscaled
     _lib.check(_lib.load().siu3r_split_h3(_p(x), x.stride(0), x.shape[0], x.shape[1], out.data_ptr(), out.stride(0), out.plane, 1 if unscaled else 0,
                                           _stream()), "split_h3")
@@ -956,6 +956,34 @@ def raster_forward(means, cov, shs, opac, viewmatrix, projmatrix, campos, bg, ta
     res = dict(color=color, depth=depth, opacity=opacity, radii=radii, n_touched=n_touched, num_rendered=int(nren.value))
     res.update(dbg)
     return res
+
+
+def raster_forward_nosync(means, cov, shs, opac, viewmatrix, projmatrix, campos, bg, tan_fovx, tan_fovy, H, W, sh_degree, sh_layout, status, ws=None,
+                          dup_capacity=None, count_touched=False, out=None):
+    """One camera without any host synchronisation (siu3r_raster_forward_nosync): `status` = 4 uint32 on the device that receive
+    {duplicates, largest tile, flags, 0}; the caller checks flags != 0 later (see renderer.render_cuda).  `ws` = reusable workspace tensor."""
+    lib = _lib.load()
+    _chk_f32(means, cov, shs, opac, viewmatrix, projmatrix, campos, bg)
+    G = means.shape[0]
+    cov_stride = 6 if cov.shape[-1] == 6 else 9
+    M = shs.shape[1] if sh_layout == 0 else shs.shape[2]
+    dev = means.device
+    if dup_capacity is None:
+        dup_capacity = max(1 << 16, 8 * G)
+    ws_bytes = int(lib.siu3r_raster_workspace_bytes(G, H, W, dup_capacity))
+    if ws is None or ws.numel() < ws_bytes:
+        ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+    if out is None:
+        out = dict(color=torch.empty(3, H, W, device=dev), depth=torch.empty(H, W, device=dev), opacity=torch.empty(H, W, device=dev),
+                   radii=torch.empty(G, device=dev, dtype=torch.int32), n_touched=torch.empty(G, device=dev, dtype=torch.int32) if count_touched else None)
+    assert status.dtype == torch.int32 and status.numel() >= 4 and status.is_cuda
+    code = lib.siu3r_raster_forward_nosync(G, H, W, sh_degree, M, sh_layout, cov_stride, _p(means), _p(cov), _p(shs), _p(opac), _p(viewmatrix),
+                                           _p(projmatrix), _p(campos), _p(bg), float(tan_fovx), float(tan_fovy), _p(out["color"]), _p(out["depth"]),
+                                           _p(out["opacity"]), _p(out["radii"]), _p(out["n_touched"]), _p(ws), ws.numel(), dup_capacity, _p(status),
+                                           _stream())
+    _lib.check(code, "raster_forward_nosync")
+    out["ws"], out["dup_capacity"] = ws, dup_capacity
+    return out
 
 
 def raster_features_forward(means, cov, opac, feats, viewmat, intr, near, far, H, W, dup_capacity=None, want_alpha=True, want_radii=False):

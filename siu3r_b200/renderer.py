@@ -76,18 +76,35 @@ def render_cuda(extrinsics, intrinsics, near, far, image_shape, background_color
     dev = gaussian_means.device
     view, full, campos, tan_x, tan_y = camera_matrices(extrinsics, intrinsics, near, far)
     cam = torch.cat([view.reshape(b, 16), full.reshape(b, 16), campos, background_color.detach().float().cpu().reshape(b, 3)], dim=1).to(dev)
-    colors, depths, aux = [], [], []
+    color = torch.empty(b, 3, h, w, device=dev)
+    depth = torch.empty(b, h, w, device=dev)
+    args = lambda i: (gaussian_means[i if gaussian_means.shape[0] == b else 0].contiguous(), gaussian_covariances[i if gaussian_covariances.shape[0] == b else 0].contiguous(),
+                      gaussian_sh_coefficients[i if gaussian_sh_coefficients.shape[0] == b else 0].contiguous(),
+                      gaussian_opacities[i if gaussian_opacities.shape[0] == b else 0].contiguous(), cam[i, 0:16], cam[i, 16:32], cam[i, 32:35], cam[i, 35:38],
+                      float(tan_x[i]), float(tan_y[i]), h, w, degree)
+    if return_aux:   # reference 5-tuple incl. n_touched / duplicate counts: the synchronising entry point
+        aux = []
+        for i in range(b):
+            res = ops.raster_forward(*args(i), sh_layout=1, count_touched=True)
+            color[i], depth[i] = res["color"], res["depth"]
+            aux.append(res)
+        return color, depth, aux
+    # All cameras are enqueued back to back on one workspace without a host round trip (the reference rasterizer synchronises once per camera to size
+    # its buffers); the per-camera status words are read ONCE afterwards, and a camera that overflowed the duplicate capacity is re-rendered.
+    # n_touched / radii / opacity are discarded like in the reference (cuda_splatting.py:109,122).
+    status = torch.zeros(b, 4, device=dev, dtype=torch.int32)
+    ws = None
+    G = gaussian_means.shape[1]
+    scratch = dict(opacity=torch.empty(h, w, device=dev), radii=torch.empty(G, device=dev, dtype=torch.int32), n_touched=None)
     for i in range(b):
-        gi = i if gaussian_means.shape[0] == b else 0
-        res = ops.raster_forward(gaussian_means[gi].contiguous(), gaussian_covariances[gi].contiguous(), gaussian_sh_coefficients[gi].contiguous(),
-                                 gaussian_opacities[gi].contiguous(), cam[i, 0:16], cam[i, 16:32], cam[i, 32:35], cam[i, 35:38], float(tan_x[i]),
-                                 float(tan_y[i]), h, w, degree, sh_layout=1,
-                                 count_touched=return_aux)   # the reference discards n_touched / radii / opacity here (cuda_splatting.py:109,122)
-        colors.append(res["color"])
-        depths.append(res["depth"])
-        aux.append(res)
-    color, depth = torch.stack(colors), torch.stack(depths)
-    return (color, depth, aux) if return_aux else (color, depth)
+        r = ops.raster_forward_nosync(*args(i), sh_layout=1, status=status[i], ws=ws, out=dict(color=color[i], depth=depth[i], **scratch))
+        ws = r["ws"]
+    st = status.cpu()
+    for i in range(b):
+        if int(st[i, 2]) != 0:
+            res = ops.raster_forward(*args(i), sh_layout=1, count_touched=False, dup_capacity=int(int(st[i, 0]) * 1.05) + 1024)
+            color[i], depth[i] = res["color"], res["depth"]
+    return color, depth
 
 
 class SplattingCUDA:

@@ -72,7 +72,7 @@ def _gen(key: str, seed: int) -> torch.Generator:
     return g
 
 
-def make_state_dict(shapes: dict | None = None, seed: int = 0) -> dict:
+def make_state_dict(shapes: dict | None = None, seed: int = 0, populated: bool = False) -> dict:
     """Seeded synthetic weights for the full reference key set (655.5 M params).
 
     No checkpoint is available offline (README.md:35,84 of the reference are downloads), so
@@ -80,6 +80,15 @@ def make_state_dict(shapes: dict | None = None, seed: int = 0) -> dict:
     (non-zero biases, spread deformable offsets, peaked class logits so that the panoptic
     post-process takes its populated branch) and keep activations O(1) so that the
     north-star tolerances are meaningful.
+
+    populated=False (parity fixtures): every Mask2Former query ends up with nearly the same state (27 unit-gain post-norm sublayers wash the query
+    identity out), the mask logits are far from their thresholds and the network is well conditioned end to end -- the segmentation logits can be
+    held to the 1e-4 north-star tolerance -- but the panoptic post-process takes its empty branch at 256^2 / 512^2.
+    populated=True (bench.py, tests/test_populated_gpu.py): unit-variance learned queries + damped decoder sublayers keep the 100 queries distinct and a
+    class bias makes most of them void; at 512^2 19 queries pass the score test, 13 fail the area test and 6 survive, four of them fused into one
+    "floor" segment (inference.py's workload).  The price is conditioning: the masked-attention decoder thresholds ~10^7 mask logits into boolean
+    attention masks, some of them sit within 1e-4 of the threshold, and ANY two evaluations that differ in the last bits (our modes, the fp32 port
+    on CPU vs GPU) flip a few mask bits and move the class logits by 1e-3..1e-2 -- so that preset is checked on everything but the decoder logits.
     """
     if shapes is None:
         shapes = load_state_shapes()
@@ -119,16 +128,13 @@ def make_state_dict(shapes: dict | None = None, seed: int = 0) -> dict:
                 gain = 0.12 if key.startswith("downstream") else 0.3
             if leaf in ("level_embed",) or "queries_" in key or "level_embed" in key:
                 gain = 1.0
-            # Mask2Former decoder: with unit-gain sublayers the 27 post-norm residual steps wash the query identity out (every query ends up with
-            # the same class logits: all void, the panoptic post-process empty).  Unit-variance learned queries + damped sublayer outputs keep the 100
-            # queries distinct, which -- with the class bias below -- populates the post-process: at 512^2 19 queries pass the score test, 13 of
-            # them are rejected by the area test and 6 survive, four of them fused into one "floor" segment.
-            if "queries_features" in key:
+            # populated preset (see the docstring): distinct queries
+            if populated and "queries_features" in key:
                 gain = 16.0
-            if "transformer_module.decoder.layers" in key and (".out_proj." in key or ".fc2." in key):
+            if populated and "transformer_module.decoder.layers" in key and (".out_proj." in key or ".fc2." in key):
                 gain = 0.3
             t = gain * torch.randn(shape, generator=g) / (fan_in ** 0.5)
-        if key == "mask2former.class_predictor.bias":
+        if populated and key == "mask2former.class_predictor.bias":
             t[20] += 30.0   # most queries void ...
             t[0] += 8.0     # ... and the two stuff classes (wall, floor) favoured so that fused segments occur
             t[1] += 8.0

@@ -696,3 +696,55 @@ def test_gemm_skinny(M, N, K):
             ref = ref + res
         tol = 3e-3 if act & 4 else 2e-5
         assert float((out - ref).abs().max()) < tol * max(1.0, float(ref.abs().max())), (act, float((out - ref).abs().max()))
+
+
+@pytest.mark.parametrize("G,H,W,pa", [(3000, 64, 64, False), (500000, 512, 512, True), (5000, 100, 180, False), (12000, 48, 48, False),
+                                      (2000000, 512, 512, True), (1, 32, 32, False)])
+def test_raster_nosync_equals_sync_and_global_sort(G, H, W, pa):
+    """siu3r_raster_forward_nosync (no host round trip, register-resident tile sorts of all three size classes: (12000, 48, 48) puts ~5000 records
+    in a tile, the 2 M case ~4300) gives bit-identical images to the synchronising entry point with the reference-shaped global radix sort."""
+    from siu3r_b200 import _lib, ops
+    lib = _lib.load()
+    sc, view, full, campos, tx, ty = _raster_case(G, H, W, 23, pa)
+    bg = torch.tensor([0.1, 0.2, 0.3], device=DEV)
+    args = (sc["means"].to(DEV), sc["covariances"].to(DEV), sc["harmonics"].to(DEV), sc["opacities"].to(DEV), view.to(DEV), full.to(DEV),
+            campos.to(DEV), bg, tx, ty, H, W, 4)
+    lib.siu3r_raster_set_binning(0)
+    try:
+        ref = ops.raster_forward(*args, sh_layout=1)
+    finally:
+        lib.siu3r_raster_set_binning(1)
+    status = torch.zeros(4, device=DEV, dtype=torch.int32)
+    got = ops.raster_forward_nosync(*args, sh_layout=1, status=status, count_touched=True, dup_capacity=max(1 << 16, int(ref["num_rendered"] * 1.1)))
+    st = status.cpu().tolist()
+    assert st[0] == ref["num_rendered"] and st[2] == 0, st
+    for kk in ("color", "depth", "opacity", "radii", "n_touched"):
+        assert torch.equal(got[kk], ref[kk]), kk
+    # the round-1 shared-memory sort and the register-resident one order every tile identically
+    a = ops.raster_forward(*args, sh_layout=1)
+    lib.siu3r_raster_set_regsort(0)
+    try:
+        b = ops.raster_forward(*args, sh_layout=1)
+    finally:
+        lib.siu3r_raster_set_regsort(1)
+    for kk in ("color", "depth", "n_touched"):
+        assert torch.equal(a[kk], b[kk]) and torch.equal(a[kk], ref[kk]), kk
+
+
+def test_raster_nosync_flags_overflow_and_render_cuda_recovers():
+    """Too small a duplicate capacity, or a tile above 8192 records: status flag raised, nothing written out of bounds; render_cuda re-renders."""
+    from siu3r_b200 import ops
+    from siu3r_b200.renderer import render_cuda
+    G, H, W = 60000, 48, 48          # ~26 000 records per tile
+    sc, view, full, campos, tx, ty = _raster_case(G, H, W, 29, False)
+    bg = torch.zeros(3, device=DEV)
+    args = (sc["means"].to(DEV), sc["covariances"].to(DEV), sc["harmonics"].to(DEV), sc["opacities"].to(DEV), view.to(DEV), full.to(DEV),
+            campos.to(DEV), bg, tx, ty, H, W, 4)
+    ref = ops.raster_forward(*args, sh_layout=1, count_touched=False)
+    status = torch.zeros(4, device=DEV, dtype=torch.int32)
+    ops.raster_forward_nosync(*args, sh_layout=1, status=status, dup_capacity=1 << 16)
+    st = status.cpu().tolist()
+    assert st[0] == ref["num_rendered"] and (st[2] & 1) == (1 if ref["num_rendered"] > (1 << 16) else 0) and (st[2] & 2) == 2, st
+    color, depth = render_cuda(sc["extrinsics"], sc["intrinsics"], sc["near"], sc["far"], (H, W), torch.zeros(1, 3), sc["means"][None].to(DEV),
+                               sc["covariances"][None].to(DEV), sc["harmonics"][None].to(DEV), sc["opacities"][None].to(DEV))
+    assert torch.equal(color[0], ref["color"]) and torch.equal(depth[0], ref["depth"])

@@ -1,6 +1,4 @@
-"""Rectangular landscape frame (64 x 96) through SIU3RModel against the golden from the unmodified reference (tests/golden/model_S64x96.npz).
-The fixture and this test were written after the round's GPU minutes were spent and the engine has never been run at a non-square shape, so
-the test is opt-in until it has been seen green once:  SIU3R_TEST_RECT=1 python -m pytest tests/test_zz_rect_gpu.py -m gpu"""
+"""Rectangular landscape frame (64 x 96) through SIU3RModel against the golden from the unmodified reference (tests/golden/model_S64x96.npz)."""
 import json
 import os
 
@@ -8,8 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("SIU3R_TEST_RECT") != "1",
-                                                  reason="non-square shapes: first GPU run pending (set SIU3R_TEST_RECT=1)")]
+pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
@@ -19,13 +16,14 @@ def _samples(t: torch.Tensor, n=2048):
     return t[(i * 2654435761 + 12345) % t.numel()].cpu().numpy()
 
 
-def test_rectangular_frame_fp32x3_meets_north_star():
+@pytest.mark.parametrize("precision", ["h3", "fp32x3"])
+def test_rectangular_frame_meets_north_star(precision):
     from siu3r_b200 import synth
     from siu3r_b200.model import ModelCfg, SIU3RModel
     H, W = 64, 96
     z = np.load(os.path.join(GOLD, f"model_S{H}x{W}.npz"), allow_pickle=False)
     meta = json.loads(str(z["meta"]))
-    model = SIU3RModel(ModelCfg(image_size=(H, W)), precision="fp32x3")
+    model = SIU3RModel(ModelCfg(image_size=(H, W)), precision=precision)
     model.load_state_dict(synth.make_state_dict())
     model.cuda()
     img, K = synth.pair_inputs(1, 2, (H, W))
@@ -38,5 +36,7 @@ def test_rectangular_frame_fp32x3_meets_north_star():
         assert list(t.shape) == meta[name]["shape"], name
         assert np.abs(_samples(t) - z[name + "__samples"]).max() < 1e-4 * meta[name]["absmax"], name
     assert [(a["id"], a["label_id"], a["was_fused"]) for a in seg_infos[0]] == [(b["id"], b["label_id"], b["was_fused"]) for b in meta["seg_infos"][0]]
-    assert torch.bincount(g.semantic_labels.flatten().long(), minlength=22).tolist() == meta["sem_hist"]
-    assert torch.bincount(g.instance_labels.flatten().long()).tolist() == meta["inst_hist"]
+    npix = g.semantic_labels.numel()
+    sh = torch.bincount(g.semantic_labels.flatten().long(), minlength=22).tolist()
+    ih = torch.bincount(g.instance_labels.flatten().long(), minlength=len(meta["inst_hist"])).tolist()
+    assert sum(abs(a - b) for a, b in zip(sh, meta["sem_hist"])) <= 1e-4 * npix and sum(abs(a - b) for a, b in zip(ih, meta["inst_hist"])) <= 1e-4 * npix

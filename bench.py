@@ -306,6 +306,10 @@ def main():
     model.disable_cuda_graph()
     model.serial = True   # no parallel branches: per-kernel CUDA-event durations are not inflated by co-running kernels
     step()
+    torch.cuda.synchronize()
+    # The eager pass issues ~1100 launches at 30-60 us of host time each; a kernel shorter than that would be timed as host latency.  A long
+    # spin kernel in front lets the host run ahead, so that every event pair below is stamped by a GPU that never waits for the host.
+    torch.cuda._sleep(int(0.45 * 1.9e9))
     ops.PROFILE = []
     step()
     torch.cuda.synchronize()

@@ -267,8 +267,10 @@ int siu3r_im2col_nhwc_h3(const float* x, int N, int H, int W, int C, int KH, int
                          int64_t plane, void* stream);
 /* tuning / debugging aids */
 void siu3r_gemm_h3_force(int tw);
+void siu3r_gemm_h3_order(int order);   /* 0 = neighbouring CTA pairs share the token tile, 1 = they share the weight rows */
 int siu3r_gemm_h3_plan(int M, int N, int K, int M1, int* tw_out, int* tiles_out, int* rounds_out);
 void siu3r_flash_h3_debug_swap(int swap);
+void siu3r_gemm_h3_debug(int mode);   /* timing experiments only: 1 = operand pipeline without MMAs, 2 = MMAs without operand loads (garbage results) */
 
 #ifdef __cplusplus
 }

@@ -75,6 +75,8 @@ SIGNATURES = {
     "siu3r_qc_logits": (_i, [_p, _l, _i, _p, _i, _p, _i, _p, _p]),
     # h3 mode (fp32-grade results on the fp16 tensor-core path)
     "siu3r_gemm_h3_force": (None, [_i]),
+    "siu3r_gemm_h3_order": (None, [_i]),
+    "siu3r_gemm_h3_debug": (None, [_i]),
     "siu3r_gemm_h3_plan": (_i, [_i, _i, _i, _i, _p, _p, _p]),
     "siu3r_split_h3": (_i, [_p, _l, _l, _i, _p, _l, _l, _i, _p]),
     "siu3r_merge_h3": (_i, [_p, _l, _l, _l, _i, _p, _l, _p]),

@@ -34,6 +34,16 @@ static inline __host__ __device__ int64_t ceil_div_i64(int64_t a, int64_t b) { r
 static inline __host__ __device__ int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline __host__ __device__ size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// cudaFuncSetAttribute (the opt-in to > 48 KB of dynamic shared memory) is PER DEVICE: once-per-process flags are kept per device index.
+static inline bool siu3r_first_use_on_device(bool (&seen)[64]) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    dev &= 63;
+    if (seen[dev]) return false;
+    seen[dev] = true;
+    return true;
+}
+
 // Every launch of one of OUR kernels bumps this counter (bench.py reports it as gpu_launches).
 extern "C" void siu3r_note_launch(int n);
 

@@ -83,7 +83,7 @@ flash_h3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * FH_V_BYTES);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_COUNT);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // (shuffle broadcast: provably warp-uniform)
     const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
     const int q0 = qt * FH_BM;
     // The innermost (key) coordinate of a V^T box must be 16-byte aligned.  When image b's keys start at an unaligned column (vt_batch_cols =
@@ -120,68 +120,82 @@ flash_h3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t tmem_O = tmem_base + 3 * FH_BN;
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
+        // ===================== TMA producer (whole warp walks the loop, one elected lane issues: uniform-datapath operands) =====================
+        if (elect_one_sync()) {
             mbar_expect_tx(&bars[B_Q], FH_Q_BYTES);
             tma_load_4d(&tmQ, &bars[B_Q], sQ, p.q_col0 + h * FH_D, q0, b, 0);
-            for (int t = 0; t < ntiles; ++t) {
-                const int buf = t & 1;
-                const uint32_t use = (uint32_t)t >> 1;
-                mbar_wait(&bars[B_KEMPTY + buf], (use & 1) ^ 1);
+        }
+        __syncwarp();
+        for (int t = 0; t < ntiles; ++t) {
+            const int buf = t & 1;
+            const uint32_t use = (uint32_t)t >> 1;
+            mbar_wait(&bars[B_KEMPTY + buf], (use & 1) ^ 1);
+            if (elect_one_sync()) {
                 mbar_expect_tx(&bars[B_KFULL + buf], FH_K_BYTES);
                 tma_load_4d(&tmK, &bars[B_KFULL + buf], sK + buf * FH_K_BYTES, p.k_col0 + h * FH_D, t * FH_BN - kshift, b, 0);
-                mbar_wait(&bars[B_VFREE + buf], (use & 1) ^ 1);      // P V of tile t-2 has read this V buffer
-                mbar_expect_tx(&bars[B_VFULL + buf], FH_V_BYTES);
-                tma_load_3d(&tmVt, &bars[B_VFULL + buf], sV + buf * FH_V_BYTES,
-                            (int)vcol0 + t * FH_BN - kshift, (p.vt_batch_cols ? h : b * p.H + h) * FH_D, 0);
             }
+            __syncwarp();
+            mbar_wait(&bars[B_VFREE + buf], (use & 1) ^ 1);      // P V of tile t-2 has read this V buffer
+            if (elect_one_sync()) {
+                mbar_expect_tx(&bars[B_VFULL + buf], FH_V_BYTES);
+                tma_load_3d(&tmVt, &bars[B_VFULL + buf], sV + buf * FH_V_BYTES, (int)vcol0 + t * FH_BN - kshift,
+                            (p.vt_batch_cols ? h : b * p.H + h) * FH_D, 0);
+            }
+            __syncwarp();
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer: S(t+1) is issued before P(t) V(t) =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_f16(FH_BM, FH_BN);   // S: N = 64 keys; O: N = 64 = head dim
-            mbar_wait(&bars[B_Q], 0);
-            const uint32_t qh = smem_u32(sQ), ql = qh + FH_BM * 128;
-            auto issue_s = [&](int t) {
-                const int buf = t & 1, sb = t % 3;
-                const uint32_t use = (uint32_t)t >> 1;
-                mbar_wait(&bars[B_KFULL + buf], use & 1);
-                mbar_wait(&bars[B_SFREE + sb], (((uint32_t)t / 3) & 1) ^ 1);   // P(t-3) (aliasing this S buffer) has been consumed
-                tc_fence_after();
-                const uint32_t kh = smem_u32(sK + buf * FH_K_BYTES), kl = kh + FH_BN * 128;
-                const uint32_t tS = tmem_base + (uint32_t)(sb * FH_BN);
+        // ===================== MMA issuer: S(t+1) is issued before P(t) V(t); whole warp, one elected lane issues =====================
+        constexpr uint32_t idesc = make_idesc_f16(FH_BM, FH_BN);   // S: N = 64 keys; O: N = 64 = head dim
+        mbar_wait(&bars[B_Q], 0);
+        const uint64_t dQh = make_smem_desc(smem_u32(sQ)), dQl = make_smem_desc(smem_u32(sQ) + FH_BM * 128);
+        auto issue_s = [&](int t) {
+            const int buf = t & 1, sb = t % 3;
+            const uint32_t use = (uint32_t)t >> 1;
+            mbar_wait(&bars[B_KFULL + buf], use & 1);
+            mbar_wait(&bars[B_SFREE + sb], (((uint32_t)t / 3) & 1) ^ 1);   // P(t-3) (aliasing this S buffer) has been consumed
+            tc_fence_after();
+            const uint32_t kh = smem_u32(sK + buf * FH_K_BYTES);
+            const uint64_t dKh = make_smem_desc(kh), dKl = make_smem_desc(kh + FH_BN * 128);
+            const uint32_t tS = tmem_base + (uint32_t)(sb * FH_BN);
+            if (elect_one_sync()) {
 #pragma unroll
                 for (int ks = 0; ks < FH_D / 16; ++ks) {
-                    const uint32_t koff = ks * 32;
-                    umma_f16(tS, make_smem_desc(ql + koff), make_smem_desc(kh + koff), idesc, ks != 0);
-                    umma_f16(tS, make_smem_desc(qh + koff), make_smem_desc(kl + koff), idesc, 1u);
-                    umma_f16(tS, make_smem_desc(qh + koff), make_smem_desc(kh + koff), idesc, 1u);
+                    const uint64_t ko = (uint64_t)(ks * 2);     // 32 bytes per k-step in the descriptor's 16-byte units
+                    umma_f16(tS, dQl + ko, dKh + ko, idesc, ks != 0);
+                    umma_f16(tS, dQh + ko, dKl + ko, idesc, 1u);
+                    umma_f16(tS, dQh + ko, dKh + ko, idesc, 1u);
                 }
                 umma_commit(&bars[B_KEMPTY + buf]);   // K buffer reusable
                 umma_commit(&bars[B_SFULL + sb]);     // S ready
-            };
-            issue_s(0);
-            for (int t = 0; t < ntiles; ++t) {
-                if (t + 1 < ntiles) issue_s(t + 1);
-                const int buf = t & 1, sb = t % 3;
-                const uint32_t use = (uint32_t)t >> 1;
-                mbar_wait(&bars[B_VFULL + buf], use & 1);
-                mbar_wait(&bars[B_PFULL + sb], ((uint32_t)t / 3) & 1);   // P written (and, if needed, O rescaled) by the softmax warps
-                tc_fence_after();
-                const uint32_t vh = smem_u32(sV + buf * FH_V_BYTES), vl = vh + FH_D * 128;
-                const uint32_t tPh = tmem_base + (uint32_t)(sb * FH_BN), tPl = tPh + 32;
+            }
+            __syncwarp();
+        };
+        issue_s(0);
+        for (int t = 0; t < ntiles; ++t) {
+            if (t + 1 < ntiles) issue_s(t + 1);
+            const int buf = t & 1, sb = t % 3;
+            const uint32_t use = (uint32_t)t >> 1;
+            mbar_wait(&bars[B_VFULL + buf], use & 1);
+            mbar_wait(&bars[B_PFULL + sb], ((uint32_t)t / 3) & 1);   // P written (and, if needed, O rescaled) by the softmax warps
+            tc_fence_after();
+            const uint32_t vh = smem_u32(sV + buf * FH_V_BYTES);
+            const uint64_t dVh = make_smem_desc(vh), dVl = make_smem_desc(vh + FH_D * 128);
+            const uint32_t tPh = tmem_base + (uint32_t)(sb * FH_BN), tPl = tPh + 32;
+            if (elect_one_sync()) {
 #pragma unroll
                 for (int ks = 0; ks < FH_BN / 16; ++ks) {
-                    const uint32_t koff = ks * 32;
-                    umma_f16_ts(tmem_O, tPl + ks * 8, make_smem_desc(vh + koff), idesc, (t | ks) != 0);
-                    umma_f16_ts(tmem_O, tPh + ks * 8, make_smem_desc(vl + koff), idesc, 1u);
-                    umma_f16_ts(tmem_O, tPh + ks * 8, make_smem_desc(vh + koff), idesc, 1u);
+                    const uint64_t ko = (uint64_t)(ks * 2);
+                    umma_f16_ts(tmem_O, tPl + ks * 8, dVh + ko, idesc, (t | ks) != 0);
+                    umma_f16_ts(tmem_O, tPh + ks * 8, dVl + ko, idesc, 1u);
+                    umma_f16_ts(tmem_O, tPh + ks * 8, dVh + ko, idesc, 1u);
                 }
                 umma_commit(&bars[B_VFREE + buf]);    // V buffer ...
                 umma_commit(&bars[B_SFREE + sb]);     // ... and the S/P buffer reusable once these MMAs are done
             }
-            umma_commit(&bars[B_OFULL]);
+            __syncwarp();
         }
+        if (elect_one_sync()) umma_commit(&bars[B_OFULL]);
+        __syncwarp();
     } else {
         // ===================== softmax / epilogue warps: thread = one query row =====================
         const int qd = warp & 3;                 // TMEM lane quarter

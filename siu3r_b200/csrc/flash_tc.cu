@@ -173,7 +173,7 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * FT_V_BYTES);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_COUNT);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // (shuffle broadcast: provably warp-uniform)
     const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
     const int q0 = qt * FT_BM;
     // TMA needs a 16-byte aligned start in the innermost (key) dimension of V^T.  When image b's keys start at an unaligned column
@@ -476,11 +476,9 @@ int siu3r_flash_attn_tc(const float* Q, int64_t q_bs, int64_t q_ts, int q_width,
     p.B = B; p.H = H; p.Nq = Nq; p.Nk = Nk; p.q_col0 = q_col0; p.k_col0 = k_col0;
     p.scale_log2e = scale * 1.4426950408889634f;
     p.O = O; p.o_bs = o_bs; p.o_ts = o_ts; p.round_out = round_out; p.vt_batch_cols = vt_batch_cols;
-    static bool attr = false;
-    if (!attr) {
+    static bool attr[64] = {false};
+    if (siu3r_first_use_on_device(attr))
         SIU3R_CUDA_CHECK(cudaFuncSetAttribute(flash_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM));
-        attr = true;
-    }
     dim3 grid(ceil_div(Nq, FT_BM), H, B);
     flash_tc_kernel<<<grid, FT_THREADS, FT_SMEM, stream>>>(mq, mk, mv, p);
     SIU3R_LAUNCH_CHECK();

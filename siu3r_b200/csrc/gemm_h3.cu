@@ -55,6 +55,9 @@ struct H3Params {
     int64_t ldr;               // fp32 residual pitch
     const long long* rope_pos; const float* rope_tab; int rope_cols;
     int vt_col0; int64_t vt_ld, vt_plane;
+    int dbg_mode;              // timing experiments only (results are garbage): 1 = TMA pipeline without MMAs, 2 = MMAs without TMA loads
+    int order;                 // tile order: 0 = weight pair fastest (neighbouring CTA pairs share the token tile), 1 = token tile fastest (share the weights)
+    int ttiles0, ttiles1;      // token tiles of problem 0 / 1
     float lo_scale;            // factor on the lo plane of split outputs: 2^11 (GEMM operands) or 1 (attention operands, see flash_h3.cu)
     // conv mode
     int conv, H, W, Cin, KW, pad_h, pad_w, tiles_w, tiles_per_img, cblocks;
@@ -76,7 +79,7 @@ struct Frag {            // where the 32 tokens of one epilogue fragment live: t
 };
 
 template <int ACTK, bool ROPE, bool RES, bool SPLIT>
-__device__ __forceinline__ void epi_chunk(const float (&v)[32], const Frag& f, int lane, int n, bool n_ok, float bias, int axis, int mrow, int jmax,
+__device__ __forceinline__ void epi_chunk(float (&v)[32], const Frag& f, int lane, int n, bool n_ok, float bias, int axis, int mrow, int jmax,
                                           const H3Params& p, const H3Problem& pr) {
     float r[32];
     if (RES) {
@@ -92,9 +95,10 @@ __device__ __forceinline__ void epi_chunk(const float (&v)[32], const Frag& f, i
         pos_l = lane < jmax ? p.rope_pos[(int64_t)(mrow + lane) * 2 + axis] : 0;   // lane j holds the position of token j of the fragment
         tab = p.rope_tab + (lane & 15) * 2;
     }
+    // Phase 1 (branch free: the warp stays converged, so the RoPE shuffles compile to plain SHFL -- with the stores in the same loop ptxas wraps
+    // every shuffle into a WARPSYNC.COLLECTIVE sequence and the fused qkv projection ran at half speed): all arithmetic, results left in v[].
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-        const int h = j >> 4;
         float x = v[j] * p.alpha + bias;
         if (ACTK == ACT_GELU) x = gelu_erf(x);
         if (ACTK == ACT_RELU) x = fmaxf(x, 0.0f);
@@ -105,17 +109,25 @@ __device__ __forceinline__ void epi_chunk(const float (&v)[32], const Frag& f, i
             x = (lane & 16) ? x * cs.x + y * cs.y : x * cs.x - y * cs.y;
         }
         if (RES) x += r[j];
-        if ((j & 15) < f.nv[h] && n_ok) {
-            const int64_t row = f.rb[h] + (j & 15);
-            if (SPLIT) {
+        v[j] = x;
+    }
+    // Phase 2: stores (one output row = 32 consecutive n of the warp: a 128-byte line in fp32, 64 bytes per plane as a plane pair)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        if (f.nv[h] <= 0 || !n_ok) continue;
+        if (SPLIT) {
+            __half* d = pr.Ch + f.rb[h] * p.ldh + n;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
                 __half hi, lo;
-                h3_split_s(x, p.lo_scale, hi, lo);
-                __half* d = pr.Ch + row * p.ldh + n;
-                d[0] = hi;
-                d[p.plane_h] = lo;
-            } else {
-                pr.C[row * p.ldc + n] = x;
+                h3_split_s(v[h * 16 + i], p.lo_scale, hi, lo);
+                if (i < f.nv[h]) { d[(int64_t)i * p.ldh] = hi; d[(int64_t)i * p.ldh + p.plane_h] = lo; }
             }
+        } else {
+            float* d = pr.C + f.rb[h] * p.ldc + n;
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                if (i < f.nv[h]) d[(int64_t)i * p.ldc] = v[h * 16 + i];
         }
     }
 }
@@ -232,7 +244,9 @@ gemm_h3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
     uint64_t* tempty_bar = tfull_bar + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index through a shuffle broadcast: tells the compiler it is warp-uniform (the role dispatch and every loop bound derived from it stay on
+    // the uniform datapath, and the epilogue's shuffles compile without the WARPSYNC.COLLECTIVE fallback)
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
     const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
@@ -263,16 +277,18 @@ gemm_h3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
     const uint32_t x_off = nbuf == 2 ? 128u : 256u;             // column distance hh -> x inside one accumulator set
 
     if (warp == 0) {
-        // ===================== TMA producer (both CTAs) =====================
-        if (lane == 0) {
+        // ===================== TMA producer (both CTAs; whole warp walks the loop, one elected lane issues: see the MMA warp) =====================
+        {
             int stage = 0; uint32_t phase = 0;
             for (int u = cluster_id; u < num_tiles; u += num_clusters) {
                 const int g = u >= grp.tiles0;
                 const int tl = g ? u - grp.tiles0 : u;
                 const CUtensorMap* mw = g ? &tmW1 : &tmW;
                 const CUtensorMap* mx = g ? &tmX1 : &tmX;
-                const int n0 = (tl % w_pairs) * 2 * W_ROWS + (int)rank * W_ROWS;    // this CTA's 128 weight rows
-                const int tt = tl / w_pairs;
+                const int tcount = g ? p.ttiles1 : p.ttiles0;
+                const int wi = p.order ? tl / tcount : tl % w_pairs;
+                const int tt = p.order ? tl % tcount : tl / w_pairs;
+                const int n0 = wi * 2 * W_ROWS + (int)rank * W_ROWS;    // this CTA's 128 weight rows
                 int m0 = tt * tw + (int)rank * xrows, img = 0, h0 = 0, w0 = 0;       // this CTA's half of the token tile
                 if (p.conv) {
                     img = tt / p.tiles_per_img;
@@ -285,23 +301,33 @@ gemm_h3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                     uint8_t* sW = smem + stage * stage_bytes;
                     uint8_t* sX = sW + W_BYTES;
                     const uint32_t lead_full = mapa_to_cta(smem_u32(&full_bar[stage]), 0);
-                    if (leader) mbar_expect_tx(&full_bar[stage], stage_tx);
-                    if (p.conv) {
-                        const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
-                        const int kh = tap / p.KW, kw = tap - kh * p.KW;
-                        tma2_load_3d(mw, lead_full, sW, tap * p.Cin + cb * BKH, n0, 0);
-                        tma2_load_5d(mx, lead_full, sX, cb * BKH, w0 + kw - p.pad_w, h0 + kh - p.pad_h, img, 0);
-                    } else {
-                        tma2_load_3d(mw, lead_full, sW, kb * BKH, n0, 0);
-                        tma2_load_3d(mx, lead_full, sX, kb * BKH, m0, 0);
+                    if (elect_one_sync()) {
+                        if (p.dbg_mode == 2) {
+                            if (leader) mbar_arrive(&full_bar[stage]);
+                        } else {
+                            if (leader) mbar_expect_tx(&full_bar[stage], stage_tx);
+                            if (p.conv) {
+                                const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
+                                const int kh = tap / p.KW, kw = tap - kh * p.KW;
+                                tma2_load_3d(mw, lead_full, sW, tap * p.Cin + cb * BKH, n0, 0);
+                                tma2_load_5d(mx, lead_full, sX, cb * BKH, w0 + kw - p.pad_w, h0 + kh - p.pad_h, img, 0);
+                            } else {
+                                tma2_load_3d(mw, lead_full, sW, kb * BKH, n0, 0);
+                                tma2_load_3d(mx, lead_full, sX, kb * BKH, m0, 0);
+                            }
+                        }
                     }
+                    __syncwarp();
                     if (++stage == nstages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer (leader CTA, one lane) =====================
-        if (leader && lane == 0) {
+        // ===================== MMA issuer (leader CTA) =====================
+        // The WHOLE warp walks the loop (warp-uniform control flow and operands: descriptors live in uniform registers); only the tcgen05
+        // instructions themselves are issued by one elected lane.  Issuing from inside an `if (lane == 0)` region instead makes ptxas wrap every
+        // MMA into an elect / R2UR-broadcast / branch loop (~20 dependent instructions, ~100 clocks per MMA: more than a 256 x 128 x 16 MMA takes).
+        if (leader) {
             const uint32_t idesc = make_idesc_f16(2 * W_ROWS, tw);
             int stage = 0; uint32_t phase = 0;
             int it = 0;
@@ -316,21 +342,24 @@ gemm_h3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     const uint32_t sWh = smem_u32(smem + stage * stage_bytes);
-                    const uint32_t sWl = sWh + W_PLANE_BYTES;
-                    const uint32_t sXh = sWh + W_BYTES;
-                    const uint32_t sXl = sXh + (uint32_t)x_plane_bytes;
+                    const uint64_t dWh = make_smem_desc(sWh), dWl = make_smem_desc(sWh + W_PLANE_BYTES);
+                    const uint64_t dXh = make_smem_desc(sWh + W_BYTES), dXl = make_smem_desc(sWh + W_BYTES + (uint32_t)x_plane_bytes);
+                    if (elect_one_sync()) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint32_t koff = k * 32;   // 16 fp16 per k-step
-                        const uint32_t acc = (kb | k) != 0;
-                        umma2_f16(acc_x, make_smem_desc(sWl + koff), make_smem_desc(sXh + koff), idesc, acc);
-                        umma2_f16(acc_x, make_smem_desc(sWh + koff), make_smem_desc(sXl + koff), idesc, 1u);
-                        umma2_f16(acc_hh, make_smem_desc(sWh + koff), make_smem_desc(sXh + koff), idesc, acc);
+                        for (int k = 0; k < (p.dbg_mode == 1 ? 0 : 4); ++k) {
+                            const uint64_t ko = (uint64_t)(k * 2);    // 16 fp16 = 32 bytes per k-step, in the descriptor's 16-byte units
+                            const uint32_t acc = (kb | k) != 0;
+                            umma2_f16(acc_x, dWl + ko, dXh + ko, idesc, acc);
+                            umma2_f16(acc_x, dWh + ko, dXl + ko, idesc, 1u);
+                            umma2_f16(acc_hh, dWh + ko, dXh + ko, idesc, acc);
+                        }
+                        umma2_commit_mc(&empty_bar[stage]);
                     }
-                    umma2_commit_mc(&empty_bar[stage]);
+                    __syncwarp();
                     if (++stage == nstages) { stage = 0; phase ^= 1; }
                 }
-                umma2_commit_mc(&tfull_bar[buf]);
+                if (elect_one_sync()) umma2_commit_mc(&tfull_bar[buf]);
+                __syncwarp();
             }
         }
     } else {
@@ -347,8 +376,10 @@ gemm_h3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
             const uint32_t use = nbuf == 2 ? ((uint32_t)it >> 1) : (uint32_t)it;
             const int g = u >= grp.tiles0;
             const int tl = g ? u - grp.tiles0 : u;
-            const int n_cta = (tl % w_pairs) * 2 * W_ROWS + (int)rank * W_ROWS;
-            const int tt = tl / w_pairs;
+            const int tcount = g ? p.ttiles1 : p.ttiles0;
+            const int wi = p.order ? tl / tcount : tl % w_pairs;
+            const int tt = p.order ? tl % tcount : tl / w_pairs;
+            const int n_cta = wi * 2 * W_ROWS + (int)rank * W_ROWS;
             // (static member selection: a runtime index into the kernel-parameter struct would force a local copy of it)
             const H3Problem prob{g ? grp.prob[1].C : grp.prob[0].C, g ? grp.prob[1].Ch : grp.prob[0].Ch, g ? grp.prob[1].bias : grp.prob[0].bias,
                                  g ? grp.prob[1].residual : grp.prob[0].residual, g ? grp.prob[1].M : grp.prob[0].M,
@@ -409,6 +440,8 @@ __global__ void __launch_bounds__(256) merge_h3_kernel(const __half* __restrict_
 // ------------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------------
+int g_dbg_mode = 0;
+int g_order = 0;      // tuning aid: tile order (see H3Params::order)
 int g_force_tw = 0;   // tuning aid (tools/gemm_sweep.py): > 0 = use this token tile width wherever it is legal
 
 // Token tile width for (M [+ M1]) tokens x N weight rows x K.  Cost model per CTA pair (clocks): rounds x (k-blocks x max(tensor time, operand
@@ -476,6 +509,8 @@ extern "C" {
 
 // tuning aid: 0 = cost model, otherwise the token tile width to use (multiple of 16 / 32 for convs, <= 256)
 void siu3r_gemm_h3_force(int tw) { g_force_tw = tw; }
+void siu3r_gemm_h3_order(int order) { g_order = order ? 1 : 0; }
+void siu3r_gemm_h3_debug(int mode) { g_dbg_mode = mode; }   // timing experiments: 1 = TMA only, 2 = MMA only (outputs are garbage)
 
 // Host-only view of the tile planner: token tile width, number of 256 x tw tiles and rounds over the 74 resident CTA pairs.
 int siu3r_gemm_h3_plan(int M, int N, int K, int M1, int* tw_out, int* tiles_out, int* rounds_out) {
@@ -560,6 +595,7 @@ int siu3r_gemm_h3(int ngroups, const int* M_host, int N, int K, const void* cons
                                 vt_cols_host ? vt_cols_host[s] : 0};
     }
     grp.tiles0 = w_pairs * ceil_div(M0, tw);
+    p.ttiles0 = ceil_div(M0, tw); p.ttiles1 = ngroups == 2 ? ceil_div(M1, tw) : 1; p.order = g_order; p.dbg_mode = g_dbg_mode;
     const int tiles = grp.tiles0 + (ngroups == 2 ? w_pairs * ceil_div(M1, tw) : 0);
     return launch_h3(mw[0], mx[0], mw[1], mx[1], p, grp, w_pairs, tiles, stream);
 }
@@ -597,6 +633,7 @@ int siu3r_conv2d_h3(int Nimg, int H, int W, int Cin, int Cout, int KH, int KW, i
     grp.prob[0] = H3Problem{y, (__half*)yh, bias, residual, Nimg, nullptr, 0};
     grp.prob[1] = grp.prob[0];
     grp.tiles0 = w_pairs * Nimg * p.tiles_per_img;
+    p.ttiles0 = Nimg * p.tiles_per_img; p.ttiles1 = 1; p.order = g_order;
     return launch_h3(mw, mx, mw, mx, p, grp, w_pairs, grp.tiles0, stream);
 }
 

@@ -355,7 +355,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* acc_bar = empty_bar + C_::STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // (shuffle broadcast: provably warp-uniform)
     const int n0 = blockIdx.y * BN;
     long long* dbg = (p.dbg && blockIdx.y == 0 && blockIdx.x < 16) ? p.dbg + blockIdx.x * 8 : nullptr;
     if (dbg && threadIdx.x == 0) dbg[0] = clock64();
@@ -520,7 +520,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
     constexpr int A_BYTES = BM * BK * 4;
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // (shuffle broadcast: provably warp-uniform)
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
     const int n0 = blockIdx.y * TC2_BN;
@@ -841,7 +841,7 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     uint64_t* tempty_bar = tfull_bar + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // (shuffle broadcast: provably warp-uniform)
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
     const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
@@ -961,7 +961,10 @@ template <bool UP2X = false>
 int launch_tc3(const CUtensorMap& w, const CUtensorMap& x, const CUtensorMap& w1, const CUtensorMap& x1, const GemmParams& p, const Tc3Group& grp,
                int w_pairs, int num_tiles, int tw, cudaStream_t stream) {
     using C_ = Tc3;
-    static int max_clusters = 0;
+    static int max_clusters_dev[64] = {0};
+    int dev_ = 0;
+    SIU3R_CUDA_CHECK(cudaGetDevice(&dev_));
+    int& max_clusters = max_clusters_dev[dev_ & 63];
     if (max_clusters == 0) {
         SIU3R_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc3_kernel<UP2X>, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM_BYTES));
         cudaLaunchConfig_t cfg = {};
@@ -983,11 +986,8 @@ int launch_tc3(const CUtensorMap& w, const CUtensorMap& x, const CUtensorMap& w1
 }
 
 int launch_tc2(const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, dim3 grid, cudaStream_t stream) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        SIU3R_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM_BYTES));
-        attr_set = true;
-    }
+    static bool attr_set[64] = {false};
+    if (siu3r_first_use_on_device(attr_set)) SIU3R_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM_BYTES));
     gemm_tc2_kernel<<<grid, NUM_THREADS, TC2_SMEM_BYTES, stream>>>(a, b, p);
     SIU3R_LAUNCH_CHECK();
     siu3r_note_launch(1);
@@ -1040,11 +1040,9 @@ template <int BN, int NSPLIT, bool DEEP = false>
 int launch(const CUtensorMap& a, const CUtensorMap& alo, const CUtensorMap& b, const CUtensorMap& blo, const GemmParams& p, dim3 grid,
            cudaStream_t stream) {
     using C_ = Cfg<BN, NSPLIT, DEEP>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {false};
+    if (siu3r_first_use_on_device(attr_set))
         SIU3R_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, NSPLIT, DEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM_BYTES));
-        attr_set = true;
-    }
     gemm_tc_kernel<BN, NSPLIT, DEEP><<<grid, NUM_THREADS, C_::SMEM_BYTES, stream>>>(a, alo, b, blo, p);
     SIU3R_LAUNCH_CHECK();
     siu3r_note_launch(1);

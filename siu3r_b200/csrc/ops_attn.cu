@@ -542,11 +542,10 @@ int siu3r_flash_attn_d64(const float* Q, int64_t q_bs, int64_t q_ts, const float
     SIU3R_REQUIRE(precision == 1 || precision == 3);
     SIU3R_REQUIRE(k_ts % 4 == 0 && v_ts % 4 == 0 && k_bs % 4 == 0 && v_bs % 4 == 0 && o_ts % 2 == 0 && o_bs % 2 == 0);
     SIU3R_REQUIRE(((uintptr_t)K & 15) == 0 && ((uintptr_t)V & 15) == 0 && ((uintptr_t)O & 7) == 0);
-    static bool attr = false;
-    if (!attr) {
+    static bool attr[64] = {false};
+    if (siu3r_first_use_on_device(attr)) {
         SIU3R_CUDA_CHECK(cudaFuncSetAttribute(flash_attn_d64_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
         SIU3R_CUDA_CHECK(cudaFuncSetAttribute(flash_attn_d64_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
-        attr = true;
     }
     dim3 grid(ceil_div(Nq, FA_BM), H, B);
     if (precision == 1)

@@ -461,11 +461,8 @@ int siu3r_gemm_skinny(int M, int N, int K, const float* A, int64_t lda, const fl
     cudaStream_t stream = (cudaStream_t)stream_;
     SIU3R_REQUIRE(M > 0 && N > 0 && K > 0 && A && W && C);
     constexpr int smem = SK_WARPS * 2 * SK_T * (SK_T + 1) * 4;   // 67.6 KB (staging) >= 32 KB (partials)
-    static bool attr = false;
-    if (!attr) {
-        SIU3R_CUDA_CHECK(cudaFuncSetAttribute(gemm_skinny_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr = true;
-    }
+    static bool attr[64] = {false};
+    if (siu3r_first_use_on_device(attr)) SIU3R_CUDA_CHECK(cudaFuncSetAttribute(gemm_skinny_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     dim3 grid(ceil_div(N, SK_T), ceil_div(M, SK_T));
     gemm_skinny_kernel<<<grid, SK_WARPS * 32, smem, stream>>>(M, N, K, A, lda, W, ldw, C, ldc, bias, residual, ldr, act, alpha);
     SIU3R_LAUNCH_CHECK();

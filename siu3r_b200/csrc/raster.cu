@@ -1018,11 +1018,10 @@ int siu3r_raster_forward(int G, int H, int W, int sh_degree, int sh_coeffs, int 
     const int ntiles = gx * gy;
     if (binned && (size_t)ntiles * 8 > 200 * 1024) binned = false;        // per-CTA tile histograms must fit shared memory (<= 25600 tiles)
     if (binned) {
-        static bool attr_bin = false;
-        if (!attr_bin) {
+        static bool attr_bin[64] = {false};
+        if (siu3r_first_use_on_device(attr_bin)) {
             SIU3R_CUDA_CHECK(cudaFuncSetAttribute(bin_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
             SIU3R_CUDA_CHECK(cudaFuncSetAttribute(bin_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            attr_bin = true;
         }
         bin_count_kernel<<<ceil_div(G, BIN_CHUNK), BIN_THREADS, (size_t)ntiles * 4, stream>>>(G, gx, ntiles, radii, w.rects, w.tile_counts);
         tile_scan_kernel<<<1, 1024, 0, stream>>>(w.tile_counts, ntiles, w.ranges, w.tile_cursors, w.total, (uint32_t)dup_capacity, nullptr);
@@ -1038,11 +1037,8 @@ int siu3r_raster_forward(int G, int H, int W, int sh_degree, int sh_coeffs, int 
             binned = false;                                   // big tiles: the O(n log^2 n) shared-memory sort loses to the global radix sort
             SIU3R_CUDA_CHECK(cudaMemsetAsync(w.ranges, 0, sizeof(uint2) * gx * gy, stream));
         } else if (D > 0) {
-            static bool attr = false;
-            if (!attr) {
-                SIU3R_CUDA_CHECK(cudaFuncSetAttribute(tile_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_CAP * 8));
-                attr = true;
-            }
+            static bool attr[64] = {false};
+            if (siu3r_first_use_on_device(attr)) SIU3R_CUDA_CHECK(cudaFuncSetAttribute(tile_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_CAP * 8));
             bin_scatter_kernel<<<ceil_div(G, BIN_CHUNK), BIN_THREADS, (size_t)ntiles * 8, stream>>>(G, gx, ntiles, radii, w.depths, w.rects,
                                                                                                   w.tile_cursors, w.keys, nullptr);
             if (g_regsort) {

@@ -70,12 +70,28 @@ class _TolerantPickle:
     HIGHEST_PROTOCOL, DEFAULT_PROTOCOL = _pickle.HIGHEST_PROTOCOL, _pickle.DEFAULT_PROTOCOL
     PickleError, PicklingError, UnpicklingError, Pickler = _pickle.PickleError, _pickle.PicklingError, _pickle.UnpicklingError, _pickle.Pickler
 
+    # Only what a tensor checkpoint needs is ever resolved to a real object; EVERY other global a pickle names -- the reference's config dataclasses,
+    # Lightning callbacks, or something hostile -- becomes an inert _Placeholder subclass (never imported, never called with side effects).
+    _SAFE_MODULES = ("torch._utils", "torch.storage", "torch._tensor", "torch.serialization", "collections", "numpy.core.multiarray",
+                     "numpy._core.multiarray", "numpy", "_codecs")
+    _SAFE_NAMES = {("torch", n) for n in ("FloatStorage", "HalfStorage", "BFloat16Storage", "DoubleStorage", "LongStorage", "IntStorage", "ShortStorage",
+                                          "CharStorage", "ByteStorage", "BoolStorage", "Size", "device", "dtype", "Tensor", "float32", "float16", "bfloat16",
+                                          "float64", "int64", "int32", "int16", "int8", "uint8", "bool")}
+    _SAFE_NUMPY = ("dtype", "ndarray", "_reconstruct", "scalar", "float32", "float64", "int64", "int32", "bool_")
+
     class Unpickler(_pickle.Unpickler):
         def find_class(self, module, name):
-            try:
-                return super().find_class(module, name)
-            except (ImportError, AttributeError):
-                return type(name, (_Placeholder,), {"__module__": module})
+            T = _TolerantPickle
+            ok = (module, name) in T._SAFE_NAMES or (module in T._SAFE_MODULES and not name.startswith("__") and
+                                                      (not module.startswith("numpy") or name in T._SAFE_NUMPY) and
+                                                      (module != "_codecs" or name == "encode") and
+                                                      (module != "collections" or name == "OrderedDict"))
+            if ok:
+                try:
+                    return super().find_class(module, name)
+                except (ImportError, AttributeError):
+                    pass
+            return type(name, (_Placeholder,), {"__module__": module})
 
 
 def load_checkpoint(path) -> dict:

@@ -104,10 +104,20 @@ class SIU3RModel:
         return self
 
     def cuda(self, device=None):
-        self.dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        """Pack the weights onto `device` (default: the current CUDA device).  Every later call runs under torch.cuda.device(self.dev), so kernels
+        are launched on that device's current stream whatever the caller's current device is."""
+        if isinstance(device, torch.device):
+            device = device.index
+        dev = torch.device("cuda", torch.cuda.current_device() if device is None else int(device))
+        if self._ready and dev == getattr(self, "dev", None):
+            return self
         if self._sd is None:
             raise RuntimeError("load_state_dict() first: this engine has no random init of its own")
-        self._pack()
+        self.dev = dev
+        self._cache, self._graphs = {}, {}
+        self._streams, self._seg_stream = None, None
+        with torch.cuda.device(self.dev):
+            self._pack()
         return self
 
     def __call__(self, *a, **k):
@@ -228,8 +238,7 @@ class SIU3RModel:
         m.cls = P.linear("mask2former.class_predictor")
         w.m2f = m
         self.w = w
-        self._sd = None  # raw tensors no longer needed
-        self._ready = True
+        self._ready = True   # (the caller's state_dict stays referenced so that .cuda(other_device) can re-pack)
 
     # ---- shape-dependent constants (host-built once per image size) -------------------------------------------------
     def _consts(self, B: int, S0: int, S1: int, V: int = 2):
@@ -1018,6 +1027,11 @@ class SIU3RModel:
         """Enqueue the device part of forward() without waiting for it and return a handle for forward_finish().  With
         enable_cuda_graph() every `slot` has its own captured graph, static buffers and stream, so the forwards of consecutive pairs
         overlap on the GPU (serving.PairPipeline, bench.py): slot s may be re-submitted once its previous handle has been finished."""
+        assert self._ready, "call load_state_dict(...).cuda() first"
+        with torch.cuda.device(self.dev):
+            return self._forward_async(context_views_images, context_views_intrinsics, slot)
+
+    def _forward_async(self, context_views_images, context_views_intrinsics, slot):
         imgs = context_views_images
         B, V, S0, S1 = self._check_inputs(imgs)
         cur = torch.cuda.current_stream()
@@ -1058,6 +1072,10 @@ class SIU3RModel:
     @torch.no_grad()
     def forward_finish(self, handle, enable_query_class_logit_lift=False):
         """Second half of forward(): waits for the device part of `handle` and runs the panoptic post-process (host decisions)."""
+        with torch.cuda.device(self.dev):
+            return self._forward_finish(handle, enable_query_class_logit_lift)
+
+    def _forward_finish(self, handle, enable_query_class_logit_lift):
         outs, done, (B, V, S0, S1) = handle
         if done is not None:
             torch.cuda.current_stream().wait_event(done)

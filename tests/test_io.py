@@ -203,3 +203,22 @@ def test_load_checkpoint_tolerates_pickled_reference_config(tmp_path):
     assert list(sd) == ["backbone.w"] and torch.equal(sd["backbone.w"], torch.arange(6.0).view(2, 3))
     torch.save({"a": torch.ones(2)}, tmp_path / "plain.pt")
     assert torch.equal(load_checkpoint(tmp_path / "plain.pt")["a"], torch.ones(2))
+
+
+def test_load_checkpoint_never_resolves_foreign_globals(tmp_path):
+    """A checkpoint that names an arbitrary importable callable (os.system through __reduce__) must load as inert placeholders: nothing outside the
+    tensor allow-list is imported or called."""
+    import os
+    import pickle
+
+    from siu3r_b200.io import load_checkpoint
+    marker = tmp_path / "pwned"
+
+    class Evil:
+        def __reduce__(self):
+            return (os.system, (f"touch {marker}",))
+
+    torch.save({"state_dict": {"model.backbone.x": torch.ones(3)}, "callbacks": Evil()}, tmp_path / "evil.ckpt", pickle_module=pickle)
+    sd = load_checkpoint(tmp_path / "evil.ckpt")
+    assert not marker.exists()
+    assert torch.equal(sd["backbone.x"], torch.ones(3))

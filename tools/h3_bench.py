@@ -14,16 +14,28 @@ H3 = ops.PREC_H3
 
 
 def timeit(fn, iters=20, warm=3):
+    """us per call, GPU time: the calls are captured into a CUDA graph and the replay is timed (the Python / ctypes / tensor-map encoding cost of a
+    call, 20-60 us, would otherwise hide every kernel shorter than that)."""
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    st = torch.cuda.Stream()
+    st.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(st):
+        with torch.cuda.graph(g, stream=st):
+            for _ in range(iters):
+                fn()
+    torch.cuda.synchronize()
+    g.replay()
+    torch.cuda.synchronize()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
-    for _ in range(iters):
-        fn()
+    g.replay()
+    g.replay()
     e.record()
     torch.cuda.synchronize()
-    return s.elapsed_time(e) / iters * 1e3   # us
+    return s.elapsed_time(e) / (2 * iters) * 1e3   # us
 
 
 def bench_gemm(out):
@@ -60,6 +72,68 @@ def bench_gemm(out):
         torch.backends.cuda.matmul.allow_tf32 = False
         print(json.dumps(row), flush=True)
         out.append(row)
+
+
+def bench_epilogue(out):
+    """epilogue variants of the encoder / decoder projections, back to back (GPU-bound timing), both tile orders"""
+    lib = ops._lib.load()
+    N_tok = 1025
+    g = 32
+    ys, xs_ = torch.meshgrid(torch.arange(g), torch.arange(g), indexing="ij")
+    pos = torch.cat([torch.stack([ys.flatten(), xs_.flatten()], -1), torch.tensor([[g, 0]])], 0)[None].repeat(2, 1, 1).contiguous().to(DEV)
+    tab = ops.rope2d_table(g + 1)
+    for order in (0,):
+        lib.siu3r_gemm_h3_order(order)
+        for (M, N, K, what) in [(2050, 3072, 1024, "qkv"), (2050, 4096, 1024, "fc1"), (2050, 1024, 4096, "fc2"), (2050, 1024, 1024, "proj")]:
+            x = ops.split(torch.randn(M, K, device=DEV))
+            wt = ops.Weight(torch.randn(N, K, device=DEV) / K ** 0.5, torch.randn(N, device=DEV), H3)
+            row = {"kind": "epilogue", "what": what, "order": order, "M": M, "N": N, "K": K}
+            o = torch.empty(M, N, device=DEV)
+            row["plain_us"] = timeit(lambda: ops.gemm(x, wt, out=o, precision=H3))
+            if what == "qkv":
+                C = 1024
+                q = ops.Split.empty(M, 3 * C, device=DEV, unscaled=True)
+                vth = ops.Split.empty(C, (M + 7) // 8 * 8, device=DEV, unscaled=True)
+                row["rope_vt_split_us"] = timeit(lambda: ops.gemm(x, wt, out=q, precision=H3, rope=(pos.view(-1, 2), tab, 2 * C), vt=(vth, 2 * C, {}), unscaled=True))
+                row["split_us"] = timeit(lambda: ops.gemm(x, wt, out=q, precision=H3, unscaled=True))
+                row["rope_split_us"] = timeit(lambda: ops.gemm(x, wt, out=q, precision=H3, rope=(pos.view(-1, 2), tab, 2 * C), unscaled=True))
+                row["vt_split_us"] = timeit(lambda: ops.gemm(x, wt, out=q, precision=H3, vt=(vth, 2 * C, {}), unscaled=True))
+                row["rope_f32_us"] = timeit(lambda: ops.gemm(x, wt, out=o, precision=H3, rope=(pos.view(-1, 2), tab, 2 * C)))
+            elif what == "fc1":
+                oh = ops.Split.empty(M, N, device=DEV)
+                row["gelu_split_us"] = timeit(lambda: ops.gemm(x, wt, out=oh, precision=H3, act=1))
+                row["gelu_f32_us"] = timeit(lambda: ops.gemm(x, wt, out=o, precision=H3, act=1))
+                row["relu_split_us"] = timeit(lambda: ops.gemm(x, wt, out=oh, precision=H3, act=2))
+            else:
+                r = torch.randn(M, N, device=DEV)
+                row["residual_us"] = timeit(lambda: ops.gemm(x, wt, out=r, residual=r, precision=H3))
+            print(json.dumps(row), flush=True)
+            out.append(row)
+    lib.siu3r_gemm_h3_order(0)
+    x = torch.randn(2050, 1024, device=DEV)
+    w_, b_ = torch.randn(1024, device=DEV), torch.randn(1024, device=DEV)
+    oh = ops.Split.empty(2050, 1024, device=DEV)
+    out.append({"kind": "layernorm_h3", "us": timeit(lambda: ops.layernorm_h3([x], [(w_, b_)], 1e-6, outs=[oh]))})
+    print(json.dumps(out[-1]), flush=True)
+
+
+def bench_limits(out):
+    """Which side bounds the mainloop: the operand pipeline alone (no MMAs), the MMAs alone (no loads), both."""
+    lib = ops._lib.load()
+    for (M, N, K) in [(2050, 3072, 1024), (2050, 1024, 4096), (8192, 4096, 1024)]:
+        x = ops.split(torch.randn(M, K, device=DEV))
+        wt = ops.Weight(torch.randn(N, K, device=DEV) / K ** 0.5, torch.randn(N, device=DEV), H3)
+        o = torch.empty(M, N, device=DEV)
+        for tw in (64, 128, 192, 256):
+            lib.siu3r_gemm_h3_force(tw)
+            row = {"kind": "limits", "M": M, "N": N, "K": K, "tw": tw}
+            for mode, name in ((0, "full_us"), (1, "tma_only_us"), (2, "mma_only_us")):
+                lib.siu3r_gemm_h3_debug(mode)
+                row[name] = timeit(lambda: ops.gemm(x, wt, out=o, precision=H3), iters=10, warm=2)
+            lib.siu3r_gemm_h3_debug(0)
+            print(json.dumps(row), flush=True)
+            out.append(row)
+    lib.siu3r_gemm_h3_force(0)
 
 
 def bench_conv(out):
@@ -118,7 +192,14 @@ def bench_model(out):
         for _ in range(3):
             model(img, K)
         torch.cuda.synchronize()
-        t = timeit(lambda: model(img, K), iters=10, warm=1)
+        torch.cuda.synchronize()
+        s0, e0 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(10):
+            model(img, K)
+        e0.record()
+        torch.cuda.synchronize()
+        t = s0.elapsed_time(e0) / 10 * 1e3
         row = {"kind": "model", "precision": prec, "ms_per_pair_serial": t / 1e3, "pairs_per_s": 1e6 / t}
         print(json.dumps(row), flush=True)
         out.append(row)
@@ -131,7 +212,7 @@ if __name__ == "__main__":
     res = []
     for w in what:
         try:
-            {"gemm": bench_gemm, "conv": bench_conv, "flash": bench_flash, "model": bench_model}[w](res)
+            {"gemm": bench_gemm, "conv": bench_conv, "flash": bench_flash, "model": bench_model, "epilogue": bench_epilogue, "limits": bench_limits}[w](res)
         except Exception as ex:  # keep going: one failing section must not lose the others
             print(json.dumps({"kind": w, "error": repr(ex)}), flush=True)
     os.makedirs("gpurun_out", exist_ok=True)

@@ -378,7 +378,7 @@ def main():
     guard.cancel()
     watchdog = AuxWatchdog(line, float(os.environ.get("SIU3R_BENCH_AUX_TIMEOUT", "300")), enabled=(rank == 0))
 
-    # ---- BASELINE configs[2]: the one collective of the path -- all-gather of the packed render records (88 fp32 per Gaussian) so that every
+    # ---- BASELINE configs[2]: the one collective of the path -- all-gather of the packed render records (85 fp32 per Gaussian) so that every
     #      rank holds the Gaussians of all pairs for joint-scene rasterisation (N > 1 only; not part of `value`) ----
     if world > 1:
         try:
@@ -389,12 +389,41 @@ def main():
                 parallel.all_gather_gaussians(rec)
             ms_ag = timed(lambda: parallel.all_gather_gaussians(rec), 5) / 5
             nbytes = rec.numel() * 4
-            line["allgather"] = {"what": "NCCL all_gather_into_tensor of the packed render records (means 3 + cov 9 + SH 75 + opacity 1 fp32 per Gaussian)",
+            line["allgather"] = {"what": "NCCL all_gather_into_tensor of the packed render records (means 3 + cov6 + SH 75 + opacity 1 = 85 fp32 per Gaussian, packed by siu3r_render_record_pack)",
                                  "bytes_contributed_per_rank": nbytes, "bytes_gathered_per_rank": nbytes * world, "ms": ms_ag,
                                  "algbw_GBs": nbytes * world / ms_ag / 1e6, "busbw_GBs": nbytes * (world - 1) / ms_ag / 1e6}
             del g0, rec
         except Exception as ex:
             line["allgather"] = {"error": repr(ex)}
+
+    # ---- BASELINE configs[2] as specified: 4 pairs per GPU per step (batch 32 on 8 GPUs), render records packed on the device and all-gathered INSIDE the
+    #      timed step (at N = 1 the same step without the collective) ----
+    if V == 2 and B == 1 and not args.no_multiview:
+        try:
+            from siu3r_b200 import parallel
+            model._use_graph = bool(args.graph)     # (the roofline pass above ran eagerly)
+            B3 = 4
+            i3, K3 = synth.pair_inputs(B3, 2, S, seed=100 + rank)
+            i3, K3 = i3.to(dev), K3.to(dev)
+
+            def step3():
+                g3 = model(i3, K3, enable_query_class_logit_lift=True)[0]
+                rec3 = parallel.pack_render_record(g3)
+                return parallel.all_gather_gaussians(rec3) if world > 1 else rec3
+            for _ in range(2):
+                step3()
+            n3 = 4
+            ms3 = timed(lambda: [step3() for _ in range(n3)], 1) / n3
+            rec_bytes = B3 * 2 * S * S * parallel.RECORD_FLOATS * 4
+            line["config3"] = {"workload": f"{B3} pairs per GPU per step ({B3 * world} pairs per step over {world} GPU(s)), forward + device-side record packing"
+                                           + (" + NCCL all-gather of the render records, all inside the timed step" if world > 1 else ""),
+                               "value": world * B3 * 1e3 / ms3, "unit": "pairs/s", "ms_per_step": ms3, "steps": n3,
+                               "record_bytes_contributed_per_rank": rec_bytes, "record_bytes_gathered_per_rank": rec_bytes * world}
+            del i3, K3
+            model._graphs = {k: v for k, v in model._graphs.items() if k[0] == B}   # drop the batch-4 graph (its static buffers) again
+            torch.cuda.empty_cache()
+        except Exception as ex:
+            line["config3"] = {"error": repr(ex)}
 
     # ---- BASELINE configs[3]: 4-view sample through SIU3RMultiViewModel (short, N = 1 only; not the headline) ----
     if V == 2 and world == 1 and not args.no_multiview:

@@ -199,6 +199,12 @@ int siu3r_label_lut(const int32_t* labels, int64_t npix, const int32_t* seg_lut,
 int siu3r_qc_logits(const float* probs, int64_t npix, int nq, const int* keep, int nk, const float* cls, int ncls,
                     float* out, void* stream);
 
+/* ---- render record of the joint-scene all-gather (no precedent in the single-GPU reference) ----
+ * 85 floats per Gaussian: means 3 | covariance upper triangle 6 (the cov3D_precomp gather of cuda_splatting.py:107,115) | harmonics 75 | opacity. */
+int siu3r_render_record_pack(const float* means, const float* cov33, const float* harmonics, const float* opacities, int64_t G, float* out,
+                             void* stream);
+int siu3r_render_record_unpack(const float* rec, int64_t G, float* means, float* cov6, float* harmonics, float* opacities, void* stream);
+
 /* ---- output wire format ------------------------------------------------------------------------------------------
  * Packed little-endian PLY vertex records of export_ply (src/utils/ply_export.py:12-97; field order :12-27, log(scales) :74,
  * rotations re-ordered xyzw -> wxyz :52-53, i4 labels :62-64, flattened seg_query_class_logits :65-71): the device buffer copied to

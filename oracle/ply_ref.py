@@ -3,8 +3,9 @@
 NumPy restatement of /root/reference/src/utils/ply_export.py:30-97 (export_ply): same attribute order, same float64 concatenate
 followed by the per-field cast into the structured vertex dtype, and the header plyfile 1.x writes for
 PlyData([PlyElement.describe(elements, "vertex")]) (binary_little_endian, 'float' / 'int' property names, no comments).
-PARITY UNPINNED for the header text: `plyfile` is an un-vendored dependency (uv.lock) that is not installed in this image, so the
-reference function itself cannot run here; the record layout follows the reference source line by line.
+PINNED for the record layout: tests/golden/ply_records.npz holds the structured records the reference's own export_ply assembles (run unmodified by
+oracle/make_golden_ply.py with `plyfile` replaced by a recorder) and tests/test_oracle_cpu.py checks this restatement against them, field by
+field (log(scales) to 1 ulp: numpy vs ATen logf).  Still UNPINNED: the ASCII header, which is plyfile's own text (un-vendored, not installed).
 """
 from __future__ import annotations
 

@@ -73,6 +73,8 @@ SIGNATURES = {
     "siu3r_argmax_area": (_i, [_p, _l, _i, _p, _f, _p, _p, _p, _p]),
     "siu3r_label_lut": (_i, [_p, _l, _p, _p, _p, _p, _p, _p]),
     "siu3r_qc_logits": (_i, [_p, _l, _i, _p, _i, _p, _i, _p, _p]),
+    "siu3r_render_record_pack": (_i, [_p, _p, _p, _p, _l, _p, _p]),
+    "siu3r_render_record_unpack": (_i, [_p, _l, _p, _p, _p, _p, _p]),
     # h3 mode (fp32-grade results on the fp16 tensor-core path)
     "siu3r_gemm_h3_force": (None, [_i]),
     "siu3r_gemm_h3_order": (None, [_i]),

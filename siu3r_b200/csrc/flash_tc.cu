@@ -72,6 +72,16 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* ba
         "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+__device__ __forceinline__ bool elect_one_sync() {   // one lane of the converged warp (see gemm_tc.cu)
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "elect.sync _|P1, 0xffffffff;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t"
+        "}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -209,21 +219,27 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t tmem_O = tmem_base + 3 * FT_BN;
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
+        // ===================== TMA producer (whole warp walks the loop, one elected lane issues) =====================
+        if (elect_one_sync()) {
             mbar_expect_tx(&bars[B_Q], FT_Q_BYTES);
             tma_load_3d(&tmQ, &bars[B_Q], sQ, p.q_col0 + h * FT_D, q0, b);
             tma_load_3d(&tmQ, &bars[B_Q], sQ + FT_BM * FT_BK * 4, p.q_col0 + h * FT_D + FT_BK, q0, b);
-            for (int t = 0; t < ntiles; ++t) {
-                const int buf = t & 1;
-                const uint32_t use = (uint32_t)t >> 1;
-                mbar_wait(&bars[B_KEMPTY + buf], (use & 1) ^ 1);
-                uint8_t* dK = sK + buf * FT_K_BYTES;
+        }
+        __syncwarp();
+        for (int t = 0; t < ntiles; ++t) {
+            const int buf = t & 1;
+            const uint32_t use = (uint32_t)t >> 1;
+            mbar_wait(&bars[B_KEMPTY + buf], (use & 1) ^ 1);
+            uint8_t* dK = sK + buf * FT_K_BYTES;
+            if (elect_one_sync()) {
                 mbar_expect_tx(&bars[B_KFULL + buf], FT_K_BYTES);
                 tma_load_3d(&tmK, &bars[B_KFULL + buf], dK, p.k_col0 + h * FT_D, t * FT_BN - kshift, b);
                 tma_load_3d(&tmK, &bars[B_KFULL + buf], dK + FT_BN * FT_BK * 4, p.k_col0 + h * FT_D + FT_BK, t * FT_BN - kshift, b);
-                mbar_wait(&bars[B_VFREE + buf], (use & 1) ^ 1);      // P V of tile t-2 has read this V buffer
-                uint8_t* dV = sV + buf * FT_V_BYTES;
+            }
+            __syncwarp();
+            mbar_wait(&bars[B_VFREE + buf], (use & 1) ^ 1);      // P V of tile t-2 has read this V buffer
+            uint8_t* dV = sV + buf * FT_V_BYTES;
+            if (elect_one_sync()) {
                 mbar_expect_tx(&bars[B_VFULL + buf], FT_V_BYTES);
 #pragma unroll
                 for (int j = 0; j < FT_BN / FT_BK; ++j)
@@ -231,20 +247,21 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                                 (int)(p.vt_batch_cols ? b * p.vt_batch_cols : 0) + t * FT_BN - kshift + j * FT_BK,
                                 (p.vt_batch_cols ? h : b * p.H + h) * FT_D);
             }
+            __syncwarp();
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer: S(t+1) is issued before P(t) V(t) =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc_s = make_idesc_tf32(FT_BM, FT_BN);
-            constexpr uint32_t idesc_o = make_idesc_tf32(FT_BM, FT_D);
-            mbar_wait(&bars[B_Q], 0);
-            auto issue_s = [&](int t) {
-                const int buf = t & 1, sb = t % 3;
-                const uint32_t use = (uint32_t)t >> 1;
-                mbar_wait(&bars[B_KFULL + buf], use & 1);
-                mbar_wait(&bars[B_SFREE + sb], (((uint32_t)t / 3) & 1) ^ 1);   // P(t-3) (aliasing this S buffer) has been consumed
-                tc_fence_after();
-                const uint32_t kb = smem_u32(sK + buf * FT_K_BYTES);
+        // ===================== MMA issuer: S(t+1) is issued before P(t) V(t); whole warp, one elected lane issues =====================
+        constexpr uint32_t idesc_s = make_idesc_tf32(FT_BM, FT_BN);
+        constexpr uint32_t idesc_o = make_idesc_tf32(FT_BM, FT_D);
+        mbar_wait(&bars[B_Q], 0);
+        auto issue_s = [&](int t) {
+            const int buf = t & 1, sb = t % 3;
+            const uint32_t use = (uint32_t)t >> 1;
+            mbar_wait(&bars[B_KFULL + buf], use & 1);
+            mbar_wait(&bars[B_SFREE + sb], (((uint32_t)t / 3) & 1) ^ 1);   // P(t-3) (aliasing this S buffer) has been consumed
+            tc_fence_after();
+            const uint32_t kb = smem_u32(sK + buf * FT_K_BYTES);
+            if (elect_one_sync()) {
 #pragma unroll
                 for (int ks = 0; ks < FT_D / 8; ++ks) {
                     const uint32_t blk = (ks >> 2), koff = (ks & 3) * 32;
@@ -253,16 +270,19 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 }
                 umma_commit(&bars[B_KEMPTY + buf]);   // K buffer reusable
                 umma_commit(&bars[B_SFULL + sb]);     // S ready
-            };
-            issue_s(0);
-            for (int t = 0; t < ntiles; ++t) {
-                if (t + 1 < ntiles) issue_s(t + 1);
-                const int buf = t & 1, sb = t % 3;
-                const uint32_t use = (uint32_t)t >> 1;
-                mbar_wait(&bars[B_VFULL + buf], use & 1);
-                mbar_wait(&bars[B_PFULL + sb], ((uint32_t)t / 3) & 1);   // P written (and, if needed, O rescaled) by the softmax warps
-                tc_fence_after();
-                const uint32_t vb = smem_u32(sV + buf * FT_V_BYTES);
+            }
+            __syncwarp();
+        };
+        issue_s(0);
+        for (int t = 0; t < ntiles; ++t) {
+            if (t + 1 < ntiles) issue_s(t + 1);
+            const int buf = t & 1, sb = t % 3;
+            const uint32_t use = (uint32_t)t >> 1;
+            mbar_wait(&bars[B_VFULL + buf], use & 1);
+            mbar_wait(&bars[B_PFULL + sb], ((uint32_t)t / 3) & 1);   // P written (and, if needed, O rescaled) by the softmax warps
+            tc_fence_after();
+            const uint32_t vb = smem_u32(sV + buf * FT_V_BYTES);
+            if (elect_one_sync()) {
 #pragma unroll
                 for (int ks = 0; ks < FT_BN / 8; ++ks) {
                     const uint32_t blk = (ks >> 2), koff = (ks & 3) * 32;
@@ -272,8 +292,10 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 umma_commit(&bars[B_VFREE + buf]);    // V buffer ...
                 umma_commit(&bars[B_SFREE + sb]);     // ... and the S/P buffer reusable once these MMAs are done
             }
-            umma_commit(&bars[B_OFULL]);
+            __syncwarp();
         }
+        if (elect_one_sync()) umma_commit(&bars[B_OFULL]);
+        __syncwarp();
     } else {
         // ===================== softmax / epilogue warps: thread = one query row =====================
         const int qd = warp & 3;                 // TMEM lane quarter

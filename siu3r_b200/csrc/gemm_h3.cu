@@ -40,7 +40,8 @@ constexpr int W_BYTES = 2 * W_PLANE_BYTES;     // hi + lo
 constexpr int PIPE_BYTES = 200 * 1024;
 constexpr int MAX_STAGES = 6;
 constexpr int SMEM_BYTES = PIPE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr int EPI_WARPS = 8;                   // two warps per TMEM lane quarter (they split the token columns)
+constexpr int EPI_WARPS = 16;                  // four warps per TMEM lane quarter (they split the token columns): the epilogue of a GELU / RoPE
+                                               // tile costs more issue slots than 8 warps provide under one tile's mainloop
 constexpr int THREADS = 64 + 32 * EPI_WARPS;   // + TMA producer warp + MMA issuer warp
 constexpr int CLUSTERS = 74;                   // TPC pairs of a B200 (148 SMs)
 
@@ -73,21 +74,18 @@ struct H3Problem {       // what differs between the problems of a grouped launc
 };
 struct H3Group { H3Problem prob[2]; int tiles0; };
 
-struct Frag {            // where the 32 tokens of one epilogue fragment live: two runs of 16 consecutive output rows
-    int64_t rb[2];       // first output row of each run
-    int nv[2];           // valid tokens in each run (0..16)
+struct Frag {            // where the 16 tokens of one epilogue fragment live: 16 consecutive output rows
+    int64_t rb;          // first output row
+    int nv;              // valid tokens (0..16)
 };
 
 template <int ACTK, bool ROPE, bool RES, bool SPLIT>
-__device__ __forceinline__ void epi_chunk(float (&v)[32], const Frag& f, int lane, int n, bool n_ok, float bias, int axis, int mrow, int jmax,
+__device__ __forceinline__ void epi_chunk(float (&v)[16], const Frag& f, int lane, int n, bool n_ok, float bias, int axis, int mrow, int jmax,
                                           const H3Params& p, const H3Problem& pr) {
-    float r[32];
+    float r[16];
     if (RES) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            const int h = j >> 4;
-            r[j] = ((j & 15) < f.nv[h] && n_ok) ? __ldcg(pr.residual + (f.rb[h] + (j & 15)) * p.ldr + n) : 0.0f;
-        }
+        for (int j = 0; j < 16; ++j) r[j] = (j < f.nv && n_ok) ? __ldcg(pr.residual + (f.rb + j) * p.ldr + n) : 0.0f;
     }
     long long pos_l = 0;
     const float* tab = nullptr;
@@ -95,10 +93,9 @@ __device__ __forceinline__ void epi_chunk(float (&v)[32], const Frag& f, int lan
         pos_l = lane < jmax ? p.rope_pos[(int64_t)(mrow + lane) * 2 + axis] : 0;   // lane j holds the position of token j of the fragment
         tab = p.rope_tab + (lane & 15) * 2;
     }
-    // Phase 1 (branch free: the warp stays converged, so the RoPE shuffles compile to plain SHFL -- with the stores in the same loop ptxas wraps
-    // every shuffle into a WARPSYNC.COLLECTIVE sequence and the fused qkv projection ran at half speed): all arithmetic, results left in v[].
+    // Phase 1 (branch free: the warp stays converged, so the RoPE shuffles compile to plain SHFL): all arithmetic, results left in v[].
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
+    for (int j = 0; j < 16; ++j) {
         float x = v[j] * p.alpha + bias;
         if (ACTK == ACT_GELU) x = gelu_erf(x);
         if (ACTK == ACT_RELU) x = fmaxf(x, 0.0f);
@@ -112,51 +109,47 @@ __device__ __forceinline__ void epi_chunk(float (&v)[32], const Frag& f, int lan
         v[j] = x;
     }
     // Phase 2: stores (one output row = 32 consecutive n of the warp: a 128-byte line in fp32, 64 bytes per plane as a plane pair)
+    if (f.nv <= 0 || !n_ok) return;
+    if (SPLIT) {
+        __half* d = pr.Ch + f.rb * p.ldh + n;
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        if (f.nv[h] <= 0 || !n_ok) continue;
-        if (SPLIT) {
-            __half* d = pr.Ch + f.rb[h] * p.ldh + n;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                __half hi, lo;
-                h3_split_s(v[h * 16 + i], p.lo_scale, hi, lo);
-                if (i < f.nv[h]) { d[(int64_t)i * p.ldh] = hi; d[(int64_t)i * p.ldh + p.plane_h] = lo; }
-            }
-        } else {
-            float* d = pr.C + f.rb[h] * p.ldc + n;
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-                if (i < f.nv[h]) d[(int64_t)i * p.ldc] = v[h * 16 + i];
+        for (int i = 0; i < 16; ++i) {
+            __half hi, lo;
+            h3_split_s(v[i], p.lo_scale, hi, lo);
+            if (i < f.nv) { d[(int64_t)i * p.ldh] = hi; d[(int64_t)i * p.ldh + p.plane_h] = lo; }
         }
+    } else {
+        float* d = pr.C + f.rb * p.ldc + n;
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            if (i < f.nv) d[(int64_t)i * p.ldc] = v[i];
     }
 }
 
-// V columns of a fused qkv / k|v projection: this lane's output column n is one row of V^T, the fragment's 32 tokens are 64 contiguous bytes
+// V columns of a fused qkv / k|v projection: this lane's output column n is one row of V^T, the fragment's 16 tokens are 32 contiguous bytes
 // of it per plane.  Tokens past M up to the padded pitch are zero-filled so that the attention kernel's TMA never stages uninitialised memory.
-__device__ __forceinline__ void epi_chunk_vt(const float (&v)[32], int jmax, int n, bool n_ok, float bias, int mrow, const H3Params& p,
+__device__ __forceinline__ void epi_chunk_vt(const float (&v)[16], int jmax, int n, bool n_ok, float bias, int mrow, const H3Params& p,
                                              const H3Problem& pr) {
     if (!n_ok) return;
     __half* dst = pr.vt + (int64_t)(n - p.vt_col0) * p.vt_ld + mrow;
-    uint32_t hi[16], lo[16];
+    uint32_t hi[8], lo[8];
 #pragma unroll
-    for (int j = 0; j < 32; j += 2) {
+    for (int j = 0; j < 16; j += 2) {
         const float x0 = j < jmax ? v[j] * p.alpha + bias : 0.0f;
         const float x1 = j + 1 < jmax ? v[j + 1] * p.alpha + bias : 0.0f;
         h3_split2_s(x0, x1, p.lo_scale, hi[j >> 1], lo[j >> 1]);
     }
-    // a fragment cut by the END OF THE PROBLEM (mrow + jmax == M) also zero-fills the pad columns [M, vt_cols); one cut by the tile edge (tw is a
-    // multiple of 16, not of 32) must stop there: the next columns belong to the neighbouring tile
-    const int lim = (mrow + jmax == pr.M) ? min(32, pr.vt_cols - mrow) : jmax;
+    // a fragment cut by the END OF THE PROBLEM (mrow + jmax == M) also zero-fills the pad columns [M, vt_cols) (fewer than 8 of them)
+    const int lim = (mrow + jmax == pr.M) ? min(16, pr.vt_cols - mrow) : jmax;
 #pragma unroll
-    for (int j = 0; j < 32; j += 8)
+    for (int j = 0; j < 16; j += 8)
         if (j < lim) {
             *reinterpret_cast<uint4*>(dst + j) = make_uint4(hi[j >> 1], hi[(j >> 1) + 1], hi[(j >> 1) + 2], hi[(j >> 1) + 3]);
             *reinterpret_cast<uint4*>(dst + p.vt_plane + j) = make_uint4(lo[j >> 1], lo[(j >> 1) + 1], lo[(j >> 1) + 2], lo[(j >> 1) + 3]);
         }
 }
 
-// Epilogue of one warp: TMEM lanes [32q, 32q+32) = weight rows n, columns [c_lo, c_hi) = its share of the tile's tokens.
+// Epilogue of one warp: TMEM lanes [32q, 32q+32) = weight rows n, columns [c_lo, c_hi) = its share of the tile's tokens, 16 at a time.
 __device__ __forceinline__ void run_epilogue(uint32_t tmem_hh, uint32_t tmem_x, int lane, int q, int c_lo, int c_hi, int n_cta, int tt,
                                              const H3Params& p, const H3Problem& pr, uint64_t* bar, uint32_t parity) {
     const int nb = n_cta + q * 32;           // warp-uniform first weight row
@@ -168,7 +161,7 @@ __device__ __forceinline__ void run_epilogue(uint32_t tmem_hh, uint32_t tmem_x, 
     const bool res = pr.residual != nullptr;
     const bool split = pr.Ch != nullptr;
     const int axis = (nb >> 5) & 1;
-    // warp-uniform variant id: branches are hoisted out of the 32-element inner loops
+    // warp-uniform variant id: branches are hoisted out of the 16-element inner loops
     const int variant = rope ? (split ? 1 : 0) : 2 + (act * 4 + (res ? 2 : 0) + (split ? 1 : 0));
     // tile coordinates
     int img = 0, h0 = 0, w0 = 0, m_base = tt * p.tw;
@@ -182,30 +175,25 @@ __device__ __forceinline__ void run_epilogue(uint32_t tmem_hh, uint32_t tmem_x, 
     tc_fence_after();
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
 #pragma unroll 1
-    for (int c0 = c_lo; c0 < c_hi && nb < p.N; c0 += 32) {
-        uint32_t a[32], b[32];
-        tmem_ld32(tmem_hh + lane_off + (uint32_t)c0, a);
-        tmem_ld32(tmem_x + lane_off + (uint32_t)c0, b);
+    for (int c0 = c_lo; c0 < c_hi && nb < p.N; c0 += 16) {
+        uint32_t a[16], b[16];
+        tmem_ld16(tmem_hh + lane_off + (uint32_t)c0, a);
+        tmem_ld16(tmem_x + lane_off + (uint32_t)c0, b);
         tmem_ld_wait();
-        float v[32];
+        float v[16];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(b[j]), H3_LO_INV, __uint_as_float(a[j]));
+        for (int j = 0; j < 16; ++j) v[j] = fmaf(__uint_as_float(b[j]), H3_LO_INV, __uint_as_float(a[j]));
         Frag f;
-        int mrow = m_base + c0, jmax = min(32, c_hi - c0);
+        int mrow = m_base + c0, jmax = 16;
         if (p.conv) {
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int jj = c0 + 16 * h;
-                const int hrow = h0 + (jj >> 4);
-                const bool ok = jj < c_hi && hrow < p.H;
-                f.rb[h] = ((int64_t)img * p.H + hrow) * p.W + w0;
-                f.nv[h] = ok ? 16 : 0;
-            }
+            const int hrow = h0 + (c0 >> 4);
+            f.rb = ((int64_t)img * p.H + hrow) * p.W + w0;
+            f.nv = hrow < p.H ? 16 : 0;
         } else {
             if (jmax > pr.M - mrow) jmax = pr.M - mrow;
             if (jmax <= 0) break;
-            f.rb[0] = mrow; f.rb[1] = mrow + 16;
-            f.nv[0] = min(jmax, 16); f.nv[1] = max(jmax - 16, 0);
+            f.rb = mrow;
+            f.nv = jmax;
             if (pr.vt != nullptr && nb >= p.vt_col0) {        // warp-uniform: a 32-column block never straddles vt_col0 (multiple of 64)
                 epi_chunk_vt(v, jmax, n, n_ok, bias, mrow, p, pr);
                 continue;
@@ -232,7 +220,7 @@ __device__ __forceinline__ void run_epilogue(uint32_t tmem_hh, uint32_t tmem_x, 
 
 // Barriers:  full[s] (leader) <- complete_tx of both CTAs' TMA loads;  empty[s] (both) <- tcgen05.commit multicast by the leader;
 //            tfull[b] (both)  <- commit multicast after the last k-block of a tile;
-//            tempty[b] (leader, 16 arrivals) <- one per epilogue warp of both CTAs once accumulator set b has been drained.
+//            tempty[b] (leader, 32 arrivals) <- one per epilogue warp of both CTAs once accumulator set b has been drained.
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 gemm_h3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
                const __grid_constant__ CUtensorMap tmX1, const H3Params p, const H3Group grp, int w_pairs, int num_tiles) {
@@ -363,12 +351,12 @@ gemm_h3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
             }
         }
     } else {
-        // ===================== epilogue (warps 2..9 of both CTAs) =====================
+        // ===================== epilogue (warps 2..17 of both CTAs) =====================
         const int q = warp & 3;                         // TMEM lane quarter this warp may access
-        const int half = (warp - 2) >> 2;               // which half of the tile's 32-column fragments
-        const int nfrag = (tw + 31) >> 5;
-        const int c_lo = half == 0 ? 0 : ((nfrag + 1) >> 1) * 32;
-        const int c_hi = half == 0 ? min(tw, ((nfrag + 1) >> 1) * 32) : tw;
+        const int sub = (warp - 2) >> 2;                // which quarter of the tile's 16-column fragments (tw is a multiple of 16)
+        const int nfrag = tw >> 4, per = (nfrag + 3) >> 2;
+        const int c_lo = min(nfrag, sub * per) * 16;
+        const int c_hi = min(nfrag, (sub + 1) * per) * 16;
         const uint32_t lead_tempty0 = mapa_to_cta(smem_u32(&tempty_bar[0]), 0);
         int it = 0;
         for (int u = cluster_id; u < num_tiles; u += num_clusters, ++it) {

@@ -108,6 +108,18 @@ __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
 
+// one lane of the converged warp (issuing tcgen05 / TMA instructions from warp-uniform code keeps their operands on the uniform datapath; from
+// inside an `if (lane == 0)` region ptxas wraps every such instruction into an elect / R2UR-broadcast / branch loop of ~20 dependent instructions)
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "elect.sync _|P1, 0xffffffff;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t"
+        "}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -385,14 +397,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (dbg && threadIdx.x == 0) dbg[1] = clock64();
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
+        // ===================== TMA producer (whole warp walks the loop, one elected lane issues) =====================
+        {
             const int cblocks = p.conv ? p.Cin / BK : 0;
             int stage = 0; uint32_t phase = 0;
             for (int kb = 0; kb < p.num_kb; ++kb) {
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 uint8_t* sA = smem + stage * C_::STAGE_BYTES;
                 uint8_t* sB = sA + C_::NOPER * C_::A_BYTES;
+                if (elect_one_sync()) {
                 mbar_expect_tx(&full_bar[stage], C_::STAGE_BYTES);
                 if (p.conv) {
                     const int tap = kb / cblocks, cb = kb - tap * cblocks;
@@ -406,20 +419,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tma_load_2d(&tmB, &full_bar[stage], sB, kb * BK, n0);
                 if (NSPLIT == 3) tma_load_2d(&tmBlo, &full_bar[stage], sB + C_::B_BYTES, kb * BK, n0);
                 if (kb == 0 && dbg) dbg[2] = clock64();
+                }
+                __syncwarp();
                 if (++stage == C_::STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (whole warp, one elected lane issues) =====================
+        {
             constexpr uint32_t idesc = make_idesc_tf32(BM, BN);
             int stage = 0; uint32_t phase = 0;
             for (int kb = 0; kb < p.num_kb; ++kb) {
                 mbar_wait(&full_bar[stage], phase);
                 tcgen05_fence_after();
-                if (kb == 0 && dbg) dbg[3] = clock64();
                 const uint32_t sA = smem_u32(smem + stage * C_::STAGE_BYTES);
                 const uint32_t sB = sA + C_::NOPER * C_::A_BYTES;
+                if (elect_one_sync()) {
 #pragma unroll
                 for (int k = 0; k < BK / UMMA_K; ++k) {
                     const uint32_t koff = k * UMMA_K * 4;
@@ -436,10 +451,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                 }
                 umma_commit(&empty_bar[stage]);  // stage reusable once these MMAs have read it
+                }
+                __syncwarp();
                 if (++stage == C_::STAGES) { stage = 0; phase ^= 1; }
             }
-            umma_commit(acc_bar);  // accumulator complete
-            if (dbg) dbg[4] = clock64();
+            if (elect_one_sync()) umma_commit(acc_bar);  // accumulator complete
+            __syncwarp();
         }
     } else {
         // ===================== epilogue (warps 2..5) =====================
@@ -550,7 +567,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
+        {
             const int cblocks = p.conv ? p.Cin / BK : 0;
             int stage = 0; uint32_t phase = 0;
             for (int kb = 0; kb < p.num_kb; ++kb) {
@@ -558,6 +575,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 uint8_t* sA = smem + stage * TC2_STAGE_BYTES;
                 uint8_t* sB = sA + A_BYTES;
                 const uint32_t lead_full = mapa_to_cta(smem_u32(&full_bar[stage]), 0);
+                if (elect_one_sync()) {
                 if (leader) mbar_expect_tx(&full_bar[stage], 2 * TC2_STAGE_BYTES);  // bytes of both CTAs land on the leader's barrier
                 if (p.conv) {
                     const int tap = kb / cblocks, cb = kb - tap * cblocks;
@@ -567,11 +585,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     tma2_load_2d(&tmA, lead_full, sA, kb * BK, m0);
                 }
                 tma2_load_2d(&tmB, lead_full, sB, kb * BK, n0 + (int)rank * (TC2_BN / 2));
+                }
+                __syncwarp();
                 if (++stage == TC2_STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
-        if (leader && lane == 0) {
+        if (leader) {
             constexpr uint32_t idesc = make_idesc_tf32(2 * BM, TC2_BN);
             int stage = 0; uint32_t phase = 0;
             for (int kb = 0; kb < p.num_kb; ++kb) {
@@ -579,15 +599,19 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 tcgen05_fence_after();
                 const uint32_t sA = smem_u32(smem + stage * TC2_STAGE_BYTES);
                 const uint32_t sB = sA + A_BYTES;
+                if (elect_one_sync()) {
 #pragma unroll
-                for (int k = 0; k < BK / UMMA_K; ++k) {
-                    const uint32_t koff = k * UMMA_K * 4;
-                    umma2_tf32(tmem_base, make_smem_desc(sA + koff), make_smem_desc(sB + koff), idesc, (kb | k) != 0);
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint32_t koff = k * UMMA_K * 4;
+                        umma2_tf32(tmem_base, make_smem_desc(sA + koff), make_smem_desc(sB + koff), idesc, (kb | k) != 0);
+                    }
+                    umma2_commit_mc(&empty_bar[stage]);
                 }
-                umma2_commit_mc(&empty_bar[stage]);
+                __syncwarp();
                 if (++stage == TC2_STAGES) { stage = 0; phase ^= 1; }
             }
-            umma2_commit_mc(acc_bar);
+            if (elect_one_sync()) umma2_commit_mc(acc_bar);
+            __syncwarp();
         }
     } else {
         const int q = warp & 3;
@@ -868,8 +892,8 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===================== TMA producer (both CTAs) =====================
-        if (lane == 0) {
+        // ===================== TMA producer (both CTAs; whole warp, one elected lane issues) =====================
+        {
             int stage = 0; uint32_t phase = 0;
             for (int u = cluster_id; u < num_units; u += num_clusters) {
                 const int split = u / num_tiles, t = u - split * num_tiles;
@@ -885,17 +909,20 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                     uint8_t* sW = smem + stage * C_::STAGE_BYTES;
                     uint8_t* sX = sW + C_::W_BYTES;
                     const uint32_t lead_full = mapa_to_cta(smem_u32(&full_bar[stage]), 0);
-                    if (leader) mbar_expect_tx(&full_bar[stage], stage_tx);
-                    tma2_load_2d(mw, lead_full, sW, kb * BK, n0);
-                    if (UP2X) tma2_load_2d(mx, lead_full, sX, 0, m0 + (kb - p.rows_pad) * p.rows_W);
-                    else tma2_load_2d(mx, lead_full, sX, kb * BK, m0);
+                    if (elect_one_sync()) {
+                        if (leader) mbar_expect_tx(&full_bar[stage], stage_tx);
+                        tma2_load_2d(mw, lead_full, sW, kb * BK, n0);
+                        if (UP2X) tma2_load_2d(mx, lead_full, sX, 0, m0 + (kb - p.rows_pad) * p.rows_W);
+                        else tma2_load_2d(mx, lead_full, sX, kb * BK, m0);
+                    }
+                    __syncwarp();
                     if (++stage == C_::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer (leader CTA, one lane) =====================
-        if (leader && lane == 0) {
+        // ===================== MMA issuer (leader CTA; whole warp, one elected lane issues) =====================
+        if (leader) {
             const uint32_t idesc = make_idesc_tf32(2 * BM, tw);
             int stage = 0; uint32_t phase = 0;
             int it = 0;
@@ -911,15 +938,19 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                     tcgen05_fence_after();
                     const uint32_t sW = smem_u32(smem + stage * C_::STAGE_BYTES);
                     const uint32_t sX = sW + C_::W_BYTES;
+                    if (elect_one_sync()) {
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k) {
-                        const uint32_t koff = k * UMMA_K * 4;
-                        umma2_tf32(acc, make_smem_desc(sW + koff), make_smem_desc(sX + koff), idesc, ((kb - kb0) | k) != 0);
+                        for (int k = 0; k < BK / UMMA_K; ++k) {
+                            const uint32_t koff = k * UMMA_K * 4;
+                            umma2_tf32(acc, make_smem_desc(sW + koff), make_smem_desc(sX + koff), idesc, ((kb - kb0) | k) != 0);
+                        }
+                        umma2_commit_mc(&empty_bar[stage]);
                     }
-                    umma2_commit_mc(&empty_bar[stage]);
+                    __syncwarp();
                     if (++stage == C_::STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma2_commit_mc(&tfull_bar[buf]);
+                if (elect_one_sync()) umma2_commit_mc(&tfull_bar[buf]);
+                __syncwarp();
             }
         }
     } else {

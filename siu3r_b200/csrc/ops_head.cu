@@ -348,7 +348,60 @@ __global__ void __launch_bounds__(256) ply_pack_kernel(const float* __restrict__
     out[t] = w;
 }
 
+// Render record of the joint-scene all-gather: what the rasterizer consumes, 85 floats per Gaussian =
+// means 3 | covariance upper triangle 6 (xx xy xz yy yz zz: the cov3D_precomp of cuda_splatting.py:107,115) | harmonics 75 | opacity 1.
+// One thread per word, record-major output: one coalesced pass instead of a torch.cat of four tensors.
+__global__ void __launch_bounds__(256) render_record_pack_kernel(const float* __restrict__ means, const float* __restrict__ cov,
+                                                                 const float* __restrict__ harm, const float* __restrict__ opac, int64_t G,
+                                                                 float* __restrict__ out) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= G * 85) return;
+    const int64_t g = t / 85;
+    const int f = (int)(t - g * 85);
+    float w;
+    if (f < 3) w = means[3 * g + f];
+    else if (f < 9) {
+        const int k = f - 3;                       // (0,0) (0,1) (0,2) (1,1) (1,2) (2,2)
+        const int idx = k < 3 ? k : (k < 5 ? k + 1 : 8);
+        w = cov[9 * g + idx];
+    } else if (f < 84) w = harm[75 * g + (f - 9)];
+    else w = opac[g];
+    out[t] = w;
+}
+__global__ void __launch_bounds__(256) render_record_unpack_kernel(const float* __restrict__ rec, int64_t G, float* __restrict__ means,
+                                                                   float* __restrict__ cov6, float* __restrict__ harm, float* __restrict__ opac) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= G * 85) return;
+    const int64_t g = t / 85;
+    const int f = (int)(t - g * 85);
+    const float w = rec[t];
+    if (f < 3) means[3 * g + f] = w;
+    else if (f < 9) cov6[6 * g + (f - 3)] = w;
+    else if (f < 84) harm[75 * g + (f - 9)] = w;
+    else opac[g] = w;
+}
+
 extern "C" {
+
+// Gaussians -> packed render records [G, 85] (see render_record_pack_kernel) and back (covariances come back as the [G, 6] upper triangle the
+// rasterizer takes with cov_stride = 6).  The record is the payload of the one NCCL all-gather of the path (siu3r_b200/parallel.py).
+int siu3r_render_record_pack(const float* means, const float* cov33, const float* harmonics, const float* opacities, int64_t G, float* out,
+                             void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    SIU3R_REQUIRE(means && cov33 && harmonics && opacities && out && G > 0);
+    render_record_pack_kernel<<<grid_for(G * 85), 256, 0, stream>>>(means, cov33, harmonics, opacities, G, out);
+    SIU3R_LAUNCH_CHECK();
+    siu3r_note_launch(1);
+    return SIU3R_OK;
+}
+int siu3r_render_record_unpack(const float* rec, int64_t G, float* means, float* cov6, float* harmonics, float* opacities, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    SIU3R_REQUIRE(rec && means && cov6 && harmonics && opacities && G > 0);
+    render_record_unpack_kernel<<<grid_for(G * 85), 256, 0, stream>>>(rec, G, means, cov6, harmonics, opacities);
+    SIU3R_LAUNCH_CHECK();
+    siu3r_note_launch(1);
+    return SIU3R_OK;
+}
 
 int siu3r_depth_exp(const float* xyz, int64_t ldx, float* pts, int64_t n, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;

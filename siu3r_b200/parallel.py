@@ -10,7 +10,7 @@ from __future__ import annotations
 import torch
 import torch.distributed as dist
 
-RECORD_FLOATS = 3 + 9 + 75 + 1  # means, covariances (3x3), harmonics (3x25), opacity
+RECORD_FLOATS = 3 + 6 + 75 + 1  # means, covariance upper triangle (what the rasterizer consumes), harmonics (3x25), opacity
 
 
 def shard_range(n_items: int, rank: int, world: int) -> range:
@@ -21,19 +21,36 @@ def shard_range(n_items: int, rank: int, world: int) -> range:
 
 
 def pack_render_record(g) -> torch.Tensor:
-    """Gaussians (batch b) -> [b, G, 88] fp32 render record (what the rasterizer consumes)."""
+    """Gaussians (batch b) -> [b, G, 85] fp32 render record.  CUDA tensors go through siu3r_render_record_pack (one coalesced pass, no torch
+    compute op); the CPU form below only serves the gloo tests of the host logic."""
     b, G = g.means.shape[:2]
-    return torch.cat([g.means.reshape(b, G, 3), g.covariances.reshape(b, G, 9), g.harmonics.reshape(b, G, 75), g.opacities.reshape(b, G, 1)], dim=-1).contiguous()
+    if g.means.is_cuda:
+        from . import _lib, ops
+        out = torch.empty(b, G, RECORD_FLOATS, device=g.means.device, dtype=torch.float32)
+        m, c, h, o = g.means.contiguous(), g.covariances.contiguous(), g.harmonics.contiguous(), g.opacities.contiguous()
+        _lib.check(_lib.load().siu3r_render_record_pack(m.data_ptr(), c.data_ptr(), h.data_ptr(), o.data_ptr(), b * G, out.data_ptr(), ops._stream()),
+                   "render_record_pack")
+        return out
+    row, col = torch.triu_indices(3, 3)
+    return torch.cat([g.means.reshape(b, G, 3), g.covariances[:, :, row, col], g.harmonics.reshape(b, G, 75), g.opacities.reshape(b, G, 1)], dim=-1).contiguous()
 
 
 def unpack_render_record(rec: torch.Tensor):
+    """[b, G, 85] -> means [b,G,3], cov6 [b,G,6] (rasterizer cov_stride = 6), harmonics [b,G,3,25], opacities [b,G]."""
     b, G = rec.shape[:2]
-    return (rec[..., 0:3].contiguous(), rec[..., 3:12].reshape(b, G, 3, 3).contiguous(), rec[..., 12:87].reshape(b, G, 3, 25).contiguous(),
-            rec[..., 87].contiguous())
+    if rec.is_cuda:
+        from . import _lib, ops
+        dev = rec.device
+        means, cov6 = torch.empty(b, G, 3, device=dev), torch.empty(b, G, 6, device=dev)
+        harm, opac = torch.empty(b, G, 3, 25, device=dev), torch.empty(b, G, device=dev)
+        _lib.check(_lib.load().siu3r_render_record_unpack(rec.contiguous().data_ptr(), b * G, means.data_ptr(), cov6.data_ptr(), harm.data_ptr(),
+                                                          opac.data_ptr(), ops._stream()), "render_record_unpack")
+        return means, cov6, harm, opac
+    return (rec[..., 0:3].contiguous(), rec[..., 3:9].contiguous(), rec[..., 9:84].reshape(b, G, 3, 25).contiguous(), rec[..., 84].contiguous())
 
 
 def all_gather_gaussians(rec: torch.Tensor, group=None) -> torch.Tensor:
-    """ONE all-gather of the packed records: [b_local, G, 88] per rank -> [world * b_local, G, 88] on every rank."""
+    """ONE all-gather of the packed records: [b_local, G, 85] per rank -> [world * b_local, G, 85] on every rank."""
     world = dist.get_world_size(group)
     out = torch.empty((world * rec.shape[0],) + tuple(rec.shape[1:]), dtype=rec.dtype, device=rec.device)
     dist.all_gather_into_tensor(out, rec.contiguous(), group=group)

@@ -267,7 +267,7 @@ def _gloo_worker(rank, world, port, q):
     pad = torch.zeros(3 - rec.shape[0], G, parallel.RECORD_FLOATS)  # equal-sized contributions (ceil(5/2) = 3 pairs per rank)
     allrec = parallel.all_gather_gaussians(torch.cat([rec, pad], 0))
     means, cov, harm, opac = parallel.unpack_render_record(allrec)
-    q.put((rank, mine, allrec.shape, float(means[0, 0, 0]), float(means[3, 0, 0]), float(cov[3, 0, 1, 1]), float(harm[0, 0, 2, 24])))
+    q.put((rank, mine, allrec.shape, float(means[0, 0, 0]), float(means[3, 0, 0]), float(cov[3, 0, 3]), float(harm[0, 0, 2, 24])))   # cov6 index 3 = (1, 1)
     dist.destroy_process_group()
 
 
@@ -282,7 +282,7 @@ def test_gloo_world2_shard_and_all_gather():
     [p.join(30) for p in procs]
     assert res[0][1] == [0, 1, 2] and res[1][1] == [3, 4]
     for r in res:
-        assert tuple(r[2]) == (6, 7, 88) and r[3] == 0.0 and r[4] == 1.0 and r[5] == 2.0 and r[6] == 74.0
+        assert tuple(r[2]) == (6, 7, 85) and r[3] == 0.0 and r[4] == 1.0 and r[5] == 2.0 and r[6] == 74.0
 
 
 def test_bench_aux_watchdog_prints_headline_and_exits():
@@ -649,3 +649,30 @@ def test_renderer_frontend_matches_reference_recording():
     Kp[:, 1, :] *= MG.H
     assert np.allclose(Kp.numpy(), z["gs_Ks"], rtol=1e-6) and np.allclose(torch.linalg.inv(Es[0]).numpy(), z["gs_viewmats"], rtol=1e-6, atol=1e-6)
     assert float(z["gs_near"]) == 1.0 and float(z["gs_far"]) == 1000.0 and list(z["gs_wh"]) == [MG.W, MG.H]
+
+
+def test_ply_oracle_records_match_reference_export_ply():
+    """oracle/ply_ref.py (the checker of the GPU packer, tests/test_io.py) against the structured records the reference's OWN export_ply assembles
+    (tests/golden/ply_records.npz, oracle/make_golden_ply.py: ply_export.py:30-97 run unmodified with `plyfile` replaced by a recorder): same field
+    names, dtypes and record bytes for all four attribute layouts (full SH / DC only, with / without labels and query-class logits)."""
+    from oracle import make_golden_ply as MG
+    from oracle import ply_ref
+    z = np.load(os.path.join(GOLD, "ply_records.npz"))
+    meta = json.loads(str(z["meta"]))
+    for tag, m in meta.items():
+        s = {k: v.numpy() for k, v in MG.scene().items()}
+        data = ply_ref.export_ply_bytes(s["means"], s["scales"], s["rotations"], s["harmonics"], s["opacities"],
+                                        s["semantic_labels"] if m["with_labels"] else None, s["instance_labels"] if m["with_labels"] else None,
+                                        s["seg_query_class_logits"] if m["with_qc"] else None, save_sh_dc_only=m["dc_only"])
+        head, body = data.split(b"end_header\n", 1)
+        props = [l.split() for l in head.decode().splitlines() if l.startswith("property")]
+        assert [p[2] for p in props] == m["names"], tag
+        assert [{"float": "<f4", "int": "<i4"}[p[1]] for p in props] == m["formats"], tag
+        assert f"element {m['element']} {m['count']}" in head.decode(), tag
+        dt = np.dtype(list(zip(m["names"], m["formats"])))
+        got, want = np.frombuffer(body, dtype=dt), np.frombuffer(z[tag + "__records"].tobytes(), dtype=dt)
+        for name in m["names"]:
+            if name.startswith("scale_"):   # log(scales): numpy's logf (oracle) vs ATen's (reference) differ by at most 1 ulp on some values
+                assert np.abs(got[name].view(np.int32).astype(np.int64) - want[name].view(np.int32).astype(np.int64)).max() <= 1, (tag, name)
+            else:
+                assert np.array_equal(got[name], want[name]), (tag, name)

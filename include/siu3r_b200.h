@@ -29,6 +29,10 @@ int siu3r_abi_version(void);
 void siu3r_note_launch(int n);
 long long siu3r_launch_count(void);      /* kernels launched by this library since the last reset */
 void siu3r_reset_launch_count(void);
+/* Programmatic dependent launch of the h3 GEMM / attention / LayerNorm kernels (prologue of kernel n+1 overlaps the tail of kernel n; results
+ * are unchanged).  Default on; SIU3R_PDL=0 in the environment or siu3r_set_pdl(0) turns it off (A/B measurements). */
+int siu3r_pdl_enabled(void);
+void siu3r_set_pdl(int on);
 
 /* ---- 3D Gaussian splatting rasterizer (forward) ---------------------------------------------------------------
  * Replaces diff_gaussian_rasterization._C.rasterize_gaussians as driven by GaussianRasterizer(settings)(...) at
@@ -273,6 +277,7 @@ int siu3r_im2col_nhwc_h3(const float* x, int N, int H, int W, int C, int KH, int
                          int64_t plane, void* stream);
 /* tuning / debugging aids */
 void siu3r_gemm_h3_force(int tw);
+void siu3r_gemm_h3_set_mhalf(int on);
 void siu3r_gemm_h3_order(int order);   /* 0 = neighbouring CTA pairs share the token tile, 1 = they share the weight rows */
 int siu3r_gemm_h3_plan(int M, int N, int K, int M1, int* tw_out, int* tiles_out, int* rounds_out);
 void siu3r_flash_h3_debug_swap(int swap);

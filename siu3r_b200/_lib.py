@@ -21,6 +21,8 @@ SIGNATURES = {
     "siu3r_note_launch": (None, [_i]),
     "siu3r_launch_count": (C.c_longlong, []),
     "siu3r_reset_launch_count": (None, []),
+    "siu3r_pdl_enabled": (_i, []),
+    "siu3r_set_pdl": (None, [_i]),
     "siu3r_raster_workspace_bytes": (_l, [_i, _i, _i, _l]),
     "siu3r_raster_forward": (_i, [_i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _l, _l,
                                   C.POINTER(C.c_int64), _p, _p, _p, _p, _p, _p]),
@@ -77,6 +79,7 @@ SIGNATURES = {
     "siu3r_render_record_unpack": (_i, [_p, _l, _p, _p, _p, _p, _p]),
     # h3 mode (fp32-grade results on the fp16 tensor-core path)
     "siu3r_gemm_h3_force": (None, [_i]),
+    "siu3r_gemm_h3_set_mhalf": (None, [_i]),
     "siu3r_gemm_h3_order": (None, [_i]),
     "siu3r_gemm_h3_debug": (None, [_i]),
     "siu3r_gemm_h3_plan": (_i, [_i, _i, _i, _i, _p, _p, _p]),

@@ -44,6 +44,27 @@ static inline bool siu3r_first_use_on_device(bool (&seen)[64]) {
     return true;
 }
 
+// Programmatic dependent launch (PDL): a kernel launched through siu3r_launch_pdl may start while the previous kernel of its stream is still
+// running -- its prologue (barrier init, TMEM allocation, tensor-map prefetch) overlaps that kernel's tail -- and calls pdl_wait() before its first
+// global-memory access; pdl_wait() returns once the previous kernel has COMPLETED and its writes are visible, so stream-order semantics are
+// unchanged.  pdl_launch_dependents() lets the next kernel's CTAs be scheduled as this kernel's CTAs retire (single-wave / persistent kernels
+// call it right after pdl_wait()).  SIU3R_PDL=0 disables the launch attribute (the device instructions are then no-ops).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+extern "C" int siu3r_pdl_enabled(void);
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+static inline cudaError_t siu3r_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = siu3r_pdl_enabled() ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 // Every launch of one of OUR kernels bumps this counter (bench.py reports it as gpu_launches).
 extern "C" void siu3r_note_launch(int n);
 

@@ -116,6 +116,8 @@ flash_h3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_wait();                 // programmatic dependent launch (common.cuh): the prologue above overlapped the tail of the kernel that produced Q/K/V^T
+    pdl_launch_dependents();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tmem_O = tmem_base + 3 * FH_BN;
 
@@ -364,7 +366,7 @@ int siu3r_flash_attn_h3(const void* Q, int64_t q_bs, int64_t q_ts, int64_t q_pla
     p.vt_batch_cols = vt_batch_cols; p.vt_b_split = vt_b_split > 0 ? vt_b_split : 0x7fffffff; p.vt_extra = vt_extra; p.swap_halves = g_swap_halves;
     SIU3R_CUDA_CHECK(cudaFuncSetAttribute(flash_h3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FH_SMEM));   // per device, cheap
     dim3 grid(ceil_div(Nq, FH_BM), H, B);
-    flash_h3_kernel<<<grid, FH_THREADS, FH_SMEM, stream>>>(mq, mk, mv, p);
+    SIU3R_CUDA_CHECK(siu3r_launch_pdl(flash_h3_kernel, grid, dim3(FH_THREADS), FH_SMEM, stream, mq, mk, mv, p));
     SIU3R_LAUNCH_CHECK();
     siu3r_note_launch(1);
     return SIU3R_OK;

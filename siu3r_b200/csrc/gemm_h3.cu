@@ -50,6 +50,7 @@ enum Act { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2, ACT_MASK = 3 };
 struct H3Params {
     int N, num_kb;             // weight rows, k-blocks
     int tw, nbuf, nstages;     // token tile width, accumulator sets in TMEM (1 or 2), pipeline depth
+    int mhalf;                 // N <= 128: MMA M = 128 (64 weight rows per CTA) instead of 256 -- no tensor time is spent on padding rows
     int act; float alpha;
     int64_t ldc;               // fp32 output pitch
     int64_t ldh, plane_h;      // split output pitch / plane distance (elements)
@@ -150,9 +151,12 @@ __device__ __forceinline__ void epi_chunk_vt(const float (&v)[16], int jmax, int
 }
 
 // Epilogue of one warp: TMEM lanes [32q, 32q+32) = weight rows n, columns [c_lo, c_hi) = its share of the tile's tokens, 16 at a time.
+// mhalf (M = 128 over the CTA pair): lanes [0, 64) hold this CTA's 64 weight rows for the first half of the tile's tokens, lanes [64, 128) the
+// same rows for the second half (the accumulator is tw/2 columns wide); tok_off = token index of column 0 for this warp.
 __device__ __forceinline__ void run_epilogue(uint32_t tmem_hh, uint32_t tmem_x, int lane, int q, int c_lo, int c_hi, int n_cta, int tt,
                                              const H3Params& p, const H3Problem& pr, uint64_t* bar, uint32_t parity) {
-    const int nb = n_cta + q * 32;           // warp-uniform first weight row
+    const int nb = n_cta + (p.mhalf ? (q & 1) : q) * 32;           // warp-uniform first weight row
+    const int tok_off = p.mhalf ? (q >> 1) * (p.tw >> 1) : 0;
     const int n = nb + lane;
     const bool n_ok = n < p.N;
     const float bias = (pr.bias && n_ok) ? __ldg(pr.bias + n) : 0.0f;
@@ -184,9 +188,9 @@ __device__ __forceinline__ void run_epilogue(uint32_t tmem_hh, uint32_t tmem_x, 
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = fmaf(__uint_as_float(b[j]), H3_LO_INV, __uint_as_float(a[j]));
         Frag f;
-        int mrow = m_base + c0, jmax = 16;
+        int mrow = m_base + tok_off + c0, jmax = 16;
         if (p.conv) {
-            const int hrow = h0 + (c0 >> 4);
+            const int hrow = h0 + ((tok_off + c0) >> 4);
             f.rb = ((int64_t)img * p.H + hrow) * p.W + w0;
             f.nv = hrow < p.H ? 16 : 0;
         } else {
@@ -241,7 +245,9 @@ gemm_h3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
     const int tw = p.tw;
     const int xrows = tw >> 1;                                  // token rows staged by each CTA
     const int x_plane_bytes = xrows * 128;
-    const int stage_bytes = W_BYTES + 2 * x_plane_bytes;
+    const int wrows = p.mhalf ? W_ROWS / 2 : W_ROWS;            // weight rows per CTA
+    const int w_plane_bytes = wrows * 128, w_bytes = 2 * w_plane_bytes;
+    const int stage_bytes = w_bytes + 2 * x_plane_bytes;
     const uint32_t stage_tx = 2u * (uint32_t)stage_bytes;      // both CTAs' bytes land on the leader's barrier
     const int nstages = p.nstages, nbuf = p.nbuf;
 
@@ -261,8 +267,12 @@ gemm_h3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
     __syncthreads();
     cluster_sync_all();
     tc_fence_after();
+    // Programmatic dependent launch: everything above overlapped the previous kernel's tail; from here on its outputs are needed (TMA loads of the
+    // activations, residual reads) or overwritten.  All CTAs of this persistent grid are resident, so the next kernel may be scheduled as they retire.
+    pdl_wait();
+    pdl_launch_dependents();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t x_off = nbuf == 2 ? 128u : 256u;             // column distance hh -> x inside one accumulator set
+    const uint32_t x_off = nbuf == 2 ? 128u : 256u;             // column distance hh -> x inside one accumulator set (mhalf: tw/2 <= 128 columns each)
 
     if (warp == 0) {
         // ===================== TMA producer (both CTAs; whole warp walks the loop, one elected lane issues: see the MMA warp) =====================
@@ -276,7 +286,7 @@ gemm_h3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                 const int tcount = g ? p.ttiles1 : p.ttiles0;
                 const int wi = p.order ? tl / tcount : tl % w_pairs;
                 const int tt = p.order ? tl % tcount : tl / w_pairs;
-                const int n0 = wi * 2 * W_ROWS + (int)rank * W_ROWS;    // this CTA's 128 weight rows
+                const int n0 = wi * 2 * wrows + (int)rank * wrows;      // this CTA's weight rows
                 int m0 = tt * tw + (int)rank * xrows, img = 0, h0 = 0, w0 = 0;       // this CTA's half of the token tile
                 if (p.conv) {
                     img = tt / p.tiles_per_img;
@@ -287,7 +297,7 @@ gemm_h3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                 for (int kb = 0; kb < p.num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sW = smem + stage * stage_bytes;
-                    uint8_t* sX = sW + W_BYTES;
+                    uint8_t* sX = sW + w_bytes;
                     const uint32_t lead_full = mapa_to_cta(smem_u32(&full_bar[stage]), 0);
                     if (elect_one_sync()) {
                         if (p.dbg_mode == 2) {
@@ -316,7 +326,7 @@ gemm_h3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
         // instructions themselves are issued by one elected lane.  Issuing from inside an `if (lane == 0)` region instead makes ptxas wrap every
         // MMA into an elect / R2UR-broadcast / branch loop (~20 dependent instructions, ~100 clocks per MMA: more than a 256 x 128 x 16 MMA takes).
         if (leader) {
-            const uint32_t idesc = make_idesc_f16(2 * W_ROWS, tw);
+            const uint32_t idesc = make_idesc_f16(2 * wrows, tw);
             int stage = 0; uint32_t phase = 0;
             int it = 0;
             for (int u = cluster_id; u < num_tiles; u += num_clusters, ++it) {
@@ -330,8 +340,8 @@ gemm_h3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     const uint32_t sWh = smem_u32(smem + stage * stage_bytes);
-                    const uint64_t dWh = make_smem_desc(sWh), dWl = make_smem_desc(sWh + W_PLANE_BYTES);
-                    const uint64_t dXh = make_smem_desc(sWh + W_BYTES), dXl = make_smem_desc(sWh + W_BYTES + (uint32_t)x_plane_bytes);
+                    const uint64_t dWh = make_smem_desc(sWh), dWl = make_smem_desc(sWh + (uint32_t)w_plane_bytes);
+                    const uint64_t dXh = make_smem_desc(sWh + (uint32_t)w_bytes), dXl = make_smem_desc(sWh + (uint32_t)(w_bytes + x_plane_bytes));
                     if (elect_one_sync()) {
 #pragma unroll
                         for (int k = 0; k < (p.dbg_mode == 1 ? 0 : 4); ++k) {
@@ -354,7 +364,7 @@ gemm_h3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
         // ===================== epilogue (warps 2..17 of both CTAs) =====================
         const int q = warp & 3;                         // TMEM lane quarter this warp may access
         const int sub = (warp - 2) >> 2;                // which quarter of the tile's 16-column fragments (tw is a multiple of 16)
-        const int nfrag = tw >> 4, per = (nfrag + 3) >> 2;
+        const int nfrag = (p.mhalf ? tw >> 1 : tw) >> 4, per = (nfrag + 3) >> 2;   // 16-column fragments of this warp's lane quarter
         const int c_lo = min(nfrag, sub * per) * 16;
         const int c_hi = min(nfrag, (sub + 1) * per) * 16;
         const uint32_t lead_tempty0 = mapa_to_cta(smem_u32(&tempty_bar[0]), 0);
@@ -367,7 +377,7 @@ gemm_h3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
             const int tcount = g ? p.ttiles1 : p.ttiles0;
             const int wi = p.order ? tl / tcount : tl % w_pairs;
             const int tt = p.order ? tl % tcount : tl / w_pairs;
-            const int n_cta = wi * 2 * W_ROWS + (int)rank * W_ROWS;
+            const int n_cta = wi * 2 * wrows + (int)rank * wrows;
             // (static member selection: a runtime index into the kernel-parameter struct would force a local copy of it)
             const H3Problem prob{g ? grp.prob[1].C : grp.prob[0].C, g ? grp.prob[1].Ch : grp.prob[0].Ch, g ? grp.prob[1].bias : grp.prob[0].bias,
                                  g ? grp.prob[1].residual : grp.prob[0].residual, g ? grp.prob[1].M : grp.prob[0].M,
@@ -431,6 +441,11 @@ __global__ void __launch_bounds__(256) merge_h3_kernel(const __half* __restrict_
 int g_dbg_mode = 0;
 int g_order = 0;      // tuning aid: tile order (see H3Params::order)
 int g_force_tw = 0;   // tuning aid (tools/gemm_sweep.py): > 0 = use this token tile width wherever it is legal
+int g_mhalf = -1;     // M = 128 mode for N <= 128 (see H3Params::mhalf); SIU3R_H3_MHALF=0 turns it off (A/B measurements)
+bool use_mhalf(int N) {
+    if (g_mhalf < 0) { const char* e = getenv("SIU3R_H3_MHALF"); g_mhalf = (e && e[0] == '0') ? 0 : 1; }
+    return g_mhalf && N <= 128;
+}
 
 // Token tile width for (M [+ M1]) tokens x N weight rows x K.  Cost model per CTA pair (clocks): rounds x (k-blocks x max(tensor time, operand
 // bytes per CTA / its L2->SM share) + tile overhead).  kind::f16 rate 8192 flop/clk/SM -> the 3 MMAs of a k-step (256 x tw x 16) take 3 * tw/2 clocks, a
@@ -438,17 +453,18 @@ int g_force_tw = 0;   // tuning aid (tools/gemm_sweep.py): > 0 = use this token 
 int pick_tw(int64_t M, int N, int K, int64_t M1, bool conv, int conv_h = 0, int conv_w = 0) {
     const int w_pairs = ceil_div(N, 256);
     const int num_kb = ceil_div(K, BKH);
+    const bool mh = use_mhalf(N);
     int best = 0; double best_t = 1e30;
-    const int step = conv ? 32 : 16;
+    const int step = (conv || mh) ? 32 : 16;
     for (int tw = 32; tw <= 256; tw += step) {
-        if (g_force_tw && tw != g_force_tw) continue;
+        if (g_force_tw && g_force_tw % step == 0 && tw != g_force_tw) continue;
         int64_t T;
         if (conv) T = M * ceil_div(conv_h, tw / 16) * (conv_w / 16);
         else T = ceil_div_i64(M, tw) + (M1 > 0 ? ceil_div_i64(M1, tw) : 0);
         const int64_t tiles = (int64_t)w_pairs * T;
         const int64_t rounds = ceil_div_i64(tiles, CLUSTERS);
-        const double kb = fmax(6.0 * tw, (32768.0 + 128.0 * tw) / 42.0);
-        const double t = (double)rounds * (num_kb * kb + 700.0 + 6.0 * tw + (tw > 128 ? 10.0 * tw : 0.0));
+        const double kb = mh ? fmax(3.0 * tw, (16384.0 + 128.0 * tw) / 42.0) : fmax(6.0 * tw, (32768.0 + 128.0 * tw) / 42.0);
+        const double t = (double)rounds * (num_kb * kb + 700.0 + 6.0 * tw + (tw > 128 && !mh ? 10.0 * tw : 0.0));
         if (t < best_t * 0.999) { best_t = t; best = tw; }
     }
     return best;
@@ -472,11 +488,12 @@ int launch_h3(const CUtensorMap& w, const CUtensorMap& x, const CUtensorMap& w1,
         max_clusters[dev] = n;
         if (getenv("SIU3R_GEMM_VERBOSE")) fprintf(stderr, "[siu3r_b200] gemm_h3: %d resident clusters, %d B smem\n", n, SMEM_BYTES);
     }
-    const int stage_bytes = W_BYTES + p.tw * 128;
-    p.nbuf = p.tw <= 128 ? 2 : 1;
+    p.mhalf = use_mhalf(p.N) ? 1 : 0;
+    const int stage_bytes = (p.mhalf ? W_BYTES / 2 : W_BYTES) + p.tw * 128;
+    p.nbuf = (p.tw <= 128 || p.mhalf) ? 2 : 1;
     p.nstages = PIPE_BYTES / stage_bytes > MAX_STAGES ? MAX_STAGES : PIPE_BYTES / stage_bytes;
     const int clusters = num_tiles < max_clusters[dev] ? num_tiles : max_clusters[dev];
-    gemm_h3_kernel<<<dim3((unsigned)(2 * clusters)), THREADS, SMEM_BYTES, stream>>>(w, x, w1, x1, p, grp, w_pairs, num_tiles);
+    SIU3R_CUDA_CHECK(siu3r_launch_pdl(gemm_h3_kernel, dim3((unsigned)(2 * clusters)), dim3(THREADS), SMEM_BYTES, stream, w, x, w1, x1, p, grp, w_pairs, num_tiles));
     SIU3R_LAUNCH_CHECK();
     siu3r_note_launch(1);
     return SIU3R_OK;
@@ -497,6 +514,8 @@ extern "C" {
 
 // tuning aid: 0 = cost model, otherwise the token tile width to use (multiple of 16 / 32 for convs, <= 256)
 void siu3r_gemm_h3_force(int tw) { g_force_tw = tw; }
+// tuning aid: 1 = M = 128 MMAs for N <= 128 (default), 0 = always M = 256
+void siu3r_gemm_h3_set_mhalf(int on) { g_mhalf = on ? 1 : 0; }
 void siu3r_gemm_h3_order(int order) { g_order = order ? 1 : 0; }
 void siu3r_gemm_h3_debug(int mode) { g_dbg_mode = mode; }   // timing experiments: 1 = TMA only, 2 = MMA only (outputs are garbage)
 
@@ -563,10 +582,10 @@ int siu3r_gemm_h3(int ngroups, const int* M_host, int N, int K, const void* cons
     }
     const int M0 = M_host[0], M1 = ngroups == 2 ? M_host[1] : 0;
     const int tw = pick_tw(M0, N, K, M1, false);
-    SIU3R_REQUIRE(tw >= 32 && tw <= 256 && tw % 16 == 0);
+    SIU3R_REQUIRE(tw >= 32 && tw <= 256 && tw % (use_mhalf(N) ? 32 : 16) == 0);
     CUtensorMap mw[2], mx[2];
     for (int g = 0; g < ngroups; ++g) {
-        int r = map_rows(&mw[g], W_host[g], K, N, ldw, w_plane, W_ROWS); if (r) return r;
+        int r = map_rows(&mw[g], W_host[g], K, N, ldw, w_plane, use_mhalf(N) ? W_ROWS / 2 : W_ROWS); if (r) return r;
         r = map_rows(&mx[g], X_host[g], K, M_host[g], lda, a_plane, tw / 2); if (r) return r;
     }
     if (ngroups == 1) { mw[1] = mw[0]; mx[1] = mx[0]; }
@@ -605,7 +624,7 @@ int siu3r_conv2d_h3(int Nimg, int H, int W, int Cin, int Cout, int KH, int KW, i
     const int tw = pick_tw(Nimg, Cout, Keff, 0, true, H, W);
     SIU3R_REQUIRE(tw >= 32 && tw <= 256 && tw % 32 == 0);
     CUtensorMap mw, mx;
-    int r = map_rows(&mw, Wt, (int64_t)KH * KW * Cin, Cout, ldw, w_plane, W_ROWS); if (r) return r;
+    int r = map_rows(&mw, Wt, (int64_t)KH * KW * Cin, Cout, ldw, w_plane, use_mhalf(Cout) ? W_ROWS / 2 : W_ROWS); if (r) return r;
     {
         uint64_t dims[5] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)Nimg, 2};
         uint64_t str[4] = {(uint64_t)ldx * 2, (uint64_t)W * ldx * 2, (uint64_t)H * W * ldx * 2, (uint64_t)x_plane * 2};

@@ -35,6 +35,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                                                         float eps, const float* __restrict__ add, int64_t ldadd, int round_out, LnSeg2 g, H3Out yh) {
     int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
+    pdl_wait();                 // launched with programmatic stream serialization (common.cuh): the producer of x has completed after this
+    pdl_launch_dependents();
     if (row >= rows) return;
     if (g.x1 && row >= g.rows0) { row -= g.rows0; x = g.x1; w = g.w1; b = g.b1; y = g.y1; yh.p = g.yh1; }
     const float4* xr = reinterpret_cast<const float4*>(x + (int64_t)row * ldx);
@@ -459,10 +461,10 @@ static int layernorm_impl(const float* x, int64_t ldx, const float* w, const flo
     const int vpl = ceil_div(nvec, 32);
     const int wpb = 8;
     dim3 grid(ceil_div(rows, wpb));
-    if (vpl <= 2) layernorm_kernel<2><<<grid, wpb * 32, 0, stream>>>(x, ldx, w, b, y, ldy, rows, C, eps, add, ldadd, round_out, g, yh);
-    else if (vpl <= 6) layernorm_kernel<6><<<grid, wpb * 32, 0, stream>>>(x, ldx, w, b, y, ldy, rows, C, eps, add, ldadd, round_out, g, yh);
-    else if (vpl <= 8) layernorm_kernel<8><<<grid, wpb * 32, 0, stream>>>(x, ldx, w, b, y, ldy, rows, C, eps, add, ldadd, round_out, g, yh);
-    else layernorm_kernel<32><<<grid, wpb * 32, 0, stream>>>(x, ldx, w, b, y, ldy, rows, C, eps, add, ldadd, round_out, g, yh);
+    if (vpl <= 2) siu3r_launch_pdl(layernorm_kernel<2>, grid, dim3(wpb * 32), 0, stream, x, ldx, w, b, y, ldy, rows, C, eps, add, ldadd, round_out, g, yh);
+    else if (vpl <= 6) siu3r_launch_pdl(layernorm_kernel<6>, grid, dim3(wpb * 32), 0, stream, x, ldx, w, b, y, ldy, rows, C, eps, add, ldadd, round_out, g, yh);
+    else if (vpl <= 8) siu3r_launch_pdl(layernorm_kernel<8>, grid, dim3(wpb * 32), 0, stream, x, ldx, w, b, y, ldy, rows, C, eps, add, ldadd, round_out, g, yh);
+    else siu3r_launch_pdl(layernorm_kernel<32>, grid, dim3(wpb * 32), 0, stream, x, ldx, w, b, y, ldy, rows, C, eps, add, ldadd, round_out, g, yh);
     SIU3R_LAUNCH_CHECK();
     siu3r_note_launch(1);
     return SIU3R_OK;

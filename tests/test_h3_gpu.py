@@ -71,6 +71,39 @@ def test_gemm_h3_plain(M, N, K):
         lib.siu3r_gemm_h3_force(0)
 
 
+@pytest.mark.parametrize("M,N,K", [(2050, 128, 1024), (1000, 96, 256), (513, 21, 256), (70, 128, 64)])
+def test_gemm_h3_half_m_mode_is_bit_identical(M, N, K):
+    """N <= 128 runs M = 128 MMAs (64 weight rows per CTA, other TMEM layout); the k-order of the accumulation is the same, so the results
+    must equal the M = 256 kernel's bit for bit -- linear and conv, fp32 and plane-pair outputs, every tile width."""
+    from siu3r_b200 import ops
+    lib = ops._lib.load()
+    x, w, b = rnd(M, K, seed=21), rnd(N, K, seed=22, scale=K ** -0.5), rnd(N, seed=23)
+    res = rnd(M, N, seed=24)
+    wt = ops.Weight(w, b, H3)
+    xs = ops.split(x)
+    img = ops.split(rnd(2, 32, 48, 128, seed=25))
+    wc = ops.Weight(rnd(N, 9 * 128, seed=26, scale=0.03), b, H3)
+    rc = rnd(2, 32, 48, N, seed=27)
+    outs = {}
+    try:
+        for mode in (0, 1):
+            lib.siu3r_gemm_h3_set_mhalf(mode)
+            for tw in (0, 32, 64, 128, 192, 256):
+                lib.siu3r_gemm_h3_force(tw)
+                a = ops.gemm(xs, wt, act=1, residual=res, precision=H3)
+                s = ops.gemm(xs, wt, act=2, precision=H3, round_out=True).t.clone()
+                c = ops.conv2d(img, wc, 3, 3, pad=1, act=2, residual=rc, precision=H3)
+                outs[(mode, tw)] = (a, s, c)
+    finally:
+        lib.siu3r_gemm_h3_set_mhalf(1)
+        lib.siu3r_gemm_h3_force(0)
+    ref = F.gelu(F.linear(x.double(), w.double(), b.double())) + res.double()
+    assert rel_err(outs[(1, 0)][0], ref) < 1e-5
+    for tw in (0, 32, 64, 128, 192, 256):
+        for i in range(3):
+            assert torch.equal(outs[(0, tw)][i], outs[(1, tw)][i]), (tw, i)
+
+
 @pytest.mark.parametrize("act", [0, 1, 2])
 @pytest.mark.parametrize("split_out", [False, True])
 def test_gemm_h3_epilogue_strided(act, split_out):

@@ -160,6 +160,28 @@ def bench_conv(out):
         out.append(row)
 
 
+def bench_mhalf(out):
+    """Cout <= 128 convs / linears: M = 128 MMAs (default) against the M = 256 kernel with half of its rows padding."""
+    lib = ops._lib.load()
+    for (n, h, w_, cin, cout, k) in [(2, 512, 512, 128, 128, 3), (2, 256, 256, 256, 128, 3), (2, 512, 512, 128, 83, 1), (2, 128, 128, 256, 128, 3)]:
+        x = torch.randn(n, h, w_, cin, device=DEV)
+        w = torch.randn(cout, k * k * cin, device=DEV) / (k * k * cin) ** 0.5
+        wt3 = ops.Weight(w, torch.randn(cout, device=DEV), H3)
+        xs = ops.split(x)
+        o = torch.empty(n, h, w_, cout, device=DEV)
+        row = {"kind": "mhalf", "shape": [n, h, w_, cin, cout, k]}
+        for mode in (0, 1):
+            lib.siu3r_gemm_h3_set_mhalf(mode)
+            for tw in (0, 64, 128, 256):
+                lib.siu3r_gemm_h3_force(tw)
+                row[f"m{mode}_tw{tw}_us"] = timeit(lambda: ops.conv2d(xs, wt3, k, k, pad=k // 2, out=o, precision=H3, act=2), iters=10, warm=2)
+        lib.siu3r_gemm_h3_force(0)
+        lib.siu3r_gemm_h3_set_mhalf(1)
+        row["tflops_m1"] = 2.0 * n * h * w_ * cout * k * k * cin / row["m1_tw0_us"] / 1e6
+        print(json.dumps(row), flush=True)
+        out.append(row)
+
+
 def bench_flash(out):
     for (B, H, N) in [(2, 16, 1025), (2, 12, 1025), (8, 16, 1025)]:
         C = H * 64
@@ -212,7 +234,7 @@ if __name__ == "__main__":
     res = []
     for w in what:
         try:
-            {"gemm": bench_gemm, "conv": bench_conv, "flash": bench_flash, "model": bench_model, "epilogue": bench_epilogue, "limits": bench_limits}[w](res)
+            {"gemm": bench_gemm, "conv": bench_conv, "flash": bench_flash, "model": bench_model, "epilogue": bench_epilogue, "limits": bench_limits, "mhalf": bench_mhalf}[w](res)
         except Exception as ex:  # keep going: one failing section must not lose the others
             print(json.dumps({"kind": w, "error": repr(ex)}), flush=True)
     os.makedirs("gpurun_out", exist_ok=True)

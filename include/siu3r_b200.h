@@ -259,6 +259,16 @@ int siu3r_gemm_h3(int ngroups, const int* M_host, int N, int K, const void* cons
                   const float* const* bias_host, const float* const* residual_host, int64_t ldr, int act, float alpha, const int64_t* positions,
                   const float* rope_tab, int rope_cols, void* const* vt_host, const int* vt_cols_host, int64_t vt_ld, int64_t vt_plane, int vt_col0,
                   int unscaled_lo, void* stream);
+/* siu3r_gemm_h3 with LayerNorm fused on either side (croco/blocks.py:127-130,186-190: x + f(norm(x)) blocks):
+ *   stats_out_host[g] (int64 [M_g][2], zeroed by the caller): the launch adds the statistics (sum, sum of squares; 2^24 fixed point) of the rows it writes;
+ *   stats_in_host[g] + ln_s_host[g]: X_g are RAW rows, W_g = W*gamma, bias_g = W beta + b, ln_s[n] = sum_k gamma_k W[n,k]; computes Linear(LayerNorm(x));
+ *   C_host and Ch_host may both be given (fp32 residual stream + plane pair for the next GEMM). */
+int siu3r_gemm_h3_ln(int ngroups, const int* M_host, int N, int K, const void* const* X_host, int64_t lda, int64_t a_plane, const void* const* W_host,
+                     int64_t ldw, int64_t w_plane, float* const* C_host, int64_t ldc, void* const* Ch_host, int64_t ldh, int64_t h_plane,
+                     const float* const* bias_host, const float* const* residual_host, int64_t ldr, int act, float alpha, const int64_t* positions,
+                     const float* rope_tab, int rope_cols, void* const* vt_host, const int* vt_cols_host, int64_t vt_ld, int64_t vt_plane, int vt_col0,
+                     int unscaled_lo, const int64_t* const* stats_in_host, const float* const* ln_s_host, float ln_eps, int64_t* const* stats_out_host,
+                     void* stream);
 int siu3r_conv2d_h3(int Nimg, int H, int W, int Cin, int Cout, int KH, int KW, int pad_h, int pad_w, const void* x, int64_t ldx, int64_t x_plane,
                     const void* Wt, int64_t ldw, int64_t w_plane, float* y, int64_t ldc, void* yh, int64_t ldh, int64_t h_plane, const float* bias,
                     const float* residual, int64_t ldr, int act, void* stream);
@@ -278,6 +288,7 @@ int siu3r_im2col_nhwc_h3(const float* x, int N, int H, int W, int C, int KH, int
 /* tuning / debugging aids */
 void siu3r_gemm_h3_force(int tw);
 void siu3r_gemm_h3_set_mhalf(int on);
+void siu3r_gemm_h3_cluster_cap(int cap);
 void siu3r_gemm_h3_order(int order);   /* 0 = neighbouring CTA pairs share the token tile, 1 = they share the weight rows */
 int siu3r_gemm_h3_plan(int M, int N, int K, int M1, int* tw_out, int* tiles_out, int* rounds_out);
 void siu3r_flash_h3_debug_swap(int swap);

@@ -80,12 +80,15 @@ SIGNATURES = {
     # h3 mode (fp32-grade results on the fp16 tensor-core path)
     "siu3r_gemm_h3_force": (None, [_i]),
     "siu3r_gemm_h3_set_mhalf": (None, [_i]),
+    "siu3r_gemm_h3_cluster_cap": (None, [_i]),
     "siu3r_gemm_h3_order": (None, [_i]),
     "siu3r_gemm_h3_debug": (None, [_i]),
     "siu3r_gemm_h3_plan": (_i, [_i, _i, _i, _i, _p, _p, _p]),
     "siu3r_split_h3": (_i, [_p, _l, _l, _i, _p, _l, _l, _i, _p]),
     "siu3r_merge_h3": (_i, [_p, _l, _l, _l, _i, _p, _l, _p]),
     "siu3r_gemm_h3": (_i, [_i, _p, _i, _i, _p, _l, _l, _p, _l, _l, _p, _l, _p, _l, _l, _p, _p, _l, _i, _f, _p, _p, _i, _p, _p, _l, _l, _i, _i, _p]),
+    "siu3r_gemm_h3_ln": (_i, [_i, _p, _i, _i, _p, _l, _l, _p, _l, _l, _p, _l, _p, _l, _l, _p, _p, _l, _i, _f, _p, _p, _i, _p, _p, _l, _l, _i, _i, _p, _p,
+                              _f, _p, _p]),
     "siu3r_conv2d_h3": (_i, [_i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _l, _l, _p, _l, _l, _p, _l, _p, _l, _l, _p, _p, _l, _i, _p]),
     "siu3r_flash_h3_debug_swap": (None, [_i]),
     "siu3r_flash_attn_h3": (_i, [_p, _l, _l, _l, _i, _i, _p, _l, _l, _l, _i, _i, _p, _l, _l, _l, _i, _l, _p, _l, _l, _p, _l, _l, _l, _i, _i, _i, _i,

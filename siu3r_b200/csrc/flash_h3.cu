@@ -59,10 +59,9 @@ __device__ __forceinline__ float4 lds_v4(uint32_t saddr) {
 }
 // (p0, p1) -> packed fp16 hi pair and packed fp16 residue pair (unscaled), first element in the low half
 __device__ __forceinline__ void split_pair(float p0, float p1, uint32_t& hi2, uint32_t& lo2) {
-    const __half h0 = __float2half_rn(p0), h1 = __float2half_rn(p1);
-    const __half l0 = __float2half_rn(p0 - __half2float(h0)), l1 = __float2half_rn(p1 - __half2float(h1));
-    hi2 = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-    lo2 = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+    hi2 = h3_pack2(p0, p1);          // packed conversions: FMA pipe, not the XU pipe the exponentials run on (h3.cuh)
+    const float2 f = h3_unpack2(hi2);
+    lo2 = h3_pack2(p0 - f.x, p1 - f.y);
 }
 
 // barrier indices (double-buffered ones: index + buffer).  K / V tiles are double-buffered, the S/P accumulator is TRIPLE-buffered: P(t)

@@ -39,7 +39,8 @@ constexpr int W_PLANE_BYTES = W_ROWS * 128;    // 16 KB
 constexpr int W_BYTES = 2 * W_PLANE_BYTES;     // hi + lo
 constexpr int PIPE_BYTES = 200 * 1024;
 constexpr int MAX_STAGES = 6;
-constexpr int SMEM_BYTES = PIPE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int LN_BYTES = 2 * 256 * 8;         // fused LayerNorm: (mean, rstd) of the tokens of the tile in flight, double buffered
+constexpr int SMEM_BYTES = PIPE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + LN_BYTES;
 constexpr int EPI_WARPS = 16;                  // four warps per TMEM lane quarter (they split the token columns): the epilogue of a GELU / RoPE
                                                // tile costs more issue slots than 8 warps provide under one tile's mainloop
 constexpr int THREADS = 64 + 32 * EPI_WARPS;   // + TMA producer warp + MMA issuer warp
@@ -60,6 +61,7 @@ struct H3Params {
     int dbg_mode;              // timing experiments only (results are garbage): 1 = TMA pipeline without MMAs, 2 = MMAs without TMA loads
     int order;                 // tile order: 0 = weight pair fastest (neighbouring CTA pairs share the token tile), 1 = token tile fastest (share the weights)
     int ttiles0, ttiles1;      // token tiles of problem 0 / 1
+    float ln_inv_c, ln_eps;    // fused LayerNorm on the A operand (H3Problem::stats_in): 1 / row length, epsilon
     float lo_scale;            // factor on the lo plane of split outputs: 2^11 (GEMM operands) or 1 (attention operands, see flash_h3.cu)
     // conv mode
     int conv, H, W, Cin, KW, pad_h, pad_w, tiles_w, tiles_per_img, cblocks;
@@ -72,7 +74,13 @@ struct H3Problem {       // what differs between the problems of a grouped launc
     int M;               // rows (linear) / images (conv)
     __half* vt;          // V^T destination (hi plane) of this problem's rows, or null
     int vt_cols;         // columns of a V^T row this problem owns (>= M, multiple of 8): [M, vt_cols) is zero-filled
+    // Fused LayerNorm (linear mode).  Row statistics are int64 fixed-point pairs (sum x, sum x^2) * 2^24 per row: integer atomics add in any order
+    // to the same bits, so the statistics -- and everything downstream -- are reproducible run to run.
+    const long long* stats_in;   // consumer: the A operand is the RAW row x, the weights carry gamma; the epilogue applies rstd*(acc - mu*ln_s[n]) + bias
+    const float* ln_s;           //           ln_s[n] = sum_k gamma_k W[n,k]  (bias[n] = sum_k beta_k W[n,k] + b[n] is folded by the host)
+    long long* stats_out;        // producer: accumulates the statistics of the rows it writes (every column block adds its 32-column partial sums)
 };
+constexpr float STATS_SCALE = 16777216.0f;   // 2^24
 struct H3Group { H3Problem prob[2]; int tiles0; };
 
 struct Frag {            // where the 16 tokens of one epilogue fragment live: 16 consecutive output rows
@@ -113,11 +121,13 @@ __device__ __forceinline__ void epi_chunk(float (&v)[16], const Frag& f, int lan
     if (f.nv <= 0 || !n_ok) return;
     if (SPLIT) {
         __half* d = pr.Ch + f.rb * p.ldh + n;
+        unsigned short* du = reinterpret_cast<unsigned short*>(d);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            __half hi, lo;
-            h3_split_s(v[i], p.lo_scale, hi, lo);
-            if (i < f.nv) { d[(int64_t)i * p.ldh] = hi; d[(int64_t)i * p.ldh + p.plane_h] = lo; }
+        for (int i = 0; i < 16; i += 2) {      // two tokens per packed conversion (h3.cuh)
+            uint32_t hi2, lo2;
+            h3_split2_s(v[i], v[i + 1], p.lo_scale, hi2, lo2);
+            if (i < f.nv) { du[(int64_t)i * p.ldh] = (unsigned short)hi2; du[(int64_t)i * p.ldh + p.plane_h] = (unsigned short)lo2; }
+            if (i + 1 < f.nv) { du[(int64_t)(i + 1) * p.ldh] = (unsigned short)(hi2 >> 16); du[(int64_t)(i + 1) * p.ldh + p.plane_h] = (unsigned short)(lo2 >> 16); }
         }
     } else {
         float* d = pr.C + f.rb * p.ldc + n;
@@ -154,12 +164,14 @@ __device__ __forceinline__ void epi_chunk_vt(const float (&v)[16], int jmax, int
 // mhalf (M = 128 over the CTA pair): lanes [0, 64) hold this CTA's 64 weight rows for the first half of the tile's tokens, lanes [64, 128) the
 // same rows for the second half (the accumulator is tw/2 columns wide); tok_off = token index of column 0 for this warp.
 __device__ __forceinline__ void run_epilogue(uint32_t tmem_hh, uint32_t tmem_x, int lane, int q, int c_lo, int c_hi, int n_cta, int tt,
-                                             const H3Params& p, const H3Problem& pr, uint64_t* bar, uint32_t parity) {
+                                             const H3Params& p, const H3Problem& pr, uint64_t* bar, uint32_t parity, float2* ln_mr, int epi_tid) {
     const int nb = n_cta + (p.mhalf ? (q & 1) : q) * 32;           // warp-uniform first weight row
     const int tok_off = p.mhalf ? (q >> 1) * (p.tw >> 1) : 0;
     const int n = nb + lane;
     const bool n_ok = n < p.N;
     const float bias = (pr.bias && n_ok) ? __ldg(pr.bias + n) : 0.0f;
+    const bool ln = pr.stats_in != nullptr;
+    const float ln_s = (ln && n_ok) ? __ldg(pr.ln_s + n) : 0.0f;
     const int act = p.act & ACT_MASK;
     const bool rope = p.rope_pos != nullptr && nb < p.rope_cols;
     const bool res = pr.residual != nullptr;
@@ -174,6 +186,21 @@ __device__ __forceinline__ void run_epilogue(uint32_t tmem_hh, uint32_t tmem_x, 
         const int rem = tt - img * p.tiles_per_img;
         h0 = (rem / p.tiles_w) * (p.tw >> 4);
         w0 = (rem % p.tiles_w) * 16;
+    }
+    if (ln) {
+        // Fused LayerNorm of the A operand: (mean, rstd) of the tile's tokens, once per CTA and tile, while the tile's MMAs are still running
+        // (one token per epilogue thread; float64 for the E[x^2] - mean^2 cancellation).
+        for (int t = epi_tid; t < p.tw; t += EPI_WARPS * 32) {
+            float2 mr = make_float2(0.0f, 0.0f);
+            if (m_base + t < pr.M) {
+                const longlong2 st = __ldcg(reinterpret_cast<const longlong2*>(pr.stats_in) + (m_base + t));
+                const double m = (double)st.x * (double)(p.ln_inv_c / STATS_SCALE);
+                const double var = fmax((double)st.y * (double)(p.ln_inv_c / STATS_SCALE) - m * m, 0.0);
+                mr = make_float2((float)m, rsqrtf((float)var + p.ln_eps));
+            }
+            ln_mr[t] = mr;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
     }
     mbar_wait(bar, parity);
     tc_fence_after();
@@ -198,6 +225,14 @@ __device__ __forceinline__ void run_epilogue(uint32_t tmem_hh, uint32_t tmem_x, 
             if (jmax <= 0) break;
             f.rb = mrow;
             f.nv = jmax;
+            if (ln) {   // acc -> rstd * (acc - mean * s_n); the (mean, rstd) pairs are warp-uniform shared-memory broadcasts
+                const float2* mr = ln_mr + tok_off + c0;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float2 t = mr[j];
+                    v[j] = t.y * fmaf(-t.x, ln_s, v[j]);
+                }
+            }
             if (pr.vt != nullptr && nb >= p.vt_col0) {        // warp-uniform: a 32-column block never straddles vt_col0 (multiple of 64)
                 epi_chunk_vt(v, jmax, n, n_ok, bias, mrow, p, pr);
                 continue;
@@ -219,6 +254,38 @@ __device__ __forceinline__ void run_epilogue(uint32_t tmem_hh, uint32_t tmem_x, 
             case 12: epi_chunk<ACT_RELU, false, true, false>(v, f, lane, n, n_ok, bias, axis, mrow, jmax, p, pr); break;
             default: epi_chunk<ACT_RELU, false, true, true>(v, f, lane, n, n_ok, bias, axis, mrow, jmax, p, pr); break;
         }
+        // v[] now holds the final values of this fragment (16 tokens x this lane's column n)
+        if (split && pr.C != nullptr && f.nv > 0 && n_ok) {     // dual output: the plane pair went out above, the fp32 copy (residual stream) here
+            float* d = pr.C + f.rb * p.ldc + n;
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                if (i < f.nv) d[(int64_t)i * p.ldc] = v[i];
+        }
+        if (pr.stats_out != nullptr) {
+            // Row statistics for a LayerNorm fused into the NEXT GEMM: 32 values per lane (16 sums, 16 sums of squares) are reduced over the warp's 32
+            // columns by a halving butterfly (31 shuffles); lane l ends up with statistic l >> 4 of token l & 15 and adds it, as a 2^-24 fixed-point
+            // integer, to the row's accumulator.
+            float w[32];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float x = (j < f.nv && n_ok) ? v[j] : 0.0f;
+                w[j] = x; w[16 + j] = x * x;
+            }
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+                const bool up = (lane & off) != 0;
+#pragma unroll
+                for (int i = 0; i < off; ++i) {
+                    const float send = up ? w[i] : w[i + off];
+                    const float keep = up ? w[i + off] : w[i];
+                    w[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                }
+            }
+            const int tj = lane & 15;
+            if (tj < f.nv)
+                atomicAdd(reinterpret_cast<unsigned long long*>(pr.stats_out) + (f.rb + tj) * 2 + (lane >> 4),
+                          (unsigned long long)__float2ll_rn(w[0] * STATS_SCALE));
+        }
     }
 }
 
@@ -235,6 +302,7 @@ gemm_h3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
     uint64_t* tfull_bar = empty_bar + MAX_STAGES;
     uint64_t* tempty_bar = tfull_bar + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    float2* ln_smem = reinterpret_cast<float2*>(smem + PIPE_BYTES + 256);
 
     // warp index through a shuffle broadcast: tells the compiler it is warp-uniform (the role dispatch and every loop bound derived from it stay on
     // the uniform datapath, and the epilogue's shuffles compile without the WARPSYNC.COLLECTIVE fallback)
@@ -381,9 +449,12 @@ gemm_h3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
             // (static member selection: a runtime index into the kernel-parameter struct would force a local copy of it)
             const H3Problem prob{g ? grp.prob[1].C : grp.prob[0].C, g ? grp.prob[1].Ch : grp.prob[0].Ch, g ? grp.prob[1].bias : grp.prob[0].bias,
                                  g ? grp.prob[1].residual : grp.prob[0].residual, g ? grp.prob[1].M : grp.prob[0].M,
-                                 g ? grp.prob[1].vt : grp.prob[0].vt, g ? grp.prob[1].vt_cols : grp.prob[0].vt_cols};
+                                 g ? grp.prob[1].vt : grp.prob[0].vt, g ? grp.prob[1].vt_cols : grp.prob[0].vt_cols,
+                                 g ? grp.prob[1].stats_in : grp.prob[0].stats_in, g ? grp.prob[1].ln_s : grp.prob[0].ln_s,
+                                 g ? grp.prob[1].stats_out : grp.prob[0].stats_out};
             const uint32_t acc_hh = tmem_base + (uint32_t)(buf * 256);
-            run_epilogue(acc_hh, acc_hh + x_off, lane, q, c_lo, c_hi, n_cta, tt, p, prob, &tfull_bar[buf], use & 1u);
+            run_epilogue(acc_hh, acc_hh + x_off, lane, q, c_lo, c_hi, n_cta, tt, p, prob, &tfull_bar[buf], use & 1u, ln_smem + (it & 1) * 256,
+                         (int)threadIdx.x - 64);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(lead_tempty0 + (uint32_t)(buf * 8));
@@ -441,6 +512,7 @@ __global__ void __launch_bounds__(256) merge_h3_kernel(const __half* __restrict_
 int g_dbg_mode = 0;
 int g_order = 0;      // tuning aid: tile order (see H3Params::order)
 int g_force_tw = 0;   // tuning aid (tools/gemm_sweep.py): > 0 = use this token tile width wherever it is legal
+int g_cluster_cap = 0; // > 0: a launch uses at most this many CTA pairs (siu3r_gemm_h3_cluster_cap)
 int g_mhalf = -1;     // M = 128 mode for N <= 128 (see H3Params::mhalf); SIU3R_H3_MHALF=0 turns it off (A/B measurements)
 bool use_mhalf(int N) {
     if (g_mhalf < 0) { const char* e = getenv("SIU3R_H3_MHALF"); g_mhalf = (e && e[0] == '0') ? 0 : 1; }
@@ -492,7 +564,8 @@ int launch_h3(const CUtensorMap& w, const CUtensorMap& x, const CUtensorMap& w1,
     const int stage_bytes = (p.mhalf ? W_BYTES / 2 : W_BYTES) + p.tw * 128;
     p.nbuf = (p.tw <= 128 || p.mhalf) ? 2 : 1;
     p.nstages = PIPE_BYTES / stage_bytes > MAX_STAGES ? MAX_STAGES : PIPE_BYTES / stage_bytes;
-    const int clusters = num_tiles < max_clusters[dev] ? num_tiles : max_clusters[dev];
+    int clusters = num_tiles < max_clusters[dev] ? num_tiles : max_clusters[dev];
+    if (g_cluster_cap > 0 && clusters > g_cluster_cap) clusters = g_cluster_cap;
     SIU3R_CUDA_CHECK(siu3r_launch_pdl(gemm_h3_kernel, dim3((unsigned)(2 * clusters)), dim3(THREADS), SMEM_BYTES, stream, w, x, w1, x1, p, grp, w_pairs, num_tiles));
     SIU3R_LAUNCH_CHECK();
     siu3r_note_launch(1);
@@ -514,6 +587,9 @@ extern "C" {
 
 // tuning aid: 0 = cost model, otherwise the token tile width to use (multiple of 16 / 32 for convs, <= 256)
 void siu3r_gemm_h3_force(int tw) { g_force_tw = tw; }
+// Scheduling aid for concurrent branches: launches issued while cap > 0 occupy at most `cap` of the 74 CTA pairs, so that a latency-bound chain of
+// small kernels on a high-priority stream (the Mask2Former decoder next to the DPT heads) always finds free SMs; 0 = no cap (default).
+void siu3r_gemm_h3_cluster_cap(int cap) { g_cluster_cap = cap > 0 ? cap : 0; }
 // tuning aid: 1 = M = 128 MMAs for N <= 128 (default), 0 = always M = 256
 void siu3r_gemm_h3_set_mhalf(int on) { g_mhalf = on ? 1 : 0; }
 void siu3r_gemm_h3_order(int order) { g_order = order ? 1 : 0; }
@@ -560,17 +636,26 @@ int siu3r_merge_h3(const void* in, int64_t ldi, int64_t plane, int64_t rows, int
 // unscaled_lo != 0: the split outputs (Ch and V^T) carry lo = fp16(x - hi) without the 2^11 factor (operands of siu3r_flash_attn_h3).
 // Pointer arrays are HOST arrays of device pointers.  This is how the two decoder streams of AsymmetricCroCo (dec_blocks / dec_blocks2:
 // backbone_croco.py:244-250, :514-531) share the machine; ngroups = 1 is the plain nn.Linear replacement.
-int siu3r_gemm_h3(int ngroups, const int* M_host, int N, int K, const void* const* X_host, int64_t lda, int64_t a_plane, const void* const* W_host,
-                  int64_t ldw, int64_t w_plane, float* const* C_host, int64_t ldc, void* const* Ch_host, int64_t ldh, int64_t h_plane,
-                  const float* const* bias_host, const float* const* residual_host, int64_t ldr, int act, float alpha, const int64_t* positions,
-                  const float* rope_tab, int rope_cols, void* const* vt_host, const int* vt_cols_host, int64_t vt_ld, int64_t vt_plane, int vt_col0,
-                  int unscaled_lo, void* stream_) {
+// Fused-LayerNorm extension of siu3r_gemm_h3 (same arguments, plus):
+//   stats_out_g != null: the launch also accumulates the row statistics (sum, sum of squares, 2^24 fixed point, int64 pairs, ZEROED by the caller) of
+//     the rows it writes -- the producer half of a LayerNorm fused into the GEMM that consumes these rows next;
+//   stats_in_g != null (with ln_s_g): X_g holds the RAW rows, W_g = W * gamma, bias_g = W beta + b, ln_s_g[n] = sum_k gamma_k W[n,k]; the epilogue applies
+//     rstd_m * (acc - mean_m * ln_s[n]) + bias[n] before activation / RoPE  ==  Linear(LayerNorm(x)) (croco/blocks.py:127-130,186-190).  alpha must be 1.
+//   C_host and Ch_host may BOTH be given: the result goes out as fp32 (the residual stream) and as a plane pair (the next GEMM's operand).
+int siu3r_gemm_h3_ln(int ngroups, const int* M_host, int N, int K, const void* const* X_host, int64_t lda, int64_t a_plane, const void* const* W_host,
+                     int64_t ldw, int64_t w_plane, float* const* C_host, int64_t ldc, void* const* Ch_host, int64_t ldh, int64_t h_plane,
+                     const float* const* bias_host, const float* const* residual_host, int64_t ldr, int act, float alpha, const int64_t* positions,
+                     const float* rope_tab, int rope_cols, void* const* vt_host, const int* vt_cols_host, int64_t vt_ld, int64_t vt_plane, int vt_col0,
+                     int unscaled_lo, const int64_t* const* stats_in_host, const float* const* ln_s_host, float ln_eps, int64_t* const* stats_out_host,
+                     void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     SIU3R_REQUIRE((ngroups == 1 || ngroups == 2) && M_host && X_host && W_host && N > 0 && K > 0);
-    SIU3R_REQUIRE((C_host != nullptr) != (Ch_host != nullptr));
+    SIU3R_REQUIRE(C_host != nullptr || Ch_host != nullptr);
     for (int g = 0; g < ngroups; ++g) {
         SIU3R_REQUIRE(M_host[g] > 0 && plane_ok(X_host[g], lda, a_plane) && plane_ok(W_host[g], ldw, w_plane));
-        SIU3R_REQUIRE(C_host ? C_host[g] != nullptr : (Ch_host[g] != nullptr && ((uintptr_t)Ch_host[g] & 1) == 0));
+        SIU3R_REQUIRE((!C_host || C_host[g] != nullptr) && (!Ch_host || (Ch_host[g] != nullptr && ((uintptr_t)Ch_host[g] & 1) == 0)));
+        if (stats_in_host) SIU3R_REQUIRE(stats_in_host[g] && ((uintptr_t)stats_in_host[g] & 15) == 0 && ln_s_host && ln_s_host[g] && alpha == 1.0f);
+        if (stats_out_host) SIU3R_REQUIRE(stats_out_host[g] && ((uintptr_t)stats_out_host[g] & 15) == 0);
     }
     SIU3R_REQUIRE(lda >= K && ldw >= K && (act & ~ACT_MASK) == 0);
     if (positions) SIU3R_REQUIRE(rope_tab && rope_cols > 0 && rope_cols % 64 == 0 && rope_cols <= N && ((uintptr_t)rope_tab & 15) == 0 && !residual_host);
@@ -593,18 +678,31 @@ int siu3r_gemm_h3(int ngroups, const int* M_host, int N, int K, const void* cons
     p.N = N; p.num_kb = ceil_div(K, BKH); p.tw = tw; p.act = act; p.alpha = alpha; p.ldc = ldc; p.ldh = ldh; p.plane_h = h_plane; p.ldr = ldr;
     p.rope_pos = (const long long*)positions; p.rope_tab = rope_tab; p.rope_cols = rope_cols;
     p.vt_col0 = vt_col0; p.vt_ld = vt_ld; p.vt_plane = vt_plane; p.conv = 0; p.lo_scale = unscaled_lo ? 1.0f : H3_LO_SCALE;
+    p.ln_inv_c = 1.0f / (float)K; p.ln_eps = ln_eps;
     const int w_pairs = ceil_div(N, 256);
     H3Group grp{};
     for (int g = 0; g < 2; ++g) {
         const int s = g < ngroups ? g : 0;
         grp.prob[g] = H3Problem{C_host ? C_host[s] : nullptr, Ch_host ? (__half*)Ch_host[s] : nullptr, bias_host ? bias_host[s] : nullptr,
                                 residual_host ? residual_host[s] : nullptr, M_host[s], vt_host ? (__half*)vt_host[s] : nullptr,
-                                vt_cols_host ? vt_cols_host[s] : 0};
+                                vt_cols_host ? vt_cols_host[s] : 0, stats_in_host ? (const long long*)stats_in_host[s] : nullptr,
+                                ln_s_host ? ln_s_host[s] : nullptr, stats_out_host ? (long long*)stats_out_host[s] : nullptr};
     }
     grp.tiles0 = w_pairs * ceil_div(M0, tw);
     p.ttiles0 = ceil_div(M0, tw); p.ttiles1 = ngroups == 2 ? ceil_div(M1, tw) : 1; p.order = g_order; p.dbg_mode = g_dbg_mode;
     const int tiles = grp.tiles0 + (ngroups == 2 ? w_pairs * ceil_div(M1, tw) : 0);
     return launch_h3(mw[0], mx[0], mw[1], mx[1], p, grp, w_pairs, tiles, stream);
+}
+
+int siu3r_gemm_h3(int ngroups, const int* M_host, int N, int K, const void* const* X_host, int64_t lda, int64_t a_plane, const void* const* W_host,
+                  int64_t ldw, int64_t w_plane, float* const* C_host, int64_t ldc, void* const* Ch_host, int64_t ldh, int64_t h_plane,
+                  const float* const* bias_host, const float* const* residual_host, int64_t ldr, int act, float alpha, const int64_t* positions,
+                  const float* rope_tab, int rope_cols, void* const* vt_host, const int* vt_cols_host, int64_t vt_ld, int64_t vt_plane, int vt_col0,
+                  int unscaled_lo, void* stream_) {
+    SIU3R_REQUIRE((C_host != nullptr) != (Ch_host != nullptr));
+    return siu3r_gemm_h3_ln(ngroups, M_host, N, K, X_host, lda, a_plane, W_host, ldw, w_plane, C_host, ldc, Ch_host, ldh, h_plane, bias_host, residual_host,
+                            ldr, act, alpha, positions, rope_tab, rope_cols, vt_host, vt_cols_host, vt_ld, vt_plane, vt_col0, unscaled_lo, nullptr, nullptr,
+                            0.0f, nullptr, stream_);
 }
 
 // Stride-1 KH x KW convolution with "same"-size output, NHWC:  y[n,h,w,co] = act(sum x[n,h+kh-pad_h,w+kw-pad_w,ci] Wt[co,(kh,kw,ci)] + bias) + residual

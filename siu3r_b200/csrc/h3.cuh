@@ -23,32 +23,32 @@
 #define H3_LO_SCALE 2048.0f
 #define H3_LO_INV 4.8828125e-4f   // 2^-11
 
-__device__ __forceinline__ void h3_split(float x, __half& hi, __half& lo) {
-    const float xc = fminf(fmaxf(x, -65504.0f), 65504.0f);
-    hi = __float2half_rn(xc);
-    lo = __float2half_rn((xc - __half2float(hi)) * H3_LO_SCALE);
+// fp32 -> fp16 conversions go through the PACKED form (cvt.rn.f16x2.f32 = F2FP.F16.F32.PACK_AB, an FMA-pipe instruction converting two values);
+// the scalar cvt.rn.f16.f32 (F2F.F16.F32) issues on the XU pipe -- 16 lanes/clk/SM, shared with MUFU.EX2 -- and made the softmax of flash_h3.cu and
+// the plane-pair epilogues XU-bound.  fp16 -> fp32 is HADD2.F32 (fp16 FMA pipe).
+__device__ __forceinline__ uint32_t h3_pack2(float first, float second) {     // first -> low half, second -> high half
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(second), "f"(first));
+    return r;
 }
-__device__ __forceinline__ void h3_split_s(float x, float lo_scale, __half& hi, __half& lo) {
-    const float xc = fminf(fmaxf(x, -65504.0f), 65504.0f);
-    hi = __float2half_rn(xc);
-    lo = __float2half_rn((xc - __half2float(hi)) * lo_scale);
-}
-// two consecutive elements -> packed (low half = first element)
-__device__ __forceinline__ void h3_split2(float x0, float x1, uint32_t& hi2, uint32_t& lo2) {
-    __half h0, l0, h1, l1;
-    h3_split(x0, h0, l0);
-    h3_split(x1, h1, l1);
-    hi2 = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-    lo2 = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
-}
+__device__ __forceinline__ float2 h3_unpack2(uint32_t h2) { return __half22float2(*reinterpret_cast<const __half2*>(&h2)); }
+__device__ __forceinline__ float h3_clamp(float x) { return fminf(fmaxf(x, -65504.0f), 65504.0f); }
 
+// two consecutive elements -> packed (hi, hi) and (lo, lo) pairs, first element in the low half; lo = fp16((x - hi) * lo_scale)
 __device__ __forceinline__ void h3_split2_s(float x0, float x1, float lo_scale, uint32_t& hi2, uint32_t& lo2) {
-    __half h0, l0, h1, l1;
-    h3_split_s(x0, lo_scale, h0, l0);
-    h3_split_s(x1, lo_scale, h1, l1);
-    hi2 = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-    lo2 = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+    const float c0 = h3_clamp(x0), c1 = h3_clamp(x1);
+    hi2 = h3_pack2(c0, c1);
+    const float2 f = h3_unpack2(hi2);
+    lo2 = h3_pack2((c0 - f.x) * lo_scale, (c1 - f.y) * lo_scale);
 }
+__device__ __forceinline__ void h3_split2(float x0, float x1, uint32_t& hi2, uint32_t& lo2) { h3_split2_s(x0, x1, H3_LO_SCALE, hi2, lo2); }
+__device__ __forceinline__ void h3_split_s(float x, float lo_scale, __half& hi, __half& lo) {
+    uint32_t h2, l2;
+    h3_split2_s(x, 0.0f, lo_scale, h2, l2);
+    hi = __ushort_as_half((unsigned short)(h2 & 0xffffu));
+    lo = __ushort_as_half((unsigned short)(l2 & 0xffffu));
+}
+__device__ __forceinline__ void h3_split(float x, __half& hi, __half& lo) { h3_split_s(x, H3_LO_SCALE, hi, lo); }
 
 namespace h3 {
 

@@ -9,6 +9,7 @@ torch.cat((img1, img2), 0) (backbone_croco.py:174-176): row block i = v * B + b.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, field
 from types import SimpleNamespace
 
@@ -24,6 +25,10 @@ PANOPTIC_SEMANTIC2NAME = {1: "wall", 2: "floor", 3: "cabinet", 4: "bed", 5: "cha
                           10: "bookshelf", 11: "picture", 12: "counter", 13: "desk", 14: "curtain", 15: "refrigerator", 16: "shower curtain",
                           17: "toilet", 18: "sink", 19: "bathtub", 20: "otherfurniture"}
 STUFF_CLASSES = [0, 1]
+# Scheduling of the two concurrent chains of a forward (A/B switches for measurements; results do not depend on them)
+SEG_PRIORITY = os.environ.get("SIU3R_SEG_PRIORITY", "1") != "0"          # panoptic chain on a high-priority stream
+FUSE_LN = os.environ.get("SIU3R_FUSE_LN", "1") != "0"                    # h3: LayerNorm of the ViT blocks fused into the adjacent GEMM epilogues
+HEAD_CLUSTER_CAP = int(os.environ.get("SIU3R_HEAD_CLUSTER_CAP", "70"))   # CTA pairs (of 74) the decoder / head GEMMs may occupy next to it; 0 = all
 
 
 @dataclass
@@ -151,6 +156,15 @@ class SIU3RModel:
                                               cproj=P.linear(p + "cross_attn.proj"), fc1=P.linear(p + "mlp.fc1"), fc2=P.linear(p + "mlp.fc2")))
             w.dec.append(blocks)
         w.dec_norm = (P.vec("backbone.dec_norm.weight"), P.vec("backbone.dec_norm.bias"))
+        self.fuse_ln = self.prec == ops.PREC_H3 and FUSE_LN
+        if self.fuse_ln:
+            # LayerNorm folded into the consuming projection (ops.Weight.fold_ln): norm1 -> qkv, norm2 -> fc1 (encoder); norm1 -> qkv, norm_y -> k|v,
+            # norm2 -> q, norm3 -> fc1 (decoder).  The un-folded weights stay: block 0 of the encoder and the un-fused reference path use them.
+            for bk in w.enc:
+                bk.qkv_ln, bk.fc1_ln = bk.qkv.fold_ln(*bk.n1), bk.fc1.fold_ln(*bk.n2)
+            for blocks in w.dec:
+                for bk in blocks:
+                    bk.qkv_ln, bk.ckv_ln, bk.cq_ln, bk.fc1_ln = bk.qkv.fold_ln(*bk.n1), bk.ckv.fold_ln(*bk.ny), bk.cq.fold_ln(*bk.n2), bk.fc1.fold_ln(*bk.n3)
         # DPT heads
         w.heads = {}
         for hname in ("downstream_head1", "downstream_head2", "gaussian_param_head1", "gaussian_param_head2"):
@@ -346,12 +360,14 @@ class SIU3RModel:
             return ops.resize_bilinear_h3(x, OH, OW, align)
         return ops.resize_bilinear(x, OH, OW, align, round_out=self.R)
 
-    def _self_attn(self, h, blk, pos, Bn, N, C, nh):
+    def _self_attn(self, h, blk, pos, Bn, N, C, nh, ln_stats=None):
         M = Bn * N
         if self.S:   # h3: q | k as an unscaled plane pair (RoPE in the epilogue), V^T plane pair written by the same launch, plane-pair output
             qkv = ops.Split.empty(M, 3 * C, device=self.dev, unscaled=True)
             vth = ops.Split.empty(C, (M + 7) // 8 * 8, device=self.dev, unscaled=True)
-            self._lin(h, blk.qkv, ro=True, out=qkv, rope=(pos, self._k.rope_tab, 2 * C), vt=(vth, 2 * C, {}), unscaled=True)
+            # ln_stats: h is the RAW residual stream and norm1 rides in the projection's epilogue
+            self._lin(h, blk.qkv if ln_stats is None else blk.qkv_ln, ro=True, out=qkv, rope=(pos, self._k.rope_tab, 2 * C), vt=(vth, 2 * C, {}),
+                      unscaled=True, ln_stats=ln_stats)
             return ops.flash_attn_h3(qkv, 0, qkv, C, vth, N, Bn, nh, N, N, 0.125, split_out=True)
         vt = st = None
         if self.R:   # the V third of the projection is written as V^T by the GEMM epilogue (no transpose pass)
@@ -369,6 +385,8 @@ class SIU3RModel:
     def _encoder(self, x, pos, Bn, N):
         """24 x Block (croco/blocks.py:127-130).  The residual stream is updated in place, except that the outputs of the
         blocks the adapter reads (interaction_indexes) are frozen: the following block writes into a fresh buffer."""
+        if self.fuse_ln:
+            return self._encoder_fused(x, pos, Bn, N)
         keep = {}
         C = 1024
         frozen = False
@@ -390,6 +408,41 @@ class SIU3RModel:
                 ev = torch.cuda.Event()
                 ev.record()
                 self._keep_ev[i] = ev   # the adapter stream starts interaction #k as soon as its ViT block is done
+        return x, keep
+
+    def _encoder_fused(self, x, pos, Bn, N):
+        """_encoder with norm1 / norm2 fused into the GEMMs around them (h3 mode): every residual-adding projection also emits the plane pair of
+        the new residual stream and its row statistics; the next projection reads the RAW rows and applies the LayerNorm in its epilogue
+        (siu3r_gemm_h3_ln).  One layernorm_kernel launch is left (block 0, whose input rows come from two different producers)."""
+        keep = {}
+        C, M = 1024, Bn * N
+        nblk = len(self.w.enc)
+        stats = torch.zeros(2 * nblk, M, 2, device=self.dev, dtype=torch.int64)   # [2i]: rows after proj of block i, [2i+1]: after its fc2
+        xs = None
+        frozen = False
+        for i, blk in enumerate(self.w.enc):
+            if i == 0:
+                a = self._self_attn(self._ln(x, blk.n1, 1e-6), blk, pos, Bn, N, C, 16)
+            else:
+                a = self._self_attn(xs, blk, pos, Bn, N, C, 16, ln_stats=stats[2 * i - 1])
+            xn = torch.empty(M, C, device=self.dev) if frozen else x      # a kept tensor stays intact: the next block writes a fresh buffer
+            frozen = False
+            xs = ops.Split.empty(M, C, device=self.dev)
+            self._lin(a, blk.proj, residual=x, out=xs, out_f32=xn, stats_out=stats[2 * i])
+            x = xn
+            f = self._lin(xs, blk.fc1_ln, ro=True, act=ACT_GELU, ln_stats=stats[2 * i])
+            if i + 1 < nblk:
+                xs = ops.Split.empty(M, C, device=self.dev)
+                self._lin(f, blk.fc2, residual=x, out=xs, out_f32=x, stats_out=stats[2 * i + 1])
+            else:
+                self._lin(f, blk.fc2, residual=x, out=x)      # enc_norm reads the fp32 stream
+            if i in self.cfg.interaction_indexes:
+                keep[i] = x
+                frozen = True
+                self._cap(f"enc{i}", x)
+                ev = torch.cuda.Event()
+                ev.record()
+                self._keep_ev[i] = ev
         return x, keep
 
     # ---- DPT heads (heads/dpt_head.py:36-79, dpt_gs_head.py:121-171, dpt_block.py) ------------------------------------
@@ -832,9 +885,58 @@ class SIU3RModel:
         self._lin2(split(m), [bk.fc2 for bk in blks], outs=split(x1), ar=True, residuals=split(x1))
         return x1
 
+    def _dec_layer_h3_fused(self, l, f, B, N):
+        """_dec_layer_h3 for V = 2 with norm1 / norm_y / norm2 / norm3 fused into the projections that consume them (siu3r_gemm_h3_ln): the
+        residual-adding projections emit fp32 rows + plane pair + row statistics, the consumers read the raw plane pair."""
+        C, nh, V = 768, 12, 2
+        dev = self.dev
+        blks = (self.w.dec[0][l], self.w.dec[1][l])
+        R0, R = B * N, V * B * N
+        rows = ((0, R0), (R0, R))
+        pos, tab = self._k.pos_enc, self._k.rope_tab
+        sp = lambda t: [t[a:b] for a, b in rows]
+        W0 = (R0 + 7) // 8 * 8
+        W1 = (R - R0 + 7) // 8 * 8
+        st = self._dec_fused
+        fs, s_in, sA, sB, sC = st["fs"], st["stats"][3 * l], st["stats"][3 * l + 1], st["stats"][3 * l + 2], st["stats"][3 * l + 3]
+
+        def vt_buf():
+            buf = ops.Split.empty(C, W0 + W1, device=dev, unscaled=True)
+            return buf, [buf[:, :W0], buf[:, W0:]]
+        # ---- self-attention: norm1 inside the qkv projection ----
+        qkv = ops.Split.empty(R, 3 * C, device=dev, unscaled=True)
+        vb, wins = vt_buf()
+        self._lin2(sp(fs), [bk.qkv_ln for bk in blks], outs=sp(qkv), ro=True, rope=(pos, tab, 2 * C), vt=(wins, [W0, W1], 2 * C, {}), unscaled=True,
+                   ln_stats=sp(s_in))
+        att = ops.flash_attn_h3(qkv, 0, qkv, C, vb, N, V * B, nh, N, N, 0.125, split_out=True, vt_b_split=B, vt_extra=W0 - R0)
+        x1 = torch.empty(R, C, device=dev)
+        x1s = ops.Split.empty(R, C, device=dev)
+        self._lin2(sp(att), [bk.proj for bk in blks], outs=sp(x1s), outs_f32=sp(x1), residuals=sp(f), stats_out=sp(sA))
+        # ---- cross-attention memory: norm_y inside the k|v projection (stream 0 reads view 1's rows and vice versa) ----
+        ctx = ops.Split.empty(R, 2 * C, device=dev, unscaled=True)
+        vb2, wins2 = vt_buf()
+        self._lin2([fs[R0:], fs[:R0]], [bk.ckv_ln for bk in blks], outs=sp(ctx), ro=True, rope=(pos, tab, C), vt=(wins2, [W0, W1], C, {}), unscaled=True,
+                   ln_stats=[s_in[R0:], s_in[:R0]])
+        q = ops.Split.empty(R, C, device=dev, unscaled=True)
+        self._lin2(sp(x1s), [bk.cq_ln for bk in blks], outs=sp(q), ro=True, rope=(pos, tab, C), unscaled=True, ln_stats=sp(sA))
+        a2 = ops.flash_attn_h3(q, 0, ctx, 0, vb2, N, V * B, nh, N, N, 0.125, split_out=True, vt_b_split=B, vt_extra=W0 - R0)
+        x2s = ops.Split.empty(R, C, device=dev)
+        self._lin2(sp(a2), [bk.cproj for bk in blks], outs=sp(x2s), outs_f32=sp(x1), residuals=sp(x1), stats_out=sp(sB))
+        # ---- MLP: norm3 inside fc1 ----
+        m = ops.Split.empty(R, 4 * C, device=dev)
+        self._lin2(sp(x2s), [bk.fc1_ln for bk in blks], outs=sp(m), ro=True, act=ACT_GELU, ln_stats=sp(sB))
+        if l + 1 < self.cfg.dec_depth:
+            st["fs"] = ops.Split.empty(R, C, device=dev)
+            self._lin2(sp(m), [bk.fc2 for bk in blks], outs=sp(st["fs"]), outs_f32=sp(x1), residuals=sp(x1), stats_out=sp(sC))
+        else:
+            self._lin2(sp(m), [bk.fc2 for bk in blks], outs=sp(x1), residuals=sp(x1))     # dec_norm reads the fp32 rows
+        return x1
+
     def _dec_layer_h3(self, l, f, B, N, V):
         """_dec_layer in h3 mode: every GEMM operand is an fp16 plane pair written by its producer (LayerNorm, projection epilogue, attention
         epilogue); q / k / V^T of both attentions are unscaled plane pairs (flash_h3.cu)."""
+        if getattr(self, "_dec_fused", None) is not None:
+            return self._dec_layer_h3_fused(l, f, B, N)
         C, nh = 768, 12
         dev = self.dev
         blks = (self.w.dec[0][l], self.w.dec[1][l])
@@ -907,6 +1009,12 @@ class SIU3RModel:
         return x1
 
     def _forward_device(self, imgs, Kin):
+        try:
+            return self._forward_device_impl(imgs, Kin)
+        finally:
+            ops._lib.load().siu3r_gemm_h3_cluster_cap(0)
+
+    def _forward_device_impl(self, imgs, Kin):
         """All device work of SIU3RModel.forward / SIU3RMultiViewModel.forward up to (and excluding) the host-assisted panoptic
         post-process.  Images are batched view-major (image j = v*B + b) in both models."""
         B, V, _, S0, S1 = imgs.shape
@@ -941,7 +1049,8 @@ class SIU3RModel:
         main = torch.cuda.current_stream()
         if not serial:
             if getattr(self, "_seg_stream", None) is None:
-                self._seg_stream = torch.cuda.Stream(device=self.dev)
+                # high priority: its tail (the Mask2Former decoder) is a chain of ~270 tiny dependent kernels that must not queue behind the heads
+                self._seg_stream = torch.cuda.Stream(device=self.dev, priority=-1 if SEG_PRIORITY else 0)
             fork = torch.cuda.Event()
             fork.record(main)
         self._mark("start")
@@ -962,10 +1071,22 @@ class SIU3RModel:
             self._seg_stream.wait_event(fork)
             with torch.cuda.stream(self._seg_stream):
                 cls_logits, mask_logits = seg_chain()
+        # The persistent GEMMs of the decoder and the heads leave a few CTA pairs free for the high-priority panoptic chain running next to them
+        # (a persistent kernel never retires a CTA early, so stream priority alone cannot get the chain's small kernels onto an SM).
+        if not serial and self.S and HEAD_CLUSTER_CAP:
+            lib.siu3r_gemm_h3_cluster_cap(HEAD_CLUSTER_CAP)     # reset by _forward_device
         feat = ops.layernorm(x, w.enc_norm[0], w.enc_norm[1], 1e-6)  # [V*B*N, 1024]
         self._cap("enc_norm", feat)
         # ---- decoder ----
-        f = self._lin(feat, w.dec_embed)  # [V*B*N, 768]
+        self._dec_fused = None
+        if self.fuse_ln and V == 2:
+            R = V * B * N
+            self._dec_fused = {"stats": torch.zeros(1 + 3 * c.dec_depth, R, 2, device=self.dev, dtype=torch.int64),
+                               "fs": ops.Split.empty(R, 768, device=self.dev)}
+            f = torch.empty(R, 768, device=self.dev)
+            self._lin(feat, w.dec_embed, out=self._dec_fused["fs"], out_f32=f, stats_out=self._dec_fused["stats"][0])
+        else:
+            f = self._lin(feat, w.dec_embed)  # [V*B*N, 768]
         # both decoder streams advance together: one grouped launch per projection, one flash launch per attention
         decs = [feat]
         for l in range(c.dec_depth):

@@ -144,7 +144,7 @@ def split_tf32(x: torch.Tensor):
 class Weight:
     """A [N, K] K-major matrix (nn.Linear.weight layout) prepared for the tensor-core path."""
 
-    __slots__ = ("w", "w_lo", "bias", "N", "K", "_rows", "h3")
+    __slots__ = ("w", "w_lo", "bias", "N", "K", "_rows", "h3", "ln_s")
 
     def __init__(self, w: torch.Tensor, bias: torch.Tensor | None, precision: int):
         w = w.contiguous().float()
@@ -165,10 +165,22 @@ class Weight:
         self.bias = None if bias is None else bias.contiguous().float()
         self._rows = None
         self.h3 = None
+        self.ln_s = None
         if precision == PREC_H3 and w.is_cuda:
             kp = (w.shape[1] + 7) // 8 * 8   # 16-byte row pitch in fp16
             self.h3 = Split(torch.zeros(2, self.N, kp, device=w.device, dtype=torch.float16))
             split(w, self.h3[:, : w.shape[1]])
+
+    def fold_ln(self, gamma: torch.Tensor, beta: torch.Tensor) -> "Weight":
+        """Linear(LayerNorm(x; gamma, beta)) with the LayerNorm folded in (h3 mode, fused-LayerNorm GEMM of siu3r_gemm_h3_ln):
+        weights W * gamma, bias W beta + b, and ln_s[n] = sum_k (W gamma)[n, k] taken over the fp16 planes the tensor cores actually multiply."""
+        assert self.h3 is not None
+        w = self.w[:, : self.K].double()
+        bias = w @ beta.double() + (self.bias.double() if self.bias is not None else 0.0)
+        r = Weight((w * gamma.double()[None, :]).float(), bias.float(), PREC_H3)
+        planes = r.h3.t[:, :, : self.K].double()
+        r.ln_s = (planes[0] + planes[1] / 2048.0).sum(1).float().contiguous()
+        return r
 
     def rowpacked(self, KH: int, KW: int, Cin: int) -> "Weight":
         """[Cout, KH*KW*Cin] conv weight re-laid as [Cout, KH*32]: the KW*Cin <= 32 taps of one filter row become one
@@ -176,7 +188,7 @@ class Weight:
         if self._rows is None:
             assert KW * Cin <= 32 and self.K == KH * KW * Cin
             r = object.__new__(Weight)
-            r.N, r.K, r.bias, r._rows = self.N, KH * 32, self.bias, None
+            r.N, r.K, r.bias, r._rows, r.ln_s = self.N, KH * 32, self.bias, None, None
 
             def relay(w):
                 if w is None:
@@ -203,7 +215,8 @@ def round_tf32(x: torch.Tensor) -> torch.Tensor:
 
 def gemm(x: torch.Tensor, wt: Weight, out: torch.Tensor | None = None, act: int = ACT_NONE, residual: torch.Tensor | None = None,
          alpha: float = 1.0, precision: int = PREC_TF32, bias: torch.Tensor | None | bool = True, M: int | None = None,
-         a_rounded: bool = False, round_out: bool = False, rope: tuple | None = None, vt: tuple | None = None, unscaled: bool = False):
+         a_rounded: bool = False, round_out: bool = False, rope: tuple | None = None, vt: tuple | None = None, unscaled: bool = False,
+         ln_stats: torch.Tensor | None = None, stats_out: torch.Tensor | None = None, out_f32: torch.Tensor | None = None):
     """out[M,N] = act(alpha * x[M,K] @ W^T + bias) + residual.  x / out / residual are 2-D row-strided views.
     rope = (positions [M,2] int64, table from rope2d_table, ncols): RoPE-2D on output columns [0, ncols) in the epilogue.
     TF32 mode: the A operand must be round-to-nearest TF32 (a_rounded=True if its producer already did that);
@@ -212,7 +225,10 @@ def gemm(x: torch.Tensor, wt: Weight, out: torch.Tensor | None = None, act: int 
         b_ = wt.bias if bias is True else (None if bias in (False, None) else bias)
         if M is not None and M != x.shape[0]:
             x = x[:M]
-        return _h3_linear([x], [wt], [out], act, [residual], alpha, [b_], rope, vt, round_out, unscaled)[0]
+        return _h3_linear([x], [wt], [out], act, [residual], alpha, [b_], rope, vt, round_out, unscaled,
+                          ln_stats=None if ln_stats is None else [ln_stats], stats_out=None if stats_out is None else [stats_out],
+                          outs_f32=None if out_f32 is None else [out_f32])[0]
+    assert ln_stats is None and stats_out is None and out_f32 is None, "fused LayerNorm exists in h3 mode only"
     _chk_f32(x, out, residual)
     assert x.dim() == 2 and x.stride(1) == 1
     M = x.shape[0] if M is None else M
@@ -280,7 +296,8 @@ def gemm(x: torch.Tensor, wt: Weight, out: torch.Tensor | None = None, act: int 
 
 
 def gemm_group2(xs, wts, outs=None, act: int = ACT_NONE, residuals=None, precision: int = PREC_TF32, a_rounded: bool = False,
-                round_out: bool = False, rope: tuple | None = None, vt: tuple | None = None, unscaled: bool = False):
+                round_out: bool = False, rope: tuple | None = None, vt: tuple | None = None, unscaled: bool = False, ln_stats=None, stats_out=None,
+                outs_f32=None):
     """Two linear layers of the same shape class (same N, K, strides, epilogue; rows may differ) in ONE persistent launch:
     outs[g] = act(xs[g] @ wts[g]^T + bias_g) + residuals[g].  Falls back to two gemm() calls when the shape / precision is not
     eligible for the grouped kernel (3xTF32 mode, tiny N or K, mismatching strides)."""
@@ -290,7 +307,8 @@ def gemm_group2(xs, wts, outs=None, act: int = ACT_NONE, residuals=None, precisi
         if vt is not None:   # vt = ([window Splits], [cols], col0, state)
             v = (vt[0], vt[2], vt[3])
         return _h3_linear(list(xs), list(wts), list(outs) if outs is not None else [None, None], act, list(residuals or [None, None]), 1.0,
-                          [w.bias for w in wts], rope, v, round_out, unscaled)
+                          [w.bias for w in wts], rope, v, round_out, unscaled, ln_stats=ln_stats, stats_out=stats_out, outs_f32=outs_f32)
+    assert ln_stats is None and stats_out is None and outs_f32 is None
     if outs is None:
         outs = [torch.empty(x.shape[0], w.N, device=x.device, dtype=torch.float32) for x, w in zip(xs, wts)]
     residuals = residuals or [None, None]
@@ -348,10 +366,14 @@ def _ptr_arr(ts):
     return (C.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
 
 
-def _h3_linear(xs, wts, outs, act, residuals, alpha, biases, rope, vt, split_out, unscaled):
+def _h3_linear(xs, wts, outs, act, residuals, alpha, biases, rope, vt, split_out, unscaled, ln_stats=None, stats_out=None, outs_f32=None,
+               ln_eps=1e-6):
     """h3 mode: outs[g] = act(alpha * xs[g] @ wts[g]^T + bias_g) [RoPE] + residuals[g] for 1 or 2 same-shape problems in one launch
     (siu3r_gemm_h3).  xs: Split plane pairs or fp32 tensors (split here, one extra pass); outs[g]: fp32 tensor, Split, or None (allocated:
-    Split if split_out else fp32).  vt = (Split [rows, ld] or [window Splits], col0, state): columns >= col0 go to V^T."""
+    Split if split_out else fp32).  vt = (Split [rows, ld] or [window Splits], col0, state): columns >= col0 go to V^T.
+    Fused LayerNorm (siu3r_gemm_h3_ln): ln_stats[g] = int64 [M_g, 2] row statistics of the RAW rows xs[g] and wts[g] = Weight.fold_ln(...) -> the
+    launch computes Linear(LayerNorm(x));  stats_out[g] = int64 [M_g, 2] (zeroed) accumulates the statistics of the rows written;  outs_f32[g]: with
+    Split outs, an additional fp32 copy of the result (the residual stream)."""
     G = len(xs)
     lib = _lib.load()
     Ms = [x.shape[0] for x in xs]
@@ -394,7 +416,12 @@ def _h3_linear(xs, wts, outs, act, residuals, alpha, biases, rope, vt, split_out
     if is_split:
         assert all(o.stride(1) == 1 and o.unscaled == unscaled for o in outs) and len({(o.stride(0), o.plane) for o in outs}) == 1
         Ch, ldh, hpl = _ptr_arr(outs), outs[0].stride(0), outs[0].plane
+        if outs_f32 is not None:
+            _chk_f32(*outs_f32)
+            assert vt is None and all(o.stride(1) == 1 and o.shape[0] == m for o, m in zip(outs_f32, Ms)) and len({o.stride(0) for o in outs_f32}) == 1
+            Cf, ldc = _ptr_arr(outs_f32), outs_f32[0].stride(0)
     else:
+        assert outs_f32 is None
         _chk_f32(*outs)
         assert all(o.stride(1) == 1 for o in outs) and len({o.stride(0) for o in outs}) == 1
         Cf, ldc = _ptr_arr(outs), outs[0].stride(0)
@@ -421,11 +448,19 @@ def _h3_linear(xs, wts, outs, act, residuals, alpha, biases, rope, vt, split_out
         vt_ld, vt_pl = wins[0].stride(0), wins[0].plane
         state["ok"] = True
     Mh = (C.c_int * G)(*Ms)
+    st_in = ln_s = st_out = None
+    if ln_stats is not None:
+        assert alpha == 1.0 and all(w.ln_s is not None for w in wts), "fused LayerNorm needs Weight.fold_ln() weights"
+        assert all(s_.dtype == torch.int64 and s_.is_contiguous() and s_.shape == (m, 2) for s_, m in zip(ln_stats, Ms))
+        st_in, ln_s = _ptr_arr(ln_stats), _ptr_arr([w.ln_s for w in wts])
+    if stats_out is not None:
+        assert all(s_.dtype == torch.int64 and s_.is_contiguous() and s_.shape == (m, 2) for s_, m in zip(stats_out, Ms))
+        st_out = _ptr_arr(stats_out)
     with _Prof("gemm_h3", 2.0 * sum(Ms) * N * K, ("h3", sum(Ms), N, K)):
-        code = lib.siu3r_gemm_h3(G, Mh, N, K, _ptr_arr(xs), xs[0].stride(0), xs[0].plane, _ptr_arr([w.h3 for w in wts]), wts[0].h3.stride(0),
-                                 wts[0].h3.plane, Cf, ldc, Ch, ldh, hpl, _ptr_arr(biases) if has_b else None,
-                                 _ptr_arr(residuals) if has_r else None, residuals[0].stride(0) if has_r else 0, act & 3, alpha, _p(pos), _p(tab),
-                                 ncols, vts, vcols, vt_ld, vt_pl, vt_col0, 1 if unscaled else 0, _stream())
+        code = lib.siu3r_gemm_h3_ln(G, Mh, N, K, _ptr_arr(xs), xs[0].stride(0), xs[0].plane, _ptr_arr([w.h3 for w in wts]), wts[0].h3.stride(0),
+                                    wts[0].h3.plane, Cf, ldc, Ch, ldh, hpl, _ptr_arr(biases) if has_b else None,
+                                    _ptr_arr(residuals) if has_r else None, residuals[0].stride(0) if has_r else 0, act & 3, alpha, _p(pos), _p(tab),
+                                    ncols, vts, vcols, vt_ld, vt_pl, vt_col0, 1 if unscaled else 0, st_in, ln_s, ln_eps, st_out, _stream())
     _lib.check(code, "gemm_h3")
     return outs
 

@@ -104,6 +104,80 @@ def test_gemm_h3_half_m_mode_is_bit_identical(M, N, K):
             assert torch.equal(outs[(0, tw)][i], outs[(1, tw)][i]), (tw, i)
 
 
+@pytest.mark.parametrize("M,C,N", [(2050, 1024, 3072), (1025, 768, 768), (77, 256, 96)])
+def test_gemm_h3_fused_layernorm(M, C, N):
+    """LayerNorm fused across two GEMMs (siu3r_gemm_h3_ln): the producer (residual-adding projection) emits fp32 rows + plane pair + fixed-point row
+    statistics, the consumer multiplies the RAW rows by gamma-folded weights and normalises in its epilogue.  Reference: the same chain in float64
+    (croco/blocks.py:127-130: x = x + proj(a); y = fc(norm(x)))."""
+    from siu3r_b200 import ops
+    a = rnd(M, C, seed=31)
+    x0 = rnd(M, C, seed=32) * 3.0 + 2.0 * rnd(M, 1, seed=33)          # residual stream with a per-row offset of ~2 sigma / 3
+    wp, bp = rnd(C, C, seed=34, scale=C ** -0.5), rnd(C, seed=35)
+    gam, bet = 1.0 + 0.3 * rnd(C, seed=36), 0.2 * rnd(C, seed=37)
+    w2, b2 = rnd(N, C, seed=38, scale=C ** -0.5), rnd(N, seed=39)
+    wproj, wfc = ops.Weight(wp, bp, H3), ops.Weight(w2, b2, H3)
+    wfold = wfc.fold_ln(gam, bet)
+    x_ref = x0.double() + F.linear(a.double(), wp.double(), bp.double())
+    y_ref = F.gelu(F.linear(F.layer_norm(x_ref, (C,), gam.double(), bet.double(), 1e-6), w2.double(), b2.double()))
+    # producer
+    x_plain = ops.gemm(a, wproj, residual=x0, precision=H3)
+    stats = torch.zeros(M, 2, device=DEV, dtype=torch.int64)
+    xs, xf = ops.Split.empty(M, C, device=DEV), torch.empty(M, C, device=DEV)
+    ops.gemm(a, wproj, residual=x0, out=xs, out_f32=xf, stats_out=stats, precision=H3)
+    assert torch.equal(xf, x_plain)                                   # the extra outputs do not change the fp32 result
+    assert torch.equal(xs.t, ops.split(xf).t)                         # the plane pair is the split of exactly those values
+    s1, s2 = stats[:, 0].double() / 2 ** 24, stats[:, 1].double() / 2 ** 24
+    assert float((s1 - xf.double().sum(1)).abs().max()) < 2e-6 * float(xf.abs().sum(1).max()) + 1e-5
+    assert float(((s2 - (xf.double() ** 2).sum(1)).abs() / (xf.double() ** 2).sum(1)).max()) < 1e-6
+    stats2 = torch.zeros_like(stats)
+    ops.gemm(a, wproj, residual=x0, out=ops.Split.empty(M, C, device=DEV), out_f32=torch.empty(M, C, device=DEV), stats_out=stats2, precision=H3)
+    assert torch.equal(stats, stats2)                                 # integer accumulation: bit-reproducible whatever the order of the atomics
+    # consumer
+    y = ops.gemm(xs, wfold, act=1, ln_stats=stats, precision=H3)
+    assert rel_err(y, y_ref) < 1e-5, rel_err(y, y_ref)
+    y_unfused = ops.gemm(ops.layernorm_h3([xf], [(gam, bet)], 1e-6)[0], wfc, act=1, precision=H3)
+    assert rel_err(y, y_unfused.double()) < 1e-5
+    # every tile width / the grouped launch
+    lib = ops._lib.load()
+    try:
+        for tw in (32, 96, 128, 256):
+            lib.siu3r_gemm_h3_force(tw)
+            assert rel_err(ops.gemm(xs, wfold, act=1, ln_stats=stats, precision=H3), y_ref) < 1e-5, tw
+            st = torch.zeros_like(stats)
+            ops.gemm(a, wproj, residual=x0, out=ops.Split.empty(M, C, device=DEV), out_f32=torch.empty(M, C, device=DEV), stats_out=st, precision=H3)
+            assert torch.equal(st, stats), tw
+    finally:
+        lib.siu3r_gemm_h3_force(0)
+    h = M // 2
+    ys = ops.gemm_group2([xs[:h], xs[h:]], [wfold, wfold], act=1, precision=H3, round_out=True, ln_stats=[stats[:h], stats[h:]])
+    assert rel_err(torch.cat([ys[0].float(), ys[1].float()]), y_ref) < 1e-5
+
+
+def test_model_fused_layernorm_matches_unfused(monkeypatch):
+    """The ViT stages of the h3 forward with LayerNorm fused into the projections agree with the un-fused reference path (separate
+    layernorm_kernel launches) far inside the parity tolerances."""
+    from siu3r_b200 import model as model_mod, synth
+    from siu3r_b200.model import ModelCfg, SIU3RModel
+    S = 128
+    sd = synth.make_state_dict()
+    img, K = synth.pair_inputs(1, 2, S)
+    caps = []
+    for fuse in (True, False):
+        monkeypatch.setattr(model_mod, "FUSE_LN", fuse)
+        m = SIU3RModel(ModelCfg(image_size=(S, S)), precision="h3")
+        m.load_state_dict(sd)
+        m.cuda()
+        assert m.fuse_ln == fuse
+        m.capture = {}
+        out = m(img.cuda(), K.cuda())
+        caps.append((m.capture, out[0]))
+    for name in ("enc_norm", "dec1_5", "dec2_11", "gs_raw"):
+        a_, b_ = caps[0][0][name], caps[1][0][name]
+        a_, b_ = (torch.cat([t.flatten() for t in a_]), torch.cat([t.flatten() for t in b_])) if isinstance(a_, (list, tuple)) else (a_, b_)
+        assert rel_err(a_, b_.double()) < 2e-5, (name, rel_err(a_, b_.double()))
+    assert float((caps[0][1].means - caps[1][1].means).abs().max()) < 1e-4
+
+
 @pytest.mark.parametrize("act", [0, 1, 2])
 @pytest.mark.parametrize("split_out", [False, True])
 def test_gemm_h3_epilogue_strided(act, split_out):

@@ -90,6 +90,9 @@ def bench_epilogue(out):
             row = {"kind": "epilogue", "what": what, "order": order, "M": M, "N": N, "K": K}
             o = torch.empty(M, N, device=DEV)
             row["plain_us"] = timeit(lambda: ops.gemm(x, wt, out=o, precision=H3))
+            stats = torch.zeros(M, 2, device=DEV, dtype=torch.int64)
+            stats[:, 1] = K << 24          # mean 0, variance 1
+            wln = wt.fold_ln(torch.ones(K, device=DEV), torch.zeros(K, device=DEV))
             if what == "qkv":
                 C = 1024
                 q = ops.Split.empty(M, 3 * C, device=DEV, unscaled=True)
@@ -98,15 +101,21 @@ def bench_epilogue(out):
                 row["split_us"] = timeit(lambda: ops.gemm(x, wt, out=q, precision=H3, unscaled=True))
                 row["rope_split_us"] = timeit(lambda: ops.gemm(x, wt, out=q, precision=H3, rope=(pos.view(-1, 2), tab, 2 * C), unscaled=True))
                 row["vt_split_us"] = timeit(lambda: ops.gemm(x, wt, out=q, precision=H3, vt=(vth, 2 * C, {}), unscaled=True))
+                row["ln_rope_vt_split_us"] = timeit(lambda: ops.gemm(x, wln, out=q, precision=H3, rope=(pos.view(-1, 2), tab, 2 * C), vt=(vth, 2 * C, {}),
+                                                                     unscaled=True, ln_stats=stats))
                 row["rope_f32_us"] = timeit(lambda: ops.gemm(x, wt, out=o, precision=H3, rope=(pos.view(-1, 2), tab, 2 * C)))
             elif what == "fc1":
                 oh = ops.Split.empty(M, N, device=DEV)
                 row["gelu_split_us"] = timeit(lambda: ops.gemm(x, wt, out=oh, precision=H3, act=1))
+                row["ln_gelu_split_us"] = timeit(lambda: ops.gemm(x, wln, out=oh, precision=H3, act=1, ln_stats=stats))
                 row["gelu_f32_us"] = timeit(lambda: ops.gemm(x, wt, out=o, precision=H3, act=1))
                 row["relu_split_us"] = timeit(lambda: ops.gemm(x, wt, out=oh, precision=H3, act=2))
             else:
                 r = torch.randn(M, N, device=DEV)
                 row["residual_us"] = timeit(lambda: ops.gemm(x, wt, out=r, residual=r, precision=H3))
+                rs_ = ops.Split.empty(M, N, device=DEV)
+                row["residual_dual_us"] = timeit(lambda: ops.gemm(x, wt, out=rs_, out_f32=r, residual=r, precision=H3))
+                row["residual_dual_stats_us"] = timeit(lambda: ops.gemm(x, wt, out=rs_, out_f32=r, residual=r, stats_out=stats, precision=H3))
             print(json.dumps(row), flush=True)
             out.append(row)
     lib.siu3r_gemm_h3_order(0)

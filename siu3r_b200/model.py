@@ -156,8 +156,7 @@ class SIU3RModel:
                                               cproj=P.linear(p + "cross_attn.proj"), fc1=P.linear(p + "mlp.fc1"), fc2=P.linear(p + "mlp.fc2")))
             w.dec.append(blocks)
         w.dec_norm = (P.vec("backbone.dec_norm.weight"), P.vec("backbone.dec_norm.bias"))
-        self.fuse_ln = self.prec == ops.PREC_H3 and FUSE_LN
-        if self.fuse_ln:
+        if self.prec == ops.PREC_H3 and FUSE_LN:
             # LayerNorm folded into the consuming projection (ops.Weight.fold_ln): norm1 -> qkv, norm2 -> fc1 (encoder); norm1 -> qkv, norm_y -> k|v,
             # norm2 -> q, norm3 -> fc1 (decoder).  The un-folded weights stay: block 0 of the encoder and the un-fused reference path use them.
             for bk in w.enc:
@@ -330,6 +329,11 @@ class SIU3RModel:
     @property
     def S(self):
         return self.prec == ops.PREC_H3
+
+    @property
+    def fuse_ln(self):
+        """LayerNorm of the ViT blocks fused into the adjacent GEMM epilogues: the packed weights carry the gamma-folded projections."""
+        return hasattr(self.w.enc[0], "qkv_ln")
 
     def _lin(self, x, wt, ar=False, ro=False, **kw):
         return ops.gemm(x, wt, precision=self.prec, a_rounded=ar and self.R, round_out=ro and (self.R or self.S), **kw)

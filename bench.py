@@ -202,6 +202,9 @@ def main():
     from siu3r_b200.model import ModelCfg, SIU3RModel, SIU3RMultiViewModel
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback exists for the product path)"
     torch.cuda.set_device(local)
+    from siu3r_b200.parallel import bind_to_gpu_numa
+    orig_affinity = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+    numa = bind_to_gpu_numa(local) if os.environ.get("SIU3R_NUMA_BIND", "1") != "0" else {"bound": False}
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
@@ -230,10 +233,13 @@ def main():
         e.record()
         barrier()
         ms = s.elapsed_time(e)
+        timed.per_rank = [ms]
         if world > 1:
             t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t)
+            allr = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(allr, t)
+            timed.per_rank = [float(x) for x in allr]
+            ms = max(timed.per_rank)
         return ms
 
     # A GPU kernel that never ends cannot be interrupted from Python: rather than sit until the caller's limit, report where the headline stopped.
@@ -290,6 +296,7 @@ def main():
 
     e2e_run(3)
     ms_e2e = timed(lambda: e2e_run(args.steps), 1)
+    e2e_per_rank = [m / args.steps for m in timed.per_rank]
     e2e_v = world * B * args.steps / (ms_e2e / 1e3)
     host_out = pipe.slots[0]["host"]
     h2d = img_pin.numel() * 4 + K_pin.numel() * 4
@@ -371,7 +378,7 @@ def main():
                        "l2": "no explicit flush: weights (2.6 GB) + activations per step exceed the 126 MB L2 many times over"},
             "clocks": clk,
             "e2e": {"value": e2e_v, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
-                    "d2h_pinned_GBs": d2h_gbs},
+                    "d2h_pinned_GBs": d2h_gbs, "ms_per_step_per_rank": e2e_per_rank, "numa": numa},
             "gpu_launches": launches,
             "vit_tensor_pipe_frac": value / world * (FLOPS_PER_PAIR_512 if V == 2 else FLOPS_PER_SAMPLE_512_V4 * V / 4) * (S / 512.0) ** 2 / 1e12 / tf32_peak,
             "roofline": roofline}
@@ -477,6 +484,8 @@ def main():
         except Exception as ex:
             line["labels2d"] = {"error": repr(ex)}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        if orig_affinity is not None:
+            os.sched_setaffinity(0, orig_affinity)   # the CPU leg may use every core the process was given, not only the GPU's NUMA node
         threads = host_threads()
         t = cpu_port_forward(S, 1, threads)
         line["cpu_baseline"] = {"value": 1.0 / t, "unit": "pairs/s", "cores": threads, "kind": "port",

@@ -13,6 +13,34 @@ import torch.distributed as dist
 RECORD_FLOATS = 3 + 6 + 75 + 1  # means, covariance upper triangle (what the rasterizer consumes), harmonics (3x25), opacity
 
 
+def bind_to_gpu_numa(device_index: int) -> dict:
+    """Pin the calling process to the CPUs next to GPU `device_index` BEFORE it allocates pinned host buffers, so that the ~200 MB of Gaussians every pair
+    downloads (Gaussians.detach_cpu_copy, gaussians_types.py:25-38) cross the GPU's own PCIe root instead of the socket interconnect.  One process per
+    GPU (torchrun) is assumed; a restriction that would leave no allowed CPU is skipped.  Returns what was done (for the bench line)."""
+    import os
+    info = {"device": device_index, "bound": False}
+    try:
+        bus = torch.cuda.get_device_properties(device_index)
+        pci = f"{bus.pci_domain_id:04x}:{bus.pci_bus_id:02x}:{bus.pci_device_id:02x}.0"
+        base = f"/sys/bus/pci/devices/{pci}"
+        node = int(open(base + "/numa_node").read())
+        cpus = set()
+        for part in open(base + "/local_cpulist").read().strip().split(","):
+            if part:
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        info.update(numa_node=node, local_cpus=len(cpus), allowed_cpus=len(allowed))
+        if use and use != allowed:
+            os.sched_setaffinity(0, use)
+            info["bound"] = True
+            info["cpus"] = len(use)
+    except Exception as e:   # no sysfs / no permission: keep the inherited affinity
+        info["error"] = repr(e)[:120]
+    return info
+
+
 def shard_range(n_items: int, rank: int, world: int) -> range:
     """Contiguous block partition: rank r owns items [r*ceil.., ...) (batch 32 on 8 GPUs -> pairs 4r .. 4r+3)."""
     per = (n_items + world - 1) // world

@@ -292,6 +292,7 @@ void siu3r_gemm_h3_cluster_cap(int cap);
 void siu3r_gemm_h3_order(int order);   /* 0 = neighbouring CTA pairs share the token tile, 1 = they share the weight rows */
 int siu3r_gemm_h3_plan(int M, int N, int K, int M1, int* tw_out, int* tiles_out, int* rounds_out);
 void siu3r_flash_h3_debug_swap(int swap);
+void siu3r_gemm_h3_debug_ts(void* dev_buf);   /* tuning aid: per-tile clock64 stamps of CTA pair 0 into dev_buf (8 u64 per tile); NULL = off */
 void siu3r_gemm_h3_debug(int mode);   /* timing experiments only: 1 = operand pipeline without MMAs, 2 = MMAs without operand loads (garbage results) */
 
 #ifdef __cplusplus

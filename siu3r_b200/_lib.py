@@ -83,6 +83,7 @@ SIGNATURES = {
     "siu3r_gemm_h3_cluster_cap": (None, [_i]),
     "siu3r_gemm_h3_order": (None, [_i]),
     "siu3r_gemm_h3_debug": (None, [_i]),
+    "siu3r_gemm_h3_debug_ts": (None, [_p]),
     "siu3r_gemm_h3_plan": (_i, [_i, _i, _i, _i, _p, _p, _p]),
     "siu3r_split_h3": (_i, [_p, _l, _l, _i, _p, _l, _l, _i, _p]),
     "siu3r_merge_h3": (_i, [_p, _l, _l, _l, _i, _p, _l, _p]),

@@ -51,6 +51,7 @@ enum Act { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2, ACT_MASK = 3 };
 struct H3Params {
     int N, num_kb;             // weight rows, k-blocks
     int tw, nbuf, nstages;     // token tile width, accumulator sets in TMEM (1 or 2), pipeline depth
+    int prew;                  // 1: weight loads of the first tile are issued before the programmatic-dependent-launch wait
     int mhalf;                 // N <= 128: MMA M = 128 (64 weight rows per CTA) instead of 256 -- no tensor time is spent on padding rows
     int act; float alpha;
     int64_t ldc;               // fp32 output pitch
@@ -58,6 +59,7 @@ struct H3Params {
     int64_t ldr;               // fp32 residual pitch
     const long long* rope_pos; const float* rope_tab; int rope_cols;
     int vt_col0; int64_t vt_ld, vt_plane;
+    unsigned long long* dbg_ts; // tuning aid: per-tile clock64 stamps of CTA pair 0 (8 per tile: MMA wait / start / issued, epilogue wait / start / end)
     int dbg_mode;              // timing experiments only (results are garbage): 1 = TMA pipeline without MMAs, 2 = MMAs without TMA loads
     int order;                 // tile order: 0 = weight pair fastest (neighbouring CTA pairs share the token tile), 1 = token tile fastest (share the weights)
     int ttiles0, ttiles1;      // token tiles of problem 0 / 1
@@ -117,23 +119,42 @@ __device__ __forceinline__ void epi_chunk(float (&v)[16], const Frag& f, int lan
         if (RES) x += r[j];
         v[j] = x;
     }
-    // Phase 2: stores (one output row = 32 consecutive n of the warp: a 128-byte line in fp32, 64 bytes per plane as a plane pair)
+    // Phase 2: stores (one output row = 32 consecutive n of the warp: a 128-byte line in fp32, 64 bytes per plane as a plane pair).  Full fragments
+    // (all but the last of a problem) take the unguarded path with running row pointers: the guarded form costs a branch and a 64-bit address
+    // computation per store, a third of the instructions of a whole GELU + split fragment.
     if (f.nv <= 0 || !n_ok) return;
     if (SPLIT) {
-        __half* d = pr.Ch + f.rb * p.ldh + n;
-        unsigned short* du = reinterpret_cast<unsigned short*>(d);
+        unsigned short* dh = reinterpret_cast<unsigned short*>(pr.Ch + f.rb * p.ldh + n);
+        unsigned short* dl = dh + p.plane_h;
+        if (f.nv == 16) {
 #pragma unroll
-        for (int i = 0; i < 16; i += 2) {      // two tokens per packed conversion (h3.cuh)
-            uint32_t hi2, lo2;
-            h3_split2_s(v[i], v[i + 1], p.lo_scale, hi2, lo2);
-            if (i < f.nv) { du[(int64_t)i * p.ldh] = (unsigned short)hi2; du[(int64_t)i * p.ldh + p.plane_h] = (unsigned short)lo2; }
-            if (i + 1 < f.nv) { du[(int64_t)(i + 1) * p.ldh] = (unsigned short)(hi2 >> 16); du[(int64_t)(i + 1) * p.ldh + p.plane_h] = (unsigned short)(lo2 >> 16); }
+            for (int i = 0; i < 16; i += 2) {      // two tokens per packed conversion (h3.cuh)
+                uint32_t hi2, lo2;
+                h3_split2_s(v[i], v[i + 1], p.lo_scale, hi2, lo2);
+                dh[0] = (unsigned short)hi2; dl[0] = (unsigned short)lo2;
+                dh += p.ldh; dl += p.ldh;
+                dh[0] = (unsigned short)(hi2 >> 16); dl[0] = (unsigned short)(lo2 >> 16);
+                dh += p.ldh; dl += p.ldh;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; i += 2) {
+                uint32_t hi2, lo2;
+                h3_split2_s(v[i], v[i + 1], p.lo_scale, hi2, lo2);
+                if (i < f.nv) { dh[(int64_t)i * p.ldh] = (unsigned short)hi2; dl[(int64_t)i * p.ldh] = (unsigned short)lo2; }
+                if (i + 1 < f.nv) { dh[(int64_t)(i + 1) * p.ldh] = (unsigned short)(hi2 >> 16); dl[(int64_t)(i + 1) * p.ldh] = (unsigned short)(lo2 >> 16); }
+            }
         }
     } else {
         float* d = pr.C + f.rb * p.ldc + n;
+        if (f.nv == 16) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
-            if (i < f.nv) d[(int64_t)i * p.ldc] = v[i];
+            for (int i = 0; i < 16; ++i) { d[0] = v[i]; d += p.ldc; }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                if (i < f.nv) d[(int64_t)i * p.ldc] = v[i];
+        }
     }
 }
 
@@ -160,11 +181,101 @@ __device__ __forceinline__ void epi_chunk_vt(const float (&v)[16], int jmax, int
         }
 }
 
+// Per-tile, per-warp constants of the epilogue (kept in one struct so that the fragment loop can be a template on the epilogue variant).
+struct EpiCtx {
+    uint32_t tmem_hh, tmem_x, lane_off;
+    int lane, c_lo, c_hi, nb, n, tok_off, axis, m_base, img, h0, w0;
+    bool n_ok, ln, split;
+    float bias, ln_s;
+    const float2* ln_mr;
+};
+
+// The fragment loop of one warp and tile, instantiated per epilogue variant: the variant dispatch happens ONCE per tile, so the hot loop is one
+// contiguous piece of code (with the switch inside the loop the executed path of a GELU + split fragment was scattered over 96 KB of SASS and a
+// quarter of the epilogue warps' stall samples were instruction fetches).
+template <int ACTK, bool ROPE, bool RES, bool SPLIT>
+__device__ __forceinline__ void epi_frag_loop(const EpiCtx& c, const H3Params& p, const H3Problem& pr) {
+    const int lane = c.lane, n = c.n, nb = c.nb, tok_off = c.tok_off, axis = c.axis, m_base = c.m_base, img = c.img, h0 = c.h0, w0 = c.w0;
+    const bool n_ok = c.n_ok, ln = c.ln, split = c.split;
+    const float bias = c.bias, ln_s = c.ln_s;
+    const float2* ln_mr = c.ln_mr;
+    const uint32_t tmem_hh = c.tmem_hh, tmem_x = c.tmem_x, lane_off = c.lane_off;
+    const int c_lo = c.c_lo, c_hi = c.c_hi;
+#pragma unroll 1
+    for (int c0 = c_lo; c0 < c_hi && nb < p.N; c0 += 16) {
+        uint32_t a[16], b[16];
+        tmem_ld16(tmem_hh + lane_off + (uint32_t)c0, a);
+        tmem_ld16(tmem_x + lane_off + (uint32_t)c0, b);
+        tmem_ld_wait();
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = fmaf(__uint_as_float(b[j]), H3_LO_INV, __uint_as_float(a[j]));
+        Frag f;
+        int mrow = m_base + tok_off + c0, jmax = 16;
+        if (p.conv) {
+            const int hrow = h0 + ((tok_off + c0) >> 4);
+            f.rb = ((int64_t)img * p.H + hrow) * p.W + w0;
+            f.nv = hrow < p.H ? 16 : 0;
+        } else {
+            if (jmax > pr.M - mrow) jmax = pr.M - mrow;
+            if (jmax <= 0) break;
+            f.rb = mrow;
+            f.nv = jmax;
+            if (ln) {   // acc -> rstd * (acc - mean * s_n); the (mean, rstd) pairs are warp-uniform shared-memory broadcasts
+                const float2* mr = ln_mr + tok_off + c0;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float2 t = mr[j];
+                    v[j] = t.y * fmaf(-t.x, ln_s, v[j]);
+                }
+            }
+            if (pr.vt != nullptr && nb >= p.vt_col0) {        // warp-uniform: a 32-column block never straddles vt_col0 (multiple of 64)
+                epi_chunk_vt(v, jmax, n, n_ok, bias, mrow, p, pr);
+                continue;
+            }
+        }
+        epi_chunk<ACTK, ROPE, RES, SPLIT>(v, f, lane, n, n_ok, bias, axis, mrow, jmax, p, pr);
+        // v[] now holds the final values of this fragment (16 tokens x this lane's column n)
+        if (split && pr.C != nullptr && f.nv > 0 && n_ok) {     // dual output: the plane pair went out above, the fp32 copy (residual stream) here
+            float* d = pr.C + f.rb * p.ldc + n;
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                if (i < f.nv) d[(int64_t)i * p.ldc] = v[i];
+        }
+        if (pr.stats_out != nullptr) {
+            // Row statistics for a LayerNorm fused into the NEXT GEMM: 32 values per lane (16 sums, 16 sums of squares) are reduced over the warp's 32
+            // columns by a halving butterfly (31 shuffles); lane l ends up with statistic l >> 4 of token l & 15 and adds it, as a 2^-24 fixed-point
+            // integer, to the row's accumulator.
+            float w[32];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float x = (j < f.nv && n_ok) ? v[j] : 0.0f;
+                w[j] = x; w[16 + j] = x * x;
+            }
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+                const bool up = (lane & off) != 0;
+#pragma unroll
+                for (int i = 0; i < off; ++i) {
+                    const float send = up ? w[i] : w[i + off];
+                    const float keep = up ? w[i + off] : w[i];
+                    w[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                }
+            }
+            const int tj = lane & 15;
+            if (tj < f.nv)
+                atomicAdd(reinterpret_cast<unsigned long long*>(pr.stats_out) + (f.rb + tj) * 2 + (lane >> 4),
+                          (unsigned long long)__float2ll_rn(w[0] * STATS_SCALE));
+        }
+    }
+}
+
 // Epilogue of one warp: TMEM lanes [32q, 32q+32) = weight rows n, columns [c_lo, c_hi) = its share of the tile's tokens, 16 at a time.
 // mhalf (M = 128 over the CTA pair): lanes [0, 64) hold this CTA's 64 weight rows for the first half of the tile's tokens, lanes [64, 128) the
 // same rows for the second half (the accumulator is tw/2 columns wide); tok_off = token index of column 0 for this warp.
 __device__ __forceinline__ void run_epilogue(uint32_t tmem_hh, uint32_t tmem_x, int lane, int q, int c_lo, int c_hi, int n_cta, int tt,
-                                             const H3Params& p, const H3Problem& pr, uint64_t* bar, uint32_t parity, float2* ln_mr, int epi_tid) {
+                                             const H3Params& p, const H3Problem& pr, uint64_t* bar, uint32_t parity, float2* ln_mr, int epi_tid,
+                                             unsigned long long* ts_start) {
     const int nb = n_cta + (p.mhalf ? (q & 1) : q) * 32;           // warp-uniform first weight row
     const int tok_off = p.mhalf ? (q >> 1) * (p.tw >> 1) : 0;
     const int n = nb + lane;
@@ -204,88 +315,26 @@ __device__ __forceinline__ void run_epilogue(uint32_t tmem_hh, uint32_t tmem_x, 
     }
     mbar_wait(bar, parity);
     tc_fence_after();
-    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-#pragma unroll 1
-    for (int c0 = c_lo; c0 < c_hi && nb < p.N; c0 += 16) {
-        uint32_t a[16], b[16];
-        tmem_ld16(tmem_hh + lane_off + (uint32_t)c0, a);
-        tmem_ld16(tmem_x + lane_off + (uint32_t)c0, b);
-        tmem_ld_wait();
-        float v[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = fmaf(__uint_as_float(b[j]), H3_LO_INV, __uint_as_float(a[j]));
-        Frag f;
-        int mrow = m_base + tok_off + c0, jmax = 16;
-        if (p.conv) {
-            const int hrow = h0 + ((tok_off + c0) >> 4);
-            f.rb = ((int64_t)img * p.H + hrow) * p.W + w0;
-            f.nv = hrow < p.H ? 16 : 0;
-        } else {
-            if (jmax > pr.M - mrow) jmax = pr.M - mrow;
-            if (jmax <= 0) break;
-            f.rb = mrow;
-            f.nv = jmax;
-            if (ln) {   // acc -> rstd * (acc - mean * s_n); the (mean, rstd) pairs are warp-uniform shared-memory broadcasts
-                const float2* mr = ln_mr + tok_off + c0;
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const float2 t = mr[j];
-                    v[j] = t.y * fmaf(-t.x, ln_s, v[j]);
-                }
-            }
-            if (pr.vt != nullptr && nb >= p.vt_col0) {        // warp-uniform: a 32-column block never straddles vt_col0 (multiple of 64)
-                epi_chunk_vt(v, jmax, n, n_ok, bias, mrow, p, pr);
-                continue;
-            }
-        }
-        switch (variant) {
-            case 0: epi_chunk<ACT_NONE, true, false, false>(v, f, lane, n, n_ok, bias, axis, mrow, jmax, p, pr); break;
-            case 1: epi_chunk<ACT_NONE, true, false, true>(v, f, lane, n, n_ok, bias, axis, mrow, jmax, p, pr); break;
-            case 2: epi_chunk<ACT_NONE, false, false, false>(v, f, lane, n, n_ok, bias, axis, mrow, jmax, p, pr); break;
-            case 3: epi_chunk<ACT_NONE, false, false, true>(v, f, lane, n, n_ok, bias, axis, mrow, jmax, p, pr); break;
-            case 4: epi_chunk<ACT_NONE, false, true, false>(v, f, lane, n, n_ok, bias, axis, mrow, jmax, p, pr); break;
-            case 5: epi_chunk<ACT_NONE, false, true, true>(v, f, lane, n, n_ok, bias, axis, mrow, jmax, p, pr); break;
-            case 6: epi_chunk<ACT_GELU, false, false, false>(v, f, lane, n, n_ok, bias, axis, mrow, jmax, p, pr); break;
-            case 7: epi_chunk<ACT_GELU, false, false, true>(v, f, lane, n, n_ok, bias, axis, mrow, jmax, p, pr); break;
-            case 8: epi_chunk<ACT_GELU, false, true, false>(v, f, lane, n, n_ok, bias, axis, mrow, jmax, p, pr); break;
-            case 9: epi_chunk<ACT_GELU, false, true, true>(v, f, lane, n, n_ok, bias, axis, mrow, jmax, p, pr); break;
-            case 10: epi_chunk<ACT_RELU, false, false, false>(v, f, lane, n, n_ok, bias, axis, mrow, jmax, p, pr); break;
-            case 11: epi_chunk<ACT_RELU, false, false, true>(v, f, lane, n, n_ok, bias, axis, mrow, jmax, p, pr); break;
-            case 12: epi_chunk<ACT_RELU, false, true, false>(v, f, lane, n, n_ok, bias, axis, mrow, jmax, p, pr); break;
-            default: epi_chunk<ACT_RELU, false, true, true>(v, f, lane, n, n_ok, bias, axis, mrow, jmax, p, pr); break;
-        }
-        // v[] now holds the final values of this fragment (16 tokens x this lane's column n)
-        if (split && pr.C != nullptr && f.nv > 0 && n_ok) {     // dual output: the plane pair went out above, the fp32 copy (residual stream) here
-            float* d = pr.C + f.rb * p.ldc + n;
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-                if (i < f.nv) d[(int64_t)i * p.ldc] = v[i];
-        }
-        if (pr.stats_out != nullptr) {
-            // Row statistics for a LayerNorm fused into the NEXT GEMM: 32 values per lane (16 sums, 16 sums of squares) are reduced over the warp's 32
-            // columns by a halving butterfly (31 shuffles); lane l ends up with statistic l >> 4 of token l & 15 and adds it, as a 2^-24 fixed-point
-            // integer, to the row's accumulator.
-            float w[32];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const float x = (j < f.nv && n_ok) ? v[j] : 0.0f;
-                w[j] = x; w[16 + j] = x * x;
-            }
-#pragma unroll
-            for (int off = 16; off >= 1; off >>= 1) {
-                const bool up = (lane & off) != 0;
-#pragma unroll
-                for (int i = 0; i < off; ++i) {
-                    const float send = up ? w[i] : w[i + off];
-                    const float keep = up ? w[i + off] : w[i];
-                    w[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-                }
-            }
-            const int tj = lane & 15;
-            if (tj < f.nv)
-                atomicAdd(reinterpret_cast<unsigned long long*>(pr.stats_out) + (f.rb + tj) * 2 + (lane >> 4),
-                          (unsigned long long)__float2ll_rn(w[0] * STATS_SCALE));
-        }
+    if (ts_start) *ts_start = clock64();
+    EpiCtx c;
+    c.tmem_hh = tmem_hh; c.tmem_x = tmem_x; c.lane_off = (uint32_t)(q * 32) << 16;
+    c.lane = lane; c.c_lo = c_lo; c.c_hi = c_hi; c.nb = nb; c.n = n; c.tok_off = tok_off; c.axis = axis; c.m_base = m_base; c.img = img; c.h0 = h0; c.w0 = w0;
+    c.n_ok = n_ok; c.ln = ln; c.split = split; c.bias = bias; c.ln_s = ln_s; c.ln_mr = ln_mr;
+    switch (variant) {
+        case 0: epi_frag_loop<ACT_NONE, true, false, false>(c, p, pr); break;
+        case 1: epi_frag_loop<ACT_NONE, true, false, true>(c, p, pr); break;
+        case 2: epi_frag_loop<ACT_NONE, false, false, false>(c, p, pr); break;
+        case 3: epi_frag_loop<ACT_NONE, false, false, true>(c, p, pr); break;
+        case 4: epi_frag_loop<ACT_NONE, false, true, false>(c, p, pr); break;
+        case 5: epi_frag_loop<ACT_NONE, false, true, true>(c, p, pr); break;
+        case 6: epi_frag_loop<ACT_GELU, false, false, false>(c, p, pr); break;
+        case 7: epi_frag_loop<ACT_GELU, false, false, true>(c, p, pr); break;
+        case 8: epi_frag_loop<ACT_GELU, false, true, false>(c, p, pr); break;
+        case 9: epi_frag_loop<ACT_GELU, false, true, true>(c, p, pr); break;
+        case 10: epi_frag_loop<ACT_RELU, false, false, false>(c, p, pr); break;
+        case 11: epi_frag_loop<ACT_RELU, false, false, true>(c, p, pr); break;
+        case 12: epi_frag_loop<ACT_RELU, false, true, false>(c, p, pr); break;
+        default: epi_frag_loop<ACT_RELU, false, true, true>(c, p, pr); break;
     }
 }
 
@@ -337,6 +386,33 @@ gemm_h3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
     tc_fence_after();
     // Programmatic dependent launch: everything above overlapped the previous kernel's tail; from here on its outputs are needed (TMA loads of the
     // activations, residual reads) or overwritten.  All CTAs of this persistent grid are resident, so the next kernel may be scheduled as they retire.
+    // Experiment (H3Params::prew, off by default, see g_prew): the producer warp starts the WEIGHT loads of its first tile (static data) before the
+    // wait, so that a CTA pair that became resident early has its weight stages in flight when the activations become visible.
+    int prew = 0;
+    if (warp == 0 && p.prew && cluster_id < num_tiles) {
+        const int u = cluster_id;
+        const int g = u >= grp.tiles0;
+        const int tl = g ? u - grp.tiles0 : u;
+        const CUtensorMap* mw = g ? &tmW1 : &tmW;
+        const int tcount = g ? p.ttiles1 : p.ttiles0;
+        const int wi = p.order ? tl / tcount : tl % w_pairs;
+        const int n0 = wi * 2 * wrows + (int)rank * wrows;
+        prew = p.num_kb < nstages ? p.num_kb : nstages;
+        for (int kb = 0; kb < prew; ++kb) {
+            uint8_t* sW = smem + kb * stage_bytes;
+            const uint32_t lead_full = mapa_to_cta(smem_u32(&full_bar[kb]), 0);
+            if (elect_one_sync()) {
+                if (leader) mbar_expect_tx(&full_bar[kb], stage_tx);
+                if (p.conv) {
+                    const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
+                    tma2_load_3d(mw, lead_full, sW, tap * p.Cin + cb * BKH, n0, 0);
+                } else {
+                    tma2_load_3d(mw, lead_full, sW, kb * BKH, n0, 0);
+                }
+            }
+            __syncwarp();
+        }
+    }
     pdl_wait();
     pdl_launch_dependents();
     const uint32_t tmem_base = *tmem_slot;
@@ -367,18 +443,19 @@ gemm_h3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                     uint8_t* sW = smem + stage * stage_bytes;
                     uint8_t* sX = sW + w_bytes;
                     const uint32_t lead_full = mapa_to_cta(smem_u32(&full_bar[stage]), 0);
+                    const bool w_done = u == cluster_id && kb < prew;     // this stage's weights (and its expect_tx) were issued before the PDL wait
                     if (elect_one_sync()) {
                         if (p.dbg_mode == 2) {
                             if (leader) mbar_arrive(&full_bar[stage]);
                         } else {
-                            if (leader) mbar_expect_tx(&full_bar[stage], stage_tx);
+                            if (leader && !w_done) mbar_expect_tx(&full_bar[stage], stage_tx);
                             if (p.conv) {
                                 const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
                                 const int kh = tap / p.KW, kw = tap - kh * p.KW;
-                                tma2_load_3d(mw, lead_full, sW, tap * p.Cin + cb * BKH, n0, 0);
+                                if (!w_done) tma2_load_3d(mw, lead_full, sW, tap * p.Cin + cb * BKH, n0, 0);
                                 tma2_load_5d(mx, lead_full, sX, cb * BKH, w0 + kw - p.pad_w, h0 + kh - p.pad_h, img, 0);
                             } else {
-                                tma2_load_3d(mw, lead_full, sW, kb * BKH, n0, 0);
+                                if (!w_done) tma2_load_3d(mw, lead_full, sW, kb * BKH, n0, 0);
                                 tma2_load_3d(mx, lead_full, sX, kb * BKH, m0, 0);
                             }
                         }
@@ -400,8 +477,11 @@ gemm_h3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
             for (int u = cluster_id; u < num_tiles; u += num_clusters, ++it) {
                 const int buf = nbuf == 2 ? (it & 1) : 0;
                 const uint32_t use = nbuf == 2 ? ((uint32_t)it >> 1) : (uint32_t)it;
+                const bool ts_on = p.dbg_ts != nullptr && cluster_id == 0 && lane == 0;
+                if (ts_on) p.dbg_ts[it * 8 + 0] = clock64();
                 mbar_wait(&tempty_bar[buf], (use & 1u) ^ 1u);   // both CTAs' epilogues have drained this accumulator set
                 tc_fence_after();
+                if (ts_on) p.dbg_ts[it * 8 + 1] = clock64();
                 const uint32_t acc_hh = tmem_base + (uint32_t)(buf * 256);
                 const uint32_t acc_x = acc_hh + x_off;
                 for (int kb = 0; kb < p.num_kb; ++kb) {
@@ -426,6 +506,7 @@ gemm_h3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                 }
                 if (elect_one_sync()) umma2_commit_mc(&tfull_bar[buf]);
                 __syncwarp();
+                if (ts_on) p.dbg_ts[it * 8 + 2] = clock64();
             }
         }
     } else {
@@ -453,8 +534,12 @@ gemm_h3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                                  g ? grp.prob[1].stats_in : grp.prob[0].stats_in, g ? grp.prob[1].ln_s : grp.prob[0].ln_s,
                                  g ? grp.prob[1].stats_out : grp.prob[0].stats_out};
             const uint32_t acc_hh = tmem_base + (uint32_t)(buf * 256);
+            const bool ts_on = p.dbg_ts != nullptr && cluster_id == 0 && leader && lane == 0 && (warp == 2 || warp == 17);
+            unsigned long long* ts = ts_on ? p.dbg_ts + it * 8 + (warp == 2 ? 3 : 6) : nullptr;
+            if (ts_on && warp == 2) ts[0] = clock64();
             run_epilogue(acc_hh, acc_hh + x_off, lane, q, c_lo, c_hi, n_cta, tt, p, prob, &tfull_bar[buf], use & 1u, ln_smem + (it & 1) * 256,
-                         (int)threadIdx.x - 64);
+                         (int)threadIdx.x - 64, (ts_on && warp == 2) ? ts + 1 : nullptr);
+            if (ts_on) ts[warp == 2 ? 2 : 0] = clock64();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(lead_tempty0 + (uint32_t)(buf * 8));
@@ -510,8 +595,11 @@ __global__ void __launch_bounds__(256) merge_h3_kernel(const __half* __restrict_
 // host side
 // ------------------------------------------------------------------------------------------------------------
 int g_dbg_mode = 0;
+unsigned long long* g_dbg_ts = nullptr;
 int g_order = 0;      // tuning aid: tile order (see H3Params::order)
 int g_force_tw = 0;   // tuning aid (tools/gemm_sweep.py): > 0 = use this token tile width wherever it is legal
+int g_prew = -1;       // SIU3R_H3_PREW=1 turns the early weight loads on.  OFF by default: measured 17.03 ms/pair without, 17.23 with (the early
+                       // stages of pairs that start ahead compete with the running kernel's operand stream for L2 -> SM bandwidth)
 int g_cluster_cap = 0; // > 0: a launch uses at most this many CTA pairs (siu3r_gemm_h3_cluster_cap)
 int g_mhalf = -1;     // M = 128 mode for N <= 128 (see H3Params::mhalf); SIU3R_H3_MHALF=0 turns it off (A/B measurements)
 bool use_mhalf(int N) {
@@ -519,10 +607,15 @@ bool use_mhalf(int N) {
     return g_mhalf && N <= 128;
 }
 
-// Token tile width for (M [+ M1]) tokens x N weight rows x K.  Cost model per CTA pair (clocks): rounds x (k-blocks x max(tensor time, operand
-// bytes per CTA / its L2->SM share) + tile overhead).  kind::f16 rate 8192 flop/clk/SM -> the 3 MMAs of a k-step (256 x tw x 16) take 3 * tw/2 clocks, a
-// k-block 6 * tw; operands per CTA and k-block: 32 KB of weights + tw/2 * 256 B of tokens at ~42 B/clk (chip-wide L2 cap of ~6300 B/clk).
-int pick_tw(int64_t M, int N, int K, int64_t M1, bool conv, int conv_h = 0, int conv_w = 0) {
+// Token tile width for (M [+ M1]) tokens x N weight rows x K.  Cost model per CTA pair (clocks), fitted to tools/h3_bench.py twsweep / tiles:
+//   mainloop of a tile = k-blocks x max(tensor time, operand bytes per CTA / its L2->SM share) + 700;  kind::f16 rate 8192 flop/clk/SM -> the 3 MMAs of a
+//   k-step (256 x tw x 16) take 3 * tw/2 clocks, a k-block 6 * tw (3 * tw in the M = 128 mode); operands per CTA and k-block: 32 KB of weights +
+//   tw/2 * 256 B of tokens at ~42 B/clk (chip-wide L2 cap of ~6300 B/clk);
+//   epilogue of a tile E = ew x tw clocks, ew = per-token cost of the epilogue variant (17 plain ... 50 GELU + plane-pair split, measured with clock64
+//   stamps);  double-buffered accumulators (tw <= 128 or M = 128 mode): E hides under the next mainloop and is exposed once; single-buffered
+//   (tw > 128): every tile pays E plus the MMA-completion / barrier hand-off (~3700 clocks by the stamps; 7500 reproduces the measured sweep).  (The first version of this model charged 10 * tw for the
+//   single buffer and put the encoder's fc1 on tw = 256: 49.9 us instead of 42.7.)
+int pick_tw(int64_t M, int N, int K, int64_t M1, bool conv, int conv_h = 0, int conv_w = 0, int ew = 17) {
     const int w_pairs = ceil_div(N, 256);
     const int num_kb = ceil_div(K, BKH);
     const bool mh = use_mhalf(N);
@@ -536,10 +629,18 @@ int pick_tw(int64_t M, int N, int K, int64_t M1, bool conv, int conv_h = 0, int 
         const int64_t tiles = (int64_t)w_pairs * T;
         const int64_t rounds = ceil_div_i64(tiles, CLUSTERS);
         const double kb = mh ? fmax(3.0 * tw, (16384.0 + 128.0 * tw) / 42.0) : fmax(6.0 * tw, (32768.0 + 128.0 * tw) / 42.0);
-        const double t = (double)rounds * (num_kb * kb + 700.0 + 6.0 * tw + (tw > 128 && !mh ? 10.0 * tw : 0.0));
+        const double mainloop = num_kb * kb + 700.0;
+        const double E = (double)ew * tw * (mh ? 0.5 : 1.0);
+        const bool dbuf = tw <= 128 || mh;
+        const double t = dbuf ? (double)rounds * fmax(mainloop, E + 1000.0) + E + 2000.0 : (double)rounds * (mainloop + E + 7500.0);
         if (t < best_t * 0.999) { best_t = t; best = tw; }
     }
     return best;
+}
+// per-token epilogue cost (clocks per token of the tile width) of a launch's epilogue variant, for pick_tw
+int epilogue_weight(int act, bool split, bool rope, bool residual, bool stats_out, bool dual, bool ln) {
+    return 17 + (split ? 13 : 0) + (act == ACT_GELU ? 15 : act == ACT_RELU ? 2 : 0) + (rope ? 12 : 0) + (residual ? 8 : 0) + (stats_out ? 6 : 0) + (dual ? 6 : 0) +
+           (ln ? 5 : 0);
 }
 
 int launch_h3(const CUtensorMap& w, const CUtensorMap& x, const CUtensorMap& w1, const CUtensorMap& x1, H3Params& p, const H3Group& grp,
@@ -561,6 +662,8 @@ int launch_h3(const CUtensorMap& w, const CUtensorMap& x, const CUtensorMap& w1,
         if (getenv("SIU3R_GEMM_VERBOSE")) fprintf(stderr, "[siu3r_b200] gemm_h3: %d resident clusters, %d B smem\n", n, SMEM_BYTES);
     }
     p.mhalf = use_mhalf(p.N) ? 1 : 0;
+    if (g_prew < 0) { const char* e = getenv("SIU3R_H3_PREW"); g_prew = (e && e[0] == '1') ? 1 : 0; }
+    p.prew = (g_prew && p.dbg_mode == 0) ? 1 : 0;
     const int stage_bytes = (p.mhalf ? W_BYTES / 2 : W_BYTES) + p.tw * 128;
     p.nbuf = (p.tw <= 128 || p.mhalf) ? 2 : 1;
     p.nstages = PIPE_BYTES / stage_bytes > MAX_STAGES ? MAX_STAGES : PIPE_BYTES / stage_bytes;
@@ -593,6 +696,7 @@ void siu3r_gemm_h3_cluster_cap(int cap) { g_cluster_cap = cap > 0 ? cap : 0; }
 // tuning aid: 1 = M = 128 MMAs for N <= 128 (default), 0 = always M = 256
 void siu3r_gemm_h3_set_mhalf(int on) { g_mhalf = on ? 1 : 0; }
 void siu3r_gemm_h3_order(int order) { g_order = order ? 1 : 0; }
+void siu3r_gemm_h3_debug_ts(void* dev_buf) { g_dbg_ts = (unsigned long long*)dev_buf; }   // tuning aid: see H3Params::dbg_ts (>= 8 * tiles-per-pair u64)
 void siu3r_gemm_h3_debug(int mode) { g_dbg_mode = mode; }   // timing experiments: 1 = TMA only, 2 = MMA only (outputs are garbage)
 
 // Host-only view of the tile planner: token tile width, number of 256 x tw tiles and rounds over the 74 resident CTA pairs.
@@ -666,7 +770,8 @@ int siu3r_gemm_h3_ln(int ngroups, const int* M_host, int N, int K, const void* c
             SIU3R_REQUIRE(vt_host[g] && ((uintptr_t)vt_host[g] & 15) == 0 && vt_cols_host[g] % 8 == 0 && vt_cols_host[g] >= M_host[g]);
     }
     const int M0 = M_host[0], M1 = ngroups == 2 ? M_host[1] : 0;
-    const int tw = pick_tw(M0, N, K, M1, false);
+    const int tw = pick_tw(M0, N, K, M1, false, 0, 0, epilogue_weight(act, Ch_host != nullptr, positions != nullptr, residual_host != nullptr,
+                                                                    stats_out_host != nullptr, C_host && Ch_host, stats_in_host != nullptr));
     SIU3R_REQUIRE(tw >= 32 && tw <= 256 && tw % (use_mhalf(N) ? 32 : 16) == 0);
     CUtensorMap mw[2], mx[2];
     for (int g = 0; g < ngroups; ++g) {
@@ -689,7 +794,7 @@ int siu3r_gemm_h3_ln(int ngroups, const int* M_host, int N, int K, const void* c
                                 ln_s_host ? ln_s_host[s] : nullptr, stats_out_host ? (long long*)stats_out_host[s] : nullptr};
     }
     grp.tiles0 = w_pairs * ceil_div(M0, tw);
-    p.ttiles0 = ceil_div(M0, tw); p.ttiles1 = ngroups == 2 ? ceil_div(M1, tw) : 1; p.order = g_order; p.dbg_mode = g_dbg_mode;
+    p.ttiles0 = ceil_div(M0, tw); p.ttiles1 = ngroups == 2 ? ceil_div(M1, tw) : 1; p.order = g_order; p.dbg_mode = g_dbg_mode; p.dbg_ts = g_dbg_ts;
     const int tiles = grp.tiles0 + (ngroups == 2 ? w_pairs * ceil_div(M1, tw) : 0);
     return launch_h3(mw[0], mx[0], mw[1], mx[1], p, grp, w_pairs, tiles, stream);
 }
@@ -719,7 +824,7 @@ int siu3r_conv2d_h3(int Nimg, int H, int W, int Cin, int Cout, int KH, int KW, i
     if (W % 16 != 0 || Cin % 8 != 0) return SIU3R_ERR_UNSUPPORTED;
     const int cblocks = ceil_div(Cin, BKH);
     const int Keff = KH * KW * cblocks * BKH;     // k-blocks run over (tap, 64-channel block); a partial last block is zero-filled by TMA
-    const int tw = pick_tw(Nimg, Cout, Keff, 0, true, H, W);
+    const int tw = pick_tw(Nimg, Cout, Keff, 0, true, H, W, epilogue_weight(act, yh != nullptr, false, residual != nullptr, false, false, false));
     SIU3R_REQUIRE(tw >= 32 && tw <= 256 && tw % 32 == 0);
     CUtensorMap mw, mx;
     int r = map_rows(&mw, Wt, (int64_t)KH * KW * Cin, Cout, ldw, w_plane, use_mhalf(Cout) ? W_ROWS / 2 : W_ROWS); if (r) return r;

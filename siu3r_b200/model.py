@@ -507,12 +507,20 @@ class SIU3RModel:
 
     def _gs_head(self, hw, toks, img4, B, N, gh, gw):
         """-> raw Gaussian parameters [B, S*S, 83] (model.py:195-210)."""
+        rows = None
+        if self.S and img4.shape[2] % 16 == 0:
+            # the 7x7 image conv runs as a 7x1 implicit GEMM over per-pixel packed filter rows (7 taps x 4 channels -> 32 wide); the packing only needs
+            # the image, so it is enqueued before the trunk instead of sitting between the trunk and the full-resolution convs
+            rows = ops.im2col_h3(img4, 1, 7, 1, 0, 3, 32).view(img4.shape[0], img4.shape[1], img4.shape[2], 32)
         p1 = self._dpt_trunk(hw, toks, B, N, gh, gw, p1_ro=not self.S)   # h3: the bilinear upsampling below reads fp32
         n, h, w_, c = p1.shape
         s = ops.conv_kxk_up2x(img4, hw.merger, 7, 7, p1, act=ACT_RELU, round_out=True) if self.R else None   # fused: no [S,S,256] upsampled map
         if s is None:
             up = ops.resize_bilinear(p1, 2 * h, 2 * w_, True)
-            s = self._conv(img4, hw.merger, 7, ro=True, pad=3, act=ACT_RELU, residual=up)
+            if rows is not None:
+                s = ops.conv2d(rows, hw.merger.rowpacked(7, 7, 4), 7, 1, pad=(3, 0), act=ACT_RELU, residual=up, precision=self.prec, round_out=True)
+            else:
+                s = self._conv(img4, hw.merger, 7, ro=True, pad=3, act=ACT_RELU, residual=up)
         t = self._conv(s, hw.head0, 3, ar=True, ro=True, pad=1, act=ACT_RELU)
         raw = torch.empty(B, 4 * h * w_, 83, device=self.dev)
         self._lin(t.view(-1, 256), hw.head4, ar=True, out=raw.view(-1, 83))

@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+L=gpurun_out/call26.log
+: > $L
+timeout -k 10 300 python tools/h3_bench.py twsweep >> $L 2>&1
+grep '"kind": "twsweep"' $L

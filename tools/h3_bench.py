@@ -126,6 +126,73 @@ def bench_epilogue(out):
     print(json.dumps(out[-1]), flush=True)
 
 
+def bench_tiles(out):
+    """Per-tile clock64 stamps of CTA pair 0 (siu3r_gemm_h3_debug_ts): where do the MMA warp and the epilogue warps wait?"""
+    lib = ops._lib.load()
+    M, N, K = 2050, 4096, 1024
+    x = ops.split(torch.randn(M, K, device=DEV))
+    wt = ops.Weight(torch.randn(N, K, device=DEV) / K ** 0.5, torch.randn(N, device=DEV), H3)
+    o = torch.empty(M, N, device=DEV)
+    oh = ops.Split.empty(M, N, device=DEV)
+    ts = torch.zeros(64, dtype=torch.int64, device=DEV)
+    for name, fn in (("plain", lambda: ops.gemm(x, wt, out=o, precision=H3)), ("gelu_split", lambda: ops.gemm(x, wt, out=oh, precision=H3, act=1)),
+                     ("relu_split", lambda: ops.gemm(x, wt, out=oh, precision=H3, act=2)), ("gelu_f32", lambda: ops.gemm(x, wt, out=o, precision=H3, act=1))):
+        for _ in range(3):
+            fn()
+        ts.zero_()
+        lib.siu3r_gemm_h3_debug_ts(ts.data_ptr())
+        fn()
+        torch.cuda.synchronize()
+        lib.siu3r_gemm_h3_debug_ts(None)
+        t = ts.cpu().view(8, 8)
+        t0 = int(t[0, 0])
+        row = {"kind": "tiles", "what": name, "cols": "mma_wait_start, mma_start, mma_issued, epi_wait_start, epi_start, epi_end(w2), epi_end(w17)",
+               "tiles": [[int(v) - t0 if int(v) else None for v in t[i, :7]] for i in range(8) if int(t[i, 0])]}
+        print(json.dumps(row), flush=True)
+        out.append(row)
+
+
+def bench_twsweep(out):
+    """Token tile width sweep WITH the model's epilogues (the cost model in pick_tw must see the exposed epilogue of single-buffered tiles)."""
+    lib = ops._lib.load()
+    g = 32
+    ys, xs_ = torch.meshgrid(torch.arange(g), torch.arange(g), indexing="ij")
+    pos = torch.cat([torch.stack([ys.flatten(), xs_.flatten()], -1), torch.tensor([[g, 0]])], 0)[None].repeat(2, 1, 1).contiguous().to(DEV)
+    tab = ops.rope2d_table(g + 1)
+    for (M, N, K, what) in [(2050, 3072, 1024, "qkv"), (2050, 4096, 1024, "fc1"), (2050, 1024, 4096, "fc2"), (2050, 1024, 1024, "proj"),
+                            (2050, 2304, 768, "qkv"), (2050, 3072, 768, "fc1"), (2050, 768, 3072, "fc2"), (2050, 768, 768, "proj"), (2050, 1536, 768, "qkv_kv"),
+                            (10752, 1024, 256, "fc1r"), (10752, 256, 1024, "fc2")]:
+        x = ops.split(torch.randn(M, K, device=DEV))
+        wt = ops.Weight(torch.randn(N, K, device=DEV) / K ** 0.5, torch.randn(N, device=DEV), H3)
+        stats = torch.zeros(M, 2, device=DEV, dtype=torch.int64)
+        stats[:, 1] = K << 24
+        wln = wt.fold_ln(torch.ones(K, device=DEV), torch.zeros(K, device=DEV))
+        if what.startswith("qkv"):
+            C = N // 3 if what == "qkv" else N // 2
+            rc = 2 * C if what == "qkv" else C
+            q = ops.Split.empty(M, N, device=DEV, unscaled=True)
+            vth = ops.Split.empty(C, (M + 7) // 8 * 8, device=DEV, unscaled=True)
+            fn = lambda: ops.gemm(x, wln, out=q, precision=H3, rope=(pos.view(-1, 2)[:M], tab, rc), vt=(vth, rc, {}), unscaled=True, ln_stats=stats)
+        elif what == "fc1":
+            oh = ops.Split.empty(M, N, device=DEV)
+            fn = lambda: ops.gemm(x, wln, out=oh, precision=H3, act=1, ln_stats=stats)
+        elif what == "fc1r":
+            oh = ops.Split.empty(M, N, device=DEV)
+            fn = lambda: ops.gemm(x, wt, out=oh, precision=H3, act=2)
+        else:
+            r = torch.randn(M, N, device=DEV)
+            rs_ = ops.Split.empty(M, N, device=DEV)
+            fn = lambda: ops.gemm(x, wt, out=rs_, out_f32=r, residual=r, stats_out=stats, precision=H3)
+        row = {"kind": "twsweep", "what": what, "M": M, "N": N, "K": K}
+        row["auto_us"] = timeit(fn, iters=10, warm=2)
+        for tw in (64, 96, 112, 128, 160, 192, 224, 256):
+            lib.siu3r_gemm_h3_force(tw)
+            row[f"tw{tw}"] = round(timeit(fn, iters=10, warm=2), 1)
+        lib.siu3r_gemm_h3_force(0)
+        print(json.dumps(row), flush=True)
+        out.append(row)
+
+
 def bench_limits(out):
     """Which side bounds the mainloop: the operand pipeline alone (no MMAs), the MMAs alone (no loads), both."""
     lib = ops._lib.load()
@@ -243,7 +310,7 @@ if __name__ == "__main__":
     res = []
     for w in what:
         try:
-            {"gemm": bench_gemm, "conv": bench_conv, "flash": bench_flash, "model": bench_model, "epilogue": bench_epilogue, "limits": bench_limits, "mhalf": bench_mhalf}[w](res)
+            {"gemm": bench_gemm, "conv": bench_conv, "flash": bench_flash, "model": bench_model, "epilogue": bench_epilogue, "limits": bench_limits, "mhalf": bench_mhalf, "tiles": bench_tiles, "twsweep": bench_twsweep}[w](res)
         except Exception as ex:  # keep going: one failing section must not lose the others
             print(json.dumps({"kind": w, "error": repr(ex)}), flush=True)
     os.makedirs("gpurun_out", exist_ok=True)

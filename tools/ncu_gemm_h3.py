@@ -13,6 +13,12 @@ if kind == "gemm":
     wt = ops.Weight(torch.randn(N, K, device="cuda") / K ** 0.5, torch.randn(N, device="cuda"), H3)
     o = torch.empty(M, N, device="cuda")
     fn = lambda: ops.gemm(x, wt, out=o, precision=H3)
+elif kind == "fc1":      # GELU + plane-pair output (the encoder's fc1 epilogue)
+    M, N, K = a
+    x = ops.split(torch.randn(M, K, device="cuda"))
+    wt = ops.Weight(torch.randn(N, K, device="cuda") / K ** 0.5, torch.randn(N, device="cuda"), H3)
+    o = ops.Split.empty(M, N, device="cuda")
+    fn = lambda: ops.gemm(x, wt, out=o, precision=H3, act=1)
 elif kind == "conv":
     h, w, cin, cout, k = a
     x = ops.split(torch.randn(1, h, w, cin, device="cuda"))

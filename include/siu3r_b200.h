@@ -67,6 +67,12 @@ int siu3r_raster_features_forward(int G, int H, int W, int C, int cov_stride, co
                                   const float* features, const float* viewmat, const float* intr_host, float near_plane, float far_plane,
                                   float* out_features, float* out_alpha, int32_t* radii_xy, void* workspace, int64_t workspace_bytes,
                                   int64_t dup_capacity, int64_t* num_rendered_host, void* stream);
+/* The same frame without host synchronisation (binned per-tile sort, as siu3r_raster_forward_nosync): status = 4 device words {duplicates, largest
+ * tile, flags, 0}; flags != 0 -> nothing rendered, re-render through siu3r_raster_features_forward.  Outputs are bit-identical to the call above. */
+int siu3r_raster_features_forward_nosync(int G, int H, int W, int C, int cov_stride, const float* means3D, const float* cov, const float* opacities,
+                                         const float* features, const float* viewmat, float fx, float fy, float cx, float cy, float near_plane,
+                                         float far_plane, float* out_features, float* out_alpha, int32_t* radii_xy, void* workspace,
+                                         int64_t workspace_bytes, int64_t dup_capacity, uint32_t* status, void* stream);
 /* testing aid: 0 disables the blend kernel's exact sub-tile culling (every pixel then evaluates every record of its tile, the
  * literal loop of the reference rasterizer); results must be bit-identical either way (tests/test_ops_gpu.py) */
 void siu3r_raster_set_culling(int enabled);

@@ -30,6 +30,7 @@ SIGNATURES = {
     "siu3r_raster_set_regsort": (None, [_i]),
     "siu3r_raster_set_culling": (None, [_i]),
     "siu3r_raster_set_binning": (None, [_i]),
+    "siu3r_raster_features_forward_nosync": (_i, [_i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _f, _f, _f, _f, _f, _f, _p, _p, _p, _p, _l, _l, _p, _p]),
     "siu3r_raster_features_forward": (_i, [_i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _l, _l, C.POINTER(C.c_int64), _p]),
     "siu3r_gemm_tc": (_i, [_i, _i, _i, _p, _p, _l, _p, _p, _l, _p, _l, _p, _p, _l, _i, _f, _i, _p]),
     "siu3r_conv2d_tc": (_i, [_i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _l, _p, _p, _l, _i, _i, _p]),

@@ -749,7 +749,9 @@ __global__ void __launch_bounds__(128) preprocess_feat_kernel(int G, int H, int 
 constexpr int FCH = 32;
 __global__ void __launch_bounds__(RB) render_feat_kernel(int W, int H, int gx, const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
                                                          const float2* __restrict__ xy, const float4* __restrict__ conic_o,
-                                                         const float* __restrict__ feats, int C, float* __restrict__ out, float* __restrict__ out_alpha) {
+                                                         const float* __restrict__ feats, int C, float* __restrict__ out, float* __restrict__ out_alpha,
+                                                         const uint32_t* __restrict__ status) {
+    if (status && status[2]) return;   // no-sync protocol: the frame overflowed, the host re-renders it
     __shared__ float2 s_xy[RB];
     __shared__ float4 s_co[RB];
     __shared__ float4 s_box[RB];
@@ -856,6 +858,19 @@ __global__ void __launch_bounds__(RB) render_feat_kernel(int W, int H, int gx, c
         }
         if (blockIdx.z == 0 && out_alpha) out_alpha[(size_t)pyi * W + pxi] = 1.0f - T;
     }
+}
+
+// camera block of the feature rasterizer: world-to-camera matrix (device) + six scalars passed by value
+__global__ void pack_feat_camera_kernel(const float* __restrict__ viewmat, float fx, float fy, float cx, float cy, float near_plane, float far_plane,
+                                        float* __restrict__ cam) {
+    const int t = threadIdx.x;
+    if (t < 16) cam[t] = viewmat[t];
+    if (t == 16) cam[16] = fx;
+    if (t == 17) cam[17] = fy;
+    if (t == 18) cam[18] = cx;
+    if (t == 19) cam[19] = cy;
+    if (t == 20) cam[20] = near_plane;
+    if (t == 21) cam[21] = far_plane;
 }
 
 __global__ void pack_camera_kernel(const float* __restrict__ view, const float* __restrict__ proj, const float* __restrict__ campos,
@@ -1202,7 +1217,54 @@ int siu3r_raster_features_forward(int G, int H, int W, int C, int cov_stride, co
         siu3r_note_launch(2);
     }
     dim3 grid(gx, gy, ceil_div(C, FCH));
-    render_feat_kernel<<<grid, RB, 0, stream>>>(W, H, gx, w.ranges, w.vals_sorted, w.xy, w.conic_o, features, C, out_features, out_alpha);
+    render_feat_kernel<<<grid, RB, 0, stream>>>(W, H, gx, w.ranges, w.vals_sorted, w.xy, w.conic_o, features, C, out_features, out_alpha, nullptr);
+    SIU3R_LAUNCH_CHECK();
+    siu3r_note_launch(1);
+    return SIU3R_OK;
+}
+
+// The same frame without any host synchronisation, on the binned path of siu3r_raster_forward_nosync (per-tile counts -> scan -> scatter of
+// (depth bits << 32 | id) words -> per-tile register sort: the order the global radix sort of (tile << 32 | depth) yields, so the outputs are
+// bit-identical).  status_dev: 4 device words {duplicates, largest tile, flags, 0}; flags != 0 (capacity exceeded / a tile above 8192 records): nothing
+// was rendered and the caller re-renders through siu3r_raster_features_forward.  intr = (fx, fy, cx, cy) are passed by value.
+int siu3r_raster_features_forward_nosync(int G, int H, int W, int C, int cov_stride, const float* means3D, const float* cov, const float* opacities,
+                                         const float* features, const float* viewmat, float fx, float fy, float cx, float cy, float near_plane,
+                                         float far_plane, float* out_features, float* out_alpha, int32_t* radii_xy, void* workspace,
+                                         int64_t workspace_bytes, int64_t dup_capacity, uint32_t* status_dev, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    SIU3R_REQUIRE(G > 0 && H > 0 && W > 0 && C > 0 && (cov_stride == 6 || cov_stride == 9) && status_dev);
+    SIU3R_REQUIRE(means3D && cov && opacities && features && viewmat && out_features && workspace);
+    SIU3R_REQUIRE(dup_capacity > 0 && dup_capacity < (1ll << 31));
+    const int gx = ceil_div(W, TILE_X), gy = ceil_div(H, TILE_Y), ntiles = gx * gy;
+    SIU3R_REQUIRE(gx < 65536 && gy < 65536 && ceil_div(C, FCH) < 65536);
+    if ((size_t)ntiles * 8 > 200 * 1024) return SIU3R_ERR_UNSUPPORTED;
+    Workspace w = carve(workspace, G, H, W, dup_capacity);
+    if ((int64_t)w.bytes > workspace_bytes) return SIU3R_ERR_CAPACITY;
+    static bool attr_bin[64] = {false};
+    int dev = 0;
+    SIU3R_CUDA_CHECK(cudaGetDevice(&dev));
+    if (!attr_bin[dev & 63]) {
+        SIU3R_CUDA_CHECK(cudaFuncSetAttribute(bin_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        SIU3R_CUDA_CHECK(cudaFuncSetAttribute(bin_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_bin[dev & 63] = true;
+    }
+    int32_t* radii = reinterpret_cast<int32_t*>(w.rgb);
+    SIU3R_CUDA_CHECK(cudaMemsetAsync(radii, 0, sizeof(int32_t) * G, stream));
+    SIU3R_CUDA_CHECK(cudaMemsetAsync(w.tiles, 0, sizeof(uint32_t) * G, stream));
+    SIU3R_CUDA_CHECK(cudaMemsetAsync(w.tile_counts, 0, sizeof(uint32_t) * ntiles, stream));
+    if (radii_xy) SIU3R_CUDA_CHECK(cudaMemsetAsync(radii_xy, 0, sizeof(int32_t) * 2 * G, stream));
+    pack_feat_camera_kernel<<<1, 32, 0, stream>>>(viewmat, fx, fy, cx, cy, near_plane, far_plane, w.cam);
+    preprocess_feat_kernel<<<ceil_div(G, 128), 128, 0, stream>>>(G, H, W, gx, gy, cov_stride, means3D, cov, opacities, w.cam, w.depths, w.xy,
+                                                                w.conic_o, w.tiles, w.rects, radii, radii_xy);
+    bin_count_kernel<<<ceil_div(G, BIN_CHUNK), BIN_THREADS, (size_t)ntiles * 4, stream>>>(G, gx, ntiles, radii, w.rects, w.tile_counts);
+    tile_scan_kernel<<<1, 1024, 0, stream>>>(w.tile_counts, ntiles, w.ranges, w.tile_cursors, w.total, (uint32_t)dup_capacity, status_dev);
+    bin_scatter_kernel<<<ceil_div(G, BIN_CHUNK), BIN_THREADS, (size_t)ntiles * 8, stream>>>(G, gx, ntiles, radii, w.depths, w.rects, w.tile_cursors,
+                                                                                          w.keys, status_dev);
+    SIU3R_LAUNCH_CHECK();
+    siu3r_note_launch(5);
+    int r = launch_tile_sorts(ntiles, w.ranges, w.keys, w.vals_sorted, TS_CAP, status_dev, stream); if (r) return r;
+    dim3 grid(gx, gy, ceil_div(C, FCH));
+    render_feat_kernel<<<grid, RB, 0, stream>>>(W, H, gx, w.ranges, w.vals_sorted, w.xy, w.conic_o, features, C, out_features, out_alpha, status_dev);
     SIU3R_LAUNCH_CHECK();
     siu3r_note_launch(1);
     return SIU3R_OK;

@@ -1021,6 +1021,31 @@ def raster_forward_nosync(means, cov, shs, opac, viewmatrix, projmatrix, campos,
     return out
 
 
+def raster_features_forward_nosync(means, cov, opac, feats, viewmat, intr, near, far, H, W, status, ws=None, dup_capacity=None, out=None, alpha=None):
+    """raster_features_forward without a host round trip (siu3r_raster_features_forward_nosync): `status` = 4 int32 on the device receiving
+    {duplicates, largest tile, flags, 0}; flags != 0 means the frame was NOT rendered (the caller re-renders it through raster_features_forward).
+    `ws` = reusable workspace.  -> dict(features [H,W,C], alpha, ws)."""
+    lib = _lib.load()
+    _chk_f32(means, cov, opac, feats, viewmat)
+    assert means.is_contiguous() and cov.is_contiguous() and opac.is_contiguous() and feats.is_contiguous() and viewmat.is_contiguous()
+    assert status.dtype == torch.int32 and status.numel() >= 4 and status.is_contiguous()
+    G, Cc = means.shape[0], feats.shape[1]
+    cov_stride = 6 if cov.shape[-1] == 6 else 9
+    dev = means.device
+    if dup_capacity is None:
+        dup_capacity = max(1 << 16, 8 * G)
+    ws_bytes = int(lib.siu3r_raster_workspace_bytes(G, H, W, dup_capacity))
+    if ws is None or ws.numel() < ws_bytes:
+        ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+    if out is None:
+        out = torch.empty(H, W, Cc, device=dev)
+    fx, fy, cx, cy = (float(v) for v in intr)
+    code = lib.siu3r_raster_features_forward_nosync(G, H, W, Cc, cov_stride, _p(means), _p(cov), _p(opac), _p(feats), _p(viewmat), fx, fy, cx, cy, float(near),
+                                                    float(far), _p(out), _p(alpha), None, _p(ws), ws.numel(), dup_capacity, _p(status), _stream())
+    _lib.check(code, "raster_features_forward_nosync")
+    return dict(features=out, alpha=alpha, ws=ws)
+
+
 def raster_features_forward(means, cov, opac, feats, viewmat, intr, near, far, H, W, dup_capacity=None, want_alpha=True, want_radii=False):
     """N-channel feature splatting of one camera (gsplat.rasterization semantics).  means [G,3]; cov [G,3,3] or [G,6]; opac [G];
     feats [G,C]; viewmat [4,4] world-to-camera (device); intr = (fx, fy, cx, cy) in pixels.  -> dict(features [H,W,C], alpha [H,W], ...)."""

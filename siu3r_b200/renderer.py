@@ -159,11 +159,19 @@ class SplattingCUDA:
                 feats = logits.reshape(n, q * c).contiguous()
                 Ks = intrinsics[bi].detach().float().cpu()
                 viewmats = torch.linalg.inv(E[bi]).contiguous().to(gaussians.means.device)
-                outs = []
+                # all V cameras are enqueued on one workspace without a host round trip (binned per-tile sort); the status words are read once and a
+                # camera that overflowed is re-rendered through the sizing path
+                mg, cg, og = gaussians.means[bi].contiguous(), gaussians.covariances[bi].contiguous(), gaussians.opacities[bi].contiguous()
+                intrs = [(float(Ks[vi, 0, 0]) * w, float(Ks[vi, 1, 1]) * h, float(Ks[vi, 0, 2]) * w, float(Ks[vi, 1, 2]) * h) for vi in range(v)]
+                stacked = torch.empty(v, h, w, q * c, device=mg.device)
+                status = torch.zeros(v, 4, device=mg.device, dtype=torch.int32)
+                ws = None
                 for vi in range(v):
-                    intr = (float(Ks[vi, 0, 0]) * w, float(Ks[vi, 1, 1]) * h, float(Ks[vi, 0, 2]) * w, float(Ks[vi, 1, 2]) * h)
-                    r = ops.raster_features_forward(gaussians.means[bi].contiguous(), gaussians.covariances[bi].contiguous(),
-                                                    gaussians.opacities[bi].contiguous(), feats, viewmats[vi], intr, near, far, h, w, want_alpha=False)
-                    outs.append(r["features"])
-                qc.append(torch.stack(outs).view(v, h, w, q, c).permute(0, 3, 4, 1, 2))     # "n h w (q c) -> n q c h w" as a view
+                    ws = ops.raster_features_forward_nosync(mg, cg, og, feats, viewmats[vi], intrs[vi], near, far, h, w, status[vi], ws=ws, out=stacked[vi])["ws"]
+                st = status.cpu()
+                for vi in range(v):
+                    if int(st[vi, 2]) != 0:
+                        stacked[vi] = ops.raster_features_forward(mg, cg, og, feats, viewmats[vi], intrs[vi], near, far, h, w, want_alpha=False,
+                                                                  dup_capacity=int(int(st[vi, 0]) * 1.05) + 1024)["features"]
+                qc.append(stacked.view(v, h, w, q, c).permute(0, 3, 4, 1, 2))     # "n h w (q c) -> n q c h w" as a view
         return {"render_color": color, "render_depth": depth, "render_qc_logits": qc}

@@ -572,6 +572,19 @@ def test_raster_features_vs_oracle(G, H, W, C):
     # linearity in the features (the blend weights do not depend on them)
     res3 = ops.raster_features_forward(t(means), t(cov), t(op), t(2 * feats), t(V), (fx, fy, cx, cy), 1.0, 1000.0, H, W)
     assert float((res3["features"] - 2 * res["features"]).abs().max()) < 1e-4 * scale
+    # the no-host-sync binned path renders the identical frame and reports the duplicate count on the device
+    status = torch.zeros(4, device=DEV, dtype=torch.int32)
+    alpha4 = torch.empty(H, W, device=DEV)
+    res4 = ops.raster_features_forward_nosync(t(means), t(cov), t(op), t(feats), t(V), (fx, fy, cx, cy), 1.0, 1000.0, H, W, status, alpha=alpha4)
+    st = status.cpu()
+    assert int(st[2]) == 0 and int(st[0]) == res["num_rendered"]
+    assert torch.equal(res4["features"], res["features"]) and torch.equal(alpha4, res["alpha"])
+    if res["num_rendered"] > 8:   # capacity overflow: flagged, nothing rendered
+        status.zero_()
+        out5 = torch.full((H, W, C), 7.0, device=DEV)
+        ops.raster_features_forward_nosync(t(means), t(cov), t(op), t(feats), t(V), (fx, fy, cx, cy), 1.0, 1000.0, H, W, status, dup_capacity=4, out=out5)
+        st = status.cpu()
+        assert int(st[2]) & 1 and int(st[0]) == res["num_rendered"] and torch.all(out5 == 7.0)
 
 
 def test_splatting_render_qc_logits_surface():

@@ -266,7 +266,7 @@ int siu3r_gemm_h3(int ngroups, const int* M_host, int N, int K, const void* cons
                   const float* rope_tab, int rope_cols, void* const* vt_host, const int* vt_cols_host, int64_t vt_ld, int64_t vt_plane, int vt_col0,
                   int unscaled_lo, void* stream);
 /* siu3r_gemm_h3 with LayerNorm fused on either side (croco/blocks.py:127-130,186-190: x + f(norm(x)) blocks):
- *   stats_out_host[g] (int64 [M_g][2], zeroed by the caller): the launch adds the statistics (sum, sum of squares; 2^24 fixed point) of the rows it writes;
+ *   stats_out_host[g] (int64 [M_g][2], zeroed by the caller): the launch adds the statistics (sum * 2^32, sum of squares * 2^26: fixed point) of the rows it writes;
  *   stats_in_host[g] + ln_s_host[g]: X_g are RAW rows, W_g = W*gamma, bias_g = W beta + b, ln_s[n] = sum_k gamma_k W[n,k]; computes Linear(LayerNorm(x));
  *   C_host and Ch_host may both be given (fp32 residual stream + plane pair for the next GEMM). */
 int siu3r_gemm_h3_ln(int ngroups, const int* M_host, int N, int K, const void* const* X_host, int64_t lda, int64_t a_plane, const void* const* W_host,

@@ -76,13 +76,15 @@ struct H3Problem {       // what differs between the problems of a grouped launc
     int M;               // rows (linear) / images (conv)
     __half* vt;          // V^T destination (hi plane) of this problem's rows, or null
     int vt_cols;         // columns of a V^T row this problem owns (>= M, multiple of 8): [M, vt_cols) is zero-filled
-    // Fused LayerNorm (linear mode).  Row statistics are int64 fixed-point pairs (sum x, sum x^2) * 2^24 per row: integer atomics add in any order
+    // Fused LayerNorm (linear mode).  Row statistics are int64 fixed-point pairs (sum x * 2^32, sum x^2 * 2^26) per row: integer atomics add in any order
     // to the same bits, so the statistics -- and everything downstream -- are reproducible run to run.
     const long long* stats_in;   // consumer: the A operand is the RAW row x, the weights carry gamma; the epilogue applies rstd*(acc - mu*ln_s[n]) + bias
     const float* ln_s;           //           ln_s[n] = sum_k gamma_k W[n,k]  (bias[n] = sum_k beta_k W[n,k] + b[n] is folded by the host)
     long long* stats_out;        // producer: accumulates the statistics of the rows it writes (every column block adds its 32-column partial sums)
 };
-constexpr float STATS_SCALE = 16777216.0f;   // 2^24
+// sum x in 2^-32 steps (range +-2.1e9), sum x^2 in 2^-26 steps: range 1.4e11 covers 1024 columns of fp16-representable magnitudes (one 65504 outlier is
+// 4.3e9), and the 1.5e-8 step is 1e-5 of the 1e-6 epsilon that floors the variance anyway (rows of magnitude 1e-3 keep rstd to 1.5e-5 relative).
+constexpr float STATS_SCALE = 4294967296.0f, STATS_SCALE_SQ = 67108864.0f;
 struct H3Group { H3Problem prob[2]; int tiles0; };
 
 struct Frag {            // where the 16 tokens of one epilogue fragment live: 16 consecutive output rows
@@ -244,7 +246,7 @@ __device__ __forceinline__ void epi_frag_loop(const EpiCtx& c, const H3Params& p
         }
         if (pr.stats_out != nullptr) {
             // Row statistics for a LayerNorm fused into the NEXT GEMM: 32 values per lane (16 sums, 16 sums of squares) are reduced over the warp's 32
-            // columns by a halving butterfly (31 shuffles); lane l ends up with statistic l >> 4 of token l & 15 and adds it, as a 2^-24 fixed-point
+            // columns by a halving butterfly (31 shuffles); lane l ends up with statistic l >> 4 of token l & 15 and adds it, as a fixed-point
             // integer, to the row's accumulator.
             float w[32];
 #pragma unroll
@@ -265,7 +267,7 @@ __device__ __forceinline__ void epi_frag_loop(const EpiCtx& c, const H3Params& p
             const int tj = lane & 15;
             if (tj < f.nv)
                 atomicAdd(reinterpret_cast<unsigned long long*>(pr.stats_out) + (f.rb + tj) * 2 + (lane >> 4),
-                          (unsigned long long)__float2ll_rn(w[0] * STATS_SCALE));
+                          (unsigned long long)__float2ll_rn(w[0] * ((lane >> 4) ? STATS_SCALE_SQ : STATS_SCALE)));
         }
     }
 }
@@ -306,7 +308,7 @@ __device__ __forceinline__ void run_epilogue(uint32_t tmem_hh, uint32_t tmem_x, 
             if (m_base + t < pr.M) {
                 const longlong2 st = __ldcg(reinterpret_cast<const longlong2*>(pr.stats_in) + (m_base + t));
                 const double m = (double)st.x * (double)(p.ln_inv_c / STATS_SCALE);
-                const double var = fmax((double)st.y * (double)(p.ln_inv_c / STATS_SCALE) - m * m, 0.0);
+                const double var = fmax((double)st.y * (double)(p.ln_inv_c / STATS_SCALE_SQ) - m * m, 0.0);
                 mr = make_float2((float)m, rsqrtf((float)var + p.ln_eps));
             }
             ln_mr[t] = mr;
@@ -741,7 +743,7 @@ int siu3r_merge_h3(const void* in, int64_t ldi, int64_t plane, int64_t rows, int
 // Pointer arrays are HOST arrays of device pointers.  This is how the two decoder streams of AsymmetricCroCo (dec_blocks / dec_blocks2:
 // backbone_croco.py:244-250, :514-531) share the machine; ngroups = 1 is the plain nn.Linear replacement.
 // Fused-LayerNorm extension of siu3r_gemm_h3 (same arguments, plus):
-//   stats_out_g != null: the launch also accumulates the row statistics (sum, sum of squares, 2^24 fixed point, int64 pairs, ZEROED by the caller) of
+//   stats_out_g != null: the launch also accumulates the row statistics (sum * 2^32, sum of squares * 2^26, int64 pairs, ZEROED by the caller) of
 //     the rows it writes -- the producer half of a LayerNorm fused into the GEMM that consumes these rows next;
 //   stats_in_g != null (with ln_s_g): X_g holds the RAW rows, W_g = W * gamma, bias_g = W beta + b, ln_s_g[n] = sum_k gamma_k W[n,k]; the epilogue applies
 //     rstd_m * (acc - mean_m * ln_s[n]) + bias[n] before activation / RoPE  ==  Linear(LayerNorm(x)) (croco/blocks.py:127-130,186-190).  alpha must be 1.

@@ -126,7 +126,7 @@ def test_gemm_h3_fused_layernorm(M, C, N):
     ops.gemm(a, wproj, residual=x0, out=xs, out_f32=xf, stats_out=stats, precision=H3)
     assert torch.equal(xf, x_plain)                                   # the extra outputs do not change the fp32 result
     assert torch.equal(xs.t, ops.split(xf).t)                         # the plane pair is the split of exactly those values
-    s1, s2 = stats[:, 0].double() / 2 ** 24, stats[:, 1].double() / 2 ** 24
+    s1, s2 = stats[:, 0].double() / 2 ** 32, stats[:, 1].double() / 2 ** 26
     assert float((s1 - xf.double().sum(1)).abs().max()) < 2e-6 * float(xf.abs().sum(1).max()) + 1e-5
     assert float(((s2 - (xf.double() ** 2).sum(1)).abs() / (xf.double() ** 2).sum(1)).max()) < 1e-6
     stats2 = torch.zeros_like(stats)
@@ -151,6 +151,27 @@ def test_gemm_h3_fused_layernorm(M, C, N):
     h = M // 2
     ys = ops.gemm_group2([xs[:h], xs[h:]], [wfold, wfold], act=1, precision=H3, round_out=True, ln_stats=[stats[:h], stats[h:]])
     assert rel_err(torch.cat([ys[0].float(), ys[1].float()]), y_ref) < 1e-5
+
+
+@pytest.mark.parametrize("mag", [1e-3, 1.0, 300.0])
+def test_gemm_h3_fused_layernorm_row_magnitudes(mag):
+    """The fixed-point row statistics (2^-32 resolution, int64 range) keep LayerNorm accurate for rows of magnitude 1e-3 as well as for rows with
+    outliers of several hundred (the 'massive activations' of real ViT checkpoints)."""
+    from siu3r_b200 import ops
+    M, C, N = 515, 768, 256
+    x0 = rnd(M, C, seed=41) * mag
+    x0[:, 7] *= 40.0                                                  # one outlier channel
+    zero_w = ops.Weight(torch.zeros(C, C, device=DEV), torch.zeros(C, device=DEV), H3)
+    gam, bet = 1.0 + 0.3 * rnd(C, seed=42), 0.2 * rnd(C, seed=43)
+    w2, b2 = rnd(N, C, seed=44, scale=C ** -0.5), rnd(N, seed=45)
+    wfold = ops.Weight(w2, b2, H3).fold_ln(gam, bet)
+    stats = torch.zeros(M, 2, device=DEV, dtype=torch.int64)
+    xs, xf = ops.Split.empty(M, C, device=DEV), torch.empty(M, C, device=DEV)
+    ops.gemm(torch.zeros(M, C, device=DEV), zero_w, residual=x0, out=xs, out_f32=xf, stats_out=stats, precision=H3)
+    assert torch.equal(xf, x0)
+    y = ops.gemm(xs, wfold, ln_stats=stats, precision=H3)
+    ref = F.linear(F.layer_norm(x0.double(), (C,), gam.double(), bet.double(), 1e-6), w2.double(), b2.double())
+    assert rel_err(y, ref) < 2e-5, (mag, rel_err(y, ref))
 
 
 def test_model_fused_layernorm_matches_unfused(monkeypatch):

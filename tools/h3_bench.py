@@ -91,7 +91,7 @@ def bench_epilogue(out):
             o = torch.empty(M, N, device=DEV)
             row["plain_us"] = timeit(lambda: ops.gemm(x, wt, out=o, precision=H3))
             stats = torch.zeros(M, 2, device=DEV, dtype=torch.int64)
-            stats[:, 1] = K << 24          # mean 0, variance 1
+            stats[:, 1] = K << 26          # mean 0, variance 1
             wln = wt.fold_ln(torch.ones(K, device=DEV), torch.zeros(K, device=DEV))
             if what == "qkv":
                 C = 1024
@@ -165,7 +165,7 @@ def bench_twsweep(out):
         x = ops.split(torch.randn(M, K, device=DEV))
         wt = ops.Weight(torch.randn(N, K, device=DEV) / K ** 0.5, torch.randn(N, device=DEV), H3)
         stats = torch.zeros(M, 2, device=DEV, dtype=torch.int64)
-        stats[:, 1] = K << 24
+        stats[:, 1] = K << 26
         wln = wt.fold_ln(torch.ones(K, device=DEV), torch.zeros(K, device=DEV))
         if what.startswith("qkv"):
             C = N // 3 if what == "qkv" else N // 2

@@ -960,6 +960,13 @@ int g_cull = 1;   // testing aid: 0 blends every record of the tile at every pix
 
 }  // namespace
 
+// The sizing entry points read the duplicate count back (cudaStreamSynchronize): not possible on a capturing stream -> use the *_nosync variants.
+static bool stream_is_capturing(cudaStream_t stream) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &st) != cudaSuccess) { cudaGetLastError(); return false; }
+    return st != cudaStreamCaptureStatusNone;
+}
+
 extern "C" {
 
 void siu3r_raster_set_culling(int enabled) { g_cull = enabled ? 1 : 0; }
@@ -1002,6 +1009,7 @@ int siu3r_raster_forward(int G, int H, int W, int sh_degree, int sh_coeffs, int 
     SIU3R_REQUIRE(means3D && cov && shs && opacities && viewmatrix && projmatrix && campos && bg);
     SIU3R_REQUIRE(out_color && out_depth && out_opacity && radii && workspace);
     SIU3R_REQUIRE(dup_capacity > 0 && dup_capacity < (1ll << 31));
+    if (stream_is_capturing(stream)) return SIU3R_ERR_UNSUPPORTED;
     const int gx = ceil_div(W, TILE_X), gy = ceil_div(H, TILE_Y);
     SIU3R_REQUIRE(gx < 65536 && gy < 65536);
     Workspace w = carve(workspace, G, H, W, dup_capacity);
@@ -1180,6 +1188,7 @@ int siu3r_raster_features_forward(int G, int H, int W, int C, int cov_stride, co
     SIU3R_REQUIRE(G > 0 && H > 0 && W > 0 && C > 0 && (cov_stride == 6 || cov_stride == 9));
     SIU3R_REQUIRE(means3D && cov && opacities && features && viewmat && intr_host && out_features && workspace);
     SIU3R_REQUIRE(dup_capacity > 0 && dup_capacity < (1ll << 31));
+    if (stream_is_capturing(stream)) return SIU3R_ERR_UNSUPPORTED;
     const int gx = ceil_div(W, TILE_X), gy = ceil_div(H, TILE_Y);
     SIU3R_REQUIRE(gx < 65536 && gy < 65536 && ceil_div(C, FCH) < 65536);
     Workspace w = carve(workspace, G, H, W, dup_capacity);

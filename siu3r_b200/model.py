@@ -92,6 +92,9 @@ class SIU3RModel:
         The reference loads with strict=False (inference.py:119-121), so e.g. the lpips.* entries of a Lightning checkpoint are ignored."""
         from .synth import load_state_shapes
         expected = load_state_shapes()
+        if any(k.startswith("model.") for k in sd) and not any(k in expected for k in sd):
+            # a Lightning checkpoint's state_dict ("model." + key, inference.py:119-121): strip the prefix BEFORE the shape check
+            sd = {(k[6:] if k.startswith("model.") else k): v for k, v in sd.items()}
         missing = [k for k in expected if k not in sd]
         unexpected = [k for k in sd if k not in expected]
         wrong = [f"{k}: checkpoint {list(sd[k].shape)} vs model {expected[k][0]}" for k in expected

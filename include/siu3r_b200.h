@@ -294,6 +294,7 @@ int siu3r_im2col_nhwc_h3(const float* x, int N, int H, int W, int C, int KH, int
 /* tuning / debugging aids */
 void siu3r_gemm_h3_force(int tw);
 void siu3r_gemm_h3_set_mhalf(int on);
+void siu3r_gemm_h3_set_remainder_tiles(int on);
 void siu3r_gemm_h3_cluster_cap(int cap);
 void siu3r_gemm_h3_order(int order);   /* 0 = neighbouring CTA pairs share the token tile, 1 = they share the weight rows */
 int siu3r_gemm_h3_plan(int M, int N, int K, int M1, int* tw_out, int* tiles_out, int* rounds_out);

@@ -81,6 +81,7 @@ SIGNATURES = {
     # h3 mode (fp32-grade results on the fp16 tensor-core path)
     "siu3r_gemm_h3_force": (None, [_i]),
     "siu3r_gemm_h3_set_mhalf": (None, [_i]),
+    "siu3r_gemm_h3_set_remainder_tiles": (None, [_i]),
     "siu3r_gemm_h3_cluster_cap": (None, [_i]),
     "siu3r_gemm_h3_order": (None, [_i]),
     "siu3r_gemm_h3_debug": (None, [_i]),

@@ -51,7 +51,6 @@ enum Act { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2, ACT_MASK = 3 };
 struct H3Params {
     int N, num_kb;             // weight rows, k-blocks
     int tw, nbuf, nstages;     // token tile width, accumulator sets in TMEM (1 or 2), pipeline depth
-    int prew;                  // 1: weight loads of the first tile are issued before the programmatic-dependent-launch wait
     int mhalf;                 // N <= 128: MMA M = 128 (64 weight rows per CTA) instead of 256 -- no tensor time is spent on padding rows
     int act; float alpha;
     int64_t ldc;               // fp32 output pitch
@@ -85,7 +84,11 @@ struct H3Problem {       // what differs between the problems of a grouped launc
 // sum x in 2^-32 steps (range +-2.1e9), sum x^2 in 2^-26 steps: range 1.4e11 covers 1024 columns of fp16-representable magnitudes (one 65504 outlier is
 // 4.3e9), and the 1.5e-8 step is 1e-5 of the 1e-6 epsilon that floors the variance anyway (rows of magnitude 1e-3 keep rstd to 1.5e-5 relative).
 constexpr float STATS_SCALE = 4294967296.0f, STATS_SCALE_SQ = 67108864.0f;
-struct H3Group { H3Problem prob[2]; int tiles0; };
+struct H3Group {
+    H3Problem prob[2]; int tiles0;
+    int tw_r[2];         // linear mode: width of each problem's LAST token tile (its remaining rows rounded up to the MMA-N granularity, <= tw): M = 2050 =
+                         // 16 x 128 + 2 would otherwise spend a full 128-wide tile on two tokens (1025 = 8 x 128 + 1 in the decoder: one tile in nine)
+};
 
 struct Frag {            // where the 16 tokens of one epilogue fragment live: 16 consecutive output rows
     int64_t rb;          // first output row
@@ -275,11 +278,11 @@ __device__ __forceinline__ void epi_frag_loop(const EpiCtx& c, const H3Params& p
 // Epilogue of one warp: TMEM lanes [32q, 32q+32) = weight rows n, columns [c_lo, c_hi) = its share of the tile's tokens, 16 at a time.
 // mhalf (M = 128 over the CTA pair): lanes [0, 64) hold this CTA's 64 weight rows for the first half of the tile's tokens, lanes [64, 128) the
 // same rows for the second half (the accumulator is tw/2 columns wide); tok_off = token index of column 0 for this warp.
-__device__ __forceinline__ void run_epilogue(uint32_t tmem_hh, uint32_t tmem_x, int lane, int q, int c_lo, int c_hi, int n_cta, int tt,
+__device__ __forceinline__ void run_epilogue(uint32_t tmem_hh, uint32_t tmem_x, int lane, int q, int c_lo, int c_hi, int twt, int n_cta, int tt,
                                              const H3Params& p, const H3Problem& pr, uint64_t* bar, uint32_t parity, float2* ln_mr, int epi_tid,
                                              unsigned long long* ts_start) {
     const int nb = n_cta + (p.mhalf ? (q & 1) : q) * 32;           // warp-uniform first weight row
-    const int tok_off = p.mhalf ? (q >> 1) * (p.tw >> 1) : 0;
+    const int tok_off = p.mhalf ? (q >> 1) * (twt >> 1) : 0;      // twt = width of THIS tile (the last token tile of a problem may be narrower)
     const int n = nb + lane;
     const bool n_ok = n < p.N;
     const float bias = (pr.bias && n_ok) ? __ldg(pr.bias + n) : 0.0f;
@@ -345,7 +348,8 @@ __device__ __forceinline__ void run_epilogue(uint32_t tmem_hh, uint32_t tmem_x, 
 //            tempty[b] (leader, 32 arrivals) <- one per epilogue warp of both CTAs once accumulator set b has been drained.
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 gemm_h3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
-               const __grid_constant__ CUtensorMap tmX1, const H3Params p, const H3Group grp, int w_pairs, int num_tiles) {
+               const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ CUtensorMap tmXr, const __grid_constant__ CUtensorMap tmXr1,
+               const H3Params p, const H3Group grp, int w_pairs, int num_tiles) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + PIPE_BYTES);
@@ -367,13 +371,13 @@ gemm_h3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
     const int wrows = p.mhalf ? W_ROWS / 2 : W_ROWS;            // weight rows per CTA
     const int w_plane_bytes = wrows * 128, w_bytes = 2 * w_plane_bytes;
     const int stage_bytes = w_bytes + 2 * x_plane_bytes;
-    const uint32_t stage_tx = 2u * (uint32_t)stage_bytes;      // both CTAs' bytes land on the leader's barrier
     const int nstages = p.nstages, nbuf = p.nbuf;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmW);
         prefetch_tmap(&tmX);
         if (grp.tiles0 < num_tiles) { prefetch_tmap(&tmW1); prefetch_tmap(&tmX1); }
+        if (!p.conv) { prefetch_tmap(&tmXr); if (grp.tiles0 < num_tiles) prefetch_tmap(&tmXr1); }
         for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 2 * EPI_WARPS); }
         fence_barrier_init();
@@ -388,33 +392,6 @@ gemm_h3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
     tc_fence_after();
     // Programmatic dependent launch: everything above overlapped the previous kernel's tail; from here on its outputs are needed (TMA loads of the
     // activations, residual reads) or overwritten.  All CTAs of this persistent grid are resident, so the next kernel may be scheduled as they retire.
-    // Experiment (H3Params::prew, off by default, see g_prew): the producer warp starts the WEIGHT loads of its first tile (static data) before the
-    // wait, so that a CTA pair that became resident early has its weight stages in flight when the activations become visible.
-    int prew = 0;
-    if (warp == 0 && p.prew && cluster_id < num_tiles) {
-        const int u = cluster_id;
-        const int g = u >= grp.tiles0;
-        const int tl = g ? u - grp.tiles0 : u;
-        const CUtensorMap* mw = g ? &tmW1 : &tmW;
-        const int tcount = g ? p.ttiles1 : p.ttiles0;
-        const int wi = p.order ? tl / tcount : tl % w_pairs;
-        const int n0 = wi * 2 * wrows + (int)rank * wrows;
-        prew = p.num_kb < nstages ? p.num_kb : nstages;
-        for (int kb = 0; kb < prew; ++kb) {
-            uint8_t* sW = smem + kb * stage_bytes;
-            const uint32_t lead_full = mapa_to_cta(smem_u32(&full_bar[kb]), 0);
-            if (elect_one_sync()) {
-                if (leader) mbar_expect_tx(&full_bar[kb], stage_tx);
-                if (p.conv) {
-                    const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
-                    tma2_load_3d(mw, lead_full, sW, tap * p.Cin + cb * BKH, n0, 0);
-                } else {
-                    tma2_load_3d(mw, lead_full, sW, kb * BKH, n0, 0);
-                }
-            }
-            __syncwarp();
-        }
-    }
     pdl_wait();
     pdl_launch_dependents();
     const uint32_t tmem_base = *tmem_slot;
@@ -428,12 +405,14 @@ gemm_h3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                 const int g = u >= grp.tiles0;
                 const int tl = g ? u - grp.tiles0 : u;
                 const CUtensorMap* mw = g ? &tmW1 : &tmW;
-                const CUtensorMap* mx = g ? &tmX1 : &tmX;
                 const int tcount = g ? p.ttiles1 : p.ttiles0;
                 const int wi = p.order ? tl / tcount : tl % w_pairs;
                 const int tt = p.order ? tl % tcount : tl / w_pairs;
+                const int twt = (!p.conv && tt == tcount - 1) ? (g ? grp.tw_r[1] : grp.tw_r[0]) : tw;      // this tile's width (narrower last tile)
+                const CUtensorMap* mx = twt != tw ? (g ? &tmXr1 : &tmXr) : (g ? &tmX1 : &tmX);
+                const uint32_t tile_tx = 2u * (uint32_t)(w_bytes + twt * 128);
                 const int n0 = wi * 2 * wrows + (int)rank * wrows;      // this CTA's weight rows
-                int m0 = tt * tw + (int)rank * xrows, img = 0, h0 = 0, w0 = 0;       // this CTA's half of the token tile
+                int m0 = tt * tw + (int)rank * (twt >> 1), img = 0, h0 = 0, w0 = 0;       // this CTA's half of the token tile
                 if (p.conv) {
                     img = tt / p.tiles_per_img;
                     const int rem = tt - img * p.tiles_per_img;
@@ -445,19 +424,18 @@ gemm_h3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                     uint8_t* sW = smem + stage * stage_bytes;
                     uint8_t* sX = sW + w_bytes;
                     const uint32_t lead_full = mapa_to_cta(smem_u32(&full_bar[stage]), 0);
-                    const bool w_done = u == cluster_id && kb < prew;     // this stage's weights (and its expect_tx) were issued before the PDL wait
                     if (elect_one_sync()) {
                         if (p.dbg_mode == 2) {
                             if (leader) mbar_arrive(&full_bar[stage]);
                         } else {
-                            if (leader && !w_done) mbar_expect_tx(&full_bar[stage], stage_tx);
+                            if (leader) mbar_expect_tx(&full_bar[stage], tile_tx);
                             if (p.conv) {
                                 const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
                                 const int kh = tap / p.KW, kw = tap - kh * p.KW;
-                                if (!w_done) tma2_load_3d(mw, lead_full, sW, tap * p.Cin + cb * BKH, n0, 0);
+                                tma2_load_3d(mw, lead_full, sW, tap * p.Cin + cb * BKH, n0, 0);
                                 tma2_load_5d(mx, lead_full, sX, cb * BKH, w0 + kw - p.pad_w, h0 + kh - p.pad_h, img, 0);
                             } else {
-                                if (!w_done) tma2_load_3d(mw, lead_full, sW, kb * BKH, n0, 0);
+                                tma2_load_3d(mw, lead_full, sW, kb * BKH, n0, 0);
                                 tma2_load_3d(mx, lead_full, sX, kb * BKH, m0, 0);
                             }
                         }
@@ -473,10 +451,19 @@ gemm_h3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
         // instructions themselves are issued by one elected lane.  Issuing from inside an `if (lane == 0)` region instead makes ptxas wrap every
         // MMA into an elect / R2UR-broadcast / branch loop (~20 dependent instructions, ~100 clocks per MMA: more than a 256 x 128 x 16 MMA takes).
         if (leader) {
-            const uint32_t idesc = make_idesc_f16(2 * wrows, tw);
             int stage = 0; uint32_t phase = 0;
             int it = 0;
             for (int u = cluster_id; u < num_tiles; u += num_clusters, ++it) {
+                int twt = tw;                                            // narrower last token tile of a linear problem (H3Group::tw_r)
+                if (!p.conv) {
+                    const int g = u >= grp.tiles0;
+                    const int tl = g ? u - grp.tiles0 : u;
+                    const int tcount = g ? p.ttiles1 : p.ttiles0;
+                    const int tt = p.order ? tl % tcount : tl / w_pairs;
+                    if (tt == tcount - 1) twt = g ? grp.tw_r[1] : grp.tw_r[0];
+                }
+                const uint32_t idesc = make_idesc_f16(2 * wrows, twt);
+                const uint32_t xl_off = (uint32_t)(w_bytes + (twt >> 1) * 128);      // lo plane of the token tile follows its hi plane
                 const int buf = nbuf == 2 ? (it & 1) : 0;
                 const uint32_t use = nbuf == 2 ? ((uint32_t)it >> 1) : (uint32_t)it;
                 const bool ts_on = p.dbg_ts != nullptr && cluster_id == 0 && lane == 0;
@@ -491,7 +478,7 @@ gemm_h3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                     tc_fence_after();
                     const uint32_t sWh = smem_u32(smem + stage * stage_bytes);
                     const uint64_t dWh = make_smem_desc(sWh), dWl = make_smem_desc(sWh + (uint32_t)w_plane_bytes);
-                    const uint64_t dXh = make_smem_desc(sWh + (uint32_t)w_bytes), dXl = make_smem_desc(sWh + (uint32_t)(w_bytes + x_plane_bytes));
+                    const uint64_t dXh = make_smem_desc(sWh + (uint32_t)w_bytes), dXl = make_smem_desc(sWh + xl_off);
                     if (elect_one_sync()) {
 #pragma unroll
                         for (int k = 0; k < (p.dbg_mode == 1 ? 0 : 4); ++k) {
@@ -529,6 +516,7 @@ gemm_h3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
             const int wi = p.order ? tl / tcount : tl % w_pairs;
             const int tt = p.order ? tl % tcount : tl / w_pairs;
             const int n_cta = wi * 2 * wrows + (int)rank * wrows;
+            const int twt = (!p.conv && tt == tcount - 1) ? (g ? grp.tw_r[1] : grp.tw_r[0]) : tw;
             // (static member selection: a runtime index into the kernel-parameter struct would force a local copy of it)
             const H3Problem prob{g ? grp.prob[1].C : grp.prob[0].C, g ? grp.prob[1].Ch : grp.prob[0].Ch, g ? grp.prob[1].bias : grp.prob[0].bias,
                                  g ? grp.prob[1].residual : grp.prob[0].residual, g ? grp.prob[1].M : grp.prob[0].M,
@@ -539,7 +527,8 @@ gemm_h3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
             const bool ts_on = p.dbg_ts != nullptr && cluster_id == 0 && leader && lane == 0 && (warp == 2 || warp == 17);
             unsigned long long* ts = ts_on ? p.dbg_ts + it * 8 + (warp == 2 ? 3 : 6) : nullptr;
             if (ts_on && warp == 2) ts[0] = clock64();
-            run_epilogue(acc_hh, acc_hh + x_off, lane, q, c_lo, c_hi, n_cta, tt, p, prob, &tfull_bar[buf], use & 1u, ln_smem + (it & 1) * 256,
+            run_epilogue(acc_hh, acc_hh + x_off, lane, q, c_lo, min(c_hi, p.mhalf ? twt >> 1 : twt), twt, n_cta, tt, p, prob, &tfull_bar[buf], use & 1u,
+                         ln_smem + (it & 1) * 256,
                          (int)threadIdx.x - 64, (ts_on && warp == 2) ? ts + 1 : nullptr);
             if (ts_on) ts[warp == 2 ? 2 : 0] = clock64();
             tc_fence_before();
@@ -600,8 +589,7 @@ int g_dbg_mode = 0;
 unsigned long long* g_dbg_ts = nullptr;
 int g_order = 0;      // tuning aid: tile order (see H3Params::order)
 int g_force_tw = 0;   // tuning aid (tools/gemm_sweep.py): > 0 = use this token tile width wherever it is legal
-int g_prew = -1;       // SIU3R_H3_PREW=1 turns the early weight loads on.  OFF by default: measured 17.03 ms/pair without, 17.23 with (the early
-                       // stages of pairs that start ahead compete with the running kernel's operand stream for L2 -> SM bandwidth)
+int g_no_rem = -1;     // tuning aid (SIU3R_H3_REM=0 in the environment, or the setter below): 1 = the last token tile of a problem is as wide as the others (siu3r_gemm_h3_set_remainder_tiles(0))
 int g_cluster_cap = 0; // > 0: a launch uses at most this many CTA pairs (siu3r_gemm_h3_cluster_cap)
 int g_mhalf = -1;     // M = 128 mode for N <= 128 (see H3Params::mhalf); SIU3R_H3_MHALF=0 turns it off (A/B measurements)
 bool use_mhalf(int N) {
@@ -645,7 +633,8 @@ int epilogue_weight(int act, bool split, bool rope, bool residual, bool stats_ou
            (ln ? 5 : 0);
 }
 
-int launch_h3(const CUtensorMap& w, const CUtensorMap& x, const CUtensorMap& w1, const CUtensorMap& x1, H3Params& p, const H3Group& grp,
+int launch_h3(const CUtensorMap& w, const CUtensorMap& x, const CUtensorMap& w1, const CUtensorMap& x1, const CUtensorMap& xr, const CUtensorMap& xr1,
+              H3Params& p, const H3Group& grp,
               int w_pairs, int num_tiles, cudaStream_t stream) {
     static int max_clusters[64] = {0};
     int dev = 0;
@@ -664,14 +653,12 @@ int launch_h3(const CUtensorMap& w, const CUtensorMap& x, const CUtensorMap& w1,
         if (getenv("SIU3R_GEMM_VERBOSE")) fprintf(stderr, "[siu3r_b200] gemm_h3: %d resident clusters, %d B smem\n", n, SMEM_BYTES);
     }
     p.mhalf = use_mhalf(p.N) ? 1 : 0;
-    if (g_prew < 0) { const char* e = getenv("SIU3R_H3_PREW"); g_prew = (e && e[0] == '1') ? 1 : 0; }
-    p.prew = (g_prew && p.dbg_mode == 0) ? 1 : 0;
     const int stage_bytes = (p.mhalf ? W_BYTES / 2 : W_BYTES) + p.tw * 128;
     p.nbuf = (p.tw <= 128 || p.mhalf) ? 2 : 1;
     p.nstages = PIPE_BYTES / stage_bytes > MAX_STAGES ? MAX_STAGES : PIPE_BYTES / stage_bytes;
     int clusters = num_tiles < max_clusters[dev] ? num_tiles : max_clusters[dev];
     if (g_cluster_cap > 0 && clusters > g_cluster_cap) clusters = g_cluster_cap;
-    SIU3R_CUDA_CHECK(siu3r_launch_pdl(gemm_h3_kernel, dim3((unsigned)(2 * clusters)), dim3(THREADS), SMEM_BYTES, stream, w, x, w1, x1, p, grp, w_pairs, num_tiles));
+    SIU3R_CUDA_CHECK(siu3r_launch_pdl(gemm_h3_kernel, dim3((unsigned)(2 * clusters)), dim3(THREADS), SMEM_BYTES, stream, w, x, w1, x1, xr, xr1, p, grp, w_pairs, num_tiles));
     SIU3R_LAUNCH_CHECK();
     siu3r_note_launch(1);
     return SIU3R_OK;
@@ -695,6 +682,8 @@ void siu3r_gemm_h3_force(int tw) { g_force_tw = tw; }
 // Scheduling aid for concurrent branches: launches issued while cap > 0 occupy at most `cap` of the 74 CTA pairs, so that a latency-bound chain of
 // small kernels on a high-priority stream (the Mask2Former decoder next to the DPT heads) always finds free SMs; 0 = no cap (default).
 void siu3r_gemm_h3_cluster_cap(int cap) { g_cluster_cap = cap > 0 ? cap : 0; }
+// tuning aid: 1 = narrower last token tile per problem (default), 0 = uniform tiles
+void siu3r_gemm_h3_set_remainder_tiles(int on) { g_no_rem = on ? 0 : 1; }
 // tuning aid: 1 = M = 128 MMAs for N <= 128 (default), 0 = always M = 256
 void siu3r_gemm_h3_set_mhalf(int on) { g_mhalf = on ? 1 : 0; }
 void siu3r_gemm_h3_order(int order) { g_order = order ? 1 : 0; }
@@ -798,7 +787,20 @@ int siu3r_gemm_h3_ln(int ngroups, const int* M_host, int N, int K, const void* c
     grp.tiles0 = w_pairs * ceil_div(M0, tw);
     p.ttiles0 = ceil_div(M0, tw); p.ttiles1 = ngroups == 2 ? ceil_div(M1, tw) : 1; p.order = g_order; p.dbg_mode = g_dbg_mode; p.dbg_ts = g_dbg_ts;
     const int tiles = grp.tiles0 + (ngroups == 2 ? w_pairs * ceil_div(M1, tw) : 0);
-    return launch_h3(mw[0], mx[0], mw[1], mx[1], p, grp, w_pairs, tiles, stream);
+    // narrower last token tile per problem (H3Group::tw_r): the remaining rows rounded up to the MMA-N granularity
+    CUtensorMap mxr[2];
+    const int gran = use_mhalf(N) ? 32 : 16;
+    for (int g = 0; g < 2; ++g) {
+        const int sg = g < ngroups ? g : 0;
+        const int Mg = M_host[sg];
+        const int rem = Mg - (ceil_div(Mg, tw) - 1) * tw;
+        int twr = ceil_div(rem, gran) * gran;
+        if (g_no_rem < 0) { const char* e = getenv("SIU3R_H3_REM"); g_no_rem = (e && e[0] == '0') ? 1 : 0; }
+        if (twr > tw || g_no_rem) twr = tw;
+        grp.tw_r[g] = twr;
+        int r = map_rows(&mxr[g], X_host[sg], K, Mg, lda, a_plane, twr / 2); if (r) return r;
+    }
+    return launch_h3(mw[0], mx[0], mw[1], mx[1], mxr[0], mxr[1], p, grp, w_pairs, tiles, stream);
 }
 
 int siu3r_gemm_h3(int ngroups, const int* M_host, int N, int K, const void* const* X_host, int64_t lda, int64_t a_plane, const void* const* W_host,
@@ -846,7 +848,8 @@ int siu3r_conv2d_h3(int Nimg, int H, int W, int Cin, int Cout, int KH, int KW, i
     grp.prob[1] = grp.prob[0];
     grp.tiles0 = w_pairs * Nimg * p.tiles_per_img;
     p.ttiles0 = Nimg * p.tiles_per_img; p.ttiles1 = 1; p.order = g_order;
-    return launch_h3(mw, mx, mw, mx, p, grp, w_pairs, grp.tiles0, stream);
+    grp.tw_r[0] = grp.tw_r[1] = tw;
+    return launch_h3(mw, mx, mw, mx, mx, mx, p, grp, w_pairs, grp.tiles0, stream);
 }
 
 }  // extern "C"

@@ -104,6 +104,37 @@ def test_gemm_h3_half_m_mode_is_bit_identical(M, N, K):
             assert torch.equal(outs[(0, tw)][i], outs[(1, tw)][i]), (tw, i)
 
 
+@pytest.mark.parametrize("M,N,K", [(2050, 1024, 512), (1025, 768, 256), (1025, 96, 256), (130, 512, 64), (17, 256, 128), (257, 83, 192)])
+def test_gemm_h3_narrow_last_tile_is_bit_identical(M, N, K):
+    """The last token tile of a problem runs narrower MMAs (its remaining rows rounded up to 16 / 32 columns) instead of a full-width tile that is
+    mostly padding; same k order, so every output bit must equal the uniform-tile kernel's -- fp32 / plane-pair / GELU / residual / grouped."""
+    from siu3r_b200 import ops
+    lib = ops._lib.load()
+    x, w, b = rnd(M, K, seed=51), rnd(N, K, seed=52, scale=K ** -0.5), rnd(N, seed=53)
+    res = rnd(M, N, seed=54)
+    wt = ops.Weight(w, b, H3)
+    xs = ops.split(x)
+    h = M // 2
+    outs = {}
+    try:
+        for mode in (0, 1):
+            lib.siu3r_gemm_h3_set_remainder_tiles(mode)
+            for tw in (0, 32, 64, 96, 128, 160, 256):
+                lib.siu3r_gemm_h3_force(tw)
+                a = ops.gemm(xs, wt, act=1, residual=res, precision=H3)
+                s = ops.gemm(xs, wt, act=2, precision=H3, round_out=True).t.clone()
+                g2 = ops.gemm_group2([xs[:h], xs[h:]], [wt, wt], precision=H3)
+                outs[(mode, tw)] = (a, s, g2[0], g2[1])
+    finally:
+        lib.siu3r_gemm_h3_set_remainder_tiles(1)
+        lib.siu3r_gemm_h3_force(0)
+    ref = F.gelu(F.linear(x.double(), w.double(), b.double())) + res.double()
+    assert rel_err(outs[(1, 0)][0], ref) < 1e-5
+    for tw in (0, 32, 64, 96, 128, 160, 256):
+        for i in range(4):
+            assert torch.equal(outs[(0, tw)][i], outs[(1, tw)][i]), (tw, i)
+
+
 @pytest.mark.parametrize("M,C,N", [(2050, 1024, 3072), (1025, 768, 768), (77, 256, 96)])
 def test_gemm_h3_fused_layernorm(M, C, N):
     """LayerNorm fused across two GEMMs (siu3r_gemm_h3_ln): the producer (residual-adding projection) emits fp32 rows + plane pair + fixed-point row

@@ -950,7 +950,9 @@ int launch_tile_sorts(int ntiles, const uint2* ranges, const uint64_t* list, uin
     tile_sort_reg_kernel<2><<<ntiles, TS_THREADS, TS_THREADS * 2 * 8, stream>>>(ranges, list, sorted_ids, 0, 512, status);
     siu3r_note_launch(1);
     if (max_tile > 512) { tile_sort_reg_kernel<8><<<ntiles, TS_THREADS, TS_THREADS * 8 * 8, stream>>>(ranges, list, sorted_ids, 512, 2048, status); siu3r_note_launch(1); }
-    if (max_tile > 2048) { tile_sort_reg_kernel<32><<<ntiles, TS_THREADS, TS_THREADS * 32 * 8, stream>>>(ranges, list, sorted_ids, 2048, TS_CAP, status); siu3r_note_launch(1); }
+    // 16 keys per thread for (2048, 4096]: a 1 M-Gaussian 512^2 frame averages 2170 records per tile, which the 32-key class sorted as 8192
+    if (max_tile > 2048) { tile_sort_reg_kernel<16><<<ntiles, TS_THREADS, TS_THREADS * 16 * 8, stream>>>(ranges, list, sorted_ids, 2048, 4096, status); siu3r_note_launch(1); }
+    if (max_tile > 4096) { tile_sort_reg_kernel<32><<<ntiles, TS_THREADS, TS_THREADS * 32 * 8, stream>>>(ranges, list, sorted_ids, 4096, TS_CAP, status); siu3r_note_launch(1); }
     SIU3R_LAUNCH_CHECK();
     return SIU3R_OK;
 }

@@ -89,13 +89,14 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(
     __syncthreads();
     const int i = base + tid;
     if (i >= G) return;
+    radii[i] = 0;          // culled Gaussians keep these zeros (the kernel zeroes its own outputs: no memset launches in front of it)
+    o.tiles[i] = 0;
 
     const float px = means[3 * (size_t)i], py = means[3 * (size_t)i + 1], pz = means[3 * (size_t)i + 2];
     const float* vm = s_cam.view;
     const float* pm = s_cam.proj;
     float tx = row_dot(vm, 0, px, py, pz), ty = row_dot(vm, 1, px, py, pz);
     const float tz = row_dot(vm, 2, px, py, pz);
-    // radii / tiles were zeroed by the host wrapper: culled Gaussians simply return
     if (tz <= 0.2f) return;
     const float hx = row_dot(pm, 0, px, py, pz), hy = row_dot(pm, 1, px, py, pz);
     const float hw = row_dot(pm, 3, px, py, pz);
@@ -681,12 +682,15 @@ __global__ void __launch_bounds__(128) preprocess_feat_kernel(int G, int H, int 
     __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= G) return;
+    radii[i] = 0;               // culled Gaussians keep these zeros
+    tiles[i] = 0;
+    if (radii_xy) { radii_xy[2 * i] = 0; radii_xy[2 * i + 1] = 0; }
     const float* V = s_cam.V;   // world-to-camera, row-major
     const float px = means[3 * (size_t)i], py = means[3 * (size_t)i + 1], pz = means[3 * (size_t)i + 2];
     const float x = ADD(ADD(ADD(MUL(V[0], px), MUL(V[1], py)), MUL(V[2], pz)), V[3]);
     const float y = ADD(ADD(ADD(MUL(V[4], px), MUL(V[5], py)), MUL(V[6], pz)), V[7]);
     const float z = ADD(ADD(ADD(MUL(V[8], px), MUL(V[9], py)), MUL(V[10], pz)), V[11]);
-    if (z < s_cam.near_plane || z > s_cam.far_plane) return;      // radii / tiles were zeroed by the host wrapper
+    if (z < s_cam.near_plane || z > s_cam.far_plane) return;
     float S[3][3];
     {
         const float* c = cov + (size_t)i * cov_stride;
@@ -1024,8 +1028,6 @@ int siu3r_raster_forward(int G, int H, int W, int sh_degree, int sh_coeffs, int 
     const bool want_debug = debug_tiles_touched || debug_offsets || debug_keys || debug_values || debug_ranges;
     bool binned = g_binned && !want_debug;
 
-    SIU3R_CUDA_CHECK(cudaMemsetAsync(radii, 0, sizeof(int32_t) * G, stream));
-    SIU3R_CUDA_CHECK(cudaMemsetAsync(w.tiles, 0, sizeof(uint32_t) * G, stream));
     SIU3R_CUDA_CHECK(cudaMemsetAsync(w.ranges, 0, sizeof(uint2) * gx * gy, stream));
     if (binned) SIU3R_CUDA_CHECK(cudaMemsetAsync(w.tile_counts, 0, sizeof(uint32_t) * gx * gy, stream));
     if (n_touched) SIU3R_CUDA_CHECK(cudaMemsetAsync(n_touched, 0, sizeof(int32_t) * G, stream));
@@ -1152,8 +1154,6 @@ int siu3r_raster_forward_nosync(int G, int H, int W, int sh_degree, int sh_coeff
         SIU3R_CUDA_CHECK(cudaFuncSetAttribute(bin_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_bin[dev & 63] = true;
     }
-    SIU3R_CUDA_CHECK(cudaMemsetAsync(radii, 0, sizeof(int32_t) * G, stream));
-    SIU3R_CUDA_CHECK(cudaMemsetAsync(w.tiles, 0, sizeof(uint32_t) * G, stream));
     SIU3R_CUDA_CHECK(cudaMemsetAsync(w.tile_counts, 0, sizeof(uint32_t) * ntiles, stream));
     if (n_touched) SIU3R_CUDA_CHECK(cudaMemsetAsync(n_touched, 0, sizeof(int32_t) * G, stream));
     pack_camera_kernel<<<1, 64, 0, stream>>>(viewmatrix, projmatrix, campos, bg, w.cam);
@@ -1196,10 +1196,7 @@ int siu3r_raster_features_forward(int G, int H, int W, int C, int cov_stride, co
     Workspace w = carve(workspace, G, H, W, dup_capacity);
     if ((int64_t)w.bytes > workspace_bytes) return SIU3R_ERR_CAPACITY;
     int32_t* radii = reinterpret_cast<int32_t*>(w.rgb);   // the colour slot of the shared workspace is free on this path
-    SIU3R_CUDA_CHECK(cudaMemsetAsync(radii, 0, sizeof(int32_t) * G, stream));
-    SIU3R_CUDA_CHECK(cudaMemsetAsync(w.tiles, 0, sizeof(uint32_t) * G, stream));
     SIU3R_CUDA_CHECK(cudaMemsetAsync(w.ranges, 0, sizeof(uint2) * gx * gy, stream));
-    if (radii_xy) SIU3R_CUDA_CHECK(cudaMemsetAsync(radii_xy, 0, sizeof(int32_t) * 2 * G, stream));
     // camera block: V (device) + 6 host scalars -> one small device buffer
     SIU3R_CUDA_CHECK(cudaMemcpyAsync(w.cam, viewmat, 16 * sizeof(float), cudaMemcpyDeviceToDevice, stream));
     const float scal[6] = {intr_host[0], intr_host[1], intr_host[2], intr_host[3], near_plane, far_plane};
@@ -1260,10 +1257,7 @@ int siu3r_raster_features_forward_nosync(int G, int H, int W, int C, int cov_str
         attr_bin[dev & 63] = true;
     }
     int32_t* radii = reinterpret_cast<int32_t*>(w.rgb);
-    SIU3R_CUDA_CHECK(cudaMemsetAsync(radii, 0, sizeof(int32_t) * G, stream));
-    SIU3R_CUDA_CHECK(cudaMemsetAsync(w.tiles, 0, sizeof(uint32_t) * G, stream));
     SIU3R_CUDA_CHECK(cudaMemsetAsync(w.tile_counts, 0, sizeof(uint32_t) * ntiles, stream));
-    if (radii_xy) SIU3R_CUDA_CHECK(cudaMemsetAsync(radii_xy, 0, sizeof(int32_t) * 2 * G, stream));
     pack_feat_camera_kernel<<<1, 32, 0, stream>>>(viewmat, fx, fy, cx, cy, near_plane, far_plane, w.cam);
     preprocess_feat_kernel<<<ceil_div(G, 128), 128, 0, stream>>>(G, H, W, gx, gy, cov_stride, means3D, cov, opacities, w.cam, w.depths, w.xy,
                                                                 w.conic_o, w.tiles, w.rects, radii, radii_xy);

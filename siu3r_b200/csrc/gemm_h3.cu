@@ -19,8 +19,13 @@
 //     halo zero-filled by TMA = the conv padding; channel counts that are no multiple of 64 ride on the same zero fill;
 //   * epilogue: TMEM lane = weight row n, column = token m, so every global access of a warp is 32 consecutive n of one token row:
 //     acc = hh + x * 2^-11, * alpha, + bias, GELU(erf) / ReLU, RoPE-2D (pairs = lanes l, l^16), + fp32 residual, then either an fp32
-//     store or the (hi, lo) fp16 split of the result when its only consumers are further h3 tensor-core operands; the V columns of a
-//     fused qkv / k|v projection go out transposed (V^T plane pair) for the attention kernel's P.V operand.
+//     store or the (hi, lo) fp16 split of the result when its only consumers are further h3 tensor-core operands (or both: the fp32
+//     residual stream plus its plane pair); the V columns of a fused qkv / k|v projection go out transposed (V^T plane pair) for the
+//     attention kernel's P.V operand;
+//   * LayerNorm fused on both sides (siu3r_gemm_h3_ln): a residual-adding projection accumulates fixed-point row statistics of the rows it
+//     writes, the next projection multiplies the RAW rows by gamma-folded weights and normalises in its epilogue;
+//   * layers with <= 128 output channels run M = 128 MMAs (64 weight rows per CTA); the last token tile of a linear problem is as wide as
+//     its remaining rows; the tile width comes from a measured cost model (pick_tw); launched with programmatic dependent launch.
 #include <cuda.h>
 #include <cuda_fp16.h>
 

@@ -676,3 +676,20 @@ def test_ply_oracle_records_match_reference_export_ply():
                 assert np.abs(got[name].view(np.int32).astype(np.int64) - want[name].view(np.int32).astype(np.int64)).max() <= 1, (tag, name)
             else:
                 assert np.array_equal(got[name], want[name]), (tag, name)
+
+
+def test_bench_arms_share_workload_string_and_numa_bind_is_harmless_without_a_gpu():
+    """Both bench arms name the workload with the same function (the driver compares `config.workload`), and the NUMA helper only ever narrows the
+    affinity when the GPU's sysfs node says so -- without a CUDA device it reports an error and leaves the process alone."""
+    import os
+    sys.path.insert(0, ROOT)
+    import bench
+    from siu3r_b200.parallel import bind_to_gpu_numa
+    assert bench.workload_name(512, 1, 2) == bench.workload_name(512, 1, 2) and "512x512" in bench.workload_name(512, 1, 2)
+    assert "SIU3RMultiViewModel" in bench.workload_name(512, 1, 4)
+    before = os.sched_getaffinity(0)
+    info = bind_to_gpu_numa(0)
+    assert isinstance(info, dict) and info["bound"] in (False, True)
+    if not torch.cuda.is_available():
+        assert info["bound"] is False and os.sched_getaffinity(0) == before
+    os.sched_setaffinity(0, before)

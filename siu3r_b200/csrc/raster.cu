@@ -462,14 +462,8 @@ __device__ __forceinline__ uint64_t shfl_xor_u64(uint64_t v, int m) {
 }
 
 template <int ITEMS>
-__global__ void __launch_bounds__(TS_THREADS) tile_sort_reg_kernel(const uint2* __restrict__ ranges, const uint64_t* __restrict__ list,
-                                                                   uint32_t* __restrict__ sorted_ids, int n_lo, int n_hi,
-                                                                   const uint32_t* __restrict__ status) {
-    extern __shared__ uint64_t s_w[];
-    if (status && status[2]) return;
-    const uint2 rg = ranges[blockIdx.x];
-    const int n = (int)(rg.y - rg.x);
-    if (n <= n_lo || n > n_hi) return;
+__device__ __forceinline__ void tile_sort_reg_body(const uint2 rg, const int n, const uint64_t* __restrict__ list, uint32_t* __restrict__ sorted_ids,
+                                                   uint64_t* s_w) {
     constexpr int P = TS_THREADS * ITEMS;
     const int tid = threadIdx.x;
     const int e0 = tid * ITEMS;
@@ -518,6 +512,22 @@ __global__ void __launch_bounds__(TS_THREADS) tile_sort_reg_kernel(const uint2* 
 #pragma unroll
     for (int r = 0; r < ITEMS; ++r)
         if (e0 + r < n) sorted_ids[rg.x + e0 + r] = (uint32_t)v[r];
+}
+
+// Two size classes per launch (A keys per thread for n_lo < n <= n_mid, B for n_mid < n <= n_hi): the no-sync path cannot know the largest tile on
+// the host, so it launches every class over all tiles: the two small classes share a launch (the two large ones would
+// need 190 registers together and stay separate).
+template <int A, int B>
+__global__ void __launch_bounds__(TS_THREADS) tile_sort_reg_kernel(const uint2* __restrict__ ranges, const uint64_t* __restrict__ list,
+                                                                   uint32_t* __restrict__ sorted_ids, int n_lo, int n_mid, int n_hi,
+                                                                   const uint32_t* __restrict__ status) {
+    extern __shared__ uint64_t s_w[];
+    if (status && status[2]) return;
+    const uint2 rg = ranges[blockIdx.x];
+    const int n = (int)(rg.y - rg.x);
+    if (n <= n_lo || n > n_hi) return;
+    if (n <= n_mid) tile_sort_reg_body<A>(rg, n, list, sorted_ids, s_w);
+    else tile_sort_reg_body<B>(rg, n, list, sorted_ids, s_w);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -948,15 +958,15 @@ int launch_tile_sorts(int ntiles, const uint2* ranges, const uint64_t* list, uin
     int dev = 0;
     SIU3R_CUDA_CHECK(cudaGetDevice(&dev));
     if (!attr[dev & 63]) {
-        SIU3R_CUDA_CHECK(cudaFuncSetAttribute(tile_sort_reg_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_THREADS * 32 * 8));
+        SIU3R_CUDA_CHECK(cudaFuncSetAttribute(tile_sort_reg_kernel<32, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_THREADS * 32 * 8));
         attr[dev & 63] = true;
     }
-    tile_sort_reg_kernel<2><<<ntiles, TS_THREADS, TS_THREADS * 2 * 8, stream>>>(ranges, list, sorted_ids, 0, 512, status);
+    // size classes: 2 / 8 / 16 / 32 keys per thread = up to 512 / 2048 / 4096 / 8192 records (a 1 M-Gaussian 512^2 frame averages 2170 records per tile,
+    // which a 32-key-only upper class sorted as 8192)
+    tile_sort_reg_kernel<2, 8><<<ntiles, TS_THREADS, TS_THREADS * 8 * 8, stream>>>(ranges, list, sorted_ids, 0, 512, 2048, status);
     siu3r_note_launch(1);
-    if (max_tile > 512) { tile_sort_reg_kernel<8><<<ntiles, TS_THREADS, TS_THREADS * 8 * 8, stream>>>(ranges, list, sorted_ids, 512, 2048, status); siu3r_note_launch(1); }
-    // 16 keys per thread for (2048, 4096]: a 1 M-Gaussian 512^2 frame averages 2170 records per tile, which the 32-key class sorted as 8192
-    if (max_tile > 2048) { tile_sort_reg_kernel<16><<<ntiles, TS_THREADS, TS_THREADS * 16 * 8, stream>>>(ranges, list, sorted_ids, 2048, 4096, status); siu3r_note_launch(1); }
-    if (max_tile > 4096) { tile_sort_reg_kernel<32><<<ntiles, TS_THREADS, TS_THREADS * 32 * 8, stream>>>(ranges, list, sorted_ids, 4096, TS_CAP, status); siu3r_note_launch(1); }
+    if (max_tile > 2048) { tile_sort_reg_kernel<16, 16><<<ntiles, TS_THREADS, TS_THREADS * 16 * 8, stream>>>(ranges, list, sorted_ids, 2048, 4096, 4096, status); siu3r_note_launch(1); }
+    if (max_tile > 4096) { tile_sort_reg_kernel<32, 32><<<ntiles, TS_THREADS, TS_THREADS * 32 * 8, stream>>>(ranges, list, sorted_ids, 4096, TS_CAP, TS_CAP, status); siu3r_note_launch(1); }
     SIU3R_LAUNCH_CHECK();
     return SIU3R_OK;
 }
